@@ -1,0 +1,122 @@
+/* oracle/ref_harness.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Function-level entry points into the UNMODIFIED reference decoder (compiled from /root/reference in
+ * place by oracle/Makefile into oracle/_ref/libmpeghref.so).  Every export here takes raw float / int
+ * arrays ("inputs + state in -> outputs + state out"), fills the reference's own structs and calls the
+ * reference's own functions, so that tests can pin both the plain-C restatement (oracle_*.c) and the CUDA
+ * path against the real thing.  Nothing in the product library may link or load this.
+ *
+ * This file contains no reference code, only calls into it.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+
+#include <impeghd_type_def.h>
+#include <impeghd_fft_ifft.h>
+#include "impeghd_intrinsics_flt.h"
+#include "ia_core_coder_cnst.h"
+#include <ia_core_coder_constants.h>
+#include "ia_core_coder_acelp_info.h"
+#include "ia_core_coder_acelp_com.h"
+#include <ia_core_coder_basic_ops32.h>
+#include <ia_core_coder_basic_ops40.h>
+#include "ia_core_coder_bitbuffer.h"
+#include "ia_core_coder_defines.h"
+#include "ia_core_coder_function_selector.h"
+#include "ia_core_coder_interface.h"
+#include "ia_core_coder_info.h"
+#include "ia_core_coder_tns_usac.h"
+#include "impeghd_tbe_dec.h"
+#include "ia_core_coder_igf_data_struct.h"
+#include "ia_core_coder_stereo_lpd.h"
+#include "ia_core_coder_main.h"
+#include "ia_core_coder_func_def.h"
+#include "ia_core_coder_rom.h"
+#include "ia_core_coder_arith_dec.h"
+#include "ia_core_coder_windows.h"
+#include "ia_core_coder_vec_baisc_ops.h"
+#include "impeghd_error_codes.h"
+
+/* ------------------------------------------------------------------------------------------------
+ * FD synthesis: ia_core_coder_fd_frm_dec (ia_core_coder_imdct.c:832)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct
+{
+  ia_usac_data_struct usac;
+  FLOAT32 scratch_float[4 * 4096];
+  FLOAT32 fft_scratch[8 * 4096];
+} ref_fd_handle;
+
+void *ref_fd_create(void)
+{
+  ref_fd_handle *h = (ref_fd_handle *)calloc(1, sizeof(ref_fd_handle));
+  int ch;
+  if (!h)
+    return 0;
+  h->usac.ccfl = 1024;
+  h->usac.scratch_buffer_float = h->scratch_float;
+  h->usac.ptr_fft_scratch = h->fft_scratch;
+  for (ch = 0; ch < MAX_NUM_CHANNELS; ch++)
+  {
+    h->usac.coef[ch] = h->usac.arr_coef[ch];
+    h->usac.str_tddec[ch] = &h->usac.arr_str_tddec[ch];
+  }
+  return h;
+}
+
+void ref_fd_destroy(void *p) { free(p); }
+
+/* One channel-frame.  coef[1024] (copied: the reference transforms in place), overlap[1024] in/out,
+ * out[1024].  FD-only channel history (td_frame_prev = 0, no FAC). Returns the reference error code. */
+int ref_fd_frm_dec(void *p, const float *coef, float *overlap, float *out, int window_sequence,
+                   int window_shape, int window_shape_prev, int prev_aliasing_symmetry,
+                   int curr_aliasing_symmetry)
+{
+  ref_fd_handle *h = (ref_fd_handle *)p;
+  ia_usac_data_struct *u = &h->usac;
+  const int ch = 0;
+  int err;
+  memcpy(u->coef[ch], coef, 1024 * sizeof(float));
+  memcpy(u->overlap_data_ptr[ch], overlap, 1024 * sizeof(float));
+  u->window_sequence[ch] = window_sequence;
+  u->window_shape[ch] = window_shape;
+  u->window_shape_prev[ch] = window_shape_prev;
+  u->prev_aliasing_symmetry[ch] = (WORD16)prev_aliasing_symmetry;
+  u->curr_aliasing_symmetry[ch] = (WORD16)curr_aliasing_symmetry;
+  u->td_frame_prev[ch] = 0;
+  u->fac_data_present[ch] = 0;
+  err = ia_core_coder_fd_frm_dec(u, ch, 0);
+  memcpy(out, u->time_sample_vector[ch], 1024 * sizeof(float));
+  memcpy(overlap, u->overlap_data_ptr[ch], 1024 * sizeof(float));
+  return err;
+}
+
+/* n_frames consecutive frames of n_ch channels, state carried; layout [frame][ch][1024].
+ * side[frame][ch][5] = {window_sequence, window_shape, window_shape_prev, prev_sym, curr_sym}. */
+int ref_fd_frm_dec_batch(void *p, const float *coef, float *overlap /*[n_ch][1024]*/, float *out,
+                         const int *side, int n_frames, int n_ch)
+{
+  int f, c, err = 0;
+  for (f = 0; f < n_frames; f++)
+    for (c = 0; c < n_ch; c++)
+    {
+      const int *s = side + ((size_t)f * n_ch + c) * 5;
+      size_t o = ((size_t)f * n_ch + c) * 1024;
+      err |= ref_fd_frm_dec(p, coef + o, overlap + (size_t)c * 1024, out + o, s[0], s[1], s[2], s[3],
+                            s[4]);
+    }
+  return err;
+}
+
+/* Plain complex transforms (impeghd_ifft.c:297, impeghd_fft.c:297). */
+void ref_rad2_cplx_ifft(float *re, float *im, int n)
+{
+  static __thread FLOAT32 scratch[8 * 4096];
+  impeghd_rad2_cplx_ifft(re, im, n, scratch);
+}
+void ref_rad2_cplx_fft(float *re, float *im, int n)
+{
+  static __thread FLOAT32 scratch[8 * 4096];
+  impeghd_rad2_cplx_fft(re, im, n, scratch);
+}
