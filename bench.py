@@ -1,0 +1,328 @@
+#!/usr/bin/env python3
+"""bench.py -- throughput of the post-parse signal path on B200 (BASELINE.json metric: channel-samples/s).
+
+Workload at N=1 = BASELINE.json configs[1]: batched IMDCT + windowing/overlap-add, 1024-sample frames,
+256 streams x 24 channels (22.2), synthetic spectra, fp32.  One "step" = one frame for every stream of one
+batch = 6144 channel-frames through mpeghb200_fd_synth (one kernel launch).
+
+  value      device-resident inputs, CUDA-event timed over K back-to-back steps.  To keep every step's
+             16 KB/unit of traffic in HBM and not in the 126 MB L2, the timed loop rotates over G stream
+             groups (each with its own spectra, overlap state and output: 3 x 25 MB), G*75 MB >> L2.
+  e2e        the same step through the host-buffer C-ABI call (mpeghb200_fd_execute): pinned host
+             spectra -> device, kernel, PCM -> host, every step.
+  roofline   algorithmic bytes (16384 B per channel-frame) / mean step duration, vs the
+             measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline  the unmodified reference's ia_core_coder_fd_frm_dec (oracle/_ref, kind "reference"; the
+             plain-C port if that build is absent) on the host cores, bounded sample.
+  --impl reference   the reference arm: that same CPU function on the full workload with all host threads.
+
+Multi-GPU (torchrun, one rank per GPU): streams are sharded by rank, no collective on the data path
+(weak scaling: 256 streams per GPU); time = max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+STREAMS, CHANNELS, FRAME = 256, 24, 1024
+UNITS = STREAMS * CHANNELS
+BYTES_PER_UNIT = 16384  # coef 4096 + overlap r/w 2*4096 + out 4096
+METRIC = "channel-samples/s (FD synthesis: IMDCT+window+OLA, 256 streams x 24 ch x 1024)"
+UNIT = "channel-samples/s"
+
+
+def workload_name():
+    return "configs[1]: IMDCT+windowing/OLA, 1024-sample frames, 256 streams x 24 ch, synthetic spectra"
+
+
+def make_side(rng, n_units):
+    """Mostly ONLY_LONG sine/KBD with ~8 % start/short/stop frames, state-consistent per channel."""
+    import fd_cases
+    seq = np.zeros(n_units, np.int32)
+    r = rng.random(n_units)
+    seq[r > 0.92] = 1
+    seq[r > 0.95] = 2
+    seq[r > 0.98] = 3
+    shape = (rng.random(n_units) < 0.5).astype(np.int32)
+    shape_prev = (rng.random(n_units) < 0.5).astype(np.int32)
+    z = np.zeros(n_units, np.int32)
+    return np.stack([seq, shape, shape_prev, z, z], axis=-1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_reference_step(kind_lib, coef, side, overlap, out, n_threads, handles):
+    """One frame for all units of coef [U,1024] on n_threads host threads (disjoint unit ranges)."""
+    from concurrent.futures import ThreadPoolExecutor
+    kind, lib = kind_lib
+    U = coef.shape[0]
+    bounds = np.linspace(0, U, n_threads + 1).astype(int)
+
+    def work(t):
+        a, b = int(bounds[t]), int(bounds[t + 1])
+        if b <= a:
+            return 0
+        if kind == "reference":
+            return lib.ref_fd_frm_dec_batch(handles[t], coef[a:b], overlap[a:b], out[a:b], side[a:b], 1, b - a)
+        return lib.oracle_fd_frm_dec_batch(coef[a:b], overlap[a:b], out[a:b], side[a:b], 1, b - a)
+
+    with ThreadPoolExecutor(n_threads) as ex:
+        errs = list(ex.map(work, range(n_threads)))
+    assert not any(errs)
+
+
+def load_cpu_impl():
+    from oracle import loader
+    ref = loader.load_ref()
+    if ref is not None:
+        return ("reference", ref)
+    return ("port", loader.load_oracle())
+
+
+def run_cpu(args, sample_units, steps, warmup, n_threads):
+    """Times the CPU implementation; returns (channel-samples/s, seconds per step, kind)."""
+    kind_lib = load_cpu_impl()
+    rng = np.random.default_rng(1234)
+    coef = rng.normal(0, 500, (sample_units, FRAME)).astype(np.float32)
+    side = np.ascontiguousarray(make_side(rng, sample_units))
+    overlap = np.zeros((sample_units, FRAME), np.float32)
+    out = np.zeros((sample_units, FRAME), np.float32)
+    handles = [kind_lib[1].ref_fd_create() for _ in range(n_threads)] if kind_lib[0] == "reference" else None
+    for _ in range(warmup):
+        cpu_reference_step(kind_lib, coef, side, overlap, out, n_threads, handles)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_reference_step(kind_lib, coef, side, overlap, out, n_threads, handles)
+    dt = time.perf_counter() - t0
+    if handles:
+        for h in handles:
+            kind_lib[1].ref_fd_destroy(h)
+    return sample_units * FRAME * steps / dt, dt / steps, kind_lib[0]
+
+
+def reference_arm(args, rank):
+    if rank != 0:
+        return
+    n_threads = cpu_threads()
+    value, sps, kind = run_cpu(args, UNITS, args.steps, args.warmup, n_threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(), "streams": STREAMS, "channels": CHANNELS, "frame": FRAME},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_threads, "kind": kind,
+                         "sample": f"full workload: {UNITS} channel-frames per step, {args.steps} steps, "
+                                   "ia_core_coder_fd_frm_dec per channel-frame"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--groups", type=int, default=8, help="stream groups rotated through (working set > L2)")
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from libmpegh_b200.lib import Lib
+    import fd_cases
+
+    if not torch.cuda.is_available():
+        sys.exit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = Lib().create(local_rank)
+    stream = torch.cuda.current_stream()
+
+    # ---- device-resident synthetic inputs: G groups of 256 streams (this rank's shard) ----------
+    G = max(1, args.groups)
+    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    rng = np.random.default_rng(1234 + rank)
+    coef = [torch.randn(UNITS, FRAME, device="cuda", generator=gen) * 500.0 for _ in range(G)]
+    ovl = [torch.zeros(UNITS, FRAME, device="cuda") for _ in range(G)]
+    outb = [torch.empty(UNITS, FRAME, device="cuda") for _ in range(G)]
+    side = [torch.from_numpy(fd_cases.pack_side(make_side(rng, UNITS)).astype(np.int32)).cuda() for _ in range(G)]
+
+    def step(i):
+        g = i % G
+        lib.fd_synth_dev(coef[g].data_ptr(), side[g].data_ptr(), ovl[g].data_ptr(), outb[g].data_ptr(), UNITS,
+                         stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for i in range(args.steps):
+        step(args.warmup + i)
+    ev1.record(stream)
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = world * UNITS * FRAME / (ms_per_step * 1e-3)
+
+    # ---- e2e: host buffers through the session API, copies inside the timed region --------------
+    sess = lib.fd_open(STREAMS, CHANNELS)
+    n_host = 3
+    h_coef = [torch.empty(STREAMS, CHANNELS, FRAME, dtype=torch.float32).pin_memory() for _ in range(n_host)]
+    for h in h_coef:
+        h.copy_(torch.from_numpy(rng.normal(0, 500, (STREAMS, CHANNELS, FRAME)).astype(np.float32)))
+    h_out = [torch.empty(STREAMS, CHANNELS, FRAME, dtype=torch.float32).pin_memory() for _ in range(n_host)]
+    h_side = np.ascontiguousarray(fd_cases.pack_side(make_side(rng, UNITS)).reshape(STREAMS, CHANNELS))
+
+    def e2e_step(i):
+        k = i % n_host
+        lib.check(lib.c.mpeghb200_fd_execute(sess.h, h_coef[k].data_ptr(), h_side.ctypes.data, h_out[k].data_ptr()))
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.e2e_steps):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = world * UNITS * FRAME / e2e_s
+    sess.close()
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        achieved = BYTES_PER_UNIT * UNITS / (ms_per_step * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "fd_synth_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(), "streams_per_gpu": STREAMS, "channels": CHANNELS,
+                       "frame": FRAME, "l2_policy": f"inputs larger than L2: {G} stream groups rotated, "
+                       f"{G * 3 * UNITS * FRAME * 4 / 1e6:.0f} MB working set, state carried per group",
+                       "sharding": "streams by rank, no collective"},
+            "realtime_factor": value / CHANNELS / 48000.0,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "fd_synth_kernel", "algorithmic_bytes_per_launch": BYTES_PER_UNIT * UNITS},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": UNITS * FRAME * 4 + UNITS * 4,
+                    "d2h_bytes_per_step": UNITS * FRAME * 4, "ms_per_step": e2e_s * 1e3,
+                    "api": "mpeghb200_fd_execute (pinned host buffers)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            n_threads = cpu_threads()
+            sample_units = 24 * 16  # 16 streams x 24 ch
+            v, sps, kind = run_cpu(args, sample_units, 2500, 5, 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": kind,
+                                    "sample": f"{sample_units} channel-frames x 2500 frames on 1 host thread "
+                                              f"(box has {n_threads}); ia_core_coder_fd_frm_dec"}
+        print(json.dumps(line), flush=True)
+    lib.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

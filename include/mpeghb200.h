@@ -1,0 +1,103 @@
+/* mpeghb200.h -- C ABI of libmpeghb200.so: the B200 (sm_100a) implementation of libmpegh's post-parse
+ * signal path, batched over many independent streams.
+ *
+ * Boundary.  The reference decodes one frame of one stream per ia_mpegh_dec_execute call
+ * (decoder/impeghd_api.h:47-51).  Inside that call the bitstream half (MHAS/USAC parse, arithmetic
+ * decoding, scale factors, OAM/HOA side info) ends at decoder/ia_core_coder_process.c:1092 with the
+ * dequantised spectra usac_data->coef[ch][1024] and the per-channel side info complete; everything after
+ * that line is signal processing on planar FLOAT32 buffers.  This library replaces that second half.
+ * Each entry point below names the reference function it stands in for; INTEGRATION.md shows the patch a
+ * maintainer applies to the reference so that N decoder handles advance one frame per batched call.
+ *
+ * Conventions
+ *   - plain C types only; every buffer is caller-owned; sizes in elements unless a name ends in _bytes
+ *   - *_dev entry points take DEVICE pointers and a CUDA stream (cudaStream_t passed as void*, NULL =
+ *     default stream) and return after enqueueing; *_host entry points take HOST pointers, perform the
+ *     host<->device copies themselves and return when the result is in the host buffer
+ *   - status: 0 = OK; errors follow the reference's IA_ERRORCODE style (decoder/impeghd_error_codes.h):
+ *     negative (bit 31 set) = fatal for that call, nothing was written
+ *   - audio is planar fp32 at 16-bit scale (+-32768), [stream][channel][1024], as in the reference's
+ *     time_sample_vector (decoder/ia_core_coder_main.h:124)
+ *   - there is no CPU fallback: with no CUDA device every call returns MPEGHB200_ERR_NO_DEVICE
+ */
+#ifndef MPEGHB200_H
+#define MPEGHB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPEGHB200_FRAME_LEN 1024
+
+typedef int32_t mpeghb200_status;
+#define MPEGHB200_OK 0
+#define MPEGHB200_ERR_NO_DEVICE ((mpeghb200_status)0xFFFF8001)
+#define MPEGHB200_ERR_CUDA ((mpeghb200_status)0xFFFF8002)
+#define MPEGHB200_ERR_BAD_ARG ((mpeghb200_status)0xFFFF8003)
+#define MPEGHB200_ERR_NO_MEM ((mpeghb200_status)0xFFFF8004)
+#define MPEGHB200_ERR_UNSUPPORTED ((mpeghb200_status)0xFFFF8005)
+
+typedef struct mpeghb200_ctx mpeghb200_ctx;
+
+/* ---- context -------------------------------------------------------------------------------- */
+const char *mpeghb200_version(void);
+/* One context per GPU (streams are sharded across GPUs by the caller: no cross-GPU traffic). Uploads
+ * the constant tables. */
+mpeghb200_status mpeghb200_create(mpeghb200_ctx **out, int device_ordinal);
+void mpeghb200_destroy(mpeghb200_ctx *ctx);
+const char *mpeghb200_last_error(const mpeghb200_ctx *ctx); /* ctx may be NULL: last create() error */
+/* Number of kernel launches issued through this context so far (bench.py's gpu_launches). */
+uint64_t mpeghb200_launch_count(const mpeghb200_ctx *ctx);
+
+/* Host copy of a generated constant table (ids: libmpegh_b200/csrc/rom_tables.h). patched = 0 returns
+ * the pure-formula table (used by tools/gen_rom_patches.py). No GPU needed. */
+const float *mpeghb200_rom_table(int id, int patched, int *n_out);
+int mpeghb200_rom_count(void);
+const char *mpeghb200_rom_name(int id);
+
+/* Device memory helpers for callers without a CUDA runtime of their own (ctypes, cgo, JNI). */
+mpeghb200_status mpeghb200_dev_alloc(mpeghb200_ctx *ctx, size_t bytes, void **dptr);
+mpeghb200_status mpeghb200_dev_free(mpeghb200_ctx *ctx, void *dptr);
+mpeghb200_status mpeghb200_dev_memset(mpeghb200_ctx *ctx, void *dptr, int value, size_t bytes);
+mpeghb200_status mpeghb200_h2d(mpeghb200_ctx *ctx, void *dptr, const void *hptr, size_t bytes);
+mpeghb200_status mpeghb200_d2h(mpeghb200_ctx *ctx, void *hptr, const void *dptr, size_t bytes);
+mpeghb200_status mpeghb200_sync(mpeghb200_ctx *ctx);
+
+/* ---- FD synthesis: IMDCT + windowing + overlap-add ------------------------------------------
+ * Replaces ia_core_coder_fd_frm_dec (decoder/ia_core_coder_imdct.c:832) for FD-coded channels with FD
+ * history and no FAC data (LPD-coded channels are synthesised by the host).
+ * One unit = one channel of one stream for one frame.
+ *
+ * side[unit] packs what the reference keeps in ia_usac_data_struct (decoder/ia_core_coder_main.h:127-200):
+ *   bits 0-2 window_sequence[ch]   (0 ONLY_LONG, 1 LONG_START, 2 EIGHT_SHORT, 3 LONG_STOP, 4 STOP_START)
+ *   bit  3   window_shape[ch]      (0 sine, 1 KBD)
+ *   bit  4   window_shape_prev[ch]
+ *   bit  5   prev_aliasing_symmetry[ch]
+ *   bit  6   curr_aliasing_symmetry[ch]
+ */
+#define MPEGHB200_FD_SIDE(seq, shape, shape_prev, prev_sym, curr_sym)                              \
+  ((uint32_t)(((seq)&7) | (((shape)&1) << 3) | (((shape_prev)&1) << 4) | (((prev_sym)&1) << 5) |   \
+              (((curr_sym)&1) << 6)))
+
+/* coef [n_units][1024] (read only), overlap [n_units][1024] (read + replaced; the per-channel state the
+ * reference keeps in overlap_data_ptr), out [n_units][1024]. */
+mpeghb200_status mpeghb200_fd_synth_dev(mpeghb200_ctx *ctx, const float *d_coef, const uint32_t *d_side,
+                                        float *d_overlap, float *d_out, int n_units, void *cuda_stream);
+
+/* Host-buffer session: device-resident overlap state for n_streams x n_ch channels, pinned staging. */
+typedef struct mpeghb200_fd_session mpeghb200_fd_session;
+mpeghb200_status mpeghb200_fd_open(mpeghb200_ctx *ctx, int n_streams, int n_ch, mpeghb200_fd_session **out);
+/* One frame for every stream: h_coef/h_out [n_streams][n_ch][1024], h_side [n_streams][n_ch]. */
+mpeghb200_status mpeghb200_fd_execute(mpeghb200_fd_session *s, const float *h_coef, const uint32_t *h_side,
+                                      float *h_out);
+/* Zero the state of one stream (the reference's flush / re-init, decoder/impeghd_api.c:1156). */
+mpeghb200_status mpeghb200_fd_reset_stream(mpeghb200_fd_session *s, int stream);
+void mpeghb200_fd_close(mpeghb200_fd_session *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPEGHB200_H */

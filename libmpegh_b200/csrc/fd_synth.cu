@@ -1,0 +1,498 @@
+// fd_synth.cu -- IMDCT + windowing + overlap-add for FD-coded channels, one warp per channel-frame.
+//
+// Stands in for ia_core_coder_fd_frm_dec (decoder/ia_core_coder_imdct.c:832) and everything below it:
+// scale + pre-twiddle (:87, :366), the N/2-point complex transform impeghd_rad2_cplx_ifft
+// (decoder/impeghd_ifft.c:297), post-twiddle (:203), the windowing kernels
+// (decoder/ia_core_coder_basic_ops.c:124-508) and the overlap save (:762-815).
+//
+// Parity: every output sample is produced by the same sequence of separately rounded binary32 operations
+// as the reference (no FMA contraction, same butterfly forms, same table entries), so the result is
+// bit-identical; only the *schedule* differs.
+//
+// Schedule (B200): a unit is 4 KB of spectrum in, 4 KB of overlap in/out, 4 KB of PCM out -> HBM bound.
+// One warp owns one unit: 512 complex points = 16 per lane.
+//   1. lane l loads the 16 coefficient pairs {X[2c], X[2c+1]}, c = l + 32u, as coalesced 8-byte loads; the
+//      mirrored operand X[N-1-2c] of the pre-twiddle is the odd half of lane 31-l's pair (one shuffle).
+//      Those 16 points are exactly the inputs of the lane's four digit-reversed radix-4 butterflies of
+//      pass 0 and, after them, of its four pass-1 butterflies: two passes in registers.
+//   2. a padded shared-memory transpose (index i -> i + i/16, conflict free both ways) regroups the data so
+//      that passes 2 and 3 again run in registers; the final radix-2 pass pairs lanes l and l^16 by shuffle.
+//   3. post-twiddled samples go to shared memory once more so that windowing, overlap-add and the new
+//      overlap are computed per float4 with fully coalesced 16-byte global accesses.
+// EIGHT_SHORT frames run eight 64-point transforms the same way (4 lanes each).
+#include "common.h"
+
+namespace mpeghb200 {
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kSmemFloats = 1088;  // 544 padded complex values, reused as 1024 real samples
+
+__device__ __forceinline__ int pad16(int i) { return i + (i >> 4); }
+
+// (r, i) *= (c - j s) in the reference's product order: (r*c + i*s, -(r*s) + i*c)
+__device__ __forceinline__ void rot(float& r, float& i, float c, float s) {
+  const float nr = fadd(fmul(r, c), fmul(i, s));
+  const float ni = fadd(-fmul(r, s), fmul(i, c));
+  r = nr;
+  i = ni;
+}
+
+// Radix-4 butterfly in the reference's "a += b; b = a - 2b" form (decoder/impeghd_ifft.c:353-378).
+// In: x0..x3. Out (natural order): x0 -> A, x1 -> B, x2 -> C, x3 -> D.
+__device__ __forceinline__ void bfly4(float& x0r, float& x0i, float& x1r, float& x1i, float& x2r,
+                                      float& x2i, float& x3r, float& x3i) {
+  x0r = fadd(x0r, x2r);
+  x0i = fadd(x0i, x2i);
+  x2r = sub2(x0r, x2r);
+  x2i = sub2(x0i, x2i);
+  x1r = fadd(x1r, x3r);
+  x1i = fadd(x1i, x3i);
+  x3r = sub2(x1r, x3r);
+  x3i = sub2(x1i, x3i);
+
+  x0r = fadd(x0r, x1r);
+  x0i = fadd(x0i, x1i);
+  x1r = sub2(x0r, x1r);
+  x1i = sub2(x0i, x1i);
+  x2r = fsub(x2r, x3i);
+  x2i = fadd(x2i, x3r);
+  const float dr = add2(x2r, x3i);
+  const float di = sub2(x2i, x3r);
+  // reorder to natural output order A, B, C, D
+  const float cr = x1r, ci = x1i;
+  x1r = x2r;
+  x1i = x2i;
+  x2r = cr;
+  x2i = ci;
+  x3r = dr;
+  x3i = di;
+}
+
+// Passes 0 and 1 on the 16 points a lane holds: zr/zi[u], u = t + 4q -> y[16g + e] in place (e = index).
+__device__ __forceinline__ void fft16_first_two_passes(float (&r)[16], float (&i)[16], const float* __restrict__ eff) {
+  // pass 0: butterfly t takes u = t, t+4, t+8, t+12 and produces y[4t .. 4t+3]
+  float ar[16], ai[16];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    float x0r = r[t], x0i = i[t], x1r = r[t + 4], x1i = i[t + 4], x2r = r[t + 8], x2i = i[t + 8],
+          x3r = r[t + 12], x3i = i[t + 12];
+    bfly4(x0r, x0i, x1r, x1i, x2r, x2i, x3r, x3i);
+    ar[4 * t + 0] = x0r, ai[4 * t + 0] = x0i;
+    ar[4 * t + 1] = x1r, ai[4 * t + 1] = x1i;
+    ar[4 * t + 2] = x2r, ai[4 * t + 2] = x2i;
+    ar[4 * t + 3] = x3r, ai[4 * t + 3] = x3i;
+  }
+  // pass 1 (span 4, table step 64): butterfly m takes e = m, m+4, m+8, m+12; twiddle index j = 64 m
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    float x0r = ar[m], x0i = ai[m], x1r = ar[m + 4], x1i = ai[m + 4], x2r = ar[m + 8], x2i = ai[m + 8],
+          x3r = ar[m + 12], x3i = ai[m + 12];
+    if (m > 0) {
+      const float* e = eff + 64 * m * 6;
+      rot(x1r, x1i, __ldg(e + 0), __ldg(e + 1));
+      rot(x2r, x2i, __ldg(e + 2), __ldg(e + 3));
+      rot(x3r, x3i, __ldg(e + 4), __ldg(e + 5));
+    }
+    bfly4(x0r, x0i, x1r, x1i, x2r, x2i, x3r, x3i);
+    r[m] = x0r, i[m] = x0i;
+    r[m + 4] = x1r, i[m + 4] = x1i;
+    r[m + 8] = x2r, i[m + 8] = x2i;
+    r[m + 12] = x3r, i[m + 12] = x3i;
+  }
+}
+
+// One twiddled radix-4 butterfly on registers; j == 0 means "no multiplication at all" in the reference.
+__device__ __forceinline__ void bfly4_tw(float& x0r, float& x0i, float& x1r, float& x1i, float& x2r,
+                                         float& x2i, float& x3r, float& x3i, const float* __restrict__ e,
+                                         bool twiddle) {
+  if (twiddle) {
+    rot(x1r, x1i, __ldg(e + 0), __ldg(e + 1));
+    rot(x2r, x2i, __ldg(e + 2), __ldg(e + 3));
+    rot(x3r, x3i, __ldg(e + 4), __ldg(e + 5));
+  }
+  bfly4(x0r, x0i, x1r, x1i, x2r, x2i, x3r, x3i);
+}
+
+struct Side {
+  int seq, shape, shape_prev, tkt;
+};
+__device__ __forceinline__ Side unpack_side(uint32_t s) {
+  Side o;
+  o.seq = int(s & 7u);
+  o.shape = int((s >> 3) & 1u);
+  o.shape_prev = int((s >> 4) & 1u);
+  o.tkt = int(((s >> 5) & 1u) << 1) | int((s >> 6) & 1u);
+  return o;
+}
+
+// ---- generic pre-twiddle for transform kernel types 1..3 (decoder/ia_core_coder_imdct.c:98-170) ----------
+// xs = scaled spectrum block in shared memory (N floats), nl = N/2, c = output index. Rare path.
+__device__ __noinline__ float2 pretwiddle_generic(const float* xs, int N, int tkt, int c, const DeviceTables& T) {
+  const int nl = N >> 1;
+  float zr, zi;
+  if (tkt == 3) {
+    const float2 cs = __ldg(((nl == 512) ? T.tw512 : T.tw64) + c);
+    const float a = xs[2 * c];               // even entries untouched by the reorder
+    const float b = -xs[N - 1 - 2 * c];      // odd entry 2c+1 after the swap-negate reorder
+    zr = fsub(fmul(b, cs.x), fmul(a, cs.y));
+    zi = fadd(fmul(a, cs.x), fmul(b, cs.y));
+    return make_float2(zr, zi);
+  }
+  // DCT-II / DST-II.  X'[n] = X[N-1-n] for type 1.
+  auto X = [&](int n) { return (tkt == 1) ? xs[N - 1 - n] : xs[n]; };
+  const float* C = T.dct_cos;
+  const float* S = T.dct_sin;
+  if (c == 0) {
+    const float s4 = 0.70710677f;  // (float)sin(pi/4)
+    zr = fadd(X(0), fmul(X(nl), s4));
+    zi = fsub(X(0), fmul(X(nl), s4));
+    return make_float2(zr, zi);
+  }
+  const int i = (c <= nl / 2) ? c : nl - c;
+  const float re1 = fmul(fadd(fmul(X(i), __ldg(C + i - 1)), fmul(X(N - i), __ldg(S + i - 1))), 0.5f);
+  const float re2 = fmul(fadd(fmul(X(nl - i), __ldg(S + nl + i - 1)), fmul(X(nl + i), __ldg(C + nl + i - 1))), 0.5f);
+  const float im1 = fmul(fsub(fmul(X(i), __ldg(S + i - 1)), fmul(X(N - i), __ldg(C + i - 1))), 0.5f);
+  const float im2 = fmul(fsub(fmul(X(nl - i), __ldg(C + nl + i - 1)), fmul(X(nl + i), __ldg(S + nl + i - 1))), 0.5f);
+  const float c4 = __ldg(C + 4 * i - 1), s4 = __ldg(S + 4 * i - 1);
+  const float tmp_i = fsub(im1, im2);
+  const float ii = fsub(fmul(fsub(re1, re2), c4), fmul(fadd(im1, im2), s4));
+  const float tmp_r = fadd(re1, re2);
+  const float rr = fadd(fmul(fadd(im1, im2), c4), fmul(fsub(re1, re2), s4));
+  if (2 * c < nl) {
+    zi = fadd(ii, tmp_i);
+    zr = fsub(tmp_r, rr);
+  } else if (2 * c > nl) {
+    zi = fsub(ii, tmp_i);
+    zr = fadd(tmp_r, rr);
+  } else {
+    // c == nl/2: the reference overwrites the element it is about to read (:140-149)
+    zi = fadd(fsub(ii, tmp_i), tmp_i);
+    zr = fsub(tmp_r, fsub(tmp_r, fadd(tmp_r, rr)));
+  }
+  return make_float2(zr, zi);
+}
+
+// Post-twiddle of transform output y[k] = (r, q) into the block's time-aliased samples xs[0..N-1]
+// (decoder/ia_core_coder_imdct.c:214-273), all four kernel types. `first_odd` selects which of the two
+// stores goes first (bank-conflict avoidance only).
+__device__ __forceinline__ void posttwiddle_store(float* xs, int N, int tkt, int k, float r, float q, float2 cs,
+                                                  bool first_odd) {
+  const int nl = N >> 1;
+  if (tkt == 1 || tkt == 2) {
+    const bool lo = k < nl / 2;
+    const int kk = lo ? k : nl - 1 - k;
+    const int nr = lo ? 4 * kk : 4 * kk + 3;
+    const int nq = lo ? 4 * kk + 2 : 4 * kk + 1;
+    xs[nr] = (tkt == 1 && (nr & 1)) ? -r : r;
+    xs[nq] = (tkt == 1 && (nq & 1)) ? -q : q;
+    return;
+  }
+  const float xa = -fsub(fmul(r, cs.x), fmul(q, cs.y));
+  float xb = -fadd(fmul(q, cs.x), fmul(r, cs.y));
+  if (tkt == 3) xb = -xb;
+  if (first_odd) {
+    xs[N - 1 - 2 * k] = xb;
+    xs[2 * k] = xa;
+  } else {
+    xs[2 * k] = xa;
+    xs[N - 1 - 2 * k] = xb;
+  }
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ldcs4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void stcs4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+__device__ __forceinline__ float4 rev4(float4 v) { return make_float4(v.w, v.z, v.y, v.x); }
+__device__ __forceinline__ float4 neg4(float4 v) { return make_float4(-v.x, -v.y, -v.z, -v.w); }
+
+// out = s*wf + o*wr per component
+__device__ __forceinline__ float4 win4(float4 s, float4 wf, float4 o, float4 wr) {
+  return make_float4(mul_add_mul(s.x, wf.x, o.x, wr.x), mul_add_mul(s.y, wf.y, o.y, wr.y),
+                     mul_add_mul(s.z, wf.z, o.z, wr.z), mul_add_mul(s.w, wf.w, o.w, wr.w));
+}
+
+// ---- long block: windowing_long1 / windowing_long3 + overlap save, gather form --------------------------
+// xs[0..1023] = IMDCT output. For position i: s(i) = xs[512+i] (i < 512), -/+ xs[1535-i] (i >= 512).
+__device__ __forceinline__ void window_long(const float* xs, float* __restrict__ ov, float* __restrict__ out,
+                                            const Side sd, const DeviceTables& T, int lane) {
+  const bool start_like = (sd.seq == 0 || sd.seq == 1);  // ONLY_LONG, LONG_START
+  const bool pos_tail = start_like ? (sd.tkt == 2 || sd.tkt == 3) : (sd.tkt == 3);
+  const bool hi_pos = (sd.tkt == 1 || sd.tkt == 2);  // sign of overlap[512 + i] = +-x[i]
+  const bool lo_pos = (sd.tkt == 2 || sd.tkt == 3);  // sign of overlap[511 - i]
+  const float* wl = T.win_long[sd.shape_prev];
+  const float* wsh = T.win_short[sd.shape_prev];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int i4 = 4 * (lane + 32 * it);
+    float4 s;
+    if (i4 < 512) {
+      s = ld4(xs + 512 + i4);
+    } else {
+      s = rev4(ld4(xs + 1532 - i4));
+      if (!pos_tail) s = neg4(s);
+    }
+    float4 o;
+    if (start_like) {
+      const float4 ovv = ldcs4(ov + i4);
+      o = win4(s, ldg4(wl + i4), ovv, rev4(ldg4(wl + 1020 - i4)));
+    } else if (i4 < 448) {
+      o = ldcs4(ov + i4);
+    } else if (i4 < 576) {
+      const float4 ovv = ldcs4(ov + i4);
+      o = win4(s, ldg4(wsh + i4 - 448), ovv, rev4(ldg4(wsh + 572 - i4)));
+    } else {
+      o = s;
+    }
+    stcs4(out + i4, o);
+    // new overlap at the same positions this lane just consumed: no cross-lane hazard
+    float4 n;
+    if (i4 >= 512) {
+      n = ld4(xs + i4 - 512);
+      if (!hi_pos) n = neg4(n);
+    } else {
+      n = rev4(ld4(xs + 508 - i4));
+      if (!lo_pos) n = neg4(n);
+    }
+    st4(ov + i4, n);
+  }
+}
+
+// ---- eight short blocks: windowing_short2/3/4, gather form ---------------------------------------------
+// xs[128k + n] = block k's IMDCT output.  Work positions P in [0, 2048): [0,1024) -> out, [1024,2048) ->
+// new overlap.  See oracle/oracle_fd.c short_blocks() for the derivation of the accumulation order.
+__device__ __forceinline__ float short_rise(const float* xk, const float* w, int t, int tkt) {
+  if (t < 64) return fmul(xk[64 + t], __ldg(w + t));
+  const float v = xk[191 - t];
+  return fmul(tkt == 3 ? v : -v, __ldg(w + t));
+}
+__device__ __forceinline__ float short_fall_val(const float* xk, int t, int tkt) {
+  if (t < 64) {
+    const float v = xk[63 - t];
+    return tkt == 3 ? v : -v;
+  }
+  return -xk[t - 64];
+}
+
+__device__ void window_short(const float* xs, float* __restrict__ ov, float* __restrict__ out, const Side sd,
+                             const DeviceTables& T, int lane) {
+  const float* wc = T.win_short[sd.shape];
+  const float* wp = T.win_short[sd.shape_prev];
+  const int tkt = sd.tkt;
+  for (int it = 0; it < 16; ++it) {
+    const int P4 = 4 * (lane + 32 * it);
+    float v[4];
+    if (P4 < 448) {
+      const float4 o = ldcs4(ov + P4);
+      v[0] = o.x, v[1] = o.y, v[2] = o.z, v[3] = o.w;
+    } else if (P4 < 576) {
+      const float4 o = ldcs4(ov + P4);
+      const float oo[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int t = P4 + e - 448;
+        float a;
+        if (t < 64) {
+          a = xs[64 + t];
+        } else {
+          a = xs[191 - t];
+          if (tkt != 3) a = -a;
+        }
+        v[e] = mul_add_mul(a, __ldg(wp + t), oo[e], __ldg(wp + 127 - t));
+      }
+    } else if (P4 < 1600) {
+      const int k = (P4 - 576) >> 7;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int t = (P4 + e - 576) & 127;
+        const float* xk = xs + 128 * k;
+        float acc;
+        if (k == 0 && tkt == 3 && t < 64) {
+          acc = fmul(xk[63 - t], fadd(__ldg(wc + 127 - t), 0.0f));  // reference quirk, basic_ops.c:404
+        } else {
+          float f = short_fall_val(xk, t, tkt);
+          if (k != 7) f = fmul(f, __ldg(wc + 127 - t));
+          acc = fadd(0.0f, f);
+        }
+        if (k != 7) acc = fadd(acc, short_rise(xk + 128, wc, t, tkt));
+        v[e] = acc;
+      }
+    } else {
+      v[0] = v[1] = v[2] = v[3] = 0.0f;
+    }
+    const float4 o4 = make_float4(v[0], v[1], v[2], v[3]);
+    if (P4 < 1024) {
+      stcs4(out + P4, o4);
+      // old overlap beyond 576 is discarded by the reference (memset in windowing_short2)
+    }
+    // new overlap position P4 - 1024 is the position this same lane read eight iterations ago: the
+    // in-place update has no cross-lane hazard
+    if (P4 >= 1024) st4(ov + P4 - 1024, o4);
+  }
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+    fd_synth_kernel(const float* __restrict__ coef, const uint32_t* __restrict__ side, float* __restrict__ overlap,
+                    float* __restrict__ out, int n_units, const DeviceTables T) {
+  __shared__ __align__(16) float smem[WARPS][kSmemFloats];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.x * WARPS + warp;
+  if (unit >= n_units) return;
+  float* sm = smem[warp];
+  float2* smc = reinterpret_cast<float2*>(sm);
+  const Side sd = unpack_side(__ldg(side + unit));
+  const float* X = coef + size_t(unit) * 1024;
+  float* ov = overlap + size_t(unit) * 1024;
+  float* o = out + size_t(unit) * 1024;
+  const bool is_short = (sd.seq == 2);
+  const int N = is_short ? 128 : 1024;            // block length
+  const float norm = is_short ? 0.0078125f : 0.0009765625f;  // 2 / (2N)
+
+  float zr[16], zi[16];
+  if (sd.tkt == 0) {
+    // c = lane + 32u (long) or, per short block T8 = lane>>2, c = g + 4u with g = lane&3
+    float2 eo[16];
+    const float2* X2 = reinterpret_cast<const float2*>(X);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = is_short ? (64 * (lane >> 2) + (lane & 3) + 4 * u) : (lane + 32 * u);
+      eo[u] = __ldcs(X2 + idx);
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      eo[u].x = fmul(eo[u].x, norm);
+      eo[u].y = fmul(eo[u].y, norm);
+    }
+    const int mirror = is_short ? 3 : 31;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int c = is_short ? ((lane & 3) + 4 * u) : (lane + 32 * u);
+      const float2 cs = __ldg((is_short ? T.tw64 : T.tw512) + c);
+      const float a = eo[u].x;
+      const float b = __shfl_xor_sync(kFull, eo[15 - u].y, mirror);
+      zr[u] = fsub(-fmul(a, cs.x), fmul(b, cs.y));
+      zi[u] = fsub(fmul(b, cs.x), fmul(a, cs.y));
+    }
+  } else {
+    // stage the scaled spectrum in shared memory, then evaluate the type-specific pre-twiddle per point
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int i4 = 4 * (lane + 32 * it);
+      float4 v = ldcs4(X + i4);
+      v.x = fmul(v.x, norm), v.y = fmul(v.y, norm), v.z = fmul(v.z, norm), v.w = fmul(v.w, norm);
+      st4(sm + i4, v);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const float2 z = is_short ? pretwiddle_generic(sm + 128 * (lane >> 2), 128, sd.tkt, (lane & 3) + 4 * u, T)
+                                : pretwiddle_generic(sm, 1024, sd.tkt, lane + 32 * u, T);
+      zr[u] = z.x, zi[u] = z.y;
+    }
+    __syncwarp();
+  }
+
+  // passes 0 + 1 in registers: lane now holds y[16 g + e] (per transform)
+  fft16_first_two_passes(zr, zi, T.eff);
+
+  // transpose through shared memory
+  {
+    int base;  // index of y[16 g] in the warp's 512-point space
+    if (is_short) {
+      base = 64 * (lane >> 2) + 16 * (lane & 3);
+    } else {
+      const int g = ((lane >> 3) & 3) | (((lane >> 1) & 3) << 2) | ((lane & 1) << 4);
+      base = 16 * g;
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) smc[pad16(base + e)] = make_float2(zr[e], zi[e]);
+  }
+  __syncwarp();
+
+  if (!is_short) {
+    const int H = lane >> 4, m16 = lane & 15;
+#pragma unroll
+    for (int v = 0; v < 16; ++v) {
+      const float2 t = smc[pad16(256 * H + m16 + 16 * v)];
+      zr[v] = t.x, zi[v] = t.y;
+    }
+    __syncwarp();
+    // pass 2 (span 16, table step 16): butterflies t' on v = 4t'..4t'+3, twiddle index j = 16 m16
+    {
+      const float* e = T.eff + 16 * m16 * 6;
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        bfly4_tw(zr[4 * t], zi[4 * t], zr[4 * t + 1], zi[4 * t + 1], zr[4 * t + 2], zi[4 * t + 2], zr[4 * t + 3],
+                 zi[4 * t + 3], e, m16 != 0);
+    }
+    // pass 3 (span 64, table step 4): butterflies r on v = r, r+4, r+8, r+12, j = 4 (m16 + 16 r)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float* e = T.eff + 4 * (m16 + 16 * r) * 6;
+      bfly4_tw(zr[r], zi[r], zr[r + 4], zi[r + 4], zr[r + 8], zi[r + 8], zr[r + 12], zi[r + 12], e,
+               (m16 + 16 * r) != 0);
+    }
+    // final radix-2 pass (decoder/impeghd_ifft.c:779-837) between lanes l and l^16, then post-twiddle
+#pragma unroll
+    for (int v = 0; v < 16; ++v) {
+      const int p = m16 + 16 * v;
+      const float pr = __shfl_xor_sync(kFull, zr[v], 16);
+      const float pi = __shfl_xor_sync(kFull, zi[v], 16);
+      const float x0r = H ? pr : zr[v], x0i = H ? pi : zi[v];
+      float x1r = H ? zr[v] : pr, x1i = H ? zi[v] : pi;
+      const float2 w = __ldg(T.rad2_512 + p);
+      rot(x1r, x1i, w.x, w.y);
+      const float yr = H ? fsub(x0r, x1r) : fadd(x0r, x1r);
+      const float yi = H ? fsub(x0i, x1i) : fadd(x0i, x1i);
+      const int k = 256 * H + p;
+      posttwiddle_store(sm, 1024, sd.tkt, k, yr, yi, __ldg(T.tw512 + k), H != 0);
+    }
+    __syncwarp();
+    window_long(sm, ov, o, sd, T, lane);
+  } else {
+    // 64-point transforms: last pass (span 16, table step 16) butterfly m = g' + 4r on y[m + 16 q]
+    const int T8 = lane >> 2, gq = lane & 3;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 t = smc[pad16(64 * T8 + gq + 4 * r + 16 * q)];
+        zr[4 * r + q] = t.x, zi[4 * r + q] = t.y;
+      }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int m = gq + 4 * r;
+      const float* e = T.eff + 16 * m * 6;
+      bfly4_tw(zr[4 * r], zi[4 * r], zr[4 * r + 1], zi[4 * r + 1], zr[4 * r + 2], zi[4 * r + 2], zr[4 * r + 3],
+               zi[4 * r + 3], e, m != 0);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = gq + 4 * r + 16 * q;
+        posttwiddle_store(sm + 128 * T8, 128, sd.tkt, k, zr[4 * r + q], zi[4 * r + q], __ldg(T.tw64 + k), false);
+      }
+    __syncwarp();
+    window_short(sm, ov, o, sd, T, lane);
+  }
+}
+
+}  // namespace
+
+mpeghb200_status fd_synth_launch(mpeghb200_ctx* ctx, const float* d_coef, const uint32_t* d_side, float* d_overlap,
+                                 float* d_out, int n_units, cudaStream_t stream) {
+  if (n_units == 0) return MPEGHB200_OK;
+  constexpr int WARPS = 4;
+  const int grid = (n_units + WARPS - 1) / WARPS;
+  fd_synth_kernel<WARPS><<<grid, WARPS * 32, 0, stream>>>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables);
+  ctx->launches.fetch_add(1);
+  MB_CUDA(ctx, cudaGetLastError());
+  return MPEGHB200_OK;
+}
+
+}  // namespace mpeghb200

@@ -1,0 +1,165 @@
+"""ctypes binding of libmpeghb200.so (see include/mpeghb200.h).  No fallbacks: a missing library raises."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "libmpeghb200.so")
+
+OK = 0
+ERR_NO_DEVICE = -0x7FFF  # 0xFFFF8001 as int32
+FRAME_LEN = 1024
+
+ONLY_LONG, LONG_START, EIGHT_SHORT, LONG_STOP, STOP_START = range(5)
+
+
+def _i32(x):
+    return ctypes.c_int32(x).value
+
+
+class MpeghError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"mpeghb200 status 0x{code & 0xFFFFFFFF:08X}: {msg}")
+        self.code = code
+
+
+def build(verbose=False):
+    """Compile libmpeghb200.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    subprocess.run(["make", "-s" if not verbose else "-k", "-C", os.path.join(HERE, "csrc"), "-j8"], check=True)
+    return SO_PATH
+
+
+def fd_side(seq, shape=0, shape_prev=0, prev_sym=0, curr_sym=0):
+    """MPEGHB200_FD_SIDE packing (numpy-broadcastable)."""
+    seq, shape, shape_prev, prev_sym, curr_sym = (np.asarray(v, dtype=np.uint32) for v in
+                                                  (seq, shape, shape_prev, prev_sym, curr_sym))
+    return ((seq & 7) | ((shape & 1) << 3) | ((shape_prev & 1) << 4) | ((prev_sym & 1) << 5) |
+            ((curr_sym & 1) << 6)).astype(np.uint32)
+
+
+class Lib:
+    """Thin object wrapper: one instance = one loaded library + (lazily) one context per device."""
+
+    def __init__(self, path=SO_PATH):
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)")
+        self.c = ctypes.CDLL(path)
+        c = self.c
+        vp, i32, u64, sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint64, ctypes.c_size_t
+        c.mpeghb200_version.restype = ctypes.c_char_p
+        c.mpeghb200_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int]
+        c.mpeghb200_create.restype = i32
+        c.mpeghb200_destroy.argtypes = [vp]
+        c.mpeghb200_last_error.argtypes = [vp]
+        c.mpeghb200_last_error.restype = ctypes.c_char_p
+        c.mpeghb200_launch_count.argtypes = [vp]
+        c.mpeghb200_launch_count.restype = u64
+        c.mpeghb200_rom_table.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+        c.mpeghb200_rom_table.restype = ctypes.POINTER(ctypes.c_float)
+        c.mpeghb200_rom_count.restype = ctypes.c_int
+        c.mpeghb200_rom_name.argtypes = [ctypes.c_int]
+        c.mpeghb200_rom_name.restype = ctypes.c_char_p
+        c.mpeghb200_dev_alloc.argtypes = [vp, sz, ctypes.POINTER(vp)]
+        c.mpeghb200_dev_alloc.restype = i32
+        c.mpeghb200_dev_free.argtypes = [vp, vp]
+        c.mpeghb200_dev_free.restype = i32
+        c.mpeghb200_dev_memset.argtypes = [vp, vp, ctypes.c_int, sz]
+        c.mpeghb200_dev_memset.restype = i32
+        c.mpeghb200_h2d.argtypes = [vp, vp, vp, sz]
+        c.mpeghb200_h2d.restype = i32
+        c.mpeghb200_d2h.argtypes = [vp, vp, vp, sz]
+        c.mpeghb200_d2h.restype = i32
+        c.mpeghb200_sync.argtypes = [vp]
+        c.mpeghb200_sync.restype = i32
+        c.mpeghb200_fd_synth_dev.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, vp]
+        c.mpeghb200_fd_synth_dev.restype = i32
+        c.mpeghb200_fd_open.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
+        c.mpeghb200_fd_open.restype = i32
+        c.mpeghb200_fd_execute.argtypes = [vp, vp, vp, vp]
+        c.mpeghb200_fd_execute.restype = i32
+        c.mpeghb200_fd_reset_stream.argtypes = [vp, ctypes.c_int]
+        c.mpeghb200_fd_reset_stream.restype = i32
+        c.mpeghb200_fd_close.argtypes = [vp]
+        self.ctx = None
+
+    # ---- context ------------------------------------------------------------------------------
+    def version(self):
+        return self.c.mpeghb200_version().decode()
+
+    def create(self, device=0):
+        h = ctypes.c_void_p()
+        st = self.c.mpeghb200_create(ctypes.byref(h), device)
+        if st != OK:
+            raise MpeghError(st, self.c.mpeghb200_last_error(None).decode())
+        self.ctx = h
+        return self
+
+    def close(self):
+        if self.ctx:
+            self.c.mpeghb200_destroy(self.ctx)
+            self.ctx = None
+
+    def check(self, st):
+        if st != OK:
+            raise MpeghError(st, self.c.mpeghb200_last_error(self.ctx).decode())
+
+    def launch_count(self):
+        return int(self.c.mpeghb200_launch_count(self.ctx))
+
+    # ---- constant tables (host side, no GPU needed) ------------------------------------------------
+    def rom_tables(self, patched=True):
+        out = {}
+        for i in range(self.c.mpeghb200_rom_count()):
+            n = ctypes.c_int()
+            p = self.c.mpeghb200_rom_table(i, 1 if patched else 0, ctypes.byref(n))
+            out[self.c.mpeghb200_rom_name(i).decode()] = np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+        return out
+
+    # ---- FD synthesis -------------------------------------------------------------------------
+    def fd_synth_dev(self, d_coef, d_side, d_overlap, d_out, n_units, stream=0):
+        """Raw device pointers (ints), e.g. torch tensor .data_ptr(); stream = cudaStream_t as int."""
+        self.check(self.c.mpeghb200_fd_synth_dev(self.ctx, d_coef, d_side, d_overlap, d_out, n_units, stream))
+
+    def fd_open(self, n_streams, n_ch):
+        return FdSession(self, n_streams, n_ch)
+
+
+class FdSession:
+    """Host-buffer FD synthesis session (mpeghb200_fd_open/execute/close)."""
+
+    def __init__(self, lib, n_streams, n_ch):
+        self.lib, self.n_streams, self.n_ch = lib, n_streams, n_ch
+        h = ctypes.c_void_p()
+        lib.check(lib.c.mpeghb200_fd_open(lib.ctx, n_streams, n_ch, ctypes.byref(h)))
+        self.h = h
+
+    def execute(self, coef, side, out=None):
+        coef = np.ascontiguousarray(coef, dtype=np.float32)
+        side = np.ascontiguousarray(side, dtype=np.uint32)
+        assert coef.shape == (self.n_streams, self.n_ch, FRAME_LEN) and side.shape == (self.n_streams, self.n_ch)
+        if out is None:
+            out = np.empty_like(coef)
+        self.lib.check(self.lib.c.mpeghb200_fd_execute(self.h, coef.ctypes.data, side.ctypes.data, out.ctypes.data))
+        return out
+
+    def reset_stream(self, idx):
+        self.lib.check(self.lib.c.mpeghb200_fd_reset_stream(self.h, idx))
+
+    def close(self):
+        if self.h:
+            self.lib.c.mpeghb200_fd_close(self.h)
+            self.h = None
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        _lib = Lib()
+    return _lib
