@@ -24,6 +24,13 @@ struct DeviceTables {
   const float* win_short[2] = {nullptr, nullptr};  // sine_128, kbd_128
   const float* dct_cos = nullptr;  // [1024] DCT/DST-II pre-twiddle
   const float* dct_sin = nullptr;
+  // lane-ordered float4 packings for the long-block fast path (two table entries per 16-byte load,
+  // a warp-wide load covers 512 contiguous bytes): index [pair][lane]
+  const float4* pre4 = nullptr;    // [8][32] tw512[lane + 32u], u = 2*pair, 2*pair+1
+  const float4* post4 = nullptr;   // [8][32] tw512[256H + m16 + 16v], v = 2*pair, 2*pair+1 (lane = 16H + m16)
+  const float4* rad2p4 = nullptr;  // [8][32] rad2_512[m16 + 16v]
+  const float4* eff8 = nullptr;    // [256][2] (c1,s1,c2,s2), (c3,s3,0,0) by twiddle index j
+  float pass1[3][6] = {};          // eff[64m], m = 1..3: warp-uniform, passed by value (constant bank)
 };
 
 }  // namespace mpeghb200
@@ -33,6 +40,7 @@ struct mpeghb200_ctx {
   int sm_count = 0;
   std::string last_error;
   std::atomic<uint64_t> launches{0};
+  int fd_variant = 0;  // tuning knob, see fd_synth_launch
   mpeghb200::DeviceTables tables;
   std::vector<void*> owned;  // device allocations released by destroy()
 };

@@ -1,4 +1,5 @@
 // ctx.cu -- context life cycle, constant-table upload, device memory helpers of the C ABI.
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -106,6 +107,34 @@ static mpeghb200_status upload_tables(mpeghb200_ctx* ctx) {
   if ((st = upload(ctx, rom_table(ROM_KBD_128), &t.win_short[1]))) return st;
   if ((st = upload(ctx, rom_table(ROM_DCTDST_COS_1024), &t.dct_cos))) return st;
   if ((st = upload(ctx, rom_table(ROM_DCTDST_SIN_1024), &t.dct_sin))) return st;
+  // lane-ordered packings for the fast path
+  {
+    const auto& tc = rom_table(ROM_TWID_COS_512);
+    const auto& ts = rom_table(ROM_TWID_SIN_512);
+    const std::vector<float> eff = effective_twiddles(w);
+    const std::vector<float2> r2 = radix2_twiddles_512(w);
+    std::vector<float4> pre(8 * 32), post(8 * 32), rad(8 * 32), e8(256 * 2);
+    for (int pair = 0; pair < 8; ++pair)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int c0 = lane + 32 * (2 * pair), c1 = lane + 32 * (2 * pair + 1);
+        pre[pair * 32 + lane] = make_float4(tc[c0], ts[c0], tc[c1], ts[c1]);
+        const int H = lane >> 4, m16 = lane & 15;
+        const int p0 = m16 + 16 * (2 * pair), p1 = m16 + 16 * (2 * pair + 1);
+        const int k0 = 256 * H + p0, k1 = 256 * H + p1;
+        post[pair * 32 + lane] = make_float4(tc[k0], ts[k0], tc[k1], ts[k1]);
+        rad[pair * 32 + lane] = make_float4(r2[p0].x, r2[p0].y, r2[p1].x, r2[p1].y);
+      }
+    for (int j = 0; j < 256; ++j) {
+      e8[2 * j] = make_float4(eff[6 * j], eff[6 * j + 1], eff[6 * j + 2], eff[6 * j + 3]);
+      e8[2 * j + 1] = make_float4(eff[6 * j + 4], eff[6 * j + 5], 0.f, 0.f);
+    }
+    for (int m = 1; m < 4; ++m)
+      for (int q = 0; q < 6; ++q) t.pass1[m - 1][q] = eff[6 * 64 * m + q];
+    if ((st = upload(ctx, pre, &t.pre4))) return st;
+    if ((st = upload(ctx, post, &t.post4))) return st;
+    if ((st = upload(ctx, rad, &t.rad2p4))) return st;
+    if ((st = upload(ctx, e8, &t.eff8))) return st;
+  }
   return MPEGHB200_OK;
 }
 
@@ -132,6 +161,7 @@ mpeghb200_status mpeghb200_create(mpeghb200_ctx** out, int device_ordinal) {
   mpeghb200_ctx* ctx = new (std::nothrow) mpeghb200_ctx();
   if (!ctx) return MPEGHB200_ERR_NO_MEM;
   ctx->device = device_ordinal;
+  if (const char* v = std::getenv("MPEGHB200_FD_VARIANT")) ctx->fd_variant = std::atoi(v);
   e = cudaSetDevice(device_ordinal);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_ordinal);
   if (e != cudaSuccess) {

@@ -333,20 +333,11 @@ __device__ void window_short(const float* xs, float* __restrict__ ov, float* __r
   }
 }
 
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
-    fd_synth_kernel(const float* __restrict__ coef, const uint32_t* __restrict__ side, float* __restrict__ overlap,
-                    float* __restrict__ out, int n_units, const DeviceTables T) {
-  __shared__ __align__(16) float smem[WARPS][kSmemFloats];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int unit = blockIdx.x * WARPS + warp;
-  if (unit >= n_units) return;
-  float* sm = smem[warp];
+// General path: every window sequence and transform kernel type (EIGHT_SHORT frames and kernel switching
+// are rare; ONLY_LONG-family frames with kernel type 0 take fd_unit_long_fast instead).
+__device__ __noinline__ void fd_unit_generic(const float* __restrict__ X, float* __restrict__ ov, float* __restrict__ o,
+                                             const Side sd, float* sm, const DeviceTables& T, int lane) {
   float2* smc = reinterpret_cast<float2*>(sm);
-  const Side sd = unpack_side(__ldg(side + unit));
-  const float* X = coef + size_t(unit) * 1024;
-  float* ov = overlap + size_t(unit) * 1024;
-  float* o = out + size_t(unit) * 1024;
   const bool is_short = (sd.seq == 2);
   const int N = is_short ? 128 : 1024;            // block length
   const float norm = is_short ? 0.0078125f : 0.0009765625f;  // 2 / (2N)
@@ -482,14 +473,244 @@ __global__ void __launch_bounds__(WARPS * 32)
   }
 }
 
+
+// ---- fast path: long block, transform kernel type 0 ---------------------------------------------------
+// Same arithmetic as fd_unit_generic, scheduled for throughput: all 16 coefficient loads and an L2 prefetch
+// of the overlap are in flight before the first dependent instruction, tables come as lane-ordered float4,
+// pass-1 twiddles from the constant bank, no divergent branches, all overlap loads issued before the
+// first store of the windowing phase.
+__device__ __forceinline__ void rot_sel(float& r, float& i, float c, float s, bool on) {
+  float nr = r, ni = i;
+  rot(nr, ni, c, s);
+  r = on ? nr : r;  // j == 0: the reference does not multiply at all (keeps signed zeros intact)
+  i = on ? ni : i;
+}
+
+__device__ __forceinline__ void fd_unit_long_fast(float2 (&eo)[16], float* __restrict__ ov, float* __restrict__ o,
+                                                  const Side sd, float* sm, const DeviceTables& T, int lane) {
+  float2* smc = reinterpret_cast<float2*>(sm);
+  const float norm = 0.0009765625f;  // 2 / 2048
+  float zr[16], zi[16];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    eo[u].x = fmul(eo[u].x, norm);
+    eo[u].y = fmul(eo[u].y, norm);
+  }
+#pragma unroll
+  for (int pr = 0; pr < 8; ++pr) {
+    const float4 cs = __ldg(T.pre4 + pr * 32 + lane);
+    {
+      const int u = 2 * pr;
+      const float a = eo[u].x, b = __shfl_xor_sync(kFull, eo[15 - u].y, 31);
+      zr[u] = fsub(-fmul(a, cs.x), fmul(b, cs.y));
+      zi[u] = fsub(fmul(b, cs.x), fmul(a, cs.y));
+    }
+    {
+      const int u = 2 * pr + 1;
+      const float a = eo[u].x, b = __shfl_xor_sync(kFull, eo[15 - u].y, 31);
+      zr[u] = fsub(-fmul(a, cs.z), fmul(b, cs.w));
+      zi[u] = fsub(fmul(b, cs.z), fmul(a, cs.w));
+    }
+  }
+  // passes 0 and 1 in registers; pass-1 twiddles are warp-uniform kernel parameters (constant bank)
+  {
+    float ar[16], ai[16];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float x0r = zr[t], x0i = zi[t], x1r = zr[t + 4], x1i = zi[t + 4], x2r = zr[t + 8], x2i = zi[t + 8],
+            x3r = zr[t + 12], x3i = zi[t + 12];
+      bfly4(x0r, x0i, x1r, x1i, x2r, x2i, x3r, x3i);
+      ar[4 * t + 0] = x0r, ai[4 * t + 0] = x0i;
+      ar[4 * t + 1] = x1r, ai[4 * t + 1] = x1i;
+      ar[4 * t + 2] = x2r, ai[4 * t + 2] = x2i;
+      ar[4 * t + 3] = x3r, ai[4 * t + 3] = x3i;
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      float x0r = ar[m], x0i = ai[m], x1r = ar[m + 4], x1i = ai[m + 4], x2r = ar[m + 8], x2i = ai[m + 8],
+            x3r = ar[m + 12], x3i = ai[m + 12];
+      if (m > 0) {
+        rot(x1r, x1i, T.pass1[m - 1][0], T.pass1[m - 1][1]);
+        rot(x2r, x2i, T.pass1[m - 1][2], T.pass1[m - 1][3]);
+        rot(x3r, x3i, T.pass1[m - 1][4], T.pass1[m - 1][5]);
+      }
+      bfly4(x0r, x0i, x1r, x1i, x2r, x2i, x3r, x3i);
+      zr[m] = x0r, zi[m] = x0i;
+      zr[m + 4] = x1r, zi[m + 4] = x1i;
+      zr[m + 8] = x2r, zi[m + 8] = x2i;
+      zr[m + 12] = x3r, zi[m + 12] = x3i;
+    }
+  }
+  {
+    const int g = ((lane >> 3) & 3) | (((lane >> 1) & 3) << 2) | ((lane & 1) << 4);
+    float2* dst = smc + 17 * g;  // pad16(16 g + e) = 17 g + e
+#pragma unroll
+    for (int e = 0; e < 16; ++e) dst[e] = make_float2(zr[e], zi[e]);
+  }
+  __syncwarp();
+  const int H = lane >> 4, m16 = lane & 15;
+  {
+    const float2* src = smc + 272 * H + m16;  // pad16(256 H + m16 + 16 v) = 272 H + m16 + 17 v
+#pragma unroll
+    for (int v = 0; v < 16; ++v) {
+      const float2 t = src[17 * v];
+      zr[v] = t.x, zi[v] = t.y;
+    }
+  }
+  __syncwarp();
+  // pass 2: twiddle index j = 16 m16 (one set per lane); lanes with m16 == 0 must not multiply
+  {
+    const float4 e0 = __ldg(T.eff8 + 2 * 16 * m16), e1 = __ldg(T.eff8 + 2 * 16 * m16 + 1);
+    const bool on = (m16 != 0);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      rot_sel(zr[4 * t + 1], zi[4 * t + 1], e0.x, e0.y, on);
+      rot_sel(zr[4 * t + 2], zi[4 * t + 2], e0.z, e0.w, on);
+      rot_sel(zr[4 * t + 3], zi[4 * t + 3], e1.x, e1.y, on);
+      bfly4(zr[4 * t], zi[4 * t], zr[4 * t + 1], zi[4 * t + 1], zr[4 * t + 2], zi[4 * t + 2], zr[4 * t + 3],
+            zi[4 * t + 3]);
+    }
+  }
+  // pass 3: j = 4 (m16 + 16 r); only (m16, r) = (0, 0) skips the multiplication
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int j = 4 * (m16 + 16 * r);
+    const float4 e0 = __ldg(T.eff8 + 2 * j), e1 = __ldg(T.eff8 + 2 * j + 1);
+    if (r == 0) {
+      const bool on = (m16 != 0);
+      rot_sel(zr[r + 4], zi[r + 4], e0.x, e0.y, on);
+      rot_sel(zr[r + 8], zi[r + 8], e0.z, e0.w, on);
+      rot_sel(zr[r + 12], zi[r + 12], e1.x, e1.y, on);
+    } else {
+      rot(zr[r + 4], zi[r + 4], e0.x, e0.y);
+      rot(zr[r + 8], zi[r + 8], e0.z, e0.w);
+      rot(zr[r + 12], zi[r + 12], e1.x, e1.y);
+    }
+    bfly4(zr[r], zi[r], zr[r + 4], zi[r + 4], zr[r + 8], zi[r + 8], zr[r + 12], zi[r + 12]);
+  }
+  // final radix-2 pass between lanes l and l^16: the upper lane rotates its own value (x1' = x1 * W) and
+  // sends it, the lower lane sends x0; then y = x0 + x1' (lower) or x0 - x1' (upper).  Post-twiddle follows.
+  const unsigned sgn = H ? 0x80000000u : 0u;
+#pragma unroll
+  for (int pr = 0; pr < 8; ++pr) {
+    const float4 w = __ldg(T.rad2p4 + pr * 32 + lane);
+    const float4 cs = __ldg(T.post4 + pr * 32 + lane);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int v = 2 * pr + h;
+      const float wc = h ? w.z : w.x, ws = h ? w.w : w.y;
+      float tr = zr[v], ti = zi[v];
+      rot(tr, ti, wc, ws);
+      tr = H ? tr : zr[v];
+      ti = H ? ti : zi[v];
+      const float rr = __shfl_xor_sync(kFull, tr, 16);
+      const float ri = __shfl_xor_sync(kFull, ti, 16);
+      const float yr = fadd(rr, __uint_as_float(__float_as_uint(tr) ^ sgn));
+      const float yi = fadd(ri, __uint_as_float(__float_as_uint(ti) ^ sgn));
+      const float c = h ? cs.z : cs.x, s = h ? cs.w : cs.y;
+      const float xa = -fsub(fmul(yr, c), fmul(yi, s));
+      const float xb = -fadd(fmul(yi, c), fmul(yr, s));
+      const int k = 256 * H + m16 + 16 * v;
+      // lower lanes store the even sample first, upper lanes the odd one: 32 distinct banks per store
+      sm[H ? (1023 - 2 * k) : (2 * k)] = H ? xb : xa;
+      sm[H ? (2 * k) : (1023 - 2 * k)] = H ? xa : xb;
+    }
+  }
+  __syncwarp();
+
+  // windowing + overlap-add + overlap save (gather form, see window_long): all loads first
+  const bool start_like = (sd.seq == 0 || sd.seq == 1);
+  float4 ovv[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int i4 = 4 * (lane + 32 * it);
+    if (start_like || i4 < 576) ovv[it] = ldcs4(ov + i4);
+  }
+  if (start_like) {
+    const float* wl = T.win_long[sd.shape_prev];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int i4 = 4 * (lane + 32 * it);
+      const float4 s = (it < 4) ? ld4(sm + 512 + i4) : neg4(rev4(ld4(sm + 1532 - i4)));
+      const float4 res = win4(s, ldg4(wl + i4), ovv[it], rev4(ldg4(wl + 1020 - i4)));
+      stcs4(o + i4, res);
+      const float4 n = (it >= 4) ? ld4(sm + i4 - 512) : rev4(ld4(sm + 508 - i4));
+      st4(ov + i4, neg4(n));
+    }
+  } else {
+    const float* wsh = T.win_short[sd.shape_prev];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int i4 = 4 * (lane + 32 * it);
+      const float4 s = (it < 4) ? ld4(sm + 512 + i4) : neg4(rev4(ld4(sm + 1532 - i4)));
+      float4 res;
+      if (i4 < 448) {
+        res = ovv[it];
+      } else if (i4 < 576) {
+        res = win4(s, ldg4(wsh + i4 - 448), ovv[it], rev4(ldg4(wsh + 572 - i4)));
+      } else {
+        res = s;
+      }
+      stcs4(o + i4, res);
+      const float4 n = (it >= 4) ? ld4(sm + i4 - 512) : rev4(ld4(sm + 508 - i4));
+      st4(ov + i4, neg4(n));
+    }
+  }
+}
+
+template <int WARPS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(WARPS * 32, MIN_BLOCKS)
+    fd_synth_kernel(const float* __restrict__ coef, const uint32_t* __restrict__ side, float* __restrict__ overlap,
+                    float* __restrict__ out, int n_units, const __grid_constant__ DeviceTables T) {
+  __shared__ __align__(16) float smem[WARPS][kSmemFloats];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.x * WARPS + warp;
+  if (unit >= n_units) return;
+  float* sm = smem[warp];
+  const float* X = coef + size_t(unit) * 1024;
+  float* ov = overlap + size_t(unit) * 1024;
+  float* o = out + size_t(unit) * 1024;
+  // Everything the unit needs from HBM is requested before the first dependent instruction: the side word,
+  // the 16 coefficient pairs of this lane (long-block order) and, as an L2 prefetch, the overlap state.
+  const uint32_t sw = __ldg(side + unit);
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(ov + 32 * lane));
+  float2 eo[16];
+  {
+    const float2* X2 = reinterpret_cast<const float2*>(X);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) eo[u] = __ldcs(X2 + lane + 32 * u);
+  }
+  const Side sd = unpack_side(sw);
+  if (sd.seq != 2 && sd.tkt == 0) {
+    fd_unit_long_fast(eo, ov, o, sd, sm, T, lane);
+  } else {
+    fd_unit_generic(X, ov, o, sd, sm, T, lane);
+  }
+}
+
 }  // namespace
+
+template <int WARPS, int MIN_BLOCKS>
+static void launch_variant(const float* d_coef, const uint32_t* d_side, float* d_overlap, float* d_out, int n_units,
+                           const DeviceTables& T, cudaStream_t stream) {
+  const int grid = (n_units + WARPS - 1) / WARPS;
+  fd_synth_kernel<WARPS, MIN_BLOCKS><<<grid, WARPS * 32, 0, stream>>>(d_coef, d_side, d_overlap, d_out, n_units, T);
+}
 
 mpeghb200_status fd_synth_launch(mpeghb200_ctx* ctx, const float* d_coef, const uint32_t* d_side, float* d_overlap,
                                  float* d_out, int n_units, cudaStream_t stream) {
   if (n_units == 0) return MPEGHB200_OK;
-  constexpr int WARPS = 4;
-  const int grid = (n_units + WARPS - 1) / WARPS;
-  fd_synth_kernel<WARPS><<<grid, WARPS * 32, 0, stream>>>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables);
+  // Launch shape (warps per CTA, CTAs per SM the register budget is sized for). Variant 0 is the default;
+  // the others exist for tuning sweeps (MPEGHB200_FD_VARIANT, read once at context creation).
+  switch (ctx->fd_variant) {
+    default:
+    case 0: launch_variant<4, 8>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables, stream); break;
+    case 1: launch_variant<4, 6>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables, stream); break;
+    case 2: launch_variant<2, 16>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables, stream); break;
+    case 3: launch_variant<8, 4>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables, stream); break;
+    case 4: launch_variant<1, 24>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables, stream); break;
+    case 5: launch_variant<2, 12>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables, stream); break;
+  }
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   return MPEGHB200_OK;
