@@ -41,14 +41,17 @@ UNIT = "channel-samples/s"
 
 
 def workload_name():
-    return "configs[1]: IMDCT+windowing/OLA, 1024-sample frames, 256 streams x 24 ch, synthetic spectra"
+    return ("configs[1]: IMDCT+windowing/OLA, 1024-sample frames, 256 streams x 24 ch, synthetic spectra, "
+            "ONLY_LONG with random sine/KBD shapes")
 
 
-def make_side(rng, n_units):
-    """Mostly ONLY_LONG sine/KBD with ~8 % start/short/stop frames, state-consistent per channel."""
-    import fd_cases
+def make_side(rng, n_units, mixed=False):
+    """SURVEY.md section 8(d) config 2.  Baseline: ONLY_LONG with random sine/KBD shapes.  mixed=True: the
+    mixed-sequence variant, ~8 % LONG_START / EIGHT_SHORT / LONG_STOP frames."""
     seq = np.zeros(n_units, np.int32)
     r = rng.random(n_units)
+    if not mixed:
+        r[:] = 0.0
     seq[r > 0.92] = 1
     seq[r > 0.95] = 2
     seq[r > 0.98] = 3
@@ -218,41 +221,47 @@ def main():
     coef = [torch.randn(UNITS, FRAME, device="cuda", generator=gen) * 500.0 for _ in range(G)]
     ovl = [torch.zeros(UNITS, FRAME, device="cuda") for _ in range(G)]
     outb = [torch.empty(UNITS, FRAME, device="cuda") for _ in range(G)]
-    side = [torch.from_numpy(fd_cases.pack_side(make_side(rng, UNITS)).astype(np.int32)).cuda() for _ in range(G)]
-
-    def step(i):
-        g = i % G
-        lib.fd_synth_dev(coef[g].data_ptr(), side[g].data_ptr(), ovl[g].data_ptr(), outb[g].data_ptr(), UNITS,
-                         stream.cuda_stream)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        step(i)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches0 = lib.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(stream)
-    for i in range(args.steps):
-        step(args.warmup + i)
-    ev1.record(stream)
-    barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
-    launches = lib.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    ms_per_step = elapsed_ms / args.steps
+    def timed(mixed, with_clocks):
+        """W warm-up + K timed steps of one workload variant; returns (ms_per_step, launches, clocks)."""
+        side = [torch.from_numpy(fd_cases.pack_side(make_side(rng, UNITS, mixed)).astype(np.int32)).cuda()
+                for _ in range(G)]
+
+        def step(i):
+            g = i % G
+            lib.fd_synth_dev(coef[g].data_ptr(), side[g].data_ptr(), ovl[g].data_ptr(), outb[g].data_ptr(), UNITS,
+                             stream.cuda_stream)
+
+        for i in range(args.warmup):
+            step(i)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0 and with_clocks:
+            sampler.start()
+        launches0 = lib.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record(stream)
+        for i in range(args.steps):
+            step(args.warmup + i)
+        ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        n_launch = lib.launch_count() - launches0
+        clk = sampler.stop() if (rank == 0 and with_clocks) else None
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / args.steps, n_launch, clk
+
+    ms_per_step, launches, clocks = timed(False, True)
     value = world * UNITS * FRAME / (ms_per_step * 1e-3)
+    ms_mixed, _, _ = timed(True, False)
 
     # ---- e2e: host buffers through the session API, copies inside the timed region --------------
     sess = lib.fd_open(STREAMS, CHANNELS)
@@ -302,6 +311,10 @@ def main():
                        f"{G * 3 * UNITS * FRAME * 4 / 1e6:.0f} MB working set, state carried per group",
                        "sharding": "streams by rank, no collective"},
             "realtime_factor": value / CHANNELS / 48000.0,
+            "mixed_sequence_variant": {
+                "note": "same shape with ~8 % LONG_START/EIGHT_SHORT/LONG_STOP frames (SURVEY.md 8d variant)",
+                "ms_per_step": ms_mixed, "value": world * UNITS * FRAME / (ms_mixed * 1e-3),
+                "roofline_frac": BYTES_PER_UNIT * UNITS / (ms_mixed * 1e-3) / 1e9 / peak},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "fd_synth_kernel", "algorithmic_bytes_per_launch": BYTES_PER_UNIT * UNITS},

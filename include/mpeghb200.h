@@ -65,6 +65,11 @@ mpeghb200_status mpeghb200_dev_memset(mpeghb200_ctx *ctx, void *dptr, int value,
 mpeghb200_status mpeghb200_h2d(mpeghb200_ctx *ctx, void *dptr, const void *hptr, size_t bytes);
 mpeghb200_status mpeghb200_d2h(mpeghb200_ctx *ctx, void *hptr, const void *dptr, size_t bytes);
 mpeghb200_status mpeghb200_sync(mpeghb200_ctx *ctx);
+/* Page-locked host memory.  The *_execute entry points DMA straight from/to such buffers (and from any other
+ * page-locked memory); ordinary malloc'ed buffers work too but are staged through an internal pinned copy.
+ * A decoder handle's coef / OUTPUT mem tables should live here. */
+mpeghb200_status mpeghb200_host_alloc(mpeghb200_ctx *ctx, size_t bytes, void **hptr);
+mpeghb200_status mpeghb200_host_free(mpeghb200_ctx *ctx, void *hptr);
 
 /* ---- FD synthesis: IMDCT + windowing + overlap-add ------------------------------------------
  * Replaces ia_core_coder_fd_frm_dec (decoder/ia_core_coder_imdct.c:832) for FD-coded channels with FD

@@ -238,6 +238,19 @@ mpeghb200_status mpeghb200_d2h(mpeghb200_ctx* ctx, void* hptr, const void* dptr,
   MB_CUDA(ctx, cudaMemcpy(hptr, dptr, bytes, cudaMemcpyDeviceToHost));
   return MPEGHB200_OK;
 }
+mpeghb200_status mpeghb200_host_alloc(mpeghb200_ctx* ctx, size_t bytes, void** hptr) {
+  if (!ctx || !hptr) return MPEGHB200_ERR_BAD_ARG;
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  MB_CUDA(ctx, cudaHostAlloc(hptr, bytes, cudaHostAllocDefault));
+  return MPEGHB200_OK;
+}
+
+mpeghb200_status mpeghb200_host_free(mpeghb200_ctx* ctx, void* hptr) {
+  if (!ctx) return MPEGHB200_ERR_BAD_ARG;
+  MB_CUDA(ctx, cudaFreeHost(hptr));
+  return MPEGHB200_OK;
+}
+
 mpeghb200_status mpeghb200_sync(mpeghb200_ctx* ctx) {
   if (!ctx) return MPEGHB200_ERR_BAD_ARG;
   MB_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -26,7 +26,6 @@ namespace mpeghb200 {
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kSmemFloats = 1088;  // 544 padded complex values, reused as 1024 real samples
 
 __device__ __forceinline__ int pad16(int i) { return i + (i >> 4); }
 
@@ -339,7 +338,6 @@ __device__ __noinline__ void fd_unit_generic(const float* __restrict__ X, float*
                                              const Side sd, float* sm, const DeviceTables& T, int lane) {
   float2* smc = reinterpret_cast<float2*>(sm);
   const bool is_short = (sd.seq == 2);
-  const int N = is_short ? 128 : 1024;            // block length
   const float norm = is_short ? 0.0078125f : 0.0009765625f;  // 2 / (2N)
 
   float zr[16], zi[16];
@@ -474,11 +472,26 @@ __device__ __noinline__ void fd_unit_generic(const float* __restrict__ X, float*
 }
 
 
-// ---- fast path: long block, transform kernel type 0 ---------------------------------------------------
-// Same arithmetic as fd_unit_generic, scheduled for throughput: all 16 coefficient loads and an L2 prefetch
-// of the overlap are in flight before the first dependent instruction, tables come as lane-ordered float4,
-// pass-1 twiddles from the constant bank, no divergent branches, all overlap loads issued before the
-// first store of the windowing phase.
+// ---- fast path: long block, transform kernel type 0, B units per warp in three phases ------------------
+// The arithmetic is that of fd_unit_generic; what changes is the schedule.  Profiling the one-unit-per-warp
+// kernel showed the L1/shared data pipe (not HBM, not issue) closest to saturation, and 40 % of its global
+// wavefronts were twiddle/window table reads.  So a warp now owns B consecutive units and walks them phase
+// by phase with the phase's table entries held in REGISTERS (loaded once per warp instead of once per unit):
+//   A  coefficients -> scale, pre-twiddle, radix-4 passes 0-1 -> transposed into the unit's shared buffer
+//      (the next unit's 16 coalesced 8-byte loads are in flight while the current one computes; the
+//      overlap state of all B units is requested into L2 with one bulk prefetch each)
+//   B  passes 2-3, final radix-2 pass across lanes l / l^16, post-twiddle -> time-aliased samples in the
+//      same shared buffer
+//   C  windowing + overlap-add + overlap save in mirrored form: a lane handles the float4 at i and the one
+//      at 1020-i, which share window entries and shared-memory operands (half the table and LDS traffic)
+// With B = 3 and 14 resident warps per SM the 6144 units of the benchmark shape are one wave.
+// Units that are EIGHT_SHORT or use another transform kernel fall through to fd_unit_generic afterwards.
+constexpr int kBufFloats = 1092;  // 545 padded complex values (see tpos), reused as 1024 real samples
+
+// padded position of complex point 16 g + e: 16 lanes of a half-warp hit 16 distinct 8-byte bank pairs both
+// for the phase-A stores (fixed e, lane -> g) and the phase-B loads (fixed v, consecutive m16)
+__device__ __forceinline__ int tpos_g(int g) { return 17 * g + 2 * (g >> 4); }
+
 __device__ __forceinline__ void rot_sel(float& r, float& i, float c, float s, bool on) {
   float nr = r, ni = i;
   rot(nr, ni, c, s);
@@ -486,105 +499,133 @@ __device__ __forceinline__ void rot_sel(float& r, float& i, float c, float s, bo
   i = on ? ni : i;
 }
 
-__device__ __forceinline__ void fd_unit_long_fast(float2 (&eo)[16], float* __restrict__ ov, float* __restrict__ o,
-                                                  const Side sd, float* sm, const DeviceTables& T, int lane) {
-  float2* smc = reinterpret_cast<float2*>(sm);
+struct TabA {
+  float4 pre[8];  // (c, s) of tw512[lane + 32u] for u = 2p, 2p+1
+};
+struct TabB {
+  float4 e2a, e2b;      // pass 2: eff[16 m16]
+  float4 e3a[4], e3b[4];  // pass 3: eff[4 (m16 + 16 r)]
+  float4 rad[4];        // radix-2: rad2_512[m16 + 16 v], v = 2p, 2p+1 < 8 (v >= 8 reuses them rotated)
+  float4 post[8];       // post-twiddle tw512[256 H + m16 + 16 v]
+};
+struct TabC {
+  float4 f[4], r[4];  // window[i4 .. i4+3], window[1020-i4 .. 1023-i4], i4 = 4 (lane + 32 it)
+};
+
+__device__ __forceinline__ void load_tab_a(TabA& t, const DeviceTables& T, int lane) {
+#pragma unroll
+  for (int p = 0; p < 8; ++p) t.pre[p] = __ldg(T.pre4 + p * 32 + lane);
+}
+__device__ __forceinline__ void load_tab_b(TabB& t, const DeviceTables& T, int lane) {
+  const int m16 = lane & 15;
+  t.e2a = __ldg(T.eff8 + 2 * 16 * m16);
+  t.e2b = __ldg(T.eff8 + 2 * 16 * m16 + 1);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int j = 4 * (m16 + 16 * r);
+    t.e3a[r] = __ldg(T.eff8 + 2 * j);
+    t.e3b[r] = __ldg(T.eff8 + 2 * j + 1);
+  }
+#pragma unroll
+  for (int p = 0; p < 4; ++p) t.rad[p] = __ldg(T.rad2p4 + p * 32 + lane);
+#pragma unroll
+  for (int p = 0; p < 8; ++p) t.post[p] = __ldg(T.post4 + p * 32 + lane);
+}
+__device__ __forceinline__ void load_tab_c(TabC& t, const float* __restrict__ w, int lane) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int i4 = 4 * (lane + 32 * it);
+    t.f[it] = ldg4(w + i4);
+    t.r[it] = ldg4(w + 1020 - i4);
+  }
+}
+
+__device__ __forceinline__ void load_coef(float2 (&eo)[16], const float* __restrict__ X, int lane) {
+  const float2* X2 = reinterpret_cast<const float2*>(X);
+#pragma unroll
+  for (int u = 0; u < 16; ++u) eo[u] = __ldcs(X2 + lane + 32 * u);
+}
+
+// Phase A (decoder/ia_core_coder_imdct.c:171-182,371-376; decoder/impeghd_ifft.c:326-449)
+__device__ __forceinline__ void phase_a(const float2 (&ein)[16], const TabA& ta, float* sm, const DeviceTables& T,
+                                        int lane) {
   const float norm = 0.0009765625f;  // 2 / 2048
   float zr[16], zi[16];
 #pragma unroll
-  for (int u = 0; u < 16; ++u) {
-    eo[u].x = fmul(eo[u].x, norm);
-    eo[u].y = fmul(eo[u].y, norm);
-  }
+  for (int p = 0; p < 8; ++p) {
+    const float4 cs = ta.pre[p];
 #pragma unroll
-  for (int pr = 0; pr < 8; ++pr) {
-    const float4 cs = __ldg(T.pre4 + pr * 32 + lane);
-    {
-      const int u = 2 * pr;
-      const float a = eo[u].x, b = __shfl_xor_sync(kFull, eo[15 - u].y, 31);
-      zr[u] = fsub(-fmul(a, cs.x), fmul(b, cs.y));
-      zi[u] = fsub(fmul(b, cs.x), fmul(a, cs.y));
-    }
-    {
-      const int u = 2 * pr + 1;
-      const float a = eo[u].x, b = __shfl_xor_sync(kFull, eo[15 - u].y, 31);
-      zr[u] = fsub(-fmul(a, cs.z), fmul(b, cs.w));
-      zi[u] = fsub(fmul(b, cs.z), fmul(a, cs.w));
+    for (int h = 0; h < 2; ++h) {
+      const int u = 2 * p + h;
+      const float c = h ? cs.z : cs.x, s = h ? cs.w : cs.y;
+      const float a = fmul(ein[u].x, norm);
+      const float b = __shfl_xor_sync(kFull, fmul(ein[15 - u].y, norm), 31);
+      zr[u] = fsub(-fmul(a, c), fmul(b, s));
+      zi[u] = fsub(fmul(b, c), fmul(a, s));
     }
   }
-  // passes 0 and 1 in registers; pass-1 twiddles are warp-uniform kernel parameters (constant bank)
-  {
-    float ar[16], ai[16];
+  float ar[16], ai[16];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      float x0r = zr[t], x0i = zi[t], x1r = zr[t + 4], x1i = zi[t + 4], x2r = zr[t + 8], x2i = zi[t + 8],
-            x3r = zr[t + 12], x3i = zi[t + 12];
-      bfly4(x0r, x0i, x1r, x1i, x2r, x2i, x3r, x3i);
-      ar[4 * t + 0] = x0r, ai[4 * t + 0] = x0i;
-      ar[4 * t + 1] = x1r, ai[4 * t + 1] = x1i;
-      ar[4 * t + 2] = x2r, ai[4 * t + 2] = x2i;
-      ar[4 * t + 3] = x3r, ai[4 * t + 3] = x3i;
-    }
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      float x0r = ar[m], x0i = ai[m], x1r = ar[m + 4], x1i = ai[m + 4], x2r = ar[m + 8], x2i = ai[m + 8],
-            x3r = ar[m + 12], x3i = ai[m + 12];
-      if (m > 0) {
-        rot(x1r, x1i, T.pass1[m - 1][0], T.pass1[m - 1][1]);
-        rot(x2r, x2i, T.pass1[m - 1][2], T.pass1[m - 1][3]);
-        rot(x3r, x3i, T.pass1[m - 1][4], T.pass1[m - 1][5]);
-      }
-      bfly4(x0r, x0i, x1r, x1i, x2r, x2i, x3r, x3i);
-      zr[m] = x0r, zi[m] = x0i;
-      zr[m + 4] = x1r, zi[m + 4] = x1i;
-      zr[m + 8] = x2r, zi[m + 8] = x2i;
-      zr[m + 12] = x3r, zi[m + 12] = x3i;
-    }
+  for (int t = 0; t < 4; ++t) {
+    float x0r = zr[t], x0i = zi[t], x1r = zr[t + 4], x1i = zi[t + 4], x2r = zr[t + 8], x2i = zi[t + 8],
+          x3r = zr[t + 12], x3i = zi[t + 12];
+    bfly4(x0r, x0i, x1r, x1i, x2r, x2i, x3r, x3i);
+    ar[4 * t + 0] = x0r, ai[4 * t + 0] = x0i;
+    ar[4 * t + 1] = x1r, ai[4 * t + 1] = x1i;
+    ar[4 * t + 2] = x2r, ai[4 * t + 2] = x2i;
+    ar[4 * t + 3] = x3r, ai[4 * t + 3] = x3i;
   }
-  {
-    const int g = ((lane >> 3) & 3) | (((lane >> 1) & 3) << 2) | ((lane & 1) << 4);
-    float2* dst = smc + 17 * g;  // pad16(16 g + e) = 17 g + e
+  const int g = ((lane >> 3) & 3) | (((lane >> 1) & 3) << 2) | ((lane & 1) << 4);
+  float2* dst = reinterpret_cast<float2*>(sm) + tpos_g(g);
 #pragma unroll
-    for (int e = 0; e < 16; ++e) dst[e] = make_float2(zr[e], zi[e]);
+  for (int m = 0; m < 4; ++m) {
+    float x0r = ar[m], x0i = ai[m], x1r = ar[m + 4], x1i = ai[m + 4], x2r = ar[m + 8], x2i = ai[m + 8],
+          x3r = ar[m + 12], x3i = ai[m + 12];
+    if (m > 0) {  // pass-1 twiddles are warp-uniform: kernel-parameter constant bank
+      rot(x1r, x1i, T.pass1[m - 1][0], T.pass1[m - 1][1]);
+      rot(x2r, x2i, T.pass1[m - 1][2], T.pass1[m - 1][3]);
+      rot(x3r, x3i, T.pass1[m - 1][4], T.pass1[m - 1][5]);
+    }
+    bfly4(x0r, x0i, x1r, x1i, x2r, x2i, x3r, x3i);
+    dst[m] = make_float2(x0r, x0i);
+    dst[m + 4] = make_float2(x1r, x1i);
+    dst[m + 8] = make_float2(x2r, x2i);
+    dst[m + 12] = make_float2(x3r, x3i);
   }
-  __syncwarp();
+}
+
+// Phase B (decoder/impeghd_ifft.c:450-837; decoder/ia_core_coder_imdct.c:259-273)
+__device__ __forceinline__ void phase_b(const TabB& tb, float* sm, int lane) {
   const int H = lane >> 4, m16 = lane & 15;
+  float zr[16], zi[16];
   {
-    const float2* src = smc + 272 * H + m16;  // pad16(256 H + m16 + 16 v) = 272 H + m16 + 17 v
+    const float2* src = reinterpret_cast<const float2*>(sm) + 274 * H + m16;  // tpos_g(16 H + v) + m16
 #pragma unroll
     for (int v = 0; v < 16; ++v) {
       const float2 t = src[17 * v];
       zr[v] = t.x, zi[v] = t.y;
     }
   }
-  __syncwarp();
-  // pass 2: twiddle index j = 16 m16 (one set per lane); lanes with m16 == 0 must not multiply
-  {
-    const float4 e0 = __ldg(T.eff8 + 2 * 16 * m16), e1 = __ldg(T.eff8 + 2 * 16 * m16 + 1);
-    const bool on = (m16 != 0);
+  __syncwarp();  // everyone has its points: the buffer may now receive the post-twiddled samples
+  const bool on = (m16 != 0);
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      rot_sel(zr[4 * t + 1], zi[4 * t + 1], e0.x, e0.y, on);
-      rot_sel(zr[4 * t + 2], zi[4 * t + 2], e0.z, e0.w, on);
-      rot_sel(zr[4 * t + 3], zi[4 * t + 3], e1.x, e1.y, on);
-      bfly4(zr[4 * t], zi[4 * t], zr[4 * t + 1], zi[4 * t + 1], zr[4 * t + 2], zi[4 * t + 2], zr[4 * t + 3],
-            zi[4 * t + 3]);
-    }
+  for (int t = 0; t < 4; ++t) {
+    rot_sel(zr[4 * t + 1], zi[4 * t + 1], tb.e2a.x, tb.e2a.y, on);
+    rot_sel(zr[4 * t + 2], zi[4 * t + 2], tb.e2a.z, tb.e2a.w, on);
+    rot_sel(zr[4 * t + 3], zi[4 * t + 3], tb.e2b.x, tb.e2b.y, on);
+    bfly4(zr[4 * t], zi[4 * t], zr[4 * t + 1], zi[4 * t + 1], zr[4 * t + 2], zi[4 * t + 2], zr[4 * t + 3],
+          zi[4 * t + 3]);
   }
-  // pass 3: j = 4 (m16 + 16 r); only (m16, r) = (0, 0) skips the multiplication
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
-    const int j = 4 * (m16 + 16 * r);
-    const float4 e0 = __ldg(T.eff8 + 2 * j), e1 = __ldg(T.eff8 + 2 * j + 1);
     if (r == 0) {
-      const bool on = (m16 != 0);
-      rot_sel(zr[r + 4], zi[r + 4], e0.x, e0.y, on);
-      rot_sel(zr[r + 8], zi[r + 8], e0.z, e0.w, on);
-      rot_sel(zr[r + 12], zi[r + 12], e1.x, e1.y, on);
+      rot_sel(zr[r + 4], zi[r + 4], tb.e3a[r].x, tb.e3a[r].y, on);
+      rot_sel(zr[r + 8], zi[r + 8], tb.e3a[r].z, tb.e3a[r].w, on);
+      rot_sel(zr[r + 12], zi[r + 12], tb.e3b[r].x, tb.e3b[r].y, on);
     } else {
-      rot(zr[r + 4], zi[r + 4], e0.x, e0.y);
-      rot(zr[r + 8], zi[r + 8], e0.z, e0.w);
-      rot(zr[r + 12], zi[r + 12], e1.x, e1.y);
+      rot(zr[r + 4], zi[r + 4], tb.e3a[r].x, tb.e3a[r].y);
+      rot(zr[r + 8], zi[r + 8], tb.e3a[r].z, tb.e3a[r].w);
+      rot(zr[r + 12], zi[r + 12], tb.e3b[r].x, tb.e3b[r].y);
     }
     bfly4(zr[r], zi[r], zr[r + 4], zi[r + 4], zr[r + 8], zi[r + 8], zr[r + 12], zi[r + 12]);
   }
@@ -592,127 +633,214 @@ __device__ __forceinline__ void fd_unit_long_fast(float2 (&eo)[16], float* __res
   // sends it, the lower lane sends x0; then y = x0 + x1' (lower) or x0 - x1' (upper).  Post-twiddle follows.
   const unsigned sgn = H ? 0x80000000u : 0u;
 #pragma unroll
-  for (int pr = 0; pr < 8; ++pr) {
-    const float4 w = __ldg(T.rad2p4 + pr * 32 + lane);
-    const float4 cs = __ldg(T.post4 + pr * 32 + lane);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int v = 2 * pr + h;
-      const float wc = h ? w.z : w.x, ws = h ? w.w : w.y;
-      float tr = zr[v], ti = zi[v];
-      rot(tr, ti, wc, ws);
-      tr = H ? tr : zr[v];
-      ti = H ? ti : zi[v];
-      const float rr = __shfl_xor_sync(kFull, tr, 16);
-      const float ri = __shfl_xor_sync(kFull, ti, 16);
-      const float yr = fadd(rr, __uint_as_float(__float_as_uint(tr) ^ sgn));
-      const float yi = fadd(ri, __uint_as_float(__float_as_uint(ti) ^ sgn));
-      const float c = h ? cs.z : cs.x, s = h ? cs.w : cs.y;
-      const float xa = -fsub(fmul(yr, c), fmul(yi, s));
-      const float xb = -fadd(fmul(yi, c), fmul(yr, s));
-      const int k = 256 * H + m16 + 16 * v;
-      // lower lanes store the even sample first, upper lanes the odd one: 32 distinct banks per store
-      sm[H ? (1023 - 2 * k) : (2 * k)] = H ? xb : xa;
-      sm[H ? (2 * k) : (1023 - 2 * k)] = H ? xa : xb;
-    }
-  }
-  __syncwarp();
-
-  // windowing + overlap-add + overlap save (gather form, see window_long): all loads first
-  const bool start_like = (sd.seq == 0 || sd.seq == 1);
-  float4 ovv[8];
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int i4 = 4 * (lane + 32 * it);
-    if (start_like || i4 < 576) ovv[it] = ldcs4(ov + i4);
-  }
-  if (start_like) {
-    const float* wl = T.win_long[sd.shape_prev];
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int i4 = 4 * (lane + 32 * it);
-      const float4 s = (it < 4) ? ld4(sm + 512 + i4) : neg4(rev4(ld4(sm + 1532 - i4)));
-      const float4 res = win4(s, ldg4(wl + i4), ovv[it], rev4(ldg4(wl + 1020 - i4)));
-      stcs4(o + i4, res);
-      const float4 n = (it >= 4) ? ld4(sm + i4 - 512) : rev4(ld4(sm + 508 - i4));
-      st4(ov + i4, neg4(n));
-    }
-  } else {
-    const float* wsh = T.win_short[sd.shape_prev];
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int i4 = 4 * (lane + 32 * it);
-      const float4 s = (it < 4) ? ld4(sm + 512 + i4) : neg4(rev4(ld4(sm + 1532 - i4)));
-      float4 res;
-      if (i4 < 448) {
-        res = ovv[it];
-      } else if (i4 < 576) {
-        res = win4(s, ldg4(wsh + i4 - 448), ovv[it], rev4(ldg4(wsh + 572 - i4)));
-      } else {
-        res = s;
-      }
-      stcs4(o + i4, res);
-      const float4 n = (it >= 4) ? ld4(sm + i4 - 512) : rev4(ld4(sm + 508 - i4));
-      st4(ov + i4, neg4(n));
-    }
+  for (int v = 0; v < 16; ++v) {
+    // rad2_512[p], p = m16 + 16 v: for p >= 128 the entry is (ws, -wc) of p - 128 (ctx.cu radix2_twiddles_512)
+    const float4 w = tb.rad[(v & 7) >> 1];
+    const float w0 = (v & 1) ? w.z : w.x, w1 = (v & 1) ? w.w : w.y;
+    const float wc = (v < 8) ? w0 : w1, ws = (v < 8) ? w1 : -w0;
+    float tr = zr[v], ti = zi[v];
+    rot(tr, ti, wc, ws);
+    tr = H ? tr : zr[v];
+    ti = H ? ti : zi[v];
+    const float rr = __shfl_xor_sync(kFull, tr, 16);
+    const float ri = __shfl_xor_sync(kFull, ti, 16);
+    const float yr = fadd(rr, __uint_as_float(__float_as_uint(tr) ^ sgn));
+    const float yi = fadd(ri, __uint_as_float(__float_as_uint(ti) ^ sgn));
+    const float4 cs = tb.post[v >> 1];
+    const float c = (v & 1) ? cs.z : cs.x, s = (v & 1) ? cs.w : cs.y;
+    const float xa = -fsub(fmul(yr, c), fmul(yi, s));
+    const float xb = -fadd(fmul(yi, c), fmul(yr, s));
+    const int k = 256 * H + m16 + 16 * v;
+    // lower lanes store the even sample first, upper lanes the odd one: 32 distinct banks per store
+    sm[H ? (1023 - 2 * k) : (2 * k)] = H ? xb : xa;
+    sm[H ? (2 * k) : (1023 - 2 * k)] = H ? xa : xb;
   }
 }
 
-template <int WARPS, int MIN_BLOCKS>
+__device__ __forceinline__ void load_overlap(float4 (&ovv)[8], const float* __restrict__ ov, int lane) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int i4 = 4 * (lane + 32 * it);
+    ovv[it] = ldcs4(ov + i4);
+    ovv[4 + it] = ldcs4(ov + 1020 - i4);
+  }
+}
+
+// Phase C (decoder/ia_core_coder_basic_ops.c:124-153,230-295; decoder/ia_core_coder_imdct.c:807-813).
+// Position block i4 < 512 and its mirror j4 = 1020 - i4 >= 512:
+//   s(i4 + e) = xs[512 + i4 + e]            s(j4 + e) = -xs[515 + i4 - e]      (same float4 P, reversed)
+//   new_ov(i4 + e) = -xs[511 - i4 - e]      new_ov(j4 + e) = -xs[508 - i4 + e]  (same float4 Q)
+__device__ __forceinline__ void phase_c(const float4 (&ovv)[8], const TabC& tc, const float* sm,
+                                        float* __restrict__ ov, float* __restrict__ o, int lane) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int i4 = 4 * (lane + 32 * it), j4 = 1020 - i4;
+    const float4 P = ld4(sm + 512 + i4), Q = ld4(sm + 508 - i4);
+    const float4 r_lo = win4(P, tc.f[it], ovv[it], rev4(tc.r[it]));
+    const float4 r_hi = win4(neg4(rev4(P)), tc.r[it], ovv[4 + it], rev4(tc.f[it]));
+    stcs4(o + i4, r_lo);
+    stcs4(o + j4, r_hi);
+    st4(ov + i4, neg4(rev4(Q)));
+    st4(ov + j4, neg4(Q));
+  }
+}
+
+// LONG_STOP / STOP_START (decoder/ia_core_coder_basic_ops.c:230-295): flat-zero left part, 128-sample window
+// slope around the centre.  Rare, kept out of line so its table loads are never speculated into phase_c.
+__device__ __noinline__ void phase_c_stop(const float* sm, float* __restrict__ ov, float* __restrict__ o,
+                                          const float* __restrict__ wsh, int lane) {
+#pragma unroll 1
+  for (int it = 0; it < 4; ++it) {
+    const int i4 = 4 * (lane + 32 * it), j4 = 1020 - i4;
+    const float4 P = ld4(sm + 512 + i4), Q = ld4(sm + 508 - i4);
+    const float4 s_hi = neg4(rev4(P));
+    float4 r_lo, r_hi;
+    if (i4 < 448) {
+      r_lo = ldcs4(ov + i4);
+      r_hi = s_hi;  // j4 >= 576
+    } else {
+      // 448 <= i4 < 512 and 512 <= j4 < 576: both inside the slope
+      r_lo = win4(P, ldg4(wsh + i4 - 448), ldcs4(ov + i4), rev4(ldg4(wsh + 572 - i4)));
+      r_hi = win4(s_hi, ldg4(wsh + j4 - 448), ldcs4(ov + j4), rev4(ldg4(wsh + 572 - j4)));
+    }
+    stcs4(o + i4, r_lo);
+    stcs4(o + j4, r_hi);
+    st4(ov + i4, neg4(rev4(Q)));
+    st4(ov + j4, neg4(Q));
+  }
+}
+
+template <int B, int WARPS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(WARPS * 32, MIN_BLOCKS)
     fd_synth_kernel(const float* __restrict__ coef, const uint32_t* __restrict__ side, float* __restrict__ overlap,
                     float* __restrict__ out, int n_units, const __grid_constant__ DeviceTables T) {
-  __shared__ __align__(16) float smem[WARPS][kSmemFloats];
+  __shared__ __align__(16) float smem[WARPS][B][kBufFloats];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int unit = blockIdx.x * WARPS + warp;
-  if (unit >= n_units) return;
-  float* sm = smem[warp];
-  const float* X = coef + size_t(unit) * 1024;
-  float* ov = overlap + size_t(unit) * 1024;
-  float* o = out + size_t(unit) * 1024;
-  // Everything the unit needs from HBM is requested before the first dependent instruction: the side word,
-  // the 16 coefficient pairs of this lane (long-block order) and, as an L2 prefetch, the overlap state.
-  const uint32_t sw = __ldg(side + unit);
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(ov + 32 * lane));
-  float2 eo[16];
-  {
-    const float2* X2 = reinterpret_cast<const float2*>(X);
+  const int unit0 = (blockIdx.x * WARPS + warp) * B;
+  if (unit0 >= n_units) return;
+  const int nb = min(B, n_units - unit0);
+
+  // side words; request the overlap state of every unit of the batch into L2 (consumed in phase C)
+  Side sd[B];
+  bool fast[B];
+  bool any_fast = false, any_slow = false;
 #pragma unroll
-    for (int u = 0; u < 16; ++u) eo[u] = __ldcs(X2 + lane + 32 * u);
+  for (int b = 0; b < B; ++b) {
+    const bool valid = b < nb;
+    sd[b] = unpack_side(valid ? __ldg(side + unit0 + b) : 0u);
+    fast[b] = valid && sd[b].seq != 2 && sd[b].tkt == 0;
+    any_fast |= fast[b];
+    any_slow |= valid && !fast[b];
   }
-  const Side sd = unpack_side(sw);
-  if (sd.seq != 2 && sd.tkt == 0) {
-    fd_unit_long_fast(eo, ov, o, sd, sm, T, lane);
-  } else {
-    fd_unit_generic(X, ov, o, sd, sm, T, lane);
+  // Everything this warp will read from HBM is requested up front: unit 0's coefficients as ordinary loads
+  // (phase A below), the other units' coefficients and the whole batch's overlap state as bulk L2
+  // prefetches (units of a batch are contiguous), so later loads are L2 hits and HBM streams while we compute.
+  float2 eo[2][16];
+  load_coef(eo[0], coef + size_t(unit0) * 1024, lane);
+  if (lane == 0 && nb > 1) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(coef + size_t(unit0 + 1) * 1024),
+                 "r"((nb - 1) * 4096)
+                 : "memory");
+  }
+  if (lane == 1) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(overlap + size_t(unit0) * 1024), "r"(nb * 4096)
+                 : "memory");
+  }
+
+  if (any_fast) {
+    // ---- phase A ----
+    {
+      TabA ta;
+      load_tab_a(ta, T, lane);
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        if (b + 1 < B && b + 1 < nb) load_coef(eo[(b + 1) & 1], coef + size_t(unit0 + b + 1) * 1024, lane);
+        if (fast[b]) phase_a(eo[b & 1], ta, smem[warp][b], T, lane);
+      }
+    }
+    __syncwarp();
+    // ---- phase B ----
+    {
+      TabB tb;
+      load_tab_b(tb, T, lane);
+#pragma unroll
+      for (int b = 0; b < B; ++b)
+        if (fast[b]) phase_b(tb, smem[warp][b], lane);
+    }
+    __syncwarp();
+    // ---- phase C: window entries are reloaded only when the previous-window shape changes ----
+    {
+      TabC tc;
+      int cur_shape = -1;
+      float4 ovv[2][8];
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        if (b == 0 && fast[0]) load_overlap(ovv[0], overlap + size_t(unit0) * 1024, lane);
+        // the next unit's overlap (an L2 hit after the prefetch) is requested before this unit's arithmetic
+        if (b + 1 < B && fast[(b + 1) % B])
+          load_overlap(ovv[(b + 1) & 1], overlap + size_t(unit0 + b + 1) * 1024, lane);
+        if (!fast[b]) continue;
+        if (sd[b].shape_prev != cur_shape) {
+          cur_shape = sd[b].shape_prev;
+          load_tab_c(tc, T.win_long[cur_shape], lane);
+        }
+        float* ov = overlap + size_t(unit0 + b) * 1024;
+        float* o = out + size_t(unit0 + b) * 1024;
+        if (sd[b].seq == 0 || sd[b].seq == 1) {
+          phase_c(ovv[b & 1], tc, smem[warp][b], ov, o, lane);
+        } else {
+          phase_c_stop(smem[warp][b], ov, o, T.win_short[cur_shape], lane);
+        }
+      }
+    }
+  }
+  if (any_slow) {
+#pragma unroll 1
+    for (int b = 0; b < nb; ++b) {
+      const Side s = unpack_side(__ldg(side + unit0 + b));
+      if (s.seq != 2 && s.tkt == 0) continue;
+      const size_t off = size_t(unit0 + b) * 1024;
+      __syncwarp();
+      fd_unit_generic(coef + off, overlap + off, out + off, s, smem[warp][b], T, lane);
+    }
   }
 }
 
 }  // namespace
 
-template <int WARPS, int MIN_BLOCKS>
-static void launch_variant(const float* d_coef, const uint32_t* d_side, float* d_overlap, float* d_out, int n_units,
-                           const DeviceTables& T, cudaStream_t stream) {
-  const int grid = (n_units + WARPS - 1) / WARPS;
-  fd_synth_kernel<WARPS, MIN_BLOCKS><<<grid, WARPS * 32, 0, stream>>>(d_coef, d_side, d_overlap, d_out, n_units, T);
+template <int B, int WARPS, int MIN_BLOCKS>
+static cudaError_t launch_variant(const float* d_coef, const uint32_t* d_side, float* d_overlap, float* d_out,
+                                  int n_units, const DeviceTables& T, cudaStream_t stream) {
+  static bool configured = false;  // per template instance; benign race (idempotent attribute)
+  auto kern = fd_synth_kernel<B, WARPS, MIN_BLOCKS>;
+  if (!configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    configured = true;
+  }
+  const int per_cta = B * WARPS;
+  const int grid = (n_units + per_cta - 1) / per_cta;
+  kern<<<grid, WARPS * 32, 0, stream>>>(d_coef, d_side, d_overlap, d_out, n_units, T);
+  return cudaGetLastError();
 }
 
 mpeghb200_status fd_synth_launch(mpeghb200_ctx* ctx, const float* d_coef, const uint32_t* d_side, float* d_overlap,
                                  float* d_out, int n_units, cudaStream_t stream) {
   if (n_units == 0) return MPEGHB200_OK;
-  // Launch shape (warps per CTA, CTAs per SM the register budget is sized for). Variant 0 is the default;
-  // the others exist for tuning sweeps (MPEGHB200_FD_VARIANT, read once at context creation).
+  // Launch shape: units per warp, warps per CTA, CTAs per SM the register budget is sized for.  Variant 0
+  // is the default; the others exist for tuning sweeps (MPEGHB200_FD_VARIANT, read at context creation).
+  cudaError_t e;
   switch (ctx->fd_variant) {
+    case 0: e = launch_variant<3, 1, 14>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables, stream); break;
+    case 1: e = launch_variant<3, 2, 7>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables, stream); break;
+    case 2: e = launch_variant<4, 1, 12>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables, stream); break;
     default:
-    case 0: launch_variant<4, 8>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables, stream); break;
-    case 1: launch_variant<4, 6>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables, stream); break;
-    case 2: launch_variant<2, 16>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables, stream); break;
-    case 3: launch_variant<8, 4>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables, stream); break;
-    case 4: launch_variant<1, 24>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables, stream); break;
-    case 5: launch_variant<2, 12>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables, stream); break;
+    case 3: e = launch_variant<2, 1, 16>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables, stream); break;
+    case 4: e = launch_variant<2, 2, 10>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables, stream); break;
+    case 5: e = launch_variant<1, 4, 8>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables, stream); break;
+    case 6: e = launch_variant<6, 1, 7>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables, stream); break;
   }
   ctx->launches.fetch_add(1);
-  MB_CUDA(ctx, cudaGetLastError());
+  MB_CUDA(ctx, e);
   return MPEGHB200_OK;
 }
 

@@ -75,6 +75,10 @@ class Lib:
         c.mpeghb200_d2h.restype = i32
         c.mpeghb200_sync.argtypes = [vp]
         c.mpeghb200_sync.restype = i32
+        c.mpeghb200_host_alloc.argtypes = [vp, sz, ctypes.POINTER(vp)]
+        c.mpeghb200_host_alloc.restype = i32
+        c.mpeghb200_host_free.argtypes = [vp, vp]
+        c.mpeghb200_host_free.restype = i32
         c.mpeghb200_fd_synth_dev.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, vp]
         c.mpeghb200_fd_synth_dev.restype = i32
         c.mpeghb200_fd_open.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
@@ -109,6 +113,21 @@ class Lib:
 
     def launch_count(self):
         return int(self.c.mpeghb200_launch_count(self.ctx))
+
+    def host_array(self, shape, dtype=np.float32):
+        """numpy view of page-locked memory from mpeghb200_host_alloc (freed with host_free(arr))."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = ctypes.c_void_p()
+        self.check(self.c.mpeghb200_host_alloc(self.ctx, n, ctypes.byref(p)))
+        buf = (ctypes.c_byte * n).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+        self._pinned = getattr(self, "_pinned", {})
+        self._pinned[arr.ctypes.data] = p
+        return arr
+
+    def host_free(self, arr):
+        p = self._pinned.pop(arr.ctypes.data)
+        self.check(self.c.mpeghb200_host_free(self.ctx, p))
 
     # ---- constant tables (host side, no GPU needed) ------------------------------------------------
     def rom_tables(self, patched=True):

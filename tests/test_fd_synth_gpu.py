@@ -85,6 +85,37 @@ def test_reset_stream(gpu_lib, oracle):
         sess.close()
 
 
+def test_pinned_and_pageable_host_buffers_agree(gpu_lib, oracle):
+    """mpeghb200_fd_execute takes the DMA-direct path for page-locked buffers and the staged path otherwise;
+    2600 units exercise the 8-chunk pipeline with a ragged last chunk."""
+    rng = np.random.default_rng(77)
+    S, C = 325, 8
+    coef = fd_cases.random_coef(rng, (S, C, 1024))
+    side5 = fd_cases.random_side(rng, 1, S * C, kernel_switch_prob=0.1, legal=False)[0]
+    side = fd_cases.pack_side(side5).reshape(S, C)
+    want = np.zeros((S * C, 1024), np.float32)
+    ov = np.zeros((S * C, 1024), np.float32)
+    assert oracle.oracle_fd_frm_dec_batch(coef.reshape(1, S * C, 1024), ov, want.reshape(1, S * C, 1024),
+                                          side5.reshape(1, S * C, 5), 1, S * C) == 0
+    p_coef = gpu_lib.host_array((S, C, 1024))
+    p_out = gpu_lib.host_array((S, C, 1024))
+    p_coef[...] = coef
+    for pinned in (False, True):
+        sess = gpu_lib.fd_open(S, C)
+        try:
+            if pinned:
+                gpu_lib.check(gpu_lib.c.mpeghb200_fd_execute(sess.h, p_coef.ctypes.data, side.ctypes.data,
+                                                             p_out.ctypes.data))
+                got = p_out.copy()
+            else:
+                got = sess.execute(coef, side)
+        finally:
+            sess.close()
+        assert bits_equal(got.reshape(S * C, 1024), want), pinned
+    gpu_lib.host_free(p_coef)
+    gpu_lib.host_free(p_out)
+
+
 def test_empty_batch(gpu_lib):
     gpu_lib.fd_synth_dev(0, 0, 0, 0, 0)
 
