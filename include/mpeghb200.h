@@ -102,6 +102,40 @@ mpeghb200_status mpeghb200_fd_execute(mpeghb200_fd_session *s, const float *h_co
 mpeghb200_status mpeghb200_fd_reset_stream(mpeghb200_fd_session *s, int stream);
 void mpeghb200_fd_close(mpeghb200_fd_session *s);
 
+/* ---- tail of the chain: loudness gain, peak limiter, PCM packer -----------------------------------
+ * Limiter: replaces impeghd_peak_limiter_init / _process (decoder/impeghd_peak_limiter.c:146,190) together
+ * with the planar<->interleaved transposes of impegh_dec_peak_limiter (decoder/ia_core_coder_decode_main.c:1429)
+ * and the loudness-normalisation multiply of impegh_dec_ln_pl_process (:1533-1544).
+ * Audio in/out: planar [stream][n_ch][1024] at 16-bit scale; output is delayed by attack_samples (240 @48 kHz)
+ * exactly like the reference.  Per-stream state lives in d_state (mpeghb200_limiter_state_floats() floats per
+ * stream, initialised by mpeghb200_limiter_state_init_dev; re-initialise a stream's slice on flush). */
+typedef struct mpeghb200_limiter_params {
+  int32_t n_ch;
+  int32_t attack_samples; /* (int)(5 ms * fs / 1000) */
+  int32_t limiter_on;     /* 0: pure delay while the smoothed gain is >= 1 (impeghd_peak_limiter.c:207-211) */
+  float threshold;        /* 0.89125094f * 32768.0f */
+  float attack_const;     /* (float)pow(0.1, 1 / (attack_samples + 1)), host double pow like the reference */
+  float release_const;    /* (float)pow(0.1, 1 / (50 ms * fs / 1000 + 1)) */
+} mpeghb200_limiter_params;
+mpeghb200_status mpeghb200_limiter_params_init(mpeghb200_limiter_params *p, int n_ch, int sample_rate,
+                                               int limiter_on);
+size_t mpeghb200_limiter_state_floats(const mpeghb200_limiter_params *p);
+mpeghb200_status mpeghb200_limiter_state_init_dev(mpeghb200_ctx *ctx, const mpeghb200_limiter_params *p,
+                                                  float *d_state, int n_streams, void *cuda_stream);
+/* d_loudness_gain: per-stream linear gain (float)pow(10, dB/20) computed by the host, or NULL. d_in != d_out. */
+mpeghb200_status mpeghb200_limiter_dev(mpeghb200_ctx *ctx, const mpeghb200_limiter_params *p, const float *d_in,
+                                       float *d_out, float *d_state, const float *d_loudness_gain,
+                                       int n_streams, void *cuda_stream);
+
+/* PCM packer: replaces ia_core_coder_samples_sat (decoder/ia_core_coder_decode_main.c:209).
+ * d_in planar [stream][n_ch][1024]; d_out [stream][1024 * n_ch * pcm_bits/8] interleaved little-endian;
+ * out_ch_map: HOST array of n_ch entries as in the reference (-1 = identity) or NULL;
+ * d_delay: per-stream start-up delay in samples (the handle's delay_in_samples), read and advanced, or NULL;
+ * d_out_bytes: per-stream valid byte count of this frame (the reference's *out_bytes), or NULL. */
+mpeghb200_status mpeghb200_pcm_pack_dev(mpeghb200_ctx *ctx, const float *d_in, int n_ch, int pcm_bits,
+                                        const int32_t *out_ch_map, int32_t *d_delay, uint8_t *d_out,
+                                        int32_t *d_out_bytes, int n_streams, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,377 @@
+// tail.cu -- end of the chain: loudness gain, look-ahead peak limiter, PCM packer.
+//
+// Stands in for impegh_dec_ln_pl_process (decoder/ia_core_coder_decode_main.c:1496), impegh_dec_peak_limiter
+// (:1429), impeghd_peak_limiter_process (decoder/impeghd_peak_limiter.c:190) and ia_core_coder_samples_sat
+// (decoder/ia_core_coder_decode_main.c:209).
+//
+// Limiter.  The reference walks the frame sample by sample on an interleaved copy.  Only one part of that is
+// inherently serial: the two-variable gain smoother (gain_modified, pre_smoothed_gain).  Everything around
+// it is data parallel and is done by the whole CTA (one CTA per stream):
+//   1. m[i]   = max_c |x[c][i]|                       (channel maximum, coalesced float4 reads per channel)
+//   2. M[i]   = max(m[i-A..i])                        (A = attack_time_samples = 240 @48 kHz; the reference's
+//                                                      max_idx bookkeeping maintains exactly this sliding
+//                                                      maximum, see oracle/oracle_tail.c) by window doubling
+//   3. g0[i]  = thr >= M ? 1 : thr / M                (IEEE division)
+//   4. g[i]   = smoother(g0[i])                       one thread, 1024 steps; skipped when the frame cannot
+//                                                      move the gain (all g0 == 1 and the state sits at 1)
+//   5. y[c][i] = clip(x[c][i-A] * g[i])               (delay line = last A samples of the previous frame)
+// State per stream, time order (oldest first): {gain_modified, pre_smoothed_gain, -, -, max_hist[A],
+// delay[n_ch][A]}.  Bytes per stream-frame: read n_ch*4096, write n_ch*4096 (+ state 2*(1+n_ch)*A*4).
+//
+// PCM packer.  planar float -> interleaved little-endian 16/24/32-bit with the reference's clamp-then-truncate
+// and its start-up delay trimming; staged through shared memory so both sides are coalesced.
+#include <cmath>
+#include <cstring>
+
+#include "common.h"
+
+namespace mpeghb200 {
+namespace {
+
+constexpr int kLimThreads = 128;
+constexpr int kMaxAttack = 240;
+constexpr int kFrame = 1024;
+
+struct LimParams {
+  int n_ch, attack, limiter_on, stride;  // stride = floats of state per stream
+  float thr, ac, rc;
+};
+
+__global__ void __launch_bounds__(kLimThreads)
+    limiter_kernel(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ state,
+                   const float* __restrict__ loud_gain, const LimParams P) {
+  __shared__ __align__(16) float m[kMaxAttack + kFrame + 16];   // channel maxima incl. history / sliding max
+  __shared__ __align__(16) float m2[kMaxAttack + kFrame + 16];  // ping-pong partner
+  __shared__ __align__(16) float g[kFrame];                     // gains; < 0 = pass through
+  __shared__ __align__(16) float xbuf[kMaxAttack + kFrame];     // delay line + current frame of one channel
+  const int tid = threadIdx.x;
+  const int A = P.attack;
+  const size_t sidx = blockIdx.x;
+  const float* x = in + sidx * size_t(P.n_ch) * kFrame;
+  float* y = out + sidx * size_t(P.n_ch) * kFrame;
+  float* st = state + sidx * size_t(P.stride);
+  float* st_hist = st + 4;
+  float* st_delay = st + 4 + A;
+  const float lg = loud_gain ? __ldg(loud_gain + sidx) : 1.0f;
+  const bool has_lg = loud_gain != nullptr;
+  const float psg0 = st[1];
+  const bool bypass = (!P.limiter_on) && (psg0 >= 1.0f);
+
+  if (!bypass) {
+    // 1. channel maxima (fmax semantics of the reference: NaN operands are dropped)
+    float4 acc[2];
+    acc[0] = acc[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < P.n_ch; ++c) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(x + size_t(c) * kFrame) + tid + kLimThreads * h);
+        if (has_lg) v = make_float4(fmul(v.x, lg), fmul(v.y, lg), fmul(v.z, lg), fmul(v.w, lg));
+        acc[h].x = fmaxf(acc[h].x, fabsf(v.x));
+        acc[h].y = fmaxf(acc[h].y, fabsf(v.y));
+        acc[h].z = fmaxf(acc[h].z, fabsf(v.z));
+        acc[h].w = fmaxf(acc[h].w, fabsf(v.w));
+      }
+    }
+    for (int i = tid; i < A; i += kLimThreads) m[i] = st_hist[i];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = 4 * (tid + kLimThreads * h);
+      m[A + i] = acc[h].x, m[A + i + 1] = acc[h].y, m[A + i + 2] = acc[h].z, m[A + i + 3] = acc[h].w;
+    }
+    for (int i = tid; i < 16; i += kLimThreads) m[A + kFrame + i] = 0.f, m2[A + kFrame + i] = 0.f;
+    __syncthreads();
+    // new history = channel maxima of the last A samples of this frame
+    for (int i = tid; i < A; i += kLimThreads) st_hist[i] = m[kFrame + i];
+    // 2. sliding maximum over A+1 values ending at sample i: W[i] = max(m[i .. i+A]) in history-first indexing.
+    //    Window doubling: after pass k, buf[i] = max(m[i .. i+2^k-1]).  A+1 is covered by two windows of length
+    //    L = 2^floor(log2(A+1)).
+    const int W = A + 1;
+    int L = 1;
+    float* src = m;
+    float* dst = m2;
+    const int total = A + kFrame;
+    while (2 * L <= W) {
+      for (int i = tid; i < total; i += kLimThreads) {
+        const int j = i + L;
+        dst[i] = (j < total) ? fmaxf(src[i], src[j]) : src[i];
+      }
+      __syncthreads();
+      float* t = src;
+      src = dst;
+      dst = t;
+      L *= 2;
+    }
+    // 3. raw gain
+    int all_one = 1;
+    for (int i = tid; i < kFrame; i += kLimThreads) {
+      const float mx = fmaxf(src[i], src[i + W - L]);
+      const float g0 = (P.thr >= mx) ? 1.0f : __fdiv_rn(P.thr, mx);
+      g[i] = g0;
+      all_one &= (g0 == 1.0f);
+    }
+    const int quiet = __syncthreads_and(all_one);
+    // 4. the serial smoother (decoder/impeghd_peak_limiter.c:248-270)
+    if (!(quiet && psg0 == 1.0f)) {
+      if (tid == 0) {
+        float gm = st[0], psg = psg0;
+        float nxt = g[0];
+        for (int i = 0; i < kFrame; ++i) {
+          const float gain = nxt;
+          if (i + 1 < kFrame) nxt = g[i + 1];
+          if (gain < psg) {
+            gm = fminf(gm, fmul(fsub(gain, fmul(0.1f, psg)), 1.11111111f));
+          } else {
+            gm = gain;
+          }
+          if (gm >= psg) {
+            psg = fadd(gm, fmul(P.rc, fsub(psg, gm)));
+          } else {
+            psg = fadd(gm, fmul(P.ac, fsub(psg, gm)));
+            psg = fmaxf(psg, gain);
+          }
+          g[i] = psg;
+        }
+        st[0] = gm;
+        st[1] = psg;
+      }
+    } else if (tid == 0) {
+      st[0] = 1.0f;  // gain_modified = gain = 1 on every sample; pre_smoothed_gain stays 1
+    }
+    __syncthreads();
+  } else {
+    for (int i = tid; i < kFrame; i += kLimThreads) g[i] = -1.0f;
+    __syncthreads();
+  }
+
+  // 5. delayed output, one channel at a time through shared memory
+  const float thr = P.thr;
+  for (int c = 0; c < P.n_ch; ++c) {
+    float* dl = st_delay + size_t(c) * A;
+    for (int i = tid; i < A / 4; i += kLimThreads)
+      reinterpret_cast<float4*>(xbuf)[i] = reinterpret_cast<const float4*>(dl)[i];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(x + size_t(c) * kFrame) + tid + kLimThreads * h);
+      if (has_lg) v = make_float4(fmul(v.x, lg), fmul(v.y, lg), fmul(v.z, lg), fmul(v.w, lg));
+      reinterpret_cast<float4*>(xbuf + A)[tid + kLimThreads * h] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = 4 * (tid + kLimThreads * h);
+      const float4 xv = *reinterpret_cast<const float4*>(xbuf + i);
+      const float4 gv = *reinterpret_cast<const float4*>(g + i);
+      float r[4] = {xv.x, xv.y, xv.z, xv.w};
+      const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (gg[e] >= 0.0f) {
+          float t = fmul(r[e], gg[e]);
+          if (thr < t)
+            t = thr;
+          else if (t < -thr)
+            t = -thr;
+          r[e] = t;
+        }
+      }
+      __stcs(reinterpret_cast<float4*>(y + size_t(c) * kFrame + i), make_float4(r[0], r[1], r[2], r[3]));
+    }
+    for (int i = tid; i < A / 4; i += kLimThreads)
+      reinterpret_cast<float4*>(dl)[i] = reinterpret_cast<const float4*>(xbuf + kFrame)[i];
+    __syncthreads();
+  }
+}
+
+__global__ void limiter_state_init_kernel(float* state, int stride, int n_streams) {
+  const size_t n = size_t(stride) * n_streams;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    const int k = int(i % stride);
+    state[i] = (k < 2) ? 1.0f : 0.0f;
+  }
+}
+
+// ---- PCM packer ------------------------------------------------------------------------------------
+constexpr int kPackSamples = 256;  // samples per CTA
+struct PackParams {
+  int n_ch, bits;
+  unsigned char pos[64];  // planar channel feeding interleave slot ch (the reference's channel_pos[])
+};
+
+__device__ __forceinline__ int sat_cast(float v) {
+  // x86 cvttss2si semantics for out-of-range / NaN: 0x80000000
+  if (!(v < 2147483648.0f) || v < -2147483648.0f) return int(0x80000000u);
+  return __float2int_rz(v);
+}
+
+__global__ void __launch_bounds__(kPackSamples)
+    pcm_pack_kernel(const float* __restrict__ in, unsigned char* __restrict__ out, int* __restrict__ delay,
+                    int* __restrict__ out_bytes, const PackParams P) {
+  extern __shared__ __align__(16) unsigned char tile[];  // [kPackSamples][n_ch][bytes]
+  const int tid = threadIdx.x;
+  const int chunk = blockIdx.x, sidx = blockIdx.y;
+  const int bps = P.bits >> 3;
+  const int frame_bytes = kFrame * P.n_ch * bps;
+  const float* x = in + size_t(sidx) * P.n_ch * kFrame;
+  const int d = delay ? delay[sidx] : 0;
+  const int s = chunk * kPackSamples + tid;
+  for (int ch = 0; ch < P.n_ch; ++ch) {
+    float v = __ldcs(x + size_t(P.pos[ch]) * kFrame + s);
+    int w;
+    if (P.bits == 24) {
+      v = fmul(v, 256.0f);
+      if (v < -8388608.0f)
+        v = -8388608.0f;
+      else if (8388607.0f < v)
+        v = 8388607.0f;
+      w = sat_cast(v);
+    } else if (P.bits == 16) {
+      if (v < -32768.0f)
+        v = -32768.0f;
+      else if (32767.0f < v)
+        v = 32767.0f;
+      w = sat_cast(v);
+    } else {
+      v = fmul(v, 65536.0f);
+      if (v < -2147483647.0f) v = -2147483647.0f;
+      // reference build quirk (see oracle/oracle_tail.c): above 2^31 -> INT32_MAX, exactly 2^31 -> INT32_MIN
+      w = (2147483647.0f < v) ? 0x7fffffff : sat_cast(v);
+    }
+    unsigned char* t = tile + (size_t(tid) * P.n_ch + ch) * bps;
+    t[0] = w & 0xff;
+    t[1] = (w >> 8) & 0xff;
+    if (bps > 2) t[2] = (w >> 16) & 0xff;
+    if (bps > 3) t[3] = (w >> 24) & 0xff;
+  }
+  __syncthreads();
+  // tile -> global; sample s lands at byte (s - d) * n_ch * bps (start-up delay trimming)
+  const int tile_bytes = kPackSamples * P.n_ch * bps;
+  const long long dst0 = (long long)(chunk * kPackSamples - d) * P.n_ch * bps;
+  unsigned char* o = out + size_t(sidx) * frame_bytes;
+  if (dst0 >= 0 && (dst0 & 15) == 0 && (tile_bytes & 15) == 0) {
+    const uint4* t4 = reinterpret_cast<const uint4*>(tile);
+    uint4* o4 = reinterpret_cast<uint4*>(o + dst0);
+    for (int i = tid; i < tile_bytes / 16; i += kPackSamples) __stcs(o4 + i, t4[i]);
+  } else {
+    for (int i = tid; i < tile_bytes; i += kPackSamples) {
+      const long long p = dst0 + i;
+      if (p >= 0) o[p] = tile[i];
+    }
+  }
+  if (chunk == 0 && tid == 0) {
+    if (out_bytes) out_bytes[sidx] = (d <= kFrame) ? (kFrame - d) * P.n_ch * bps : 0;
+  }
+}
+
+// the delay state is advanced by a separate tiny kernel so that every chunk CTA of a stream sees the old value
+__global__ void pcm_delay_advance_kernel(int* delay, int n_streams) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_streams) {
+    const int d = delay[i];
+    delay[i] = (d <= kFrame) ? 0 : d - kFrame;
+  }
+}
+
+}  // namespace
+}  // namespace mpeghb200
+
+using namespace mpeghb200;
+
+extern "C" {
+
+mpeghb200_status mpeghb200_limiter_params_init(mpeghb200_limiter_params* p, int n_ch, int sample_rate,
+                                               int limiter_on) {
+  if (!p || n_ch <= 0 || n_ch > 64 || sample_rate <= 0) return MPEGHB200_ERR_BAD_ARG;
+  // decoder/impeghd_peak_limiter.c:152-177; the constants come from the host's double-precision pow(),
+  // as in the reference (GPU libm is not bit-compatible)
+  const int attack = int(5.0f * sample_rate / 1000);
+  if (attack < 4 || attack > kMaxAttack || (attack & 3)) return MPEGHB200_ERR_UNSUPPORTED;
+  p->n_ch = n_ch;
+  p->attack_samples = attack;
+  p->limiter_on = limiter_on;
+  p->threshold = 0.89125094f * 32768.0f;
+  p->attack_const = float(std::pow(0.1, 1.0 / (attack + 1)));
+  p->release_const = float(std::pow(0.1, 1.0 / (50.0f * sample_rate / 1000 + 1)));
+  return MPEGHB200_OK;
+}
+
+size_t mpeghb200_limiter_state_floats(const mpeghb200_limiter_params* p) {
+  return p ? size_t(4 + p->attack_samples * (1 + p->n_ch)) : 0;
+}
+
+mpeghb200_status mpeghb200_limiter_state_init_dev(mpeghb200_ctx* ctx, const mpeghb200_limiter_params* p,
+                                                  float* d_state, int n_streams, void* cuda_stream) {
+  if (!ctx || !p || n_streams < 0 || (n_streams > 0 && !d_state)) return MPEGHB200_ERR_BAD_ARG;
+  if (n_streams == 0) return MPEGHB200_OK;
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  limiter_state_init_kernel<<<148, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+      d_state, int(mpeghb200_limiter_state_floats(p)), n_streams);
+  ctx->launches.fetch_add(1);
+  MB_CUDA(ctx, cudaGetLastError());
+  return MPEGHB200_OK;
+}
+
+mpeghb200_status mpeghb200_limiter_dev(mpeghb200_ctx* ctx, const mpeghb200_limiter_params* p, const float* d_in,
+                                       float* d_out, float* d_state, const float* d_loudness_gain, int n_streams,
+                                       void* cuda_stream) {
+  if (!ctx || !p) return MPEGHB200_ERR_BAD_ARG;
+  if (n_streams < 0 || (n_streams > 0 && (!d_in || !d_out || !d_state)))
+    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "limiter_dev: null buffer or negative stream count");
+  if (d_in == d_out) return fail(ctx, MPEGHB200_ERR_BAD_ARG, "limiter_dev: in-place operation is not supported");
+  if (n_streams == 0) return MPEGHB200_OK;
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  LimParams P;
+  P.n_ch = p->n_ch;
+  P.attack = p->attack_samples;
+  P.limiter_on = p->limiter_on;
+  P.stride = int(mpeghb200_limiter_state_floats(p));
+  P.thr = p->threshold;
+  P.ac = p->attack_const;
+  P.rc = p->release_const;
+  limiter_kernel<<<n_streams, kLimThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(d_in, d_out, d_state,
+                                                                                       d_loudness_gain, P);
+  ctx->launches.fetch_add(1);
+  MB_CUDA(ctx, cudaGetLastError());
+  return MPEGHB200_OK;
+}
+
+mpeghb200_status mpeghb200_pcm_pack_dev(mpeghb200_ctx* ctx, const float* d_in, int n_ch, int pcm_bits,
+                                        const int32_t* out_ch_map, int32_t* d_delay, uint8_t* d_out,
+                                        int32_t* d_out_bytes, int n_streams, void* cuda_stream) {
+  if (!ctx) return MPEGHB200_ERR_BAD_ARG;
+  if (n_ch <= 0 || n_ch > 64 || (pcm_bits != 16 && pcm_bits != 24 && pcm_bits != 32) || n_streams < 0 ||
+      (n_streams > 0 && (!d_in || !d_out)))
+    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "pcm_pack_dev: bad channel count, sample size or buffer");
+  if (n_streams == 0) return MPEGHB200_OK;
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  PackParams P;
+  P.n_ch = n_ch;
+  P.bits = pcm_bits;
+  // decoder/ia_core_coder_decode_main.c:231-236: channel_pos[out_ch_map[ch]] = ch, -1 meaning identity
+  for (int ch = 0; ch < 64; ++ch) P.pos[ch] = static_cast<unsigned char>(ch < n_ch ? ch : 0);
+  if (out_ch_map) {
+    for (int ch = 0; ch < n_ch; ++ch) {
+      const int m = out_ch_map[ch] == -1 ? ch : out_ch_map[ch];
+      if (m < 0 || m >= n_ch) return fail(ctx, MPEGHB200_ERR_BAD_ARG, "pcm_pack_dev: out_ch_map entry out of range");
+      P.pos[m] = static_cast<unsigned char>(ch);
+    }
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const size_t smem = size_t(kPackSamples) * n_ch * (pcm_bits >> 3);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(pcm_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    configured = true;
+  }
+  dim3 grid(kFrame / kPackSamples, n_streams);
+  pcm_pack_kernel<<<grid, kPackSamples, smem, st>>>(d_in, d_out, d_delay, d_out_bytes, P);
+  ctx->launches.fetch_add(1);
+  MB_CUDA(ctx, cudaGetLastError());
+  if (d_delay) {
+    pcm_delay_advance_kernel<<<(n_streams + 255) / 256, 256, 0, st>>>(d_delay, n_streams);
+    ctx->launches.fetch_add(1);
+    MB_CUDA(ctx, cudaGetLastError());
+  }
+  return MPEGHB200_OK;
+}
+
+}  // extern "C"

@@ -39,6 +39,12 @@ def fd_side(seq, shape=0, shape_prev=0, prev_sym=0, curr_sym=0):
             ((curr_sym & 1) << 6)).astype(np.uint32)
 
 
+class LimiterParams(ctypes.Structure):
+    """mpeghb200_limiter_params"""
+    _fields_ = [("n_ch", ctypes.c_int32), ("attack_samples", ctypes.c_int32), ("limiter_on", ctypes.c_int32),
+                ("threshold", ctypes.c_float), ("attack_const", ctypes.c_float), ("release_const", ctypes.c_float)]
+
+
 class Lib:
     """Thin object wrapper: one instance = one loaded library + (lazily) one context per device."""
 
@@ -88,6 +94,17 @@ class Lib:
         c.mpeghb200_fd_reset_stream.argtypes = [vp, ctypes.c_int]
         c.mpeghb200_fd_reset_stream.restype = i32
         c.mpeghb200_fd_close.argtypes = [vp]
+        c.mpeghb200_limiter_params_init.argtypes = [ctypes.POINTER(LimiterParams), ctypes.c_int, ctypes.c_int,
+                                                    ctypes.c_int]
+        c.mpeghb200_limiter_params_init.restype = i32
+        c.mpeghb200_limiter_state_floats.argtypes = [ctypes.POINTER(LimiterParams)]
+        c.mpeghb200_limiter_state_floats.restype = sz
+        c.mpeghb200_limiter_state_init_dev.argtypes = [vp, ctypes.POINTER(LimiterParams), vp, ctypes.c_int, vp]
+        c.mpeghb200_limiter_state_init_dev.restype = i32
+        c.mpeghb200_limiter_dev.argtypes = [vp, ctypes.POINTER(LimiterParams), vp, vp, vp, vp, ctypes.c_int, vp]
+        c.mpeghb200_limiter_dev.restype = i32
+        c.mpeghb200_pcm_pack_dev.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, vp]
+        c.mpeghb200_pcm_pack_dev.restype = i32
         self.ctx = None
 
     # ---- context ------------------------------------------------------------------------------
@@ -145,6 +162,29 @@ class Lib:
 
     def fd_open(self, n_streams, n_ch):
         return FdSession(self, n_streams, n_ch)
+
+    # ---- tail of the chain ----------------------------------------------------------------------
+    def limiter_params(self, n_ch, sample_rate=48000, limiter_on=1):
+        p = LimiterParams()
+        st = self.c.mpeghb200_limiter_params_init(ctypes.byref(p), n_ch, sample_rate, limiter_on)
+        if st != OK:
+            raise MpeghError(st, "limiter_params_init: unsupported channel count or sample rate")
+        return p
+
+    def limiter_state_floats(self, p):
+        return int(self.c.mpeghb200_limiter_state_floats(ctypes.byref(p)))
+
+    def limiter_state_init_dev(self, p, d_state, n_streams, stream=0):
+        self.check(self.c.mpeghb200_limiter_state_init_dev(self.ctx, ctypes.byref(p), d_state, n_streams, stream))
+
+    def limiter_dev(self, p, d_in, d_out, d_state, n_streams, d_gain=None, stream=0):
+        self.check(self.c.mpeghb200_limiter_dev(self.ctx, ctypes.byref(p), d_in, d_out, d_state, d_gain, n_streams,
+                                                stream))
+
+    def pcm_pack_dev(self, d_in, n_ch, bits, d_out, n_streams, ch_map=None, d_delay=None, d_out_bytes=None, stream=0):
+        m = None if ch_map is None else np.ascontiguousarray(ch_map, dtype=np.int32)
+        self.check(self.c.mpeghb200_pcm_pack_dev(self.ctx, d_in, n_ch, bits, None if m is None else m.ctypes.data,
+                                                 d_delay, d_out, d_out_bytes, n_streams, stream))
 
 
 class FdSession:

@@ -66,8 +66,50 @@ def load_oracle():
     lib.oracle_fd_frm_dec.restype = ctypes.c_int
     lib.oracle_fd_frm_dec_batch.argtypes = [_f32p, _f32p, _f32p, _i32p, ctypes.c_int, ctypes.c_int]
     lib.oracle_fd_frm_dec_batch.restype = ctypes.c_int
+    lib.oracle_limiter_init.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.oracle_limiter_process.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int]
+    lib.oracle_loudness_gain.argtypes = [ctypes.c_float]
+    lib.oracle_loudness_gain.restype = ctypes.c_float
+    lib.oracle_samples_sat.argtypes = [_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _i32p, _i32p, _u8p]
+    lib.oracle_samples_sat.restype = ctypes.c_int
     _oracle = lib
     return lib
+
+
+LIM_MAX_ATTACK, LIM_MAX_CH = 240, 32
+
+
+class OracleLimiter(ctypes.Structure):
+    """Mirror of oracle.h's oracle_limiter (state in time order: the layout the CUDA kernels use too)."""
+    _fields_ = [("n_ch", ctypes.c_int), ("attack_samples", ctypes.c_int), ("limiter_on", ctypes.c_int),
+                ("threshold", ctypes.c_float), ("attack_const", ctypes.c_float), ("release_const", ctypes.c_float),
+                ("gain_modified", ctypes.c_float), ("pre_smoothed_gain", ctypes.c_float),
+                ("max_hist", ctypes.c_float * LIM_MAX_ATTACK),
+                ("delay", (ctypes.c_float * LIM_MAX_ATTACK) * LIM_MAX_CH)]
+
+
+def oracle_limiter_new(n_ch, sample_rate=48000, limiter_on=1):
+    st = OracleLimiter()
+    load_oracle().oracle_limiter_init(ctypes.byref(st), n_ch, sample_rate, limiter_on)
+    return st
+
+
+def oracle_limiter_run(st, planar):
+    """planar [n_ch, n] float32 -> limited copy; st is advanced."""
+    x = np.ascontiguousarray(planar, dtype=np.float32).copy()
+    load_oracle().oracle_limiter_process(ctypes.byref(st), x, x.shape[1])
+    return x
+
+
+def oracle_samples_sat(planar, pcmsize, ch_map=None, delay=0):
+    """-> (bytes ndarray, new_delay)"""
+    planar = np.ascontiguousarray(planar, dtype=np.float32)
+    nch, n = planar.shape
+    m = np.full(nch, -1, np.int32) if ch_map is None else np.ascontiguousarray(ch_map, dtype=np.int32)
+    d = np.array([delay], np.int32)
+    out = np.zeros(nch * n * (pcmsize // 8), np.uint8)
+    nb = load_oracle().oracle_samples_sat(planar, n, nch, pcmsize, m, d, out)
+    return out[:nb].copy(), int(d[0])
 
 
 def load_ref():
@@ -91,7 +133,33 @@ def load_ref():
     lib.ref_fd_frm_dec_batch.restype = ctypes.c_int
     lib.ref_rad2_cplx_ifft.argtypes = [_f32p, _f32p, ctypes.c_int]
     lib.ref_rad2_cplx_fft.argtypes = [_f32p, _f32p, ctypes.c_int]
+    lib.ref_limiter_create.restype = ctypes.c_void_p
+    lib.ref_limiter_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.ref_limiter_destroy.argtypes = [ctypes.c_void_p]
+    lib.ref_limiter_process.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int]
+    lib.ref_limiter_constants.argtypes = [ctypes.c_void_p, _f32p]
     _ref = lib
+    return lib
+
+
+_ref_ns = None
+
+
+def load_ref_ns():
+    """Reference build with the needed `static` functions exported (libmpeghref_ns.so), or None."""
+    global _ref_ns
+    if _ref_ns is not None:
+        return _ref_ns
+    so = os.path.join(HERE, "_ref", "libmpeghref_ns.so")
+    if not os.path.exists(so):
+        if os.path.isdir("/root/reference/decoder"):
+            build("ref")
+        else:
+            return None
+    lib = ctypes.CDLL(so)
+    lib.ref_samples_sat.argtypes = [_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _i32p, _i32p, _u8p]
+    lib.ref_samples_sat.restype = ctypes.c_int
+    _ref_ns = lib
     return lib
 
 

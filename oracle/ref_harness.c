@@ -120,3 +120,51 @@ void ref_rad2_cplx_fft(float *re, float *im, int n)
   static __thread FLOAT32 scratch[8 * 4096];
   impeghd_rad2_cplx_fft(re, im, n, scratch);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Peak limiter: impeghd_peak_limiter_init / _process (impeghd_peak_limiter.c:146,190) with the planar <->
+ * interleaved transposes of impegh_dec_peak_limiter (ia_core_coder_decode_main.c:1429).
+ * ---------------------------------------------------------------------------------------------- */
+#include "impeghd_peak_limiter_struct_def.h"
+IA_ERRORCODE impeghd_peak_limiter_init(ia_peak_limiter_struct *peak_limiter, UWORD32 num_channels,
+                                       UWORD32 sample_rate, FLOAT32 *buffer);
+VOID impeghd_peak_limiter_process(ia_peak_limiter_struct *peak_limiter, FLOAT32 *samples,
+                                  UWORD32 frame_len);
+
+typedef struct
+{
+  ia_peak_limiter_struct lim;
+  FLOAT32 inter[MAX_NUM_CHANNELS * 4096];
+} ref_limiter_handle;
+
+void *ref_limiter_create(int n_ch, int sample_rate, int limiter_on)
+{
+  ref_limiter_handle *h = (ref_limiter_handle *)calloc(1, sizeof(ref_limiter_handle));
+  if (!h)
+    return 0;
+  impeghd_peak_limiter_init(&h->lim, (UWORD32)n_ch, (UWORD32)sample_rate, &h->lim.buffer[0]);
+  h->lim.limiter_on = (UWORD32)limiter_on;
+  return h;
+}
+void ref_limiter_destroy(void *p) { free(p); }
+
+/* planar [n_ch][n] in place, one frame */
+void ref_limiter_process(void *p, float *planar, int n)
+{
+  ref_limiter_handle *h = (ref_limiter_handle *)p;
+  int nch = (int)h->lim.num_channels, i, j;
+  for (i = 0; i < nch; i++)
+    for (j = 0; j < n; j++)
+      h->inter[j * nch + i] = planar[i * n + j];
+  impeghd_peak_limiter_process(&h->lim, h->inter, (UWORD32)n);
+  for (i = 0; i < nch; i++)
+    for (j = 0; j < n; j++)
+      planar[i * n + j] = h->inter[j * nch + i];
+}
+void ref_limiter_constants(void *p, float *out3)
+{
+  ref_limiter_handle *h = (ref_limiter_handle *)p;
+  out3[0] = h->lim.attack_constant;
+  out3[1] = h->lim.release_constant;
+  out3[2] = h->lim.limit_threshold;
+}
