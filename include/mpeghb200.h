@@ -136,6 +136,65 @@ mpeghb200_status mpeghb200_pcm_pack_dev(mpeghb200_ctx *ctx, const float *d_in, i
                                         const int32_t *out_ch_map, int32_t *d_delay, uint8_t *d_out,
                                         int32_t *d_out_bytes, int n_streams, void *cuda_stream);
 
+/* ---- object renderer: VBAP gains + ramped mix ------------------------------------------------------
+ * Replaces impeghd_obj_renderer_dec (decoder/impeghd_obj_ren_dec.c:1319) and everything below
+ * impegh_obj_ren_vbap_process (decoder/impeghd_obj_ren_vbap.c:485) for OAM frame length 1024.
+ *
+ * Layout tables: the reference's init (impeghd_obj_renderer_dec_init, impeghd_obj_ren_dec.c:1057) stays host
+ * code; after it has run, copy these members of ia_obj_ren_dec_state_struct
+ * (decoder/impeghd_obj_ren_dec_struct_def.h:90-120) into the descriptor:
+ *   n_spk = num_cicp_speakers, n_non_lfe = num_non_lfe_ls, n_imag = num_imag_ls, n_tri = num_triangles,
+ *   height_present = height_spks_present, lfe[ch] = ptr_cicp_ls_geo[ch]->lfe_flag,
+ *   tri[t][k] = ls_triangle[t].spk_index[k], inv[t][3*r + {0,1,2}] = ls_inv_mtx[t].row[r].{x,y,z},
+ *   cart[i] = non_lfe_ls_str[i].ls_cart_coord.{x,y,z}, dmx[i][j] = downmix_mtx[i][j]. */
+#define MPEGHB200_OBJ_MAX_LS 44
+#define MPEGHB200_OBJ_MAX_OBJECTS 32
+typedef struct mpeghb200_obj_layout_desc {
+  int32_t n_spk, n_non_lfe, n_imag, n_tri, height_present;
+  int32_t lfe[MPEGHB200_OBJ_MAX_LS];
+  int32_t tri[MPEGHB200_OBJ_MAX_LS][3];
+  float inv[MPEGHB200_OBJ_MAX_LS][9];
+  float cart[MPEGHB200_OBJ_MAX_LS][3];
+  float dmx[MPEGHB200_OBJ_MAX_LS][MPEGHB200_OBJ_MAX_LS];
+} mpeghb200_obj_layout_desc;
+typedef struct mpeghb200_obj_layout mpeghb200_obj_layout;
+mpeghb200_status mpeghb200_obj_layout_create(mpeghb200_ctx *ctx, const mpeghb200_obj_layout_desc *desc,
+                                             mpeghb200_obj_layout **out);
+void mpeghb200_obj_layout_destroy(mpeghb200_obj_layout *layout);
+
+/* Per object and frame: the OAM decoder's descaled metadata after the host-side trigonometry (the reference
+ * evaluates sin/cos/tan in double-precision libm, decoder/impeghd_3d_vec_basic_ops.c:86 and
+ * impeghd_obj_ren_vbap.c:370; those are not bit-reproducible on a GPU, everything else is). 64 bytes. */
+typedef struct mpeghb200_obj_side {
+  float vec_c[3];  /* impeghd_pol_2_cart_degree(elevation, azimuth, radius) */
+  float gain;      /* gain_descaled */
+  float spread_w;  /* spread_width_descaled (raw) */
+  float spread_h;  /* spread_height_descaled */
+  float tan_alpha; /* (float)tan(clamp(width, 0.001, 90) * DEG_2_RAD); only read when spreading */
+  float pad0;
+  float p0[3];     /* pol_2_cart(elevation, azimuth, 1) */
+  float pad1;
+  float v[3];      /* pol_2_cart(elevation -/+ 90, azimuth, 1) */
+  float pad2;
+} mpeghb200_obj_side;
+/* Host helper (no GPU needed): params7[n][7] = {azimuth, elevation, radius, gain, spread width, height, depth}
+ * as ia_oam_dec_state_struct keeps them (decoder/impeghd_oam_dec_struct_def.h:86-92). */
+void mpeghb200_obj_side_from_polar(const float *params7, int n, mpeghb200_obj_side *out);
+
+/* State per stream: previous gains + first-frame flag of every object (mpeghb200_obj_state_floats floats per
+ * stream).  d_first_flags: DEVICE int32[n_obj] copy of the reference's first_frame_flag[] or NULL (all 1). */
+size_t mpeghb200_obj_state_floats(const mpeghb200_obj_layout *layout, int n_obj);
+size_t mpeghb200_obj_scratch_floats(const mpeghb200_obj_layout *layout, int n_obj);
+mpeghb200_status mpeghb200_obj_state_init_dev(mpeghb200_ctx *ctx, const mpeghb200_obj_layout *layout, int n_obj,
+                                              const int32_t *d_first_flags, float *d_state, int n_streams,
+                                              void *cuda_stream);
+/* d_side [n_streams][n_obj], d_in [n_streams][n_obj][1024], d_out [n_streams][n_spk][1024] (overwritten; LFE
+ * rows zero, like the memset at decoder/ia_core_coder_decode_main.c:1374), d_scratch
+ * [n_streams][mpeghb200_obj_scratch_floats]. */
+mpeghb200_status mpeghb200_obj_render_dev(mpeghb200_ctx *ctx, const mpeghb200_obj_layout *layout, int n_obj,
+                                          const mpeghb200_obj_side *d_side, const float *d_in, float *d_out,
+                                          float *d_state, float *d_scratch, int n_streams, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

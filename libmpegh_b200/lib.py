@@ -45,6 +45,35 @@ class LimiterParams(ctypes.Structure):
                 ("threshold", ctypes.c_float), ("attack_const", ctypes.c_float), ("release_const", ctypes.c_float)]
 
 
+OBJ_MAX_LS = 44
+
+
+class ObjLayoutDesc(ctypes.Structure):
+    """mpeghb200_obj_layout_desc"""
+    _fields_ = [("n_spk", ctypes.c_int32), ("n_non_lfe", ctypes.c_int32), ("n_imag", ctypes.c_int32),
+                ("n_tri", ctypes.c_int32), ("height_present", ctypes.c_int32),
+                ("lfe", ctypes.c_int32 * OBJ_MAX_LS), ("tri", (ctypes.c_int32 * 3) * OBJ_MAX_LS),
+                ("inv", (ctypes.c_float * 9) * OBJ_MAX_LS), ("cart", (ctypes.c_float * 3) * OBJ_MAX_LS),
+                ("dmx", (ctypes.c_float * OBJ_MAX_LS) * OBJ_MAX_LS)]
+
+    @classmethod
+    def from_arrays(cls, a):
+        """a: dict with counts[>=5], lfe[44], tri[44,3], inv[44,9], cart[44,3], dmx[44,44]"""
+        d = cls()
+        c = a["counts"]
+        d.n_spk, d.n_non_lfe, d.n_imag, d.n_tri, d.height_present = (int(c[i]) for i in range(5))
+        for name, dt in (("lfe", np.int32), ("tri", np.int32), ("inv", np.float32), ("cart", np.float32),
+                         ("dmx", np.float32)):
+            src = np.ascontiguousarray(a[name], dtype=dt)
+            ctypes.memmove(getattr(d, name), src.ctypes.data, src.nbytes)
+        return d
+
+
+OBJ_SIDE_DTYPE = np.dtype([("vec_c", np.float32, 3), ("gain", np.float32), ("spread_w", np.float32),
+                           ("spread_h", np.float32), ("tan_alpha", np.float32), ("pad0", np.float32),
+                           ("p0", np.float32, 3), ("pad1", np.float32), ("v", np.float32, 3), ("pad2", np.float32)])
+
+
 class Lib:
     """Thin object wrapper: one instance = one loaded library + (lazily) one context per device."""
 
@@ -105,6 +134,18 @@ class Lib:
         c.mpeghb200_limiter_dev.restype = i32
         c.mpeghb200_pcm_pack_dev.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, vp]
         c.mpeghb200_pcm_pack_dev.restype = i32
+        c.mpeghb200_obj_layout_create.argtypes = [vp, ctypes.POINTER(ObjLayoutDesc), ctypes.POINTER(vp)]
+        c.mpeghb200_obj_layout_create.restype = i32
+        c.mpeghb200_obj_layout_destroy.argtypes = [vp]
+        c.mpeghb200_obj_side_from_polar.argtypes = [vp, ctypes.c_int, vp]
+        c.mpeghb200_obj_state_floats.argtypes = [vp, ctypes.c_int]
+        c.mpeghb200_obj_state_floats.restype = sz
+        c.mpeghb200_obj_scratch_floats.argtypes = [vp, ctypes.c_int]
+        c.mpeghb200_obj_scratch_floats.restype = sz
+        c.mpeghb200_obj_state_init_dev.argtypes = [vp, vp, ctypes.c_int, vp, vp, ctypes.c_int, vp]
+        c.mpeghb200_obj_state_init_dev.restype = i32
+        c.mpeghb200_obj_render_dev.argtypes = [vp, vp, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_int, vp]
+        c.mpeghb200_obj_render_dev.restype = i32
         self.ctx = None
 
     # ---- context ------------------------------------------------------------------------------
@@ -162,6 +203,36 @@ class Lib:
 
     def fd_open(self, n_streams, n_ch):
         return FdSession(self, n_streams, n_ch)
+
+    # ---- object renderer ------------------------------------------------------------------------
+    def obj_layout_create(self, arrays):
+        desc = ObjLayoutDesc.from_arrays(arrays)
+        h = ctypes.c_void_p()
+        self.check(self.c.mpeghb200_obj_layout_create(self.ctx, ctypes.byref(desc), ctypes.byref(h)))
+        return h
+
+    def obj_layout_destroy(self, h):
+        self.c.mpeghb200_obj_layout_destroy(h)
+
+    def obj_side_from_polar(self, params):
+        """params [..., 7] float32 -> structured array [...] of mpeghb200_obj_side (host trig, no GPU)."""
+        params = np.ascontiguousarray(params, dtype=np.float32)
+        side = np.zeros(params.shape[:-1], OBJ_SIDE_DTYPE)
+        self.c.mpeghb200_obj_side_from_polar(params.ctypes.data, int(side.size), side.ctypes.data)
+        return side
+
+    def obj_state_floats(self, layout, n_obj):
+        return int(self.c.mpeghb200_obj_state_floats(layout, n_obj))
+
+    def obj_scratch_floats(self, layout, n_obj):
+        return int(self.c.mpeghb200_obj_scratch_floats(layout, n_obj))
+
+    def obj_state_init_dev(self, layout, n_obj, d_state, n_streams, d_first=None, stream=0):
+        self.check(self.c.mpeghb200_obj_state_init_dev(self.ctx, layout, n_obj, d_first, d_state, n_streams, stream))
+
+    def obj_render_dev(self, layout, n_obj, d_side, d_in, d_out, d_state, d_scratch, n_streams, stream=0):
+        self.check(self.c.mpeghb200_obj_render_dev(self.ctx, layout, n_obj, d_side, d_in, d_out, d_state, d_scratch,
+                                                   n_streams, stream))
 
     # ---- tail of the chain ----------------------------------------------------------------------
     def limiter_params(self, n_ch, sample_rate=48000, limiter_on=1):

@@ -72,6 +72,9 @@ def load_oracle():
     lib.oracle_loudness_gain.restype = ctypes.c_float
     lib.oracle_samples_sat.argtypes = [_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _i32p, _i32p, _u8p]
     lib.oracle_samples_sat.restype = ctypes.c_int
+    lib.oracle_obj_trig.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    lib.oracle_obj_gains.argtypes = [ctypes.c_void_p, ctypes.c_void_p, _f32p]
+    lib.oracle_obj_render.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _f32p, _f32p]
     _oracle = lib
     return lib
 
@@ -138,8 +141,100 @@ def load_ref():
     lib.ref_limiter_destroy.argtypes = [ctypes.c_void_p]
     lib.ref_limiter_process.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int]
     lib.ref_limiter_constants.argtypes = [ctypes.c_void_p, _f32p]
+    lib.ref_obj_create.restype = ctypes.c_void_p
+    lib.ref_obj_create.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    lib.ref_obj_destroy.argtypes = [ctypes.c_void_p]
+    lib.ref_obj_layout.argtypes = [ctypes.c_void_p, _i32p, _i32p, _i32p, _f32p, _f32p, _f32p]
+    lib.ref_obj_first_flags.argtypes = [ctypes.c_void_p, _i32p, ctypes.c_int]
+    lib.ref_obj_render.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int, _f32p, _f32p, _f32p]
+    lib.ref_obj_render.restype = ctypes.c_int
     _ref = lib
     return lib
+
+
+# ---- object renderer ------------------------------------------------------------------------------
+OBJ_MAX_LS, OBJ_MAX_OBJ = 44, 96
+
+
+class ObjLayout(ctypes.Structure):
+    """oracle.h oracle_obj_layout"""
+    _fields_ = [("n_spk", ctypes.c_int), ("n_non_lfe", ctypes.c_int), ("n_imag", ctypes.c_int),
+                ("n_tri", ctypes.c_int), ("height_present", ctypes.c_int),
+                ("lfe", ctypes.c_int * OBJ_MAX_LS), ("tri", (ctypes.c_int * 3) * OBJ_MAX_LS),
+                ("inv", (ctypes.c_float * 9) * OBJ_MAX_LS), ("cart", (ctypes.c_float * 3) * OBJ_MAX_LS),
+                ("dmx", (ctypes.c_float * OBJ_MAX_LS) * OBJ_MAX_LS)]
+
+
+class ObjState(ctypes.Structure):
+    _fields_ = [("initial_gains", (ctypes.c_float * OBJ_MAX_LS) * OBJ_MAX_OBJ),
+                ("first_frame", ctypes.c_int * OBJ_MAX_OBJ)]
+
+
+OBJ_SIDE_DTYPE = np.dtype([("vec_c", np.float32, 3), ("gain", np.float32), ("spread_w", np.float32),
+                           ("spread_h", np.float32), ("tan_alpha", np.float32), ("pad0", np.float32),
+                           ("p0", np.float32, 3), ("pad1", np.float32), ("v", np.float32, 3), ("pad2", np.float32)])
+assert OBJ_SIDE_DTYPE.itemsize == 64
+
+
+def obj_layout_from_arrays(a):
+    """dict of arrays (counts, lfe, tri, inv, cart, dmx as ref_obj_layout returns them) -> ObjLayout"""
+    L = ObjLayout()
+    c = a["counts"]
+    L.n_spk, L.n_non_lfe, L.n_imag, L.n_tri, L.height_present = (int(c[i]) for i in range(5))
+    ctypes.memmove(L.lfe, np.ascontiguousarray(a["lfe"], np.int32).ctypes.data, 4 * OBJ_MAX_LS)
+    ctypes.memmove(L.tri, np.ascontiguousarray(a["tri"], np.int32).ctypes.data, 12 * OBJ_MAX_LS)
+    ctypes.memmove(L.inv, np.ascontiguousarray(a["inv"], np.float32).ctypes.data, 36 * OBJ_MAX_LS)
+    ctypes.memmove(L.cart, np.ascontiguousarray(a["cart"], np.float32).ctypes.data, 12 * OBJ_MAX_LS)
+    ctypes.memmove(L.dmx, np.ascontiguousarray(a["dmx"], np.float32).ctypes.data, 4 * OBJ_MAX_LS * OBJ_MAX_LS)
+    return L
+
+
+def ref_obj_layout_arrays(ref, h):
+    a = {"counts": np.zeros(8, np.int32), "lfe": np.zeros(OBJ_MAX_LS, np.int32),
+         "tri": np.zeros((OBJ_MAX_LS, 3), np.int32), "inv": np.zeros((OBJ_MAX_LS, 9), np.float32),
+         "cart": np.zeros((OBJ_MAX_LS, 3), np.float32), "dmx": np.zeros((OBJ_MAX_LS, OBJ_MAX_LS), np.float32)}
+    ref.ref_obj_layout(h, a["counts"], a["lfe"], a["tri"].reshape(-1), a["inv"].reshape(-1), a["cart"].reshape(-1),
+                       a["dmx"].reshape(-1))
+    return a
+
+
+def obj_layout_golden(cicp):
+    """Layout tables dumped from the reference init (tests/golden/obj_layouts.npz)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "obj_layouts.npz"))
+    return {k: g[f"cicp{cicp}_{k}"] for k in ("counts", "lfe", "tri", "inv", "cart", "dmx")}
+
+
+def oracle_obj_side(params):
+    """params [n_obj, 7] (az, el, radius, gain, spread w/h/d) -> structured side array (host trig)."""
+    params = np.ascontiguousarray(params, dtype=np.float32)
+    side = np.zeros(params.shape[0], OBJ_SIDE_DTYPE)
+    lib = load_oracle()
+    for o in range(params.shape[0]):
+        lib.oracle_obj_trig(params[o].ctypes.data_as(ctypes.c_void_p),
+                            ctypes.c_void_p(side.ctypes.data + 64 * o))
+    return side
+
+
+def oracle_obj_state_new(n_first=24):
+    st = ObjState()
+    for i in range(min(n_first, OBJ_MAX_OBJ)):
+        st.first_frame[i] = 1
+    return st
+
+
+def oracle_obj_render(L, st, side, x):
+    """x [n_obj, 1024] -> out [n_spk, 1024]"""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.zeros((L.n_spk, 1024), np.float32)
+    load_oracle().oracle_obj_render(ctypes.byref(L), ctypes.byref(st), ctypes.c_void_p(side.ctypes.data), x.shape[0],
+                                    x, out)
+    return out
+
+
+def oracle_obj_gains(L, side_one):
+    fg = np.zeros(OBJ_MAX_LS, np.float32)
+    load_oracle().oracle_obj_gains(ctypes.byref(L), ctypes.c_void_p(side_one.ctypes.data), fg)
+    return fg[:L.n_non_lfe].copy()
 
 
 _ref_ns = None
