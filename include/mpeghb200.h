@@ -195,6 +195,26 @@ mpeghb200_status mpeghb200_obj_render_dev(mpeghb200_ctx *ctx, const mpeghb200_ob
                                           const mpeghb200_obj_side *d_side, const float *d_in, float *d_out,
                                           float *d_state, float *d_scratch, int n_streams, void *cuda_stream);
 
+/* ---- HOA loudspeaker rendering: NFC filtering + render matrix + clip ---------------------------------
+ * Replaces impeghd_hoa_ren_block_process (decoder/impeghd_hoa_renderer.c:181) incl. the near-field
+ * compensation pre-filter (impeghd_hoa_ren_nfc_filter_apply, decoder/impeghd_hoa_nfc_filtering.c:201).
+ * The reference's host init stays in charge of the design; after impeghd_hoa_ren_renderer_init / _nfc_init:
+ *   matrix [n_out][n_coef]  = ia_render_hoa_str.v_render_mtrx[mtrx_selected].sm_mtrx.mtrx (row-major),
+ *   nfc_coeffs [n_coef][17] = per ia_render_hoa_nfc_filtering_str: {global_gain, num_iir_2_filts,
+ *                             num_iir_1_filts, (a1, a2, b1, b2) of str_iir_2[0..2], (a1, b1) of str_iir_1},
+ *                             or NULL when use_nfc == 0,
+ *   clip                    = is_clipping_protect_enabled (1 at the reference's only call site,
+ *                             decoder/impeghd_hoa_decoder.c:223).
+ * d_in [stream][n_coef][1024] (not modified), d_out [stream][n_out][1024], d_nfc_state
+ * [stream][mpeghb200_hoa_nfc_state_floats] zero-initialised by the caller (cudaMemset / dev_memset). */
+typedef struct mpeghb200_hoa_renderer mpeghb200_hoa_renderer;
+mpeghb200_status mpeghb200_hoa_renderer_create(mpeghb200_ctx *ctx, const float *matrix, int n_out, int n_coef,
+                                               const float *nfc_coeffs, int clip, mpeghb200_hoa_renderer **out);
+void mpeghb200_hoa_renderer_destroy(mpeghb200_hoa_renderer *r);
+size_t mpeghb200_hoa_nfc_state_floats(const mpeghb200_hoa_renderer *r);
+mpeghb200_status mpeghb200_hoa_render_dev(mpeghb200_ctx *ctx, const mpeghb200_hoa_renderer *r, const float *d_in,
+                                          float *d_out, float *d_nfc_state, int n_streams, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

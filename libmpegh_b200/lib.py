@@ -146,6 +146,14 @@ class Lib:
         c.mpeghb200_obj_state_init_dev.restype = i32
         c.mpeghb200_obj_render_dev.argtypes = [vp, vp, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_int, vp]
         c.mpeghb200_obj_render_dev.restype = i32
+        c.mpeghb200_hoa_renderer_create.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int,
+                                                    ctypes.POINTER(vp)]
+        c.mpeghb200_hoa_renderer_create.restype = i32
+        c.mpeghb200_hoa_renderer_destroy.argtypes = [vp]
+        c.mpeghb200_hoa_nfc_state_floats.argtypes = [vp]
+        c.mpeghb200_hoa_nfc_state_floats.restype = sz
+        c.mpeghb200_hoa_render_dev.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, vp]
+        c.mpeghb200_hoa_render_dev.restype = i32
         self.ctx = None
 
     # ---- context ------------------------------------------------------------------------------
@@ -203,6 +211,24 @@ class Lib:
 
     def fd_open(self, n_streams, n_ch):
         return FdSession(self, n_streams, n_ch)
+
+    # ---- HOA renderer ---------------------------------------------------------------------------
+    def hoa_renderer_create(self, matrix, nfc=None, clip=1):
+        m = np.ascontiguousarray(matrix, dtype=np.float32)
+        n = None if nfc is None else np.ascontiguousarray(nfc, dtype=np.float32)
+        h = ctypes.c_void_p()
+        self.check(self.c.mpeghb200_hoa_renderer_create(self.ctx, m.ctypes.data, m.shape[0], m.shape[1],
+                                                        None if n is None else n.ctypes.data, clip, ctypes.byref(h)))
+        return h
+
+    def hoa_renderer_destroy(self, h):
+        self.c.mpeghb200_hoa_renderer_destroy(h)
+
+    def hoa_nfc_state_floats(self, h):
+        return int(self.c.mpeghb200_hoa_nfc_state_floats(h))
+
+    def hoa_render_dev(self, h, d_in, d_out, d_state, n_streams, stream=0):
+        self.check(self.c.mpeghb200_hoa_render_dev(self.ctx, h, d_in, d_out, d_state, n_streams, stream))
 
     # ---- object renderer ------------------------------------------------------------------------
     def obj_layout_create(self, arrays):

@@ -75,6 +75,8 @@ def load_oracle():
     lib.oracle_obj_trig.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
     lib.oracle_obj_gains.argtypes = [ctypes.c_void_p, ctypes.c_void_p, _f32p]
     lib.oracle_obj_render.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _f32p, _f32p]
+    lib.oracle_hoa_render.argtypes = [_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, _f32p,
+                                      ctypes.c_int, ctypes.c_int, _f32p]
     _oracle = lib
     return lib
 
@@ -148,6 +150,14 @@ def load_ref():
     lib.ref_obj_first_flags.argtypes = [ctypes.c_void_p, _i32p, ctypes.c_int]
     lib.ref_obj_render.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int, _f32p, _f32p, _f32p]
     lib.ref_obj_render.restype = ctypes.c_int
+    lib.ref_hoa_ren_create.restype = ctypes.c_void_p
+    lib.ref_hoa_ren_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int,
+                                       ctypes.POINTER(ctypes.c_int)]
+    lib.ref_hoa_ren_destroy.argtypes = [ctypes.c_void_p]
+    lib.ref_hoa_ren_matrix.argtypes = [ctypes.c_void_p, _i32p, _f32p]
+    lib.ref_hoa_ren_nfc_coeffs.argtypes = [ctypes.c_void_p, ctypes.c_int, _f32p]
+    lib.ref_hoa_ren_process.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p]
+    lib.ref_hoa_ren_process.restype = ctypes.c_int
     _ref = lib
     return lib
 
@@ -235,6 +245,28 @@ def oracle_obj_gains(L, side_one):
     fg = np.zeros(OBJ_MAX_LS, np.float32)
     load_oracle().oracle_obj_gains(ctypes.byref(L), ctypes.c_void_p(side_one.ctypes.data), fg)
     return fg[:L.n_non_lfe].copy()
+
+
+# ---- HOA renderer -----------------------------------------------------------------------------------
+def oracle_hoa_render(M, x, nfc=None, nfc_state=None, clip=1):
+    """M [n_out, n_coef], x [n_coef, n]; nfc [n_coef, 17] + nfc_state [n_coef, 14] (advanced in place) or None."""
+    M = np.ascontiguousarray(M, dtype=np.float32)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.zeros((M.shape[0], x.shape[1]), np.float32)
+    load_oracle().oracle_hoa_render(M, M.shape[0], M.shape[1], None if nfc is None else nfc.ctypes.data,
+                                    None if nfc is None else nfc_state.ctypes.data, x, x.shape[1], clip, out)
+    return out
+
+
+def ref_hoa_ren_tables(ref, h, order):
+    info = np.zeros(4, np.int32)
+    m = np.zeros(64 * 64, np.float32)
+    ref.ref_hoa_ren_matrix(h, info, m)
+    n_out, rows, cols = int(info[0]), int(info[1]), int(info[2])
+    nc = (order + 1) ** 2
+    nfc = np.zeros((nc, 17), np.float32)
+    ref.ref_hoa_ren_nfc_coeffs(h, nc, nfc.reshape(-1))
+    return m[:rows * cols].reshape(rows, cols).copy(), nfc, n_out
 
 
 _ref_ns = None
