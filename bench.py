@@ -213,6 +213,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = Lib().create(local_rank)
     stream = torch.cuda.current_stream()
+    # weak scaling: world x 256 streams in total, rank r owns the contiguous block shard.stream_range gives it
+    from libmpegh_b200 import shard
+    s_begin, s_end = shard.stream_range(rank, world, world * STREAMS)
+    assert s_end - s_begin == STREAMS
 
     # ---- device-resident synthetic inputs: G groups of 256 streams (this rank's shard) ----------
     G = max(1, args.groups)

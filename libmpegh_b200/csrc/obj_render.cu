@@ -14,11 +14,10 @@
 //                     state update (previous gains, first-frame flag).  Tiny.
 //   obj_mix_kernel    out[ch][j] = sum_obj in[obj][j] * scale_{obj,ch}(j), scale_{j+1} = scale_j + step.
 //                     The running scale is a chain of separately rounded additions (a closed form drifts by
-//                     an ulp and flips PCM LSBs), so a thread walks time sequentially for its channel, keeping
-//                     the 32 per-object scales in registers.  To get 4x the parallelism each frame is cut into
-//                     four 256-sample quarters; the thread of quarter q first advances its scales by 256 q
-//                     additions (+12.5 % flops on average, exact).  Object sums follow the reference's order
-//                     (object 0 first, starting from the zeroed output buffer).
+//                     an ulp and flips PCM LSBs).  The chain is evaluated once per (object, channel) to get the
+//                     scale at the 16 chunk boundaries; after that the 16 chunks are independent and a thread
+//                     walks its 64 samples with the 32 per-object scales in registers.  Object sums follow the
+//                     reference's order (object 0 first, starting from the zeroed output buffer).
 // Per stream-frame (32 objects -> 7.1.4): reads 32*4096 B, writes 12*4096 B; 1.08 MFLOP of unfused mul/add:
 // at the HBM roofline that is ~36 TFLOP/s of FP32 issue, so this stage is FP-issue bound, not HBM bound.
 #include <cmath>
@@ -40,8 +39,6 @@ namespace {
 constexpr int kMaxLs = MPEGHB200_OBJ_MAX_LS;  // 44
 constexpr int kMaxObj = 32;
 constexpr int kFrame = 1024;
-constexpr int kQuarters = 4;
-constexpr int kQLen = kFrame / kQuarters;
 constexpr float kDeg2Rad = float(M_PI / 180.0f);
 constexpr float kMinVecCtrDist = 0.01f;
 
@@ -197,65 +194,79 @@ __global__ void __launch_bounds__(128)
   st[0] = 0.0f;
 }
 
-// grid (stream groups, 4 quarters); block = streams_per_cta * n_non_lfe threads, thread = (stream, channel)
+// One CTA per stream, thread = (output channel, 64-sample chunk).
+//   phase A  ramp values at the 16 chunk boundaries for every (object, channel): a chain of 64 c separately
+//            rounded additions each, computed once per frame into shared memory (threads stride over pairs)
+//   phase B  the mix: 8 samples at a time, the 32 per-object scales of this thread's channel in registers,
+//            object signals read straight from global memory (each 32-byte piece is shared by the channel
+//            threads of the chunk and served by L1)
+constexpr int kChunks = 16;
+constexpr int kCLen = kFrame / kChunks;  // 64
+
 __global__ void __launch_bounds__(384)
     obj_mix_kernel(const DevLayout* __restrict__ Lp, const float* __restrict__ in, float* __restrict__ out,
-                   const float* __restrict__ scratch, int n_obj, int n_streams, int streams_per_cta) {
+                   const float* __restrict__ scratch, int n_obj) {
+  extern __shared__ float bound[];  // [n_obj * NL][kChunks + 1]: chunk-start scales, last = step
   const DevLayout& L = *Lp;
   const int NL = L.n_non_lfe;
-  const int q = blockIdx.y;
-  const int sl = threadIdx.x / NL, ci = threadIdx.x - sl * NL;
-  const int s = blockIdx.x * streams_per_cta + sl;
-  if (sl >= streams_per_cta || s >= n_streams) return;
-  float scale[kMaxObj], step[kMaxObj];
-  const float* sc = scratch + (size_t(s) * n_obj * NL + ci) * 2;
-#pragma unroll
-  for (int o = 0; o < kMaxObj; ++o) {
-    if (o < n_obj) {
-      const float2 t = __ldg(reinterpret_cast<const float2*>(sc + size_t(o) * NL * 2));
-      scale[o] = t.x;
-      step[o] = t.y;
-    } else {
-      scale[o] = 0.f, step[o] = 0.f;
+  const int s = blockIdx.x;
+  const int n_pairs = n_obj * NL;
+  const float* sc = scratch + size_t(s) * n_pairs * 2;
+  for (int p = threadIdx.x; p < n_pairs; p += blockDim.x) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(sc) + p);
+    float v = t.x;
+    float* b = bound + p * (kChunks + 1);
+    b[kChunks] = t.y;
+    for (int c = 0; c < kChunks; ++c) {
+      b[c] = v;
+#pragma unroll 8
+      for (int k = 0; k < kCLen; ++k) v = fadd(v, t.y);
     }
   }
-  // advance to the start of this quarter: 256 q separately rounded additions per object
-  for (int k = 0; k < q * kQLen; ++k) {
-#pragma unroll
-    for (int o = 0; o < kMaxObj; ++o)
-      if (o < n_obj) scale[o] = fadd(scale[o], step[o]);
-  }
-  const float* x = in + size_t(s) * n_obj * kFrame + q * kQLen;
-  float* y = out + (size_t(s) * L.n_spk + L.nonlfe_to_spk[ci]) * kFrame + q * kQLen;
-  for (int j = 0; j < kQLen; j += 8) {
-    float acc[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+  __syncthreads();
+  const int ci = threadIdx.x % NL, chunk = threadIdx.x / NL;
+  if (chunk < kChunks) {
+    float scale[kMaxObj], step[kMaxObj];
 #pragma unroll
     for (int o = 0; o < kMaxObj; ++o) {
       if (o < n_obj) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(x + size_t(o) * kFrame + j));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(x + size_t(o) * kFrame + j + 4));
-        const float xv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        float sc_o = scale[o];
-        const float st_o = step[o];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          acc[e] = fadd(acc[e], fmul(xv[e], sc_o));
-          sc_o = fadd(sc_o, st_o);
-        }
-        scale[o] = sc_o;
+        const float* b = bound + (o * NL + ci) * (kChunks + 1);
+        scale[o] = b[chunk];
+        step[o] = b[kChunks];
+      } else {
+        scale[o] = 0.f, step[o] = 0.f;
       }
     }
-    __stcs(reinterpret_cast<float4*>(y + j), make_float4(acc[0], acc[1], acc[2], acc[3]));
-    __stcs(reinterpret_cast<float4*>(y + j + 4), make_float4(acc[4], acc[5], acc[6], acc[7]));
-  }
-  // LFE rows stay zero (decode_main.c:1374 memset): the channel-0 threads of quarter q clear them
-  if (ci == 0) {
-    for (int l = 0; l < L.n_lfe; ++l) {
-      float4* z = reinterpret_cast<float4*>(out + (size_t(s) * L.n_spk + L.lfe_spk[l]) * kFrame + q * kQLen);
-      for (int j = 0; j < kQLen / 4; ++j) z[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* x = in + size_t(s) * n_obj * kFrame + chunk * kCLen;
+    float* y = out + (size_t(s) * L.n_spk + L.nonlfe_to_spk[ci]) * kFrame + chunk * kCLen;
+    for (int j = 0; j < kCLen; j += 8) {
+      float acc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+#pragma unroll
+      for (int o = 0; o < kMaxObj; ++o) {
+        if (o < n_obj) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(x + size_t(o) * kFrame + j));
+          const float4 b = __ldg(reinterpret_cast<const float4*>(x + size_t(o) * kFrame + j + 4));
+          const float xv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+          float sc_o = scale[o];
+          const float st_o = step[o];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            acc[e] = fadd(acc[e], fmul(xv[e], sc_o));
+            sc_o = fadd(sc_o, st_o);
+          }
+          scale[o] = sc_o;
+        }
+      }
+      __stcs(reinterpret_cast<float4*>(y + j), make_float4(acc[0], acc[1], acc[2], acc[3]));
+      __stcs(reinterpret_cast<float4*>(y + j + 4), make_float4(acc[4], acc[5], acc[6], acc[7]));
     }
+  }
+  // LFE rows stay zero (decode_main.c:1374 memset)
+  for (int l = 0; l < L.n_lfe; ++l) {
+    float4* z = reinterpret_cast<float4*>(out + (size_t(s) * L.n_spk + L.lfe_spk[l]) * kFrame);
+    for (int j = threadIdx.x; j < kFrame / 4; j += blockDim.x) z[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -400,9 +411,13 @@ mpeghb200_status mpeghb200_obj_render_dev(mpeghb200_ctx* ctx, const mpeghb200_ob
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   const int NL = L->host.n_non_lfe;
-  const int spc = NL <= 12 ? 8 : 4;  // (stream, channel) threads per CTA: 88 for 7.1.4, 88 for 22.2
-  dim3 grid((n_streams + spc - 1) / spc, kQuarters);
-  obj_mix_kernel<<<grid, spc * NL, 0, st>>>(dl, d_in, d_out, d_scratch, n_obj, n_streams, spc);
+  const size_t smem = size_t(n_obj) * NL * (kChunks + 1) * sizeof(float);
+  static size_t configured_smem = 48 * 1024;
+  if (smem > configured_smem) {
+    MB_CUDA(ctx, cudaFuncSetAttribute(obj_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    configured_smem = smem;
+  }
+  obj_mix_kernel<<<n_streams, NL * kChunks, smem, st>>>(dl, d_in, d_out, d_scratch, n_obj);
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   return MPEGHB200_OK;
