@@ -20,6 +20,8 @@
 //   3. post-twiddled samples go to shared memory once more so that windowing, overlap-add and the new
 //      overlap are computed per float4 with fully coalesced 16-byte global accesses.
 // EIGHT_SHORT frames run eight 64-point transforms the same way (4 lanes each).
+#include <type_traits>
+
 #include "common.h"
 
 namespace mpeghb200 {
@@ -262,24 +264,28 @@ __device__ __forceinline__ void window_long(const float* xs, float* __restrict__
 // ---- eight short blocks: windowing_short2/3/4, gather form ---------------------------------------------
 // xs[128k + n] = block k's IMDCT output.  Work positions P in [0, 2048): [0,1024) -> out, [1024,2048) ->
 // new overlap.  See oracle/oracle_fd.c short_blocks() for the derivation of the accumulation order.
-__device__ __forceinline__ float short_rise(const float* xk, const float* w, int t, int tkt) {
-  if (t < 64) return fmul(xk[64 + t], __ldg(w + t));
-  const float v = xk[191 - t];
-  return fmul(tkt == 3 ? v : -v, __ldg(w + t));
-}
-__device__ __forceinline__ float short_fall_val(const float* xk, int t, int tkt) {
-  if (t < 64) {
-    const float v = xk[63 - t];
-    return tkt == 3 ? v : -v;
-  }
-  return -xk[t - 64];
+// A lane's four consecutive work positions always fall on the same window phase t0 = (4 lane + 64) & 127
+// (all region boundaries 448, 576, 1600 are 64 mod 128 and a row of 32 lanes spans exactly 128 positions), so
+// the window entries a lane ever needs are 8 per shape: w[t0..t0+3] and w[127-t0-3..127-t0].
+struct ShortWin {
+  float f[4], r[4];  // f[e] = w[t0 + e], r[e] = w[127 - t0 - e]
+};
+__device__ __forceinline__ ShortWin load_short_win(const float* __restrict__ w, int t0) {
+  const float4 a = ldg4(w + t0), b = ldg4(w + 124 - t0);
+  ShortWin s;
+  s.f[0] = a.x, s.f[1] = a.y, s.f[2] = a.z, s.f[3] = a.w;
+  s.r[0] = b.w, s.r[1] = b.z, s.r[2] = b.y, s.r[3] = b.x;
+  return s;
 }
 
 __device__ void window_short(const float* xs, float* __restrict__ ov, float* __restrict__ out, const Side sd,
                              const DeviceTables& T, int lane) {
-  const float* wc = T.win_short[sd.shape];
-  const float* wp = T.win_short[sd.shape_prev];
   const int tkt = sd.tkt;
+  const int t0 = (4 * lane + 64) & 127;
+  const ShortWin wc = load_short_win(T.win_short[sd.shape], t0);
+  const ShortWin wp = load_short_win(T.win_short[sd.shape_prev], t0);
+  const bool lo = t0 < 64;  // t0 .. t0+3 lie on one side of 64
+#pragma unroll 1
   for (int it = 0; it < 16; ++it) {
     const int P4 = 4 * (lane + 32 * it);
     float v[4];
@@ -291,31 +297,46 @@ __device__ void window_short(const float* xs, float* __restrict__ ov, float* __r
       const float oo[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int t = P4 + e - 448;
+        const int t = t0 + e;
         float a;
-        if (t < 64) {
+        if (lo) {
           a = xs[64 + t];
         } else {
           a = xs[191 - t];
           if (tkt != 3) a = -a;
         }
-        v[e] = mul_add_mul(a, __ldg(wp + t), oo[e], __ldg(wp + 127 - t));
+        v[e] = mul_add_mul(a, wp.f[e], oo[e], wp.r[e]);
       }
     } else if (P4 < 1600) {
       const int k = (P4 - 576) >> 7;
+      const float* xk = xs + 128 * k;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int t = (P4 + e - 576) & 127;
-        const float* xk = xs + 128 * k;
+        const int t = t0 + e;
         float acc;
-        if (k == 0 && tkt == 3 && t < 64) {
-          acc = fmul(xk[63 - t], fadd(__ldg(wc + 127 - t), 0.0f));  // reference quirk, basic_ops.c:404
+        if (k == 0 && tkt == 3 && lo) {
+          acc = fmul(xk[63 - t], fadd(wc.r[e], 0.0f));  // reference quirk, basic_ops.c:404
         } else {
-          float f = short_fall_val(xk, t, tkt);
-          if (k != 7) f = fmul(f, __ldg(wc + 127 - t));
+          float f;  // falling half of block k
+          if (lo) {
+            f = xk[63 - t];
+            if (tkt != 3) f = -f;
+          } else {
+            f = -xk[t - 64];
+          }
+          if (k != 7) f = fmul(f, wc.r[e]);
           acc = fadd(0.0f, f);
         }
-        if (k != 7) acc = fadd(acc, short_rise(xk + 128, wc, t, tkt));
+        if (k != 7) {  // rising half of block k + 1
+          float r;
+          if (lo) {
+            r = xk[128 + 64 + t];
+          } else {
+            r = xk[128 + 191 - t];
+            if (tkt != 3) r = -r;
+          }
+          acc = fadd(acc, fmul(r, wc.f[e]));
+        }
         v[e] = acc;
       }
     } else {
@@ -806,6 +827,109 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_BLOCKS)
   }
 }
 
+// ---- warp-specialised persistent variant -----------------------------------------------------------
+// The three phases become three ROLES that keep their tables in registers for the whole kernel and hand units
+// to each other through a ring of shared-memory slots:
+//   warp 0   A  loads coefficients (next unit's loads in flight while the current one computes), phase_a
+//   warp 1,2 B  phase_b on alternate units (B is the longest phase)
+//   warp 3   C  overlap loads, phase_c / the generic path, all global stores
+// Hand-over uses named barriers in the producer/consumer form (bar.arrive by the producer warp, bar.sync by
+// the consumer warp, 64 participants), one barrier per slot and edge: A->B, B->C and C->A ("slot free").
+// CTAs are persistent: CTA c processes units c, c + gridDim.x, ...
+constexpr int kSlots = 4;
+
+__device__ __forceinline__ void bar_sync64(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void bar_arrive64(int id) {
+  __threadfence_block();  // bar.arrive itself orders nothing: make this warp's shared-memory writes visible first
+  asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory");
+}
+
+__global__ void __launch_bounds__(128, 3)
+    fd_synth_ws_kernel(const float* __restrict__ coef, const uint32_t* __restrict__ side, float* __restrict__ overlap,
+                       float* __restrict__ out, int n_units, const __grid_constant__ DeviceTables T) {
+  __shared__ __align__(16) float slots[kSlots][kBufFloats];
+  __shared__ int fast_flag[kSlots];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int n_local = first < n_units ? (n_units - first + stride - 1) / stride : 0;
+  constexpr int AB = 1, BC = 1 + kSlots, FREE = 1 + 2 * kSlots;  // barrier ids (0 is __syncthreads)
+  if (n_local == 0) return;
+
+  if (warp == 0) {
+    // ---------------- role A ----------------
+    TabA ta;
+    load_tab_a(ta, T, lane);
+    float2 eo[2][16];
+    uint32_t sw[2];
+    sw[0] = __ldg(side + first);
+    load_coef(eo[0], coef + size_t(first) * 1024, lane);
+    auto body = [&](auto cur_c, int i) {
+      constexpr int cur = decltype(cur_c)::value;
+      const int slot = i % kSlots;
+      if (i + 1 < n_local) {
+        const size_t un = size_t(first) + size_t(i + 1) * stride;
+        sw[cur ^ 1] = __ldg(side + un);
+        load_coef(eo[cur ^ 1], coef + un * 1024, lane);
+        if (lane == 0)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(overlap + un * 1024), "r"(4096) : "memory");
+      }
+      if (i >= kSlots) bar_sync64(FREE + slot);
+      const Side sd = unpack_side(sw[cur]);
+      const bool fast = sd.seq != 2 && sd.tkt == 0;
+      if (lane == 0) fast_flag[slot] = fast;
+      if (fast) phase_a(eo[cur], ta, slots[slot], T, lane);
+      bar_arrive64(AB + slot);
+    };
+    if (lane == 0)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(overlap + size_t(first) * 1024), "r"(4096)
+                   : "memory");
+    for (int i = 0; i < n_local; i += 2) {
+      body(std::integral_constant<int, 0>{}, i);
+      if (i + 1 < n_local) body(std::integral_constant<int, 1>{}, i + 1);
+    }
+  } else if (warp <= 2) {
+    // ---------------- role B ----------------
+    TabB tb;
+    load_tab_b(tb, T, lane);
+    for (int i = warp - 1; i < n_local; i += 2) {
+      const int slot = i % kSlots;
+      bar_sync64(AB + slot);
+      if (fast_flag[slot]) phase_b(tb, slots[slot], lane);
+      bar_arrive64(BC + slot);
+    }
+  } else {
+    // ---------------- role C ----------------
+    TabC tc0, tc1;
+    load_tab_c(tc0, T.win_long[0], lane);
+    load_tab_c(tc1, T.win_long[1], lane);
+    for (int i = 0; i < n_local; ++i) {
+      const int slot = i % kSlots;
+      const size_t u = size_t(first) + size_t(i) * stride;
+      const Side sd = unpack_side(__ldg(side + u));
+      float* ov = overlap + u * 1024;
+      float* o = out + u * 1024;
+      const bool fast = sd.seq != 2 && sd.tkt == 0;
+      const bool start_like = (sd.seq == 0 || sd.seq == 1);
+      float4 ovv[8];
+      if (fast && start_like) load_overlap(ovv, ov, lane);  // in flight while we wait for phase B
+      bar_sync64(BC + slot);
+      if (fast) {
+        if (start_like) {
+          if (sd.shape_prev)
+            phase_c(ovv, tc1, slots[slot], ov, o, lane);
+          else
+            phase_c(ovv, tc0, slots[slot], ov, o, lane);
+        } else {
+          phase_c_stop(slots[slot], ov, o, T.win_short[sd.shape_prev], lane);
+        }
+      } else {
+        fd_unit_generic(coef + u * 1024, ov, o, sd, slots[slot], T, lane);
+      }
+      if (i + kSlots < n_local) bar_arrive64(FREE + slot);
+    }
+  }
+}
+
 }  // namespace
 
 template <int B, int WARPS, int MIN_BLOCKS>
@@ -833,11 +957,19 @@ mpeghb200_status fd_synth_launch(mpeghb200_ctx* ctx, const float* d_coef, const 
     case 0: e = launch_variant<3, 1, 14>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables, stream); break;
     case 1: e = launch_variant<3, 2, 7>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables, stream); break;
     case 2: e = launch_variant<4, 1, 12>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables, stream); break;
-    default:
     case 3: e = launch_variant<2, 1, 16>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables, stream); break;
     case 4: e = launch_variant<2, 2, 10>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables, stream); break;
     case 5: e = launch_variant<1, 4, 8>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables, stream); break;
     case 6: e = launch_variant<6, 1, 7>(d_coef, d_side, d_overlap, d_out, n_units, ctx->tables, stream); break;
+    default:
+    case 7:
+    case 8: {
+      const int ctas = ctx->sm_count * (ctx->fd_variant == 7 ? 3 : 2);
+      fd_synth_ws_kernel<<<n_units < ctas ? n_units : ctas, 128, 0, stream>>>(d_coef, d_side, d_overlap, d_out, n_units,
+                                                                            ctx->tables);
+      e = cudaGetLastError();
+      break;
+    }
   }
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, e);
