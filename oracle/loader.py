@@ -77,6 +77,15 @@ def load_oracle():
     lib.oracle_obj_render.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _f32p, _f32p]
     lib.oracle_hoa_render.argtypes = [_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, _f32p,
                                       ctypes.c_int, ctypes.c_int, _f32p]
+    lib.oracle_cplx_fft_pow2.argtypes = [_f32p, _f32p, ctypes.c_int]
+    for f in (lib.oracle_cplx_ifft_big, lib.oracle_cplx_fft_big):
+        f.argtypes = [_f32p, _f32p, ctypes.c_int]
+        f.restype = ctypes.c_int
+    lib.oracle_binaural_spectrum.argtypes = [_f32p, ctypes.c_int, ctypes.c_int, _f32p]
+    lib.oracle_binaural_spectrum.restype = ctypes.c_int
+    lib.oracle_binaural_block.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p, _f32p, _i32p, _i32p, _f32p,
+                                          _f32p, _i32p, _f32p, _f32p, _f32p]
+    lib.oracle_binaural_block.restype = ctypes.c_int
     _oracle = lib
     return lib
 
@@ -158,6 +167,16 @@ def load_ref():
     lib.ref_hoa_ren_nfc_coeffs.argtypes = [ctypes.c_void_p, ctypes.c_int, _f32p]
     lib.ref_hoa_ren_process.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p]
     lib.ref_hoa_ren_process.restype = ctypes.c_int
+    lib.ref_cplx_ifft_8k.argtypes = [_f32p, _f32p, ctypes.c_int]
+    lib.ref_cplx_fft_16k.argtypes = [_f32p, _f32p, ctypes.c_int]
+    lib.ref_bin_create.restype = ctypes.c_void_p
+    lib.ref_bin_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p, _f32p, _f32p, _f32p, _f32p,
+                                   ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    lib.ref_bin_destroy.argtypes = [ctypes.c_void_p]
+    lib.ref_bin_info.argtypes = [ctypes.c_void_p, _i32p]
+    lib.ref_bin_spectra.argtypes = [ctypes.c_void_p, _f32p, _f32p, _i32p, _i32p]
+    lib.ref_bin_process.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int, _f32p, ctypes.c_int]
+    lib.ref_bin_process.restype = ctypes.c_int
     _ref = lib
     return lib
 
@@ -295,3 +314,58 @@ def bits_equal(a, b):
     a = np.ascontiguousarray(a, dtype=np.float32)
     b = np.ascontiguousarray(b, dtype=np.float32)
     return a.shape == b.shape and bool(np.array_equal(a.view(np.uint32), b.view(np.uint32)))
+
+
+# ---- binaural renderer ------------------------------------------------------------------------------
+class OracleBinaural:
+    """Per-stream state + filter spectra of the oracle's binaural renderer (oracle_binaural.c)."""
+
+    def __init__(self, taps_direct, taps_diffuse, direct_fc, diffuse_fc, weight):
+        """taps_direct [2, n_in, len], taps_diffuse [n_blocks, 2, len], direct_fc [2, n_in], diffuse_fc [2, n_blocks]"""
+        lib = load_oracle()
+        self.n_in, self.len = taps_direct.shape[1], taps_direct.shape[2]
+        self.n_blocks = taps_diffuse.shape[0]
+        fft = 2
+        while fft < 2 * self.len:
+            fft <<= 1
+        self.fft, self.B = fft, fft // 2
+        self.h_direct = np.zeros((2, self.n_in, fft), np.float32)
+        self.h_diffuse = np.zeros((max(self.n_blocks, 1), 2, fft), np.float32)
+        for o in range(2):
+            for i in range(self.n_in):
+                assert lib.oracle_binaural_spectrum(np.ascontiguousarray(taps_direct[o, i], np.float32),
+                                                    min(self.len, self.B), fft, self.h_direct[o, i]) == 0
+        for b in range(self.n_blocks):
+            for o in range(2):
+                assert lib.oracle_binaural_spectrum(np.ascontiguousarray(taps_diffuse[b, o], np.float32),
+                                                    min(self.len, self.B), fft, self.h_diffuse[b, o]) == 0
+        self.direct_len = (np.minimum(np.asarray(direct_fc, np.float32), np.float32(1.0)) *
+                           np.float32(self.B)).astype(np.int32).reshape(2, self.n_in).copy()
+        self.diffuse_len = np.zeros((max(self.n_blocks, 1), 2), np.int32)
+        if self.n_blocks:
+            dl = (np.minimum(np.asarray(diffuse_fc, np.float32), np.float32(1.0)) * np.float32(self.B)).astype(np.int32)
+            self.diffuse_len[:self.n_blocks] = dl.reshape(2, self.n_blocks).T
+        self.weight = np.ascontiguousarray(weight, np.float32)
+        self.reset()
+
+    def reset(self):
+        self.prev_in = np.zeros((self.n_blocks + 1, self.fft), np.float32)
+        self.tail = np.zeros((2, self.B), np.float32)
+        self.write_idx = np.zeros(1, np.int32)
+
+    def clone_state(self):
+        import copy
+        c = copy.copy(self)
+        c.reset()
+        return c
+
+    def block(self, x):
+        """x [n_in, B] -> [2, B]"""
+        x = np.ascontiguousarray(x, np.float32)
+        out = np.zeros((2, self.B), np.float32)
+        rc = load_oracle().oracle_binaural_block(self.fft, self.n_in, self.n_blocks, self.h_direct.reshape(-1),
+                                                 self.h_diffuse.reshape(-1), self.direct_len.reshape(-1),
+                                                 self.diffuse_len.reshape(-1), self.weight, self.prev_in.reshape(-1),
+                                                 self.write_idx, self.tail.reshape(-1), x.reshape(-1), out.reshape(-1))
+        assert rc == 0
+        return out

@@ -13,6 +13,7 @@
 
 static oracle_rom g_rom;
 void oracle_set_rom(const oracle_rom *rom) { g_rom = *rom; }
+const oracle_rom *oracle_get_rom(void) { return &g_rom; }
 
 /* ------------------------------------------------------------------------------------------------
  * Complex transform, n = 2^lg.  Follows impeghd_rad2_cplx_ifft (impeghd_ifft.c:297-843):
