@@ -215,6 +215,45 @@ size_t mpeghb200_hoa_nfc_state_floats(const mpeghb200_hoa_renderer *r);
 mpeghb200_status mpeghb200_hoa_render_dev(mpeghb200_ctx *ctx, const mpeghb200_hoa_renderer *r, const float *d_in,
                                           float *d_out, float *d_nfc_state, int n_streams, void *cuda_stream);
 
+/* ---- binaural renderer: FFT overlap-add fast convolution -----------------------------------------------
+ * Replaces impeghd_binaural_struct_process_ld_ola (decoder/impeghd_binaural_renderer.c:543) and the filter
+ * preparation of impeghd_binaural_renderer_init / impeghd_binaural_struct_set (:346, :244), including the long
+ * transforms impeghd_cplx_ifft_8k / impeghd_cplx_fft_16k (decoder/impeghd_ifft.c:1264, impeghd_fft.c:1415).
+ *
+ * create: the members of ia_td_binaural_ren_param_str (decoder/impeghd_binaural.h:76-87) after the BRIR
+ * parameterisation, for n_sets independent filter sets (1 = every stream shares one BRIR set):
+ *   taps_direct [set][2][n_in][len_direct], taps_diffuse [set][n_diffuse_blocks][2][len_direct],
+ *   direct_fc [set][2][n_in], diffuse_fc [set][2][n_diffuse_blocks], inv_diffuse_weight [set][n_in].
+ * The transform length N is the smallest power of two >= 2 * len_direct; N = 2048 and N = 8192 are supported
+ * (the reference's own N = 4096 and N = 16384 e^{+j} transforms read outside their rows / lack the column
+ * stage: MPEGHB200_ERR_UNSUPPORTED).  A block is B = N/2 samples per input.
+ *
+ * block_dev: one block for every stream.  d_in layout 0 = [stream][n_in][B]; layout 1 = [B/1024][stream][n_in][1024]
+ * (B/1024 consecutive decoder frames stacked, what the reference accumulates in input_mem_buf).  Inputs are
+ * multiplied by in_scale (1/32768: ia_div_q15_flt at decoder/ia_core_coder_decode_main.c:2833) and outputs by
+ * out_scale (32768, :2851); pass 1.0f for the renderer's own +-1 domain.  d_out [stream][2][B].
+ * d_state [stream][mpeghb200_binaural_state_floats], zero-initialised by the caller, holds the overlap tail,
+ * the diffuse downmix ring and its write index.  d_filter_set [stream] selects the set per stream (NULL: set 0).
+ * With 2 diffuse blocks the reference indexes prev_in_buf[2][..] out of bounds; this library keeps a 3-slot
+ * ring instead (0 and 1 diffuse blocks are bit-identical to the reference). */
+typedef struct mpeghb200_binaural mpeghb200_binaural;
+mpeghb200_status mpeghb200_binaural_create(mpeghb200_ctx *ctx, int n_in, int len_direct, int n_diffuse_blocks,
+                                           int n_sets, const float *taps_direct, const float *taps_diffuse,
+                                           const float *direct_fc, const float *diffuse_fc,
+                                           const float *inv_diffuse_weight, mpeghb200_binaural **out);
+void mpeghb200_binaural_destroy(mpeghb200_binaural *b);
+int mpeghb200_binaural_block_len(const mpeghb200_binaural *b);
+size_t mpeghb200_binaural_state_floats(const mpeghb200_binaural *b);
+/* Host copies of the prepared filter spectra in the reference's packed format (taps_direct / taps_diffuse of
+ * ia_binaural_ren_pers_mem_str): h_direct [set][2][n_in][N], h_diffuse [set][n_diffuse_blocks][2][N]; either
+ * may be NULL. */
+mpeghb200_status mpeghb200_binaural_spectra(mpeghb200_ctx *ctx, const mpeghb200_binaural *b, float *h_direct,
+                                            float *h_diffuse);
+mpeghb200_status mpeghb200_binaural_block_dev(mpeghb200_ctx *ctx, const mpeghb200_binaural *b, const float *d_in,
+                                              int in_layout, float in_scale, float out_scale, float *d_out,
+                                              float *d_state, const int32_t *d_filter_set, int n_streams,
+                                              void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

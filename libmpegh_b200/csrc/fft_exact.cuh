@@ -1,0 +1,242 @@
+// fft_exact.cuh -- CTA-level 1024 x DIM2 point complex transforms with the reference's exact rounding sequence.
+//
+// Mirrors impeghd_rad2_cplx_ifft / impeghd_rad2_cplx_fft for n = 1024 (decoder/impeghd_ifft.c:297,
+// decoder/impeghd_fft.c:297) and the 1024 x {2, 8} decompositions built on them, impeghd_cplx_ifft_8k
+// (impeghd_ifft.c:1264) and impeghd_cplx_fft_16k (impeghd_fft.c:1415): DIM2 row transforms over the
+// decimated input, inter-stage twiddle, DIM2-point column transform, transposed output.  INV = true is the
+// e^{+j} ("ifft") family, INV = false the e^{-j} ("fft") family.  The two differ by conjugate-mirrored
+// product forms and by the first pass of the e^{-j} transform forming a - 2b as (a - b) - b.
+//
+// Work layout: DIM2 rows of 1024 float2 in shared memory, element p of a row at phys(p) = p + p/16, rows
+// kRowStride float2 apart (both paddings make every access pattern below bank-conflict free).  A CTA has
+// 64 * DIM2 threads; each thread owns 16 points per stage:
+//   stage A  passes 0 + 1 of the radix-4 DIT in registers (reads digit-reversed positions r3(g) + 64 t)
+//   stage B  passes 2 + 3 (elements base + 16 t)
+//   stage C  pass 4, four butterflies per thread
+//   columns  16 / DIM2 columns per thread: twiddle + DIM2-point transform in registers
+#pragma once
+#include "common.h"
+
+namespace mpeghb200 {
+namespace fftx {
+
+constexpr int kRowStride = 1090;  // float2 units; 1024 + 63 padding, == 2 mod 16
+
+__device__ __forceinline__ int phys(int p) { return p + (p >> 4); }
+
+// a - 2b and a + 2b in the two forms the reference uses
+template <bool TWO_STEP>
+__device__ __forceinline__ float m2(float a, float b) {
+  return TWO_STEP ? fsub(fsub(a, b), b) : sub2(a, b);
+}
+template <bool TWO_STEP>
+__device__ __forceinline__ float p2(float a, float b) {
+  return TWO_STEP ? fadd(fadd(a, b), b) : add2(a, b);
+}
+
+// x *= (c -/+ j s): INV (r*c + i*s, -(r*s) + i*c), else (r*c - i*s, r*s + i*c)
+template <bool INV>
+__device__ __forceinline__ void rot(float2& x, float c, float s) {
+  float nr, ni;
+  if (INV) {
+    nr = fadd(fmul(x.x, c), fmul(x.y, s));
+    ni = fadd(-fmul(x.x, s), fmul(x.y, c));
+  } else {
+    nr = fsub(fmul(x.x, c), fmul(x.y, s));
+    ni = fadd(fmul(x.x, s), fmul(x.y, c));
+  }
+  x = make_float2(nr, ni);
+}
+
+// Radix-4 butterfly, "a += b; b = a - 2b" form; outputs in natural order a, b, c, d.
+template <bool INV, bool TWO_STEP>
+__device__ __forceinline__ void bfly(float2& a, float2& b, float2& c, float2& d) {
+  float x0r = a.x, x0i = a.y, x1r = b.x, x1i = b.y, x2r = c.x, x2i = c.y, x3r = d.x, x3i = d.y;
+  x0r = fadd(x0r, x2r);
+  x0i = fadd(x0i, x2i);
+  x2r = m2<TWO_STEP>(x0r, x2r);
+  x2i = m2<TWO_STEP>(x0i, x2i);
+  x1r = fadd(x1r, x3r);
+  x1i = fadd(x1i, x3i);
+  x3r = m2<TWO_STEP>(x1r, x3r);
+  x3i = m2<TWO_STEP>(x1i, x3i);
+  x0r = fadd(x0r, x1r);
+  x0i = fadd(x0i, x1i);
+  x1r = m2<TWO_STEP>(x0r, x1r);
+  x1i = m2<TWO_STEP>(x0i, x1i);
+  float dr, di;
+  if (INV) {
+    x2r = fsub(x2r, x3i);
+    x2i = fadd(x2i, x3r);
+    dr = p2<TWO_STEP>(x2r, x3i);
+    di = m2<TWO_STEP>(x2i, x3r);
+  } else {
+    x2r = fadd(x2r, x3i);
+    x2i = fsub(x2i, x3r);
+    dr = m2<TWO_STEP>(x2r, x3i);
+    di = p2<TWO_STEP>(x2i, x3r);
+  }
+  a = make_float2(x0r, x0i);
+  b = make_float2(x2r, x2i);
+  c = make_float2(x1r, x1i);
+  d = make_float2(dr, di);
+}
+
+// Twiddled butterfly; j = index into the effective-twiddle table (DeviceTables::eff8), j == 0 means the
+// reference multiplies nothing.
+template <bool INV>
+__device__ __forceinline__ void bfly_tw(float2& a, float2& b, float2& c, float2& d, const float4* __restrict__ eff8,
+                                        int j) {
+  if (j) {
+    const float4 e0 = __ldg(eff8 + 2 * j), e1 = __ldg(eff8 + 2 * j + 1);
+    rot<INV>(b, e0.x, e0.y);
+    rot<INV>(c, e0.z, e0.w);
+    rot<INV>(d, e1.x, e1.y);
+  }
+  bfly<INV, false>(a, b, c, d);
+}
+
+// ---- stage A: passes 0 and 1 on v[t], t = q + 4 i (butterfly q, input i) -> y[16 g + e] in v[e] -----------
+template <bool INV>
+__device__ __forceinline__ void stage_a(float2 (&v)[16], const float4* __restrict__ eff8) {
+  float2 y[16];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float2 a = v[q], b = v[q + 4], c = v[q + 8], d = v[q + 12];
+    bfly<INV, !INV>(a, b, c, d);
+    y[4 * q + 0] = a, y[4 * q + 1] = b, y[4 * q + 2] = c, y[4 * q + 3] = d;
+  }
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    float2 a = y[m], b = y[m + 4], c = y[m + 8], d = y[m + 12];
+    bfly_tw<INV>(a, b, c, d, eff8, 64 * m);
+    v[m] = a, v[m + 4] = b, v[m + 8] = c, v[m + 12] = d;
+  }
+}
+
+// ---- stage B: passes 2 and 3 on v[t] = y[base + 16 t], t = a + 4 q; mm = base & 15 ------------------------
+template <bool INV>
+__device__ __forceinline__ void stage_b(float2 (&v)[16], const float4* __restrict__ eff8, int mm) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) bfly_tw<INV>(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3], eff8, 16 * mm);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) bfly_tw<INV>(v[a], v[a + 4], v[a + 8], v[a + 12], eff8, 4 * (mm + 16 * a));
+}
+
+// 8-point column transforms (decoder/impeghd_ifft.c:1118 with its swapped bins 2 and 6 kept,
+// decoder/impeghd_fft.c:1304)
+template <bool INV>
+__device__ __forceinline__ void col8(float (&xr)[8], float (&xi)[8]) {
+  const float s = 0.7071067811f;
+  float ar = fadd(xr[0], xr[4]), ai = fadd(xi[0], xi[4]), br = fsub(xr[0], xr[4]), bi = fsub(xi[0], xi[4]);
+  float cr = fadd(xr[2], xr[6]), ci = fadd(xi[2], xi[6]), dr = fsub(xr[2], xr[6]), di = fsub(xi[2], xi[6]);
+  float n00 = fadd(ar, cr), n01 = fadd(ai, ci), n20 = fsub(ar, cr), n21 = fsub(ai, ci);
+  float n10, n11, n30, n31;
+  if (INV) {
+    n10 = fsub(br, di), n11 = fadd(bi, dr), n30 = fadd(br, di), n31 = fsub(bi, dr);
+  } else {
+    n10 = fadd(br, di), n11 = fsub(bi, dr), n30 = fsub(br, di), n31 = fadd(bi, dr);
+  }
+  ar = fadd(xr[1], xr[5]), ai = fadd(xi[1], xi[5]), br = fsub(xr[1], xr[5]), bi = fsub(xi[1], xi[5]);
+  cr = fadd(xr[3], xr[7]), ci = fadd(xi[3], xi[7]), dr = fsub(xr[3], xr[7]), di = fsub(xi[3], xi[7]);
+  float e0 = fadd(ar, cr), e1 = fadd(ai, ci), e4 = fsub(ar, cr), e5 = fsub(ai, ci);
+  float e2, e3, e6, e7;
+  if (INV) {
+    e2 = fsub(br, di), e3 = fadd(bi, dr), e6 = fadd(br, di), e7 = fsub(bi, dr);
+    const float t0 = fmul(fsub(e2, e3), s), t1 = fmul(fadd(e3, e2), s);
+    e2 = t0, e3 = t1;
+    const float t2 = fmul(fadd(e6, e7), -s), t3 = fmul(fsub(e6, e7), s);
+    e6 = t2, e7 = t3;
+  } else {
+    e2 = fadd(br, di), e3 = fsub(bi, dr), e6 = fsub(br, di), e7 = fadd(bi, dr);
+    const float t0 = fmul(fadd(e2, e3), s), t1 = fmul(fsub(e3, e2), s);
+    e2 = t0, e3 = t1;
+    const float t2 = fmul(fsub(e7, e6), s), t3 = fmul(fadd(e6, e7), -s);
+    e6 = t2, e7 = t3;
+    const float t4 = e4;
+    e4 = e5;
+    e5 = -t4;
+  }
+  xr[0] = fadd(n00, e0), xi[0] = fadd(n01, e1);
+  xr[1] = fadd(n10, e2), xi[1] = fadd(n11, e3);
+  xr[3] = fadd(n30, e6), xi[3] = fadd(n31, e7);
+  xr[4] = fsub(n00, e0), xi[4] = fsub(n01, e1);
+  xr[5] = fsub(n10, e2), xi[5] = fsub(n11, e3);
+  xr[7] = fsub(n30, e6), xi[7] = fsub(n31, e7);
+  if (INV) {
+    xr[2] = fsub(n21, e4), xi[2] = fadd(n20, e5);
+    xr[6] = fadd(n21, e4), xi[6] = fsub(n20, e5);
+  } else {
+    xr[2] = fadd(n20, e4), xi[2] = fadd(n21, e5);
+    xr[6] = fsub(n20, e4), xi[6] = fsub(n21, e5);
+  }
+}
+
+// The row transforms (stages A..C) of all DIM2 rows, in place.  Entry: work holds the rows in natural order,
+// preceded by a __syncthreads() issued by the caller.  Exit: rows transformed, __syncthreads() issued.
+template <int DIM2, bool INV>
+__device__ __forceinline__ void rows_1024(float2* __restrict__ work, const float4* __restrict__ eff8) {
+  const int tid = threadIdx.x;
+  const int r = tid >> 6, g = tid & 63;
+  float2* row = work + r * kRowStride;
+  float2 v[16];
+  {
+    // digit-reversed read: butterfly b = 4g + q reads r3(g) + 64 q + 256 i
+    const int r3 = ((g & 3) << 4) | (g & 12) | (g >> 4);
+#pragma unroll
+    for (int t = 0; t < 16; ++t) v[t] = row[phys(r3 + 64 * t)];
+    __syncthreads();
+    stage_a<INV>(v, eff8);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) row[phys(16 * g + e)] = v[e];
+    __syncthreads();
+  }
+  {
+    const int base = 256 * (g >> 4) + (g & 15);
+#pragma unroll
+    for (int t = 0; t < 16; ++t) v[t] = row[phys(base + 16 * t)];
+    stage_b<INV>(v, eff8, g & 15);
+#pragma unroll
+    for (int t = 0; t < 16; ++t) row[phys(base + 16 * t)] = v[t];
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int w = tid + 64 * DIM2 * u;
+    float2* rw = work + (w >> 8) * kRowStride;
+    const int m = w & 255;
+    float2 a = rw[phys(m)], b = rw[phys(m + 256)], c = rw[phys(m + 512)], d = rw[phys(m + 768)];
+    bfly_tw<INV>(a, b, c, d, eff8, m);
+    rw[phys(m)] = a, rw[phys(m + 256)] = b, rw[phys(m + 512)] = c, rw[phys(m + 768)] = d;
+  }
+  __syncthreads();
+}
+
+// Column i of the transformed rows: inter-stage twiddle (mix[j * 1024 + i] = (cos, sin) of 2 pi i j / N)
+// and the DIM2-point transform.  Output k = j * 1024 + i in (xr[j], xi[j]).
+template <int DIM2, bool INV>
+__device__ __forceinline__ void column(const float2* __restrict__ work, const float2* __restrict__ mix, int i,
+                                       float (&xr)[DIM2], float (&xi)[DIM2]) {
+#pragma unroll
+  for (int j = 0; j < DIM2; ++j) {
+    const float2 v = work[j * kRowStride + phys(i)];
+    const float2 cs = __ldg(mix + j * 1024 + i);
+    if (INV) {
+      xr[j] = fsub(fmul(v.x, cs.x), fmul(v.y, cs.y));
+      xi[j] = fadd(fmul(v.x, cs.y), fmul(v.y, cs.x));
+    } else {
+      xr[j] = fadd(fmul(v.x, cs.x), fmul(v.y, cs.y));
+      xi[j] = fsub(fmul(v.y, cs.x), fmul(v.x, cs.y));
+    }
+  }
+  if constexpr (DIM2 == 8) {
+    col8<INV>(xr, xi);
+  } else {
+    static_assert(DIM2 == 2, "column transforms exist for 2 and 8 rows");
+    const float a = fadd(xr[0], xr[1]), b = fsub(xr[0], xr[1]), c = fadd(xi[0], xi[1]), d = fsub(xi[0], xi[1]);
+    xr[0] = a, xr[1] = b, xi[0] = c, xi[1] = d;
+  }
+}
+
+}  // namespace fftx
+}  // namespace mpeghb200

@@ -154,6 +154,19 @@ class Lib:
         c.mpeghb200_hoa_nfc_state_floats.restype = sz
         c.mpeghb200_hoa_render_dev.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, vp]
         c.mpeghb200_hoa_render_dev.restype = i32
+        c.mpeghb200_binaural_create.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp,
+                                                vp, vp, ctypes.POINTER(vp)]
+        c.mpeghb200_binaural_create.restype = i32
+        c.mpeghb200_binaural_destroy.argtypes = [vp]
+        c.mpeghb200_binaural_block_len.argtypes = [vp]
+        c.mpeghb200_binaural_block_len.restype = ctypes.c_int
+        c.mpeghb200_binaural_state_floats.argtypes = [vp]
+        c.mpeghb200_binaural_state_floats.restype = sz
+        c.mpeghb200_binaural_spectra.argtypes = [vp, vp, vp, vp]
+        c.mpeghb200_binaural_spectra.restype = i32
+        c.mpeghb200_binaural_block_dev.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_float, ctypes.c_float, vp, vp,
+                                                   vp, ctypes.c_int, vp]
+        c.mpeghb200_binaural_block_dev.restype = i32
         self.ctx = None
 
     # ---- context ------------------------------------------------------------------------------
@@ -229,6 +242,46 @@ class Lib:
 
     def hoa_render_dev(self, h, d_in, d_out, d_state, n_streams, stream=0):
         self.check(self.c.mpeghb200_hoa_render_dev(self.ctx, h, d_in, d_out, d_state, n_streams, stream))
+
+    # ---- binaural renderer -----------------------------------------------------------------------
+    def binaural_create(self, taps_direct, taps_diffuse, direct_fc, diffuse_fc, weight):
+        """taps_direct [n_sets, 2, n_in, len], taps_diffuse [n_sets, n_blocks, 2, len], direct_fc [n_sets, 2, n_in],
+        diffuse_fc [n_sets, 2, n_blocks], weight [n_sets, n_in] (a missing leading n_sets axis means one set)."""
+        td = np.ascontiguousarray(taps_direct, dtype=np.float32)
+        if td.ndim == 3:
+            td = td[None]
+        n_sets, _, n_in, length = td.shape
+        tf = np.ascontiguousarray(taps_diffuse, dtype=np.float32).reshape(n_sets, -1, 2, length)
+        nb = tf.shape[1]
+        dfc = np.ascontiguousarray(direct_fc, dtype=np.float32).reshape(n_sets, 2, n_in)
+        ffc = np.ascontiguousarray(diffuse_fc, dtype=np.float32).reshape(n_sets, 2, nb)
+        w = np.ascontiguousarray(weight, dtype=np.float32).reshape(n_sets, n_in)
+        h = ctypes.c_void_p()
+        self.check(self.c.mpeghb200_binaural_create(self.ctx, n_in, length, nb, n_sets, td.ctypes.data,
+                                                    tf.ctypes.data if nb else None, dfc.ctypes.data,
+                                                    ffc.ctypes.data if nb else None, w.ctypes.data, ctypes.byref(h)))
+        return h
+
+    def binaural_destroy(self, h):
+        self.c.mpeghb200_binaural_destroy(h)
+
+    def binaural_block_len(self, h):
+        return int(self.c.mpeghb200_binaural_block_len(h))
+
+    def binaural_state_floats(self, h):
+        return int(self.c.mpeghb200_binaural_state_floats(h))
+
+    def binaural_spectra(self, h, n_sets, n_in, n_blocks):
+        n = 2 * self.binaural_block_len(h)
+        d = np.zeros((n_sets, 2, n_in, n), np.float32)
+        f = np.zeros((n_sets, max(n_blocks, 1), 2, n), np.float32)
+        self.check(self.c.mpeghb200_binaural_spectra(self.ctx, h, d.ctypes.data, f.ctypes.data if n_blocks else None))
+        return d, f
+
+    def binaural_block_dev(self, h, d_in, d_out, d_state, n_streams, layout=0, in_scale=1.0, out_scale=1.0,
+                           d_set=None, stream=0):
+        self.check(self.c.mpeghb200_binaural_block_dev(self.ctx, h, d_in, layout, in_scale, out_scale, d_out, d_state,
+                                                       d_set, n_streams, stream))
 
     # ---- object renderer ------------------------------------------------------------------------
     def obj_layout_create(self, arrays):
