@@ -86,6 +86,9 @@ def load_oracle():
     lib.oracle_binaural_block.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p, _f32p, _i32p, _i32p, _f32p,
                                           _f32p, _i32p, _f32p, _f32p, _f32p]
     lib.oracle_binaural_block.restype = ctypes.c_int
+    lib.oracle_hoasp_state_init.argtypes = [ctypes.c_void_p]
+    lib.oracle_hoasp_process.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _f32p, _f32p]
+    lib.oracle_hoasp_process.restype = ctypes.c_int
     _oracle = lib
     return lib
 
@@ -177,6 +180,12 @@ def load_ref():
     lib.ref_bin_spectra.argtypes = [ctypes.c_void_p, _f32p, _f32p, _i32p, _i32p]
     lib.ref_bin_process.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int, _f32p, ctypes.c_int]
     lib.ref_bin_process.restype = ctypes.c_int
+    lib.ref_hoasp_create.restype = ctypes.c_void_p
+    lib.ref_hoasp_create.argtypes = [_i32p, ctypes.POINTER(ctypes.c_int)]
+    lib.ref_hoasp_destroy.argtypes = [ctypes.c_void_p]
+    lib.ref_hoasp_tables.argtypes = [ctypes.c_void_p, _i32p] + [_f32p] * 7
+    lib.ref_hoasp_process.argtypes = [ctypes.c_void_p, ctypes.c_void_p, _f32p, _f32p]
+    lib.ref_hoasp_process.restype = ctypes.c_int
     _ref = lib
     return lib
 
@@ -367,5 +376,55 @@ class OracleBinaural:
                                                  self.h_diffuse.reshape(-1), self.direct_len.reshape(-1),
                                                  self.diffuse_len.reshape(-1), self.weight, self.prev_in.reshape(-1),
                                                  self.write_idx, self.tail.reshape(-1), x.reshape(-1), out.reshape(-1))
+        assert rc == 0
+        return out
+
+
+# ---- HOA spatial decoder ------------------------------------------------------------------------------
+HOASP_TABLE_KEYS = ("order_matrix", "fine", "coarse", "wins", "dyn_pow", "dyn_win", "pow2")
+
+
+def ref_hoasp_tables(ref, h):
+    """Tables designed by the reference init -> dict (info = low_order_mat_sz, vec_start, n_coef, 0)."""
+    t = {"info": np.zeros(4, np.int32), "order_matrix": np.zeros(49 * 49, np.float32),
+         "fine": np.zeros(900 * 49, np.float32), "coarse": np.zeros(49 * 49, np.float32),
+         "wins": np.zeros(4 * 1024, np.float32), "dyn_pow": np.zeros(7 * 1024, np.float32),
+         "dyn_win": np.zeros(1024, np.float32), "pow2": np.zeros(128, np.float32)}
+    ref.ref_hoasp_tables(h, t["info"], *[t[k] for k in HOASP_TABLE_KEYS])
+    return t
+
+
+class OracleHoaspTables(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in ("n_coef", "n_transport", "n_addnl", "low_order", "vec_start",
+                                            "coded_v_vec_length", "spat_interp_time", "pred_dir_sigs",
+                                            "num_bits_per_sf", "use_phase_shift_decorr")] + \
+               [(n, ctypes.POINTER(ctypes.c_float)) for n in HOASP_TABLE_KEYS]
+
+
+class OracleHoasp:
+    """oracle_hoasp.c: one stream's spatial decoder (tables from the reference init or the golden fixture)."""
+    STATE_BYTES = 4 * (16 + 16 + 4 + 16 + 16 + 17 + 17 + 49 + 4 * 49 + 4 * 49 + 16 * 49)
+
+    def __init__(self, cfg, tables):
+        self.cfg, self.t = cfg, {k: np.ascontiguousarray(v) for k, v in tables.items()}
+        tb = OracleHoaspTables()
+        tb.n_coef = (cfg[0] + 1) ** 2
+        tb.n_transport, tb.n_addnl = cfg[1], cfg[2]
+        tb.low_order, tb.vec_start = int(self.t["info"][0]), int(self.t["info"][1])
+        tb.coded_v_vec_length, tb.spat_interp_time, tb.pred_dir_sigs, tb.num_bits_per_sf = cfg[4], cfg[5], cfg[7], cfg[8]
+        tb.use_phase_shift_decorr = cfg[9]
+        for k in HOASP_TABLE_KEYS:
+            setattr(tb, k, self.t[k].ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+        self.tb = tb
+        self.n_coef = tb.n_coef
+        self.state = ctypes.create_string_buffer(self.STATE_BYTES)
+        load_oracle().oracle_hoasp_state_init(self.state)
+
+    def process(self, side, x):
+        x = np.ascontiguousarray(x, np.float32)
+        out = np.zeros((self.n_coef, 1024), np.float32)
+        side = np.ascontiguousarray(side)
+        rc = load_oracle().oracle_hoasp_process(ctypes.byref(self.tb), self.state, side.ctypes.data, x.reshape(-1),
+                                                out.reshape(-1))
         assert rc == 0
         return out

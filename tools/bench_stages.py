@@ -49,6 +49,45 @@ def report(name, ms, bytes_per_step, units, unit_name, extra=None):
     print(json.dumps(line), flush=True)
 
 
+ONLY = sys.argv[1] if len(sys.argv) > 1 else ""
+
+
+def binaural_stage():
+    """config 4: 22.2 -> 2 ears, 4096-tap BRIRs, 1024 streams; per-stream filter sets and one shared set."""
+    import bin_cases
+    S, n_in, L = 1024, 24, 4096
+    rng = np.random.default_rng(3456)
+    for label, n_sets, nb in (("per-stream filters", S, 0), ("per-stream filters, 1 diffuse block", S, 1),
+                              ("shared filters", 1, 0)):
+        env = np.exp(-6.0 * np.arange(L) / L).astype(np.float32)
+        td = rng.standard_normal((n_sets, 2, n_in, L), dtype=np.float32) * np.float32(0.2) * env
+        tf = rng.standard_normal((n_sets, nb, 2, L), dtype=np.float32) * np.float32(0.02) * env
+        h = lib.binaural_create(td, tf, np.ones((n_sets, 2, n_in), np.float32), np.ones((n_sets, 2, nb), np.float32),
+                                np.ones((n_sets, n_in), np.float32))
+        del td, tf
+        B = lib.binaural_block_len(h)
+        x = torch.randn(S, n_in, B, device="cuda") * 0.1
+        y = torch.empty(S, 2, B, device="cuda")
+        state = torch.zeros(S * lib.binaural_state_floats(h), device="cuda")
+        sets = torch.arange(S, dtype=torch.int32, device="cuda") % n_sets
+        ms = timeit(lambda i: lib.binaural_block_dev(h, x.data_ptr(), y.data_ptr(), state.data_ptr(), S, 0, 1.0, 1.0,
+                                                     sets.data_ptr(), st), steps=10, warmup=2)
+        N = 2 * B
+        per_unit = n_in * B * 4 + 2 * B * 4 + 2 * 2 * B * 4 + (2 * n_in * N * 4 if n_sets > 1 else 0) + \
+            nb * (2 * N * 4 * (n_sets > 1) + 2 * N * 4)
+        report(f"binaural 22.2 -> 2, 4096 taps, 1024 streams, {label}", ms, S * per_unit, S * n_in * B,
+               "input_channel_samples", {"stream_blocks_per_s": S / (ms * 1e-3),
+                                         "audio_s_per_wall_s": S * B / 48000.0 / (ms * 1e-3),
+                                         "algorithmic_bytes_per_unit": per_unit})
+        lib.binaural_destroy(h)
+        del x, y, state
+
+
+if ONLY == "binaural":
+    binaural_stage()
+    lib.close()
+    sys.exit(0)
+
 # ---- config 5: 32 objects -> 7.1.4 (512 streams per GPU) + limiter + 24-bit PCM --------------------------
 S, O = 512, 32
 lay = lib.obj_layout_create(loader.obj_layout_golden(19))
@@ -98,4 +137,5 @@ for use_nfc in (1, 0):
     report(f"hoa_render order 4 -> 22.2, 1024 streams, nfc={use_nfc}", ms, S * (25 + 24) * 4096, S * 24 * 1024,
            "output_channel_samples", {"fp32_unfused_Gops": S * 24 * 25 * 1024 * 2 / (ms * 1e-3) / 1e9})
     lib.hoa_renderer_destroy(h)
+binaural_stage()
 lib.close()
