@@ -254,6 +254,74 @@ mpeghb200_status mpeghb200_binaural_block_dev(mpeghb200_ctx *ctx, const mpeghb20
                                               float *d_state, const int32_t *d_filter_set, int n_streams,
                                               void *cuda_stream);
 
+/* ---- HOA spatial decoding: transport channels -> HOA coefficient signals ----------------------------------
+ * Replaces the signal half of impeghd_hoa_spatial_process (decoder/impeghd_hoa_spatial_decoder.c:663): inverse
+ * dynamic correction (impeghd_hoa_inverse_dyn_correction.c:75), ambience synthesis (impeghd_hoa_amb_syn.c:76),
+ * channel reassignment (impeghd_hoa_ch_reassignment.c:71), vector-based and direction-based predominant sound
+ * synthesis incl. spatial prediction (impeghd_hoa_vector_based_predom_sound_syn.c:76,
+ * impeghd_hoa_dir_based_pre_dom_sound_syn.c:145-605).  The bitstream side, impeghd_hoa_frame and
+ * impeghd_hoa_spatial_decode_frame_side_info (:291), stays host code; what it leaves in
+ * ia_hoa_dec_frame_param_str (decoder/impeghd_hoa_frame_params.h:38-62) is handed over per frame as one
+ * mpeghb200_hoa_spatial_side per stream.  Copy the arrays whole: the reference itself reads slots beyond the
+ * current counts (stale entries of vectors[].index and of active_and_grid_dir_indices[]).
+ *
+ * desc: after impeghd_hoa_spatial_init (:154) copy from ia_spatial_dec_str / ia_hoa_config_struct
+ *   order, n_transport = num_transport_ch, n_addnl_coders = num_addnl_coders,
+ *   low_order_mat_sz = amb_syn_handle.low_order_mat_sz, vec_start, coded_v_vec_length,
+ *   spat_interp_time = spat_interpolation_time, pred_dir_sigs, num_bits_per_sf, use_phase_shift_decorr (must be 0),
+ *   order_matrix            = amb_syn_handle.order_matrix                      [low][low]
+ *   fine_grid_mode_matrix   = transpose_mod_mtx_grid_pts                       [900][49]
+ *   coarse_grid_mode_matrix = ...dir_based_pre_dom_sound_syn_handle.mode_mt_all_coarse_grid_points [n_coef][n_coef]
+ *   fade_windows            = fade_in_win_for_vec_sigs, fade_out_win_for_vec_sigs, fade_in_win_for_dir_sigs,
+ *                             fade_out_win_for_dir_sigs                        [4][1024]
+ *   dyn_win_pow_table       = ia_hoa_inv_dyn_win_pow_table                     [7][1024]
+ *   dyn_win_func            = inv_dyn_corr_win_func                            [1024]
+ *   pow2_table              = impeghd_hoa_pow_2(0..63), impeghd_hoa_pow_2(-0..-63)  [128] (the reference's
+ *                             negative-power table is a decimal literal, exact only down to 2^-17)
+ * Results are bit-identical to the reference except for gain-correction exponents beyond +-6, where the
+ * reference evaluates double-precision pow() per sample (device pow: <= 1 ulp of the float result). */
+#define MPEGHB200_HOASP_MAX_CH 16
+#define MPEGHB200_HOASP_MAX_COEF 49
+#define MPEGHB200_HOASP_MAX_PRED 4
+typedef struct mpeghb200_hoa_spatial_side {
+  int32_t n_vec, n_dir, n_enable, n_disable; /* num_vec/dir_predom_sounds, num_enable/disable_coeff */
+  int32_t exponents[MPEGHB200_HOASP_MAX_CH];
+  int32_t is_exception[MPEGHB200_HOASP_MAX_CH];
+  float prev_gain_reset[MPEGHB200_HOASP_MAX_CH]; /* hoa_independency_flag: pow_2(gain_corr_prev_amp_exp), else 0 */
+  int32_t amb_hoa_assign[MPEGHB200_HOASP_MAX_CH];
+  int32_t vec_index[MPEGHB200_HOASP_MAX_CH];     /* vectors[].index, all 16 slots */
+  int32_t dir_ch[MPEGHB200_HOASP_MAX_CH + 1];    /* active_and_grid_dir_indices[0..16].ch_idx */
+  int32_t dir_id[MPEGHB200_HOASP_MAX_CH + 1];
+  int32_t pad0[2];
+  int32_t enable[MPEGHB200_HOASP_MAX_COEF];      /* amb_coeff_indices_to_enable (sorted, -1 padded) */
+  int32_t disable[MPEGHB200_HOASP_MAX_COEF];
+  int32_t non_en_dis[MPEGHB200_HOASP_MAX_COEF];  /* non_en_dis_able_act_hoa_coeff_indices */
+  int32_t pred_type[MPEGHB200_HOASP_MAX_COEF];
+  int32_t pred_idx[MPEGHB200_HOASP_MAX_PRED][MPEGHB200_HOASP_MAX_COEF];   /* prediction_indices_mat[r * n_coef + g] */
+  int32_t pred_quant[MPEGHB200_HOASP_MAX_PRED][MPEGHB200_HOASP_MAX_COEF]; /* quant_pred_fact_mat */
+  float vec[MPEGHB200_HOASP_MAX_CH][MPEGHB200_HOASP_MAX_COEF];            /* vectors[].sig_id */
+} mpeghb200_hoa_spatial_side;
+typedef struct mpeghb200_hoa_spatial_desc {
+  int32_t order, n_transport, n_addnl_coders, low_order_mat_sz, vec_start, coded_v_vec_length, spat_interp_time,
+      pred_dir_sigs, num_bits_per_sf, use_phase_shift_decorr;
+  const float *order_matrix, *fine_grid_mode_matrix, *coarse_grid_mode_matrix, *fade_windows, *dyn_win_pow_table,
+      *dyn_win_func, *pow2_table;
+} mpeghb200_hoa_spatial_desc;
+typedef struct mpeghb200_hoa_spatial mpeghb200_hoa_spatial;
+mpeghb200_status mpeghb200_hoa_spatial_create(mpeghb200_ctx *ctx, const mpeghb200_hoa_spatial_desc *desc,
+                                              mpeghb200_hoa_spatial **out);
+void mpeghb200_hoa_spatial_destroy(mpeghb200_hoa_spatial *h);
+int mpeghb200_hoa_spatial_num_coeffs(const mpeghb200_hoa_spatial *h);
+/* Per-stream device state (what ia_spatial_dec_str carries between frames + per-frame scratch), in bytes. */
+size_t mpeghb200_hoa_spatial_state_bytes(const mpeghb200_hoa_spatial *h);
+mpeghb200_status mpeghb200_hoa_spatial_state_init_dev(mpeghb200_ctx *ctx, const mpeghb200_hoa_spatial *h,
+                                                      void *d_state, int n_streams, void *cuda_stream);
+/* d_side [stream] (device), d_in [stream][n_transport][1024] (perceptually decoded transport signals),
+ * d_out [stream][n_coef][1024]. */
+mpeghb200_status mpeghb200_hoa_spatial_dev(mpeghb200_ctx *ctx, const mpeghb200_hoa_spatial *h,
+                                           const mpeghb200_hoa_spatial_side *d_side, const float *d_in, float *d_out,
+                                           void *d_state, int n_streams, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,6 +69,15 @@ class ObjLayoutDesc(ctypes.Structure):
         return d
 
 
+class HoaSpatialDesc(ctypes.Structure):
+    """mpeghb200_hoa_spatial_desc"""
+    _fields_ = [(n, ctypes.c_int32) for n in ("order", "n_transport", "n_addnl_coders", "low_order_mat_sz",
+                                              "vec_start", "coded_v_vec_length", "spat_interp_time", "pred_dir_sigs",
+                                              "num_bits_per_sf", "use_phase_shift_decorr")] + \
+               [(n, ctypes.c_void_p) for n in ("order_matrix", "fine_grid_mode_matrix", "coarse_grid_mode_matrix",
+                                               "fade_windows", "dyn_win_pow_table", "dyn_win_func", "pow2_table")]
+
+
 OBJ_SIDE_DTYPE = np.dtype([("vec_c", np.float32, 3), ("gain", np.float32), ("spread_w", np.float32),
                            ("spread_h", np.float32), ("tan_alpha", np.float32), ("pad0", np.float32),
                            ("p0", np.float32, 3), ("pad1", np.float32), ("v", np.float32, 3), ("pad2", np.float32)])
@@ -167,6 +176,17 @@ class Lib:
         c.mpeghb200_binaural_block_dev.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_float, ctypes.c_float, vp, vp,
                                                    vp, ctypes.c_int, vp]
         c.mpeghb200_binaural_block_dev.restype = i32
+        c.mpeghb200_hoa_spatial_create.argtypes = [vp, ctypes.POINTER(HoaSpatialDesc), ctypes.POINTER(vp)]
+        c.mpeghb200_hoa_spatial_create.restype = i32
+        c.mpeghb200_hoa_spatial_destroy.argtypes = [vp]
+        c.mpeghb200_hoa_spatial_num_coeffs.argtypes = [vp]
+        c.mpeghb200_hoa_spatial_num_coeffs.restype = ctypes.c_int
+        c.mpeghb200_hoa_spatial_state_bytes.argtypes = [vp]
+        c.mpeghb200_hoa_spatial_state_bytes.restype = sz
+        c.mpeghb200_hoa_spatial_state_init_dev.argtypes = [vp, vp, vp, ctypes.c_int, vp]
+        c.mpeghb200_hoa_spatial_state_init_dev.restype = i32
+        c.mpeghb200_hoa_spatial_dev.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
+        c.mpeghb200_hoa_spatial_dev.restype = i32
         self.ctx = None
 
     # ---- context ------------------------------------------------------------------------------
@@ -242,6 +262,42 @@ class Lib:
 
     def hoa_render_dev(self, h, d_in, d_out, d_state, n_streams, stream=0):
         self.check(self.c.mpeghb200_hoa_render_dev(self.ctx, h, d_in, d_out, d_state, n_streams, stream))
+
+    # ---- HOA spatial decoder ---------------------------------------------------------------------
+    def hoa_spatial_create(self, cfg, tables):
+        """cfg = (order, n_transport, n_addnl, min_amb_order, coded_v_vec_length, spat_interp_time, interp_method,
+        pred_dir_sigs, num_bits_per_sf, use_phase_shift_decorr); tables: dict with info = (low_order_mat_sz,
+        vec_start, ..) and the float tables named as in mpeghb200_hoa_spatial_desc's comment."""
+        d = HoaSpatialDesc()
+        d.order, d.n_transport, d.n_addnl_coders = cfg[0], cfg[1], cfg[2]
+        d.low_order_mat_sz, d.vec_start = int(tables["info"][0]), int(tables["info"][1])
+        d.coded_v_vec_length, d.spat_interp_time, d.pred_dir_sigs, d.num_bits_per_sf = cfg[4], cfg[5], cfg[7], cfg[8]
+        d.use_phase_shift_decorr = cfg[9]
+        keep = []
+        for field, key in (("order_matrix", "order_matrix"), ("fine_grid_mode_matrix", "fine"),
+                           ("coarse_grid_mode_matrix", "coarse"), ("fade_windows", "wins"),
+                           ("dyn_win_pow_table", "dyn_pow"), ("dyn_win_func", "dyn_win"), ("pow2_table", "pow2")):
+            a = np.ascontiguousarray(tables[key], dtype=np.float32)
+            keep.append(a)
+            setattr(d, field, a.ctypes.data)
+        h = ctypes.c_void_p()
+        self.check(self.c.mpeghb200_hoa_spatial_create(self.ctx, ctypes.byref(d), ctypes.byref(h)))
+        return h
+
+    def hoa_spatial_destroy(self, h):
+        self.c.mpeghb200_hoa_spatial_destroy(h)
+
+    def hoa_spatial_state_bytes(self, h):
+        return int(self.c.mpeghb200_hoa_spatial_state_bytes(h))
+
+    def hoa_spatial_num_coeffs(self, h):
+        return int(self.c.mpeghb200_hoa_spatial_num_coeffs(h))
+
+    def hoa_spatial_state_init_dev(self, h, d_state, n_streams, stream=0):
+        self.check(self.c.mpeghb200_hoa_spatial_state_init_dev(self.ctx, h, d_state, n_streams, stream))
+
+    def hoa_spatial_dev(self, h, d_side, d_in, d_out, d_state, n_streams, stream=0):
+        self.check(self.c.mpeghb200_hoa_spatial_dev(self.ctx, h, d_side, d_in, d_out, d_state, n_streams, stream))
 
     # ---- binaural renderer -----------------------------------------------------------------------
     def binaural_create(self, taps_direct, taps_diffuse, direct_fc, diffuse_fc, weight):

@@ -132,3 +132,14 @@ class SideGen:
 
 def signals(rng, n_frames, T, sigma=2000.0):
     return rng.normal(0.0, sigma, size=(n_frames, T, 1024)).astype(np.float32)
+
+
+def golden_tables(g, cfg):
+    """Tables of one configuration from tests/golden/hoasp_golden.npz, re-expanded to the strides the API takes."""
+    k = key(cfg)
+    nc = (cfg[0] + 1) ** 2
+    fine = np.zeros((900, 49), np.float32)
+    fine[:, :nc] = g[k + "_fine"]
+    return {"info": g[k + "_info"], "order_matrix": g[k + "_order_matrix"], "fine": fine.reshape(-1),
+            "coarse": g[k + "_coarse"], "wins": g[k + "_wins"], "dyn_pow": g["dyn_pow"], "dyn_win": g["dyn_win"],
+            "pow2": g["pow2"]}

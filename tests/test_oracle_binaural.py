@@ -119,3 +119,14 @@ def test_binaural_vs_reference(ref, oracle, n_in, length, nb, cut):
     for t in range(T):
         assert bits_equal(o.block(x[t]), got_ref[t]), (t,)
     ref.ref_bin_destroy(h)
+
+
+def test_binaural_golden(oracle):
+    """Committed vectors from the reference build (tests/golden/make_binaural_golden.py); no reference needed."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "binaural_golden.npz"))
+    for tag in ("a", "b"):
+        o = loader.OracleBinaural(g[f"{tag}_taps_direct"], g[f"{tag}_taps_diffuse"], g[f"{tag}_direct_fc"],
+                                  g[f"{tag}_diffuse_fc"], g[f"{tag}_weight"])
+        for t in range(g[f"{tag}_in"].shape[0]):
+            assert bits_equal(o.block(g[f"{tag}_in"][t]), g[f"{tag}_out"][t]), (tag, t)

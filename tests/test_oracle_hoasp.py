@@ -40,3 +40,15 @@ def test_spatial_vs_reference(ref, oracle, cfg):
     if cfg[2] >= 4:
         assert {"n_vec", "n_dir", "n_enable", "n_disable", "pred"} <= seen, seen
     ref.ref_hoasp_destroy(h)
+
+
+def test_hoasp_golden(oracle):
+    """Committed vectors from the reference build (tests/golden/make_hoasp_golden.py); no reference needed."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "hoasp_golden.npz"))
+    for cfg in hoasp_cases.CONFIGS[:3]:
+        k = hoasp_cases.key(cfg)
+        o = loader.OracleHoasp(cfg, hoasp_cases.golden_tables(g, cfg))
+        sides = g[k + "_sides"].view(hoasp_cases.SIDE_DTYPE).reshape(-1)
+        for f in range(len(sides)):
+            assert bits_equal(o.process(sides[f:f + 1], g[k + "_in"][f]), g[k + "_out"][f]), (k, f)
