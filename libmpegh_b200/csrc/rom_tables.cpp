@@ -91,6 +91,15 @@ std::vector<float> generate(RomId id) {
     }
     case ROM_SINE_1024: t = sine_window(1024); break;
     case ROM_SINE_128: t = sine_window(128); break;
+    case ROM_SINE_256: {  // this one is printed with eight decimals (decoder/ia_core_coder_avq_rom.c:539)
+      t.resize(256);
+      for (int i = 0; i < 256; ++i) {
+        char buf[48];
+        std::snprintf(buf, sizeof(buf), "%.8f", std::sin(kPi * (i + 0.5) / 512.0));
+        t[i] = std::strtof(buf, nullptr);
+      }
+      break;
+    }
     case ROM_KBD_1024: t = kbd_window(1024, 4.0); break;
     case ROM_KBD_128: t = kbd_window(128, 6.0); break;
     case ROM_MIXED_RAD_COS:
@@ -146,7 +155,7 @@ const char* rom_name(RomId id) {
   static const char* names[ROM_COUNT] = {"fft_twiddle",    "twid_cos_512",   "twid_sin_512", "twid_cos_64",
                                          "twid_sin_64",    "dctdst_cos_1024", "dctdst_sin_1024",
                                          "sine_1024",      "sine_128",       "kbd_1024",     "kbd_128",
-                                         "mixed_rad_cos",  "mixed_rad_sin"};
+                                         "mixed_rad_cos",  "mixed_rad_sin",  "sine_256"};
   return (id >= 0 && id < ROM_COUNT) ? names[id] : "?";
 }
 

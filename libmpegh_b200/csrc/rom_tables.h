@@ -27,6 +27,7 @@ enum RomId : int {
   ROM_KBD_128 = 10,      // ia_core_coder_kbd_window128
   ROM_MIXED_RAD_COS = 11,  // ia_mixed_rad_twiddle_cos[16384]      impeghd_fft_ifft_rom.c:1122
   ROM_MIXED_RAD_SIN = 12,  // ia_mixed_rad_twiddle_sin[16384]      impeghd_fft_ifft_rom.c:4401
+  ROM_SINE_256 = 13,       // ia_core_coder_sine_window256 (format converter STFT window)
   ROM_COUNT
 };
 

@@ -20,6 +20,7 @@ _f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 _u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
 
+ROM_EXTRA = ["sine_256"]  # in the fixture, not part of oracle_rom
 ROM_FIELDS = [
     "fft_twiddle", "twid_cos_512", "twid_sin_512", "twid_cos_64", "twid_sin_64", "dctdst_cos_1024",
     "dctdst_sin_1024", "sine_1024", "sine_128", "kbd_1024", "kbd_128", "mixed_rad_cos", "mixed_rad_sin",
@@ -89,6 +90,8 @@ def load_oracle():
     lib.oracle_hoasp_state_init.argtypes = [ctypes.c_void_p]
     lib.oracle_hoasp_process.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _f32p, _f32p]
     lib.oracle_hoasp_process.restype = ctypes.c_int
+    lib.oracle_fc_state_init.argtypes = [ctypes.c_void_p]
+    lib.oracle_fc_process.argtypes = [_f32p, ctypes.c_int, ctypes.c_int, _f32p, ctypes.c_void_p, _f32p, _f32p]
     _oracle = lib
     return lib
 
@@ -186,6 +189,14 @@ def load_ref():
     lib.ref_hoasp_tables.argtypes = [ctypes.c_void_p, _i32p] + [_f32p] * 7
     lib.ref_hoasp_process.argtypes = [ctypes.c_void_p, ctypes.c_void_p, _f32p, _f32p]
     lib.ref_hoasp_process.restype = ctypes.c_int
+    lib.ref_fc_create.restype = ctypes.c_void_p
+    lib.ref_fc_create.argtypes = [ctypes.c_int] * 3 + [ctypes.POINTER(ctypes.c_int)]
+    lib.ref_fc_destroy.argtypes = [ctypes.c_void_p]
+    lib.ref_fc_info.argtypes = [ctypes.c_void_p, _i32p]
+    lib.ref_fc_get_matrix.argtypes = [ctypes.c_void_p, _f32p]
+    lib.ref_fc_set_matrix.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _f32p]
+    lib.ref_fc_process.argtypes = [ctypes.c_void_p, _f32p, _f32p]
+    lib.ref_fc_process.restype = ctypes.c_int
     _ref = lib
     return lib
 
@@ -428,3 +439,37 @@ class OracleHoasp:
                                                 out.reshape(-1))
         assert rc == 0
         return out
+
+
+# ---- format converter ---------------------------------------------------------------------------------
+FC_STATE_BYTES = 4 * 24 * (256 + 256 + 58 + 58)
+
+
+class OracleFc:
+    """oracle_fc.c: one stream's format converter; D [n_out, n_in, 257] from the reference init / golden fixture."""
+
+    def __init__(self, D):
+        self.D = np.ascontiguousarray(D, np.float32)
+        self.n_out, self.n_in = self.D.shape[:2]
+        self.win = np.ascontiguousarray(golden_rom()["sine_256"], np.float32)
+        self.state = ctypes.create_string_buffer(FC_STATE_BYTES)
+        load_oracle().oracle_fc_state_init(self.state)
+
+    def process(self, x):
+        x = np.ascontiguousarray(x, np.float32)
+        out = np.zeros((self.n_out, 1024), np.float32)
+        load_oracle().oracle_fc_process(self.D.reshape(-1), self.n_in, self.n_out, self.win, self.state, x.reshape(-1),
+                                        out.reshape(-1))
+        return out
+
+
+def ref_fc_new(ref, cicp_in, cicp_out, sample_rate=48000):
+    """-> (handle, D [n_out, n_in, 257]) designed by the reference init"""
+    err = ctypes.c_int()
+    h = ref.ref_fc_create(cicp_in, cicp_out, sample_rate, ctypes.byref(err))
+    assert err.value == 0, hex(err.value & 0xFFFFFFFF)
+    info = np.zeros(2, np.int32)
+    ref.ref_fc_info(h, info)
+    D = np.zeros((int(info[1]), int(info[0]), 257), np.float32)
+    ref.ref_fc_get_matrix(h, D.reshape(-1))
+    return h, D

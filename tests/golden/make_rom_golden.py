@@ -37,6 +37,7 @@ TABLES = {
     "sine_128": ("ia_core_coder_sine_window128", ctypes.c_float, 128),
     "kbd_1024": ("ia_core_coder_kbd_win1024", ctypes.c_float, 1024),
     "kbd_128": ("ia_core_coder_kbd_window128", ctypes.c_float, 128),
+    "sine_256": ("ia_core_coder_sine_window256", ctypes.c_float, 256),
 }
 
 
