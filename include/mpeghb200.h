@@ -322,6 +322,23 @@ mpeghb200_status mpeghb200_hoa_spatial_dev(mpeghb200_ctx *ctx, const mpeghb200_h
                                            const mpeghb200_hoa_spatial_side *d_side, const float *d_in, float *d_out,
                                            void *d_state, int n_streams, void *cuda_stream);
 
+/* ---- format converter: STFT-domain active downmix ------------------------------------------------------
+ * Replaces impeghd_format_converter_process (decoder/ia_core_coder_process.c:641) and
+ * impeghd_format_conv_active_dmx_stft_process (:127).  The frequency-dependent downmix tensor is designed by
+ * the reference's host init (impeghd_format_conv_init, decoder/ia_core_coder_decode_main.c:519) and handed over:
+ *   dmx [n_out][n_in][257] = fc_params->active_dmx_stft->downmix_mat[out][in][band].
+ * d_in [stream][n_in][1024] -> d_out [stream][n_out][1024] (the reference converts in place in
+ * time_sample_vector; here input and output are separate buffers).  d_state
+ * [stream][mpeghb200_format_conv_state_floats], zero-initialised by the caller: STFT input/output memories
+ * (stft_input_buf, stft_output_buf) and the smoothed ERB-band energies (target/realized_energy_prev). */
+typedef struct mpeghb200_format_conv mpeghb200_format_conv;
+mpeghb200_status mpeghb200_format_conv_create(mpeghb200_ctx *ctx, int n_in, int n_out, const float *dmx,
+                                              mpeghb200_format_conv **out);
+void mpeghb200_format_conv_destroy(mpeghb200_format_conv *h);
+size_t mpeghb200_format_conv_state_floats(const mpeghb200_format_conv *h);
+mpeghb200_status mpeghb200_format_conv_dev(mpeghb200_ctx *ctx, const mpeghb200_format_conv *h, const float *d_in,
+                                           float *d_out, float *d_state, int n_streams, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,372 @@
+// format_conv.cu -- format converter: STFT-domain active downmix with ERB-band energy equalisation.
+//
+// Stands in for impeghd_format_converter_process (decoder/ia_core_coder_process.c:641) and
+// impeghd_format_conv_active_dmx_stft_process (:127).  Per frame and stream, 4 slots of 256 samples:
+//   1. every input channel: sine-windowed [previous 256 | current 256] block -> 512-point e^{+j} transform
+//   2. Y[out] = sum_in D[out][in][band] * X[in] over the inputs whose D[out][in][0] != 0, in input order;
+//      target energy (sum of |D X|^2) and realised energy (|Y|^2) per ERB band, one-pole smoothing against the
+//      previous slot, EQ = sqrt(target / (1e-35 + realised)) clipped to [-10 dB, +8 dB], Y *= EQ
+//   3. every output channel: Hermitian extension -> 512-point e^{-j} transform -> /512 -> windowed overlap-add.
+// The downmix tensor D comes from the reference's host init (impeghd_format_conv_init_data or its VBAP
+// fallback, decoder/ia_core_coder_decode_main.c:519) and is handed over.
+//
+// One CTA (12 warps) per stream walks the four slots; spectra never leave shared memory.  A warp owns one
+// 512-point transform (16 points per lane, same exact radix-4 DAG as fft_exact.cuh plus the final radix-2 pass).
+// The energy sums are strictly sequential float chains in the reference; they are cut where the reference's
+// data flow allows it: one chain per (output, ERB band), 58 x n_out chains running side by side, while the
+// spectrum accumulation itself runs per (output, bin).  Rounding order within every chain is the reference's.
+// HBM traffic per stream-frame: (n_in + n_out) * 4 KB of audio + (n_in + n_out) * 1 KB + n_out * 464 B of state.
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "fft_exact.cuh"
+
+namespace mpeghb200 {
+namespace {
+
+using namespace fftx;
+
+constexpr int kMaxFcCh = 24;
+constexpr int kErb = 58;
+constexpr int kWarps = 12;
+constexpr int kBufStride = 544;  // float2: 512 + 512/16 padding
+constexpr float kAlpha = 0.0435f;
+constexpr float kBeta = (1 - kAlpha);
+constexpr float kEps = 1e-35f;
+constexpr float kEqMax = 2.51188636f;
+constexpr float kEqMin = 0.316227764f;
+
+__constant__ int c_erb_stop[kErb] = {1,  2,  3,  4,  5,  6,  7,   8,   9,   10,  11,  12,  13,  14,  15,
+                                     16, 17, 18, 19, 20, 21, 22,  23,  24,  25,  26,  27,  28,  29,  30,
+                                     31, 32, 33, 36, 39, 43, 47,  51,  55,  60,  65,  70,  77,  84,  91,
+                                     98, 106, 115, 125, 136, 148, 160, 174, 189, 205, 222, 241, 256};
+__constant__ unsigned char c_erb_of_bin[256];
+
+struct FcParams {
+  const float* in;   // [stream][n_in][1024]
+  float* out;        // [stream][n_out][1024]
+  float* state;      // [stream][state_floats]: in_prev [n_in][256], out_prev [n_out][256], t_prev, r_prev [n_out][58]
+  const float* D;    // [n_out][n_in][257]
+  const int* active;  // [n_out][1 + n_in]: count, then input indices with D[out][in][0] != 0
+  const float* win;  // [256]
+  const float4* eff8;
+  const float2* rad2;
+  int n_in, n_out, state_floats;
+};
+
+// 512-point transform of one warp's buffer (natural order in, natural order out).
+template <bool INV>
+__device__ __forceinline__ void fft512_warp(float2* __restrict__ buf, int lane, const float4* __restrict__ eff8,
+                                            const float2* __restrict__ rad2) {
+  float2 v[16];
+  {
+    const int r3 = 8 * (lane & 3) + 2 * ((lane >> 2) & 3) + (lane >> 4);
+#pragma unroll
+    for (int t = 0; t < 16; ++t) v[t] = buf[phys(r3 + 32 * t)];
+    __syncwarp();
+    stage_a<INV>(v, eff8);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) buf[phys(16 * lane + e)] = v[e];
+    __syncwarp();
+  }
+  {
+    const int base = 256 * (lane >> 4) + (lane & 15);
+#pragma unroll
+    for (int t = 0; t < 16; ++t) v[t] = buf[phys(base + 16 * t)];
+    stage_b<INV>(v, eff8, lane & 15);
+#pragma unroll
+    for (int t = 0; t < 16; ++t) buf[phys(base + 16 * t)] = v[t];
+    __syncwarp();
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int i = lane + 32 * u;
+    const float2 x0 = buf[phys(i)];
+    float2 t = buf[phys(i + 256)];
+    const float2 cs = __ldg(rad2 + i);
+    rot<INV>(t, cs.x, cs.y);
+    buf[phys(i + 256)] = make_float2(fsub(x0.x, t.x), fsub(x0.y, t.y));
+    buf[phys(i)] = make_float2(fadd(x0.x, t.x), fadd(x0.y, t.y));
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ float clip_eq(float t, float r) {
+  float eq = __fsqrt_rn(__fdiv_rn(t, fadd(kEps, r)));
+  return eq > kEqMax ? kEqMax : (eq < kEqMin ? kEqMin : eq);
+}
+
+__global__ void __launch_bounds__(kWarps * 32) format_conv_kernel(const __grid_constant__ FcParams P) {
+  extern __shared__ float smem[];
+  float2* work = reinterpret_cast<float2*>(smem);                       // [kWarps][kBufStride]
+  float* X = smem + 2 * kWarps * kBufStride;                            // [n_in][512] packed spectra
+  float* Y = X + P.n_in * 512;                                          // [n_out][512]
+  float* outprev = Y + P.n_out * 512;                                   // [n_out][256]
+  float* eqs = outprev + P.n_out * 256;                                 // [n_out][58]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t s = blockIdx.x;
+  const float* x = P.in + s * size_t(P.n_in) * 1024;
+  float* yo = P.out + s * size_t(P.n_out) * 1024;
+  float* st_in = P.state + s * size_t(P.state_floats);
+  float* st_out = st_in + P.n_in * 256;
+  float* st_t = st_out + P.n_out * 256;
+  float* st_r = st_t + P.n_out * kErb;
+  float2* buf = work + warp * kBufStride;
+
+  for (int i = tid; i < P.n_out * 256; i += blockDim.x) outprev[i] = st_out[i];
+  float wv[8], wr[8];  // window entries of the lane's sample positions i = lane + 32 u
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    wv[u] = __ldg(P.win + lane + 32 * u);
+    wr[u] = __ldg(P.win + 255 - lane - 32 * u);
+  }
+  // per (output, ERB band) chains owned by this thread: smoothed energies carried in registers across slots
+  constexpr int kChains = 4;  // ceil(24 * 58 / 384)
+  float tprev[kChains], rprev[kChains];
+  const int n_chain = P.n_out * kErb;
+#pragma unroll
+  for (int q = 0; q < kChains; ++q) {
+    const int c = tid + q * blockDim.x;
+    tprev[q] = (c < n_chain) ? st_t[c] : 0.0f;
+    rprev[q] = (c < n_chain) ? st_r[c] : 0.0f;
+  }
+  __syncthreads();
+
+  for (int slot = 0; slot < 4; ++slot) {
+    // ---- 1. input transforms ------------------------------------------------------------------------
+    for (int ci = warp; ci < P.n_in; ci += kWarps) {
+      const float* cur = x + size_t(ci) * 1024 + slot * 256;
+      const float* prev = slot ? cur - 256 : st_in + ci * 256;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = lane + 32 * u;
+        buf[phys(i)] = make_float2(fmul(prev[i], wv[u]), 0.0f);
+        buf[phys(256 + i)] = make_float2(fmul(wr[u], cur[i]), 0.0f);
+      }
+      __syncwarp();
+      fft512_warp<true>(buf, lane, P.eff8, P.rad2);
+      float2* Xc = reinterpret_cast<float2*>(X + ci * 512);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = lane + 32 * u;
+        float2 v = buf[phys(k)];
+        if (k == 0) v.y = buf[phys(256)].x;
+        Xc[k] = v;
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- 2a. spectrum accumulation per (output, bin); k == 0 carries the (DC, Nyquist) pair ------------
+    for (int item = tid; item < P.n_out * 256; item += blockDim.x) {
+      const int co = item >> 8, k = item & 255;
+      const int* act = P.active + co * (1 + P.n_in);
+      const int na = act[0];
+      float yr = 0.0f, yi = 0.0f;
+      for (int a = 0; a < na; ++a) {
+        const int ci = act[1 + a];
+        const float* d = P.D + (size_t(co) * P.n_in + ci) * 257;
+        const float2 xv = reinterpret_cast<const float2*>(X + ci * 512)[k];
+        const float d0 = __ldg(d + k), d1 = (k == 0) ? __ldg(d + 256) : d0;
+        yr = fadd(fmul(d0, xv.x), yr);
+        yi = fadd(fmul(d1, xv.y), yi);
+      }
+      reinterpret_cast<float2*>(Y + co * 512)[k] = make_float2(yr, yi);
+    }
+    // ---- 2b. target energy chains per (output, ERB band), same order as the reference: inputs outermost
+    float tcur[kChains];
+#pragma unroll
+    for (int q = 0; q < kChains; ++q) {
+      const int c = tid + q * blockDim.x;
+      float t = 0.0f;
+      if (c < n_chain) {
+        const int co = c / kErb, erb = c - co * kErb;
+        const int* act = P.active + co * (1 + P.n_in);
+        const int na = act[0];
+        const int k0 = (erb == 0) ? 256 : (erb == 1 ? 1 : c_erb_stop[erb - 1]);
+        const int k1 = (erb == 0) ? 256 : c_erb_stop[erb];
+        for (int a = 0; a < na; ++a) {
+          const int ci = act[1 + a];
+          const float* d = P.D + (size_t(co) * P.n_in + ci) * 257;
+          const float* xc = X + ci * 512;
+          if (erb == 0) {
+            const float tmp = fmul(__ldg(d), xc[0]);
+            t = fadd(t, fmul(tmp, tmp));
+          } else if (erb == kErb - 1) {
+            const float tmp = fmul(__ldg(d + 256), xc[1]);
+            t = fadd(t, fmul(tmp, tmp));
+          }
+          for (int k = k0; k < k1; ++k) {
+            const float dk = __ldg(d + k);
+            float tmp = fmul(dk, xc[2 * k]);
+            t = fadd(t, fmul(tmp, tmp));
+            tmp = fmul(dk, xc[2 * k + 1]);
+            t = fadd(t, fmul(tmp, tmp));
+          }
+        }
+      }
+      tcur[q] = t;
+    }
+    __syncthreads();
+    // ---- 2c. realised energy, smoothing, EQ ----------------------------------------------------------------
+#pragma unroll
+    for (int q = 0; q < kChains; ++q) {
+      const int c = tid + q * blockDim.x;
+      if (c < n_chain) {
+        const int co = c / kErb, erb = c - co * kErb;
+        const float* yc = Y + co * 512;
+        float r = 0.0f;
+        if (erb == 0) r = fmul(yc[0], yc[0]);
+        if (erb == kErb - 1) r = fmul(yc[1], yc[1]);
+        const int k0 = (erb <= 1) ? 1 : c_erb_stop[erb - 1];
+        const int k1 = (erb == 0) ? 1 : c_erb_stop[erb];
+        for (int k = k0; k < k1; ++k) {
+          r = fadd(r, fmul(yc[2 * k], yc[2 * k]));
+          r = fadd(r, fmul(yc[2 * k + 1], yc[2 * k + 1]));
+        }
+        const float tn = fadd(fmul(kAlpha, tcur[q]), fmul(kBeta, tprev[q]));
+        const float rn = fadd(fmul(kAlpha, r), fmul(kBeta, rprev[q]));
+        tprev[q] = tn, rprev[q] = rn;
+        eqs[c] = clip_eq(tn, rn);
+      }
+    }
+    __syncthreads();
+
+    // ---- 3. output transforms + overlap-add ----------------------------------------------------------------
+    for (int co = warp; co < P.n_out; co += kWarps) {
+      const float2* Yc = reinterpret_cast<const float2*>(Y + co * 512);
+      const float* eq = eqs + co * kErb;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = lane + 32 * u;
+        const float2 v = Yc[k];
+        if (k == 0) {
+          buf[phys(0)] = make_float2(fmul(v.x, eq[0]), 0.0f);
+          buf[phys(256)] = make_float2(fmul(v.y, eq[kErb - 1]), 0.0f);
+        } else {
+          const float e = eq[c_erb_of_bin[k]];
+          const float re = fmul(v.x, e), im = fmul(e, v.y);
+          buf[phys(k)] = make_float2(re, im);
+          buf[phys(512 - k)] = make_float2(re, -im);
+        }
+      }
+      __syncwarp();
+      fft512_warp<false>(buf, lane, P.eff8, P.rad2);
+      float* o = yo + size_t(co) * 1024 + slot * 256;
+      float* op = outprev + co * 256;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = lane + 32 * u;
+        const float a = __fdiv_rn(buf[phys(i)].x, 512.0f);
+        __stcs(o + i, fadd(fmul(a, wv[u]), fmul(op[i], wr[u])));
+        op[i] = __fdiv_rn(buf[phys(256 + i)].x, 512.0f);
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+  }
+
+  // ---- state for the next frame --------------------------------------------------------------------------
+  for (int i = tid; i < P.n_in * 256; i += blockDim.x) st_in[i] = x[size_t(i >> 8) * 1024 + 768 + (i & 255)];
+  for (int i = tid; i < P.n_out * 256; i += blockDim.x) st_out[i] = outprev[i];
+#pragma unroll
+  for (int q = 0; q < kChains; ++q) {
+    const int c = tid + q * blockDim.x;
+    if (c < n_chain) st_t[c] = tprev[q], st_r[c] = rprev[q];
+  }
+}
+
+}  // namespace
+}  // namespace mpeghb200
+
+using namespace mpeghb200;
+
+struct mpeghb200_format_conv {
+  mpeghb200_ctx* ctx = nullptr;
+  int n_in = 0, n_out = 0;
+  float* d_D = nullptr;
+  int* d_active = nullptr;
+  float* d_win = nullptr;
+};
+
+extern "C" {
+
+mpeghb200_status mpeghb200_format_conv_create(mpeghb200_ctx* ctx, int n_in, int n_out, const float* dmx,
+                                              mpeghb200_format_conv** out) {
+  if (!ctx || !out || !dmx) return MPEGHB200_ERR_BAD_ARG;
+  *out = nullptr;
+  if (n_in < 1 || n_in > kMaxFcCh || n_out < 1 || n_out > kMaxFcCh)
+    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "format_conv_create: 1..24 input and output channels");
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  auto* h = new (std::nothrow) mpeghb200_format_conv();
+  if (!h) return MPEGHB200_ERR_NO_MEM;
+  h->ctx = ctx, h->n_in = n_in, h->n_out = n_out;
+  std::vector<int> active(size_t(n_out) * (1 + n_in), 0);
+  for (int o = 0; o < n_out; ++o) {
+    int n = 0;
+    for (int i = 0; i < n_in; ++i)
+      if (dmx[(size_t(o) * n_in + i) * 257] != 0.0f) active[size_t(o) * (1 + n_in) + 1 + n++] = i;
+    active[size_t(o) * (1 + n_in)] = n;
+  }
+  static bool erb_table_done[64] = {};
+  cudaError_t e = cudaSuccess;
+  if (ctx->device < 64 && !erb_table_done[ctx->device]) {
+    static const int stop[kErb] = {1,  2,  3,  4,  5,  6,  7,   8,   9,   10,  11,  12,  13,  14,  15,
+                                   16, 17, 18, 19, 20, 21, 22,  23,  24,  25,  26,  27,  28,  29,  30,
+                                   31, 32, 33, 36, 39, 43, 47,  51,  55,  60,  65,  70,  77,  84,  91,
+                                   98, 106, 115, 125, 136, 148, 160, 174, 189, 205, 222, 241, 256};
+    unsigned char erb_of_bin[256] = {};
+    for (int erb = 1, k = 1; erb < kErb; ++erb)
+      for (; k < stop[erb]; ++k) erb_of_bin[k] = (unsigned char)erb;
+    e = cudaMemcpyToSymbol(c_erb_of_bin, erb_of_bin, sizeof(erb_of_bin));
+    erb_table_done[ctx->device] = (e == cudaSuccess);
+  }
+  const std::vector<float>& win = rom_table(ROM_SINE_256);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_D, size_t(n_out) * n_in * 257 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_active, active.size() * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_win, 256 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_D, dmx, size_t(n_out) * n_in * 257 * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_active, active.data(), active.size() * sizeof(int), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_win, win.data(), 256 * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(h->d_D), cudaFree(h->d_active), cudaFree(h->d_win);
+    delete h;
+    return cuda_fail(ctx, e, "format_conv_create");
+  }
+  *out = h;
+  return MPEGHB200_OK;
+}
+
+void mpeghb200_format_conv_destroy(mpeghb200_format_conv* h) {
+  if (!h) return;
+  cudaSetDevice(h->ctx->device);
+  cudaFree(h->d_D), cudaFree(h->d_active), cudaFree(h->d_win);
+  delete h;
+}
+
+size_t mpeghb200_format_conv_state_floats(const mpeghb200_format_conv* h) {
+  return h ? size_t(h->n_in) * 256 + size_t(h->n_out) * (256 + 2 * kErb) : 0;
+}
+
+mpeghb200_status mpeghb200_format_conv_dev(mpeghb200_ctx* ctx, const mpeghb200_format_conv* h, const float* d_in,
+                                           float* d_out, float* d_state, int n_streams, void* cuda_stream) {
+  if (!ctx || !h) return MPEGHB200_ERR_BAD_ARG;
+  if (n_streams < 0 || (n_streams > 0 && (!d_in || !d_out || !d_state)))
+    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "format_conv_dev: null buffer or negative stream count");
+  if (n_streams == 0) return MPEGHB200_OK;
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  FcParams P{};
+  P.in = d_in, P.out = d_out, P.state = d_state, P.D = h->d_D, P.active = h->d_active, P.win = h->d_win;
+  P.eff8 = ctx->tables.eff8, P.rad2 = ctx->tables.rad2_512;
+  P.n_in = h->n_in, P.n_out = h->n_out, P.state_floats = int(mpeghb200_format_conv_state_floats(h));
+  const size_t smem = sizeof(float) * (size_t(2) * kWarps * kBufStride + size_t(h->n_in) * 512 +
+                                       size_t(h->n_out) * (512 + 256 + kErb));
+  MB_CUDA(ctx, cudaFuncSetAttribute(format_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  format_conv_kernel<<<n_streams, kWarps * 32, smem, static_cast<cudaStream_t>(cuda_stream)>>>(P);
+  ctx->launches.fetch_add(1);
+  MB_CUDA(ctx, cudaGetLastError());
+  return MPEGHB200_OK;
+}
+
+}  // extern "C"

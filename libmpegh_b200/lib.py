@@ -187,6 +187,13 @@ class Lib:
         c.mpeghb200_hoa_spatial_state_init_dev.restype = i32
         c.mpeghb200_hoa_spatial_dev.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
         c.mpeghb200_hoa_spatial_dev.restype = i32
+        c.mpeghb200_format_conv_create.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.POINTER(vp)]
+        c.mpeghb200_format_conv_create.restype = i32
+        c.mpeghb200_format_conv_destroy.argtypes = [vp]
+        c.mpeghb200_format_conv_state_floats.argtypes = [vp]
+        c.mpeghb200_format_conv_state_floats.restype = sz
+        c.mpeghb200_format_conv_dev.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, vp]
+        c.mpeghb200_format_conv_dev.restype = i32
         self.ctx = None
 
     # ---- context ------------------------------------------------------------------------------
@@ -262,6 +269,23 @@ class Lib:
 
     def hoa_render_dev(self, h, d_in, d_out, d_state, n_streams, stream=0):
         self.check(self.c.mpeghb200_hoa_render_dev(self.ctx, h, d_in, d_out, d_state, n_streams, stream))
+
+    # ---- format converter ------------------------------------------------------------------------
+    def format_conv_create(self, dmx):
+        """dmx [n_out, n_in, 257] float32"""
+        d = np.ascontiguousarray(dmx, dtype=np.float32)
+        h = ctypes.c_void_p()
+        self.check(self.c.mpeghb200_format_conv_create(self.ctx, d.shape[1], d.shape[0], d.ctypes.data, ctypes.byref(h)))
+        return h
+
+    def format_conv_destroy(self, h):
+        self.c.mpeghb200_format_conv_destroy(h)
+
+    def format_conv_state_floats(self, h):
+        return int(self.c.mpeghb200_format_conv_state_floats(h))
+
+    def format_conv_dev(self, h, d_in, d_out, d_state, n_streams, stream=0):
+        self.check(self.c.mpeghb200_format_conv_dev(self.ctx, h, d_in, d_out, d_state, n_streams, stream))
 
     # ---- HOA spatial decoder ---------------------------------------------------------------------
     def hoa_spatial_create(self, cfg, tables):
