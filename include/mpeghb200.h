@@ -339,6 +339,42 @@ size_t mpeghb200_format_conv_state_floats(const mpeghb200_format_conv *h);
 mpeghb200_status mpeghb200_format_conv_dev(mpeghb200_ctx *ctx, const mpeghb200_format_conv *h, const float *d_in,
                                            float *d_out, float *d_state, int n_streams, void *cuda_stream);
 
+/* ---- TNS: all-pole filtering of spectral ranges, in place, before the FD synthesis ------------------------
+ * Replaces the filtering of ia_core_coder_tns_apply (decoder/ia_core_coder_tns.c:204) /
+ * impeghd_tns_decode_coeff_ar_filter (:83).  The host resolves each transmitted filter the way :240-297 does
+ * (band clamps against tns_max_bands / nbands / IGF, sfb table lookup) and decodes its coefficients with
+ * mpeghb200_tns_lpc_from_coef (double-precision sin like the reference, no GPU needed), then hands over one
+ * mpeghb200_tns_filter per filter with order > 0 and size > 0.  Filters of the same window of the same channel
+ * form a chain and are applied in array order; chain k = filters [chain_first[k], chain_first[k+1]). */
+typedef struct mpeghb200_tns_filter {
+  int32_t unit;  /* channel-frame index into d_coef [n_units][1024] */
+  int32_t start; /* first bin of the range inside the unit (window offset 128 * w included) */
+  int32_t size;  /* number of bins */
+  int32_t inc;   /* +1: upwards from start; -1: downwards from start + size - 1 (direction != 0) */
+  int32_t order; /* 1..15 */
+  int32_t pad[3];
+  float lpc[16]; /* lpc[j] = the reference's lpc[j + 1] */
+} mpeghb200_tns_filter;
+mpeghb200_status mpeghb200_tns_lpc_from_coef(int order, int coef_res, const int16_t *coef, float *lpc16);
+mpeghb200_status mpeghb200_tns_dev(mpeghb200_ctx *ctx, float *d_coef, const mpeghb200_tns_filter *d_filters,
+                                   const int32_t *d_chain_first, int n_chains, void *cuda_stream);
+
+/* ---- output resampler ------------------------------------------------------------------------------------
+ * Replaces impeghd_resample (decoder/impeghd_resampler.c:93): fac_up/fac_down = 2/1, 3/1 or 3/2
+ * (impeghd_resampler_get_sampling_ratio, decoder/impeghd_api.c:132).  filter_up = impeghd_resampler_filter
+ * (x2) or impeghd_resampler_filter_3 (x3), filter_down = impeghd_resampler_filter (only for fac_down = 2),
+ * 60 taps each (decoder/impeghd_resampler_rom.h).  One unit = one channel-frame: d_in [n_units][1024] ->
+ * d_out [n_units][1024 * fac_up / fac_down]; d_state [n_units][mpeghb200_resampler_state_floats], zero-initialised
+ * by the caller (ia_resampler_struct's delay lines and polyphase memory). */
+typedef struct mpeghb200_resampler mpeghb200_resampler;
+mpeghb200_status mpeghb200_resampler_create(mpeghb200_ctx *ctx, int fac_up, int fac_down, const float *filter_up,
+                                            const float *filter_down, mpeghb200_resampler **out);
+void mpeghb200_resampler_destroy(mpeghb200_resampler *r);
+size_t mpeghb200_resampler_state_floats(const mpeghb200_resampler *r);
+int mpeghb200_resampler_out_len(const mpeghb200_resampler *r);
+mpeghb200_status mpeghb200_resample_dev(mpeghb200_ctx *ctx, const mpeghb200_resampler *r, const float *d_in,
+                                        float *d_out, float *d_state, int n_units, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

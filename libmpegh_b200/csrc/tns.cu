@@ -1,0 +1,88 @@
+// tns.cu -- temporal noise shaping: all-pole filtering of spectral ranges, in place.
+//
+// Stands in for the filtering half of ia_core_coder_tns_apply (decoder/ia_core_coder_tns.c:204) /
+// impeghd_tns_decode_coeff_ar_filter (:83).  The host keeps what depends on libm and on bitstream tables:
+// coefficient decoding (double-precision sin, mpeghb200_tns_lpc_from_coef below does it the reference's way)
+// and the band -> bin resolution with its clamps (:262-284).  What is left is a strictly serial recurrence per
+// filter (y[n] = x[n] - sum lpc[j] y[n-1-j], every product and difference rounded separately), up to 3
+// filters per window applied in order.  One thread runs one chain (= the filters of one window of one channel);
+// chains are independent, so a launch keeps every SM busy with chains of different channels.  The recurrence
+// latency (order dependent subtractions per bin), not HBM, bounds this stage; it touches only the filtered bins.
+#include <cmath>
+
+#include "common.h"
+
+namespace mpeghb200 {
+namespace {
+
+__global__ void __launch_bounds__(128)
+    tns_kernel(float* __restrict__ coef, const mpeghb200_tns_filter* __restrict__ filters,
+               const int32_t* __restrict__ chain_first, int n_chains) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chains) return;
+  for (int f = chain_first[c]; f < chain_first[c + 1]; ++f) {
+    const mpeghb200_tns_filter& F = filters[f];
+    const int order = F.order, size = F.size, inc = F.inc;
+    if (order <= 0 || size <= 0) continue;
+    float lpc[15], st[15];
+#pragma unroll
+    for (int j = 0; j < 15; ++j) lpc[j] = F.lpc[j], st[j] = 0.0f;
+    float* p = coef + size_t(F.unit) * 1024 + F.start + (inc < 0 ? size - 1 : 0);
+    for (int i = 0; i < size; ++i) {
+      float y = *p;
+#pragma unroll
+      for (int j = 0; j < 15; ++j)
+        if (j < order) y = fsub(y, fmul(lpc[j], st[j]));
+#pragma unroll
+      for (int j = 14; j > 0; --j) st[j] = st[j - 1];
+      st[0] = y;
+      *p = y;
+      p += inc;
+    }
+  }
+}
+
+}  // namespace
+}  // namespace mpeghb200
+
+using namespace mpeghb200;
+
+extern "C" {
+
+mpeghb200_status mpeghb200_tns_lpc_from_coef(int order, int coef_res, const int16_t* coef, float* lpc) {
+  if (order < 0 || order > 15 || (coef_res != 3 && coef_res != 4) || !coef || !lpc) return MPEGHB200_ERR_BAD_ARG;
+  // decoder/ia_core_coder_tns.c:93-117, same expression types (float / double mix) as the reference
+  float tmp[16], b[16], a[16];
+  const float pi2 = (float)3.14159265358979323846264338327950288 / 2;
+  const float iqfac = (float)(((float)(1 << (coef_res - 1)) - 0.5) / (pi2));
+  const float iqfac_m = (float)(((float)(1 << (coef_res - 1)) + 0.5) / (pi2));
+  for (int i = 0; i < order; i++) tmp[i + 1] = (float)std::sin(coef[i] / ((coef[i] >= 0) ? iqfac : iqfac_m));
+  a[0] = 1;
+  for (int m = 1; m <= order; m++) {
+    b[0] = a[0];
+    for (int i = 1; i < m; i++) {
+      const float prod = tmp[m] * a[m - i];
+      b[i] = a[i] + prod;
+    }
+    b[m] = tmp[m];
+    for (int i = 0; i <= m; i++) a[i] = b[i];
+  }
+  for (int i = 0; i < 16; i++) lpc[i] = (i < order) ? a[i + 1] : 0.0f;
+  return MPEGHB200_OK;
+}
+
+mpeghb200_status mpeghb200_tns_dev(mpeghb200_ctx* ctx, float* d_coef, const mpeghb200_tns_filter* d_filters,
+                                   const int32_t* d_chain_first, int n_chains, void* cuda_stream) {
+  if (!ctx) return MPEGHB200_ERR_BAD_ARG;
+  if (n_chains < 0 || (n_chains > 0 && (!d_coef || !d_filters || !d_chain_first)))
+    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "tns_dev: null buffer or negative chain count");
+  if (n_chains == 0) return MPEGHB200_OK;
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  tns_kernel<<<(n_chains + 127) / 128, 128, 0, static_cast<cudaStream_t>(cuda_stream)>>>(d_coef, d_filters,
+                                                                                         d_chain_first, n_chains);
+  ctx->launches.fetch_add(1);
+  MB_CUDA(ctx, cudaGetLastError());
+  return MPEGHB200_OK;
+}
+
+}  // extern "C"

@@ -78,6 +78,8 @@ class HoaSpatialDesc(ctypes.Structure):
                                                "fade_windows", "dyn_win_pow_table", "dyn_win_func", "pow2_table")]
 
 
+TNS_FILTER_DTYPE = np.dtype([("unit", np.int32), ("start", np.int32), ("size", np.int32), ("inc", np.int32),
+                             ("order", np.int32), ("pad", np.int32, 3), ("lpc", np.float32, 16)])
 OBJ_SIDE_DTYPE = np.dtype([("vec_c", np.float32, 3), ("gain", np.float32), ("spread_w", np.float32),
                            ("spread_h", np.float32), ("tan_alpha", np.float32), ("pad0", np.float32),
                            ("p0", np.float32, 3), ("pad1", np.float32), ("v", np.float32, 3), ("pad2", np.float32)])
@@ -194,6 +196,19 @@ class Lib:
         c.mpeghb200_format_conv_state_floats.restype = sz
         c.mpeghb200_format_conv_dev.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, vp]
         c.mpeghb200_format_conv_dev.restype = i32
+        c.mpeghb200_tns_lpc_from_coef.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp]
+        c.mpeghb200_tns_lpc_from_coef.restype = i32
+        c.mpeghb200_tns_dev.argtypes = [vp, vp, vp, vp, ctypes.c_int, vp]
+        c.mpeghb200_tns_dev.restype = i32
+        c.mpeghb200_resampler_create.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.POINTER(vp)]
+        c.mpeghb200_resampler_create.restype = i32
+        c.mpeghb200_resampler_destroy.argtypes = [vp]
+        c.mpeghb200_resampler_state_floats.argtypes = [vp]
+        c.mpeghb200_resampler_state_floats.restype = sz
+        c.mpeghb200_resampler_out_len.argtypes = [vp]
+        c.mpeghb200_resampler_out_len.restype = ctypes.c_int
+        c.mpeghb200_resample_dev.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, vp]
+        c.mpeghb200_resample_dev.restype = i32
         self.ctx = None
 
     # ---- context ------------------------------------------------------------------------------
@@ -269,6 +284,40 @@ class Lib:
 
     def hoa_render_dev(self, h, d_in, d_out, d_state, n_streams, stream=0):
         self.check(self.c.mpeghb200_hoa_render_dev(self.ctx, h, d_in, d_out, d_state, n_streams, stream))
+
+    # ---- TNS / resampler ---------------------------------------------------------------------------
+    def tns_lpc_from_coef(self, order, coef_res, coef):
+        """Host-side coefficient decode (no GPU needed) -> lpc[16]"""
+        c16 = np.zeros(16, np.int16)
+        c16[:order] = np.asarray(coef[:order], np.int16)
+        lpc = np.zeros(16, np.float32)
+        st = self.c.mpeghb200_tns_lpc_from_coef(order, coef_res, c16.ctypes.data, lpc.ctypes.data)
+        if st != OK:
+            raise MpeghError(st, "tns_lpc_from_coef: bad order or coefficient resolution")
+        return lpc
+
+    def tns_dev(self, d_coef, d_filters, d_chain_first, n_chains, stream=0):
+        self.check(self.c.mpeghb200_tns_dev(self.ctx, d_coef, d_filters, d_chain_first, n_chains, stream))
+
+    def resampler_create(self, up, down, f_up, f_down=None):
+        fu = np.ascontiguousarray(f_up, np.float32)
+        fd = None if f_down is None else np.ascontiguousarray(f_down, np.float32)
+        h = ctypes.c_void_p()
+        self.check(self.c.mpeghb200_resampler_create(self.ctx, up, down, fu.ctypes.data,
+                                                     None if fd is None else fd.ctypes.data, ctypes.byref(h)))
+        return h
+
+    def resampler_destroy(self, h):
+        self.c.mpeghb200_resampler_destroy(h)
+
+    def resampler_state_floats(self, h):
+        return int(self.c.mpeghb200_resampler_state_floats(h))
+
+    def resampler_out_len(self, h):
+        return int(self.c.mpeghb200_resampler_out_len(h))
+
+    def resample_dev(self, h, d_in, d_out, d_state, n_units, stream=0):
+        self.check(self.c.mpeghb200_resample_dev(self.ctx, h, d_in, d_out, d_state, n_units, stream))
 
     # ---- format converter ------------------------------------------------------------------------
     def format_conv_create(self, dmx):

@@ -92,6 +92,13 @@ def load_oracle():
     lib.oracle_hoasp_process.restype = ctypes.c_int
     lib.oracle_fc_state_init.argtypes = [ctypes.c_void_p]
     lib.oracle_fc_process.argtypes = [_f32p, ctypes.c_int, ctypes.c_int, _f32p, ctypes.c_void_p, _f32p, _f32p]
+    _i16p = np.ctypeslib.ndpointer(dtype=np.int16, flags="C_CONTIGUOUS")
+    lib.oracle_tns_lpc.argtypes = [ctypes.c_int, ctypes.c_int, _i32p, _f32p]
+    lib.oracle_tns_filter.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p]
+    lib.oracle_tns_range.argtypes = [ctypes.c_int] * 4 + [_i16p, ctypes.c_int, _i32p, _i32p]
+    lib.oracle_tns_range.restype = ctypes.c_int
+    lib.oracle_rs_state_init.argtypes = [ctypes.c_void_p]
+    lib.oracle_rs_process.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _f32p, _f32p, _f32p, _f32p]
     _oracle = lib
     return lib
 
@@ -197,6 +204,14 @@ def load_ref():
     lib.ref_fc_set_matrix.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _f32p]
     lib.ref_fc_process.argtypes = [ctypes.c_void_p, _f32p, _f32p]
     lib.ref_fc_process.restype = ctypes.c_int
+    _i16p = np.ctypeslib.ndpointer(dtype=np.int16, flags="C_CONTIGUOUS")
+    lib.ref_tns_apply.argtypes = [_f32p, ctypes.c_int, _i32p, _i32p, _i16p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.ref_tns_apply.restype = ctypes.c_int
+    lib.ref_rs_create.restype = ctypes.c_void_p
+    lib.ref_rs_create.argtypes = [ctypes.c_int, ctypes.c_int]
+    lib.ref_rs_destroy.argtypes = [ctypes.c_void_p]
+    lib.ref_rs_filters.argtypes = [_f32p, _f32p]
+    lib.ref_rs_process.argtypes = [ctypes.c_void_p, _f32p, _f32p]
     _ref = lib
     return lib
 
@@ -473,3 +488,49 @@ def ref_fc_new(ref, cicp_in, cicp_out, sample_rate=48000):
     D = np.zeros((int(info[1]), int(info[0]), 257), np.float32)
     ref.ref_fc_get_matrix(h, D.reshape(-1))
     return h, D
+
+
+# ---- TNS ------------------------------------------------------------------------------------------------
+def oracle_tns_apply(spec, islong, n_filt, filt, sfb_tbl, tns_max_band, nbands):
+    """Restatement-level TNS of one channel: returns (filtered copy, list of resolved filters).
+    filt [n_win, 3, 20] ints as ref_tns_apply takes them; each resolved filter = (start, size, inc, order, lpc[16])
+    with start relative to the 1024-bin frame."""
+    lib = load_oracle()
+    spec = np.ascontiguousarray(spec, np.float32).copy()
+    n_win, bins = (1, 1024) if islong else (8, 128)
+    sfb_tbl = np.ascontiguousarray(sfb_tbl, np.int16)
+    resolved = []
+    for w in range(n_win):
+        for f in range(int(n_filt[w])):
+            order, sb, eb, direction, res = (int(v) for v in filt[w, f, :5])
+            if order == 0:
+                continue
+            a, b = np.zeros(1, np.int32), np.zeros(1, np.int32)
+            assert lib.oracle_tns_range(sb, eb, tns_max_band, nbands, sfb_tbl, len(sfb_tbl), a, b) == 0
+            size = int(b[0] - a[0])
+            if size <= 0:
+                continue
+            lpc = np.zeros(16, np.float32)
+            lib.oracle_tns_lpc(order, res, np.ascontiguousarray(filt[w, f, 5:20], np.int32), lpc)
+            start = w * bins + int(a[0])
+            inc = -1 if direction else 1
+            seg = spec[start:start + size]
+            lib.oracle_tns_filter(seg.ctypes.data, size, inc, order, lpc)
+            resolved.append((start, size, inc, order, lpc))
+    return spec, resolved
+
+
+# ---- resampler ----------------------------------------------------------------------------------------
+class OracleResampler:
+    def __init__(self, up, down, f2, f3):
+        self.up, self.down = up, down
+        self.f_up = np.ascontiguousarray(f3 if up == 3 else f2, np.float32)
+        self.f_down = np.ascontiguousarray(f2, np.float32)
+        self.state = ctypes.create_string_buffer(4 * (32 + 64 + 4))
+        load_oracle().oracle_rs_state_init(self.state)
+
+    def process(self, x):
+        x = np.ascontiguousarray(x, np.float32)
+        out = np.zeros(1024 * self.up // self.down, np.float32)
+        load_oracle().oracle_rs_process(self.state, self.up, self.down, self.f_up, self.f_down, x, out)
+        return out

@@ -168,3 +168,46 @@ void ref_limiter_constants(void *p, float *out3)
   out3[1] = h->lim.release_constant;
   out3[2] = h->lim.limit_threshold;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * TNS: ia_core_coder_tns_apply (ia_core_coder_tns.c:204) on one channel's spectrum.
+ * filt [n_win][3][20] ints = {order, start_band, stop_band, direction, coef_res, coef[15]} (order 0 = unused),
+ * sfb_tbl = upper band edges of one window, spec [1024] in place.
+ * ---------------------------------------------------------------------------------------------- */
+int ref_tns_apply(float *spec, int islong, const int *n_filt, const int *filt, const short *sfb_tbl, int sfb_per_sbk,
+                  int tns_max_band, int nbands)
+{
+  static __thread ia_usac_data_struct usac;
+  static __thread FLOAT32 scratch[4096];
+  static __thread WORD32 max_tbl[16][2];
+  ia_sfb_info_struct info;
+  ia_tns_frame_info_struct tns;
+  ia_usac_igf_config_struct igf;
+  int w, f, k, n_win = islong ? 1 : 8;
+  memset(&info, 0, sizeof(info));
+  memset(&tns, 0, sizeof(tns));
+  memset(&igf, 0, sizeof(igf));
+  info.islong = islong;
+  info.ptr_sfb_tbl = sfb_tbl;
+  info.sfb_per_sbk = sfb_per_sbk;
+  info.bins_per_sbk = islong ? 1024 : 128;
+  max_tbl[0][0] = max_tbl[0][1] = tns_max_band;
+  usac.tns_max_bands_tbl_usac = &max_tbl;
+  usac.sampling_rate_idx = 0;
+  usac.scratch_buffer_float = scratch;
+  tns.n_subblocks = n_win;
+  for (w = 0; w < n_win; w++)
+  {
+    tns.str_tns_info[w].n_filt = n_filt[w];
+    for (f = 0; f < 3; f++)
+    {
+      const int *p = filt + (w * 3 + f) * 20;
+      ia_tns_filter_struct *q = &tns.str_tns_info[w].str_filter[f];
+      tns.str_tns_info[w].coef_res = p[4] ? p[4] : tns.str_tns_info[w].coef_res;
+      q->order = p[0], q->start_band = p[1], q->stop_band = p[2], q->direction = p[3];
+      for (k = 0; k < 15; k++)
+        q->coef[k] = (WORD16)p[5 + k];
+    }
+  }
+  return (int)ia_core_coder_tns_apply(&usac, spec, nbands, &info, &tns, &igf);
+}
