@@ -83,8 +83,101 @@ def binaural_stage():
         del x, y, state
 
 
-if ONLY == "binaural":
-    binaural_stage()
+def hoa_chain_stage():
+    """config 3: 1024 streams, order 4, 16 (and 8) transport channels -> spatial decode -> NFC + render to 22.2."""
+    import hoasp_cases
+    import hoa_cases as hc
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hoasp_golden.npz"))
+    gr = np.load(os.path.join(ROOT, "tests", "golden", "hoa_ren_golden.npz"))
+    kr = hc.key(hc.CONFIGS[0])
+    S = 1024
+    for cfg in (hoasp_cases.CONFIGS[0], hoasp_cases.CONFIGS[1]):
+        T = cfg[1]
+        tables = hoasp_cases.golden_tables(g, cfg)
+        h = lib.hoa_spatial_create(cfg, tables)
+        state = torch.empty(S * lib.hoa_spatial_state_bytes(h), dtype=torch.uint8, device="cuda")
+        lib.hoa_spatial_state_init_dev(h, state.data_ptr(), S, st)
+        gens = [hoasp_cases.SideGen(cfg, np.random.default_rng(s), pred_prob=0.0) for s in range(64)]
+        sides = []
+        for f in range(4):
+            a = np.array([gen.next() for gen in gens], hoasp_cases.SIDE_DTYPE)
+            a = np.tile(a, S // 64)
+            sides.append(torch.from_numpy(a.view(np.uint8).reshape(S, -1).copy()).cuda())
+        x = torch.randn(S, T, 1024, device="cuda") * 2000
+        coef = torch.empty(S, 25, 1024, device="cuda")
+        ms = timeit(lambda i: lib.hoa_spatial_dev(h, sides[i % 4].data_ptr(), x.data_ptr(), coef.data_ptr(),
+                                                  state.data_ptr(), S, st))
+        report(f"hoa_spatial order 4, T={T}, 1024 streams (plan + render kernels)", ms, S * (T + 25) * 4096,
+               S * 25 * 1024, "coefficient_samples")
+        r = lib.hoa_renderer_create(gr[kr + "_M"], gr[kr + "_nfc"])
+        hout = torch.empty(S, 24, 1024, device="cuda")
+        hst = torch.zeros(S * 25 * 14, device="cuda")
+
+        def chain(i):
+            lib.hoa_spatial_dev(h, sides[i % 4].data_ptr(), x.data_ptr(), coef.data_ptr(), state.data_ptr(), S, st)
+            lib.hoa_render_dev(r, coef.data_ptr(), hout.data_ptr(), hst.data_ptr(), S, st)
+        ms = timeit(chain)
+        report(f"config 3 chain: hoa_spatial + NFC + render to 22.2, T={T}, 1024 streams", ms, S * (T + 24) * 4096,
+               S * 24 * 1024, "output_channel_samples",
+               {"stream_frames_per_s": S / (ms * 1e-3), "audio_s_per_wall_s": S * 1024 / 48000.0 / (ms * 1e-3)})
+        lib.hoa_renderer_destroy(r)
+        lib.hoa_spatial_destroy(h)
+
+
+def fc_stage():
+    """config 5 bed: 22.2 -> 7.1.4 format conversion, 512 streams."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "fc_golden.npz"))
+    D = g["c13_c19_D"]
+    S = 512
+    h = lib.format_conv_create(D)
+    x = torch.randn(S, 24, 1024, device="cuda") * 3000
+    y = torch.empty(S, 12, 1024, device="cuda")
+    state = torch.zeros(S * lib.format_conv_state_floats(h), device="cuda")
+    ms = timeit(lambda i: lib.format_conv_dev(h, x.data_ptr(), y.data_ptr(), state.data_ptr(), S, st))
+    per_unit = 24 * 4096 + 12 * 4096 + 2 * 24 * 256 * 4 + 2 * 12 * 256 * 4 + 2 * 2 * 12 * 58 * 4
+    report("format_conv 22.2 -> 7.1.4, 512 streams", ms, S * per_unit, S * 24 * 1024, "input_channel_samples",
+           {"stream_frames_per_s": S / (ms * 1e-3)})
+    lib.format_conv_destroy(h)
+
+
+def tns_rs_stage():
+    import tns_cases
+    from libmpegh_b200.lib import TNS_FILTER_DTYPE
+    U = 6144
+    rng = np.random.default_rng(1)
+    coef = torch.randn(U, 1024, device="cuda") * 500
+    chains = []
+    bins = 0
+    for u in range(U):
+        if rng.random() < 0.5:
+            continue
+        islong = int(rng.random() < 0.9)
+        n_filt, filt = tns_cases.random_tns(rng, islong)
+        ch = tns_cases.resolve_filters(lib, u, islong, n_filt, filt, 49 if islong else 14, lib.tns_lpc_from_coef)
+        chains += ch
+        bins += sum(int(r["size"]) for c in ch for r in c)
+    recs = np.array([r for c in chains for r in c], TNS_FILTER_DTYPE)
+    first = np.cumsum([0] + [len(c) for c in chains]).astype(np.int32)
+    d_f = torch.from_numpy(recs.view(np.uint8).reshape(len(recs), -1).copy()).cuda()
+    d_first = torch.from_numpy(first).cuda()
+    ms = timeit(lambda i: lib.tns_dev(coef.data_ptr(), d_f.data_ptr(), d_first.data_ptr(), len(chains), st))
+    report(f"tns 6144 channel-frames, {len(chains)} chains, {bins} filtered bins", ms, bins * 8 + recs.nbytes, bins,
+           "filtered_bins")
+    g = np.load(os.path.join(ROOT, "tests", "golden", "tns_rs_golden.npz"))
+    for up, down in ((3, 2), (2, 1)):
+        h = lib.resampler_create(up, down, g["rs_filter_3"] if up == 3 else g["rs_filter_2"], g["rs_filter_2"])
+        x = torch.randn(U, 1024, device="cuda") * 5000
+        y = torch.empty(U, lib.resampler_out_len(h), device="cuda")
+        state = torch.zeros(U * lib.resampler_state_floats(h), device="cuda")
+        ms = timeit(lambda i: lib.resample_dev(h, x.data_ptr(), y.data_ptr(), state.data_ptr(), U, st))
+        report(f"resampler x{up}/{down}, 6144 channel-frames", ms, U * (4096 + 4 * lib.resampler_out_len(h)), U * 1024,
+               "input_samples")
+        lib.resampler_destroy(h)
+
+
+STAGES = {"binaural": binaural_stage, "hoa": hoa_chain_stage, "fc": fc_stage, "tns_rs": tns_rs_stage}
+if ONLY in STAGES:
+    STAGES[ONLY]()
     lib.close()
     sys.exit(0)
 
@@ -137,5 +230,8 @@ for use_nfc in (1, 0):
     report(f"hoa_render order 4 -> 22.2, 1024 streams, nfc={use_nfc}", ms, S * (25 + 24) * 4096, S * 24 * 1024,
            "output_channel_samples", {"fp32_unfused_Gops": S * 24 * 25 * 1024 * 2 / (ms * 1e-3) / 1e9})
     lib.hoa_renderer_destroy(h)
+hoa_chain_stage()
+fc_stage()
+tns_rs_stage()
 binaural_stage()
 lib.close()
