@@ -321,7 +321,7 @@ def main():
                 "roofline_frac": BYTES_PER_UNIT * UNITS / (ms_mixed * 1e-3) / 1e9 / peak},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "fd_synth_kernel", "algorithmic_bytes_per_launch": BYTES_PER_UNIT * UNITS},
+                         "kernel": "fd_synth_ws_kernel", "algorithmic_bytes_per_launch": BYTES_PER_UNIT * UNITS},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": UNITS * FRAME * 4 + UNITS * 4,
                     "d2h_bytes_per_step": UNITS * FRAME * 4, "ms_per_step": e2e_s * 1e3,
                     "api": "mpeghb200_fd_execute (pinned host buffers)"},

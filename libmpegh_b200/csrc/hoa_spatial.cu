@@ -20,6 +20,7 @@
 //   render kernel  (stream, 256-sample chunk) CTAs: stage the T corrected transport samples in shared memory,
 //                  then each thread evaluates all n_coef outputs of its sample; control flow is uniform per CTA.
 // HBM traffic per stream-frame: T * 4 KB in, n_coef * 4 KB out, ~6 KB side info, <= 12 KB plan.
+#include <cstddef>
 #include <cstring>
 #include <new>
 
@@ -340,34 +341,107 @@ __device__ __forceinline__ float win_mul(float v, int win, const float (&w)[4]) 
 
 constexpr int kPredCache = 6;
 
-__global__ void __launch_bounds__(kChunk)
+// |exponent| > 6: the reference's per-sample double pow (kept out of line: rare, and it would bloat the kernel)
+__device__ __noinline__ float dyn_pow_path(float win, int e, float v) {
+  return fmul(__double2float_rn(pow(double(win), double(e))), v);
+}
+
+// NC = (order + 1)^2 at compile time: the per-coefficient accumulators of a sample live in registers and the
+// contribution lists are walked entry-outermost (the order of additions per coefficient stays the reference's).
+template <int NC>
+__global__ void __launch_bounds__(kChunk, (NC <= 25) ? 3 : 2)
     hoasp_render_kernel(const float* __restrict__ in, float* __restrict__ out, const Slot* __restrict__ slots,
                         const __grid_constant__ Cfg C) {
-  __shared__ float xs[kMaxCh][kChunk];  // corrected transport samples (before clearing)
-  const Plan& pl = slots[blockIdx.x].plan;
+  __shared__ float xs[kMaxCh][kChunk];        // corrected transport samples (before clearing)
+  __shared__ Plan pl;                         // this stream's plan: every thread walks it, so keep it on chip
+  __shared__ float fine_rows[2 * kMaxCh][NC]; // mode-matrix rows of the direction entries
   const int tid = threadIdx.x;
+  {
+    const Plan& gp = slots[blockIdx.x].plan;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&gp);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&pl);
+    constexpr int kHead = int(offsetof(Plan, pred_g) / 4), kPredEnd = int(offsetof(Plan, vec_v) / 4);
+    for (int i = tid; i < kHead; i += kChunk) dst[i] = src[i];
+    if (gp.n_pred[0] | gp.n_pred[1])
+      for (int i = kHead + tid; i < kPredEnd; i += kChunk) dst[i] = src[i];
+    const int nv = gp.n_vec_e * kMaxCoef;
+    for (int i = tid; i < nv; i += kChunk) dst[kPredEnd + i] = src[kPredEnd + i];
+    const int nd = gp.n_dir_e;
+    for (int i = tid; i < nd * NC; i += kChunk) {
+      const int n = i / NC, c = i - n * NC;
+      fine_rows[n][c] = __ldg(C.fine + (gp.dir_grid[n] - 1) * kMaxCoef + c);
+    }
+  }
   const int t = blockIdx.y * kChunk + tid;
   const float* x = in + size_t(blockIdx.x) * C.n_transport * kFrame;
-  float* y = out + size_t(blockIdx.x) * C.n_coef * kFrame;
+  float* y = out + size_t(blockIdx.x) * NC * kFrame;
   const float w[4] = {__ldg(C.wins + t), __ldg(C.wins + kFrame + t), __ldg(C.wins + 2 * kFrame + t),
                       __ldg(C.wins + 3 * kFrame + t)};
-
-  for (int ch = 0; ch < C.n_transport; ++ch) {
-    const float v = __ldcs(x + size_t(ch) * kFrame + t);
-    const float a = pl.dyn_a[ch];
-    const int mode = pl.dyn_mode[ch], arg = pl.dyn_arg[ch];
-    float r;
-    if (mode == 0) {
-      r = fmul(a, v);
-    } else if (mode == 1) {
-      r = fmul(fmul(v, a), __ldg(C.dyn_pow + arg * kFrame + t));
-    } else {
-      r = fmul(__double2float_rn(pow(double(__ldg(C.dyn_win + t)), double(arg))), fmul(a, v));
+  {
+    // all transport samples of this thread's column are requested before the first one is used
+    float xv[kMaxCh];
+#pragma unroll
+    for (int ch = 0; ch < kMaxCh; ++ch) xv[ch] = (ch < C.n_transport) ? __ldcs(x + size_t(ch) * kFrame + t) : 0.0f;
+    __syncthreads();  // plan staged
+#pragma unroll
+    for (int ch = 0; ch < kMaxCh; ++ch) {
+      if (ch < C.n_transport) {
+        const float v = xv[ch];
+        const float a = pl.dyn_a[ch];
+        const int mode = pl.dyn_mode[ch], arg = pl.dyn_arg[ch];
+        float r;
+        if (mode == 0) {
+          r = fmul(a, v);
+        } else if (mode == 1) {
+          r = fmul(fmul(v, a), __ldg(C.dyn_pow + arg * kFrame + t));
+        } else {
+          r = dyn_pow_path(__ldg(C.dyn_win + t), arg, fmul(a, v));
+        }
+        xs[ch][tid] = r;
+      }
     }
-    xs[ch][tid] = r;
   }
   // own column only: no barrier needed.  xc(ch) = sample after the channel clearing
   auto xc = [&](int ch) { return pl.clear[ch] ? 0.0f : xs[ch][tid]; };
+  auto wsel = [&](int win) { return win == kWinInVec ? w[0] : win == kWinOutVec ? w[1] : win == kWinInDir ? w[2] : w[3]; };
+
+  // ---- vector-based part: v[c] += (V[n][c] * win) * x ---------------------------------------------------
+  float v[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) v[c] = 0.0f;
+  const int vs = C.vec_start;
+  for (int n = 0; n < pl.n_vec_e; ++n) {
+    if (t >= pl.vec_ns[n]) continue;
+    const float xv = xc(pl.vec_ch[n]);
+    const int win = pl.vec_win[n];
+    const float* V = pl.vec_v[n] - vs;
+    if (win == kWinNone) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        if (c >= vs) v[c] = fadd(v[c], fmul(V[c], xv));
+    } else {
+      const float wv = wsel(win);
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        if (c >= vs) v[c] = fadd(v[c], fmul(fmul(V[c], wv), xv));
+    }
+  }
+  // ---- direction signals: d[c] += (x * M[grid][c]) * win ------------------------------------------------------
+  float d[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) d[c] = 0.0f;
+  for (int n = 0; n < pl.n_dir_e; ++n) {
+    const float xv = xc(pl.dir_ch[n]);
+    const int win = pl.dir_win[n];
+    if (win == kWinNone) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) d[c] = fadd(d[c], fmul(xv, fine_rows[n][c]));
+    } else {
+      const float wv = wsel(win);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) d[c] = fadd(d[c], fmul(fmul(xv, fine_rows[n][c]), wv));
+    }
+  }
 
   // predicted grid signals of the first few active grid points are kept, the rest recomputed per coefficient
   auto pred_tmp = [&](int k, int n) {
@@ -376,27 +450,20 @@ __global__ void __launch_bounds__(kChunk)
     for (int s = 0; s < nv; ++s) a = fadd(a, fmul(pl.pred_fac[k][n][s], xc(pl.pred_idx[k][n][s] - 1)));
     return fmul(a, k ? w[2] : w[3]);
   };
+  const bool any_pred = (pl.n_pred[0] | pl.n_pred[1]) != 0;
   float tcache[2][kPredCache];
 #pragma unroll
   for (int k = 0; k < 2; ++k)
 #pragma unroll
-    for (int n = 0; n < kPredCache; ++n) tcache[k][n] = (n < pl.n_pred[k]) ? pred_tmp(k, n) : 0.0f;
+    for (int n = 0; n < kPredCache; ++n) tcache[k][n] = (any_pred && n < pl.n_pred[k]) ? pred_tmp(k, n) : 0.0f;
 
-  const int nv_e = pl.n_vec_e, nd_e = pl.n_dir_e;
-  for (int c = 0; c < C.n_coef; ++c) {
-    float v = 0.0f;
-    if (c >= C.vec_start) {
-      for (int n = 0; n < nv_e; ++n) {
-        if (t < pl.vec_ns[n]) {
-          const float iv = win_mul(pl.vec_v[n][c - C.vec_start], pl.vec_win[n], w);
-          v = fadd(v, fmul(iv, xc(pl.vec_ch[n])));
-        }
-      }
-    }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    float vv = v[c];
     const int in_en = pl.in_en[c], in_dis = pl.in_dis[c];
     if (C.coded_v_vec_length == 1) {
-      for (int i = 0; i < in_en; ++i) v = fmul(v, w[3]);
-      for (int i = 0; i < in_dis; ++i) v = fmul(v, w[2]);
+      for (int i = 0; i < in_en; ++i) vv = fmul(vv, w[3]);
+      for (int i = 0; i < in_dis; ++i) vv = fmul(vv, w[2]);
     }
     float amb;
     if (c >= C.low_order) {
@@ -409,8 +476,8 @@ __global__ void __launch_bounds__(kChunk)
         amb = fadd(amb, fmul(__ldg(C.order_matrix + c * C.low_order + m), src < 0 ? 0.0f : xs[src][tid]));
       }
     }
-    float pred;
-    {
+    float pred = 0.0f;
+    if (any_pred) {
       float pk[2];
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
@@ -426,7 +493,7 @@ __global__ void __launch_bounds__(kChunk)
           } else {
             tv = pred_tmp(k, n);
           }
-          p = fadd(p, fmul(tv, __ldg(C.coarse + c * C.n_coef + pl.pred_g[k][n])));
+          p = fadd(p, fmul(tv, __ldg(C.coarse + c * NC + pl.pred_g[k][n])));
         }
         pk[k] = p;
       }
@@ -436,14 +503,15 @@ __global__ void __launch_bounds__(kChunk)
       if (pl.pred_flag[0])
         for (int i = 0; i < in_dis; ++i) pred = fmul(pred, w[2]);
     }
-    float dir = 0.0f;
-    for (int n = 0; n < nd_e; ++n) {
-      float cc = fmul(xc(pl.dir_ch[n]), __ldg(C.fine + (pl.dir_grid[n] - 1) * kMaxCoef + c));
-      cc = win_mul(cc, pl.dir_win[n], w);
-      dir = fadd(dir, cc);
-    }
-    __stcs(y + size_t(c) * kFrame + t, fadd(v, fadd(fadd(amb, pred), dir)));
+    __stcs(y + size_t(c) * kFrame + t, fadd(vv, fadd(fadd(amb, pred), d[c])));
   }
+}
+
+template <int NC>
+cudaError_t launch_render(const float* in, float* out, const Slot* slots, const Cfg& cfg, int n_streams,
+                          cudaStream_t st) {
+  hoasp_render_kernel<NC><<<dim3(n_streams, kFrame / kChunk), kChunk, 0, st>>>(in, out, slots, cfg);
+  return cudaGetLastError();
 }
 
 }  // namespace
@@ -548,9 +616,17 @@ mpeghb200_status mpeghb200_hoa_spatial_dev(mpeghb200_ctx* ctx, const mpeghb200_h
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   Slot* slots = static_cast<Slot*>(d_state);
   hoasp_plan_kernel<<<n_streams, 128, 0, st>>>(d_side, slots, h->cfg);
-  hoasp_render_kernel<<<dim3(n_streams, kFrame / kChunk), kChunk, 0, st>>>(d_in, d_out, slots, h->cfg);
+  cudaError_t e;
+  switch (h->cfg.n_coef) {
+    case 4: e = launch_render<4>(d_in, d_out, slots, h->cfg, n_streams, st); break;
+    case 9: e = launch_render<9>(d_in, d_out, slots, h->cfg, n_streams, st); break;
+    case 16: e = launch_render<16>(d_in, d_out, slots, h->cfg, n_streams, st); break;
+    case 25: e = launch_render<25>(d_in, d_out, slots, h->cfg, n_streams, st); break;
+    case 36: e = launch_render<36>(d_in, d_out, slots, h->cfg, n_streams, st); break;
+    default: e = launch_render<49>(d_in, d_out, slots, h->cfg, n_streams, st); break;
+  }
   ctx->launches.fetch_add(2);
-  MB_CUDA(ctx, cudaGetLastError());
+  MB_CUDA(ctx, e);
   return MPEGHB200_OK;
 }
 

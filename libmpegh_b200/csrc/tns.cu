@@ -24,20 +24,30 @@ __global__ void __launch_bounds__(128)
     const mpeghb200_tns_filter& F = filters[f];
     const int order = F.order, size = F.size, inc = F.inc;
     if (order <= 0 || size <= 0) continue;
-    float lpc[15], st[15];
+    // the last 16 outputs live in a register ring addressed with compile-time indices (the bin loop is unrolled
+    // by 16), so a bin costs its `order` product/difference pairs and nothing else
+    float lpc[15], ring[16];
 #pragma unroll
-    for (int j = 0; j < 15; ++j) lpc[j] = F.lpc[j], st[j] = 0.0f;
+    for (int j = 0; j < 15; ++j) lpc[j] = F.lpc[j];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) ring[j] = 0.0f;
     float* p = coef + size_t(F.unit) * 1024 + F.start + (inc < 0 ? size - 1 : 0);
-    for (int i = 0; i < size; ++i) {
-      float y = *p;
+    for (int i0 = 0; i0 < size; i0 += 16) {
+      float xb[16];
 #pragma unroll
-      for (int j = 0; j < 15; ++j)
-        if (j < order) y = fsub(y, fmul(lpc[j], st[j]));
+      for (int e = 0; e < 16; ++e) xb[e] = (i0 + e < size) ? p[(i0 + e) * inc] : 0.0f;
 #pragma unroll
-      for (int j = 14; j > 0; --j) st[j] = st[j - 1];
-      st[0] = y;
-      *p = y;
-      p += inc;
+      for (int e = 0; e < 16; ++e) {
+        float y = xb[e];
+#pragma unroll
+        for (int j = 0; j < 15; ++j)
+          if (j < order) y = fsub(y, fmul(lpc[j], ring[(e - 1 - j) & 15]));  // y[n-1-j]
+        ring[e] = y;
+        xb[e] = y;
+      }
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        if (i0 + e < size) p[(i0 + e) * inc] = xb[e];
     }
   }
 }
