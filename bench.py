@@ -62,7 +62,14 @@ def make_side(rng, n_units, mixed=False):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md recipe).
+
+    nvidia-smi needs a few hundred ms to deliver its first row, so the caller starts it before the warm-up,
+    keeps the same kernel running until the first row has arrived (wait_first), and marks the timed region with
+    mark_begin/mark_end; rows are time-stamped on arrival.  `samples` counts the rows that arrived inside the
+    timed region, `samples_under_load` all rows taken while the identical load was running (warm-up tail,
+    timed region and, if the region was too short for 3 rows, an untimed continuation of the same load).
+    """
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -70,11 +77,12 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -83,27 +91,40 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def n_rows(self):
+        return len(self.rows)
+
+    def alive(self):
+        return self.proc is not None and self.proc.poll() is None
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def stop(self):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         self.t.join(timeout=2)
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, inside = [], [], set(), 0
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
                 for n, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
+                if self.t_begin is not None and self.t_begin <= ts <= (self.t_end or ts):
+                    inside += 1
             except (ValueError, IndexError):
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": inside, "samples_under_load": len(sm), "reasons": sorted(reasons)}
 
 
 def cpu_threads():
@@ -166,15 +187,22 @@ def reference_arm(args, rank):
     if rank != 0:
         return
     n_threads = cpu_threads()
-    value, sps, kind = run_cpu(args, UNITS, args.steps, args.warmup, n_threads)
+    # bounded sample: a step is the full 6144 channel-frames unless K+W full steps would take more than ~90 s on
+    # this box, in which case each step is a proportionally smaller slice of the same workload (whole streams).
+    _, t_full, _ = run_cpu(args, UNITS, 1, 1, n_threads)
+    sample_units = UNITS
+    total = t_full * (args.steps + args.warmup)
+    if total > 90.0:
+        sample_units = max(CHANNELS * n_threads, int(UNITS * 90.0 / total) // CHANNELS * CHANNELS)
+    value, sps, kind = run_cpu(args, sample_units, args.steps, args.warmup, n_threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(), "streams": STREAMS, "channels": CHANNELS, "frame": FRAME},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_threads, "kind": kind,
-                         "sample": f"full workload: {UNITS} channel-frames per step, {args.steps} steps, "
-                                   "ia_core_coder_fd_frm_dec per channel-frame"},
+                         "sample": f"{sample_units} of the workload's {UNITS} channel-frames per step, "
+                                   f"{args.steps} steps, ia_core_coder_fd_frm_dec per channel-frame"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -184,8 +212,8 @@ def reference_arm(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=20000)
+    ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--groups", type=int, default=8, help="stream groups rotated through (working set > L2)")
     ap.add_argument("--e2e-steps", type=int, default=20)
@@ -241,23 +269,44 @@ def main():
             lib.fd_synth_dev(coef[g].data_ptr(), side[g].data_ptr(), ovl[g].data_ptr(), outb[g].data_ptr(), UNITS,
                              stream.cuda_stream)
 
+        sampler = ClockSampler(local_rank)
+        sampling = rank == 0 and with_clocks
+        if sampling:
+            sampler.start()
         for i in range(args.warmup):
             step(i)
+        n_extra = 0
+        if sampling:
+            # same load, untimed, until nvidia-smi has delivered its first row (bounded: 5 s)
+            t_wait = time.perf_counter()
+            while sampler.alive() and sampler.n_rows() == 0 and time.perf_counter() - t_wait < 5.0:
+                for _ in range(64):
+                    step(n_extra)
+                    n_extra += 1
+                torch.cuda.synchronize()
         barrier()
-        sampler = ClockSampler(local_rank)
-        if rank == 0 and with_clocks:
-            sampler.start()
         launches0 = lib.launch_count()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        sampler.mark_begin()
         ev0.record(stream)
         for i in range(args.steps):
             step(args.warmup + i)
         ev1.record(stream)
         barrier()
+        sampler.mark_end()
         ms = ev0.elapsed_time(ev1)
         n_launch = lib.launch_count() - launches0
-        clk = sampler.stop() if (rank == 0 and with_clocks) else None
+        clk = None
+        if sampling:
+            # a timed region shorter than three sampling periods: continue the identical load, untimed
+            t_wait = time.perf_counter()
+            while sampler.alive() and sampler.n_rows() < 3 and time.perf_counter() - t_wait < 3.0:
+                for _ in range(64):
+                    step(n_extra)
+                    n_extra += 1
+                torch.cuda.synchronize()
+            clk = sampler.stop()
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
