@@ -359,6 +359,45 @@ mpeghb200_status mpeghb200_tns_lpc_from_coef(int order, int coef_res, const int1
 mpeghb200_status mpeghb200_tns_dev(mpeghb200_ctx *ctx, float *d_coef, const mpeghb200_tns_filter *d_filters,
                                    const int32_t *d_chain_first, int n_chains, void *cuda_stream);
 
+/* ---- joint-stereo tools of a channel-pair element, on the spectra, before TNS / FD synthesis ---------------
+ * Replaces impeghd_ms_stereo (decoder/ia_core_coder_ext_ch_ele.c:1427), ia_core_coder_cplx_pred_upmixing (:561)
+ * incl. ia_core_coder_estimate_dmx_im (:495), the previous-frame downmix ia_core_coder_cplx_prev_mdct_dmx (:703)
+ * and the spectrum save ia_core_coder_usac_cplx_save_prev (:93).  The host keeps the bitstream side: mask and
+ * alpha_q decoding (ia_core_coder_read_ms_mask :262, ia_core_coder_cplx_pred_data :128) and expands window
+ * groups to windows.  Order of the launches for one frame, as ia_core_coder_data_process (:1695) runs them:
+ *   tns_on_lr == 0:  mpeghb200_tns_dev, mpeghb200_stereo_dev      tns_on_lr == 1:  stereo, then TNS
+ *   then mpeghb200_stereo_save_dev, then mpeghb200_fd_synth_dev.
+ * The same side record applied to other unit pairs (left/right of the IGF source tiles) repeats the tool there.
+ * Pair state: mpeghb200_stereo_state_floats() floats per slot (the two saved spectra), zero-initialised. */
+typedef struct mpeghb200_stereo_pair {
+  int32_t left, right; /* unit indices of the two spectra in d_coef [n_units][1024] */
+  int32_t slot;        /* pair-state slot */
+  uint8_t tool;        /* ms_mask_present: 0 none, 1 (or 2 with a full mask) M/S by band mask, 3 complex prediction */
+  uint8_t is_short;    /* EIGHT_SHORT: 8 windows of 128 bins */
+  uint8_t window_sequence, window_shape, window_shape_prev; /* select the MDST filter pair */
+  uint8_t pred_dir, complex_coef, use_prev_frame;
+  uint8_t first_band, last_band; /* M/S band range; band range of real-only prediction (0, max_sfb_ste) */
+  uint8_t prev_dmx; /* 1: previous-frame downmix from the saved spectra; 0: zeros (independency flag, LPD history) */
+  uint8_t save;     /* mpeghb200_stereo_save_dev: 0 keep, 1 save the last window, 2 save zeros (:1955-1963) */
+  uint8_t used[128];     /* ms_used / cplx_pred_used per (window, band): long [band], short [16 * window + band] */
+  int16_t alpha_re[128]; /* alpha_q_re, same indexing */
+  int16_t alpha_im[128];
+} mpeghb200_stereo_pair;
+typedef struct mpeghb200_stereo mpeghb200_stereo;
+/* sfb_top_*: upper band edges of one window (ptr_sfb_1024 / ptr_sfb_128 of the stream's sampling rate). */
+mpeghb200_status mpeghb200_stereo_create(mpeghb200_ctx *ctx, const int16_t *sfb_top_long, int n_long,
+                                         const int16_t *sfb_top_short, int n_short, mpeghb200_stereo **out);
+void mpeghb200_stereo_destroy(mpeghb200_stereo *s);
+size_t mpeghb200_stereo_state_floats(void);
+mpeghb200_status mpeghb200_stereo_dev(mpeghb200_ctx *ctx, const mpeghb200_stereo *s, float *d_coef,
+                                      const mpeghb200_stereo_pair *d_pairs, const float *d_state, int n_pairs,
+                                      void *cuda_stream);
+mpeghb200_status mpeghb200_stereo_save_dev(mpeghb200_ctx *ctx, const mpeghb200_stereo *s, const float *d_coef,
+                                           const mpeghb200_stereo_pair *d_pairs, float *d_state, int n_pairs,
+                                           void *cuda_stream);
+/* MDST filter table of the complex-prediction tool: curr [4][2][2][7], prev [2][2][7] (host, no GPU needed). */
+void mpeghb200_stereo_mdst_rom(float *curr112, float *prev28);
+
 /* ---- output resampler ------------------------------------------------------------------------------------
  * Replaces impeghd_resample (decoder/impeghd_resampler.c:93): fac_up/fac_down = 2/1, 3/1 or 3/2
  * (impeghd_resampler_get_sampling_ratio, decoder/impeghd_api.c:132).  filter_up = impeghd_resampler_filter

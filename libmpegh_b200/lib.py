@@ -209,6 +209,17 @@ class Lib:
         c.mpeghb200_resampler_out_len.restype = ctypes.c_int
         c.mpeghb200_resample_dev.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, vp]
         c.mpeghb200_resample_dev.restype = i32
+        c.mpeghb200_stereo_create.argtypes = [vp, vp, ctypes.c_int, vp, ctypes.c_int, ctypes.POINTER(vp)]
+        c.mpeghb200_stereo_create.restype = i32
+        c.mpeghb200_stereo_destroy.argtypes = [vp]
+        c.mpeghb200_stereo_state_floats.argtypes = []
+        c.mpeghb200_stereo_state_floats.restype = sz
+        c.mpeghb200_stereo_dev.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, vp]
+        c.mpeghb200_stereo_dev.restype = i32
+        c.mpeghb200_stereo_save_dev.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, vp]
+        c.mpeghb200_stereo_save_dev.restype = i32
+        c.mpeghb200_stereo_mdst_rom.argtypes = [vp, vp]
+        c.mpeghb200_stereo_mdst_rom.restype = None
         self.ctx = None
 
     # ---- context ------------------------------------------------------------------------------
@@ -298,6 +309,32 @@ class Lib:
 
     def tns_dev(self, d_coef, d_filters, d_chain_first, n_chains, stream=0):
         self.check(self.c.mpeghb200_tns_dev(self.ctx, d_coef, d_filters, d_chain_first, n_chains, stream))
+
+    # ---- joint-stereo tools -------------------------------------------------------------------------
+    def stereo_create(self, sfb_long, sfb_short):
+        a = np.ascontiguousarray(sfb_long, np.int16)
+        b = np.ascontiguousarray(sfb_short, np.int16)
+        h = ctypes.c_void_p()
+        self.check(self.c.mpeghb200_stereo_create(self.ctx, a.ctypes.data, len(a), b.ctypes.data, len(b),
+                                                  ctypes.byref(h)))
+        return h
+
+    def stereo_destroy(self, h):
+        self.c.mpeghb200_stereo_destroy(h)
+
+    def stereo_state_floats(self):
+        return int(self.c.mpeghb200_stereo_state_floats())
+
+    def stereo_dev(self, h, d_coef, d_pairs, d_state, n_pairs, stream=0):
+        self.check(self.c.mpeghb200_stereo_dev(self.ctx, h, d_coef, d_pairs, d_state, n_pairs, stream))
+
+    def stereo_save_dev(self, h, d_coef, d_pairs, d_state, n_pairs, stream=0):
+        self.check(self.c.mpeghb200_stereo_save_dev(self.ctx, h, d_coef, d_pairs, d_state, n_pairs, stream))
+
+    def stereo_mdst_rom(self):
+        curr, prev = np.zeros((4, 2, 2, 7), np.float32), np.zeros((2, 2, 7), np.float32)
+        self.c.mpeghb200_stereo_mdst_rom(curr.ctypes.data, prev.ctypes.data)
+        return curr, prev
 
     def resampler_create(self, up, down, f_up, f_down=None):
         fu = np.ascontiguousarray(f_up, np.float32)

@@ -99,6 +99,14 @@ def load_oracle():
     lib.oracle_tns_range.restype = ctypes.c_int
     lib.oracle_rs_state_init.argtypes = [ctypes.c_void_p]
     lib.oracle_rs_process.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, _f32p, _f32p, _f32p, _f32p]
+    lib.oracle_stereo_set_rom.argtypes = [_f32p, _f32p]
+    lib.oracle_stereo_apply.argtypes = [ctypes.c_char_p, _i16p, ctypes.c_int, _f32p, _f32p, _f32p]
+    lib.oracle_stereo_save.argtypes = [ctypes.c_char_p, _f32p, _f32p, _f32p]
+    sg_path = os.path.join(ROOT, "tests", "golden", "stereo_golden.npz")
+    if os.path.exists(sg_path):  # MDST filter ROM of the complex-prediction tool (absent only while it is being made)
+        sg = np.load(sg_path)
+        lib.oracle_stereo_set_rom(np.ascontiguousarray(sg["mdst_curr"], np.float32).reshape(-1),
+                                  np.ascontiguousarray(sg["mdst_prev"], np.float32).reshape(-1))
     _oracle = lib
     return lib
 
@@ -207,6 +215,15 @@ def load_ref():
     _i16p = np.ctypeslib.ndpointer(dtype=np.int16, flags="C_CONTIGUOUS")
     lib.ref_tns_apply.argtypes = [_f32p, ctypes.c_int, _i32p, _i32p, _i16p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     lib.ref_tns_apply.restype = ctypes.c_int
+    lib.ref_cpe_create.restype = ctypes.c_void_p
+    lib.ref_cpe_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.ref_cpe_destroy.argtypes = [ctypes.c_void_p]
+    lib.ref_cpe_sfb_table.argtypes = [ctypes.c_int, ctypes.c_int, _i16p, ctypes.c_int]
+    lib.ref_cpe_sfb_table.restype = ctypes.c_int
+    lib.ref_cpe_process.argtypes = [ctypes.c_void_p, ctypes.c_char_p, _i32p, ctypes.c_int, _i32p, _i32p, _i32p, _f32p,
+                                    _f32p, _f32p, _f32p, _f32p, _f32p]
+    lib.ref_cpe_process.restype = ctypes.c_int
+    lib.ref_mdst_rom.argtypes = [_f32p, _f32p]
     lib.ref_rs_create.restype = ctypes.c_void_p
     lib.ref_rs_create.argtypes = [ctypes.c_int, ctypes.c_int]
     lib.ref_rs_destroy.argtypes = [ctypes.c_void_p]
