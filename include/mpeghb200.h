@@ -383,20 +383,54 @@ typedef struct mpeghb200_stereo_pair {
   int16_t alpha_re[128]; /* alpha_q_re, same indexing */
   int16_t alpha_im[128];
 } mpeghb200_stereo_pair;
-typedef struct mpeghb200_stereo mpeghb200_stereo;
-/* sfb_top_*: upper band edges of one window (ptr_sfb_1024 / ptr_sfb_128 of the stream's sampling rate). */
-mpeghb200_status mpeghb200_stereo_create(mpeghb200_ctx *ctx, const int16_t *sfb_top_long, int n_long,
-                                         const int16_t *sfb_top_short, int n_short, mpeghb200_stereo **out);
-void mpeghb200_stereo_destroy(mpeghb200_stereo *s);
+/* Scale-factor-band tables of one sampling rate, shared by the spectral tools (stereo, IGF).
+ * sfb_top_*: upper band edges of one window (ptr_sfb_1024 / ptr_sfb_128 of the stream's sampling rate,
+ * decoder/ia_core_coder_rom.c:1393); they must end at 1024 / 128. */
+typedef struct mpeghb200_bands mpeghb200_bands;
+mpeghb200_status mpeghb200_bands_create(mpeghb200_ctx *ctx, const int16_t *sfb_top_long, int n_long,
+                                        const int16_t *sfb_top_short, int n_short, mpeghb200_bands **out);
+void mpeghb200_bands_destroy(mpeghb200_bands *b);
 size_t mpeghb200_stereo_state_floats(void);
-mpeghb200_status mpeghb200_stereo_dev(mpeghb200_ctx *ctx, const mpeghb200_stereo *s, float *d_coef,
+mpeghb200_status mpeghb200_stereo_dev(mpeghb200_ctx *ctx, const mpeghb200_bands *bands, float *d_coef,
                                       const mpeghb200_stereo_pair *d_pairs, const float *d_state, int n_pairs,
                                       void *cuda_stream);
-mpeghb200_status mpeghb200_stereo_save_dev(mpeghb200_ctx *ctx, const mpeghb200_stereo *s, const float *d_coef,
+mpeghb200_status mpeghb200_stereo_save_dev(mpeghb200_ctx *ctx, const mpeghb200_bands *bands, const float *d_coef,
                                            const mpeghb200_stereo_pair *d_pairs, float *d_state, int n_pairs,
                                            void *cuda_stream);
 /* MDST filter table of the complex-prediction tool: curr [4][2][2][7], prev [2][2][7] (host, no GPU needed). */
 void mpeghb200_stereo_mdst_rom(float *curr112, float *prev28);
+
+/* ---- intelligent gap filling (IGF), mono path, on the spectra, in place -----------------------------------
+ * Replaces ia_core_coder_igf_mono (decoder/ia_core_coder_igf_dec.c:2479: whitening :913, energies :1083, gains
+ * and fill :1321) and ia_core_coder_igf_tnf (:2297) for FD long and eight-short blocks.  The host keeps the
+ * bitstream side: ia_core_coder_get_igf_levels / _get_igf_data (:1901, :2048; arithmetic decoding, the level
+ * dequantisation with pow) and the source tiles igf_input_spec it builds while parsing
+ * (decoder/ia_core_coder_arith_dec.c:686-790).  Position in the frame: where ia_core_coder_data_process calls
+ * igf_mono (before or after TNS, igf_after_tns_synth).
+ * d_tiles [n][4][1024]: the unit's four source tiles (tile t of the reference lives at igf_input_spec +
+ * 2048 * t; the first 1024 floats of each are used by FD blocks), consumed (whitened in place is NOT written
+ * back).  d_tnf_state [n_units][2048], zero-initialised, indexed by side.unit: igf_tnf_spec_float / igf_tnf_mask,
+ * which persist in the reference handle.  d_seed_out [n]: seed_value[ch] after the frame (the noise-filling
+ * parser of the next frame continues from it). */
+typedef struct mpeghb200_igf_side {
+  int32_t unit;   /* channel-frame index into d_coef [n_units][1024] and d_tnf_state */
+  uint32_t seed;  /* seed_value[ch] before the frame */
+  uint8_t win_type; /* igf_win_type: 0 long block, 1 eight short */
+  uint8_t sfb_start, sfb_stop, igf_min; /* igf_grid[win_type] of the element (ia_core_coder_igf_init :2171) */
+  uint8_t use_high_res, use_whitening, use_tnf;
+  uint8_t all_zero, is_tnf; /* igf_all_zero, igf_is_tnf of the frame */
+  uint8_t num_groups;
+  uint8_t pad[2];
+  uint8_t group_len[8];
+  uint8_t tile_num[4];        /* igf_tile_num */
+  uint8_t whitening_level[4]; /* igf_whitening_level */
+  float levels[128];          /* igf_levels_curr_float: long [band], short [16 * group + band] */
+} mpeghb200_igf_side;
+mpeghb200_status mpeghb200_igf_dev(mpeghb200_ctx *ctx, const mpeghb200_bands *bands, float *d_coef,
+                                   const float *d_tiles, const mpeghb200_igf_side *d_side, float *d_tnf_state,
+                                   uint32_t *d_seed_out, int n_units, void *cuda_stream);
+/* whitening gain tables [2][64] (host, no GPU needed): pinned against the reference ROM by the tests */
+void mpeghb200_igf_whitening_rom(float *out128);
 
 /* ---- output resampler ------------------------------------------------------------------------------------
  * Replaces impeghd_resample (decoder/impeghd_resampler.c:93): fac_up/fac_down = 2/1, 3/1 or 3/2

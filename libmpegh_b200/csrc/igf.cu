@@ -1,0 +1,472 @@
+// igf.cu -- intelligent gap filling of FD channel-frames, mono path, in place on the spectra.
+//
+// Stands in for ia_core_coder_igf_mono (decoder/ia_core_coder_igf_dec.c:2479) -- source-tile whitening (:913),
+// band energies of the coded spectrum and of the mapped source (:1083; tile mapping :726-880), group
+// normalisation (:1002), energy-matching gain and fill of the zero bins (:1321) with random-sign noise for
+// whitening level 2 (:882) -- followed by ia_core_coder_igf_tnf (:2297): temporal noise flattening of the filled
+// range (detect :503, reflection / prediction coefficients :330-416, filter :418).  Long blocks (igf_win_type 0)
+// and eight-short blocks (type 1); TCX window types 2/3 belong to the LPD path, which stays on the host.
+//
+// One CTA of 256 threads per channel-frame, everything staged in shared memory (coded spectrum 4 KB, four source
+// tiles 16 KB, mapped source 4 KB, TNF buffers 8 KB).  What the reference does bin after bin splits into
+//   * per-bin work (whitening envelope, tile / source-bin mapping, fill, TNF FIR): 4 bins per thread,
+//   * strictly ordered float sums (band energies, TNF norms and autocorrelations): one thread per sum, in the
+//     reference's order, so every partial sum rounds as it does there,
+//   * the noise generator: the reference draws one LCG step per zero bin of a level-2 tile in bin order; a block
+//     scan gives each such bin its draw index k and the thread jumps the LCG by k + 1 steps (affine powers),
+//   * scalar chains (gains with double sqrt, Levinson recursion of order 8): one thread.
+// Bytes per channel-frame: spectrum 4096 r + 4096 w, tiles 16384 r, side 548 r; long blocks with TNF enabled
+// also write the 8 KB of carried TNF buffers (igf_tnf_spec_float / igf_tnf_mask persist in the reference handle
+// and are re-applied by a frame that signals TNF on top of igf_all_zero).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "common.h"
+#include "bands.h"
+
+namespace mpeghb200 {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kFrame = 1024;
+constexpr float kNoise = 2097152.0f;
+
+struct IgfRom {
+  float whiten[2][64];  // [0]: 2^((42-n)/2) as the reference ROM prints it, [1]: 2^21 * 2^(n/2)
+  float acf_win[8];
+  uint32_t lcg_a[11], lcg_c[11];  // x -> a x + c composed 2^b times
+};
+
+__device__ __forceinline__ uint32_t lcg_jump(uint32_t seed, uint32_t steps, const IgfRom& R) {
+#pragma unroll
+  for (int b = 0; b < 11; ++b)
+    if (steps & (1u << b)) seed = seed * R.lcg_a[b] + R.lcg_c[b];
+  return seed;
+}
+
+struct Grid {
+  int n_tiles, tile[4];
+  int bgn, end;
+};
+
+__device__ __forceinline__ int tile_of(int tb, const Grid& G) {
+  int t, sum = G.bgn;
+  for (t = 0; t < G.n_tiles; ++t) {
+    sum += G.tile[t];
+    if (tb < sum) break;
+  }
+  return t;
+}
+
+__device__ __forceinline__ int source_bin(int igf_min, int tb, const Grid& G, const uint8_t* tile_num) {
+  const int src = G.bgn - igf_min;
+  int sbs = G.bgn, offset = 0, sb = tb;
+  if (src > 0) {
+    for (int i = 0; i < G.n_tiles; ++i) {
+      if (tb >= sbs && tb < sbs + G.tile[i]) {
+        const float sel = float(int8_t(tile_num[i]));
+        offset = int(fsub(fadd(fmul(fadd(2.5f, fmul(-0.5f, sel)), float(G.tile[i])), float(sbs)), float(G.bgn)));
+        offset += offset % 2;
+        break;
+      }
+      sbs += G.tile[i];
+    }
+    sb = tb - offset;
+    if (sb < igf_min) sb = igf_min + tb % src;
+  }
+  return sb;
+}
+
+__global__ void __launch_bounds__(kThreads)
+    igf_kernel(float* __restrict__ coef_g, const float* __restrict__ tiles_g,
+               const mpeghb200_igf_side* __restrict__ sides, float* __restrict__ tnf_state,
+               uint32_t* __restrict__ seed_out, const int16_t* __restrict__ sfb_long, int n_long,
+               const int16_t* __restrict__ sfb_short, int n_short, const IgfRom R) {
+  __shared__ mpeghb200_igf_side sd;
+  __shared__ __align__(16) float coef[kFrame];
+  __shared__ __align__(16) float tiles[4 * kFrame];
+  __shared__ __align__(16) float val[kFrame];   // mapped source value of every bin of the IGF range (noise incl.)
+  __shared__ __align__(16) float tnf[kFrame];   // igf_tnf_spec_float
+  __shared__ __align__(16) float tbuf[kFrame];  // unfiltered copy for the FIR / igf_tnf_mask staging
+  __shared__ float gn[128];                     // gains, [16 * group + sfb] (long: [sfb])
+  __shared__ int16_t swb[72];
+  __shared__ Grid G;
+  __shared__ uint32_t warp_cnt[kThreads / 32];
+  __shared__ float norms[3], acfp[3][8], pred[17];
+  __shared__ int tnf_order;
+
+  const int tid = threadIdx.x;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(sides + blockIdx.x);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sd);
+    for (int i = tid; i < int(sizeof(sd) / 4); i += kThreads) dst[i] = src[i];
+  }
+  __syncthreads();
+  const bool is_short = sd.win_type == 1;
+  const int bins = is_short ? 128 : kFrame;
+  const int n_sfb = is_short ? n_short : n_long;
+  const bool noise_ok = !is_short && sd.use_whitening;
+  const bool tnf_on = sd.use_tnf && !is_short;
+  const bool do_tnf = tnf_on && sd.is_tnf == 1;
+  const bool all_zero = sd.all_zero != 0;
+  if (all_zero && !do_tnf) {
+    if (tid == 0) seed_out[blockIdx.x] = sd.seed;
+    return;
+  }
+  float* cg = coef_g + size_t(sd.unit) * kFrame;
+  float* stg = tnf_state ? tnf_state + size_t(sd.unit) * 2 * kFrame : nullptr;
+
+  // ---- stage: band edges, spectrum, tiles -----------------------------------------------------------
+  for (int i = tid; i <= n_sfb; i += kThreads) swb[i] = i ? (is_short ? sfb_short : sfb_long)[i - 1] : 0;
+  reinterpret_cast<float4*>(coef)[tid] = reinterpret_cast<const float4*>(cg)[tid];
+  if (!all_zero) {
+    const float4* tg = reinterpret_cast<const float4*>(tiles_g + size_t(blockIdx.x) * 4 * kFrame);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) reinterpret_cast<float4*>(tiles)[t * 256 + tid] = tg[t * 256 + tid];
+  }
+  __syncthreads();
+  if (tid == 0) {  // tile widths of the grid (ia_core_coder_igf_get_num_tiles :760)
+    const int s0 = sd.sfb_start, s1 = sd.sfb_stop;
+    const int bgn = swb[s0], end = swb[s1];
+    int range = end - bgn < 8 ? 8 : end - bgn, mem = s0, sbs = bgn, n = 0;
+    int tile[4] = {range >> 2, range >> 2, range >> 2, range >> 2};
+    if (bgn > sd.igf_min && bgn < end) {
+      for (int i = 0; i < 4; ++i) {
+        const int lim = min(sbs + tile[i], end);
+        int j = 1;
+        while (lim > swb[j]) ++j;
+        if (!sd.use_high_res) {
+          if (i == 3)
+            j = s1;
+          else if ((((j - s0) & 1) == 1) && ((j - mem) > 1))
+            --j;
+          mem = j;
+        }
+        tile[i] = max(2, min(swb[j] - sbs, end - sbs));
+        ++n;
+        sbs += tile[i];
+        if (sbs == end) break;
+      }
+    }
+    for (int i = 0; i < 4; ++i) G.tile[i] = i < n ? tile[i] : 0;
+    G.n_tiles = n, G.bgn = bgn, G.end = end;
+  }
+  __syncthreads();
+  const int bgn = G.bgn, end = G.end;
+
+  if (!all_zero) {
+    // ---- whitening of the level-0 source tiles (long blocks) -----------------------------------------
+    if (noise_ok) {
+      const int lo = sd.igf_min, stop = bgn;
+      for (int t = 0; t < G.n_tiles; ++t) {
+        if (sd.whitening_level[t] != 0) continue;  // uniform
+        const float* x = tiles + t * kFrame;
+        float out[4];
+        bool has[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = 4 * tid + k;
+          has[k] = i >= lo && i < stop;
+          out[k] = 0.0f;
+          if (has[k]) {
+            const int ie = i < stop - 3 ? i : stop - 4;  // the last three bins reuse the gain of bin stop - 4
+            float fac = 0.0f;
+            if (ie >= lo) {
+              float env = 1e-3f;
+#pragma unroll
+              for (int j = -3; j <= 3; ++j) env = fadd(env, fmul(x[ie + j], x[ie + j]));
+              // the reference searches its power-of-two tables: floor(log2 env) above 1, ceil(-log2 env) below
+              const int ex = int((__float_as_uint(env) >> 23) & 0xff) - 127;
+              fac = env >= 1.0f ? R.whiten[0][ex & 63] : R.whiten[1][(-ex) & 63];
+            }
+            out[k] = fmul(x[i], fac);
+          }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (has[k]) tiles[t * kFrame + 4 * tid + k] = out[k];
+        __syncthreads();
+      }
+    }
+
+    // ---- map every bin of the IGF range to its source value; number the noise draws ---------------------
+    uint32_t my_noise = 0;
+    bool noise[4];
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = 4 * tid + k;
+      const int w = is_short ? i >> 7 : 0;
+      const int b = i - w * bins;
+      noise[k] = false;
+      v[k] = 0.0f;
+      if (b >= bgn && b < end) {
+        const int ix = tile_of(b, G);
+        const int sb = source_bin(sd.igf_min, b, G, sd.tile_num);
+        v[k] = tiles[ix * kFrame + w * bins + sb];
+        noise[k] = noise_ok && coef[i] == 0.0f && sd.whitening_level[ix] == 2;
+        my_noise += noise[k];
+      }
+    }
+    // exclusive block scan of the draw counts (bin order == the reference's band-by-band order)
+    uint32_t incl = my_noise;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+      if ((tid & 31) >= d) incl += o;
+    }
+    if ((tid & 31) == 31) warp_cnt[tid >> 5] = incl;
+    __syncthreads();
+    uint32_t base = 0, total = 0;
+#pragma unroll
+    for (int wv = 0; wv < kThreads / 32; ++wv) {
+      if (wv < (tid >> 5)) base += warp_cnt[wv];
+      total += warp_cnt[wv];
+    }
+    uint32_t kdraw = base + incl - my_noise;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (noise[k]) {
+        const uint32_t s = lcg_jump(sd.seed, ++kdraw, R);
+        v[k] = fmul((s & 0x10000u) ? -1.0f : 1.0f, kNoise);
+      }
+      val[4 * tid + k] = v[k];
+    }
+    if (tid == 0) seed_out[blockIdx.x] = lcg_jump(sd.seed, total, R);  // the energy pass drew the same count
+    __syncthreads();
+
+    // ---- band energies per (group, band), windows of a group in order (:1083, :1002) ---------------------
+    const int step = (sd.use_high_res || is_short) ? 1 : 2;
+    if (tid < 128) {
+      const int g = is_short ? tid >> 4 : 0;
+      const int sfb = is_short ? tid & 15 : tid;
+      const bool live = g < sd.num_groups && sfb >= sd.sfb_start && sfb < sd.sfb_stop &&
+                        ((sfb - sd.sfb_start) % step) == 0 && (is_short || tid < 64);
+      if (live) {
+        int w0 = 0;
+        for (int q = 0; q < g; ++q) w0 += sd.group_len[q];
+        const int hi = min(sfb + step, int(sd.sfb_stop));
+        float s_acc = 0.0f, p_acc = 0.0f;
+        for (int q = 0; q < sd.group_len[g]; ++q) {
+          const float* c = coef + (w0 + q) * bins;
+          const float* sv = val + (w0 + q) * bins;
+          float e = 0.0f, pe = 0.0f;
+          for (int b = swb[sfb]; b < swb[hi]; ++b) {
+            const float cb = c[b];
+            e = fadd(e, fmul(cb, cb));
+            if (cb == 0.0f) pe = fadd(pe, fmul(sv[b], sv[b]));
+          }
+          s_acc = fadd(s_acc, e);
+          p_acc = fadd(p_acc, pe);
+        }
+        const float gl = float(sd.group_len[g]);
+        s_acc = __fdiv_rn(s_acc, gl);
+        p_acc = __fdiv_rn(p_acc, gl);
+        const int width = swb[hi] - swb[sfb];
+        const float lev = sd.levels[(is_short ? 16 * g : 0) + sfb];
+        const float mn = fsub(fmul(fmul(lev, lev), float(width)), s_acc);
+        float gain = 0.0f;
+        if (0.0f < mn && 0.0f < p_acc) {
+          gain = float(__dsqrt_rn(__ddiv_rn(double(mn), double(p_acc))));
+          gain = gain < 10.f ? gain : 10.f;
+        }
+        const int slot = (is_short ? 16 * g : 0) + sfb;
+        gn[slot] = gain;
+        if (step == 2 && sfb + 1 < sd.sfb_stop) gn[slot + 1] = gain;  // both bands of a low-resolution pair
+      }
+    }
+    __syncthreads();
+
+    // ---- fill the zero bins (:1321) -------------------------------------------------------------------
+    int sfb_of = sd.sfb_start;  // band of this thread's first bin: linear search once, bins are consecutive
+    {
+      const int i = 4 * tid, w = is_short ? i >> 7 : 0, b = i - w * bins;
+      while (sfb_of + 1 < n_sfb && swb[sfb_of + 1] <= b) ++sfb_of;
+    }
+    // group of each window (short blocks)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = 4 * tid + k;
+      const int w = is_short ? i >> 7 : 0;
+      const int b = i - w * bins;
+      float spec = 0.0f, mask = 1.0f;
+      if (b >= bgn && b < end) {
+        while (sfb_of + 1 < n_sfb && swb[sfb_of + 1] <= b) ++sfb_of;
+        int g = 0;
+        if (is_short) {
+          int acc = sd.group_len[0];
+          while (w >= acc) acc += sd.group_len[++g];
+        }
+        const float gv = fmul(gn[(is_short ? 16 * g : 0) + sfb_of], val[i]);
+        spec = gv;
+        if (coef[i] == 0.0f) {
+          coef[i] = gv;
+          mask = 0.0f;
+        }
+      }
+      tnf[i] = spec;
+      tbuf[i] = mask;
+    }
+    __syncthreads();
+    if (tnf_on && stg && !do_tnf) {  // leave the buffers behind for a later all-zero frame
+      reinterpret_cast<float4*>(stg)[tid] = reinterpret_cast<const float4*>(tnf)[tid];
+      reinterpret_cast<float4*>(stg + kFrame)[tid] = reinterpret_cast<const float4*>(tbuf)[tid];
+    }
+  } else {
+    // igf_all_zero with TNF signalled: the reference flattens and applies what its buffers still hold
+    if (tid == 0) seed_out[blockIdx.x] = sd.seed;
+    reinterpret_cast<float4*>(tnf)[tid] = reinterpret_cast<const float4*>(stg)[tid];
+    reinterpret_cast<float4*>(tbuf)[tid] = reinterpret_cast<const float4*>(stg + kFrame)[tid];
+    __syncthreads();
+  }
+
+  // ---- temporal noise flattening (:503-584, :2297) ------------------------------------------------------
+  if (do_tnf) {
+    const int range = end - bgn;
+    float mask4[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) mask4[k] = tbuf[4 * tid + k];
+    if (stg) reinterpret_cast<float4*>(stg + kFrame)[tid] = make_float4(mask4[0], mask4[1], mask4[2], mask4[3]);
+    __syncthreads();
+    if (tid < 3) {
+      const int a = bgn + range * tid / 3, b = bgn + range * (tid + 1) / 3;
+      float acc = 0.0f;
+      for (int j = a; j < b; ++j) acc = fadd(acc, fmul(tnf[j], tnf[j]));
+      norms[tid] = acc;
+    } else if (tid >= 32 && tid < 56) {
+      const int i = (tid - 32) >> 3, lag = ((tid - 32) & 7) + 1;
+      const int a = bgn + range * i / 3, b = bgn + range * (i + 1) / 3, n = b - a;
+      float acc = 0.0f;
+      if (n - lag) acc = fmul(tnf[a], tnf[a + lag]);
+      for (int j = 1; j < n - lag; ++j) acc = fadd(acc, fmul(tnf[a + j], tnf[a + j + lag]));
+      acfp[i][lag - 1] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float acf[9], par[16], mem[32];
+      int i;
+      for (i = 0; i < 9; ++i) acf[i] = 0.0f;
+      for (i = 0; i < 3 && norms[i] > 0.0000000037f; ++i) {
+        const float fac = __fdiv_rn(1.0f, norms[i]);
+        for (int lag = 1; lag <= 8; ++lag)
+          acf[lag] = fadd(acf[lag], fmul(fac, fmul(R.acf_win[lag - 1], acfp[i][lag - 1])));
+      }
+      int order = 0;
+      for (int q = 0; q < 17; ++q) pred[q] = 0.0f;
+      if (i == 3) {
+        order = 8;
+        acf[0] = 3.0f;
+        const int lo = min(8, range >> 2);
+        for (int q = 0; q < 16; ++q) par[q] = 0.0f;
+        for (int q = 0; q < 32; ++q) mem[q] = 0.0f;
+        float* pm = mem + lo;
+        for (int q = 0; q < lo; ++q) mem[q] = acf[q];
+        for (int q = 0; q < lo; ++q) pm[q] = acf[q + 1];
+        for (int q = 0; q < lo; ++q) {
+          float t = 0.0f;
+          if (mem[0] >= 0.0000152f) t = __fdiv_rn(-pm[q], mem[0]);
+          t = fminf(0.999f, fmaxf(-0.999f, t));
+          par[q] = t;
+          for (int j = q; j < lo; ++j) {
+            const float t2 = fadd(pm[j], fmul(t, mem[j - q]));
+            mem[j - q] = fadd(mem[j - q], fmul(t, pm[j]));
+            pm[j] = t2;
+          }
+        }
+        pred[0] = 1.0f;
+        pred[1] = par[0];
+        for (int q = 1; q < lo; ++q) {
+          int j;
+          for (j = 0; j < (q >> 1); ++j) {
+            const float t = pred[j + 1];
+            pred[j + 1] = fadd(pred[j + 1], fmul(par[q], pred[q - j]));
+            pred[q - j] = fadd(pred[q - j], fmul(par[q], t));
+          }
+          if (q & 1) pred[j + 1] = fadd(pred[j + 1], fmul(par[q], pred[j + 1]));
+          pred[q + 1] = par[q];
+        }
+      }
+      tnf_order = order;
+    }
+    __syncthreads();
+    // FIR over the unfiltered values; each bin adds its taps in the reference's order (i = 1 .. order - 1)
+    float y[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = 4 * tid + k;
+      y[k] = tnf[i];
+      if (i >= bgn && i < end) {
+        const int j = i - bgn;
+        for (int t = 1; t < tnf_order && j >= t; ++t) y[k] = fadd(y[k], fmul(pred[t], tnf[i - t]));
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = 4 * tid + k;
+      tnf[i] = y[k];
+      if (i >= bgn && i < end && mask4[k] == 0.0f) coef[i] = y[k];
+    }
+    if (stg) reinterpret_cast<float4*>(stg)[tid] = make_float4(y[0], y[1], y[2], y[3]);
+    __syncthreads();
+  }
+  reinterpret_cast<float4*>(cg)[tid] = reinterpret_cast<const float4*>(coef)[tid];
+}
+
+IgfRom make_rom() {
+  IgfRom R{};
+  for (int n = 0; n < 64; ++n) {
+    char buf[64];
+    std::snprintf(buf, sizeof(buf), "%.7f", std::pow(2.0, (42 - n) / 2.0));  // the ROM prints seven decimals
+    R.whiten[0][n] = std::strtof(buf, nullptr);
+    R.whiten[1][n] = float(2097152.0 * std::pow(2.0, n / 2.0));
+  }
+  R.whiten[0][41] = 1.4142135f;  // truncated, not rounded, in decoder/ia_core_coder_rom.c:1296
+  const float win[8] = {0.997803f, 0.991211f, 0.980225f, 0.964844f, 0.945068f, 0.920898f, 0.892334f, 0.859375f};
+  std::memcpy(R.acf_win, win, sizeof(win));
+  uint32_t a = 69069u, c = 5u;
+  for (int b = 0; b < 11; ++b) {
+    R.lcg_a[b] = a, R.lcg_c[b] = c;
+    c = a * c + c;
+    a = a * a;
+  }
+  return R;
+}
+
+}  // namespace
+}  // namespace mpeghb200
+
+using namespace mpeghb200;
+
+static_assert(sizeof(mpeghb200_igf_side) == 548, "mpeghb200_igf_side layout");
+
+extern "C" {
+
+void mpeghb200_igf_whitening_rom(float* out128) {
+  if (!out128) return;
+  const IgfRom R = make_rom();
+  std::memcpy(out128, R.whiten, sizeof(R.whiten));
+}
+
+mpeghb200_status mpeghb200_igf_dev(mpeghb200_ctx* ctx, const mpeghb200_bands* bands, float* d_coef,
+                                   const float* d_tiles, const mpeghb200_igf_side* d_side, float* d_tnf_state,
+                                   uint32_t* d_seed_out, int n_units, void* cuda_stream) {
+  if (!ctx || !bands) return MPEGHB200_ERR_BAD_ARG;
+  if (n_units < 0 || (n_units > 0 && (!d_coef || !d_tiles || !d_side || !d_tnf_state || !d_seed_out)))
+    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "igf_dev: null buffer or negative unit count");
+  if (n_units == 0) return MPEGHB200_OK;
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  static const IgfRom R = make_rom();
+  igf_kernel<<<n_units, kThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+      d_coef, d_tiles, d_side, d_tnf_state, d_seed_out, bands->d_sfb_long, bands->n_long, bands->d_sfb_short,
+      bands->n_short, R);
+  ctx->launches.fetch_add(1);
+  MB_CUDA(ctx, cudaGetLastError());
+  return MPEGHB200_OK;
+}
+
+}  // extern "C"

@@ -19,6 +19,7 @@
 #include <new>
 
 #include "common.h"
+#include "bands.h"
 
 namespace mpeghb200 {
 namespace {
@@ -222,13 +223,16 @@ __global__ void __launch_bounds__(kThreads)
 
 using namespace mpeghb200;
 
-struct mpeghb200_stereo {
-  mpeghb200_ctx* ctx = nullptr;
-  uint8_t* d_tables = nullptr;  // [1024 + 128]
-  StereoTables T{};
-};
-
 static_assert(sizeof(mpeghb200_stereo_pair) == 664, "mpeghb200_stereo_pair layout");
+
+static StereoTables stereo_tables(const mpeghb200_bands* b) {
+  StereoTables T{};
+  T.bin2sfb_long = b->d_bin2sfb_long;
+  T.bin2sfb_short = b->d_bin2sfb_short;
+  std::memcpy(T.rom.curr, kMdstCurr, sizeof(kMdstCurr));
+  std::memcpy(T.rom.prev, kMdstPrev, sizeof(kMdstPrev));
+  return T;
+}
 
 extern "C" {
 
@@ -239,16 +243,16 @@ void mpeghb200_stereo_mdst_rom(float* curr112, float* prev28) {
 
 size_t mpeghb200_stereo_state_floats(void) { return kStateFloats; }
 
-mpeghb200_status mpeghb200_stereo_create(mpeghb200_ctx* ctx, const int16_t* sfb_top_long, int n_long,
-                                         const int16_t* sfb_top_short, int n_short, mpeghb200_stereo** out) {
+mpeghb200_status mpeghb200_bands_create(mpeghb200_ctx* ctx, const int16_t* sfb_top_long, int n_long,
+                                        const int16_t* sfb_top_short, int n_short, mpeghb200_bands** out) {
   if (!ctx || !out || !sfb_top_long || !sfb_top_short) return MPEGHB200_ERR_BAD_ARG;
   *out = nullptr;
-  // the band tables must tile the window exactly (they do for every sampling rate of the reference ROM); the
-  // side record addresses at most 128 long bands and 16 bands per short window
-  if (n_long < 1 || n_long > 128 || n_short < 1 || n_short > 16 || sfb_top_long[n_long - 1] != 1024 ||
+  // the band tables must tile the window exactly (they do for every sampling rate of the reference ROM); side
+  // records address at most 64 long bands and 16 bands per short window
+  if (n_long < 1 || n_long > 64 || n_short < 1 || n_short > 16 || sfb_top_long[n_long - 1] != 1024 ||
       sfb_top_short[n_short - 1] != 128)
-    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "stereo_create: band tables must end at 1024 / 128 bins");
-  std::vector<uint8_t> h(1024 + 128);
+    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "bands_create: band tables must end at 1024 / 128 bins");
+  std::vector<uint8_t> h(1024 + 128 + 2 * 64 + 2 * 16);
   auto fill = [&](const int16_t* top, int n, uint8_t* dst, int len) {
     int b = 0;
     for (int s = 0; s < n; ++s) {
@@ -258,32 +262,35 @@ mpeghb200_status mpeghb200_stereo_create(mpeghb200_ctx* ctx, const int16_t* sfb_
     return true;
   };
   if (!fill(sfb_top_long, n_long, h.data(), 1024) || !fill(sfb_top_short, n_short, h.data() + 1024, 128))
-    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "stereo_create: band edges must increase");
-  auto* s = new (std::nothrow) mpeghb200_stereo();
+    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "bands_create: band edges must increase");
+  std::memcpy(h.data() + 1152, sfb_top_long, sizeof(int16_t) * n_long);
+  std::memcpy(h.data() + 1152 + 128, sfb_top_short, sizeof(int16_t) * n_short);
+  auto* s = new (std::nothrow) mpeghb200_bands();
   if (!s) return MPEGHB200_ERR_NO_MEM;
   s->ctx = ctx;
-  if (cudaSetDevice(ctx->device) != cudaSuccess || cudaMalloc(&s->d_tables, h.size()) != cudaSuccess ||
-      cudaMemcpy(s->d_tables, h.data(), h.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+  if (cudaSetDevice(ctx->device) != cudaSuccess || cudaMalloc(&s->d_blob, h.size()) != cudaSuccess ||
+      cudaMemcpy(s->d_blob, h.data(), h.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
     cudaError_t e = cudaGetLastError();
-    if (s->d_tables) cudaFree(s->d_tables);
+    if (s->d_blob) cudaFree(s->d_blob);
     delete s;
-    return cuda_fail(ctx, e, "stereo_create: table upload");
+    return cuda_fail(ctx, e, "bands_create: table upload");
   }
-  s->T.bin2sfb_long = s->d_tables;
-  s->T.bin2sfb_short = s->d_tables + 1024;
-  std::memcpy(s->T.rom.curr, kMdstCurr, sizeof(kMdstCurr));
-  std::memcpy(s->T.rom.prev, kMdstPrev, sizeof(kMdstPrev));
+  s->d_bin2sfb_long = s->d_blob;
+  s->d_bin2sfb_short = s->d_blob + 1024;
+  s->d_sfb_long = reinterpret_cast<const int16_t*>(s->d_blob + 1152);
+  s->d_sfb_short = reinterpret_cast<const int16_t*>(s->d_blob + 1152 + 128);
+  s->n_long = n_long, s->n_short = n_short;
   *out = s;
   return MPEGHB200_OK;
 }
 
-void mpeghb200_stereo_destroy(mpeghb200_stereo* s) {
+void mpeghb200_bands_destroy(mpeghb200_bands* s) {
   if (!s) return;
-  if (s->d_tables) cudaFree(s->d_tables);
+  if (s->d_blob) cudaFree(s->d_blob);
   delete s;
 }
 
-mpeghb200_status mpeghb200_stereo_dev(mpeghb200_ctx* ctx, const mpeghb200_stereo* s, float* d_coef,
+mpeghb200_status mpeghb200_stereo_dev(mpeghb200_ctx* ctx, const mpeghb200_bands* s, float* d_coef,
                                       const mpeghb200_stereo_pair* d_pairs, const float* d_state, int n_pairs,
                                       void* cuda_stream) {
   if (!ctx || !s) return MPEGHB200_ERR_BAD_ARG;
@@ -291,13 +298,14 @@ mpeghb200_status mpeghb200_stereo_dev(mpeghb200_ctx* ctx, const mpeghb200_stereo
     return fail(ctx, MPEGHB200_ERR_BAD_ARG, "stereo_dev: null buffer or negative pair count");
   if (n_pairs == 0) return MPEGHB200_OK;
   MB_CUDA(ctx, cudaSetDevice(ctx->device));
-  stereo_kernel<<<n_pairs, kThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(d_coef, d_pairs, d_state, s->T);
+  stereo_kernel<<<n_pairs, kThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(d_coef, d_pairs, d_state,
+                                                                                       stereo_tables(s));
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   return MPEGHB200_OK;
 }
 
-mpeghb200_status mpeghb200_stereo_save_dev(mpeghb200_ctx* ctx, const mpeghb200_stereo* s, const float* d_coef,
+mpeghb200_status mpeghb200_stereo_save_dev(mpeghb200_ctx* ctx, const mpeghb200_bands* s, const float* d_coef,
                                            const mpeghb200_stereo_pair* d_pairs, float* d_state, int n_pairs,
                                            void* cuda_stream) {
   if (!ctx || !s) return MPEGHB200_ERR_BAD_ARG;

@@ -209,9 +209,13 @@ class Lib:
         c.mpeghb200_resampler_out_len.restype = ctypes.c_int
         c.mpeghb200_resample_dev.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, vp]
         c.mpeghb200_resample_dev.restype = i32
-        c.mpeghb200_stereo_create.argtypes = [vp, vp, ctypes.c_int, vp, ctypes.c_int, ctypes.POINTER(vp)]
-        c.mpeghb200_stereo_create.restype = i32
-        c.mpeghb200_stereo_destroy.argtypes = [vp]
+        c.mpeghb200_bands_create.argtypes = [vp, vp, ctypes.c_int, vp, ctypes.c_int, ctypes.POINTER(vp)]
+        c.mpeghb200_bands_create.restype = i32
+        c.mpeghb200_bands_destroy.argtypes = [vp]
+        c.mpeghb200_igf_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
+        c.mpeghb200_igf_dev.restype = i32
+        c.mpeghb200_igf_whitening_rom.argtypes = [vp]
+        c.mpeghb200_igf_whitening_rom.restype = None
         c.mpeghb200_stereo_state_floats.argtypes = []
         c.mpeghb200_stereo_state_floats.restype = sz
         c.mpeghb200_stereo_dev.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, vp]
@@ -311,16 +315,25 @@ class Lib:
         self.check(self.c.mpeghb200_tns_dev(self.ctx, d_coef, d_filters, d_chain_first, n_chains, stream))
 
     # ---- joint-stereo tools -------------------------------------------------------------------------
-    def stereo_create(self, sfb_long, sfb_short):
+    def bands_create(self, sfb_long, sfb_short):
         a = np.ascontiguousarray(sfb_long, np.int16)
         b = np.ascontiguousarray(sfb_short, np.int16)
         h = ctypes.c_void_p()
-        self.check(self.c.mpeghb200_stereo_create(self.ctx, a.ctypes.data, len(a), b.ctypes.data, len(b),
-                                                  ctypes.byref(h)))
+        self.check(self.c.mpeghb200_bands_create(self.ctx, a.ctypes.data, len(a), b.ctypes.data, len(b),
+                                                 ctypes.byref(h)))
         return h
 
-    def stereo_destroy(self, h):
-        self.c.mpeghb200_stereo_destroy(h)
+    def bands_destroy(self, h):
+        self.c.mpeghb200_bands_destroy(h)
+
+    def igf_dev(self, bands, d_coef, d_tiles, d_side, d_tnf_state, d_seed_out, n_units, stream=0):
+        self.check(self.c.mpeghb200_igf_dev(self.ctx, bands, d_coef, d_tiles, d_side, d_tnf_state, d_seed_out,
+                                            n_units, stream))
+
+    def igf_whitening_rom(self):
+        t = np.zeros((2, 64), np.float32)
+        self.c.mpeghb200_igf_whitening_rom(t.ctypes.data)
+        return t
 
     def stereo_state_floats(self):
         return int(self.c.mpeghb200_stereo_state_floats())

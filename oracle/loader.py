@@ -102,6 +102,11 @@ def load_oracle():
     lib.oracle_stereo_set_rom.argtypes = [_f32p, _f32p]
     lib.oracle_stereo_apply.argtypes = [ctypes.c_char_p, _i16p, ctypes.c_int, _f32p, _f32p, _f32p]
     lib.oracle_stereo_save.argtypes = [ctypes.c_char_p, _f32p, _f32p, _f32p]
+    lib.oracle_igf_mono.argtypes = [ctypes.c_char_p, _i16p, ctypes.c_int, _f32p, _f32p, _f32p]
+    lib.oracle_igf_mono.restype = ctypes.c_uint
+    lib.oracle_igf_tiles.argtypes = [ctypes.c_int] * 4 + [_i16p, _i32p]
+    lib.oracle_igf_tiles.restype = ctypes.c_int
+    lib.oracle_igf_whitening_table.argtypes = [_f32p]
     sg_path = os.path.join(ROOT, "tests", "golden", "stereo_golden.npz")
     if os.path.exists(sg_path):  # MDST filter ROM of the complex-prediction tool (absent only while it is being made)
         sg = np.load(sg_path)
@@ -224,6 +229,12 @@ def load_ref():
                                     _f32p, _f32p, _f32p, _f32p, _f32p]
     lib.ref_cpe_process.restype = ctypes.c_int
     lib.ref_mdst_rom.argtypes = [_f32p, _f32p]
+    lib.ref_igf_create.restype = ctypes.c_void_p
+    lib.ref_igf_create.argtypes = [ctypes.c_int] * 7
+    lib.ref_igf_destroy.argtypes = [ctypes.c_void_p]
+    lib.ref_igf_grid.argtypes = [ctypes.c_void_p, _i32p]
+    lib.ref_igf_process.argtypes = [ctypes.c_void_p, ctypes.c_char_p, _f32p, _f32p]
+    lib.ref_igf_process.restype = ctypes.c_uint
     lib.ref_rs_create.restype = ctypes.c_void_p
     lib.ref_rs_create.argtypes = [ctypes.c_int, ctypes.c_int]
     lib.ref_rs_destroy.argtypes = [ctypes.c_void_p]

@@ -247,3 +247,83 @@ void ref_mdst_rom(float *curr /*[4][2][2][7]*/, float *prev /*[2][2][7]*/)
       for (k = 0; k < 7; k++)
         prev[(c * 2 + a) * 7 + k] = prv[c][a][k];
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * IGF, mono path: ia_core_coder_igf_init (decoder/ia_core_coder_igf_dec.c:2171) derives the grid from the
+ * configuration indices, then per frame ia_core_coder_igf_mono (:2479) + ia_core_coder_igf_tnf (:2297), called
+ * the way ia_core_coder_data_process does (:1880-1890).
+ * ---------------------------------------------------------------------------------------------- */
+#include "ia_core_coder_igf_dec.h"
+
+typedef struct
+{
+  ref_cpe_handle cpe;
+} ref_igf_handle;
+
+void *ref_igf_create(int sampling_rate_idx, int sample_rate, int igf_start_index, int igf_stop_index, int use_high_res,
+                     int use_whitening, int use_enf)
+{
+  ref_cpe_handle *h = (ref_cpe_handle *)ref_cpe_create(sampling_rate_idx, 0, 0);
+  ia_usac_dec_element_config_struct ele;
+  if (!h)
+    return 0;
+  memset(&ele, 0, sizeof(ele));
+  ele.enhanced_noise_filling = 1;
+  ele.str_usac_ele_igf_init_config.igf_use_enf = (WORD8)use_enf;
+  ele.str_usac_ele_igf_init_config.igf_use_whitening = (WORD8)use_whitening;
+  ele.str_usac_ele_igf_init_config.igf_independent_tilling = 1;
+  ele.str_usac_ele_igf_init_config.igf_start_index = (WORD8)igf_start_index;
+  ele.str_usac_ele_igf_init_config.igf_stop_index = (WORD8)igf_stop_index;
+  ele.str_usac_ele_igf_init_config.igf_use_high_resolution = (WORD8)use_high_res;
+  ia_core_coder_igf_init(&h->usac, &ele, ID_USAC_SCE, 0, (UINT32)sample_rate, 0);
+  return h;
+}
+
+void ref_igf_destroy(void *p) { free(p); }
+
+/* out[2][4] = {sfb_start, sfb_stop, igf_min, num_tiles} of the long and the short grid */
+void ref_igf_grid(void *p, int *out)
+{
+  ref_cpe_handle *h = (ref_cpe_handle *)p;
+  int g;
+  for (g = 0; g < 2; g++)
+  {
+    const ia_usac_igf_grid_config_struct *q = &h->usac.igf_config[0].igf_grid[g];
+    out[4 * g + 0] = q->igf_sfb_start, out[4 * g + 1] = q->igf_sfb_stop;
+    out[4 * g + 2] = q->igf_min, out[4 * g + 3] = q->igf_num_tiles;
+  }
+}
+
+/* one channel-frame: coef [1024] in place, tiles [4][1024] (source tiles, window-major inside a tile);
+ * returns seed_value after the frame */
+unsigned int ref_igf_process(void *p, const oracle_igf_side *sd, float *coef, const float *tiles)
+{
+  ref_cpe_handle *h = (ref_cpe_handle *)p;
+  ia_usac_data_struct *u = &h->usac;
+  ia_usac_igf_config_struct *cfg = &u->igf_config[0];
+  ia_usac_igf_dec_data_struct *d = &u->igf_dec_data[0];
+  ia_usac_igf_bitstream_struct *bs = &d->igf_bitstream[0];
+  const int win = sd->win_type == 1 ? EIGHT_SHORT_SEQUENCE : ONLY_LONG_SEQUENCE;
+  WORD16 group_len[8];
+  int t, g, sfb;
+  for (t = 0; t < 4; t++)
+  {
+    memset(&d->igf_input_spec[t * MAX_IGF_LEN], 0, MAX_IGF_LEN * sizeof(FLOAT32));
+    memcpy(&d->igf_input_spec[t * MAX_IGF_LEN], tiles + t * 1024, 1024 * sizeof(FLOAT32));
+    bs->igf_tile_num[t] = (WORD8)sd->tile_num[t];
+    bs->igf_whitening_level[t] = sd->whitening_level[t];
+  }
+  bs->igf_all_zero = sd->all_zero;
+  bs->igf_is_tnf = (WORD8)sd->is_tnf;
+  for (g = 0; g < 8; g++)
+  {
+    group_len[g] = sd->group_len[g];
+    for (sfb = 0; sfb < (sd->win_type == 1 ? 16 : 64) && sfb < NSFB_LONG; sfb++)
+      bs->igf_levels_curr_float[g][sfb] = sd->levels[(sd->win_type == 1 ? 16 * g : 0) + sfb];
+  }
+  u->seed_value[0] = sd->seed;
+  ia_core_coder_igf_mono(u, cfg, 0, sd->win_type, sd->win_type, sd->num_groups, group_len,
+                         sd->win_type == 1 ? 128 : 1024, win, coef, h->fft_scratch);
+  ia_core_coder_igf_tnf(u, cfg, 0, sd->win_type, sd->win_type, win, coef, h->fft_scratch);
+  return u->seed_value[0];
+}

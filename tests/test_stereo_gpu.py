@@ -20,13 +20,13 @@ class GpuPairs:
     def __init__(self, lib, n_pairs):
         import torch
         self.torch, self.lib, self.n = torch, lib, n_pairs
-        self.h = lib.stereo_create(stereo_cases.SFB_LONG, stereo_cases.SFB_SHORT)
+        self.h = lib.bands_create(stereo_cases.SFB_LONG, stereo_cases.SFB_SHORT)
         self.state = torch.zeros(n_pairs, lib.stereo_state_floats(), device="cuda")
         self.ovl = torch.zeros(2 * n_pairs, 1024, device="cuda")
         self.stream = torch.cuda.current_stream().cuda_stream
 
     def close(self):
-        self.lib.stereo_destroy(self.h)
+        self.lib.bands_destroy(self.h)
 
     def _tns(self, d_coef, frames, which):
         from libmpegh_b200.lib import TNS_FILTER_DTYPE
@@ -116,7 +116,7 @@ def test_stereo_edge_cases(gpu_lib, oracle):
     """tool 0 leaves the spectra alone; save modes 0/1/2; signed zeros survive (the '+ 0' of the MDST estimate)."""
     import torch
     lib = gpu_lib
-    h = lib.stereo_create(stereo_cases.SFB_LONG, stereo_cases.SFB_SHORT)
+    h = lib.bands_create(stereo_cases.SFB_LONG, stereo_cases.SFB_SHORT)
     rng = np.random.default_rng(5)
     n = 8
     sds = np.zeros(n, stereo_cases.STEREO_SIDE)
@@ -146,4 +146,4 @@ def test_stereo_edge_cases(gpu_lib, oracle):
         assert bits_equal(got[2 * p], l) and bits_equal(got[2 * p + 1], r), p
         assert bits_equal(got_state[p], stt), p
     lib.stereo_dev(h, 0, 0, 0, 0, st)  # zero pairs: accepted, nothing launched
-    lib.stereo_destroy(h)
+    lib.bands_destroy(h)
