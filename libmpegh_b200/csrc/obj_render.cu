@@ -53,10 +53,15 @@ struct DevLayout {
   int n_lfe;
 };
 
-__device__ void one_source_point(const DevLayout& L, float vx, float vy, float vz, float* ls) {
-  int winner = 0, hi_lo = 3;
+// One source direction -> gains of the best triangle, accumulated into ls[] (impeghd_calc_one_source_point :156).
+// The reference scans the triangles in order and keeps a candidate when it has fewer negative gains, or as many
+// and a larger smallest gain: a strict lexicographic improvement, so the survivor is the lexicographic best with
+// the lowest index among exact ties -- which a warp can find with one triangle per lane and a shuffle reduction.
+// Called by all 32 lanes of a warp with identical arguments; ls[] lives in shared memory.
+__device__ void one_source_point(const DevLayout& L, float vx, float vy, float vz, float* ls, int lane) {
+  int winner = 0x7fffffff, hi_lo = 3;
   float highest_least = -100000.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
-  for (int i = 0; i < L.n_tri; ++i) {
+  for (int i = lane; i < L.n_tri; i += 32) {
     float gains[3], min_gain = 10000000.f;
     int neg = 3;
 #pragma unroll
@@ -76,6 +81,17 @@ __device__ void one_source_point(const DevLayout& L, float vx, float vy, float v
       winner = i;
     }
   }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    const int o_neg = __shfl_xor_sync(0xffffffffu, hi_lo, d), o_win = __shfl_xor_sync(0xffffffffu, winner, d);
+    const float o_least = __shfl_xor_sync(0xffffffffu, highest_least, d);
+    const float o0 = __shfl_xor_sync(0xffffffffu, g0, d), o1 = __shfl_xor_sync(0xffffffffu, g1, d),
+                o2 = __shfl_xor_sync(0xffffffffu, g2, d);
+    const bool take = (o_neg < hi_lo) || (o_neg == hi_lo && (o_least > highest_least ||
+                                                              (o_least == highest_least && o_win < winner)));
+    if (take) hi_lo = o_neg, highest_least = o_least, winner = o_win, g0 = o0, g1 = o1, g2 = o2;
+  }
+  if (winner == 0x7fffffff) winner = 0;  // nothing beat the initial state: the reference keeps triangle 0, gains 0
   if (g2 < 0.f) g2 = 0.f;  // covers both the -0.01 test (:204-210) and the < 0 clamps (:224-235)
   if (g1 < 0.f) g1 = 0.f;
   if (g0 < 0.f) g0 = 0.f;
@@ -85,10 +101,13 @@ __device__ void one_source_point(const DevLayout& L, float vx, float vy, float v
     g1 = __fdiv_rn(g1, power);
     g2 = __fdiv_rn(g2, power);
   }
-  const int i2 = __ldg(&L.tri[winner][2]), i1 = __ldg(&L.tri[winner][1]), i0 = __ldg(&L.tri[winner][0]);
-  ls[i2] = fadd(g2, ls[i2]);
-  ls[i1] = fadd(g1, ls[i1]);
-  ls[i0] = fadd(g0, ls[i0]);
+  if (lane == 0) {
+    const int i2 = __ldg(&L.tri[winner][2]), i1 = __ldg(&L.tri[winner][1]), i0 = __ldg(&L.tri[winner][0]);
+    ls[i2] = fadd(g2, ls[i2]);
+    ls[i1] = fadd(g1, ls[i1]);
+    ls[i0] = fadd(g0, ls[i0]);
+  }
+  __syncwarp();
 }
 
 struct V3 {
@@ -103,18 +122,26 @@ __device__ __forceinline__ V3 sva(V3 a, float ga, V3 b, float gb) {
 }
 
 // scratch per (stream, object): [n_non_lfe][2] = {ramp start, ramp step}
-__global__ void __launch_bounds__(128)
+// One warp per (stream, object).  The triangle search runs one triangle per lane; the loudspeaker gain vector
+// ls[] sits in shared memory; the ordered sums of the reference (spread norm, vector norm, power sum) are walked
+// in index order, the imaginary-speaker downmix has one output channel per lane.
+constexpr int kGainWarps = 4;
+
+__global__ void __launch_bounds__(32 * kGainWarps)
     obj_gains_kernel(const DevLayout* __restrict__ Lp, const mpeghb200_obj_side* __restrict__ side,
                      float* __restrict__ state, float* __restrict__ scratch, int n_obj, int n_streams) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float ls_all[kGainWarps][kMaxLs];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int idx = blockIdx.x * kGainWarps + wib;
   if (idx >= n_obj * n_streams) return;
   const DevLayout& L = *Lp;
   const mpeghb200_obj_side s = side[idx];
   const int NL = L.n_non_lfe, tot = NL + L.n_imag;
-  float ls[kMaxLs];
-  for (int i = 0; i < tot; ++i) ls[i] = 0.f;
+  float* ls = ls_all[wib];
+  for (int i = lane; i < tot; i += 32) ls[i] = 0.f;
+  __syncwarp();
   if (s.spread_w <= 0.0f && s.spread_h <= 0.0f) {
-    one_source_point(L, s.vec_c[0], s.vec_c[1], s.vec_c[2], ls);
+    one_source_point(L, s.vec_c[0], s.vec_c[1], s.vec_c[2], ls, lane);
   } else {
     V3 p0{s.p0[0], s.p0[1], s.p0[2]}, v{s.v[0], s.v[1], s.v[2]}, u;
     u.z = fsub(fmul(v.x, p0.y), fmul(v.y, p0.x));
@@ -149,7 +176,7 @@ __global__ void __launch_bounds__(128)
         const float inv = __fdiv_rn(1.0f, vl);
         x = fmul(x, inv), y = fmul(y, inv), z = fmul(z, inv);
       }
-      one_source_point(L, x, y, z, ls);
+      one_source_point(L, x, y, z, ls, lane);
     }
     // impeghd_calc_spread_gains (:113) with the raw width; the double-precision expression is IEEE on both sides
     float alpha = float(double(fmul(s.spread_w, kDeg2Rad)) / (M_PI / 2.0) - 1.0);
@@ -161,113 +188,195 @@ __global__ void __launch_bounds__(128)
     else if (alpha < 0.0f)
       alpha = 0.0f;
     const float oma = fsub(1.f, alpha), au = fmul(alpha, L.unit_gain);
-    for (int i = 0; i < tot; ++i) ls[i] = fadd(__fdiv_rn(fmul(oma, ls[i]), norm), au);
+    __syncwarp();
+    for (int i = lane; i < tot; i += 32) ls[i] = fadd(__fdiv_rn(fmul(oma, ls[i]), norm), au);
+    __syncwarp();
   }
   // impeghd_nrm_values (:82)
   float len = 0.0f;
   for (int i = 0; i < tot; ++i) len = fadd(len, fmul(ls[i], ls[i]));
   len = __fdiv_rn(1.0f, __fsqrt_rn(len));
+  __syncwarp();
   if (len != 0.0f)
-    for (int i = 0; i < tot; ++i) ls[i] = fmul(ls[i], len);
-  // imaginary-speaker downmix + power normalisation (:563-586), then the ramp of impeghd_obj_renderer_dec
-  float fg[24];
+    for (int i = lane; i < tot; i += 32) ls[i] = fmul(ls[i], len);
+  __syncwarp();
+  // imaginary-speaker downmix + power normalisation (:563-586), then the ramp of impeghd_obj_renderer_dec;
+  // output channel = lane
+  float value = 0.f;
+  if (lane < NL)
+    for (int j = 0; j < tot; ++j) value = fadd(value, fmul(__ldg(&L.dmx[lane][j]), ls[j]));
+  const float sq = fmul(value, value);
   float gain_sum = 0.0f;
-  for (int i = 0; i < NL; ++i) {
-    float value = 0.f;
-    for (int j = 0; j < tot; ++j) value = fadd(value, fmul(__ldg(&L.dmx[i][j]), ls[j]));
-    fg[i] = value;
-    gain_sum = fadd(gain_sum, fmul(value, value));
-  }
+  for (int i = 0; i < NL; ++i) gain_sum = fadd(gain_sum, __shfl_sync(0xffffffffu, sq, i));
   gain_sum = __fsqrt_rn(gain_sum);
   float* st = state + size_t(idx) * (NL + 1);
   const bool first = st[0] != 0.0f;
+  __syncwarp();
   float* sc = scratch + size_t(idx) * NL * 2;
-  for (int i = 0; i < NL; ++i) {
-    float f = fg[i];
+  if (lane < NL) {
+    float f = value;
     if (gain_sum != 0.0f) f = __fdiv_rn(fmul(f, s.gain), gain_sum);
-    const float init = first ? f : st[1 + i];
+    const float init = first ? f : st[1 + lane];
     const float step = __fdiv_rn(fsub(f, init), 1024.0f);
-    sc[2 * i] = fadd(init, step);
-    sc[2 * i + 1] = step;
-    st[1 + i] = f;
+    reinterpret_cast<float2*>(sc)[lane] = make_float2(fadd(init, step), step);
+    st[1 + lane] = f;
   }
-  st[0] = 0.0f;
+  if (lane == 0) st[0] = 0.0f;
 }
 
-// One CTA per stream, thread = (output channel, 64-sample chunk).
-//   phase A  ramp values at the 16 chunk boundaries for every (object, channel): a chain of 64 c separately
-//            rounded additions each, computed once per frame into shared memory (threads stride over pairs)
-//   phase B  the mix: 8 samples at a time, the 32 per-object scales of this thread's channel in registers,
-//            object signals read straight from global memory (each 32-byte piece is shared by the channel
-//            threads of the chunk and served by L1)
+// Two CTAs per stream (each takes half of the non-LFE output channels), thread = (output channel, 64-sample chunk).
+//   phase A  ramp values at the 16 chunk boundaries for every (object, channel) of this CTA: a chain of 64 c
+//            separately rounded additions each, computed once per frame into shared memory (two chains per thread
+//            at a time)
+//   phase B  the mix in 16 steps of 4 samples per chunk, the per-object scales and steps of this thread's channel
+//            in registers.  The object signals of a step (16 chunks x NOBJ objects x 16 B) are staged in shared
+//            memory with cp.async, double buffered, so the FP pipe never waits on an L2 / HBM round trip: the
+//            step-0 copy overlaps phase A, the copy of step t + 1 overlaps the arithmetic of step t.
+// NOBJ (8, 16, 24, 32) is the compile-time object count the loops are unrolled for; a stream with fewer objects
+// is padded with zero signals and zero scales, which is exact: the accumulator starts at +0, so adding a (+-0)
+// product never changes it.
 constexpr int kChunks = 16;
 constexpr int kCLen = kFrame / kChunks;  // 64
+constexpr int kStep = 4;                 // samples per chunk and step
+constexpr int kSteps = kCLen / kStep;    // 16
+constexpr int kMixMaxThreads = 12 * kChunks;  // up to 12 channels per CTA (24 non-LFE loudspeakers)
 
-__global__ void __launch_bounds__(384)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+template <int NOBJ>
+struct MixSmem {
+  static constexpr int kChunkStride = NOBJ * kStep + 4;  // floats; +16 B skews the chunks across banks
+  static constexpr int kStageFloats = 2 * kChunks * kChunkStride;
+  static size_t bytes(int n_ch_cta) { return (size_t(kStageFloats) + size_t(NOBJ) * n_ch_cta * (kChunks + 1)) * 4; }
+};
+
+template <int NOBJ>
+__global__ void __launch_bounds__(kMixMaxThreads)
     obj_mix_kernel(const DevLayout* __restrict__ Lp, const float* __restrict__ in, float* __restrict__ out,
                    const float* __restrict__ scratch, int n_obj) {
-  extern __shared__ float bound[];  // [n_obj * NL][kChunks + 1]: chunk-start scales, last = step
+  extern __shared__ __align__(16) float smem_f[];
+  using SM = MixSmem<NOBJ>;
   const DevLayout& L = *Lp;
   const int NL = L.n_non_lfe;
-  const int s = blockIdx.x;
-  const int n_pairs = n_obj * NL;
-  const float* sc = scratch + size_t(s) * n_pairs * 2;
-  for (int p = threadIdx.x; p < n_pairs; p += blockDim.x) {
-    const float2 t = __ldg(reinterpret_cast<const float2*>(sc) + p);
-    float v = t.x;
-    float* b = bound + p * (kChunks + 1);
-    b[kChunks] = t.y;
-    for (int c = 0; c < kChunks; ++c) {
-      b[c] = v;
-#pragma unroll 8
-      for (int k = 0; k < kCLen; ++k) v = fadd(v, t.y);
+  const int s = blockIdx.y;
+  const int half = (NL + 1) / 2;
+  const int c_first = blockIdx.x * half;                       // first channel of this CTA
+  const int n_c = blockIdx.x == 0 ? half : NL - half;          // its channel count
+  const int n_pairs = NOBJ * n_c;                              // (object, channel) chains, padded objects included
+  float* stage = smem_f;                                       // [2][kChunks][kChunkStride]: x[chunk][obj][4]
+  float* bound = smem_f + SM::kStageFloats;                    // [n_pairs][kChunks + 1]: chunk-start scales, step
+  const float* xs = in + size_t(s) * n_obj * kFrame;
+
+  auto issue = [&](int t) {
+    float* dst = stage + (t & 1) * kChunks * SM::kChunkStride;
+    for (int p = threadIdx.x; p < kChunks * NOBJ; p += blockDim.x) {
+      const int chunk = p / NOBJ, o = p % NOBJ;
+      if (o < n_obj)
+        cp_async16(dst + chunk * SM::kChunkStride + o * kStep, xs + size_t(o) * kFrame + chunk * kCLen + t * kStep);
     }
+    cp_async_commit();
+  };
+  if (n_obj < NOBJ)  // padded objects: zero signal in both buffers, never overwritten
+    for (int p = threadIdx.x; p < 2 * kChunks * (NOBJ - n_obj) * kStep; p += blockDim.x) {
+      const int e = p % kStep, q = p / kStep, o = n_obj + q % (NOBJ - n_obj), cb = q / (NOBJ - n_obj);
+      stage[cb * SM::kChunkStride + o * kStep + e] = 0.0f;
+    }
+  issue(0);
+
+  const float* sc = scratch + size_t(s) * n_obj * NL * 2;
+  auto ramp = [&](int p) {  // chain p = o * n_c + c  ->  (start, step) of (object o, channel c_first + c)
+    const int o = p / n_c, c = p - o * n_c;
+    return o < n_obj ? __ldg(reinterpret_cast<const float2*>(sc) + o * NL + c_first + c) : make_float2(0.f, 0.f);
+  };
+  for (int p = threadIdx.x; p < n_pairs; p += 2 * blockDim.x) {
+    const int q = p + blockDim.x;
+    const bool two = q < n_pairs;
+    const float2 t0 = ramp(p);
+    const float2 t1 = two ? ramp(q) : make_float2(0.f, 0.f);
+    float v0 = t0.x, v1 = t1.x;
+    float* b0 = bound + p * (kChunks + 1);
+    float* b1 = bound + (two ? q : p) * (kChunks + 1);
+    for (int c = 0; c < kChunks; ++c) {
+      b0[c] = v0;
+      if (two) b1[c] = v1;
+      if (c + 1 < kChunks) {
+#pragma unroll 8
+        for (int k = 0; k < kCLen; ++k) v0 = fadd(v0, t0.y), v1 = fadd(v1, t1.y);
+      }
+    }
+    b0[kChunks] = t0.y;
+    if (two) b1[kChunks] = t1.y;
   }
   __syncthreads();
-  const int ci = threadIdx.x % NL, chunk = threadIdx.x / NL;
-  if (chunk < kChunks) {
-    float scale[kMaxObj], step[kMaxObj];
+  const int ci = threadIdx.x % n_c, chunk = threadIdx.x / n_c;
+  const bool active = chunk < kChunks;
+  float scale[NOBJ], step[NOBJ];
 #pragma unroll
-    for (int o = 0; o < kMaxObj; ++o) {
-      if (o < n_obj) {
-        const float* b = bound + (o * NL + ci) * (kChunks + 1);
-        scale[o] = b[chunk];
-        step[o] = b[kChunks];
-      } else {
-        scale[o] = 0.f, step[o] = 0.f;
-      }
+  for (int o = 0; o < NOBJ; ++o) {
+    const float* b = bound + (o * n_c + ci) * (kChunks + 1);
+    scale[o] = active ? b[chunk] : 0.f;
+    step[o] = active ? b[kChunks] : 0.f;
+  }
+  float* y = out + (size_t(s) * L.n_spk + L.nonlfe_to_spk[c_first + ci]) * kFrame + (active ? chunk : 0) * kCLen;
+  for (int t = 0; t < kSteps; ++t) {
+    if (t + 1 < kSteps) {
+      issue(t + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
-    const float* x = in + size_t(s) * n_obj * kFrame + chunk * kCLen;
-    float* y = out + (size_t(s) * L.n_spk + L.nonlfe_to_spk[ci]) * kFrame + chunk * kCLen;
-    for (int j = 0; j < kCLen; j += 8) {
-      float acc[8];
+    __syncthreads();
+    if (active) {
+      const float* x = stage + (t & 1) * kChunks * SM::kChunkStride + chunk * SM::kChunkStride;
+      float acc[kStep];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+      for (int e = 0; e < kStep; ++e) acc[e] = 0.0f;
 #pragma unroll
-      for (int o = 0; o < kMaxObj; ++o) {
-        if (o < n_obj) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(x + size_t(o) * kFrame + j));
-          const float4 b = __ldg(reinterpret_cast<const float4*>(x + size_t(o) * kFrame + j + 4));
-          const float xv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-          float sc_o = scale[o];
-          const float st_o = step[o];
+      for (int o = 0; o < NOBJ; ++o) {
+        const float4 a = *reinterpret_cast<const float4*>(x + o * kStep);
+        const float xv[4] = {a.x, a.y, a.z, a.w};
+        float sc_o = scale[o];
+        const float st_o = step[o];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            acc[e] = fadd(acc[e], fmul(xv[e], sc_o));
-            sc_o = fadd(sc_o, st_o);
-          }
-          scale[o] = sc_o;
+        for (int e = 0; e < kStep; ++e) {
+          acc[e] = fadd(acc[e], fmul(xv[e], sc_o));
+          sc_o = fadd(sc_o, st_o);
         }
+        scale[o] = sc_o;
       }
-      __stcs(reinterpret_cast<float4*>(y + j), make_float4(acc[0], acc[1], acc[2], acc[3]));
-      __stcs(reinterpret_cast<float4*>(y + j + 4), make_float4(acc[4], acc[5], acc[6], acc[7]));
+      __stcs(reinterpret_cast<float4*>(y + t * kStep), make_float4(acc[0], acc[1], acc[2], acc[3]));
     }
+    __syncthreads();  // the buffer of step t is overwritten by the copy issued in iteration t + 1
   }
   // LFE rows stay zero (decode_main.c:1374 memset)
-  for (int l = 0; l < L.n_lfe; ++l) {
-    float4* z = reinterpret_cast<float4*>(out + (size_t(s) * L.n_spk + L.lfe_spk[l]) * kFrame);
-    for (int j = threadIdx.x; j < kFrame / 4; j += blockDim.x) z[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (blockIdx.x == 0)
+    for (int l = 0; l < L.n_lfe; ++l) {
+      float4* z = reinterpret_cast<float4*>(out + (size_t(s) * L.n_spk + L.lfe_spk[l]) * kFrame);
+      for (int j = threadIdx.x; j < kFrame / 4; j += blockDim.x) z[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+template <int NOBJ>
+cudaError_t launch_mix(const DevLayout* dl, int NL, const float* d_in, float* d_out, const float* d_scratch, int n_obj,
+                       int n_streams, cudaStream_t st) {
+  const int half = (NL + 1) / 2;
+  const size_t smem = MixSmem<NOBJ>::bytes(half);
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(obj_mix_kernel<NOBJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    configured = smem;
   }
+  obj_mix_kernel<NOBJ><<<dim3(NL > 1 ? 2 : 1, n_streams), half * kChunks, smem, st>>>(dl, d_in, d_out, d_scratch, n_obj);
+  return cudaGetLastError();
 }
 
 __global__ void obj_state_init_kernel(float* state, const int* first, int n_obj, int nl1, size_t total) {
@@ -407,17 +516,22 @@ mpeghb200_status mpeghb200_obj_render_dev(mpeghb200_ctx* ctx, const mpeghb200_ob
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   const DevLayout* dl = static_cast<const DevLayout*>(L->d_desc);
   const int n_pairs = n_obj * n_streams;
-  obj_gains_kernel<<<(n_pairs + 127) / 128, 128, 0, st>>>(dl, d_side, d_state, d_scratch, n_obj, n_streams);
+  obj_gains_kernel<<<(n_pairs + kGainWarps - 1) / kGainWarps, 32 * kGainWarps, 0, st>>>(dl, d_side, d_state, d_scratch, n_obj, n_streams);
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   const int NL = L->host.n_non_lfe;
-  const size_t smem = size_t(n_obj) * NL * (kChunks + 1) * sizeof(float);
-  static size_t configured_smem = 48 * 1024;
-  if (smem > configured_smem) {
-    MB_CUDA(ctx, cudaFuncSetAttribute(obj_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    configured_smem = smem;
-  }
-  obj_mix_kernel<<<n_streams, NL * kChunks, smem, st>>>(dl, d_in, d_out, d_scratch, n_obj);
+  if (NL > 2 * (kMixMaxThreads / kChunks))
+    return fail(ctx, MPEGHB200_ERR_UNSUPPORTED, "obj_render_dev: more than 24 non-LFE loudspeakers");
+  cudaError_t e;
+  if (n_obj <= 8)
+    e = launch_mix<8>(dl, NL, d_in, d_out, d_scratch, n_obj, n_streams, st);
+  else if (n_obj <= 16)
+    e = launch_mix<16>(dl, NL, d_in, d_out, d_scratch, n_obj, n_streams, st);
+  else if (n_obj <= 24)
+    e = launch_mix<24>(dl, NL, d_in, d_out, d_scratch, n_obj, n_streams, st);
+  else
+    e = launch_mix<32>(dl, NL, d_in, d_out, d_scratch, n_obj, n_streams, st);
+  MB_CUDA(ctx, e);
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   return MPEGHB200_OK;

@@ -113,23 +113,26 @@ __global__ void __launch_bounds__(kLimThreads)
     // 4. the serial smoother (decoder/impeghd_peak_limiter.c:248-270)
     if (!(quiet && psg0 == 1.0f)) {
       if (tid == 0) {
+        // branch-free, eight gains at a time through registers: the chain psg -> gm -> psg is the only thing
+        // that has to wait (about ten dependent operations per sample); loads, stores and selects ride along
         float gm = st[0], psg = psg0;
-        float nxt = g[0];
-        for (int i = 0; i < kFrame; ++i) {
-          const float gain = nxt;
-          if (i + 1 < kFrame) nxt = g[i + 1];
-          if (gain < psg) {
-            gm = fminf(gm, fmul(fsub(gain, fmul(0.1f, psg)), 1.11111111f));
-          } else {
-            gm = gain;
+        const float rc = P.rc, ac = P.ac;
+        for (int i0 = 0; i0 < kFrame; i0 += 8) {
+          const float4 a = *reinterpret_cast<const float4*>(g + i0);
+          const float4 b = *reinterpret_cast<const float4*>(g + i0 + 4);
+          float gv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float gain = gv[e];
+            const float cand = fmul(fsub(gain, fmul(0.1f, psg)), 1.11111111f);
+            gm = (gain < psg) ? fminf(gm, cand) : gain;
+            const bool up = gm >= psg;
+            const float r = fadd(gm, fmul(up ? rc : ac, fsub(psg, gm)));
+            psg = up ? r : fmaxf(r, gain);
+            gv[e] = psg;
           }
-          if (gm >= psg) {
-            psg = fadd(gm, fmul(P.rc, fsub(psg, gm)));
-          } else {
-            psg = fadd(gm, fmul(P.ac, fsub(psg, gm)));
-            psg = fmaxf(psg, gain);
-          }
-          g[i] = psg;
+          *reinterpret_cast<float4*>(g + i0) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+          *reinterpret_cast<float4*>(g + i0 + 4) = make_float4(gv[4], gv[5], gv[6], gv[7]);
         }
         st[0] = gm;
         st[1] = psg;
