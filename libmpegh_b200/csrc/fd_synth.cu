@@ -837,6 +837,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_BLOCKS)
 // the consumer warp, 64 participants), one barrier per slot and edge: A->B, B->C and C->A ("slot free").
 // CTAs are persistent: CTA c processes units c, c + gridDim.x, ...
 constexpr int kSlots = 4;
+constexpr int kSlowCap = 256;
 
 __device__ __forceinline__ void bar_sync64(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void bar_arrive64(int id) {
@@ -844,16 +845,33 @@ __device__ __forceinline__ void bar_arrive64(int id) {
   asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory");
 }
 
+__device__ __noinline__ void slow_units(const float* __restrict__ coef, const uint32_t* __restrict__ side,
+                                        float* __restrict__ overlap, float* __restrict__ out, const int* list, int count,
+                                        float* slots, const DeviceTables& T) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = warp; k < count; k += 4) {
+    const size_t u = size_t(list[k]);
+    const Side sd = unpack_side(__ldg(side + u));
+    fd_unit_generic(coef + u * 1024, overlap + u * 1024, out + u * 1024, sd, slots + warp * kBufFloats, T, lane);
+  }
+}
+
+template <bool DEFER>
 __global__ void __launch_bounds__(128, 3)
     fd_synth_ws_kernel(const float* __restrict__ coef, const uint32_t* __restrict__ side, float* __restrict__ overlap,
                        float* __restrict__ out, int n_units, const __grid_constant__ DeviceTables T) {
   __shared__ __align__(16) float slots[kSlots][kBufFloats];
   __shared__ int fast_flag[kSlots];
+  // Units that need the generic path (EIGHT_SHORT, transform-kernel switching) cost ~5x a fast unit and would stall
+  // the A/B/C pipeline, so role C only notes them down; after the CTA's fast pass its four warps do them side by
+  // side, one unit per warp, each in its own slot.  (List full: the unit is done in line, as before.)
+  __shared__ int slow_list[kSlowCap];
+  __shared__ int slow_count;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 96) slow_count = 0;  // lane 0 of the role-C warp, its only writer until the final barrier
   const int first = blockIdx.x, stride = gridDim.x;
   const int n_local = first < n_units ? (n_units - first + stride - 1) / stride : 0;
   constexpr int AB = 1, BC = 1 + kSlots, FREE = 1 + 2 * kSlots;  // barrier ids (0 is __syncthreads)
-  if (n_local == 0) return;
 
   if (warp == 0) {
     // ---------------- role A ----------------
@@ -922,11 +940,19 @@ __global__ void __launch_bounds__(128, 3)
         } else {
           phase_c_stop(slots[slot], ov, o, T.win_short[sd.shape_prev], lane);
         }
+      } else if (DEFER && slow_count < kSlowCap) {  // only this warp writes slow_count
+        if (lane == 0) slow_list[slow_count] = int(u), slow_count = slow_count + 1;
+        __syncwarp();
       } else {
         fd_unit_generic(coef + u * 1024, ov, o, sd, slots[slot], T, lane);
       }
       if (i + kSlots < n_local) bar_arrive64(FREE + slot);
     }
+  }
+  // ---------------- all roles: the generic-path units of this CTA, one per warp ----------------
+  if (DEFER) {
+    __syncthreads();
+    if (slow_count) slow_units(coef, side, overlap, out, slow_list, slow_count, &slots[0][0], T);
   }
 }
 
@@ -964,9 +990,13 @@ mpeghb200_status fd_synth_launch(mpeghb200_ctx* ctx, const float* d_coef, const 
     default:
     case 7:
     case 8: {
-      const int ctas = ctx->sm_count * (ctx->fd_variant == 7 ? 3 : 2);
-      fd_synth_ws_kernel<<<n_units < ctas ? n_units : ctas, 128, 0, stream>>>(d_coef, d_side, d_overlap, d_out, n_units,
-                                                                            ctx->tables);
+      const int ctas = ctx->sm_count * 3;
+      if (ctx->fd_variant == 8)
+        fd_synth_ws_kernel<false><<<n_units < ctas ? n_units : ctas, 128, 0, stream>>>(d_coef, d_side, d_overlap, d_out,
+                                                                                   n_units, ctx->tables);
+      else
+        fd_synth_ws_kernel<true><<<n_units < ctas ? n_units : ctas, 128, 0, stream>>>(d_coef, d_side, d_overlap, d_out,
+                                                                                  n_units, ctx->tables);
       e = cudaGetLastError();
       break;
     }

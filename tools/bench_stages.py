@@ -236,7 +236,63 @@ def hoa_render_stage():
         lib.hoa_renderer_destroy(h)
 
 
+def spectral_stage():
+    """Joint-stereo tools and IGF at the config-2 shape: 256 streams x 24 ch = 3072 pairs / 6144 channel-frames."""
+    import igf_cases
+    import stereo_cases
+    bands = lib.bands_create(stereo_cases.SFB_LONG, stereo_cases.SFB_SHORT)
+    P = 3072
+    rng = np.random.default_rng(11)
+    coef = torch.randn(2 * P, 1024, device="cuda") * 500
+    sds = np.zeros(P, stereo_cases.STEREO_SIDE)
+    side = np.zeros((P, 3), np.int64)
+    for p in range(P):
+        seq = int(rng.choice([0, 1, 2, 3], p=[0.9, 0.03, 0.04, 0.03]))
+        sd, _ = stereo_cases.random_frame(rng, seq, int(rng.integers(2)), int(rng.integers(2)), tool=3)
+        sd["complex_coef"], sd["use_prev_frame"], sd["prev_dmx"] = 1, 1, 1
+        sd["left"], sd["right"], sd["slot"] = 2 * p, 2 * p + 1, p
+        sds[p] = sd
+    d_pairs = torch.from_numpy(sds.view(np.uint8).reshape(P, -1).copy()).cuda()
+    state = torch.randn(P, lib.stereo_state_floats(), device="cuda")
+    ms = timeit(lambda i: (lib.stereo_dev(bands, coef.data_ptr(), d_pairs.data_ptr(), state.data_ptr(), P, st),
+                           lib.stereo_save_dev(bands, coef.data_ptr(), d_pairs.data_ptr(), state.data_ptr(), P, st)))
+    # per pair: spectra 2 x 4096 read + written, saved spectra 2 x 4096 read (previous-frame downmix) + written, side
+    report("stereo tools (complex prediction with previous-frame downmix) + save, 3072 pairs", ms,
+           P * (4 * 4096 + 4 * 4096 + 664), 2 * P * 1024, "channel_samples")
+    sds["tool"] = 1
+    d_pairs = torch.from_numpy(sds.view(np.uint8).reshape(P, -1).copy()).cuda()
+    ms = timeit(lambda i: lib.stereo_dev(bands, coef.data_ptr(), d_pairs.data_ptr(), state.data_ptr(), P, st))
+    report("stereo tools (M/S by mask), 3072 pairs", ms, P * (4 * 4096 + 664), 2 * P * 1024, "channel_samples")
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "igf_golden.npz"))
+    U = 6144
+    cfg, grid = igf_cases.CONFIGS[1], g["c1_grid"]
+    isd = np.zeros(U, igf_cases.IGF_SIDE)
+    base = [igf_cases.random_frame(rng, cfg, grid, win_type=int(k % 16 == 15), all_zero_prob=0.0) for k in range(64)]
+    icoef = np.stack([base[u % 64][1] for u in range(U)])
+    itiles = np.stack([base[u % 64][2] for u in range(U)])
+    for u in range(U):
+        isd[u] = base[u % 64][0]
+        isd[u]["unit"] = u
+    d_isd = torch.from_numpy(isd.view(np.uint8).reshape(U, -1).copy()).cuda()
+    d_icoef0 = torch.from_numpy(icoef).cuda()
+    d_icoef = d_icoef0.clone()
+    d_tiles = torch.from_numpy(itiles).cuda()
+    d_tnf = torch.zeros(U, 2048, device="cuda")
+    d_seed = torch.zeros(U, dtype=torch.int32, device="cuda")
+
+    def igf_step(i):
+        d_icoef.copy_(d_icoef0)  # the gap must be empty again; the copy is inside the timed region (4 KB r + w per unit)
+        lib.igf_dev(bands, d_icoef.data_ptr(), d_tiles.data_ptr(), d_isd.data_ptr(), d_tnf.data_ptr(), d_seed.data_ptr(),
+                    U, st)
+    ms = timeit(igf_step)
+    report("igf mono (whitening, noise, TNF on long blocks) incl. a 25 MB spectrum reset copy, 6144 channel-frames", ms,
+           U * (2 * 4096 + 4 * 4096 + 548 + 8192), U * 1024, "channel_samples")
+    lib.bands_destroy(bands)
+
+
 STAGES = {"binaural": binaural_stage, "hoa": hoa_chain_stage, "fc": fc_stage, "tns_rs": tns_rs_stage,
+          "spectral": spectral_stage,
           "obj": obj_stage, "hoa_render": hoa_render_stage}
 if ONLY in STAGES:
     STAGES[ONLY]()
@@ -248,5 +304,6 @@ hoa_render_stage()
 hoa_chain_stage()
 fc_stage()
 tns_rs_stage()
+spectral_stage()
 binaural_stage()
 lib.close()
