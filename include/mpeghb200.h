@@ -429,6 +429,23 @@ typedef struct mpeghb200_igf_side {
 mpeghb200_status mpeghb200_igf_dev(mpeghb200_ctx *ctx, const mpeghb200_bands *bands, float *d_coef,
                                    const float *d_tiles, const mpeghb200_igf_side *d_side, float *d_tnf_state,
                                    uint32_t *d_seed_out, int n_units, void *cuda_stream);
+/* Joint-stereo IGF of channel pairs (igf_independent_tiling == 0 with a common window): replaces
+ * ia_core_coder_igf_apply_stereo (decoder/ia_core_coder_igf_dec.c:1661; calc :1169, proc :1431).  Pair p uses the
+ * side records d_side[2p] (left) and [2p+1] (right) -- same grid, window type and grouping, each channel's own
+ * unit, seed, levels, tile numbers and whitening levels, already synchronised the way ia_core_coder_sync_data
+ * (:1615) does -- the tiles d_tiles[2p], [2p+1] and the stereo band mask d_mask[p][128] per (group, band)
+ * (cplx_pred_used or ms_used; long [band], short [16 * group + band]; zeros without a mask).  It fills both
+ * spectra and always leaves the TNF buffers behind.  The frame then continues as
+ * ia_core_coder_data_process_igf_joint_stereo_* (decoder/ia_core_coder_ext_ch_ele.c:1500,1590) does:
+ * mpeghb200_stereo_dev over the IGF band range on the spectra AND on the TNF spectra (unit index 2 * unit into
+ * d_tnf_state viewed as [.][1024]), then mpeghb200_igf_tnf_dev (= ia_core_coder_igf_tnf, :2297) per channel. */
+mpeghb200_status mpeghb200_igf_stereo_dev(mpeghb200_ctx *ctx, const mpeghb200_bands *bands, float *d_coef,
+                                          const float *d_tiles, const mpeghb200_igf_side *d_side,
+                                          const uint8_t *d_mask, float *d_tnf_state, uint32_t *d_seed_out,
+                                          int n_pairs, void *cuda_stream);
+mpeghb200_status mpeghb200_igf_tnf_dev(mpeghb200_ctx *ctx, const mpeghb200_bands *bands, float *d_coef,
+                                       const mpeghb200_igf_side *d_side, float *d_tnf_state, int n_units,
+                                       void *cuda_stream);
 /* whitening gain tables [2][64] (host, no GPU needed): pinned against the reference ROM by the tests */
 void mpeghb200_igf_whitening_rom(float *out128);
 

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(kThreads)
     igf_kernel(float* __restrict__ coef_g, const float* __restrict__ tiles_g,
                const mpeghb200_igf_side* __restrict__ sides, float* __restrict__ tnf_state,
                uint32_t* __restrict__ seed_out, const int16_t* __restrict__ sfb_long, int n_long,
-               const int16_t* __restrict__ sfb_short, int n_short, const IgfRom R) {
+               const int16_t* __restrict__ sfb_short, int n_short, const int tnf_only, const IgfRom R) {
   __shared__ mpeghb200_igf_side sd;
   __shared__ __align__(16) float coef[kFrame];
   __shared__ __align__(16) float tiles[4 * kFrame];
@@ -111,9 +111,11 @@ __global__ void __launch_bounds__(kThreads)
   const bool noise_ok = !is_short && sd.use_whitening;
   const bool tnf_on = sd.use_tnf && !is_short;
   const bool do_tnf = tnf_on && sd.is_tnf == 1;
-  const bool all_zero = sd.all_zero != 0;
+  // tnf_only: the TNF stage on its own (after the joint-stereo fill and the stereo tools): same as the reference's
+  // igf_tnf on a frame whose fill left its buffers behind
+  const bool all_zero = sd.all_zero != 0 || tnf_only;
   if (all_zero && !do_tnf) {
-    if (tid == 0) seed_out[blockIdx.x] = sd.seed;
+    if (tid == 0 && !tnf_only) seed_out[blockIdx.x] = sd.seed;
     return;
   }
   float* cg = coef_g + size_t(sd.unit) * kFrame;
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(kThreads)
     }
   } else {
     // igf_all_zero with TNF signalled: the reference flattens and applies what its buffers still hold
-    if (tid == 0) seed_out[blockIdx.x] = sd.seed;
+    if (tid == 0 && !tnf_only) seed_out[blockIdx.x] = sd.seed;
     reinterpret_cast<float4*>(tnf)[tid] = reinterpret_cast<const float4*>(stg)[tid];
     reinterpret_cast<float4*>(tbuf)[tid] = reinterpret_cast<const float4*>(stg + kFrame)[tid];
     __syncthreads();
@@ -417,6 +419,279 @@ __global__ void __launch_bounds__(kThreads)
   reinterpret_cast<float4*>(cg)[tid] = reinterpret_cast<const float4*>(coef)[tid];
 }
 
+// ---- joint-stereo fill of a channel pair (ia_core_coder_igf_apply_stereo :1661, calc :1169, proc :1431) -------
+// Same building blocks as the mono kernel, both channels side by side in one CTA: the source value of every bin of
+// the range is determined once per channel (tile mapping; for whitening level 2 a noise draw on EVERY bin of that
+// tile, zero or not), mixed to mid/side on the masked bands, and then feeds the energies, the gains (float
+// quotient, double square root here) and the fill.  The TNF buffers of both channels are always left behind: the
+// stereo tools act on the filled spectra and on those buffers before mpeghb200_igf_tnf_dev flattens them.
+__global__ void __launch_bounds__(kThreads)
+    igf_stereo_kernel(float* __restrict__ coef_g, const float* __restrict__ tiles_g,
+                      const mpeghb200_igf_side* __restrict__ sides, const uint8_t* __restrict__ masks,
+                      float* __restrict__ tnf_state, uint32_t* __restrict__ seed_out,
+                      const int16_t* __restrict__ sfb_long, int n_long, const int16_t* __restrict__ sfb_short,
+                      int n_short, const IgfRom R) {
+  extern __shared__ __align__(16) float dsm[];
+  float* coef = dsm;                   // [2][1024]
+  float* tiles = coef + 2 * kFrame;    // [2][4][1024]
+  float* val = tiles + 8 * kFrame;     // [2][1024]
+  float* tnf = val + 2 * kFrame;       // [2][1024] spectrum
+  float* tmask = tnf + 2 * kFrame;     // [2][1024] 1 = coded, 0 = filled
+  __shared__ mpeghb200_igf_side sd2[2];
+  __shared__ uint8_t mask[128];
+  __shared__ float gn[2][128];
+  __shared__ int16_t swb[72];
+  __shared__ Grid G;
+  __shared__ uint32_t warp_cnt[2][kThreads / 32];
+  const int tid = threadIdx.x;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(sides + 2 * blockIdx.x);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(sd2);
+    for (int i = tid; i < int(2 * sizeof(mpeghb200_igf_side) / 4); i += kThreads) dst[i] = src[i];
+    if (tid < 32) reinterpret_cast<uint32_t*>(mask)[tid] = reinterpret_cast<const uint32_t*>(masks + 128 * blockIdx.x)[tid];
+  }
+  __syncthreads();
+  const mpeghb200_igf_side& sl = sd2[0];
+  if (sd2[0].all_zero && sd2[1].all_zero) {
+    if (tid < 2) seed_out[2 * blockIdx.x + tid] = sd2[tid].seed;
+    return;
+  }
+  const bool is_short = sl.win_type == 1;
+  const int bins = is_short ? 128 : kFrame;
+  const int n_sfb = is_short ? n_short : n_long;
+  const bool noise_ok = !is_short && sl.use_whitening;
+  const bool tnf_on = sl.use_tnf && !is_short;
+  float* cg[2] = {coef_g + size_t(sd2[0].unit) * kFrame, coef_g + size_t(sd2[1].unit) * kFrame};
+
+  for (int i = tid; i <= n_sfb; i += kThreads) swb[i] = i ? (is_short ? sfb_short : sfb_long)[i - 1] : 0;
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    reinterpret_cast<float4*>(coef + ch * kFrame)[tid] = reinterpret_cast<const float4*>(cg[ch])[tid];
+    const float4* tg = reinterpret_cast<const float4*>(tiles_g + (size_t(2 * blockIdx.x) + ch) * 4 * kFrame);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) reinterpret_cast<float4*>(tiles + ch * 4 * kFrame)[t * 256 + tid] = tg[t * 256 + tid];
+  }
+  __syncthreads();
+  if (tid == 0) {  // tile widths of the grid (ia_core_coder_igf_get_num_tiles :760)
+    const int s0 = sl.sfb_start, s1 = sl.sfb_stop;
+    const int bgn = swb[s0], end = swb[s1];
+    int range = end - bgn < 8 ? 8 : end - bgn, mem = s0, sbs = bgn, n = 0;
+    int tile[4] = {range >> 2, range >> 2, range >> 2, range >> 2};
+    if (bgn > sl.igf_min && bgn < end) {
+      for (int i = 0; i < 4; ++i) {
+        const int lim = min(sbs + tile[i], end);
+        int j = 1;
+        while (lim > swb[j]) ++j;
+        if (!sl.use_high_res) {
+          if (i == 3)
+            j = s1;
+          else if ((((j - s0) & 1) == 1) && ((j - mem) > 1))
+            --j;
+          mem = j;
+        }
+        tile[i] = max(2, min(swb[j] - sbs, end - sbs));
+        ++n;
+        sbs += tile[i];
+        if (sbs == end) break;
+      }
+    }
+    for (int i = 0; i < 4; ++i) G.tile[i] = i < n ? tile[i] : 0;
+    G.n_tiles = n, G.bgn = bgn, G.end = end;
+  }
+  __syncthreads();
+  const int bgn = G.bgn, end = G.end;
+
+  // ---- whitening of the level-0 source tiles of both channels (long blocks) --------------------------------
+  if (noise_ok) {
+    const int lo = sl.igf_min, stop = bgn;
+    for (int ct = 0; ct < 2 * G.n_tiles; ++ct) {
+      const int ch = ct / G.n_tiles, t = ct - ch * G.n_tiles;
+      if (sd2[ch].whitening_level[t] != 0) continue;  // uniform
+      float* x = tiles + (ch * 4 + t) * kFrame;
+      float out[4];
+      bool has[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = 4 * tid + k;
+        has[k] = i >= lo && i < stop;
+        out[k] = 0.0f;
+        if (has[k]) {
+          const int ie = i < stop - 3 ? i : stop - 4;
+          float fac = 0.0f;
+          if (ie >= lo) {
+            float env = 1e-3f;
+#pragma unroll
+            for (int j = -3; j <= 3; ++j) env = fadd(env, fmul(x[ie + j], x[ie + j]));
+            const int ex = int((__float_as_uint(env) >> 23) & 0xff) - 127;
+            fac = env >= 1.0f ? R.whiten[0][ex & 63] : R.whiten[1][(-ex) & 63];
+          }
+          out[k] = fmul(x[i], fac);
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (has[k]) x[4 * tid + k] = out[k];
+      __syncthreads();
+    }
+  }
+
+  // ---- source values of both channels, noise draws numbered in bin order, mid/side on the masked bands -------
+  const int step = (sl.use_high_res || is_short) ? 1 : 2;
+  int sfb_of = sl.sfb_start;
+  {
+    const int i = 4 * tid, w = is_short ? i >> 7 : 0, b = i - w * bins;
+    while (sfb_of + 1 < n_sfb && swb[sfb_of + 1] <= b) ++sfb_of;
+  }
+  int sfb4[4], grp4 = 0;
+  {
+    const int w = is_short ? (4 * tid) >> 7 : 0;
+    if (is_short) {
+      int acc = sl.group_len[0];
+      while (w >= acc) acc += sl.group_len[++grp4];
+    }
+  }
+  float v[2][4];
+  bool in_range[4];
+  uint32_t my_noise[2] = {0, 0};
+  bool noise[2][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = 4 * tid + k;
+    const int w = is_short ? i >> 7 : 0;
+    const int b = i - w * bins;
+    in_range[k] = b >= bgn && b < end;
+    sfb4[k] = sfb_of;
+    v[0][k] = v[1][k] = 0.0f;
+    noise[0][k] = noise[1][k] = false;
+    if (in_range[k]) {
+      while (sfb_of + 1 < n_sfb && swb[sfb_of + 1] <= b) ++sfb_of;
+      // the reference walks the range in steps of one or two bands and indexes mask, level and gain by the first
+      // band of the step
+      sfb4[k] = sl.sfb_start + ((sfb_of - sl.sfb_start) / step) * step;
+      const int ix = tile_of(b, G);
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        const int sb = source_bin(sl.igf_min, b, G, sd2[ch].tile_num);
+        v[ch][k] = tiles[(ch * 4 + ix) * kFrame + w * bins + sb];
+        noise[ch][k] = noise_ok && sd2[ch].whitening_level[ix] == 2;
+        my_noise[ch] += noise[ch][k];
+      }
+    }
+  }
+  uint32_t incl[2] = {my_noise[0], my_noise[1]};
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o0 = __shfl_up_sync(0xffffffffu, incl[0], d), o1 = __shfl_up_sync(0xffffffffu, incl[1], d);
+    if ((tid & 31) >= d) incl[0] += o0, incl[1] += o1;
+  }
+  if ((tid & 31) == 31) warp_cnt[0][tid >> 5] = incl[0], warp_cnt[1][tid >> 5] = incl[1];
+  __syncthreads();
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    uint32_t base = 0, total = 0;
+#pragma unroll
+    for (int wv = 0; wv < kThreads / 32; ++wv) {
+      if (wv < (tid >> 5)) base += warp_cnt[ch][wv];
+      total += warp_cnt[ch][wv];
+    }
+    uint32_t kdraw = base + incl[ch] - my_noise[ch];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (noise[ch][k]) {
+        const uint32_t s = lcg_jump(sd2[ch].seed, ++kdraw, R);
+        v[ch][k] = fmul(kNoise, (s & 0x10000u) ? -1.0f : 1.0f);
+      }
+    if (tid == 0) seed_out[2 * blockIdx.x + ch] = lcg_jump(sd2[ch].seed, total, R);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (in_range[k] && mask[(is_short ? 16 * grp4 : 0) + sfb4[k]]) {
+      const float t = v[0][k];
+      v[0][k] = fmul(0.5f, fadd(t, v[1][k]));
+      v[1][k] = fmul(0.5f, fsub(t, v[1][k]));
+    }
+    val[4 * tid + k] = v[0][k];
+    val[kFrame + 4 * tid + k] = v[1][k];
+  }
+  __syncthreads();
+
+  // ---- band energies and gains per (channel, group, band) ----------------------------------------------
+  {
+    const int ch = tid >> 7, r = tid & 127;
+    const int g = is_short ? r >> 4 : 0;
+    const int sfb = is_short ? r & 15 : r;
+    const bool live = g < sl.num_groups && sfb >= sl.sfb_start && sfb < sl.sfb_stop &&
+                      ((sfb - sl.sfb_start) % step) == 0 && (is_short || r < 64);
+    if (live) {
+      int w0 = 0;
+      for (int q = 0; q < g; ++q) w0 += sl.group_len[q];
+      const int hi = min(sfb + step, int(sl.sfb_stop));
+      float s_acc = 0.0f, p_acc = 0.0f;
+      for (int q = 0; q < sl.group_len[g]; ++q) {
+        const float* c = coef + ch * kFrame + (w0 + q) * bins;
+        const float* sv = val + ch * kFrame + (w0 + q) * bins;
+        float e = 0.0f, pe = 0.0f;
+        for (int b = swb[sfb]; b < swb[hi]; ++b) {
+          const float cb = c[b];
+          e = fadd(e, fmul(cb, cb));
+          if (cb == 0.0f) pe = fadd(pe, fmul(sv[b], sv[b]));
+        }
+        s_acc = fadd(s_acc, e);
+        p_acc = fadd(p_acc, pe);
+      }
+      if (sl.group_len[g] != 1) {
+        const float gl = float(sl.group_len[g]);
+        s_acc = __fdiv_rn(s_acc, gl);
+        p_acc = __fdiv_rn(p_acc, gl);
+      }
+      const int width = swb[hi] - swb[sfb];
+      const float lev = sd2[ch].levels[(is_short ? 16 * g : 0) + sfb];
+      const float mn = fsub(fmul(fmul(lev, lev), float(width)), s_acc);
+      float gain = 0.0f;
+      if (0.0f < mn && 0.0f < p_acc) {
+        gain = float(__dsqrt_rn(double(__fdiv_rn(mn, p_acc))));
+        gain = gain < 10.f ? gain : 10.f;
+      }
+      const int slot = (is_short ? 16 * g : 0) + sfb;
+      gn[ch][slot] = gain;
+      if (step == 2 && sfb + 1 < sl.sfb_stop) gn[ch][slot + 1] = gain;
+    }
+  }
+  __syncthreads();
+
+  // ---- fill; TNF buffers with the either-channel-coded rule on the masked bands (:1560-1580) ---------------
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = 4 * tid + k;
+    float spec[2] = {0.0f, 0.0f}, mk[2] = {1.0f, 1.0f};
+    if (in_range[k]) {
+      const int slot = (is_short ? 16 * grp4 : 0) + sfb4[k];
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        spec[ch] = fmul(gn[ch][slot], val[ch * kFrame + i]);
+        if (coef[ch * kFrame + i] == 0.0f) {
+          coef[ch * kFrame + i] = spec[ch];
+          mk[ch] = 0.0f;
+        }
+      }
+      if (mask[slot]) mk[0] = mk[1] = (mk[0] != 0.0f || mk[1] != 0.0f) ? 1.0f : 0.0f;
+    }
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) tnf[ch * kFrame + i] = spec[ch], tmask[ch * kFrame + i] = mk[ch];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    reinterpret_cast<float4*>(cg[ch])[tid] = reinterpret_cast<const float4*>(coef + ch * kFrame)[tid];
+    if (tnf_on) {
+      float* stg = tnf_state + size_t(sd2[ch].unit) * 2 * kFrame;
+      reinterpret_cast<float4*>(stg)[tid] = reinterpret_cast<const float4*>(tnf + ch * kFrame)[tid];
+      reinterpret_cast<float4*>(stg + kFrame)[tid] = reinterpret_cast<const float4*>(tmask + ch * kFrame)[tid];
+    }
+  }
+}
+
 IgfRom make_rom() {
   IgfRom R{};
   for (int n = 0; n < 64; ++n) {
@@ -463,6 +738,47 @@ mpeghb200_status mpeghb200_igf_dev(mpeghb200_ctx* ctx, const mpeghb200_bands* ba
   static const IgfRom R = make_rom();
   igf_kernel<<<n_units, kThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
       d_coef, d_tiles, d_side, d_tnf_state, d_seed_out, bands->d_sfb_long, bands->n_long, bands->d_sfb_short,
+      bands->n_short, 0, R);
+  ctx->launches.fetch_add(1);
+  MB_CUDA(ctx, cudaGetLastError());
+  return MPEGHB200_OK;
+}
+
+mpeghb200_status mpeghb200_igf_tnf_dev(mpeghb200_ctx* ctx, const mpeghb200_bands* bands, float* d_coef,
+                                       const mpeghb200_igf_side* d_side, float* d_tnf_state, int n_units,
+                                       void* cuda_stream) {
+  if (!ctx || !bands) return MPEGHB200_ERR_BAD_ARG;
+  if (n_units < 0 || (n_units > 0 && (!d_coef || !d_side || !d_tnf_state)))
+    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "igf_tnf_dev: null buffer or negative unit count");
+  if (n_units == 0) return MPEGHB200_OK;
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  static const IgfRom R = make_rom();
+  igf_kernel<<<n_units, kThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+      d_coef, nullptr, d_side, d_tnf_state, nullptr, bands->d_sfb_long, bands->n_long, bands->d_sfb_short,
+      bands->n_short, 1, R);
+  ctx->launches.fetch_add(1);
+  MB_CUDA(ctx, cudaGetLastError());
+  return MPEGHB200_OK;
+}
+
+mpeghb200_status mpeghb200_igf_stereo_dev(mpeghb200_ctx* ctx, const mpeghb200_bands* bands, float* d_coef,
+                                          const float* d_tiles, const mpeghb200_igf_side* d_side,
+                                          const uint8_t* d_mask, float* d_tnf_state, uint32_t* d_seed_out,
+                                          int n_pairs, void* cuda_stream) {
+  if (!ctx || !bands) return MPEGHB200_ERR_BAD_ARG;
+  if (n_pairs < 0 || (n_pairs > 0 && (!d_coef || !d_tiles || !d_side || !d_mask || !d_tnf_state || !d_seed_out)))
+    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "igf_stereo_dev: null buffer or negative pair count");
+  if (n_pairs == 0) return MPEGHB200_OK;
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  static const IgfRom R = make_rom();
+  constexpr size_t smem = size_t(16) * kFrame * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    MB_CUDA(ctx, cudaFuncSetAttribute(igf_stereo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    configured = true;
+  }
+  igf_stereo_kernel<<<n_pairs, kThreads, smem, static_cast<cudaStream_t>(cuda_stream)>>>(
+      d_coef, d_tiles, d_side, d_mask, d_tnf_state, d_seed_out, bands->d_sfb_long, bands->n_long, bands->d_sfb_short,
       bands->n_short, R);
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());

@@ -214,6 +214,10 @@ class Lib:
         c.mpeghb200_bands_destroy.argtypes = [vp]
         c.mpeghb200_igf_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
         c.mpeghb200_igf_dev.restype = i32
+        c.mpeghb200_igf_stereo_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
+        c.mpeghb200_igf_stereo_dev.restype = i32
+        c.mpeghb200_igf_tnf_dev.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, vp]
+        c.mpeghb200_igf_tnf_dev.restype = i32
         c.mpeghb200_igf_whitening_rom.argtypes = [vp]
         c.mpeghb200_igf_whitening_rom.restype = None
         c.mpeghb200_stereo_state_floats.argtypes = []
@@ -329,6 +333,13 @@ class Lib:
     def igf_dev(self, bands, d_coef, d_tiles, d_side, d_tnf_state, d_seed_out, n_units, stream=0):
         self.check(self.c.mpeghb200_igf_dev(self.ctx, bands, d_coef, d_tiles, d_side, d_tnf_state, d_seed_out,
                                             n_units, stream))
+
+    def igf_stereo_dev(self, bands, d_coef, d_tiles, d_side, d_mask, d_tnf_state, d_seed_out, n_pairs, stream=0):
+        self.check(self.c.mpeghb200_igf_stereo_dev(self.ctx, bands, d_coef, d_tiles, d_side, d_mask, d_tnf_state,
+                                                   d_seed_out, n_pairs, stream))
+
+    def igf_tnf_dev(self, bands, d_coef, d_side, d_tnf_state, n_units, stream=0):
+        self.check(self.c.mpeghb200_igf_tnf_dev(self.ctx, bands, d_coef, d_side, d_tnf_state, n_units, stream))
 
     def igf_whitening_rom(self):
         t = np.zeros((2, 64), np.float32)

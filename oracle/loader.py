@@ -104,6 +104,9 @@ def load_oracle():
     lib.oracle_stereo_save.argtypes = [ctypes.c_char_p, _f32p, _f32p, _f32p]
     lib.oracle_igf_mono.argtypes = [ctypes.c_char_p, _i16p, ctypes.c_int, _f32p, _f32p, _f32p]
     lib.oracle_igf_mono.restype = ctypes.c_uint
+    lib.oracle_igf_stereo.argtypes = [ctypes.c_char_p, ctypes.c_char_p, _u8p, _i16p, ctypes.c_int, _f32p, _f32p, _f32p,
+                                      _f32p, _f32p, _f32p, np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")]
+    lib.oracle_igf_tnf.argtypes = [ctypes.c_char_p, _i16p, ctypes.c_int, _f32p, _f32p]
     lib.oracle_igf_tiles.argtypes = [ctypes.c_int] * 4 + [_i16p, _i32p]
     lib.oracle_igf_tiles.restype = ctypes.c_int
     lib.oracle_igf_whitening_table.argtypes = [_f32p]
@@ -235,6 +238,9 @@ def load_ref():
     lib.ref_igf_grid.argtypes = [ctypes.c_void_p, _i32p]
     lib.ref_igf_process.argtypes = [ctypes.c_void_p, ctypes.c_char_p, _f32p, _f32p]
     lib.ref_igf_process.restype = ctypes.c_uint
+    lib.ref_igf_stereo_process.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, _u8p, ctypes.c_int, _f32p,
+                                           _f32p, _f32p, _f32p,
+                                           np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")]
     lib.ref_rs_create.restype = ctypes.c_void_p
     lib.ref_rs_create.argtypes = [ctypes.c_int, ctypes.c_int]
     lib.ref_rs_destroy.argtypes = [ctypes.c_void_p]

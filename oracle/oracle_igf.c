@@ -368,3 +368,164 @@ tnf:
   }
   return sd->all_zero ? sd->seed : seed_calc;
 }
+
+void oracle_igf_tnf(const oracle_igf_side *sd, const short *sfb_top, int n_sfb, float *coef, float *tnf_state)
+{
+  short swb[72];
+  int sfb, bin, igf_bgn, igf_end;
+  float *tnf_spec = tnf_state, *tnf_mask = tnf_state + 1024;
+  if (!(sd->use_tnf && sd->win_type != 1 && sd->is_tnf == 1))
+    return;
+  swb[0] = 0;
+  for (sfb = 0; sfb < n_sfb; sfb++)
+    swb[sfb + 1] = sfb_top[sfb];
+  igf_bgn = swb[sd->sfb_start], igf_end = swb[sd->sfb_stop];
+  tnf_flatten(tnf_spec, igf_bgn, igf_end);
+  for (bin = igf_bgn; bin < igf_end; bin++)
+    if (tnf_mask[bin] == 0)
+      coef[bin] = tnf_spec[bin];
+}
+
+void oracle_igf_stereo(const oracle_igf_side *sl, const oracle_igf_side *sr, const unsigned char *mask,
+                       const short *sfb_top, int n_sfb, float *coef_l, float *coef_r, float *tiles_l, float *tiles_r,
+                       float *tnf_l, float *tnf_r, unsigned int *seeds_out)
+{
+  const oracle_igf_side *sd[2] = {sl, sr};
+  float *coef[2] = {coef_l, coef_r}, *tiles[2] = {tiles_l, tiles_r}, *tnf[2] = {tnf_l, tnf_r};
+  short swb[72];
+  int tile[4], n_tiles, sfb, bin, w = 0, g, k, ch;
+  const int bins = sl->win_type == 1 ? 128 : 1024;
+  const int stride = sl->win_type == 1 ? 16 : 0;
+  const int step = (sl->use_high_res || sl->win_type >= 1) ? 1 : 2;
+  const int noise_ok = sl->win_type != 1 && sl->use_whitening;
+  const int tnf_on = sl->use_tnf && sl->win_type != 1;
+  unsigned int seed_calc[2] = {sl->seed, sr->seed}, seed_apply[2] = {sl->seed, sr->seed};
+  int igf_bgn;
+
+  seeds_out[0] = sl->seed, seeds_out[1] = sr->seed;
+  if (sl->all_zero && sr->all_zero)
+    return;
+  swb[0] = 0;
+  for (sfb = 0; sfb < n_sfb; sfb++)
+    swb[sfb + 1] = sfb_top[sfb];
+  igf_bgn = swb[sl->sfb_start];
+  n_tiles = oracle_igf_tiles(sl->sfb_start, sl->sfb_stop, sl->igf_min, sl->use_high_res, swb, tile);
+  if (noise_ok)
+  {
+    whiten(sl, n_tiles, igf_bgn, tiles_l);
+    whiten(sr, n_tiles, igf_bgn, tiles_r);
+  }
+  for (g = 0; g < sl->num_groups; g++)
+  {
+    float sn[2][64] = {{0}}, pn[2][64] = {{0}};
+    const unsigned char *m = mask + stride * g;
+    const int w0 = w;
+    for (k = 0; k < sl->group_len[g]; k++, w++)
+    { /* ia_core_coder_igf_calc_stereo (:1169) */
+      for (sfb = sl->sfb_start; sfb < sl->sfb_stop; sfb += step)
+      {
+        const int hi = sfb + step < sl->sfb_stop ? sfb + step : sl->sfb_stop;
+        float e[2] = {0.0f, 0.0f};
+        for (bin = swb[sfb]; bin < swb[hi]; bin++)
+          for (ch = 1; ch >= 0; ch--)
+            e[ch] = e[ch] + coef[ch][w * bins + bin] * coef[ch][w * bins + bin];
+        for (ch = 1; ch >= 0; ch--)
+          sn[ch][sfb] = sn[ch][sfb] + e[ch];
+        e[0] = e[1] = 0.0f;
+        for (bin = swb[sfb]; bin < swb[hi]; bin++)
+        {
+          const int ix = tile_of(bin, igf_bgn, n_tiles, tile);
+          float v[2];
+          for (ch = 1; ch >= 0; ch--)
+          {
+            const int sb = source_bin(sl->igf_min, igf_bgn, bin, n_tiles, tile, sd[ch]->tile_num);
+            v[ch] = tiles[ch][ix * TILE_STRIDE + w * bins + sb];
+            if (noise_ok && sd[ch]->whitening_level[ix] == 2)
+              v[ch] = 2097152.f * random_sign(&seed_calc[ch]);
+          }
+          if (m[sfb])
+          {
+            const float t = v[0];
+            v[0] = 0.5f * (t + v[1]);
+            v[1] = 0.5f * (t - v[1]);
+          }
+          for (ch = 1; ch >= 0; ch--)
+            if (coef[ch][w * bins + bin] == 0.0f)
+              e[ch] = e[ch] + v[ch] * v[ch];
+        }
+        for (ch = 1; ch >= 0; ch--)
+          pn[ch][sfb] = pn[ch][sfb] + e[ch];
+      }
+    }
+    if (sl->group_len[g] != 1)
+      for (ch = 0; ch < 2; ch++)
+        for (sfb = sl->sfb_stop - 1; sfb >= sl->sfb_start; sfb--)
+        {
+          sn[ch][sfb] /= sl->group_len[g];
+          pn[ch][sfb] /= sl->group_len[g];
+        }
+    for (w = w0, k = 0; k < sl->group_len[g]; k++, w++)
+    { /* ia_core_coder_igf_stereo_proc (:1431) */
+      if (tnf_on)
+        for (ch = 0; ch < 2; ch++)
+          for (bin = 0; bin < 1024; bin++)
+            tnf[ch][bin] = 0.0f, tnf[ch][1024 + bin] = 1.0f;
+      for (sfb = sl->sfb_start; sfb < sl->sfb_stop; sfb += step)
+      {
+        const int hi = sfb + step < sl->sfb_stop ? sfb + step : sl->sfb_stop;
+        const int width = swb[hi] - swb[sfb];
+        float gn[2];
+        for (ch = 1; ch >= 0; ch--)
+        {
+          const float lev = sd[ch]->levels[stride * g + sfb];
+          const float mn = (lev * lev) * (float)width - sn[ch][sfb];
+          gn[ch] = 0.0f;
+          if (0.0f < mn && 0.0f < pn[ch][sfb])
+          {
+            const float q = (float)sqrt((double)(mn / pn[ch][sfb])); /* float quotient, then double sqrt */
+            gn[ch] = q < 10.f ? q : 10.f;
+          }
+        }
+        for (bin = swb[sfb]; bin < swb[hi]; bin++)
+        {
+          const int ix = tile_of(bin, igf_bgn, n_tiles, tile);
+          const int i = w * bins + bin;
+          float v[2], cb[2];
+          for (ch = 1; ch >= 0; ch--)
+          {
+            const int sb = source_bin(sl->igf_min, igf_bgn, bin, n_tiles, tile, sd[ch]->tile_num);
+            v[ch] = tiles[ch][ix * TILE_STRIDE + w * bins + sb];
+            if (noise_ok && sd[ch]->whitening_level[ix] == 2)
+              v[ch] = 2097152.f * random_sign(&seed_apply[ch]);
+          }
+          if (m[sfb])
+          {
+            const float t = v[0];
+            v[0] = 0.5f * (t + v[1]);
+            v[1] = 0.5f * (t - v[1]);
+          }
+          cb[0] = coef[0][i], cb[1] = coef[1][i];
+          if (tnf_on)
+          {
+            for (ch = 1; ch >= 0; ch--)
+            {
+              tnf[ch][bin] = gn[ch] * v[ch];
+              if (cb[ch] == 0.0f)
+                tnf[ch][1024 + bin] = 0.0f;
+            }
+            if (m[sfb])
+            {
+              const float any = (tnf[1][1024 + bin] != 0.0f || tnf[0][1024 + bin] != 0.0f) ? 1.0f : 0.0f;
+              tnf[1][1024 + bin] = any;
+              tnf[0][1024 + bin] = any;
+            }
+          }
+          for (ch = 1; ch >= 0; ch--)
+            if (cb[ch] == 0.0f)
+              coef[ch][i] = gn[ch] * v[ch];
+        }
+      }
+    }
+  }
+  seeds_out[0] = seed_calc[0], seeds_out[1] = seed_calc[1];
+}

@@ -327,3 +327,72 @@ unsigned int ref_igf_process(void *p, const oracle_igf_side *sd, float *coef, co
   ia_core_coder_igf_tnf(u, cfg, 0, sd->win_type, sd->win_type, win, coef, h->fft_scratch);
   return u->seed_value[0];
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * IGF, joint-stereo path of a channel pair, in the order of ia_core_coder_data_process_igf_joint_stereo_*
+ * (decoder/ia_core_coder_ext_ch_ele.c:1500,1590): ia_core_coder_igf_apply_stereo (igf_dec.c:1661) with an M/S-type
+ * band mask, optionally impeghd_ms_stereo (:1427) over the IGF band range on the filled spectra and on the TNF
+ * buffers, then ia_core_coder_igf_tnf (:2297) per channel.  Handle from ref_igf_create.
+ * mask: per (group, band) [n_groups][sfb_per_sbk]; tiles_* [4][1024]; seeds_out[2].
+ * ---------------------------------------------------------------------------------------------- */
+extern VOID impeghd_ms_stereo(ia_sfb_info_struct *info, WORD8 *group, WORD8 *mask, WORD32 first_band, WORD32 last_band,
+                              FLOAT32 *right_spec, FLOAT32 *left_spec);
+
+static void fill_igf_channel(ia_usac_data_struct *u, int ch, const oracle_igf_side *sd, const float *tiles)
+{
+  ia_usac_igf_dec_data_struct *d = &u->igf_dec_data[ch];
+  ia_usac_igf_bitstream_struct *bs = &d->igf_bitstream[0];
+  int t, g, sfb;
+  for (t = 0; t < 4; t++)
+  {
+    memset(&d->igf_input_spec[t * MAX_IGF_LEN], 0, MAX_IGF_LEN * sizeof(FLOAT32));
+    memcpy(&d->igf_input_spec[t * MAX_IGF_LEN], tiles + t * 1024, 1024 * sizeof(FLOAT32));
+    bs->igf_tile_num[t] = (WORD8)sd->tile_num[t];
+    bs->igf_whitening_level[t] = sd->whitening_level[t];
+  }
+  bs->igf_all_zero = sd->all_zero;
+  bs->igf_is_tnf = (WORD8)sd->is_tnf;
+  for (g = 0; g < 8; g++)
+    for (sfb = 0; sfb < (sd->win_type == 1 ? 16 : 64) && sfb < NSFB_LONG; sfb++)
+      bs->igf_levels_curr_float[g][sfb] = sd->levels[(sd->win_type == 1 ? 16 * g : 0) + sfb];
+  u->seed_value[ch] = sd->seed;
+}
+
+void ref_igf_stereo_process(void *p, const oracle_igf_side *sl, const oracle_igf_side *sr, const unsigned char *mask,
+                            int ms_after, float *coef_l, float *coef_r, const float *tiles_l, const float *tiles_r,
+                            unsigned int *seeds_out)
+{
+  ref_cpe_handle *h = (ref_cpe_handle *)p;
+  ia_usac_data_struct *u = &h->usac;
+  ia_usac_igf_config_struct *cfg = &u->igf_config[0];
+  const int win = sl->win_type == 1 ? EIGHT_SHORT_SEQUENCE : ONLY_LONG_SEQUENCE;
+  ia_sfb_info_struct *info = u->pstr_usac_winmap[win];
+  WORD16 group_len[8];
+  UWORD8 group_dis[8];
+  int g, ch, acc = 0;
+  fill_igf_channel(u, 0, sl, tiles_l);
+  fill_igf_channel(u, 1, sr, tiles_r);
+  memcpy(u->coef[0], coef_l, 1024 * sizeof(float));
+  memcpy(u->coef[1], coef_r, 1024 * sizeof(float));
+  u->window_sequence[0] = u->window_sequence[1] = win;
+  for (g = 0; g < 8; g++)
+  {
+    group_len[g] = sl->group_len[g];
+    acc += sl->group_len[g];
+    group_dis[g] = (UWORD8)acc;
+  }
+  ia_core_coder_igf_apply_stereo(u, 0, cfg, sl->win_type, (const WORD8 *)mask, 1, sl->num_groups, group_len,
+                                 sl->win_type == 1 ? 128 : 1024, info->sfb_per_sbk);
+  if (ms_after)
+  {
+    impeghd_ms_stereo(info, (WORD8 *)group_dis, (WORD8 *)mask, sl->sfb_start, sl->sfb_stop, u->coef[1], u->coef[0]);
+    if (cfg->use_tnf && win != EIGHT_SHORT_SEQUENCE)
+      impeghd_ms_stereo(info, (WORD8 *)group_dis, (WORD8 *)mask, sl->sfb_start, sl->sfb_stop,
+                        u->igf_dec_data[1].igf_tnf_spec_float, u->igf_dec_data[0].igf_tnf_spec_float);
+  }
+  for (ch = 0; ch < 2; ch++)
+    ia_core_coder_igf_tnf(u, cfg, ch, sl->win_type, sl->win_type, win, u->coef[ch], h->fft_scratch);
+  memcpy(coef_l, u->coef[0], 1024 * sizeof(float));
+  memcpy(coef_r, u->coef[1], 1024 * sizeof(float));
+  seeds_out[0] = u->seed_value[0], seeds_out[1] = u->seed_value[1];
+}

@@ -59,3 +59,77 @@ def random_frame(rng, cfg, grid, win_type, all_zero_prob=0.05):
     if rng.random() < 0.1:
         tiles[int(rng.integers(4))] = 0.0  # a silent source tile: zero source energy, gain 0
     return sd, coef.reshape(1024), tiles
+
+
+def random_pair_frame(rng, cfg, grid, win_type):
+    """Joint-stereo IGF frame of a channel pair: -> (sd_l, sd_r, mask[128], coef[2,1024], tiles[2,4,1024]);
+    both sides share grid, window type and grouping and are synchronised the way ia_core_coder_sync_data does."""
+    sd_l, c_l, t_l = random_frame(rng, cfg, grid, win_type)
+    sd_r, c_r, t_r = random_frame(rng, cfg, grid, win_type)
+    sd_r["num_groups"], sd_r["group_len"] = sd_l["num_groups"], sd_l["group_len"]
+    if sd_l["all_zero"] and not sd_r["all_zero"]:
+        sd_l["tile_num"], sd_l["whitening_level"], sd_l["is_tnf"] = sd_r["tile_num"], sd_r["whitening_level"], sd_r["is_tnf"]
+    elif sd_r["all_zero"] and not sd_l["all_zero"]:
+        sd_r["tile_num"], sd_r["whitening_level"], sd_r["is_tnf"] = sd_l["tile_num"], sd_l["whitening_level"], sd_l["is_tnf"]
+    n_sfb = len(SFB_SHORT) if win_type else len(SFB_LONG)
+    stride = 16 if win_type else 0
+    mask = np.zeros(128, np.uint8)
+    for g in range(int(sd_l["num_groups"])):
+        mask[stride * g:stride * g + n_sfb] = rng.random(n_sfb) < 0.5
+    return sd_l, sd_r, mask, np.stack([c_l, c_r]), np.stack([t_l, t_r])
+
+
+def mask_reference_layout(mask, sd):
+    """oracle layout (16 per group) -> the reference's ms_used layout (sfb_per_sbk per group)"""
+    win_type = int(sd["win_type"])
+    n_sfb = len(SFB_SHORT) if win_type else len(SFB_LONG)
+    stride = 16 if win_type else 0
+    out = np.zeros(8 * 64, np.uint8)
+    for g in range(int(sd["num_groups"])):
+        out[g * n_sfb:(g + 1) * n_sfb] = mask[stride * g:stride * g + n_sfb]
+    return out
+
+
+def mask_per_window(mask, sd):
+    """oracle per-group mask -> per-window `used` array of a STEREO_SIDE record"""
+    win_type = int(sd["win_type"])
+    if not win_type:
+        return mask.copy()
+    out = np.zeros(128, np.uint8)
+    w = 0
+    for g in range(int(sd["num_groups"])):
+        for _ in range(int(sd["group_len"][g])):
+            out[16 * w:16 * w + 16] = mask[16 * g:16 * g + 16]
+            w += 1
+    return out
+
+
+class OracleIgfPair:
+    """Oracle-level joint-stereo IGF of one pair with carried TNF buffers."""
+
+    def __init__(self):
+        from oracle import loader
+        self.lib = loader.load_oracle()
+        self.tnf = np.zeros((2, 2048), np.float32)
+
+    def frame(self, sd_l, sd_r, mask, coef, tiles, ms_after):
+        sfb = np.ascontiguousarray(SFB_SHORT if sd_l["win_type"] else SFB_LONG, np.int16)
+        c = [coef[0].copy(), coef[1].copy()]
+        t = [np.ascontiguousarray(tiles[0]).reshape(-1).copy(), np.ascontiguousarray(tiles[1]).reshape(-1).copy()]
+        seeds = np.zeros(2, np.uint32)
+        self.lib.oracle_igf_stereo(sd_l.tobytes(), sd_r.tobytes(), np.ascontiguousarray(mask), sfb, len(sfb), c[0], c[1],
+                                   t[0], t[1], self.tnf[0], self.tnf[1], seeds)
+        if ms_after:
+            ms = np.zeros((), stereo_cases.STEREO_SIDE)
+            ms["tool"], ms["is_short"] = 1, sd_l["win_type"]
+            ms["first_band"], ms["last_band"] = sd_l["sfb_start"], sd_l["sfb_stop"]
+            ms["used"] = mask_per_window(mask, sd_l)
+            dummy = np.zeros(2048, np.float32)
+            self.lib.oracle_stereo_apply(ms.tobytes(), sfb, len(sfb), dummy, c[0], c[1])
+            if sd_l["use_tnf"] and not sd_l["win_type"]:
+                a, b = self.tnf[0][:1024].copy(), self.tnf[1][:1024].copy()
+                self.lib.oracle_stereo_apply(ms.tobytes(), sfb, len(sfb), dummy, a, b)
+                self.tnf[0][:1024], self.tnf[1][:1024] = a, b
+        self.lib.oracle_igf_tnf(sd_l.tobytes(), sfb, len(sfb), c[0], self.tnf[0])
+        self.lib.oracle_igf_tnf(sd_r.tobytes(), sfb, len(sfb), c[1], self.tnf[1])
+        return np.stack(c), seeds

@@ -84,3 +84,96 @@ def test_igf_batch_vs_oracle(gpu_lib, oracle):
                 assert int(seed[u]) == want_seed, (u, f)
     finally:
         gi.close()
+
+
+class GpuIgfPairs:
+    """n channel pairs through the joint-stereo IGF chain: fill, optional M/S over the IGF range (spectra and TNF
+    buffers), TNF -- units 2p (left), 2p+1 (right)."""
+
+    def __init__(self, lib, n_pairs):
+        import torch
+        self.torch, self.lib, self.n = torch, lib, n_pairs
+        self.bands = lib.bands_create(igf_cases.SFB_LONG, igf_cases.SFB_SHORT)
+        self.tnf = torch.zeros(2 * n_pairs, 2048, device="cuda")
+        self.dummy = torch.zeros(n_pairs, 2048, device="cuda")
+
+    def close(self):
+        self.lib.bands_destroy(self.bands)
+
+    def frame(self, sdl, sdr, masks, coef, tiles, ms_after):
+        import stereo_cases
+        torch, lib, n = self.torch, self.lib, self.n
+        st = torch.cuda.current_stream().cuda_stream
+        sides = np.zeros(2 * n, igf_cases.IGF_SIDE)
+        sides[0::2], sides[1::2] = sdl, sdr
+        sides["unit"] = np.arange(2 * n)
+        d_side = torch.from_numpy(sides.view(np.uint8).reshape(2 * n, -1).copy()).cuda()
+        d_coef = torch.from_numpy(np.ascontiguousarray(coef, np.float32).reshape(2 * n, 1024)).cuda()
+        d_tiles = torch.from_numpy(np.ascontiguousarray(tiles, np.float32).reshape(2 * n, 4, 1024)).cuda()
+        d_mask = torch.from_numpy(np.ascontiguousarray(masks, np.uint8)).cuda()
+        d_seed = torch.zeros(2 * n, dtype=torch.int32, device="cuda")
+        lib.igf_stereo_dev(self.bands, d_coef.data_ptr(), d_tiles.data_ptr(), d_side.data_ptr(), d_mask.data_ptr(),
+                           self.tnf.data_ptr(), d_seed.data_ptr(), n, st)
+        # stereo tool over the IGF band range on the spectra, and on the TNF spectra of long blocks with TNF enabled
+        ms = np.zeros(n, stereo_cases.STEREO_SIDE)
+        ms_t = np.zeros(n, stereo_cases.STEREO_SIDE)
+        for p in range(n):
+            ms[p]["left"], ms[p]["right"], ms[p]["slot"] = 2 * p, 2 * p + 1, p
+            ms[p]["tool"] = 1 if ms_after[p] else 0
+            ms[p]["is_short"] = sdl[p]["win_type"]
+            ms[p]["first_band"], ms[p]["last_band"] = sdl[p]["sfb_start"], sdl[p]["sfb_stop"]
+            ms[p]["used"] = igf_cases.mask_per_window(masks[p], sdl[p])
+            ms_t[p] = ms[p]
+            ms_t[p]["left"], ms_t[p]["right"] = 4 * p, 4 * p + 2  # TNF spectra inside [unit][2048] viewed as [.][1024]
+            if not (sdl[p]["use_tnf"] and not sdl[p]["win_type"]):
+                ms_t[p]["tool"] = 0
+        d_ms = torch.from_numpy(ms.view(np.uint8).reshape(n, -1).copy()).cuda()
+        d_ms_t = torch.from_numpy(ms_t.view(np.uint8).reshape(n, -1).copy()).cuda()
+        lib.stereo_dev(self.bands, d_coef.data_ptr(), d_ms.data_ptr(), self.dummy.data_ptr(), n, st)
+        lib.stereo_dev(self.bands, self.tnf.data_ptr(), d_ms_t.data_ptr(), self.dummy.data_ptr(), n, st)
+        lib.igf_tnf_dev(self.bands, d_coef.data_ptr(), d_side.data_ptr(), self.tnf.data_ptr(), 2 * n, st)
+        torch.cuda.synchronize()
+        return d_coef.cpu().numpy().reshape(n, 2, 1024), d_seed.cpu().numpy().view(np.uint32).reshape(n, 2)
+
+
+def test_igf_stereo_golden(gpu_lib):
+    g = np.load(GOLD)
+    C = len(igf_cases.CONFIGS)
+    sdl = [g[f"s{ci}_sdl"].view(igf_cases.IGF_SIDE).reshape(-1) for ci in range(C)]
+    sdr = [g[f"s{ci}_sdr"].view(igf_cases.IGF_SIDE).reshape(-1) for ci in range(C)]
+    gp = GpuIgfPairs(gpu_lib, C)
+    try:
+        for k in range(len(sdl[0])):
+            y, seeds = gp.frame([sdl[ci][k] for ci in range(C)], [sdr[ci][k] for ci in range(C)],
+                                np.stack([g[f"s{ci}_mask"][k] for ci in range(C)]),
+                                np.stack([g[f"s{ci}_in"][k] for ci in range(C)]),
+                                np.stack([g[f"s{ci}_tiles"][k] for ci in range(C)]),
+                                [int(g[f"s{ci}_ms"][k]) for ci in range(C)])
+            for ci in range(C):
+                assert bits_equal(y[ci], g[f"s{ci}_out"][k]), (ci, k)
+                assert np.array_equal(seeds[ci], g[f"s{ci}_seeds"][k]), (ci, k)
+    finally:
+        gp.close()
+
+
+def test_igf_stereo_batch_vs_oracle(gpu_lib, oracle):
+    """300 pairs x 4 frames against the oracle chain (fill, M/S on spectra and TNF buffers, TNF)."""
+    g = np.load(GOLD)
+    P, F = 300, 4
+    rngs = [np.random.default_rng(88000 + p) for p in range(P)]
+    cfgs = [p % len(igf_cases.CONFIGS) for p in range(P)]
+    pairs = [igf_cases.OracleIgfPair() for _ in range(P)]
+    gp = GpuIgfPairs(gpu_lib, P)
+    try:
+        for f in range(F):
+            fr = [igf_cases.random_pair_frame(rngs[p], igf_cases.CONFIGS[cfgs[p]], g[f"c{cfgs[p]}_grid"],
+                                              win_type=int(rngs[p].random() < 0.3)) for p in range(P)]
+            ms_after = [int(rngs[p].integers(2)) for p in range(P)]
+            y, seeds = gp.frame([x[0] for x in fr], [x[1] for x in fr], np.stack([x[2] for x in fr]),
+                                np.stack([x[3] for x in fr]), np.stack([x[4] for x in fr]), ms_after)
+            for p in range(P):
+                want, want_seeds = pairs[p].frame(fr[p][0], fr[p][1], fr[p][2], fr[p][3], fr[p][4], ms_after[p])
+                assert bits_equal(y[p], want), (p, f, int(fr[p][0]["win_type"]), ms_after[p])
+                assert np.array_equal(seeds[p], want_seeds), (p, f)
+    finally:
+        gp.close()

@@ -58,3 +58,38 @@ def test_oracle_matches_reference_live(oracle, ref):
             assert bits_equal(y, want), (ci, k, int(sd["win_type"]))
             assert seed == want_seed
         ref.ref_igf_destroy(h)
+
+
+def test_stereo_oracle_matches_golden(oracle):
+    g = np.load(GOLD)
+    for ci in range(len(igf_cases.CONFIGS)):
+        sdl = g[f"s{ci}_sdl"].view(igf_cases.IGF_SIDE).reshape(-1)
+        sdr = g[f"s{ci}_sdr"].view(igf_cases.IGF_SIDE).reshape(-1)
+        pair = igf_cases.OracleIgfPair()
+        for k in range(len(sdl)):
+            y, seeds = pair.frame(sdl[k], sdr[k], g[f"s{ci}_mask"][k], g[f"s{ci}_in"][k], g[f"s{ci}_tiles"][k],
+                                  int(g[f"s{ci}_ms"][k]))
+            assert bits_equal(y, g[f"s{ci}_out"][k]), (ci, k, int(sdl[k]["win_type"]))
+            assert np.array_equal(seeds, g[f"s{ci}_seeds"][k]), (ci, k)
+
+
+def test_stereo_oracle_matches_reference_live(oracle, ref):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_igf_golden as mg
+    for ci, cfg in enumerate(igf_cases.CONFIGS):
+        h, grid = mg.reference_grid(cfg)
+        rng = np.random.default_rng(14000 + ci)
+        pair = igf_cases.OracleIgfPair()
+        for k in range(30):
+            sd_l, sd_r, mask, coef, tiles = igf_cases.random_pair_frame(rng, cfg, grid, win_type=int(rng.random() < 0.3))
+            ms_after = int(rng.integers(2))
+            want = coef.copy()
+            want_seeds = np.zeros(2, np.uint32)
+            ref.ref_igf_stereo_process(h, sd_l.tobytes(), sd_r.tobytes(), igf_cases.mask_reference_layout(mask, sd_l),
+                                       ms_after, want[0], want[1], np.ascontiguousarray(tiles[0]).reshape(-1),
+                                       np.ascontiguousarray(tiles[1]).reshape(-1), want_seeds)
+            y, seeds = pair.frame(sd_l, sd_r, mask, coef, tiles, ms_after)
+            assert bits_equal(y, want), (ci, k, int(sd_l["win_type"]), ms_after)
+            assert np.array_equal(seeds, want_seeds), (ci, k)
+        ref.ref_igf_destroy(h)
