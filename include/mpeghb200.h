@@ -449,6 +449,23 @@ mpeghb200_status mpeghb200_igf_tnf_dev(mpeghb200_ctx *ctx, const mpeghb200_bands
 /* whitening gain tables [2][64] (host, no GPU needed): pinned against the reference ROM by the tests */
 void mpeghb200_igf_whitening_rom(float *out128);
 
+/* ---- element-wise steps between the renderers and the limiter -----------------
+ * Bus add: d_out[i] = d_a[i] + d_b[i] over n_floats samples (a multiple of 4; d_out may alias d_a or d_b): the
+ * bed + objects / bed + HOA / HOA + objects sums of decoder/ia_core_coder_decode_main.c:2185-2195, 2203-2213,
+ * 2276-2302.  Channel mask: channel c of d_audio [n_channels][1024] becomes zeros where d_on[c] == 0 -- the
+ * per-channel outcome of impeghd_mdp_dec_process (decode_main.c:906-1070); the metadata group / preset logic that
+ * produces d_on stays on the host. */
+mpeghb200_status mpeghb200_bus_add_dev(mpeghb200_ctx *ctx, const float *d_a, const float *d_b, float *d_out,
+                                       size_t n_floats, void *cuda_stream);
+mpeghb200_status mpeghb200_channel_mask_dev(mpeghb200_ctx *ctx, float *d_audio, const uint8_t *d_on, int n_channels,
+                                            void *cuda_stream);
+/* Per-sample gain curves: d_audio[c][s] *= d_gains[d_seq_of_ch[c]][s] for every
+ * channel with d_seq_of_ch[c] >= 0 -- the time-domain application of single-band DRC gain sequences,
+ * impd_drc_apply_gains_and_add (decoder/impd_drc_process.c:68-175).  Gain decoding, DRC set selection and the
+ * spline interpolation into the per-sample curve lpcm_gains (libm) stay on the host: d_gains [n_seq][1024]. */
+mpeghb200_status mpeghb200_gain_apply_dev(mpeghb200_ctx *ctx, float *d_audio, const float *d_gains,
+                                          const int32_t *d_seq_of_ch, int n_channels, void *cuda_stream);
+
 /* ---- output resampler ------------------------------------------------------------------------------------
  * Replaces impeghd_resample (decoder/impeghd_resampler.c:93): fac_up/fac_down = 2/1, 3/1 or 3/2
  * (impeghd_resampler_get_sampling_ratio, decoder/impeghd_api.c:132).  filter_up = impeghd_resampler_filter

@@ -1,0 +1,96 @@
+// mix.cu -- the element-wise steps that sit between the renderers and the limiter:
+//   bus add       time_sample_vector[ch][s] = a[ch][s] + b[ch][s]: bed + objects, bed + HOA, HOA + objects
+//                 (decoder/ia_core_coder_decode_main.c:2185-2195, :2203-2213, :2276-2302)
+//   channel mask  a member channel of a switched-off metadata group is replaced by zeros, the others pass
+//                 (impeghd_mdp_dec_process, decoder/ia_core_coder_decode_main.c:906-1070: the group / preset logic
+//                 that decides on or off stays with the host, the kernel applies the per-channel verdict)
+//   gain apply    audio[ch][s] *= gain[seq(ch)][s]: the time-domain application of single-band DRC gain sequences
+//                 (impd_drc_apply_gains_and_add, decoder/impd_drc_process.c:68-175 with impd_apply_gains == 1,
+//                 SURVEY.md section 8f rank 2); decoding, selecting and interpolating the gains (spline nodes,
+//                 libm exp/log) stays with the host, which hands over one 1024-sample curve per sequence and frame
+// All are pure HBM streams: float4 per thread.
+#include "common.h"
+
+namespace mpeghb200 {
+namespace {
+
+__global__ void __launch_bounds__(256)
+    bus_add_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ out, size_t n4) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n4; i += size_t(gridDim.x) * blockDim.x) {
+    const float4 x = a[i], y = b[i];
+    out[i] = make_float4(fadd(x.x, y.x), fadd(x.y, y.y), fadd(x.z, y.z), fadd(x.w, y.w));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    channel_mask_kernel(float4* __restrict__ audio, const uint8_t* __restrict__ on, int n_channels) {
+  const int c = blockIdx.x;
+  if (c < n_channels && !on[c]) audio[size_t(c) * 256 + threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__global__ void __launch_bounds__(256)
+    gain_apply_kernel(float4* __restrict__ audio, const float4* __restrict__ gains, const int32_t* __restrict__ seq_of_ch,
+                      int n_channels) {
+  const int c = blockIdx.x;
+  if (c >= n_channels) return;
+  const int q = seq_of_ch[c];
+  if (q < 0) return;  // channel without a DRC channel group
+  float4 x = audio[size_t(c) * 256 + threadIdx.x];
+  const float4 g = gains[size_t(q) * 256 + threadIdx.x];
+  x.x = fmul(x.x, g.x), x.y = fmul(x.y, g.y), x.z = fmul(x.z, g.z), x.w = fmul(x.w, g.w);
+  audio[size_t(c) * 256 + threadIdx.x] = x;
+}
+
+}  // namespace
+}  // namespace mpeghb200
+
+using namespace mpeghb200;
+
+extern "C" {
+
+mpeghb200_status mpeghb200_bus_add_dev(mpeghb200_ctx* ctx, const float* d_a, const float* d_b, float* d_out,
+                                       size_t n_floats, void* cuda_stream) {
+  if (!ctx) return MPEGHB200_ERR_BAD_ARG;
+  if (n_floats == 0) return MPEGHB200_OK;
+  if (!d_a || !d_b || !d_out || (n_floats & 3))
+    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "bus_add_dev: null buffer, or a length that is not a multiple of 4");
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t n4 = n_floats / 4;
+  const size_t want = (n4 + 255) / 256;
+  const int grid = int(want < size_t(ctx->sm_count) * 8 ? want : size_t(ctx->sm_count) * 8);
+  bus_add_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+      reinterpret_cast<const float4*>(d_a), reinterpret_cast<const float4*>(d_b), reinterpret_cast<float4*>(d_out), n4);
+  ctx->launches.fetch_add(1);
+  MB_CUDA(ctx, cudaGetLastError());
+  return MPEGHB200_OK;
+}
+
+mpeghb200_status mpeghb200_channel_mask_dev(mpeghb200_ctx* ctx, float* d_audio, const uint8_t* d_on, int n_channels,
+                                            void* cuda_stream) {
+  if (!ctx) return MPEGHB200_ERR_BAD_ARG;
+  if (n_channels < 0 || (n_channels > 0 && (!d_audio || !d_on)))
+    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "channel_mask_dev: null buffer or negative channel count");
+  if (n_channels == 0) return MPEGHB200_OK;
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  channel_mask_kernel<<<n_channels, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+      reinterpret_cast<float4*>(d_audio), d_on, n_channels);
+  ctx->launches.fetch_add(1);
+  MB_CUDA(ctx, cudaGetLastError());
+  return MPEGHB200_OK;
+}
+
+mpeghb200_status mpeghb200_gain_apply_dev(mpeghb200_ctx* ctx, float* d_audio, const float* d_gains,
+                                          const int32_t* d_seq_of_ch, int n_channels, void* cuda_stream) {
+  if (!ctx) return MPEGHB200_ERR_BAD_ARG;
+  if (n_channels < 0 || (n_channels > 0 && (!d_audio || !d_gains || !d_seq_of_ch)))
+    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "gain_apply_dev: null buffer or negative channel count");
+  if (n_channels == 0) return MPEGHB200_OK;
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  gain_apply_kernel<<<n_channels, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+      reinterpret_cast<float4*>(d_audio), reinterpret_cast<const float4*>(d_gains), d_seq_of_ch, n_channels);
+  ctx->launches.fetch_add(1);
+  MB_CUDA(ctx, cudaGetLastError());
+  return MPEGHB200_OK;
+}
+
+}  // extern "C"

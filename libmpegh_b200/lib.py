@@ -214,6 +214,12 @@ class Lib:
         c.mpeghb200_bands_destroy.argtypes = [vp]
         c.mpeghb200_igf_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
         c.mpeghb200_igf_dev.restype = i32
+        c.mpeghb200_bus_add_dev.argtypes = [vp, vp, vp, vp, sz, vp]
+        c.mpeghb200_bus_add_dev.restype = i32
+        c.mpeghb200_channel_mask_dev.argtypes = [vp, vp, vp, ctypes.c_int, vp]
+        c.mpeghb200_channel_mask_dev.restype = i32
+        c.mpeghb200_gain_apply_dev.argtypes = [vp, vp, vp, vp, ctypes.c_int, vp]
+        c.mpeghb200_gain_apply_dev.restype = i32
         c.mpeghb200_igf_stereo_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
         c.mpeghb200_igf_stereo_dev.restype = i32
         c.mpeghb200_igf_tnf_dev.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, vp]
@@ -340,6 +346,15 @@ class Lib:
 
     def igf_tnf_dev(self, bands, d_coef, d_side, d_tnf_state, n_units, stream=0):
         self.check(self.c.mpeghb200_igf_tnf_dev(self.ctx, bands, d_coef, d_side, d_tnf_state, n_units, stream))
+
+    def bus_add_dev(self, d_a, d_b, d_out, n_floats, stream=0):
+        self.check(self.c.mpeghb200_bus_add_dev(self.ctx, d_a, d_b, d_out, n_floats, stream))
+
+    def channel_mask_dev(self, d_audio, d_on, n_channels, stream=0):
+        self.check(self.c.mpeghb200_channel_mask_dev(self.ctx, d_audio, d_on, n_channels, stream))
+
+    def gain_apply_dev(self, d_audio, d_gains, d_seq_of_ch, n_channels, stream=0):
+        self.check(self.c.mpeghb200_gain_apply_dev(self.ctx, d_audio, d_gains, d_seq_of_ch, n_channels, stream))
 
     def igf_whitening_rom(self):
         t = np.zeros((2, 64), np.float32)
