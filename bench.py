@@ -8,8 +8,9 @@ batch = 6144 channel-frames through mpeghb200_fd_synth (one kernel launch).
   value      device-resident inputs, CUDA-event timed over K back-to-back steps.  To keep every step's
              16 KB/unit of traffic in HBM and not in the 126 MB L2, the timed loop rotates over G stream
              groups (each with its own spectra, overlap state and output: 3 x 25 MB), G*75 MB >> L2.
-  e2e        the same step through the host-buffer C-ABI call (mpeghb200_fd_execute): pinned host
-             spectra -> device, kernel, PCM -> host, every step.
+  e2e        the same step through the host-buffer C ABI (mpeghb200_fd_submit / _wait, two frames in flight; the
+             synchronous mpeghb200_fd_execute is reported beside it): pinned host spectra -> device, kernel,
+             PCM -> host, every step, all inside the timed region.
   roofline   algorithmic bytes (16384 B per channel-frame) / mean step duration, vs the
              measured HBM copy bandwidth in MEASURED_PEAKS.json.
   cpu_baseline  the unmodified reference's ia_core_coder_fd_frm_dec (oracle/_ref, kind "reference"; the
@@ -216,7 +217,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--groups", type=int, default=8, help="stream groups rotated through (working set > L2)")
-    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -318,25 +319,43 @@ def main():
 
     # ---- e2e: host buffers through the session API, copies inside the timed region --------------
     sess = lib.fd_open(STREAMS, CHANNELS)
-    n_host = 3
+    n_host = 4
     h_coef = [torch.empty(STREAMS, CHANNELS, FRAME, dtype=torch.float32).pin_memory() for _ in range(n_host)]
     for h in h_coef:
         h.copy_(torch.from_numpy(rng.normal(0, 500, (STREAMS, CHANNELS, FRAME)).astype(np.float32)))
     h_out = [torch.empty(STREAMS, CHANNELS, FRAME, dtype=torch.float32).pin_memory() for _ in range(n_host)]
     h_side = np.ascontiguousarray(fd_cases.pack_side(make_side(rng, UNITS)).reshape(STREAMS, CHANNELS))
 
-    def e2e_step(i):
+    def e2e_submit(i):
         k = i % n_host
-        lib.check(lib.c.mpeghb200_fd_execute(sess.h, h_coef[k].data_ptr(), h_side.ctypes.data, h_out[k].data_ptr()))
+        lib.check(lib.c.mpeghb200_fd_submit(sess.h, h_coef[k].data_ptr(), h_side.ctypes.data, h_out[k].data_ptr()))
 
-    for i in range(3):
-        e2e_step(i)
+    def e2e_wait():
+        lib.check(lib.c.mpeghb200_fd_wait(sess.h))
+
+    # two frames in flight: frame i is submitted, then frame i - 1 is waited for (its PCM is in host memory);
+    # every frame's spectra go host -> device and its PCM device -> host inside the timed region
+    e2e_submit(0)
+    for i in range(1, 4):
+        e2e_submit(i)
+        e2e_wait()
+    e2e_wait()
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.e2e_steps):
-        e2e_step(i)
+    e2e_submit(0)
+    for i in range(1, args.e2e_steps):
+        e2e_submit(i)
+        e2e_wait()
+    e2e_wait()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    # the same through the synchronous call (one frame at a time: upload, kernel and download of a frame only
+    # overlap chunk-wise inside the call)
+    t0 = time.perf_counter()
+    for i in range(args.e2e_steps):
+        k = i % n_host
+        lib.check(lib.c.mpeghb200_fd_execute(sess.h, h_coef[k].data_ptr(), h_side.ctypes.data, h_out[k].data_ptr()))
+    e2e_sync_s = (time.perf_counter() - t0) / args.e2e_steps
     t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -373,7 +392,8 @@ def main():
                          "kernel": "fd_synth_ws_kernel", "algorithmic_bytes_per_launch": BYTES_PER_UNIT * UNITS},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": UNITS * FRAME * 4 + UNITS * 4,
                     "d2h_bytes_per_step": UNITS * FRAME * 4, "ms_per_step": e2e_s * 1e3,
-                    "api": "mpeghb200_fd_execute (pinned host buffers)"},
+                    "api": "mpeghb200_fd_submit / mpeghb200_fd_wait, two frames in flight (pinned host buffers)",
+                    "synchronous_call_ms_per_step": e2e_sync_s * 1e3},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

@@ -98,6 +98,14 @@ mpeghb200_status mpeghb200_fd_open(mpeghb200_ctx *ctx, int n_streams, int n_ch, 
 /* One frame for every stream: h_coef/h_out [n_streams][n_ch][1024], h_side [n_streams][n_ch]. */
 mpeghb200_status mpeghb200_fd_execute(mpeghb200_fd_session *s, const float *h_coef, const uint32_t *h_side,
                                       float *h_out);
+/* The same, asynchronous: submit enqueues the frame (uploads, kernels, downloads) and returns; wait blocks until
+ * the OLDEST submitted frame is complete (its h_out filled).  At most two frames may be in flight; with two, the
+ * download of frame f overlaps the upload of frame f + 1 (PCIe is full duplex).  Frames execute in submission
+ * order.  The host buffers of a frame must stay valid and untouched until its wait returns.
+ * mpeghb200_fd_execute = drain, submit, wait. */
+mpeghb200_status mpeghb200_fd_submit(mpeghb200_fd_session *s, const float *h_coef, const uint32_t *h_side,
+                                     float *h_out);
+mpeghb200_status mpeghb200_fd_wait(mpeghb200_fd_session *s);
 /* Zero the state of one stream (the reference's flush / re-init, decoder/impeghd_api.c:1156). */
 mpeghb200_status mpeghb200_fd_reset_stream(mpeghb200_fd_session *s, int stream);
 void mpeghb200_fd_close(mpeghb200_fd_session *s);

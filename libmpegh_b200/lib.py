@@ -131,6 +131,10 @@ class Lib:
         c.mpeghb200_fd_open.restype = i32
         c.mpeghb200_fd_execute.argtypes = [vp, vp, vp, vp]
         c.mpeghb200_fd_execute.restype = i32
+        c.mpeghb200_fd_submit.argtypes = [vp, vp, vp, vp]
+        c.mpeghb200_fd_submit.restype = i32
+        c.mpeghb200_fd_wait.argtypes = [vp]
+        c.mpeghb200_fd_wait.restype = i32
         c.mpeghb200_fd_reset_stream.argtypes = [vp, ctypes.c_int]
         c.mpeghb200_fd_reset_stream.restype = i32
         c.mpeghb200_fd_close.argtypes = [vp]
@@ -559,6 +563,16 @@ class FdSession:
             out = np.empty_like(coef)
         self.lib.check(self.lib.c.mpeghb200_fd_execute(self.h, coef.ctypes.data, side.ctypes.data, out.ctypes.data))
         return out
+
+    def submit(self, coef, side, out):
+        """Asynchronous frame: the three arrays must stay alive and untouched until the matching wait()."""
+        assert coef.dtype == np.float32 and side.dtype == np.uint32 and out.dtype == np.float32
+        assert coef.flags.c_contiguous and side.flags.c_contiguous and out.flags.c_contiguous
+        assert coef.shape == (self.n_streams, self.n_ch, FRAME_LEN) and side.shape == (self.n_streams, self.n_ch)
+        self.lib.check(self.lib.c.mpeghb200_fd_submit(self.h, coef.ctypes.data, side.ctypes.data, out.ctypes.data))
+
+    def wait(self):
+        self.lib.check(self.lib.c.mpeghb200_fd_wait(self.h))
 
     def reset_stream(self, idx):
         self.lib.check(self.lib.c.mpeghb200_fd_reset_stream(self.h, idx))

@@ -168,3 +168,37 @@ def test_vs_reference_build_if_present(gpu_lib):
             assert bits_equal(out[0], out_r[f]), f
     finally:
         sess.close()
+
+
+def test_session_submit_wait_pipelined(gpu_lib, oracle):
+    """Two frames in flight (mpeghb200_fd_submit / _wait): results and carried overlap state equal the oracle's
+    frame-by-frame run; a third submit without a wait is refused; execute() drains what is in flight first."""
+    from libmpegh_b200.lib import MpeghError
+    rng = np.random.default_rng(77)
+    S, C, F = 40, 24, 7  # 960 units: two chunks per frame
+    U = S * C
+    side = fd_cases.random_side(rng, F, U, kernel_switch_prob=0.1)
+    coef = fd_cases.random_coef(rng, (F, U, 1024))
+    ov = np.zeros((U, 1024), np.float32)
+    want = np.zeros((F, U, 1024), np.float32)
+    assert oracle.oracle_fd_frm_dec_batch(coef, ov, want, side, F, U) == 0
+    packed = [np.ascontiguousarray(fd_cases.pack_side(side[f]).reshape(S, C).astype(np.uint32)) for f in range(F)]
+    cf = [np.ascontiguousarray(coef[f].reshape(S, C, 1024)) for f in range(F)]
+    outs = [np.zeros((S, C, 1024), np.float32) for _ in range(F)]
+    sess = gpu_lib.fd_open(S, C)
+    try:
+        sess.submit(cf[0], packed[0], outs[0])
+        sess.submit(cf[1], packed[1], outs[1])
+        with pytest.raises(MpeghError):
+            sess.submit(cf[2], packed[2], outs[2])
+        for f in range(2, F - 1):
+            sess.wait()
+            assert bits_equal(outs[f - 2].reshape(U, 1024), want[f - 2]), f - 2
+            sess.submit(cf[f], packed[f], outs[f])
+        got_last = sess.execute(cf[F - 1], packed[F - 1])  # drains frames F-3, F-2, then runs the last one
+        for f in range(F - 1):
+            assert bits_equal(outs[f].reshape(U, 1024), want[f]), f
+        assert bits_equal(got_last.reshape(U, 1024), want[F - 1])
+        sess.wait()  # nothing in flight: no-op
+    finally:
+        sess.close()
