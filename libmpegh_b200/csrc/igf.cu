@@ -49,42 +49,78 @@ __device__ __forceinline__ uint32_t lcg_jump(uint32_t seed, uint32_t steps, cons
 
 struct Grid {
   int n_tiles, tile[4];
+  int tstart[4];  // first bin of tile t
+  int toff[4];    // source offset of tile t for this frame's tile numbers: source bin = target bin - toff
   int bgn, end;
 };
 
 __device__ __forceinline__ int tile_of(int tb, const Grid& G) {
-  int t, sum = G.bgn;
-  for (t = 0; t < G.n_tiles; ++t) {
-    sum += G.tile[t];
-    if (tb < sum) break;
-  }
-  return t;
+  int t = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) t += (q < G.n_tiles && tb >= G.tstart[q] + G.tile[q]);
+  return t;  // == n_tiles when the bin lies behind the last tile, like the reference's loop
 }
 
-__device__ __forceinline__ int source_bin(int igf_min, int tb, const Grid& G, const uint8_t* tile_num) {
+// ia_core_coder_igf_get_sb (:839) with the per-tile offset precomputed (source_offset below)
+__device__ __forceinline__ int source_bin(int igf_min, int tb, int ix, const Grid& G, const int* toff) {
   const int src = G.bgn - igf_min;
-  int sbs = G.bgn, offset = 0, sb = tb;
+  int sb = tb;
   if (src > 0) {
-    for (int i = 0; i < G.n_tiles; ++i) {
-      if (tb >= sbs && tb < sbs + G.tile[i]) {
-        const float sel = float(int8_t(tile_num[i]));
-        offset = int(fsub(fadd(fmul(fadd(2.5f, fmul(-0.5f, sel)), float(G.tile[i])), float(sbs)), float(G.bgn)));
-        offset += offset % 2;
-        break;
-      }
-      sbs += G.tile[i];
-    }
-    sb = tb - offset;
+    if (ix < G.n_tiles && tb >= G.tstart[ix]) sb = tb - toff[ix];
     if (sb < igf_min) sb = igf_min + tb % src;
   }
   return sb;
+}
+
+__device__ __forceinline__ int source_offset(int tile_len, int sbs, int bgn, int tile_num) {
+  const float sel = float(int8_t(tile_num));
+  int offset = int(fsub(fadd(fmul(fadd(2.5f, fmul(-0.5f, sel)), float(tile_len)), float(sbs)), float(bgn)));
+  offset += offset % 2;
+  return offset;
+}
+
+// Tile widths of the grid (ia_core_coder_igf_get_num_tiles :760) by one thread; b2s maps a bin to its band, so the
+// reference's "first band edge at or above lim" search is one lookup: j = band(lim - 1) + 1.
+__device__ void compute_grid(Grid& G, const mpeghb200_igf_side& sd, const int16_t* __restrict__ tbl,
+                             const uint8_t* __restrict__ b2s) {
+  auto edge = [&](int i) { return i ? int(__ldg(tbl + i - 1)) : 0; };
+  const int s0 = sd.sfb_start, s1 = sd.sfb_stop;
+  const int bgn = edge(s0), end = edge(s1);
+  int range = end - bgn < 8 ? 8 : end - bgn, mem = s0, sbs = bgn, n = 0;
+  int tile[4] = {range >> 2, range >> 2, range >> 2, range >> 2};
+  if (bgn > sd.igf_min && bgn < end) {
+    for (int i = 0; i < 4; ++i) {
+      const int lim = min(sbs + tile[i], end);
+      int j = lim > 0 ? int(__ldg(b2s + lim - 1)) + 1 : 1;
+      if (j < 1) j = 1;
+      if (!sd.use_high_res) {
+        if (i == 3)
+          j = s1;
+        else if ((((j - s0) & 1) == 1) && ((j - mem) > 1))
+          --j;
+        mem = j;
+      }
+      tile[i] = max(2, min(edge(j) - sbs, end - sbs));
+      ++n;
+      sbs += tile[i];
+      if (sbs == end) break;
+    }
+  }
+  int st = bgn;
+  for (int i = 0; i < 4; ++i) {
+    G.tile[i] = i < n ? tile[i] : 0;
+    G.tstart[i] = st;
+    st += G.tile[i];
+  }
+  G.n_tiles = n, G.bgn = bgn, G.end = end;
 }
 
 __global__ void __launch_bounds__(kThreads)
     igf_kernel(float* __restrict__ coef_g, const float* __restrict__ tiles_g,
                const mpeghb200_igf_side* __restrict__ sides, float* __restrict__ tnf_state,
                uint32_t* __restrict__ seed_out, const int16_t* __restrict__ sfb_long, int n_long,
-               const int16_t* __restrict__ sfb_short, int n_short, const int tnf_only, const IgfRom R) {
+               const int16_t* __restrict__ sfb_short, int n_short, const uint8_t* __restrict__ b2s_long,
+               const uint8_t* __restrict__ b2s_short, const int tnf_only, const IgfRom R) {
   __shared__ mpeghb200_igf_side sd;
   __shared__ __align__(16) float coef[kFrame];
   __shared__ __align__(16) float tiles[4 * kFrame];
@@ -92,8 +128,10 @@ __global__ void __launch_bounds__(kThreads)
   __shared__ __align__(16) float tnf[kFrame];   // igf_tnf_spec_float
   __shared__ __align__(16) float tbuf[kFrame];  // unfiltered copy for the FIR / igf_tnf_mask staging
   __shared__ float gn[128];                     // gains, [16 * group + sfb] (long: [sfb])
+  __shared__ float esum[2][128];                // group-normalised band energies: coded, source
   __shared__ int16_t swb[72];
   __shared__ Grid G;
+  __shared__ int toff[4];
   __shared__ uint32_t warp_cnt[kThreads / 32];
   __shared__ float norms[3], acfp[3][8], pred[17];
   __shared__ int tnf_order;
@@ -123,38 +161,21 @@ __global__ void __launch_bounds__(kThreads)
 
   // ---- stage: band edges, spectrum, tiles -----------------------------------------------------------
   for (int i = tid; i <= n_sfb; i += kThreads) swb[i] = i ? (is_short ? sfb_short : sfb_long)[i - 1] : 0;
-  reinterpret_cast<float4*>(coef)[tid] = reinterpret_cast<const float4*>(cg)[tid];
+  const float4 rc = reinterpret_cast<const float4*>(cg)[tid];
+  float4 rt[4];
   if (!all_zero) {
     const float4* tg = reinterpret_cast<const float4*>(tiles_g + size_t(blockIdx.x) * 4 * kFrame);
 #pragma unroll
-    for (int t = 0; t < 4; ++t) reinterpret_cast<float4*>(tiles)[t * 256 + tid] = tg[t * 256 + tid];
+    for (int t = 0; t < 4; ++t) rt[t] = tg[t * 256 + tid];
   }
-  __syncthreads();
-  if (tid == 0) {  // tile widths of the grid (ia_core_coder_igf_get_num_tiles :760)
-    const int s0 = sd.sfb_start, s1 = sd.sfb_stop;
-    const int bgn = swb[s0], end = swb[s1];
-    int range = end - bgn < 8 ? 8 : end - bgn, mem = s0, sbs = bgn, n = 0;
-    int tile[4] = {range >> 2, range >> 2, range >> 2, range >> 2};
-    if (bgn > sd.igf_min && bgn < end) {
-      for (int i = 0; i < 4; ++i) {
-        const int lim = min(sbs + tile[i], end);
-        int j = 1;
-        while (lim > swb[j]) ++j;
-        if (!sd.use_high_res) {
-          if (i == 3)
-            j = s1;
-          else if ((((j - s0) & 1) == 1) && ((j - mem) > 1))
-            --j;
-          mem = j;
-        }
-        tile[i] = max(2, min(swb[j] - sbs, end - sbs));
-        ++n;
-        sbs += tile[i];
-        if (sbs == end) break;
-      }
-    }
-    for (int i = 0; i < 4; ++i) G.tile[i] = i < n ? tile[i] : 0;
-    G.n_tiles = n, G.bgn = bgn, G.end = end;
+  if (tid == 0) {  // while the loads are in flight
+    compute_grid(G, sd, is_short ? sfb_short : sfb_long, is_short ? b2s_short : b2s_long);
+    for (int i = 0; i < 4; ++i) toff[i] = source_offset(G.tile[i], G.tstart[i], G.bgn, sd.tile_num[i]);
+  }
+  reinterpret_cast<float4*>(coef)[tid] = rc;
+  if (!all_zero) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) reinterpret_cast<float4*>(tiles)[t * 256 + tid] = rt[t];
   }
   __syncthreads();
   const int bgn = G.bgn, end = G.end;
@@ -208,7 +229,7 @@ __global__ void __launch_bounds__(kThreads)
       v[k] = 0.0f;
       if (b >= bgn && b < end) {
         const int ix = tile_of(b, G);
-        const int sb = source_bin(sd.igf_min, b, G, sd.tile_num);
+        const int sb = source_bin(sd.igf_min, b, ix, G, toff);
         v[k] = tiles[ix * kFrame + w * bins + sb];
         noise[k] = noise_ok && coef[i] == 0.0f && sd.whitening_level[ix] == 2;
         my_noise += noise[k];
@@ -242,41 +263,63 @@ __global__ void __launch_bounds__(kThreads)
     __syncthreads();
 
     // ---- band energies per (group, band), windows of a group in order (:1083, :1002) ---------------------
+    // The squares are formed by everybody first (tnf / tbuf are free until the fill); what stays serial is the
+    // pure addition chain of every band, one thread per (sum, group, band).  Adding the +0 of a coded bin to the
+    // source-energy chain leaves it unchanged, so that chain runs over all bins of the band, branch-free.
     const int step = (sd.use_high_res || is_short) ? 1 : 2;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = 4 * tid + k;
+      const float cb = coef[i];
+      tnf[i] = fmul(cb, cb);
+      tbuf[i] = cb == 0.0f ? fmul(val[i], val[i]) : 0.0f;
+    }
+    __syncthreads();
+    {
+      const int which = tid >> 7, r = tid & 127;  // 0: coded energy, 1: source energy on the zero bins
+      const int g = is_short ? r >> 4 : 0;
+      const int sfb = is_short ? r & 15 : r;
+      const bool live = g < sd.num_groups && sfb >= sd.sfb_start && sfb < sd.sfb_stop &&
+                        ((sfb - sd.sfb_start) % step) == 0 && (is_short || r < 64);
+      if (live) {
+        int w0 = 0;
+        for (int q = 0; q < g; ++q) w0 += sd.group_len[q];
+        const int hi = min(sfb + step, int(sd.sfb_stop));
+        const float* arr = which ? tbuf : tnf;
+        float acc = 0.0f;
+        for (int q = 0; q < sd.group_len[g]; ++q) {
+          const float* a = arr + (w0 + q) * bins;
+          float e = 0.0f;
+          int b = swb[sfb];
+          const int b1 = swb[hi];
+          for (; (b & 3) == 0 && b + 4 <= b1; b += 4) {  // band edges are multiples of 4 in every standard table
+            const float4 x = *reinterpret_cast<const float4*>(a + b);
+            e = fadd(fadd(fadd(fadd(e, x.x), x.y), x.z), x.w);
+          }
+          for (; b < b1; ++b) e = fadd(e, a[b]);
+          acc = fadd(acc, e);
+        }
+        esum[which][(is_short ? 16 * g : 0) + sfb] = __fdiv_rn(acc, float(sd.group_len[g]));
+      }
+    }
+    __syncthreads();
     if (tid < 128) {
       const int g = is_short ? tid >> 4 : 0;
       const int sfb = is_short ? tid & 15 : tid;
       const bool live = g < sd.num_groups && sfb >= sd.sfb_start && sfb < sd.sfb_stop &&
                         ((sfb - sd.sfb_start) % step) == 0 && (is_short || tid < 64);
       if (live) {
-        int w0 = 0;
-        for (int q = 0; q < g; ++q) w0 += sd.group_len[q];
+        const int slot = (is_short ? 16 * g : 0) + sfb;
         const int hi = min(sfb + step, int(sd.sfb_stop));
-        float s_acc = 0.0f, p_acc = 0.0f;
-        for (int q = 0; q < sd.group_len[g]; ++q) {
-          const float* c = coef + (w0 + q) * bins;
-          const float* sv = val + (w0 + q) * bins;
-          float e = 0.0f, pe = 0.0f;
-          for (int b = swb[sfb]; b < swb[hi]; ++b) {
-            const float cb = c[b];
-            e = fadd(e, fmul(cb, cb));
-            if (cb == 0.0f) pe = fadd(pe, fmul(sv[b], sv[b]));
-          }
-          s_acc = fadd(s_acc, e);
-          p_acc = fadd(p_acc, pe);
-        }
-        const float gl = float(sd.group_len[g]);
-        s_acc = __fdiv_rn(s_acc, gl);
-        p_acc = __fdiv_rn(p_acc, gl);
+        const float s_acc = esum[0][slot], p_acc = esum[1][slot];
         const int width = swb[hi] - swb[sfb];
-        const float lev = sd.levels[(is_short ? 16 * g : 0) + sfb];
+        const float lev = sd.levels[slot];
         const float mn = fsub(fmul(fmul(lev, lev), float(width)), s_acc);
         float gain = 0.0f;
         if (0.0f < mn && 0.0f < p_acc) {
           gain = float(__dsqrt_rn(__ddiv_rn(double(mn), double(p_acc))));
           gain = gain < 10.f ? gain : 10.f;
         }
-        const int slot = (is_short ? 16 * g : 0) + sfb;
         gn[slot] = gain;
         if (step == 2 && sfb + 1 < sd.sfb_stop) gn[slot + 1] = gain;  // both bands of a low-resolution pair
       }
@@ -284,11 +327,7 @@ __global__ void __launch_bounds__(kThreads)
     __syncthreads();
 
     // ---- fill the zero bins (:1321) -------------------------------------------------------------------
-    int sfb_of = sd.sfb_start;  // band of this thread's first bin: linear search once, bins are consecutive
-    {
-      const int i = 4 * tid, w = is_short ? i >> 7 : 0, b = i - w * bins;
-      while (sfb_of + 1 < n_sfb && swb[sfb_of + 1] <= b) ++sfb_of;
-    }
+    const uint8_t* b2s = is_short ? b2s_short : b2s_long;
     // group of each window (short blocks)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -297,7 +336,7 @@ __global__ void __launch_bounds__(kThreads)
       const int b = i - w * bins;
       float spec = 0.0f, mask = 1.0f;
       if (b >= bgn && b < end) {
-        while (sfb_of + 1 < n_sfb && swb[sfb_of + 1] <= b) ++sfb_of;
+        const int sfb_of = __ldg(b2s + b);
         int g = 0;
         if (is_short) {
           int acc = sd.group_len[0];
@@ -430,7 +469,8 @@ __global__ void __launch_bounds__(kThreads)
                       const mpeghb200_igf_side* __restrict__ sides, const uint8_t* __restrict__ masks,
                       float* __restrict__ tnf_state, uint32_t* __restrict__ seed_out,
                       const int16_t* __restrict__ sfb_long, int n_long, const int16_t* __restrict__ sfb_short,
-                      int n_short, const IgfRom R) {
+                      int n_short, const uint8_t* __restrict__ b2s_long, const uint8_t* __restrict__ b2s_short,
+                      const IgfRom R) {
   extern __shared__ __align__(16) float dsm[];
   float* coef = dsm;                   // [2][1024]
   float* tiles = coef + 2 * kFrame;    // [2][4][1024]
@@ -442,6 +482,7 @@ __global__ void __launch_bounds__(kThreads)
   __shared__ float gn[2][128];
   __shared__ int16_t swb[72];
   __shared__ Grid G;
+  __shared__ int toff2[2][4];
   __shared__ uint32_t warp_cnt[2][kThreads / 32];
   const int tid = threadIdx.x;
   {
@@ -472,31 +513,10 @@ __global__ void __launch_bounds__(kThreads)
     for (int t = 0; t < 4; ++t) reinterpret_cast<float4*>(tiles + ch * 4 * kFrame)[t * 256 + tid] = tg[t * 256 + tid];
   }
   __syncthreads();
-  if (tid == 0) {  // tile widths of the grid (ia_core_coder_igf_get_num_tiles :760)
-    const int s0 = sl.sfb_start, s1 = sl.sfb_stop;
-    const int bgn = swb[s0], end = swb[s1];
-    int range = end - bgn < 8 ? 8 : end - bgn, mem = s0, sbs = bgn, n = 0;
-    int tile[4] = {range >> 2, range >> 2, range >> 2, range >> 2};
-    if (bgn > sl.igf_min && bgn < end) {
-      for (int i = 0; i < 4; ++i) {
-        const int lim = min(sbs + tile[i], end);
-        int j = 1;
-        while (lim > swb[j]) ++j;
-        if (!sl.use_high_res) {
-          if (i == 3)
-            j = s1;
-          else if ((((j - s0) & 1) == 1) && ((j - mem) > 1))
-            --j;
-          mem = j;
-        }
-        tile[i] = max(2, min(swb[j] - sbs, end - sbs));
-        ++n;
-        sbs += tile[i];
-        if (sbs == end) break;
-      }
-    }
-    for (int i = 0; i < 4; ++i) G.tile[i] = i < n ? tile[i] : 0;
-    G.n_tiles = n, G.bgn = bgn, G.end = end;
+  if (tid == 0) {
+    compute_grid(G, sl, is_short ? sfb_short : sfb_long, is_short ? b2s_short : b2s_long);
+    for (int ch = 0; ch < 2; ++ch)
+      for (int i = 0; i < 4; ++i) toff2[ch][i] = source_offset(G.tile[i], G.tstart[i], G.bgn, sd2[ch].tile_num[i]);
   }
   __syncthreads();
   const int bgn = G.bgn, end = G.end;
@@ -538,11 +558,7 @@ __global__ void __launch_bounds__(kThreads)
 
   // ---- source values of both channels, noise draws numbered in bin order, mid/side on the masked bands -------
   const int step = (sl.use_high_res || is_short) ? 1 : 2;
-  int sfb_of = sl.sfb_start;
-  {
-    const int i = 4 * tid, w = is_short ? i >> 7 : 0, b = i - w * bins;
-    while (sfb_of + 1 < n_sfb && swb[sfb_of + 1] <= b) ++sfb_of;
-  }
+  const uint8_t* b2s = is_short ? b2s_short : b2s_long;
   int sfb4[4], grp4 = 0;
   {
     const int w = is_short ? (4 * tid) >> 7 : 0;
@@ -561,18 +577,18 @@ __global__ void __launch_bounds__(kThreads)
     const int w = is_short ? i >> 7 : 0;
     const int b = i - w * bins;
     in_range[k] = b >= bgn && b < end;
-    sfb4[k] = sfb_of;
+    sfb4[k] = 0;
     v[0][k] = v[1][k] = 0.0f;
     noise[0][k] = noise[1][k] = false;
     if (in_range[k]) {
-      while (sfb_of + 1 < n_sfb && swb[sfb_of + 1] <= b) ++sfb_of;
       // the reference walks the range in steps of one or two bands and indexes mask, level and gain by the first
       // band of the step
+      const int sfb_of = __ldg(b2s + b);
       sfb4[k] = sl.sfb_start + ((sfb_of - sl.sfb_start) / step) * step;
       const int ix = tile_of(b, G);
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
-        const int sb = source_bin(sl.igf_min, b, G, sd2[ch].tile_num);
+        const int sb = source_bin(sl.igf_min, b, ix, G, toff2[ch]);
         v[ch][k] = tiles[(ch * 4 + ix) * kFrame + w * bins + sb];
         noise[ch][k] = noise_ok && sd2[ch].whitening_level[ix] == 2;
         my_noise[ch] += noise[ch][k];
@@ -738,7 +754,7 @@ mpeghb200_status mpeghb200_igf_dev(mpeghb200_ctx* ctx, const mpeghb200_bands* ba
   static const IgfRom R = make_rom();
   igf_kernel<<<n_units, kThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
       d_coef, d_tiles, d_side, d_tnf_state, d_seed_out, bands->d_sfb_long, bands->n_long, bands->d_sfb_short,
-      bands->n_short, 0, R);
+      bands->n_short, bands->d_bin2sfb_long, bands->d_bin2sfb_short, 0, R);
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   return MPEGHB200_OK;
@@ -755,7 +771,7 @@ mpeghb200_status mpeghb200_igf_tnf_dev(mpeghb200_ctx* ctx, const mpeghb200_bands
   static const IgfRom R = make_rom();
   igf_kernel<<<n_units, kThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
       d_coef, nullptr, d_side, d_tnf_state, nullptr, bands->d_sfb_long, bands->n_long, bands->d_sfb_short,
-      bands->n_short, 1, R);
+      bands->n_short, bands->d_bin2sfb_long, bands->d_bin2sfb_short, 1, R);
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   return MPEGHB200_OK;
@@ -779,7 +795,7 @@ mpeghb200_status mpeghb200_igf_stereo_dev(mpeghb200_ctx* ctx, const mpeghb200_ba
   }
   igf_stereo_kernel<<<n_pairs, kThreads, smem, static_cast<cudaStream_t>(cuda_stream)>>>(
       d_coef, d_tiles, d_side, d_mask, d_tnf_state, d_seed_out, bands->d_sfb_long, bands->n_long, bands->d_sfb_short,
-      bands->n_short, R);
+      bands->n_short, bands->d_bin2sfb_long, bands->d_bin2sfb_short, R);
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   return MPEGHB200_OK;
