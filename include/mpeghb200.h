@@ -474,6 +474,24 @@ mpeghb200_status mpeghb200_channel_mask_dev(mpeghb200_ctx *ctx, float *d_audio, 
 mpeghb200_status mpeghb200_gain_apply_dev(mpeghb200_ctx *ctx, float *d_audio, const float *d_gains,
                                           const int32_t *d_seq_of_ch, int n_channels, void *cuda_stream);
 
+/* ---- LTPF: long-term post-filter of FD channels, in place on the time signal after FD synthesis -------------
+ * Replaces ia_core_coder_usac_ltpf_process (decoder/ia_core_coder_ltpf.c:395), called per FD channel right after
+ * ia_core_coder_fd_frm_dec (decoder/ia_core_coder_ext_ch_ele.c:1977); SURVEY.md section 8f rank 3.  The side record
+ * carries the frame's ltpf_data fields as parsed (decoder/ia_core_coder_acelp_bitparse.c:554-571); a frame without
+ * LTPF data (data_present == 0) still has to be passed while the channel's previous frame had it (fade-out) and
+ * costs a copy otherwise.  d_state [channel][mpeghb200_ltpf_state_floats(sample_rate)], zero-initialised, indexed
+ * by side.unit: previous parameters, the last 6 inputs and the last pitch_max + 4 outputs. */
+typedef struct mpeghb200_ltpf_side {
+  int32_t unit;           /* channel-frame index into d_audio [n_units][1024] and d_state */
+  uint16_t pitch_lag_idx; /* 9 bits */
+  uint8_t data_present;
+  uint8_t gain_idx;       /* 2 bits */
+} mpeghb200_ltpf_side;
+size_t mpeghb200_ltpf_state_floats(int sample_rate);
+mpeghb200_status mpeghb200_ltpf_dev(mpeghb200_ctx *ctx, int sample_rate, float *d_audio,
+                                    const mpeghb200_ltpf_side *d_side, float *d_state, int n_units,
+                                    void *cuda_stream);
+
 /* ---- output resampler ------------------------------------------------------------------------------------
  * Replaces impeghd_resample (decoder/impeghd_resampler.c:93): fac_up/fac_down = 2/1, 3/1 or 3/2
  * (impeghd_resampler_get_sampling_ratio, decoder/impeghd_api.c:132).  filter_up = impeghd_resampler_filter

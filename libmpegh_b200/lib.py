@@ -78,6 +78,7 @@ class HoaSpatialDesc(ctypes.Structure):
                                                "fade_windows", "dyn_win_pow_table", "dyn_win_func", "pow2_table")]
 
 
+LTPF_SIDE_DTYPE = np.dtype([("unit", "<i4"), ("pitch_lag_idx", "<u2"), ("data_present", "u1"), ("gain_idx", "u1")])
 TNS_FILTER_DTYPE = np.dtype([("unit", np.int32), ("start", np.int32), ("size", np.int32), ("inc", np.int32),
                              ("order", np.int32), ("pad", np.int32, 3), ("lpc", np.float32, 16)])
 OBJ_SIDE_DTYPE = np.dtype([("vec_c", np.float32, 3), ("gain", np.float32), ("spread_w", np.float32),
@@ -222,6 +223,10 @@ class Lib:
         c.mpeghb200_bus_add_dev.restype = i32
         c.mpeghb200_channel_mask_dev.argtypes = [vp, vp, vp, ctypes.c_int, vp]
         c.mpeghb200_channel_mask_dev.restype = i32
+        c.mpeghb200_ltpf_state_floats.argtypes = [ctypes.c_int]
+        c.mpeghb200_ltpf_state_floats.restype = sz
+        c.mpeghb200_ltpf_dev.argtypes = [vp, ctypes.c_int, vp, vp, vp, ctypes.c_int, vp]
+        c.mpeghb200_ltpf_dev.restype = i32
         c.mpeghb200_gain_apply_dev.argtypes = [vp, vp, vp, vp, ctypes.c_int, vp]
         c.mpeghb200_gain_apply_dev.restype = i32
         c.mpeghb200_igf_stereo_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
@@ -359,6 +364,12 @@ class Lib:
 
     def gain_apply_dev(self, d_audio, d_gains, d_seq_of_ch, n_channels, stream=0):
         self.check(self.c.mpeghb200_gain_apply_dev(self.ctx, d_audio, d_gains, d_seq_of_ch, n_channels, stream))
+
+    def ltpf_state_floats(self, sample_rate=48000):
+        return int(self.c.mpeghb200_ltpf_state_floats(sample_rate))
+
+    def ltpf_dev(self, sample_rate, d_audio, d_side, d_state, n_units, stream=0):
+        self.check(self.c.mpeghb200_ltpf_dev(self.ctx, sample_rate, d_audio, d_side, d_state, n_units, stream))
 
     def igf_whitening_rom(self):
         t = np.zeros((2, 64), np.float32)

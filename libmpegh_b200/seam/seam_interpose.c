@@ -7,6 +7,7 @@
  *
  *   ia_core_coder_fd_frm_dec             decoder/ia_core_coder_imdct.c:832      -> mpeghb200_fd_synth_dev
  *   impeghd_tns_decode_coeff_ar_filter   decoder/ia_core_coder_tns.c:83         -> mpeghb200_tns_dev
+ *   ia_core_coder_usac_ltpf_process      decoder/ia_core_coder_ltpf.c:395       -> mpeghb200_ltpf_dev
  *   impeghd_peak_limiter_init/_process   decoder/impeghd_peak_limiter.c:146,190 -> mpeghb200_limiter_dev
  *
  * Every call here handles ONE handle's frame, so it moves a few KB per launch: this object exists to prove that
@@ -78,7 +79,9 @@ static struct
     int fresh;
   } lim[MAX_LIM];
   float *h_planar;
-  unsigned long n_fd_gpu, n_fd_host, n_tns, n_lim;
+  float *d_ltpf_state;
+  mpeghb200_ltpf_side *d_ltpf_side;
+  unsigned long n_fd_gpu, n_fd_host, n_tns, n_lim, n_ltpf;
 } g;
 
 static void seam_die(const char *what, mpeghb200_status st)
@@ -99,8 +102,8 @@ static void seam_stats(void)
   if (getenv("MPEGHB200_SEAM_STATS"))
     fprintf(stderr,
             "mpeghb200 seam: fd_frm_dec gpu=%lu host(LPD transition)=%lu tns_filters gpu=%lu limiter_frames gpu=%lu "
-            "kernel_launches=%llu\n",
-            g.n_fd_gpu, g.n_fd_host, g.n_tns, g.n_lim,
+            "ltpf_frames gpu=%lu kernel_launches=%llu\n",
+            g.n_fd_gpu, g.n_fd_host, g.n_tns, g.n_lim, g.n_ltpf,
             g.ctx ? (unsigned long long)mpeghb200_launch_count(g.ctx) : 0ull);
 }
 
@@ -118,6 +121,8 @@ static void seam_init(void)
   CK(mpeghb200_dev_alloc(g.ctx, 2 * sizeof(int32_t), (void **)&g.d_chain));
   CK(mpeghb200_dev_alloc(g.ctx, MAX_NUM_CHANNELS * FRAME * sizeof(float), (void **)&g.d_lim_in));
   CK(mpeghb200_dev_alloc(g.ctx, MAX_NUM_CHANNELS * FRAME * sizeof(float), (void **)&g.d_lim_out));
+  CK(mpeghb200_dev_alloc(g.ctx, 4096 * sizeof(float), (void **)&g.d_ltpf_state));
+  CK(mpeghb200_dev_alloc(g.ctx, sizeof(mpeghb200_ltpf_side), (void **)&g.d_ltpf_side));
   g.h_planar = (float *)malloc(MAX_NUM_CHANNELS * FRAME * sizeof(float));
   atexit(seam_stats);
 }
@@ -172,6 +177,51 @@ VOID impeghd_tns_decode_coeff_ar_filter(WORD32 order, WORD32 coef_res, WORD16 *c
   CK(mpeghb200_tns_dev(g.ctx, g.d_coef, g.d_filt, g.d_chain, 1, NULL));
   CK(mpeghb200_d2h(g.ctx, ptr_spec, g.d_coef, (size_t)size * sizeof(float)));
   g.n_tns++;
+}
+
+/* ---- LTPF: the filter state stays in the reference handle (the LPD path shares it), round trip per call ---- */
+VOID ia_core_coder_usac_ltpf_process(ia_ltpf_data_str *ptr_ltpf_data, FLOAT32 *time_sample_vector)
+{
+  typedef VOID (*fn_t)(ia_ltpf_data_str *, FLOAT32 *);
+  const int hist = ptr_ltpf_data->pitch_max + LTPF_NUM_FILT_COEF1 / 2;
+  float st[4096];
+  mpeghb200_ltpf_side sd;
+  int32_t iv;
+  size_t n_state;
+  if (ptr_ltpf_data->frame_len != FRAME || ptr_ltpf_data->pitch_min != 128)
+  { /* not a 48 kHz / 1024-sample FD channel: the LPD path's own use of the filter stays on the host */
+    static fn_t real;
+    if (!real)
+      real = (fn_t)dlsym(RTLD_NEXT, "ia_core_coder_usac_ltpf_process");
+    real(ptr_ltpf_data, time_sample_vector);
+    return;
+  }
+  seam_init();
+  n_state = mpeghb200_ltpf_state_floats(48000);
+  memset(st, 0, sizeof(st));
+  iv = ptr_ltpf_data->prev_pitch, memcpy(&st[0], &iv, 4);
+  iv = ptr_ltpf_data->prev_pitch_fr, memcpy(&st[1], &iv, 4);
+  iv = ptr_ltpf_data->prev_gain_idx, memcpy(&st[2], &iv, 4);
+  st[3] = ptr_ltpf_data->prev_gain;
+  memcpy(&st[4], ptr_ltpf_data->prev_in_buf, 6 * sizeof(float));
+  memcpy(&st[16], ptr_ltpf_data->prev_out_buf, hist * sizeof(float));
+  sd.unit = 0;
+  sd.data_present = (uint8_t)ptr_ltpf_data->data_present;
+  sd.pitch_lag_idx = (uint16_t)ptr_ltpf_data->pitch_lag_idx;
+  sd.gain_idx = (uint8_t)ptr_ltpf_data->gain_idx;
+  CK(mpeghb200_h2d(g.ctx, g.d_ltpf_state, st, n_state * sizeof(float)));
+  CK(mpeghb200_h2d(g.ctx, g.d_ltpf_side, &sd, sizeof(sd)));
+  CK(mpeghb200_h2d(g.ctx, g.d_out, time_sample_vector, FRAME * sizeof(float)));
+  CK(mpeghb200_ltpf_dev(g.ctx, 48000, g.d_out, g.d_ltpf_side, g.d_ltpf_state, 1, NULL));
+  CK(mpeghb200_d2h(g.ctx, time_sample_vector, g.d_out, FRAME * sizeof(float)));
+  CK(mpeghb200_d2h(g.ctx, st, g.d_ltpf_state, n_state * sizeof(float)));
+  memcpy(&iv, &st[0], 4), ptr_ltpf_data->prev_pitch = iv;
+  memcpy(&iv, &st[1], 4), ptr_ltpf_data->prev_pitch_fr = iv;
+  memcpy(&iv, &st[2], 4), ptr_ltpf_data->prev_gain_idx = iv;
+  ptr_ltpf_data->prev_gain = st[3];
+  memcpy(ptr_ltpf_data->prev_in_buf, &st[4], 6 * sizeof(float));
+  memcpy(ptr_ltpf_data->prev_out_buf, &st[16], hist * sizeof(float));
+  g.n_ltpf++;
 }
 
 /* ---- peak limiter ---------------------------------------------------------------------------------- */

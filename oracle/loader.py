@@ -107,6 +107,9 @@ def load_oracle():
     lib.oracle_igf_stereo.argtypes = [ctypes.c_char_p, ctypes.c_char_p, _u8p, _i16p, ctypes.c_int, _f32p, _f32p, _f32p,
                                       _f32p, _f32p, _f32p, np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")]
     lib.oracle_igf_tnf.argtypes = [ctypes.c_char_p, _i16p, ctypes.c_int, _f32p, _f32p]
+    lib.oracle_ltpf_cfg_init.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.oracle_ltpf_state_init.argtypes = [ctypes.c_void_p]
+    lib.oracle_ltpf_process.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p]
     lib.oracle_igf_tiles.argtypes = [ctypes.c_int] * 4 + [_i16p, _i32p]
     lib.oracle_igf_tiles.restype = ctypes.c_int
     lib.oracle_igf_whitening_table.argtypes = [_f32p]
@@ -232,6 +235,11 @@ def load_ref():
                                     _f32p, _f32p, _f32p, _f32p, _f32p]
     lib.ref_cpe_process.restype = ctypes.c_int
     lib.ref_mdst_rom.argtypes = [_f32p, _f32p]
+    lib.ref_ltpf_create.restype = ctypes.c_void_p
+    lib.ref_ltpf_create.argtypes = [ctypes.c_int]
+    lib.ref_ltpf_destroy.argtypes = [ctypes.c_void_p]
+    lib.ref_ltpf_cfg.argtypes = [ctypes.c_void_p, _i32p]
+    lib.ref_ltpf_process.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p]
     lib.ref_igf_create.restype = ctypes.c_void_p
     lib.ref_igf_create.argtypes = [ctypes.c_int] * 7
     lib.ref_igf_destroy.argtypes = [ctypes.c_void_p]
@@ -568,3 +576,20 @@ class OracleResampler:
         out = np.zeros(1024 * self.up // self.down, np.float32)
         load_oracle().oracle_rs_process(self.state, self.up, self.down, self.f_up, self.f_down, x, out)
         return out
+
+
+# ---- LTPF -----------------------------------------------------------------------------------------------
+class OracleLtpf:
+    """One channel's LTPF (oracle/oracle_ltpf.c) with carried state."""
+
+    def __init__(self, sample_rate=48000):
+        self.lib = load_oracle()
+        self.cfg = (ctypes.c_int * 5)()
+        self.lib.oracle_ltpf_cfg_init(self.cfg, sample_rate)
+        self.state = ctypes.create_string_buffer(4 * (4 + 6 + 1600))
+        self.lib.oracle_ltpf_state_init(self.state)
+
+    def process(self, data_present, pitch_lag_idx, gain_idx, x):
+        y = np.ascontiguousarray(x, np.float32).copy()
+        self.lib.oracle_ltpf_process(self.cfg, self.state, int(data_present), int(pitch_lag_idx), int(gain_idx), y)
+        return y

@@ -396,3 +396,36 @@ void ref_igf_stereo_process(void *p, const oracle_igf_side *sl, const oracle_igf
   memcpy(coef_r, u->coef[1], 1024 * sizeof(float));
   seeds_out[0] = u->seed_value[0], seeds_out[1] = u->seed_value[1];
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * LTPF: ia_core_coder_ltpf_init (decoder/ia_core_coder_ltpf.c:356) + ia_core_coder_usac_ltpf_process (:395)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct
+{
+  ia_ltpf_data_str d;
+  FLOAT32 scratch[16384];
+} ref_ltpf_handle;
+
+void *ref_ltpf_create(int sample_rate)
+{
+  ref_ltpf_handle *h = (ref_ltpf_handle *)calloc(1, sizeof(ref_ltpf_handle));
+  if (h)
+    ia_core_coder_ltpf_init(&h->d, sample_rate, 1024, h->scratch);
+  return h;
+}
+void ref_ltpf_destroy(void *p) { free(p); }
+/* out5: pitch_min, pitch_fr1, pitch_fr2, pitch_res, pitch_max */
+void ref_ltpf_cfg(void *p, int *out5)
+{
+  ref_ltpf_handle *h = (ref_ltpf_handle *)p;
+  out5[0] = h->d.pitch_min, out5[1] = h->d.pitch_fr1, out5[2] = h->d.pitch_fr2, out5[3] = h->d.pitch_res;
+  out5[4] = h->d.pitch_max;
+}
+void ref_ltpf_process(void *p, int data_present, int pitch_lag_idx, int gain_idx, float *x)
+{
+  ref_ltpf_handle *h = (ref_ltpf_handle *)p;
+  h->d.data_present = data_present;
+  h->d.pitch_lag_idx = pitch_lag_idx;
+  h->d.gain_idx = gain_idx;
+  ia_core_coder_usac_ltpf_process(&h->d, x);
+}

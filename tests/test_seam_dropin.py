@@ -1,6 +1,6 @@
 """Library-level drop-in (BASELINE.json configs[0]): the reference testbench decodes the smoke_test_suite streams
 through the reference's own ia_mpegh_dec_* API while libmpeghb200_seam.so (libmpegh_b200/seam/seam_interpose.c)
-takes over FD synthesis, TNS filtering and the peak limiter on the GPU.  The WAV files must be byte-identical to
+takes over FD synthesis, TNS filtering, the LTPF pass and the peak limiter on the GPU.  The WAV files must be byte-identical to
 what the unmodified reference writes (tests/golden/smoke_wav.json, made by tests/golden/make_smoke_golden.py;
 the cicp1 entry equals the WAV the reference repository ships).
 """
@@ -79,10 +79,10 @@ def test_seam_dropin_bit_exact(tmp_path, name, stream, extra):
     r = _decode(TB_DYN, stream, extra, wav, preload=SEAM)
     assert r.returncode == 0, r.stderr[-600:]
     m = re.search(r"fd_frm_dec gpu=(\d+) host\(LPD transition\)=(\d+) tns_filters gpu=(\d+) "
-                  r"limiter_frames gpu=(\d+) kernel_launches=(\d+)", r.stderr)
+                  r"limiter_frames gpu=(\d+) ltpf_frames gpu=(\d+) kernel_launches=(\d+)", r.stderr)
     assert m, r.stderr[-600:]
-    fd_gpu, fd_host, _tns, lim, launches = map(int, m.groups())
-    assert fd_gpu > 0 and fd_host == 0 and lim > 0 and launches >= fd_gpu + lim
+    fd_gpu, fd_host, _tns, lim, ltpf, launches = map(int, m.groups())
+    assert fd_gpu > 0 and fd_host == 0 and lim > 0 and ltpf == fd_gpu and launches >= 2 * fd_gpu + lim
     assert os.path.getsize(wav) == GOLD[name]["bytes"]
     assert _sha(wav) == GOLD[name]["sha256"], f"{name}: PCM differs from the reference decoder"
     # and against the unmodified static testbench run on this very box

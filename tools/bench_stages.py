@@ -290,6 +290,24 @@ def spectral_stage():
            U * (2 * 4096 + 4 * 4096 + 548 + 8192), U * 1024, "channel_samples")
     lib.bands_destroy(bands)
 
+    # LTPF at the config-2 shape, every channel filtering with a new pitch each frame (ZIR transition, the costly mode)
+    from libmpegh_b200.lib import LTPF_SIDE_DTYPE
+    audio = torch.randn(U, 1024, device="cuda") * 3000
+    lst = torch.zeros(U, lib.ltpf_state_floats(48000), device="cuda")
+    lsd = []
+    for k in range(2):
+        sd = np.zeros(U, LTPF_SIDE_DTYPE)
+        sd["unit"], sd["data_present"] = np.arange(U), 1
+        sd["pitch_lag_idx"], sd["gain_idx"] = rng.integers(0, 512, U), rng.integers(0, 4, U)
+        lsd.append(torch.from_numpy(sd.view(np.uint8).reshape(U, -1).copy()).cuda())
+    ms = timeit(lambda i: lib.ltpf_dev(48000, audio.data_ptr(), lsd[i % 2].data_ptr(), lst.data_ptr(), U, st))
+    report("ltpf, new pitch every frame (ZIR transition), 6144 channel-frames", ms,
+           U * (2 * 4096 + 2 * 4 * lib.ltpf_state_floats(48000)), U * 1024, "channel_samples")
+    same = lsd[0]
+    ms = timeit(lambda i: lib.ltpf_dev(48000, audio.data_ptr(), same.data_ptr(), lst.data_ptr(), U, st))
+    report("ltpf, steady pitch, 6144 channel-frames", ms, U * (2 * 4096 + 2 * 4 * lib.ltpf_state_floats(48000)),
+           U * 1024, "channel_samples")
+
 
 STAGES = {"binaural": binaural_stage, "hoa": hoa_chain_stage, "fc": fc_stage, "tns_rs": tns_rs_stage,
           "spectral": spectral_stage,
