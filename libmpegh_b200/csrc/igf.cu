@@ -66,7 +66,9 @@ __device__ __forceinline__ int source_bin(int igf_min, int tb, int ix, const Gri
   const int src = G.bgn - igf_min;
   int sb = tb;
   if (src > 0) {
-    if (ix < G.n_tiles && tb >= G.tstart[ix]) sb = tb - toff[ix];
+    // select instead of indexing: G and toff stay in registers (tb >= bgn == tstart[0] for every caller's bin)
+    const int off = ix == 0 ? toff[0] : ix == 1 ? toff[1] : ix == 2 ? toff[2] : toff[3];
+    if (ix < G.n_tiles && tb >= G.bgn) sb = tb - off;
     if (sb < igf_min) sb = igf_min + tb % src;
   }
   return sb;
@@ -115,7 +117,7 @@ __device__ void compute_grid(Grid& G, const mpeghb200_igf_side& sd, const int16_
   G.n_tiles = n, G.bgn = bgn, G.end = end;
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 6)
     igf_kernel(float* __restrict__ coef_g, const float* __restrict__ tiles_g,
                const mpeghb200_igf_side* __restrict__ sides, float* __restrict__ tnf_state,
                uint32_t* __restrict__ seed_out, const int16_t* __restrict__ sfb_long, int n_long,
@@ -220,6 +222,10 @@ __global__ void __launch_bounds__(kThreads)
     uint32_t my_noise = 0;
     bool noise[4];
     float v[4];
+    const Grid Gr = G;  // registers
+    int toff_r[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) toff_r[q] = toff[q];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int i = 4 * tid + k;
@@ -228,8 +234,8 @@ __global__ void __launch_bounds__(kThreads)
       noise[k] = false;
       v[k] = 0.0f;
       if (b >= bgn && b < end) {
-        const int ix = tile_of(b, G);
-        const int sb = source_bin(sd.igf_min, b, ix, G, toff);
+        const int ix = tile_of(b, Gr);
+        const int sb = source_bin(sd.igf_min, b, ix, Gr, toff_r);
         v[k] = tiles[ix * kFrame + w * bins + sb];
         noise[k] = noise_ok && coef[i] == 0.0f && sd.whitening_level[ix] == 2;
         my_noise += noise[k];
@@ -435,14 +441,19 @@ __global__ void __launch_bounds__(kThreads)
     }
     __syncthreads();
     // FIR over the unfiltered values; each bin adds its taps in the reference's order (i = 1 .. order - 1)
-    float y[4];
+    float y[4], pr[8];
+#pragma unroll
+    for (int t = 1; t < 8; ++t) pr[t] = pred[t];
+    const int n_taps = tnf_order;  // 0 or 8
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int i = 4 * tid + k;
       y[k] = tnf[i];
-      if (i >= bgn && i < end) {
+      if (i >= bgn && i < end && n_taps) {
         const int j = i - bgn;
-        for (int t = 1; t < tnf_order && j >= t; ++t) y[k] = fadd(y[k], fmul(pred[t], tnf[i - t]));
+#pragma unroll
+        for (int t = 1; t < 8; ++t)
+          if (j >= t) y[k] = fadd(y[k], fmul(pr[t], tnf[i - t]));
       }
     }
     __syncthreads();

@@ -309,7 +309,85 @@ def spectral_stage():
            U * 1024, "channel_samples")
 
 
+def fd_path_stage():
+    """Subsystem (1) of BASELINE.json north_star as one chain at the config-2 shape (256 streams x 24 ch): IGF on every
+    channel, TNS on half of them (realistic orders <= 8 over the upper half of the spectrum), joint stereo on every
+    pair (complex prediction with previous-frame downmix), FD synthesis, LTPF with a steady pitch."""
+    import fd_cases
+    import igf_cases
+    import stereo_cases
+    import tns_cases
+    from libmpegh_b200.lib import LTPF_SIDE_DTYPE, TNS_FILTER_DTYPE
+    U, P = 6144, 3072
+    rng = np.random.default_rng(21)
+    bands = lib.bands_create(stereo_cases.SFB_LONG, stereo_cases.SFB_SHORT)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "igf_golden.npz"))
+    cfg, grid = igf_cases.CONFIGS[1], g["c1_grid"]
+    base = [igf_cases.random_frame(rng, cfg, grid, win_type=0, all_zero_prob=0.0) for _ in range(64)]
+    isd = np.zeros(U, igf_cases.IGF_SIDE)
+    for u in range(U):
+        isd[u] = base[u % 64][0]
+        isd[u]["unit"] = u
+    d_isd = torch.from_numpy(isd.view(np.uint8).reshape(U, -1).copy()).cuda()
+    coef0 = torch.from_numpy(np.stack([base[u % 64][1] for u in range(U)])).cuda()
+    coef = coef0.clone()
+    d_tiles = torch.from_numpy(np.stack([base[u % 64][2] for u in range(U)])).cuda()
+    d_tnf = torch.zeros(U, 2048, device="cuda")
+    d_seed = torch.zeros(U, dtype=torch.int32, device="cuda")
+    # TNS: one or two filters of order 4..8 over the bands above 4 kHz on half of the channels
+    chains = []
+    for u in range(0, U, 2):
+        n_filt, filt = np.zeros(8, np.int32), np.zeros((8, 3, 20), np.int32)
+        n_filt[0] = int(rng.integers(1, 3))
+        top = 49
+        for f in range(n_filt[0]):
+            order = int(rng.integers(4, 9))
+            length = int(rng.integers(6, 12))
+            filt[0, f, :5] = (order, top - length, top, int(rng.integers(2)), 4)
+            filt[0, f, 5:5 + order] = rng.integers(-8, 8, order)
+            top -= length
+        chains += tns_cases.resolve_filters(lib, u, 1, n_filt, filt, 49, lib.tns_lpc_from_coef)
+    recs = np.array([r for c in chains for r in c], TNS_FILTER_DTYPE)
+    first = np.cumsum([0] + [len(c) for c in chains]).astype(np.int32)
+    d_f = torch.from_numpy(recs.view(np.uint8).reshape(len(recs), -1).copy()).cuda()
+    d_first = torch.from_numpy(first).cuda()
+    sds = np.zeros(P, stereo_cases.STEREO_SIDE)
+    for p in range(P):
+        sd, _ = stereo_cases.random_frame(rng, 0, int(rng.integers(2)), int(rng.integers(2)), tool=3)
+        sd["complex_coef"], sd["use_prev_frame"], sd["prev_dmx"] = 1, 1, 1
+        sd["left"], sd["right"], sd["slot"] = 2 * p, 2 * p + 1, p
+        sds[p] = sd
+    d_pairs = torch.from_numpy(sds.view(np.uint8).reshape(P, -1).copy()).cuda()
+    pstate = torch.zeros(P, lib.stereo_state_floats(), device="cuda")
+    side = torch.from_numpy(fd_cases.pack_side(np.stack([np.zeros(U, np.int32), rng.integers(0, 2, U).astype(np.int32),
+                                                         rng.integers(0, 2, U).astype(np.int32), np.zeros(U, np.int32),
+                                                         np.zeros(U, np.int32)], -1)).astype(np.int32)).cuda()
+    ovl = torch.zeros(U, 1024, device="cuda")
+    pcm = torch.empty(U, 1024, device="cuda")
+    lsd = np.zeros(U, LTPF_SIDE_DTYPE)
+    lsd["unit"], lsd["data_present"] = np.arange(U), 1
+    lsd["pitch_lag_idx"], lsd["gain_idx"] = rng.integers(0, 512, U), rng.integers(0, 4, U)
+    d_lsd = torch.from_numpy(lsd.view(np.uint8).reshape(U, -1).copy()).cuda()
+    lst = torch.zeros(U, lib.ltpf_state_floats(48000), device="cuda")
+
+    def step(i):
+        coef.copy_(coef0)  # the frame's dequantised spectra "arrive" (stands in for the upload)
+        lib.igf_dev(bands, coef.data_ptr(), d_tiles.data_ptr(), d_isd.data_ptr(), d_tnf.data_ptr(), d_seed.data_ptr(), U, st)
+        lib.tns_dev(coef.data_ptr(), d_f.data_ptr(), d_first.data_ptr(), len(chains), st)
+        lib.stereo_dev(bands, coef.data_ptr(), d_pairs.data_ptr(), pstate.data_ptr(), P, st)
+        lib.stereo_save_dev(bands, coef.data_ptr(), d_pairs.data_ptr(), pstate.data_ptr(), P, st)
+        lib.fd_synth_dev(coef.data_ptr(), side.data_ptr(), ovl.data_ptr(), pcm.data_ptr(), U, st)
+        lib.ltpf_dev(48000, pcm.data_ptr(), d_lsd.data_ptr(), lst.data_ptr(), U, st)
+    ms = timeit(step)
+    per_unit = 4096 + 4 * 4096 + 4096 + 2 * 4096 + 2 * 4 * lib.ltpf_state_floats(48000)  # coef, tiles, pcm, overlap r/w, ltpf state
+    report("FD path chain: IGF + TNS + joint stereo + FD synthesis + LTPF, 256 streams x 24 ch (7 launches)", ms,
+           U * per_unit, U * 1024, "channel_samples", {"audio_s_per_wall_s": 256 * 1024 / 48000 / (ms * 1e-3),
+                                                       "tns_chains": len(chains)})
+    lib.bands_destroy(bands)
+
+
 STAGES = {"binaural": binaural_stage, "hoa": hoa_chain_stage, "fc": fc_stage, "tns_rs": tns_rs_stage,
+          "fd_path": fd_path_stage,
           "spectral": spectral_stage,
           "obj": obj_stage, "hoa_render": hoa_render_stage}
 if ONLY in STAGES:
@@ -323,5 +401,6 @@ hoa_chain_stage()
 fc_stage()
 tns_rs_stage()
 spectral_stage()
+fd_path_stage()
 binaural_stage()
 lib.close()
