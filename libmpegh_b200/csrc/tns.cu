@@ -5,9 +5,11 @@
 // coefficient decoding (double-precision sin, mpeghb200_tns_lpc_from_coef below does it the reference's way)
 // and the band -> bin resolution with its clamps (:262-284).  What is left is a strictly serial recurrence per
 // filter (y[n] = x[n] - sum lpc[j] y[n-1-j], every product and difference rounded separately), up to 3
-// filters per window applied in order.  One thread runs one chain (= the filters of one window of one channel);
-// chains are independent, so a launch keeps every SM busy with chains of different channels.  The recurrence
-// latency (order dependent subtractions per bin), not HBM, bounds this stage; it touches only the filtered bins.
+// filters per window applied in order.  One WARP runs one chain (= the filters of one window of one channel): the
+// warp moves the range through shared memory, one lane does the recurrence (see tns_kernel).  The recurrence
+// latency (`order` dependent subtractions per bin), not HBM, bounds this stage; it touches only the filtered bins.
+// Worst case (3 filters of order 15 over all 1024 bins) = 3072 x 15 dependent subtractions = 94 us at 4 cycles
+// each: the stress stage bench sits at that floor; typical side info (order <= 8, upper bands) takes 20-40 us.
 #include <cmath>
 
 #include "common.h"
@@ -15,40 +17,61 @@
 namespace mpeghb200 {
 namespace {
 
-__global__ void __launch_bounds__(128)
+// One warp per chain.  The warp stages the filter's bins in shared memory in filtering order (coalesced in either
+// direction), lane 0 runs the recurrence there with the last 16 outputs in a register ring, the warp writes the
+// range back.  A chain-per-thread layout leaves the GPU with a few dozen warps whose every load is a scattered,
+// latency-exposed access; this way there is one warp per chain (thousands), the memory side is coalesced, and what
+// remains per bin is the dependent chain of `order` subtractions.
+constexpr int kTnsWarps = 4;
+
+__global__ void __launch_bounds__(32 * kTnsWarps)
     tns_kernel(float* __restrict__ coef, const mpeghb200_tns_filter* __restrict__ filters,
                const int32_t* __restrict__ chain_first, int n_chains) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_chains) return;
+  __shared__ __align__(16) float stage[kTnsWarps][1024 + 16];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int c = blockIdx.x * kTnsWarps + wib;
+  if (c >= n_chains) return;  // whole warp
+  float* buf = stage[wib];
   for (int f = chain_first[c]; f < chain_first[c + 1]; ++f) {
     const mpeghb200_tns_filter& F = filters[f];
     const int order = F.order, size = F.size, inc = F.inc;
-    if (order <= 0 || size <= 0) continue;
-    // the last 16 outputs live in a register ring addressed with compile-time indices (the bin loop is unrolled
-    // by 16), so a bin costs its `order` product/difference pairs and nothing else
-    float lpc[15], ring[16];
-#pragma unroll
-    for (int j = 0; j < 15; ++j) lpc[j] = F.lpc[j];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) ring[j] = 0.0f;
+    if (order <= 0 || size <= 0 || size > 1024) continue;
     float* p = coef + size_t(F.unit) * 1024 + F.start + (inc < 0 ? size - 1 : 0);
-    for (int i0 = 0; i0 < size; i0 += 16) {
-      float xb[16];
+    for (int i = lane; i < size; i += 32) buf[i] = p[i * inc];
+    for (int i = size + lane; i < ((size + 15) & ~15); i += 32) buf[i] = 0.0f;
+    __syncwarp();
+    if (lane == 0) {
+      // the last 16 outputs live in a register ring addressed with compile-time indices (the bin loop is
+      // unrolled by 16), so a bin costs its `order` product/difference pairs and nothing else
+      float lpc[15], ring[16];
 #pragma unroll
-      for (int e = 0; e < 16; ++e) xb[e] = (i0 + e < size) ? p[(i0 + e) * inc] : 0.0f;
+      for (int j = 0; j < 15; ++j) lpc[j] = F.lpc[j];
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        float y = xb[e];
+      for (int j = 0; j < 16; ++j) ring[j] = 0.0f;
+      for (int i0 = 0; i0 < size; i0 += 16) {
+        float xb[16];
 #pragma unroll
-        for (int j = 0; j < 15; ++j)
-          if (j < order) y = fsub(y, fmul(lpc[j], ring[(e - 1 - j) & 15]));  // y[n-1-j]
-        ring[e] = y;
-        xb[e] = y;
+        for (int q = 0; q < 4; ++q) {
+          const float4 v = *reinterpret_cast<const float4*>(buf + i0 + 4 * q);
+          xb[4 * q] = v.x, xb[4 * q + 1] = v.y, xb[4 * q + 2] = v.z, xb[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          float y = xb[e];
+#pragma unroll
+          for (int j = 0; j < 15; ++j)
+            if (j < order) y = fsub(y, fmul(lpc[j], ring[(e - 1 - j) & 15]));  // y[n-1-j]
+          ring[e] = y;
+          xb[e] = y;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(buf + i0 + 4 * q) = make_float4(xb[4 * q], xb[4 * q + 1], xb[4 * q + 2], xb[4 * q + 3]);
       }
-#pragma unroll
-      for (int e = 0; e < 16; ++e)
-        if (i0 + e < size) p[(i0 + e) * inc] = xb[e];
     }
+    __syncwarp();
+    for (int i = lane; i < size; i += 32) p[i * inc] = buf[i];
+    __syncwarp();
   }
 }
 
@@ -88,8 +111,8 @@ mpeghb200_status mpeghb200_tns_dev(mpeghb200_ctx* ctx, float* d_coef, const mpeg
     return fail(ctx, MPEGHB200_ERR_BAD_ARG, "tns_dev: null buffer or negative chain count");
   if (n_chains == 0) return MPEGHB200_OK;
   MB_CUDA(ctx, cudaSetDevice(ctx->device));
-  tns_kernel<<<(n_chains + 127) / 128, 128, 0, static_cast<cudaStream_t>(cuda_stream)>>>(d_coef, d_filters,
-                                                                                         d_chain_first, n_chains);
+  tns_kernel<<<(n_chains + kTnsWarps - 1) / kTnsWarps, 32 * kTnsWarps, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+      d_coef, d_filters, d_chain_first, n_chains);
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   return MPEGHB200_OK;
