@@ -217,33 +217,43 @@ __global__ void __launch_bounds__(kPackSamples)
   const float* x = in + size_t(sidx) * P.n_ch * kFrame;
   const int d = delay ? delay[sidx] : 0;
   const int s = chunk * kPackSamples + tid;
-  for (int ch = 0; ch < P.n_ch; ++ch) {
-    float v = __ldcs(x + size_t(P.pos[ch]) * kFrame + s);
-    int w;
-    if (P.bits == 24) {
-      v = fmul(v, 256.0f);
-      if (v < -8388608.0f)
-        v = -8388608.0f;
-      else if (8388607.0f < v)
-        v = 8388607.0f;
-      w = sat_cast(v);
-    } else if (P.bits == 16) {
-      if (v < -32768.0f)
-        v = -32768.0f;
-      else if (32767.0f < v)
-        v = 32767.0f;
-      w = sat_cast(v);
-    } else {
-      v = fmul(v, 65536.0f);
-      if (v < -2147483647.0f) v = -2147483647.0f;
-      // reference build quirk (see oracle/oracle_tail.c): above 2^31 -> INT32_MAX, exactly 2^31 -> INT32_MIN
-      w = (2147483647.0f < v) ? 0x7fffffff : sat_cast(v);
+  constexpr int kBatch = 8;
+  for (int ch0 = 0; ch0 < P.n_ch; ch0 += kBatch) {
+    float vin[kBatch];  // eight channel loads in flight before the first conversion
+#pragma unroll
+    for (int q = 0; q < kBatch; ++q)
+      vin[q] = (ch0 + q < P.n_ch) ? __ldcs(x + size_t(P.pos[ch0 + q]) * kFrame + s) : 0.0f;
+#pragma unroll
+    for (int q = 0; q < kBatch; ++q) {
+      const int ch = ch0 + q;
+      if (ch >= P.n_ch) break;
+      float v = vin[q];
+      int w;
+      if (P.bits == 24) {
+        v = fmul(v, 256.0f);
+        if (v < -8388608.0f)
+          v = -8388608.0f;
+        else if (8388607.0f < v)
+          v = 8388607.0f;
+        w = sat_cast(v);
+      } else if (P.bits == 16) {
+        if (v < -32768.0f)
+          v = -32768.0f;
+        else if (32767.0f < v)
+          v = 32767.0f;
+        w = sat_cast(v);
+      } else {
+        v = fmul(v, 65536.0f);
+        if (v < -2147483647.0f) v = -2147483647.0f;
+        // reference build quirk (see oracle/oracle_tail.c): above 2^31 -> INT32_MAX, exactly 2^31 -> INT32_MIN
+        w = (2147483647.0f < v) ? 0x7fffffff : sat_cast(v);
+      }
+      unsigned char* t = tile + (size_t(tid) * P.n_ch + ch) * bps;
+      t[0] = w & 0xff;
+      t[1] = (w >> 8) & 0xff;
+      if (bps > 2) t[2] = (w >> 16) & 0xff;
+      if (bps > 3) t[3] = (w >> 24) & 0xff;
     }
-    unsigned char* t = tile + (size_t(tid) * P.n_ch + ch) * bps;
-    t[0] = w & 0xff;
-    t[1] = (w >> 8) & 0xff;
-    if (bps > 2) t[2] = (w >> 16) & 0xff;
-    if (bps > 3) t[3] = (w >> 24) & 0xff;
   }
   __syncthreads();
   // tile -> global; sample s lands at byte (s - d) * n_ch * bps (start-up delay trimming)
