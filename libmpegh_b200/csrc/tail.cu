@@ -43,7 +43,6 @@ __global__ void __launch_bounds__(kLimThreads)
   __shared__ __align__(16) float m[kMaxAttack + kFrame + 16];   // channel maxima incl. history / sliding max
   __shared__ __align__(16) float m2[kMaxAttack + kFrame + 16];  // ping-pong partner
   __shared__ __align__(16) float g[kFrame];                     // gains; < 0 = pass through
-  __shared__ __align__(16) float xbuf[kMaxAttack + kFrame];     // delay line + current frame of one channel
   const int tid = threadIdx.x;
   const int A = P.attack;
   const size_t sidx = blockIdx.x;
@@ -61,6 +60,7 @@ __global__ void __launch_bounds__(kLimThreads)
     // 1. channel maxima (fmax semantics of the reference: NaN operands are dropped)
     float4 acc[2];
     acc[0] = acc[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 6
     for (int c = 0; c < P.n_ch; ++c) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -146,26 +146,39 @@ __global__ void __launch_bounds__(kLimThreads)
     __syncthreads();
   }
 
-  // 5. delayed output, one channel at a time through shared memory
+  // 5. delayed output: sample i of the frame leaves as input sample i - A (this frame for i >= A, the delay line
+  //    before), times the gain, clipped.  Straight from global memory (the frame is L2-resident since step 1, A is
+  //    a multiple of 4 so every float4 stays aligned): no staging, no barriers, loads of several channels in flight.
   const float thr = P.thr;
+  float4 gv[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) gv[h] = *reinterpret_cast<const float4*>(g + 4 * (tid + kLimThreads * h));
+#pragma unroll 4
   for (int c = 0; c < P.n_ch; ++c) {
     float* dl = st_delay + size_t(c) * A;
-    for (int i = tid; i < A / 4; i += kLimThreads)
-      reinterpret_cast<float4*>(xbuf)[i] = reinterpret_cast<const float4*>(dl)[i];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      float4 v = __ldg(reinterpret_cast<const float4*>(x + size_t(c) * kFrame) + tid + kLimThreads * h);
-      if (has_lg) v = make_float4(fmul(v.x, lg), fmul(v.y, lg), fmul(v.z, lg), fmul(v.w, lg));
-      reinterpret_cast<float4*>(xbuf + A)[tid + kLimThreads * h] = v;
-    }
-    __syncthreads();
+    const float* xc = x + size_t(c) * kFrame;
+    float4 xv[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int i = 4 * (tid + kLimThreads * h);
-      const float4 xv = *reinterpret_cast<const float4*>(xbuf + i);
-      const float4 gv = *reinterpret_cast<const float4*>(g + i);
-      float r[4] = {xv.x, xv.y, xv.z, xv.w};
-      const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
+      if (i >= A) {
+        xv[h] = __ldg(reinterpret_cast<const float4*>(xc + i - A));
+        if (has_lg) xv[h] = make_float4(fmul(xv[h].x, lg), fmul(xv[h].y, lg), fmul(xv[h].z, lg), fmul(xv[h].w, lg));
+      } else {
+        xv[h] = *reinterpret_cast<const float4*>(dl + i);  // already carries the loudness gain
+      }
+    }
+    // the last A samples of the frame are the next frame's delay line (same thread that just read dl + 4 tid)
+    if (4 * tid < A) {
+      float4 t = __ldg(reinterpret_cast<const float4*>(xc + kFrame - A + 4 * tid));
+      if (has_lg) t = make_float4(fmul(t.x, lg), fmul(t.y, lg), fmul(t.z, lg), fmul(t.w, lg));
+      *reinterpret_cast<float4*>(dl + 4 * tid) = t;
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = 4 * (tid + kLimThreads * h);
+      float r[4] = {xv[h].x, xv[h].y, xv[h].z, xv[h].w};
+      const float gg[4] = {gv[h].x, gv[h].y, gv[h].z, gv[h].w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         if (gg[e] >= 0.0f) {
@@ -179,9 +192,6 @@ __global__ void __launch_bounds__(kLimThreads)
       }
       __stcs(reinterpret_cast<float4*>(y + size_t(c) * kFrame + i), make_float4(r[0], r[1], r[2], r[3]));
     }
-    for (int i = tid; i < A / 4; i += kLimThreads)
-      reinterpret_cast<float4*>(dl)[i] = reinterpret_cast<const float4*>(xbuf + kFrame)[i];
-    __syncthreads();
   }
 }
 
