@@ -856,8 +856,11 @@ __device__ __noinline__ void slow_units(const float* __restrict__ coef, const ui
   }
 }
 
+#ifndef MPEGHB200_FD_CTAS_PER_SM
+#define MPEGHB200_FD_CTAS_PER_SM 3
+#endif
 template <bool DEFER>
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(128, MPEGHB200_FD_CTAS_PER_SM)
     fd_synth_ws_kernel(const float* __restrict__ coef, const uint32_t* __restrict__ side, float* __restrict__ overlap,
                        float* __restrict__ out, int n_units, const __grid_constant__ DeviceTables T) {
   __shared__ __align__(16) float slots[kSlots][kBufFloats];
@@ -990,7 +993,7 @@ mpeghb200_status fd_synth_launch(mpeghb200_ctx* ctx, const float* d_coef, const 
     default:
     case 7:
     case 8: {
-      const int ctas = ctx->sm_count * 3;
+      const int ctas = ctx->sm_count * MPEGHB200_FD_CTAS_PER_SM;
       if (ctx->fd_variant == 8)
         fd_synth_ws_kernel<false><<<n_units < ctas ? n_units : ctas, 128, 0, stream>>>(d_coef, d_side, d_overlap, d_out,
                                                                                    n_units, ctx->tables);
