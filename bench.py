@@ -237,13 +237,22 @@ def main():
 
     if not torch.cuda.is_available():
         sys.exit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    # the host side of a rank lives next to its GPU: CPU affinity first, so that the pinned staging buffers
+    # allocated below land on that NUMA node (first touch)
+    from libmpegh_b200 import shard
+    numa_cpus = shard.bind_to_gpu_numa(local_rank) if world > 1 else None
+    # Libraries print banners on stdout (NCCL's version line under NCCL_DEBUG=VERSION/WARN does); the contract is ONE
+    # JSON line there.  File descriptor 1 is pointed at stderr for the duration of the run and the line is written
+    # to the saved descriptor at the end.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = Lib().create(local_rank)
     stream = torch.cuda.current_stream()
     # weak scaling: world x 256 streams in total, rank r owns the contiguous block shard.stream_range gives it
-    from libmpegh_b200 import shard
     s_begin, s_end = shard.stream_range(rank, world, world * STREAMS)
     assert s_end - s_begin == STREAMS
 
@@ -381,7 +390,9 @@ def main():
             "config": {"workload": workload_name(), "streams_per_gpu": STREAMS, "channels": CHANNELS,
                        "frame": FRAME, "l2_policy": f"inputs larger than L2: {G} stream groups rotated, "
                        f"{G * 3 * UNITS * FRAME * 4 / 1e6:.0f} MB working set, state carried per group",
-                       "sharding": "streams by rank, no collective"},
+                       "sharding": "streams by rank, no collective",
+                       "host_numa_binding": (f"rank 0 on {len(numa_cpus)} CPUs of its GPU's NUMA node" if numa_cpus
+                                             else "none")},
             "realtime_factor": value / CHANNELS / 48000.0,
             "mixed_sequence_variant": {
                 "note": "same shape with ~8 % LONG_START/EIGHT_SHORT/LONG_STOP frames (SURVEY.md 8d variant)",
@@ -404,7 +415,8 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": kind,
                                     "sample": f"{sample_units} channel-frames x 2500 frames on 1 host thread "
                                               f"(box has {n_threads}); ia_core_coder_fd_frm_dec"}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     lib.close()
     if world > 1:
         dist.destroy_process_group()

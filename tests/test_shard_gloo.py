@@ -69,3 +69,10 @@ def test_world_size_2_gloo():
         assert tmax == 11.0                      # max over ranks
         assert (cover == 1).all()                # disjoint and complete
         assert np.array_equal(local, want)       # union of the shards == the unsharded result
+
+
+def test_numa_helpers():
+    from libmpegh_b200 import shard
+    assert shard._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert shard._parse_cpulist("") == []
+    assert shard.gpu_numa_cpus("00000000:FF:1F.7") is None  # no such device: the caller keeps its affinity
