@@ -364,6 +364,27 @@ typedef struct mpeghb200_tns_filter {
   float lpc[16]; /* lpc[j] = the reference's lpc[j + 1] */
 } mpeghb200_tns_filter;
 mpeghb200_status mpeghb200_tns_lpc_from_coef(int order, int coef_res, const int16_t *coef, float *lpc16);
+/* Host half of ia_core_coder_tns_apply for one channel-frame (no GPU needed): the transmitted TNS data as the
+ * parser leaves it in ia_tns_frame_info_struct (decoder/ia_core_coder_tns_usac.h:50-71) -> filter records, one
+ * chain per window with an effective filter.  Same clamps as the reference (:240-284: tns_max_bands, max_sfb, the
+ * IGF start / stop band via ia_core_coder_igf_nbands :147); a band index beyond the table returns
+ * MPEGHB200_ERR_BAD_ARG where the reference returns IA_MPEGH_DEC_EXE_FATAL_INVALID_TNS_SFB. */
+typedef struct mpeghb200_tns_channel {
+  int32_t unit;    /* channel-frame index the records will carry */
+  int32_t is_long; /* 1: one window of 1024 bins, 0: eight windows of 128 */
+  int32_t max_sfb; /* the nbands argument of ia_core_coder_tns_apply */
+  int32_t igf_active, igf_after_tns_synth, igf_sfb_start, igf_sfb_stop; /* igf_grid of the block type */
+  int32_t n_filt[8];   /* per window */
+  int32_t coef_res[8]; /* 3 or 4, per window */
+  struct {
+    int32_t order, start_band, stop_band, direction;
+    int16_t coef[16];
+  } filt[8][3];
+} mpeghb200_tns_channel;
+mpeghb200_status mpeghb200_tns_resolve(const mpeghb200_tns_channel *ch, const int16_t *sfb_top, int sfb_per_sbk,
+                                       int tns_max_band, mpeghb200_tns_filter *filters_out, int filters_cap,
+                                       int32_t *chain_len_out, int chains_cap, int *n_filters_out,
+                                       int *n_chains_out);
 mpeghb200_status mpeghb200_tns_dev(mpeghb200_ctx *ctx, float *d_coef, const mpeghb200_tns_filter *d_filters,
                                    const int32_t *d_chain_first, int n_chains, void *cuda_stream);
 

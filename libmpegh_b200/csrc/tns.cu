@@ -11,6 +11,7 @@
 // Worst case (3 filters of order 15 over all 1024 bins) = 3072 x 15 dependent subtractions = 94 us at 4 cycles
 // each: the stress stage bench sits at that floor; typical side info (order <= 8, upper bands) takes 20-40 us.
 #include <cmath>
+#include <cstring>
 
 #include "common.h"
 
@@ -101,6 +102,58 @@ mpeghb200_status mpeghb200_tns_lpc_from_coef(int order, int coef_res, const int1
     for (int i = 0; i <= m; i++) a[i] = b[i];
   }
   for (int i = 0; i < 16; i++) lpc[i] = (i < order) ? a[i + 1] : 0.0f;
+  return MPEGHB200_OK;
+}
+
+// Host half of ia_core_coder_tns_apply (decoder/ia_core_coder_tns.c:204-300): band clamps, band -> bin lookup,
+// coefficient decoding; one chain per window that has at least one effective filter.
+mpeghb200_status mpeghb200_tns_resolve(const mpeghb200_tns_channel* ch, const int16_t* sfb_top, int sfb_per_sbk,
+                                       int tns_max_band, mpeghb200_tns_filter* filters_out, int filters_cap,
+                                       int32_t* chain_len_out, int chains_cap, int* n_filters_out,
+                                       int* n_chains_out) {
+  if (!ch || !sfb_top || !filters_out || !chain_len_out || !n_filters_out || !n_chains_out || sfb_per_sbk <= 0)
+    return MPEGHB200_ERR_BAD_ARG;
+  *n_filters_out = 0, *n_chains_out = 0;
+  const int n_win = ch->is_long ? 1 : 8, bins = ch->is_long ? 1024 : 128;
+  int nbands = ch->max_sfb;
+  if (ch->igf_active) {  // ia_core_coder_igf_nbands (:147)
+    if (ch->igf_after_tns_synth) {
+      if (ch->igf_sfb_start < nbands) nbands = ch->igf_sfb_start;
+    } else {
+      if (ch->igf_sfb_stop > nbands) nbands = ch->igf_sfb_stop;
+    }
+  }
+  int nf = 0, nc = 0;
+  for (int w = 0; w < n_win; ++w) {
+    int in_chain = 0;
+    const int n_filt = ch->n_filt[w] < 0 ? 0 : (ch->n_filt[w] > 3 ? 3 : ch->n_filt[w]);
+    for (int f = 0; f < n_filt; ++f) {
+      const auto& t = ch->filt[w][f];
+      if (!t.order) continue;
+      int start = t.start_band < tns_max_band ? t.start_band : tns_max_band;
+      start = start < nbands ? start : nbands;
+      if (start > sfb_per_sbk) return MPEGHB200_ERR_BAD_ARG;  // IA_MPEGH_DEC_EXE_FATAL_INVALID_TNS_SFB (:262)
+      int stop = t.stop_band;
+      if (!ch->igf_active) stop = stop < tns_max_band ? stop : tns_max_band;
+      stop = stop < nbands ? stop : nbands;
+      if (stop > sfb_per_sbk) return MPEGHB200_ERR_BAD_ARG;
+      const int a = start > 0 ? sfb_top[start - 1] : 0, b = stop > 0 ? sfb_top[stop - 1] : 0;
+      if (b - a <= 0) continue;
+      if (t.order < 0 || t.order > 15 || b > bins) return MPEGHB200_ERR_BAD_ARG;
+      if (nf >= filters_cap) return MPEGHB200_ERR_NO_MEM;
+      mpeghb200_tns_filter& r = filters_out[nf];
+      std::memset(&r, 0, sizeof(r));
+      r.unit = ch->unit, r.start = w * bins + a, r.size = b - a, r.inc = t.direction ? -1 : 1, r.order = t.order;
+      const mpeghb200_status st = mpeghb200_tns_lpc_from_coef(t.order, ch->coef_res[w], t.coef, r.lpc);
+      if (st != MPEGHB200_OK) return st;
+      ++nf, ++in_chain;
+    }
+    if (in_chain) {
+      if (nc >= chains_cap) return MPEGHB200_ERR_NO_MEM;
+      chain_len_out[nc++] = in_chain;
+    }
+  }
+  *n_filters_out = nf, *n_chains_out = nc;
   return MPEGHB200_OK;
 }
 

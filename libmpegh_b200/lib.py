@@ -79,6 +79,11 @@ class HoaSpatialDesc(ctypes.Structure):
 
 
 LTPF_SIDE_DTYPE = np.dtype([("unit", "<i4"), ("pitch_lag_idx", "<u2"), ("data_present", "u1"), ("gain_idx", "u1")])
+TNS_CHANNEL_DTYPE = np.dtype([
+    ("unit", "<i4"), ("is_long", "<i4"), ("max_sfb", "<i4"), ("igf_active", "<i4"), ("igf_after_tns_synth", "<i4"),
+    ("igf_sfb_start", "<i4"), ("igf_sfb_stop", "<i4"), ("n_filt", "<i4", 8), ("coef_res", "<i4", 8),
+    ("filt", [("order", "<i4"), ("start_band", "<i4"), ("stop_band", "<i4"), ("direction", "<i4"),
+              ("coef", "<i2", 16)], (8, 3))])
 TNS_FILTER_DTYPE = np.dtype([("unit", np.int32), ("start", np.int32), ("size", np.int32), ("inc", np.int32),
                              ("order", np.int32), ("pad", np.int32, 3), ("lpc", np.float32, 16)])
 OBJ_SIDE_DTYPE = np.dtype([("vec_c", np.float32, 3), ("gain", np.float32), ("spread_w", np.float32),
@@ -203,6 +208,8 @@ class Lib:
         c.mpeghb200_format_conv_dev.restype = i32
         c.mpeghb200_tns_lpc_from_coef.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp]
         c.mpeghb200_tns_lpc_from_coef.restype = i32
+        c.mpeghb200_tns_resolve.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp, ctypes.c_int, vp, vp]
+        c.mpeghb200_tns_resolve.restype = i32
         c.mpeghb200_tns_dev.argtypes = [vp, vp, vp, vp, ctypes.c_int, vp]
         c.mpeghb200_tns_dev.restype = i32
         c.mpeghb200_resampler_create.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.POINTER(vp)]
@@ -329,6 +336,21 @@ class Lib:
         if st != OK:
             raise MpeghError(st, "tns_lpc_from_coef: bad order or coefficient resolution")
         return lpc
+
+    def tns_resolve(self, ch, sfb_top, tns_max_band):
+        """ch: TNS_CHANNEL_DTYPE record -> list of chains (lists of TNS_FILTER_DTYPE records); raises MpeghError"""
+        sfb = np.ascontiguousarray(sfb_top, np.int16)
+        recs = np.zeros(24, TNS_FILTER_DTYPE)
+        lens = np.zeros(8, np.int32)
+        nf, nc = ctypes.c_int(), ctypes.c_int()
+        buf = ch.tobytes()
+        self.check(self.c.mpeghb200_tns_resolve(buf, sfb.ctypes.data, len(sfb), tns_max_band, recs.ctypes.data, 24,
+                                                lens.ctypes.data, 8, ctypes.byref(nf), ctypes.byref(nc)))
+        out, k = [], 0
+        for i in range(nc.value):
+            out.append([recs[k + j].copy() for j in range(int(lens[i]))])
+            k += int(lens[i])
+        return out
 
     def tns_dev(self, d_coef, d_filters, d_chain_first, n_chains, stream=0):
         self.check(self.c.mpeghb200_tns_dev(self.ctx, d_coef, d_filters, d_chain_first, n_chains, stream))
