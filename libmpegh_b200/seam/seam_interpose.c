@@ -8,6 +8,8 @@
  *   ia_core_coder_fd_frm_dec             decoder/ia_core_coder_imdct.c:832      -> mpeghb200_fd_synth_dev
  *   impeghd_tns_decode_coeff_ar_filter   decoder/ia_core_coder_tns.c:83         -> mpeghb200_tns_dev
  *   ia_core_coder_usac_ltpf_process      decoder/ia_core_coder_ltpf.c:395       -> mpeghb200_ltpf_dev
+ *   impeghd_format_converter_process     decoder/ia_core_coder_process.c:641    -> mpeghb200_format_conv_dev
+ *                                        (seam_interpose_fc.c)
  *   impeghd_peak_limiter_init/_process   decoder/impeghd_peak_limiter.c:146,190 -> mpeghb200_limiter_dev
  *
  * Every call here handles ONE handle's frame, so it moves a few KB per launch: this object exists to prove that
@@ -56,7 +58,7 @@
 #include "impeghd_error_codes.h"
 #include "impeghd_peak_limiter_struct_def.h"
 
-#include "mpeghb200.h"
+#include "seam_internal.h"
 
 #define FRAME 1024
 #define MAX_LIM 8
@@ -81,29 +83,21 @@ static struct
   float *h_planar;
   float *d_ltpf_state;
   mpeghb200_ltpf_side *d_ltpf_side;
-  unsigned long n_fd_gpu, n_fd_host, n_tns, n_lim, n_ltpf;
+  unsigned long n_fd_gpu, n_fd_host, n_tns, n_lim, n_ltpf, n_fc;
 } g;
 
-static void seam_die(const char *what, mpeghb200_status st)
+void seam_die(const char *what, mpeghb200_status st)
 {
   fprintf(stderr, "mpeghb200 seam: %s failed (0x%08x): %s\n", what, (unsigned)st, mpeghb200_last_error(g.ctx));
   abort();
 }
-#define CK(call)                                                                                   \
-  do                                                                                               \
-  {                                                                                                \
-    mpeghb200_status st_ = (call);                                                                 \
-    if (st_ != MPEGHB200_OK)                                                                       \
-      seam_die(#call, st_);                                                                        \
-  } while (0)
-
 static void seam_stats(void)
 {
   if (getenv("MPEGHB200_SEAM_STATS"))
     fprintf(stderr,
             "mpeghb200 seam: fd_frm_dec gpu=%lu host(LPD transition)=%lu tns_filters gpu=%lu limiter_frames gpu=%lu "
-            "ltpf_frames gpu=%lu kernel_launches=%llu\n",
-            g.n_fd_gpu, g.n_fd_host, g.n_tns, g.n_lim, g.n_ltpf,
+            "ltpf_frames gpu=%lu format_conv_frames gpu=%lu kernel_launches=%llu\n",
+            g.n_fd_gpu, g.n_fd_host, g.n_tns, g.n_lim, g.n_ltpf, g.n_fc,
             g.ctx ? (unsigned long long)mpeghb200_launch_count(g.ctx) : 0ull);
 }
 
@@ -126,6 +120,13 @@ static void seam_init(void)
   g.h_planar = (float *)malloc(MAX_NUM_CHANNELS * FRAME * sizeof(float));
   atexit(seam_stats);
 }
+
+mpeghb200_ctx *seam_ctx(void)
+{
+  seam_init();
+  return g.ctx;
+}
+void seam_count_fc(void) { g.n_fc++; }
 
 /* ---- FD synthesis ------------------------------------------------------------------------------------ */
 IA_ERRORCODE ia_core_coder_fd_frm_dec(ia_usac_data_struct *usac_data, WORD32 i_ch, WORD32 ele_id)

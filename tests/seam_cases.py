@@ -13,8 +13,7 @@ CASES = [
     ("cicp19_mp4", "sine_1khz_cicp19.mp4", []),
     ("cicp6_pcm24", "sine_1khz_cicp6.mhas", ["-pcmsz:24"]),
     ("cicp16_pcm32", "sine_1khz_cicp16.mhas", ["-pcmsz:32"]),
-    # loudspeaker retargeting: the format converter (still reference code at library level) sits between the
-    # interposed FD synthesis and the interposed limiter
+    # loudspeaker retargeting: the format converter (interposed too) sits between FD synthesis and the limiter
     ("cicp16_to_cicp6", "sine_1khz_cicp16.mhas", ["-cicp:6"]),
     ("cicp19_to_cicp2", "sine_1khz_cicp19.mhas", ["-cicp:2"]),
 ]

@@ -1,6 +1,7 @@
 """Library-level drop-in (BASELINE.json configs[0]): the reference testbench decodes the smoke_test_suite streams
 through the reference's own ia_mpegh_dec_* API while libmpeghb200_seam.so (libmpegh_b200/seam/seam_interpose.c)
-takes over FD synthesis, TNS filtering, the LTPF pass and the peak limiter on the GPU.  The WAV files must be byte-identical to
+takes over FD synthesis, TNS filtering, the LTPF pass, the format converter (-cicp: retargeting) and the peak
+limiter on the GPU.  The WAV files must be byte-identical to
 what the unmodified reference writes (tests/golden/smoke_wav.json, made by tests/golden/make_smoke_golden.py;
 the cicp1 entry equals the WAV the reference repository ships).
 """
@@ -9,7 +10,9 @@ import json
 import os
 import re
 import subprocess
+import sys
 
+import numpy as np
 import pytest
 
 import seam_cases
@@ -79,10 +82,12 @@ def test_seam_dropin_bit_exact(tmp_path, name, stream, extra):
     r = _decode(TB_DYN, stream, extra, wav, preload=SEAM)
     assert r.returncode == 0, r.stderr[-600:]
     m = re.search(r"fd_frm_dec gpu=(\d+) host\(LPD transition\)=(\d+) tns_filters gpu=(\d+) "
-                  r"limiter_frames gpu=(\d+) ltpf_frames gpu=(\d+) kernel_launches=(\d+)", r.stderr)
+                  r"limiter_frames gpu=(\d+) ltpf_frames gpu=(\d+) format_conv_frames gpu=(\d+) "
+                  r"kernel_launches=(\d+)", r.stderr)
     assert m, r.stderr[-600:]
-    fd_gpu, fd_host, _tns, lim, ltpf, launches = map(int, m.groups())
-    assert fd_gpu > 0 and fd_host == 0 and lim > 0 and ltpf == fd_gpu and launches >= 2 * fd_gpu + lim
+    fd_gpu, fd_host, _tns, lim, ltpf, fc, launches = map(int, m.groups())
+    assert fd_gpu > 0 and fd_host == 0 and lim > 0 and ltpf == fd_gpu and launches >= 2 * fd_gpu + lim + fc
+    assert fc == 0  # none of the shipped streams reaches the format converter (see test_seam_format_converter)
     assert os.path.getsize(wav) == GOLD[name]["bytes"]
     assert _sha(wav) == GOLD[name]["sha256"], f"{name}: PCM differs from the reference decoder"
     # and against the unmodified static testbench run on this very box
@@ -90,3 +95,53 @@ def test_seam_dropin_bit_exact(tmp_path, name, stream, extra):
         wav2 = str(tmp_path / "r.wav")
         assert _decode(TB, stream, extra, wav2).returncode == 0
         assert _sha(wav2) == _sha(wav)
+
+
+FC_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+from oracle import loader
+ref = loader.load_ref()
+cicp_in, cicp_out, out_path = int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
+import ctypes
+err = ctypes.c_int(0)
+h = ref.ref_fc_create(cicp_in, cicp_out, 48000, ctypes.byref(err))
+assert err.value == 0, err.value
+info = np.zeros(2, np.int32)
+ref.ref_fc_info(h, info)
+n_in, n_out = int(info[0]), int(info[1])
+rng = np.random.default_rng(100 * cicp_in + cicp_out)
+outs = []
+for f in range(4):
+    x = rng.normal(0, 3000, (n_in, 1024)).astype(np.float32)
+    y = np.zeros((n_out, 1024), np.float32)
+    assert ref.ref_fc_process(h, x.reshape(-1), y.reshape(-1)) == 0
+    outs.append(y)
+np.save(out_path, np.stack(outs))
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cicp_in,cicp_out", [(13, 6), (6, 2), (14, 19)])
+def test_seam_format_converter(tmp_path, cicp_in, cicp_out):
+    """The interposed impeghd_format_converter_process against the reference's own, both driven through the
+    reference's API struct by oracle/ref_harness_fc.c (none of the shipped streams enables the converter): the same
+    script runs once plainly (reference code) and once with the seam preloaded (GPU), outputs must be identical."""
+    libref = os.path.join(REF_DIR, "libmpeghref.so")
+    _need(libref, SEAM)
+    script = tmp_path / "fc.py"
+    script.write_text(FC_SCRIPT)
+    outs = []
+    for preload in (None, SEAM):
+        env = dict(os.environ)
+        if preload:
+            env["LD_PRELOAD"], env["MPEGHB200_SEAM_STATS"] = preload, "1"
+        out = str(tmp_path / ("gpu.npy" if preload else "ref.npy"))
+        r = subprocess.run([sys.executable, str(script), ROOT, str(cicp_in), str(cicp_out), out], env=env,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-800:]
+        if preload:
+            assert "format_conv_frames gpu=4" in r.stderr, r.stderr[-400:]
+        outs.append(np.load(out))
+    assert outs[0].shape == outs[1].shape and outs[0].shape[0] == 4
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
