@@ -41,8 +41,15 @@ METRIC = "channel-samples/s (FD synthesis: IMDCT+window+OLA, 256 streams x 24 ch
 UNIT = "channel-samples/s"
 
 
+def set_streams(n):
+    global STREAMS, UNITS, METRIC
+    STREAMS, UNITS = n, n * CHANNELS
+    METRIC = f"channel-samples/s (FD synthesis: IMDCT+window+OLA, {n} streams x 24 ch x 1024)"
+
+
 def workload_name():
-    return ("configs[1]: IMDCT+windowing/OLA, 1024-sample frames, 256 streams x 24 ch, synthetic spectra, "
+    tag = "configs[1]" if STREAMS == 256 else "configs[1] shape at a different stream count"
+    return (f"{tag}: IMDCT+windowing/OLA, 1024-sample frames, {STREAMS} streams x 24 ch, synthetic spectra, "
             "ONLY_LONG with random sine/KBD shapes")
 
 
@@ -219,7 +226,10 @@ def main():
     ap.add_argument("--groups", type=int, default=8, help="stream groups rotated through (working set > L2)")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=STREAMS,
+                    help="streams per GPU (default 256 = BASELINE.json configs[1]; 4096 = the north-star stream count)")
     args = ap.parse_args()
+    set_streams(args.streams)
     args.warmup = max(args.warmup, 3)
 
     rank = int(os.environ.get("RANK", "0"))
