@@ -839,6 +839,13 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_BLOCKS)
 constexpr int kSlots = 4;
 constexpr int kSlowCap = 256;
 
+// Programmatic dependent launch: consecutive frames are consecutive launches of this kernel on one stream.  Every
+// CTA lets the next launch be scheduled right away (its CTAs start as this launch's CTAs retire and SMs free up)
+// and loads its role's constant tables before it waits for the previous launch to be complete, so the prologue of
+// frame f + 1 runs under the tail of frame f.
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void bar_sync64(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void bar_arrive64(int id) {
   __threadfence_block();  // bar.arrive itself orders nothing: make this warp's shared-memory writes visible first
@@ -871,6 +878,7 @@ __global__ void __launch_bounds__(128, MPEGHB200_FD_CTAS_PER_SM)
   __shared__ int slow_list[kSlowCap];
   __shared__ int slow_count;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  grid_launch_dependents();
   if (threadIdx.x == 96) slow_count = 0;  // lane 0 of the role-C warp, its only writer until the final barrier
   const int first = blockIdx.x, stride = gridDim.x;
   const int n_local = first < n_units ? (n_units - first + stride - 1) / stride : 0;
@@ -880,6 +888,7 @@ __global__ void __launch_bounds__(128, MPEGHB200_FD_CTAS_PER_SM)
     // ---------------- role A ----------------
     TabA ta;
     load_tab_a(ta, T, lane);
+    grid_dependency_wait();  // tables are constants; everything below reads what the previous launch wrote
     float2 eo[2][16];
     uint32_t sw[2];
     sw[0] = __ldg(side + first);
@@ -912,6 +921,7 @@ __global__ void __launch_bounds__(128, MPEGHB200_FD_CTAS_PER_SM)
     // ---------------- role B ----------------
     TabB tb;
     load_tab_b(tb, T, lane);
+    grid_dependency_wait();  // tables are constants; everything below reads what the previous launch wrote
     for (int i = warp - 1; i < n_local; i += 2) {
       const int slot = i % kSlots;
       bar_sync64(AB + slot);
@@ -923,6 +933,7 @@ __global__ void __launch_bounds__(128, MPEGHB200_FD_CTAS_PER_SM)
     TabC tc0, tc1;
     load_tab_c(tc0, T.win_long[0], lane);
     load_tab_c(tc1, T.win_long[1], lane);
+    grid_dependency_wait();  // tables are constants; everything below reads what the previous launch wrote
     for (int i = 0; i < n_local; ++i) {
       const int slot = i % kSlots;
       const size_t u = size_t(first) + size_t(i) * stride;
@@ -994,13 +1005,17 @@ mpeghb200_status fd_synth_launch(mpeghb200_ctx* ctx, const float* d_coef, const 
     case 7:
     case 8: {
       const int ctas = ctx->sm_count * MPEGHB200_FD_CTAS_PER_SM;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(n_units < ctas ? n_units : ctas), cfg.blockDim = dim3(128), cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr, cfg.numAttrs = ctx->fd_variant == 9 ? 0 : 1;  // variant 9: plain launches, for comparison
       if (ctx->fd_variant == 8)
-        fd_synth_ws_kernel<false><<<n_units < ctas ? n_units : ctas, 128, 0, stream>>>(d_coef, d_side, d_overlap, d_out,
-                                                                                   n_units, ctx->tables);
+        e = cudaLaunchKernelEx(&cfg, fd_synth_ws_kernel<false>, d_coef, d_side, d_overlap, d_out, n_units, ctx->tables);
       else
-        fd_synth_ws_kernel<true><<<n_units < ctas ? n_units : ctas, 128, 0, stream>>>(d_coef, d_side, d_overlap, d_out,
-                                                                                  n_units, ctx->tables);
-      e = cudaGetLastError();
+        e = cudaLaunchKernelEx(&cfg, fd_synth_ws_kernel<true>, d_coef, d_side, d_overlap, d_out, n_units, ctx->tables);
+      if (e == cudaSuccess) e = cudaGetLastError();
       break;
     }
   }
