@@ -56,6 +56,30 @@ mpeghb200_status cuda_fail(mpeghb200_ctx* ctx, cudaError_t e, const char* what);
     if (_e != cudaSuccess) return ::mpeghb200::cuda_fail((ctx), _e, #expr);       \
   } while (0)
 
+// ---- programmatic dependent launch ------------------------------------------------------------------
+// The stages of a frame are consecutive launches on one stream.  Launched with launch_pdl, a kernel may be scheduled
+// while its predecessor is still running; its CTAs call pdl_prologue() first thing: allow the next launch in turn,
+// then wait until the predecessor has completed and its writes are visible.  What is saved is the launch latency
+// and CTA ramp-up between the stages.  Every kernel launched this way MUST call pdl_prologue() (or wait itself)
+// before it touches global memory.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 // ---- exact binary32 arithmetic ---------------------------------------------------------------
 // The reference is compiled for x86-64 without FMA contraction: every product and every sum is rounded
 // separately.  These wrappers keep nvcc from contracting (the files are also built with -fmad=false).

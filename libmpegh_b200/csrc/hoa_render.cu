@@ -41,6 +41,7 @@ template <int NC, int NO>
 __global__ void __launch_bounds__(kChunk)
     hoa_render_kernel(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ nfc_state,
                       const float* __restrict__ nfc, const __grid_constant__ HoaParams P) {
+  pdl_prologue();
   extern __shared__ float tile[];  // [NC][kPitch]
   const int t = threadIdx.x;
   const size_t s = blockIdx.x;
@@ -134,8 +135,8 @@ __global__ void __launch_bounds__(kChunk)
 template <int NC, int NO>
 cudaError_t launch(const float* in, float* out, float* st, const float* nfc, const HoaParams& P, int n_streams,
                    cudaStream_t stream) {
-  hoa_render_kernel<NC, NO><<<n_streams, kChunk, NC * kPitch * sizeof(float), stream>>>(in, out, st, nfc, P);
-  return cudaGetLastError();
+  return launch_pdl(hoa_render_kernel<NC, NO>, dim3(n_streams), dim3(kChunk), NC * kPitch * sizeof(float), stream, in, out,
+                    st, nfc, P);
 }
 
 }  // namespace

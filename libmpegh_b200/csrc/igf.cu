@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(kThreads, 6)
                uint32_t* __restrict__ seed_out, const int16_t* __restrict__ sfb_long, int n_long,
                const int16_t* __restrict__ sfb_short, int n_short, const uint8_t* __restrict__ b2s_long,
                const uint8_t* __restrict__ b2s_short, const int tnf_only, const IgfRom R) {
+  pdl_prologue();
   __shared__ mpeghb200_igf_side sd;
   __shared__ __align__(16) float coef[kFrame];
   __shared__ __align__(16) float tiles[4 * kFrame];
@@ -482,6 +483,7 @@ __global__ void __launch_bounds__(kThreads)
                       const int16_t* __restrict__ sfb_long, int n_long, const int16_t* __restrict__ sfb_short,
                       int n_short, const uint8_t* __restrict__ b2s_long, const uint8_t* __restrict__ b2s_short,
                       const IgfRom R) {
+  pdl_prologue();
   extern __shared__ __align__(16) float dsm[];
   float* coef = dsm;                   // [2][1024]
   float* tiles = coef + 2 * kFrame;    // [2][4][1024]
@@ -763,9 +765,9 @@ mpeghb200_status mpeghb200_igf_dev(mpeghb200_ctx* ctx, const mpeghb200_bands* ba
   if (n_units == 0) return MPEGHB200_OK;
   MB_CUDA(ctx, cudaSetDevice(ctx->device));
   static const IgfRom R = make_rom();
-  igf_kernel<<<n_units, kThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
-      d_coef, d_tiles, d_side, d_tnf_state, d_seed_out, bands->d_sfb_long, bands->n_long, bands->d_sfb_short,
-      bands->n_short, bands->d_bin2sfb_long, bands->d_bin2sfb_short, 0, R);
+  MB_CUDA(ctx, launch_pdl(igf_kernel, dim3(n_units), dim3(kThreads), 0, static_cast<cudaStream_t>(cuda_stream), d_coef,
+                          d_tiles, d_side, d_tnf_state, d_seed_out, bands->d_sfb_long, bands->n_long, bands->d_sfb_short,
+                          bands->n_short, bands->d_bin2sfb_long, bands->d_bin2sfb_short, 0, R));
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   return MPEGHB200_OK;
@@ -780,9 +782,10 @@ mpeghb200_status mpeghb200_igf_tnf_dev(mpeghb200_ctx* ctx, const mpeghb200_bands
   if (n_units == 0) return MPEGHB200_OK;
   MB_CUDA(ctx, cudaSetDevice(ctx->device));
   static const IgfRom R = make_rom();
-  igf_kernel<<<n_units, kThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
-      d_coef, nullptr, d_side, d_tnf_state, nullptr, bands->d_sfb_long, bands->n_long, bands->d_sfb_short,
-      bands->n_short, bands->d_bin2sfb_long, bands->d_bin2sfb_short, 1, R);
+  MB_CUDA(ctx, launch_pdl(igf_kernel, dim3(n_units), dim3(kThreads), 0, static_cast<cudaStream_t>(cuda_stream), d_coef,
+                          static_cast<const float*>(nullptr), d_side, d_tnf_state, static_cast<uint32_t*>(nullptr),
+                          bands->d_sfb_long, bands->n_long, bands->d_sfb_short, bands->n_short, bands->d_bin2sfb_long,
+                          bands->d_bin2sfb_short, 1, R));
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   return MPEGHB200_OK;
@@ -804,9 +807,9 @@ mpeghb200_status mpeghb200_igf_stereo_dev(mpeghb200_ctx* ctx, const mpeghb200_ba
     MB_CUDA(ctx, cudaFuncSetAttribute(igf_stereo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     configured = true;
   }
-  igf_stereo_kernel<<<n_pairs, kThreads, smem, static_cast<cudaStream_t>(cuda_stream)>>>(
-      d_coef, d_tiles, d_side, d_mask, d_tnf_state, d_seed_out, bands->d_sfb_long, bands->n_long, bands->d_sfb_short,
-      bands->n_short, bands->d_bin2sfb_long, bands->d_bin2sfb_short, R);
+  MB_CUDA(ctx, launch_pdl(igf_stereo_kernel, dim3(n_pairs), dim3(kThreads), smem, static_cast<cudaStream_t>(cuda_stream),
+                          d_coef, d_tiles, d_side, d_mask, d_tnf_state, d_seed_out, bands->d_sfb_long, bands->n_long,
+                          bands->d_sfb_short, bands->n_short, bands->d_bin2sfb_long, bands->d_bin2sfb_short, R));
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   return MPEGHB200_OK;

@@ -115,6 +115,7 @@ __device__ void filter_stretch(const float* in, float* out, int n0, int n1, cons
 __global__ void __launch_bounds__(kThreads)
     ltpf_kernel(float* __restrict__ audio, const mpeghb200_ltpf_side* __restrict__ sides, float* __restrict__ state,
                 const LtpfCfg C, const LtpfRom R) {
+  pdl_prologue();
   extern __shared__ __align__(16) float sm[];
   float* bin = sm;                      // [8 + 1024]: 6 history samples right-aligned in the first 8
   float* bout = sm + 8 + kFrame;        // [hist4 + 1024]
@@ -276,7 +277,8 @@ mpeghb200_status mpeghb200_ltpf_dev(mpeghb200_ctx* ctx, int sample_rate, float* 
   const LtpfCfg C = make_cfg(sample_rate);
   if (C.pitch_min < 8) return fail(ctx, MPEGHB200_ERR_UNSUPPORTED, "ltpf_dev: sampling rate too low for a block walk");
   const size_t smem = sizeof(float) * (8 + kFrame + ((C.hist + 3) / 4) * 4 + kFrame);
-  ltpf_kernel<<<n_units, kThreads, smem, static_cast<cudaStream_t>(cuda_stream)>>>(d_audio, d_side, d_state, C, kRom);
+  MB_CUDA(ctx, launch_pdl(ltpf_kernel, dim3(n_units), dim3(kThreads), smem, static_cast<cudaStream_t>(cuda_stream), d_audio,
+                          d_side, d_state, C, kRom));
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   return MPEGHB200_OK;

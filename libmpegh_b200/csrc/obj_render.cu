@@ -130,6 +130,7 @@ constexpr int kGainWarps = 4;
 __global__ void __launch_bounds__(32 * kGainWarps)
     obj_gains_kernel(const DevLayout* __restrict__ Lp, const mpeghb200_obj_side* __restrict__ side,
                      float* __restrict__ state, float* __restrict__ scratch, int n_obj, int n_streams) {
+  pdl_prologue();
   __shared__ float ls_all[kGainWarps][kMaxLs];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int idx = blockIdx.x * kGainWarps + wib;
@@ -262,6 +263,7 @@ template <int NOBJ>
 __global__ void __launch_bounds__(kMixMaxThreads)
     obj_mix_kernel(const DevLayout* __restrict__ Lp, const float* __restrict__ in, float* __restrict__ out,
                    const float* __restrict__ scratch, int n_obj) {
+  pdl_prologue();
   extern __shared__ __align__(16) float smem_f[];
   using SM = MixSmem<NOBJ>;
   const DevLayout& L = *Lp;
@@ -375,8 +377,8 @@ cudaError_t launch_mix(const DevLayout* dl, int NL, const float* d_in, float* d_
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  obj_mix_kernel<NOBJ><<<dim3(NL > 1 ? 2 : 1, n_streams), half * kChunks, smem, st>>>(dl, d_in, d_out, d_scratch, n_obj);
-  return cudaGetLastError();
+  return launch_pdl(obj_mix_kernel<NOBJ>, dim3(NL > 1 ? 2 : 1, n_streams), dim3(half * kChunks), smem, st, dl, d_in, d_out,
+                    d_scratch, n_obj);
 }
 
 __global__ void obj_state_init_kernel(float* state, const int* first, int n_obj, int nl1, size_t total) {
@@ -516,7 +518,8 @@ mpeghb200_status mpeghb200_obj_render_dev(mpeghb200_ctx* ctx, const mpeghb200_ob
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   const DevLayout* dl = static_cast<const DevLayout*>(L->d_desc);
   const int n_pairs = n_obj * n_streams;
-  obj_gains_kernel<<<(n_pairs + kGainWarps - 1) / kGainWarps, 32 * kGainWarps, 0, st>>>(dl, d_side, d_state, d_scratch, n_obj, n_streams);
+  MB_CUDA(ctx, launch_pdl(obj_gains_kernel, dim3((n_pairs + kGainWarps - 1) / kGainWarps), dim3(32 * kGainWarps), 0, st, dl,
+                          d_side, d_state, d_scratch, n_obj, n_streams));
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   const int NL = L->host.n_non_lfe;

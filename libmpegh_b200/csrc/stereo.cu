@@ -89,6 +89,7 @@ __device__ __forceinline__ float tap_sum(const float* __restrict__ in, int len, 
 __global__ void __launch_bounds__(kThreads)
     stereo_kernel(float* __restrict__ coef, const mpeghb200_stereo_pair* __restrict__ pairs,
                   const float* __restrict__ state, const StereoTables T) {
+  pdl_prologue();
   __shared__ mpeghb200_stereo_pair sd;
   __shared__ __align__(16) float dmx_re[kFrame];
   __shared__ __align__(16) float dmx_prev[kFrame];
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(kThreads)
 __global__ void __launch_bounds__(kThreads)
     stereo_save_kernel(const float* __restrict__ coef, const mpeghb200_stereo_pair* __restrict__ pairs,
                        float* __restrict__ state) {
+  pdl_prologue();
   const mpeghb200_stereo_pair* sd = pairs + blockIdx.x;
   const int save = sd->save;
   if (save != 1 && save != 2) return;
@@ -298,8 +300,8 @@ mpeghb200_status mpeghb200_stereo_dev(mpeghb200_ctx* ctx, const mpeghb200_bands*
     return fail(ctx, MPEGHB200_ERR_BAD_ARG, "stereo_dev: null buffer or negative pair count");
   if (n_pairs == 0) return MPEGHB200_OK;
   MB_CUDA(ctx, cudaSetDevice(ctx->device));
-  stereo_kernel<<<n_pairs, kThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(d_coef, d_pairs, d_state,
-                                                                                       stereo_tables(s));
+  MB_CUDA(ctx, launch_pdl(stereo_kernel, dim3(n_pairs), dim3(kThreads), 0, static_cast<cudaStream_t>(cuda_stream), d_coef,
+                          d_pairs, d_state, stereo_tables(s)));
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   return MPEGHB200_OK;
@@ -313,7 +315,8 @@ mpeghb200_status mpeghb200_stereo_save_dev(mpeghb200_ctx* ctx, const mpeghb200_b
     return fail(ctx, MPEGHB200_ERR_BAD_ARG, "stereo_save_dev: null buffer or negative pair count");
   if (n_pairs == 0) return MPEGHB200_OK;
   MB_CUDA(ctx, cudaSetDevice(ctx->device));
-  stereo_save_kernel<<<n_pairs, kThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(d_coef, d_pairs, d_state);
+  MB_CUDA(ctx, launch_pdl(stereo_save_kernel, dim3(n_pairs), dim3(kThreads), 0, static_cast<cudaStream_t>(cuda_stream),
+                          d_coef, d_pairs, d_state));
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   return MPEGHB200_OK;

@@ -40,6 +40,7 @@ struct LimParams {
 __global__ void __launch_bounds__(kLimThreads)
     limiter_kernel(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ state,
                    const float* __restrict__ loud_gain, const LimParams P) {
+  pdl_prologue();
   __shared__ __align__(16) float m[kMaxAttack + kFrame + 16];   // channel maxima incl. history / sliding max
   __shared__ __align__(16) float m2[kMaxAttack + kFrame + 16];  // ping-pong partner
   __shared__ __align__(16) float g[kFrame];                     // gains; < 0 = pass through
@@ -219,6 +220,7 @@ __device__ __forceinline__ int sat_cast(float v) {
 __global__ void __launch_bounds__(kPackSamples)
     pcm_pack_kernel(const float* __restrict__ in, unsigned char* __restrict__ out, int* __restrict__ delay,
                     int* __restrict__ out_bytes, const PackParams P) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char tile[];  // [kPackSamples][n_ch][bytes]
   const int tid = threadIdx.x;
   const int chunk = blockIdx.x, sidx = blockIdx.y;
@@ -350,8 +352,8 @@ mpeghb200_status mpeghb200_limiter_dev(mpeghb200_ctx* ctx, const mpeghb200_limit
   P.thr = p->threshold;
   P.ac = p->attack_const;
   P.rc = p->release_const;
-  limiter_kernel<<<n_streams, kLimThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(d_in, d_out, d_state,
-                                                                                       d_loudness_gain, P);
+  MB_CUDA(ctx, launch_pdl(limiter_kernel, dim3(n_streams), dim3(kLimThreads), 0, static_cast<cudaStream_t>(cuda_stream),
+                          d_in, d_out, d_state, d_loudness_gain, P));
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   return MPEGHB200_OK;
@@ -386,7 +388,7 @@ mpeghb200_status mpeghb200_pcm_pack_dev(mpeghb200_ctx* ctx, const float* d_in, i
     configured = true;
   }
   dim3 grid(kFrame / kPackSamples, n_streams);
-  pcm_pack_kernel<<<grid, kPackSamples, smem, st>>>(d_in, d_out, d_delay, d_out_bytes, P);
+  MB_CUDA(ctx, launch_pdl(pcm_pack_kernel, grid, dim3(kPackSamples), smem, st, d_in, d_out, d_delay, d_out_bytes, P));
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   if (d_delay) {

@@ -28,6 +28,7 @@ constexpr int kTnsWarps = 4;
 __global__ void __launch_bounds__(32 * kTnsWarps)
     tns_kernel(float* __restrict__ coef, const mpeghb200_tns_filter* __restrict__ filters,
                const int32_t* __restrict__ chain_first, int n_chains) {
+  pdl_prologue();
   __shared__ __align__(16) float stage[kTnsWarps][1024 + 16];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int c = blockIdx.x * kTnsWarps + wib;
@@ -164,8 +165,8 @@ mpeghb200_status mpeghb200_tns_dev(mpeghb200_ctx* ctx, float* d_coef, const mpeg
     return fail(ctx, MPEGHB200_ERR_BAD_ARG, "tns_dev: null buffer or negative chain count");
   if (n_chains == 0) return MPEGHB200_OK;
   MB_CUDA(ctx, cudaSetDevice(ctx->device));
-  tns_kernel<<<(n_chains + kTnsWarps - 1) / kTnsWarps, 32 * kTnsWarps, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
-      d_coef, d_filters, d_chain_first, n_chains);
+  MB_CUDA(ctx, launch_pdl(tns_kernel, dim3((n_chains + kTnsWarps - 1) / kTnsWarps), dim3(32 * kTnsWarps), 0,
+                          static_cast<cudaStream_t>(cuda_stream), d_coef, d_filters, d_chain_first, n_chains));
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   return MPEGHB200_OK;
