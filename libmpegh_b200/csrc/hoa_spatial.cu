@@ -457,14 +457,13 @@ __global__ void __launch_bounds__(kChunk, (NC <= 25) ? 3 : 2)
 #pragma unroll
     for (int n = 0; n < kPredCache; ++n) tcache[k][n] = (any_pred && n < pl.n_pred[k]) ? pred_tmp(k, n) : 0.0f;
 
-#pragma unroll
+  // Ambience + spatial prediction per coefficient in a ROLLED loop (its body is big: unrolled 25 times it thrashed
+  // the instruction cache -- ncu: most stall samples of the first version were "no instruction"); the sum is parked
+  // in the output element this thread owns and picked up again by the small unrolled loop below, which needs the
+  // register arrays v[] and d[].
+#pragma unroll 1
   for (int c = 0; c < NC; ++c) {
-    float vv = v[c];
     const int in_en = pl.in_en[c], in_dis = pl.in_dis[c];
-    if (C.coded_v_vec_length == 1) {
-      for (int i = 0; i < in_en; ++i) vv = fmul(vv, w[3]);
-      for (int i = 0; i < in_dis; ++i) vv = fmul(vv, w[2]);
-    }
     float amb;
     if (c >= C.low_order) {
       const int src = pl.reassign[c];
@@ -503,7 +502,18 @@ __global__ void __launch_bounds__(kChunk, (NC <= 25) ? 3 : 2)
       if (pl.pred_flag[0])
         for (int i = 0; i < in_dis; ++i) pred = fmul(pred, w[2]);
     }
-    __stcs(y + size_t(c) * kFrame + t, fadd(vv, fadd(fadd(amb, pred), d[c])));
+    y[size_t(c) * kFrame + t] = fadd(amb, pred);
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    float vv = v[c];
+    if (C.coded_v_vec_length == 1) {
+      const int in_en = pl.in_en[c], in_dis = pl.in_dis[c];
+      for (int i = 0; i < in_en; ++i) vv = fmul(vv, w[3]);
+      for (int i = 0; i < in_dis; ++i) vv = fmul(vv, w[2]);
+    }
+    const float ap = y[size_t(c) * kFrame + t];  // written by this very thread above
+    __stcs(y + size_t(c) * kFrame + t, fadd(vv, fadd(ap, d[c])));
   }
 }
 
