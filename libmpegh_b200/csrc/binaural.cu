@@ -57,14 +57,37 @@ struct Geo {
   static constexpr int HB = DIM2 / 2;        // bins per column kept (k < N/2)
   static constexpr int COLS = 1024 / NT;     // columns per thread
   static constexpr int NB = COLS * HB;       // bins per thread (= 8)
-  static constexpr size_t kSmem = size_t(DIM2) * kRowStride * sizeof(float2);
+  // shared memory: transform rows | row twiddles (fft_exact.cuh RowTw) | inter-stage twiddles [DIM2][1024]
+  static constexpr int kWorkF2 = DIM2 * kRowStride;
+  static constexpr int kTwF2 = (kRowTwFloats + 1) / 2;
+  static constexpr size_t kSmem = size_t(kWorkF2 + kTwF2 + DIM2 * 1024) * sizeof(float2);
 };
+
+// Tables every CTA stages once; returns the row twiddles, *mix_s = the staged inter-stage twiddles.
+template <int DIM2>
+__device__ __forceinline__ RowTw stage_tables(float2* __restrict__ work, const float4* __restrict__ eff8,
+                                              const float2* __restrict__ mix, const float2** mix_s) {
+  using G = Geo<DIM2>;
+  const RowTw tw = fill_row_tw(reinterpret_cast<float*>(work + G::kWorkF2), eff8);
+  float2* m = work + G::kWorkF2 + G::kTwF2;
+  for (int i = threadIdx.x; i < DIM2 * 1024; i += G::NT) m[i] = __ldg(mix + i);
+  *mix_s = m;
+  return tw;  // the first __syncthreads() of forward_real orders these writes before their first use
+}
+
+// Streaming 8-byte load that does not allocate in L1: the filter spectra (1.5 MB per stream-block) must not evict
+// what the transforms keep re-reading.
+__device__ __forceinline__ float2 ld_stream(const float2* p) {
+  float2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
 
 // Forward transform of one real, zero-padded block.  src(n) returns sample n < n_valid (scaled).  On return
 // X[b] = (Re X[k], -Im X[k]) for the thread's bins k = (b % HB) * 1024 + tid + NT * (b / HB); for thread 0
 // X[0] = (Re X[0], Re X[N/2]); im0/imn = Im X[0], Im X[N/2] (thread 0 only).
 template <int DIM2, typename Src>
-__device__ __forceinline__ void forward_real(float2* __restrict__ work, const float4* __restrict__ eff8,
+__device__ __forceinline__ void forward_real(float2* __restrict__ work, const RowTw tw,
                                              const float2* __restrict__ mix, Src src, int n_valid,
                                              float2 (&X)[8], float& im0, float& imn) {
   using G = Geo<DIM2>;
@@ -76,7 +99,7 @@ __device__ __forceinline__ void forward_real(float2* __restrict__ work, const fl
     work[(n % DIM2) * kRowStride + phys(n / DIM2)] = make_float2(x, 0.0f);
   }
   __syncthreads();
-  rows_1024<DIM2, true>(work, eff8);
+  rows_1024<DIM2, true>(work, tw);
 #pragma unroll
   for (int c = 0; c < G::COLS; ++c) {
     const int i = tid + G::NT * c;
@@ -120,6 +143,9 @@ __global__ void __launch_bounds__(64 * DIM2) binaural_block_kernel(const __grid_
   const int32_t* dlen = P.direct_len + size_t(set) * 2 * P.n_in;
   const float* wgt = P.weight + size_t(set) * P.n_in;
 
+  const float2* mix_s;
+  const RowTw tw = stage_tables<DIM2>(work, P.eff8, P.mix, &mix_s);
+
   int kbin[G::NB];
 #pragma unroll
   for (int b = 0; b < G::NB; ++b) kbin[b] = (b % G::HB) * 1024 + tid + G::NT * (b / G::HB);
@@ -133,7 +159,7 @@ __global__ void __launch_bounds__(64 * DIM2) binaural_block_kernel(const __grid_
     const float* x = P.in + s * P.in_stream_stride + inp * P.in_chan_stride;
     float2 X[G::NB];
     forward_real<DIM2>(
-        work, P.eff8, P.mix,
+        work, tw, mix_s,
         [&](int n) { return fmul(__ldcs(x + (n >> 10) * P.in_chunk_stride + (n & 1023)), P.in_scale); }, G::B, X,
         im0, imn);
     const int l0 = dlen[inp], l1 = dlen[P.n_in + inp];
@@ -142,8 +168,8 @@ __global__ void __launch_bounds__(64 * DIM2) binaural_block_kernel(const __grid_
     const float w = wgt[inp];
 #pragma unroll
     for (int b = 0; b < G::NB; ++b) {
-      const float2 a0 = __ldg(reinterpret_cast<const float2*>(h0) + kbin[b]);
-      const float2 a1 = __ldg(reinterpret_cast<const float2*>(h1) + kbin[b]);
+      const float2 a0 = ld_stream(reinterpret_cast<const float2*>(h0) + kbin[b]);
+      const float2 a1 = ld_stream(reinterpret_cast<const float2*>(h1) + kbin[b]);
       mac_perm(acc[0][b], a0, X[b], kbin[b], l0);
       mac_perm(acc[1][b], a1, X[b], kbin[b], l1);
       if (P.n_blocks) {
@@ -171,7 +197,7 @@ __global__ void __launch_bounds__(64 * DIM2) binaural_block_kernel(const __grid_
         const float2 xin = pin[kbin[b]];
 #pragma unroll
         for (int o = 0; o < 2; ++o) {
-          const float2 h = __ldg(reinterpret_cast<const float2*>(hf + size_t(j * 2 + o) * G::N) + kbin[b]);
+          const float2 h = ld_stream(reinterpret_cast<const float2*>(hf + size_t(j * 2 + o) * G::N) + kbin[b]);
           mac_perm(acc[o][b], h, xin, kbin[b], flen[j * 2 + o]);
         }
       }
@@ -197,14 +223,14 @@ __global__ void __launch_bounds__(64 * DIM2) binaural_block_kernel(const __grid_
       }
     }
     __syncthreads();
-    rows_1024<DIM2, false>(work, P.eff8);
+    rows_1024<DIM2, false>(work, tw);
     float* yo = P.out + (s * 2 + o) * G::B;
     float* tl = tail + o * G::B;
 #pragma unroll
     for (int c = 0; c < G::COLS; ++c) {
       const int i = tid + G::NT * c;
       float xr[DIM2], xi[DIM2];
-      column<DIM2, false>(work, P.mix, i, xr, xi);
+      column<DIM2, false>(work, mix_s, i, xr, xi);
 #pragma unroll
       for (int j = 0; j < G::HB; ++j) {
         const int t = j * 1024 + i;
@@ -232,7 +258,9 @@ __global__ void __launch_bounds__(64 * DIM2)
   const float* t = taps + size_t(blockIdx.x) * len;
   float2 X[G::NB];
   float im0, imn;
-  forward_real<DIM2>(work, eff8, mix, [&](int n) { return t[n]; }, len < G::B ? len : G::B, X, im0, imn);
+  const float2* mix_s;
+  const RowTw tw = stage_tables<DIM2>(work, eff8, mix, &mix_s);
+  forward_real<DIM2>(work, tw, mix_s, [&](int n) { return t[n]; }, len < G::B ? len : G::B, X, im0, imn);
   float2* o = reinterpret_cast<float2*>(spec + size_t(blockIdx.x) * G::N);
 #pragma unroll
   for (int b = 0; b < G::NB; ++b) o[(b % G::HB) * 1024 + threadIdx.x + G::NT * (b / G::HB)] = X[b];

@@ -172,33 +172,117 @@ __device__ __forceinline__ void col8(float (&xr)[8], float (&xi)[8]) {
   }
 }
 
+// ---- twiddles of the row transforms, staged in shared memory ------------------------------------------------
+// The effective-twiddle table is indexed per lane in stages B and C (16 distinct entries 512 B apart for a warp in
+// stage B: a global load costs 16 L1 wavefronts and its latency).  The CTA stages what it needs once, transposed so
+// that every warp-wide load is one conflict-free wavefront:
+//   a [3][6]      eff[64 m], m = 1..3 (stage A, warp-uniform)
+//   b [5][6][16]  entry e for lane class mm = g & 15: e = 0 -> eff[16 mm], e = 1 + a -> eff[4 mm + 64 a]
+//   c [6][256]    eff[m], transposed (stage C)
+struct RowTw {
+  const float* a;
+  const float* b;
+  const float* c;
+};
+constexpr int kRowTwFloats = 18 + 480 + 1536;
+
+// Every thread of the CTA calls this; the caller issues the __syncthreads().
+__device__ __forceinline__ RowTw fill_row_tw(float* __restrict__ dst, const float4* __restrict__ eff8) {
+  const float* eff = reinterpret_cast<const float*>(eff8);  // [256][8]: c1 s1 c2 s2 c3 s3 0 0
+  for (int i = threadIdx.x; i < kRowTwFloats; i += blockDim.x) {
+    int j, f;
+    if (i < 18) {
+      j = 64 * (1 + i / 6), f = i % 6;
+    } else if (i < 498) {
+      const int r = i - 18, mm = r & 15, ef = r >> 4, e = ef / 6;
+      f = ef - 6 * e;
+      j = e == 0 ? 16 * mm : 4 * mm + 64 * (e - 1);
+    } else {
+      const int r = i - 498;
+      j = r & 255, f = r >> 8;
+    }
+    dst[i] = __ldg(eff + 8 * j + f);
+  }
+  return RowTw{dst, dst + 18, dst + 498};
+}
+
+// b, c, d *= their twiddles (e[0..5] = c1 s1 c2 s2 c3 s3)
+template <bool INV>
+__device__ __forceinline__ void rot3(float2& b, float2& c, float2& d, const float (&e)[6]) {
+  rot<INV>(b, e[0], e[1]);
+  rot<INV>(c, e[2], e[3]);
+  rot<INV>(d, e[4], e[5]);
+}
+
 // The row transforms (stages A..C) of all DIM2 rows, in place.  Entry: work holds the rows in natural order,
 // preceded by a __syncthreads() issued by the caller.  Exit: rows transformed, __syncthreads() issued.
+// An index j == 0 into the twiddle table means the reference multiplies nothing (kept: x * 1 + y * 0 would turn a
+// -0 into +0).
 template <int DIM2, bool INV>
-__device__ __forceinline__ void rows_1024(float2* __restrict__ work, const float4* __restrict__ eff8) {
+__device__ __forceinline__ void rows_1024(float2* __restrict__ work, const RowTw tw) {
   const int tid = threadIdx.x;
   const int r = tid >> 6, g = tid & 63;
   float2* row = work + r * kRowStride;
   float2 v[16];
+  float e[6];
   {
     // digit-reversed read: butterfly b = 4g + q reads r3(g) + 64 q + 256 i
     const int r3 = ((g & 3) << 4) | (g & 12) | (g >> 4);
 #pragma unroll
     for (int t = 0; t < 16; ++t) v[t] = row[phys(r3 + 64 * t)];
     __syncthreads();
-    stage_a<INV>(v, eff8);
+    float2 y[16];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) row[phys(16 * g + e)] = v[e];
+    for (int q = 0; q < 4; ++q) {
+      float2 a = v[q], b = v[q + 4], c = v[q + 8], d = v[q + 12];
+      bfly<INV, !INV>(a, b, c, d);
+      y[4 * q + 0] = a, y[4 * q + 1] = b, y[4 * q + 2] = c, y[4 * q + 3] = d;
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      float2 a = y[m], b = y[m + 4], c = y[m + 8], d = y[m + 12];
+      if (m) {
+#pragma unroll
+        for (int f = 0; f < 6; ++f) e[f] = tw.a[6 * (m - 1) + f];
+        rot3<INV>(b, c, d, e);
+      }
+      bfly<INV, false>(a, b, c, d);
+      v[m] = a, v[m + 4] = b, v[m + 8] = c, v[m + 12] = d;
+    }
+#pragma unroll
+    for (int t = 0; t < 16; ++t) row[phys(16 * g + t)] = v[t];
     __syncthreads();
   }
   {
-    const int base = 256 * (g >> 4) + (g & 15);
+    const int mm = g & 15;
+    const int base = 256 * (g >> 4) + mm;
 #pragma unroll
     for (int t = 0; t < 16; ++t) v[t] = row[phys(base + 16 * t)];
-    stage_b<INV>(v, eff8, g & 15);
+    if (mm) {
+#pragma unroll
+      for (int f = 0; f < 6; ++f) e[f] = tw.b[f * 16 + mm];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) rot3<INV>(v[4 * q + 1], v[4 * q + 2], v[4 * q + 3], e);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bfly<INV, false>(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      if (a || mm) {
+#pragma unroll
+        for (int f = 0; f < 6; ++f) e[f] = tw.b[((1 + a) * 6 + f) * 16 + mm];
+        rot3<INV>(v[a + 4], v[a + 8], v[a + 12], e);
+      }
+      bfly<INV, false>(v[a], v[a + 4], v[a + 8], v[a + 12]);
+    }
 #pragma unroll
     for (int t = 0; t < 16; ++t) row[phys(base + 16 * t)] = v[t];
     __syncthreads();
+  }
+  constexpr bool kSameM = (64 * DIM2) % 256 == 0;  // the thread's four pass-4 butterflies share one twiddle
+  if (kSameM) {
+#pragma unroll
+    for (int f = 0; f < 6; ++f) e[f] = tw.c[f * 256 + (tid & 255)];
   }
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
@@ -206,21 +290,28 @@ __device__ __forceinline__ void rows_1024(float2* __restrict__ work, const float
     float2* rw = work + (w >> 8) * kRowStride;
     const int m = w & 255;
     float2 a = rw[phys(m)], b = rw[phys(m + 256)], c = rw[phys(m + 512)], d = rw[phys(m + 768)];
-    bfly_tw<INV>(a, b, c, d, eff8, m);
+    if (m) {
+      if (!kSameM) {
+#pragma unroll
+        for (int f = 0; f < 6; ++f) e[f] = tw.c[f * 256 + m];
+      }
+      rot3<INV>(b, c, d, e);
+    }
+    bfly<INV, false>(a, b, c, d);
     rw[phys(m)] = a, rw[phys(m + 256)] = b, rw[phys(m + 512)] = c, rw[phys(m + 768)] = d;
   }
   __syncthreads();
 }
 
-// Column i of the transformed rows: inter-stage twiddle (mix[j * 1024 + i] = (cos, sin) of 2 pi i j / N)
-// and the DIM2-point transform.  Output k = j * 1024 + i in (xr[j], xi[j]).
+// Column i of the transformed rows: inter-stage twiddle (mix[j * 1024 + i] = (cos, sin) of 2 pi i j / N, staged in
+// shared memory by the caller) and the DIM2-point transform.  Output k = j * 1024 + i in (xr[j], xi[j]).
 template <int DIM2, bool INV>
 __device__ __forceinline__ void column(const float2* __restrict__ work, const float2* __restrict__ mix, int i,
                                        float (&xr)[DIM2], float (&xi)[DIM2]) {
 #pragma unroll
   for (int j = 0; j < DIM2; ++j) {
     const float2 v = work[j * kRowStride + phys(i)];
-    const float2 cs = __ldg(mix + j * 1024 + i);
+    const float2 cs = mix[j * 1024 + i];
     if (INV) {
       xr[j] = fsub(fmul(v.x, cs.x), fmul(v.y, cs.y));
       xi[j] = fadd(fmul(v.x, cs.y), fmul(v.y, cs.x));

@@ -124,12 +124,19 @@ __global__ void __launch_bounds__(kWarps * 32) format_conv_kernel(const __grid_c
   // per (output, ERB band) chains owned by this thread: smoothed energies carried in registers across slots
   constexpr int kChains = 4;  // ceil(24 * 58 / 384)
   float tprev[kChains], rprev[kChains];
+  // Chain j of the CTA is (erb, co) = (j / n_out, j % n_out): band-major, so the 32 chains of a warp have (nearly) the
+  // same number of bins.  Output-major order put a 1-bin and a 19-bin band into the same warp, and the warp paid
+  // for the longest in every pass over the inputs.
   const int n_chain = P.n_out * kErb;
+  int chain_co[kChains], chain_erb[kChains];
 #pragma unroll
   for (int q = 0; q < kChains; ++q) {
-    const int c = tid + q * blockDim.x;
-    tprev[q] = (c < n_chain) ? st_t[c] : 0.0f;
-    rprev[q] = (c < n_chain) ? st_r[c] : 0.0f;
+    const int j = tid + q * blockDim.x;
+    chain_erb[q] = (j < n_chain) ? j / P.n_out : -1;
+    chain_co[q] = j - chain_erb[q] * P.n_out;
+    const int c = chain_co[q] * kErb + chain_erb[q];
+    tprev[q] = (j < n_chain) ? st_t[c] : 0.0f;
+    rprev[q] = (j < n_chain) ? st_r[c] : 0.0f;
   }
   __syncthreads();
 
@@ -178,10 +185,9 @@ __global__ void __launch_bounds__(kWarps * 32) format_conv_kernel(const __grid_c
     float tcur[kChains];
 #pragma unroll
     for (int q = 0; q < kChains; ++q) {
-      const int c = tid + q * blockDim.x;
       float t = 0.0f;
-      if (c < n_chain) {
-        const int co = c / kErb, erb = c - co * kErb;
+      if (chain_erb[q] >= 0) {
+        const int co = chain_co[q], erb = chain_erb[q];
         const int* act = P.active + co * (1 + P.n_in);
         const int na = act[0];
         const int k0 = (erb == 0) ? 256 : (erb == 1 ? 1 : c_erb_stop[erb - 1]);
@@ -212,9 +218,8 @@ __global__ void __launch_bounds__(kWarps * 32) format_conv_kernel(const __grid_c
     // ---- 2c. realised energy, smoothing, EQ ----------------------------------------------------------------
 #pragma unroll
     for (int q = 0; q < kChains; ++q) {
-      const int c = tid + q * blockDim.x;
-      if (c < n_chain) {
-        const int co = c / kErb, erb = c - co * kErb;
+      if (chain_erb[q] >= 0) {
+        const int co = chain_co[q], erb = chain_erb[q], c = co * kErb + erb;
         const float* yc = Y + co * 512;
         float r = 0.0f;
         if (erb == 0) r = fmul(yc[0], yc[0]);
@@ -272,8 +277,8 @@ __global__ void __launch_bounds__(kWarps * 32) format_conv_kernel(const __grid_c
   for (int i = tid; i < P.n_out * 256; i += blockDim.x) st_out[i] = outprev[i];
 #pragma unroll
   for (int q = 0; q < kChains; ++q) {
-    const int c = tid + q * blockDim.x;
-    if (c < n_chain) st_t[c] = tprev[q], st_r[c] = rprev[q];
+    const int c = chain_co[q] * kErb + chain_erb[q];
+    if (chain_erb[q] >= 0) st_t[c] = tprev[q], st_r[c] = rprev[q];
   }
 }
 
