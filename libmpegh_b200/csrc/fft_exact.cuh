@@ -82,47 +82,6 @@ __device__ __forceinline__ void bfly(float2& a, float2& b, float2& c, float2& d)
   d = make_float2(dr, di);
 }
 
-// Twiddled butterfly; j = index into the effective-twiddle table (DeviceTables::eff8), j == 0 means the
-// reference multiplies nothing.
-template <bool INV>
-__device__ __forceinline__ void bfly_tw(float2& a, float2& b, float2& c, float2& d, const float4* __restrict__ eff8,
-                                        int j) {
-  if (j) {
-    const float4 e0 = __ldg(eff8 + 2 * j), e1 = __ldg(eff8 + 2 * j + 1);
-    rot<INV>(b, e0.x, e0.y);
-    rot<INV>(c, e0.z, e0.w);
-    rot<INV>(d, e1.x, e1.y);
-  }
-  bfly<INV, false>(a, b, c, d);
-}
-
-// ---- stage A: passes 0 and 1 on v[t], t = q + 4 i (butterfly q, input i) -> y[16 g + e] in v[e] -----------
-template <bool INV>
-__device__ __forceinline__ void stage_a(float2 (&v)[16], const float4* __restrict__ eff8) {
-  float2 y[16];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    float2 a = v[q], b = v[q + 4], c = v[q + 8], d = v[q + 12];
-    bfly<INV, !INV>(a, b, c, d);
-    y[4 * q + 0] = a, y[4 * q + 1] = b, y[4 * q + 2] = c, y[4 * q + 3] = d;
-  }
-#pragma unroll
-  for (int m = 0; m < 4; ++m) {
-    float2 a = y[m], b = y[m + 4], c = y[m + 8], d = y[m + 12];
-    bfly_tw<INV>(a, b, c, d, eff8, 64 * m);
-    v[m] = a, v[m + 4] = b, v[m + 8] = c, v[m + 12] = d;
-  }
-}
-
-// ---- stage B: passes 2 and 3 on v[t] = y[base + 16 t], t = a + 4 q; mm = base & 15 ------------------------
-template <bool INV>
-__device__ __forceinline__ void stage_b(float2 (&v)[16], const float4* __restrict__ eff8, int mm) {
-#pragma unroll
-  for (int q = 0; q < 4; ++q) bfly_tw<INV>(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3], eff8, 16 * mm);
-#pragma unroll
-  for (int a = 0; a < 4; ++a) bfly_tw<INV>(v[a], v[a + 4], v[a + 8], v[a + 12], eff8, 4 * (mm + 16 * a));
-}
-
 // 8-point column transforms (decoder/impeghd_ifft.c:1118 with its swapped bins 2 and 6 kept,
 // decoder/impeghd_fft.c:1304)
 template <bool INV>
@@ -187,9 +146,10 @@ struct RowTw {
 constexpr int kRowTwFloats = 18 + 480 + 1536;
 
 // Every thread of the CTA calls this; the caller issues the __syncthreads().
-__device__ __forceinline__ RowTw fill_row_tw(float* __restrict__ dst, const float4* __restrict__ eff8) {
+__device__ __forceinline__ RowTw fill_row_tw(float* __restrict__ dst, const float4* __restrict__ eff8,
+                                             int n_floats = kRowTwFloats) {
   const float* eff = reinterpret_cast<const float*>(eff8);  // [256][8]: c1 s1 c2 s2 c3 s3 0 0
-  for (int i = threadIdx.x; i < kRowTwFloats; i += blockDim.x) {
+  for (int i = threadIdx.x; i < n_floats; i += blockDim.x) {  // 498: stages A and B only
     int j, f;
     if (i < 18) {
       j = 64 * (1 + i / 6), f = i % 6;
@@ -214,10 +174,57 @@ __device__ __forceinline__ void rot3(float2& b, float2& c, float2& d, const floa
   rot<INV>(d, e[4], e[5]);
 }
 
-// The row transforms (stages A..C) of all DIM2 rows, in place.  Entry: work holds the rows in natural order,
-// preceded by a __syncthreads() issued by the caller.  Exit: rows transformed, __syncthreads() issued.
+// ---- stage A: passes 0 and 1 on v[t], t = q + 4 i (butterfly q, input i) -> y[16 g + e] in v[e] -----------
 // An index j == 0 into the twiddle table means the reference multiplies nothing (kept: x * 1 + y * 0 would turn a
 // -0 into +0).
+template <bool INV>
+__device__ __forceinline__ void stage_a(float2 (&v)[16], const RowTw tw) {
+  float2 y[16];
+  float e[6];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float2 a = v[q], b = v[q + 4], c = v[q + 8], d = v[q + 12];
+    bfly<INV, !INV>(a, b, c, d);
+    y[4 * q + 0] = a, y[4 * q + 1] = b, y[4 * q + 2] = c, y[4 * q + 3] = d;
+  }
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    float2 a = y[m], b = y[m + 4], c = y[m + 8], d = y[m + 12];
+    if (m) {
+#pragma unroll
+      for (int f = 0; f < 6; ++f) e[f] = tw.a[6 * (m - 1) + f];
+      rot3<INV>(b, c, d, e);
+    }
+    bfly<INV, false>(a, b, c, d);
+    v[m] = a, v[m + 4] = b, v[m + 8] = c, v[m + 12] = d;
+  }
+}
+
+// ---- stage B: passes 2 and 3 on v[t] = y[base + 16 t], t = a + 4 q; mm = base & 15 ------------------------
+template <bool INV>
+__device__ __forceinline__ void stage_b(float2 (&v)[16], const RowTw tw, int mm) {
+  float e[6];
+  if (mm) {
+#pragma unroll
+    for (int f = 0; f < 6; ++f) e[f] = tw.b[f * 16 + mm];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) rot3<INV>(v[4 * q + 1], v[4 * q + 2], v[4 * q + 3], e);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) bfly<INV, false>(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    if (a || mm) {
+#pragma unroll
+      for (int f = 0; f < 6; ++f) e[f] = tw.b[((1 + a) * 6 + f) * 16 + mm];
+      rot3<INV>(v[a + 4], v[a + 8], v[a + 12], e);
+    }
+    bfly<INV, false>(v[a], v[a + 4], v[a + 8], v[a + 12]);
+  }
+}
+
+// The row transforms (stages A..C) of all DIM2 rows, in place.  Entry: work holds the rows in natural order,
+// preceded by a __syncthreads() issued by the caller.  Exit: rows transformed, __syncthreads() issued.
 template <int DIM2, bool INV>
 __device__ __forceinline__ void rows_1024(float2* __restrict__ work, const RowTw tw) {
   const int tid = threadIdx.x;
@@ -231,24 +238,7 @@ __device__ __forceinline__ void rows_1024(float2* __restrict__ work, const RowTw
 #pragma unroll
     for (int t = 0; t < 16; ++t) v[t] = row[phys(r3 + 64 * t)];
     __syncthreads();
-    float2 y[16];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float2 a = v[q], b = v[q + 4], c = v[q + 8], d = v[q + 12];
-      bfly<INV, !INV>(a, b, c, d);
-      y[4 * q + 0] = a, y[4 * q + 1] = b, y[4 * q + 2] = c, y[4 * q + 3] = d;
-    }
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      float2 a = y[m], b = y[m + 4], c = y[m + 8], d = y[m + 12];
-      if (m) {
-#pragma unroll
-        for (int f = 0; f < 6; ++f) e[f] = tw.a[6 * (m - 1) + f];
-        rot3<INV>(b, c, d, e);
-      }
-      bfly<INV, false>(a, b, c, d);
-      v[m] = a, v[m + 4] = b, v[m + 8] = c, v[m + 12] = d;
-    }
+    stage_a<INV>(v, tw);
 #pragma unroll
     for (int t = 0; t < 16; ++t) row[phys(16 * g + t)] = v[t];
     __syncthreads();
@@ -258,23 +248,7 @@ __device__ __forceinline__ void rows_1024(float2* __restrict__ work, const RowTw
     const int base = 256 * (g >> 4) + mm;
 #pragma unroll
     for (int t = 0; t < 16; ++t) v[t] = row[phys(base + 16 * t)];
-    if (mm) {
-#pragma unroll
-      for (int f = 0; f < 6; ++f) e[f] = tw.b[f * 16 + mm];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) rot3<INV>(v[4 * q + 1], v[4 * q + 2], v[4 * q + 3], e);
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) bfly<INV, false>(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      if (a || mm) {
-#pragma unroll
-        for (int f = 0; f < 6; ++f) e[f] = tw.b[((1 + a) * 6 + f) * 16 + mm];
-        rot3<INV>(v[a + 4], v[a + 8], v[a + 12], e);
-      }
-      bfly<INV, false>(v[a], v[a + 4], v[a + 8], v[a + 12]);
-    }
+    stage_b<INV>(v, tw, mm);
 #pragma unroll
     for (int t = 0; t < 16; ++t) row[phys(base + 16 * t)] = v[t];
     __syncthreads();

@@ -31,6 +31,8 @@ constexpr int kMaxFcCh = 24;
 constexpr int kErb = 58;
 constexpr int kWarps = 12;
 constexpr int kBufStride = 544;  // float2: 512 + 512/16 padding
+constexpr int kYStride = 514;    // floats per output spectrum row: the chains of a warp walk rows 514 apart conflict free
+static_assert(kMaxFcCh * kYStride <= 2 * kWarps * kBufStride, "the squares of a batch must fit the transform buffers");
 constexpr float kAlpha = 0.0435f;
 constexpr float kBeta = (1 - kAlpha);
 constexpr float kEps = 1e-35f;
@@ -52,12 +54,12 @@ struct FcParams {
   const float* win;  // [256]
   const float4* eff8;
   const float2* rad2;
-  int n_in, n_out, state_floats;
+  int n_in, n_out, state_floats, max_active;
 };
 
 // 512-point transform of one warp's buffer (natural order in, natural order out).
 template <bool INV>
-__device__ __forceinline__ void fft512_warp(float2* __restrict__ buf, int lane, const float4* __restrict__ eff8,
+__device__ __forceinline__ void fft512_warp(float2* __restrict__ buf, int lane, const RowTw eff8,
                                             const float2* __restrict__ rad2) {
   float2 v[16];
   {
@@ -84,7 +86,7 @@ __device__ __forceinline__ void fft512_warp(float2* __restrict__ buf, int lane, 
     const int i = lane + 32 * u;
     const float2 x0 = buf[phys(i)];
     float2 t = buf[phys(i + 256)];
-    const float2 cs = __ldg(rad2 + i);
+    const float2 cs = rad2[i];
     rot<INV>(t, cs.x, cs.y);
     buf[phys(i + 256)] = make_float2(fsub(x0.x, t.x), fsub(x0.y, t.y));
     buf[phys(i)] = make_float2(fadd(x0.x, t.x), fadd(x0.y, t.y));
@@ -101,9 +103,14 @@ __global__ void __launch_bounds__(kWarps * 32) format_conv_kernel(const __grid_c
   extern __shared__ float smem[];
   float2* work = reinterpret_cast<float2*>(smem);                       // [kWarps][kBufStride]
   float* X = smem + 2 * kWarps * kBufStride;                            // [n_in][512] packed spectra
-  float* Y = X + P.n_in * 512;                                          // [n_out][512]
-  float* outprev = Y + P.n_out * 512;                                   // [n_out][256]
+  float* Y = X + P.n_in * 512;                                          // [n_out][kYStride]
+  float* sq = smem;                                                     // [n_out][kYStride], aliases work (idle in phase 2)
+  float* outprev = Y + P.n_out * kYStride;                              // [n_out][256]
   float* eqs = outprev + P.n_out * 256;                                 // [n_out][58]
+  float* twf = eqs + ((P.n_out * kErb + 1) & ~1);                       // twiddles: stages A, B (498) | rad2 [256] float2
+  float2* rad2_s = reinterpret_cast<float2*>(twf + 500);
+  const RowTw tw = fill_row_tw(twf, P.eff8, 498);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) rad2_s[i] = __ldg(P.rad2 + i);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t s = blockIdx.x;
   const float* x = P.in + s * size_t(P.n_in) * 1024;
@@ -128,12 +135,15 @@ __global__ void __launch_bounds__(kWarps * 32) format_conv_kernel(const __grid_c
   // same number of bins.  Output-major order put a 1-bin and a 19-bin band into the same warp, and the warp paid
   // for the longest in every pass over the inputs.
   const int n_chain = P.n_out * kErb;
-  int chain_co[kChains], chain_erb[kChains];
+  int chain_co[kChains], chain_erb[kChains], chain_na[kChains], chain_k[kChains];  // chain_k = first bin | end << 16
 #pragma unroll
   for (int q = 0; q < kChains; ++q) {
     const int j = tid + q * blockDim.x;
     chain_erb[q] = (j < n_chain) ? j / P.n_out : -1;
     chain_co[q] = j - chain_erb[q] * P.n_out;
+    chain_na[q] = (j < n_chain) ? P.active[chain_co[q] * (1 + P.n_in)] : 0;
+    const int erb = chain_erb[q] < 0 ? 0 : chain_erb[q];
+    chain_k[q] = (erb <= 1 ? 1 : c_erb_stop[erb - 1]) | ((erb == 0 ? 1 : c_erb_stop[erb]) << 16);
     const int c = chain_co[q] * kErb + chain_erb[q];
     tprev[q] = (j < n_chain) ? st_t[c] : 0.0f;
     rprev[q] = (j < n_chain) ? st_r[c] : 0.0f;
@@ -152,7 +162,7 @@ __global__ void __launch_bounds__(kWarps * 32) format_conv_kernel(const __grid_c
         buf[phys(256 + i)] = make_float2(fmul(wr[u], cur[i]), 0.0f);
       }
       __syncwarp();
-      fft512_warp<true>(buf, lane, P.eff8, P.rad2);
+      fft512_warp<true>(buf, lane, tw, rad2_s);
       float2* Xc = reinterpret_cast<float2*>(X + ci * 512);
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
@@ -165,70 +175,65 @@ __global__ void __launch_bounds__(kWarps * 32) format_conv_kernel(const __grid_c
     }
     __syncthreads();
 
-    // ---- 2a. spectrum accumulation per (output, bin); k == 0 carries the (DC, Nyquist) pair ------------
-    for (int item = tid; item < P.n_out * 256; item += blockDim.x) {
-      const int co = item >> 8, k = item & 255;
-      const int* act = P.active + co * (1 + P.n_in);
-      const int na = act[0];
-      float yr = 0.0f, yi = 0.0f;
-      for (int a = 0; a < na; ++a) {
-        const int ci = act[1 + a];
-        const float* d = P.D + (size_t(co) * P.n_in + ci) * 257;
-        const float2 xv = reinterpret_cast<const float2*>(X + ci * 512)[k];
-        const float d0 = __ldg(d + k), d1 = (k == 0) ? __ldg(d + 256) : d0;
-        yr = fadd(fmul(d0, xv.x), yr);
-        yi = fadd(fmul(d1, xv.y), yi);
-      }
-      reinterpret_cast<float2*>(Y + co * 512)[k] = make_float2(yr, yi);
-    }
-    // ---- 2b. target energy chains per (output, ERB band), same order as the reference: inputs outermost
+    // ---- 2a/2b. downmix, one batch per rank a: the a-th active input of every output at once ---------------------
+    // All threads form the terms D * X of the batch (one (output, bin) item each), add them into Y and leave their
+    // squares in `sq`; then the (output, ERB band) chains add the squares in the reference's order (inputs outermost,
+    // bins ascending, re before im).  The chains carry only dependent additions: the products, the table loads and
+    // the spectrum loads are off their critical path.
     float tcur[kChains];
 #pragma unroll
-    for (int q = 0; q < kChains; ++q) {
-      float t = 0.0f;
-      if (chain_erb[q] >= 0) {
-        const int co = chain_co[q], erb = chain_erb[q];
+    for (int q = 0; q < kChains; ++q) tcur[q] = 0.0f;
+    for (int a = 0; a < P.max_active; ++a) {  // max_active >= 1: the first batch also clears Y of outputs without inputs
+      for (int item = tid; item < P.n_out * 256; item += blockDim.x) {
+        const int co = item >> 8, k = item & 255;
         const int* act = P.active + co * (1 + P.n_in);
-        const int na = act[0];
-        const int k0 = (erb == 0) ? 256 : (erb == 1 ? 1 : c_erb_stop[erb - 1]);
-        const int k1 = (erb == 0) ? 256 : c_erb_stop[erb];
-        for (int a = 0; a < na; ++a) {
-          const int ci = act[1 + a];
+        float2* yp = reinterpret_cast<float2*>(Y + co * kYStride) + k;
+        if (a < __ldg(act)) {
+          const int ci = __ldg(act + 1 + a);
           const float* d = P.D + (size_t(co) * P.n_in + ci) * 257;
-          const float* xc = X + ci * 512;
-          if (erb == 0) {
-            const float tmp = fmul(__ldg(d), xc[0]);
-            t = fadd(t, fmul(tmp, tmp));
-          } else if (erb == kErb - 1) {
-            const float tmp = fmul(__ldg(d + 256), xc[1]);
-            t = fadd(t, fmul(tmp, tmp));
-          }
-          for (int k = k0; k < k1; ++k) {
-            const float dk = __ldg(d + k);
-            float tmp = fmul(dk, xc[2 * k]);
-            t = fadd(t, fmul(tmp, tmp));
-            tmp = fmul(dk, xc[2 * k + 1]);
-            t = fadd(t, fmul(tmp, tmp));
-          }
+          const float2 xv = reinterpret_cast<const float2*>(X + ci * 512)[k];
+          const float d0 = __ldg(d + k), d1 = (k == 0) ? __ldg(d + 256) : d0;
+          const float tr = fmul(d0, xv.x), ti = fmul(d1, xv.y);
+          const float2 y = a ? *yp : make_float2(0.0f, 0.0f);
+          *yp = make_float2(fadd(tr, y.x), fadd(ti, y.y));
+          reinterpret_cast<float2*>(sq + co * kYStride)[k] = make_float2(fmul(tr, tr), fmul(ti, ti));
+        } else if (a == 0) {
+          *yp = make_float2(0.0f, 0.0f);
         }
       }
-      tcur[q] = t;
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < kChains; ++q) {
+        if (chain_erb[q] >= 0 && a < chain_na[q]) {
+          const int erb = chain_erb[q];
+          const float* sc = sq + chain_co[q] * kYStride;
+          float t = tcur[q];
+          if (erb == 0) t = fadd(t, sc[0]);                 // DC
+          if (erb == kErb - 1) t = fadd(t, sc[1]);          // Nyquist, ahead of the band's bins
+          const int k0 = (erb == 0) ? 256 : (chain_k[q] & 0xffff), k1 = chain_k[q] >> 16;
+          for (int k = k0; k < k1; ++k) {
+            const float2 v = *reinterpret_cast<const float2*>(sc + 2 * k);
+            t = fadd(fadd(t, v.x), v.y);
+          }
+          tcur[q] = t;
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
     // ---- 2c. realised energy, smoothing, EQ ----------------------------------------------------------------
 #pragma unroll
     for (int q = 0; q < kChains; ++q) {
       if (chain_erb[q] >= 0) {
         const int co = chain_co[q], erb = chain_erb[q], c = co * kErb + erb;
-        const float* yc = Y + co * 512;
+        const float* yc = Y + co * kYStride;
         float r = 0.0f;
         if (erb == 0) r = fmul(yc[0], yc[0]);
         if (erb == kErb - 1) r = fmul(yc[1], yc[1]);
-        const int k0 = (erb <= 1) ? 1 : c_erb_stop[erb - 1];
-        const int k1 = (erb == 0) ? 1 : c_erb_stop[erb];
+        const int k0 = (erb == 0) ? 256 : (chain_k[q] & 0xffff), k1 = chain_k[q] >> 16;
         for (int k = k0; k < k1; ++k) {
-          r = fadd(r, fmul(yc[2 * k], yc[2 * k]));
-          r = fadd(r, fmul(yc[2 * k + 1], yc[2 * k + 1]));
+          const float2 v = *reinterpret_cast<const float2*>(yc + 2 * k);
+          r = fadd(r, fmul(v.x, v.x));
+          r = fadd(r, fmul(v.y, v.y));
         }
         const float tn = fadd(fmul(kAlpha, tcur[q]), fmul(kBeta, tprev[q]));
         const float rn = fadd(fmul(kAlpha, r), fmul(kBeta, rprev[q]));
@@ -240,7 +245,7 @@ __global__ void __launch_bounds__(kWarps * 32) format_conv_kernel(const __grid_c
 
     // ---- 3. output transforms + overlap-add ----------------------------------------------------------------
     for (int co = warp; co < P.n_out; co += kWarps) {
-      const float2* Yc = reinterpret_cast<const float2*>(Y + co * 512);
+      const float2* Yc = reinterpret_cast<const float2*>(Y + co * kYStride);
       const float* eq = eqs + co * kErb;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
@@ -257,15 +262,15 @@ __global__ void __launch_bounds__(kWarps * 32) format_conv_kernel(const __grid_c
         }
       }
       __syncwarp();
-      fft512_warp<false>(buf, lane, P.eff8, P.rad2);
+      fft512_warp<false>(buf, lane, tw, rad2_s);
       float* o = yo + size_t(co) * 1024 + slot * 256;
       float* op = outprev + co * 256;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int i = lane + 32 * u;
-        const float a = __fdiv_rn(buf[phys(i)].x, 512.0f);
+        const float a = fmul(buf[phys(i)].x, 0.001953125f);  // == x / 512 bit for bit (power of two)
         __stcs(o + i, fadd(fmul(a, wv[u]), fmul(op[i], wr[u])));
-        op[i] = __fdiv_rn(buf[phys(256 + i)].x, 512.0f);
+        op[i] = fmul(buf[phys(256 + i)].x, 0.001953125f);
       }
       __syncwarp();
     }
@@ -289,7 +294,7 @@ using namespace mpeghb200;
 
 struct mpeghb200_format_conv {
   mpeghb200_ctx* ctx = nullptr;
-  int n_in = 0, n_out = 0;
+  int n_in = 0, n_out = 0, max_active = 0;
   float* d_D = nullptr;
   int* d_active = nullptr;
   float* d_win = nullptr;
@@ -313,6 +318,7 @@ mpeghb200_status mpeghb200_format_conv_create(mpeghb200_ctx* ctx, int n_in, int 
     for (int i = 0; i < n_in; ++i)
       if (dmx[(size_t(o) * n_in + i) * 257] != 0.0f) active[size_t(o) * (1 + n_in) + 1 + n++] = i;
     active[size_t(o) * (1 + n_in)] = n;
+    if (n > h->max_active) h->max_active = n;
   }
   static bool erb_table_done[64] = {};
   cudaError_t e = cudaSuccess;
@@ -364,9 +370,9 @@ mpeghb200_status mpeghb200_format_conv_dev(mpeghb200_ctx* ctx, const mpeghb200_f
   FcParams P{};
   P.in = d_in, P.out = d_out, P.state = d_state, P.D = h->d_D, P.active = h->d_active, P.win = h->d_win;
   P.eff8 = ctx->tables.eff8, P.rad2 = ctx->tables.rad2_512;
-  P.n_in = h->n_in, P.n_out = h->n_out, P.state_floats = int(mpeghb200_format_conv_state_floats(h));
+  P.n_in = h->n_in, P.n_out = h->n_out, P.max_active = h->max_active > 0 ? h->max_active : 1, P.state_floats = int(mpeghb200_format_conv_state_floats(h));
   const size_t smem = sizeof(float) * (size_t(2) * kWarps * kBufStride + size_t(h->n_in) * 512 +
-                                       size_t(h->n_out) * (512 + 256 + kErb));
+                                       size_t(h->n_out) * (kYStride + 256 + kErb) + 2 + 500 + 512);
   MB_CUDA(ctx, cudaFuncSetAttribute(format_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   format_conv_kernel<<<n_streams, kWarps * 32, smem, static_cast<cudaStream_t>(cuda_stream)>>>(P);
   ctx->launches.fetch_add(1);
