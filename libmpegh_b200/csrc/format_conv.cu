@@ -107,10 +107,11 @@ __global__ void __launch_bounds__(kWarps * 32) format_conv_kernel(const __grid_c
   float* sq = smem;                                                     // [n_out][kYStride], aliases work (idle in phase 2)
   float* outprev = Y + P.n_out * kYStride;                              // [n_out][256]
   float* eqs = outprev + P.n_out * 256;                                 // [n_out][58]
-  float* twf = eqs + ((P.n_out * kErb + 1) & ~1);                       // twiddles: stages A, B (498) | rad2 [256] float2
+  unsigned char* erb_s = reinterpret_cast<unsigned char*>(eqs + ((P.n_out * kErb + 1) & ~1));  // [256] band of a bin
+  float* twf = eqs + ((P.n_out * kErb + 1) & ~1) + 64;                       // twiddles: stages A, B (498) | rad2 [256] float2
   float2* rad2_s = reinterpret_cast<float2*>(twf + 500);
   const RowTw tw = fill_row_tw(twf, P.eff8, 498);
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) rad2_s[i] = __ldg(P.rad2 + i);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) rad2_s[i] = __ldg(P.rad2 + i), erb_s[i] = c_erb_of_bin[i];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t s = blockIdx.x;
   const float* x = P.in + s * size_t(P.n_in) * 1024;
@@ -184,21 +185,31 @@ __global__ void __launch_bounds__(kWarps * 32) format_conv_kernel(const __grid_c
 #pragma unroll
     for (int q = 0; q < kChains; ++q) tcur[q] = 0.0f;
     for (int a = 0; a < P.max_active; ++a) {  // max_active >= 1: the first batch also clears Y of outputs without inputs
-      for (int item = tid; item < P.n_out * 256; item += blockDim.x) {
-        const int co = item >> 8, k = item & 255;
+      // a warp takes whole outputs: which input, which table row are warp-uniform, the lane's 8 bins k = lane + 32 u
+      for (int co = warp; co < P.n_out; co += kWarps) {
         const int* act = P.active + co * (1 + P.n_in);
-        float2* yp = reinterpret_cast<float2*>(Y + co * kYStride) + k;
+        float2* yp = reinterpret_cast<float2*>(Y + co * kYStride) + lane;
         if (a < __ldg(act)) {
           const int ci = __ldg(act + 1 + a);
-          const float* d = P.D + (size_t(co) * P.n_in + ci) * 257;
-          const float2 xv = reinterpret_cast<const float2*>(X + ci * 512)[k];
-          const float d0 = __ldg(d + k), d1 = (k == 0) ? __ldg(d + 256) : d0;
-          const float tr = fmul(d0, xv.x), ti = fmul(d1, xv.y);
-          const float2 y = a ? *yp : make_float2(0.0f, 0.0f);
-          *yp = make_float2(fadd(tr, y.x), fadd(ti, y.y));
-          reinterpret_cast<float2*>(sq + co * kYStride)[k] = make_float2(fmul(tr, tr), fmul(ti, ti));
+          const float* d = P.D + (size_t(co) * P.n_in + ci) * 257 + lane;
+          const float2* xp = reinterpret_cast<const float2*>(X + ci * 512) + lane;
+          float2* sp = reinterpret_cast<float2*>(sq + co * kYStride) + lane;
+          float dk[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) dk[u] = __ldg(d + 32 * u);
+          const float d_nyq = __ldg(d + 256 - lane);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float2 xv = xp[32 * u];
+            const float d1 = (u == 0 && lane == 0) ? d_nyq : dk[u];
+            const float tr = fmul(dk[u], xv.x), ti = fmul(d1, xv.y);
+            const float2 y = a ? yp[32 * u] : make_float2(0.0f, 0.0f);
+            yp[32 * u] = make_float2(fadd(tr, y.x), fadd(ti, y.y));
+            sp[32 * u] = make_float2(fmul(tr, tr), fmul(ti, ti));
+          }
         } else if (a == 0) {
-          *yp = make_float2(0.0f, 0.0f);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) yp[32 * u] = make_float2(0.0f, 0.0f);
         }
       }
       __syncthreads();
@@ -255,7 +266,7 @@ __global__ void __launch_bounds__(kWarps * 32) format_conv_kernel(const __grid_c
           buf[phys(0)] = make_float2(fmul(v.x, eq[0]), 0.0f);
           buf[phys(256)] = make_float2(fmul(v.y, eq[kErb - 1]), 0.0f);
         } else {
-          const float e = eq[c_erb_of_bin[k]];
+          const float e = eq[erb_s[k]];
           const float re = fmul(v.x, e), im = fmul(e, v.y);
           buf[phys(k)] = make_float2(re, im);
           buf[phys(512 - k)] = make_float2(re, -im);
@@ -372,7 +383,7 @@ mpeghb200_status mpeghb200_format_conv_dev(mpeghb200_ctx* ctx, const mpeghb200_f
   P.eff8 = ctx->tables.eff8, P.rad2 = ctx->tables.rad2_512;
   P.n_in = h->n_in, P.n_out = h->n_out, P.max_active = h->max_active > 0 ? h->max_active : 1, P.state_floats = int(mpeghb200_format_conv_state_floats(h));
   const size_t smem = sizeof(float) * (size_t(2) * kWarps * kBufStride + size_t(h->n_in) * 512 +
-                                       size_t(h->n_out) * (kYStride + 256 + kErb) + 2 + 500 + 512);
+                                       size_t(h->n_out) * (kYStride + 256 + kErb) + 2 + 64 + 500 + 512);
   MB_CUDA(ctx, cudaFuncSetAttribute(format_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   format_conv_kernel<<<n_streams, kWarps * 32, smem, static_cast<cudaStream_t>(cuda_stream)>>>(P);
   ctx->launches.fetch_add(1);
