@@ -47,6 +47,7 @@ struct BinParams {
   const float4* eff8;
   const float2* mix;    // [DIM2][1024]
   int n_in, n_blocks;
+  int in_vec;  // input rows are 16-byte aligned
 };
 
 template <int DIM2>
@@ -59,9 +60,22 @@ struct Geo {
   static constexpr int NB = COLS * HB;       // bins per thread (= 8)
   // shared memory: transform rows | row twiddles (fft_exact.cuh RowTw) | inter-stage twiddles [DIM2][1024]
   static constexpr int kWorkF2 = DIM2 * kRowStride;
-  static constexpr int kTwF2 = (kRowTwFloats + 1) / 2;
-  static constexpr size_t kSmem = size_t(kWorkF2 + kTwF2 + DIM2 * 1024) * sizeof(float2);
+  static constexpr int kTwF2 = (kRowTwFloats + 3) / 4 * 2;  // even: what follows stays 16-byte aligned
+  static constexpr int kTabF2 = kWorkF2 + kTwF2 + DIM2 * 1024;
+  // block kernel only: | filter spectra of the current input, both ears [2][N] | samples of the next input [B]
+  static constexpr size_t kSmemTab = size_t(kTabF2) * sizeof(float2);
+  static constexpr size_t kSmem = kSmemTab + size_t(2 * N + B) * sizeof(float);
 };
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(unsigned(__cvta_generic_to_shared(smem_dst))), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(unsigned(__cvta_generic_to_shared(smem_dst))), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // Tables every CTA stages once; returns the row twiddles, *mix_s = the staged inter-stage twiddles.
 template <int DIM2>
@@ -86,10 +100,12 @@ __device__ __forceinline__ float2 ld_stream(const float2* p) {
 // Forward transform of one real, zero-padded block.  src(n) returns sample n < n_valid (scaled).  On return
 // X[b] = (Re X[k], -Im X[k]) for the thread's bins k = (b % HB) * 1024 + tid + NT * (b / HB); for thread 0
 // X[0] = (Re X[0], Re X[N/2]); im0/imn = Im X[0], Im X[N/2] (thread 0 only).
-template <int DIM2, typename Src>
+// prefetch() runs once every thread has staged its samples: the place to start asynchronous copies into buffers the
+// previous block of work was still reading; they are complete and visible to the CTA on return.
+template <int DIM2, typename Src, typename Prefetch>
 __device__ __forceinline__ void forward_real(float2* __restrict__ work, const RowTw tw,
                                              const float2* __restrict__ mix, Src src, int n_valid,
-                                             float2 (&X)[8], float& im0, float& imn) {
+                                             float2 (&X)[8], float& im0, float& imn, Prefetch prefetch) {
   using G = Geo<DIM2>;
   const int tid = threadIdx.x;
 #pragma unroll
@@ -99,6 +115,7 @@ __device__ __forceinline__ void forward_real(float2* __restrict__ work, const Ro
     work[(n % DIM2) * kRowStride + phys(n / DIM2)] = make_float2(x, 0.0f);
   }
   __syncthreads();
+  prefetch();
   rows_1024<DIM2, true>(work, tw);
 #pragma unroll
   for (int c = 0; c < G::COLS; ++c) {
@@ -113,6 +130,7 @@ __device__ __forceinline__ void forward_real(float2* __restrict__ work, const Ro
       imn = xi[G::HB];
     }
   }
+  cp_async_wait_all();
   __syncthreads();  // the caller may overwrite work
 }
 
@@ -155,21 +173,43 @@ __global__ void __launch_bounds__(64 * DIM2) binaural_block_kernel(const __grid_
   for (int b = 0; b < G::NB; ++b) acc[0][b] = acc[1][b] = dmx[b] = make_float2(0.0f, 0.0f);
   float im0 = 0.0f, imn = 0.0f;
 
-  for (int inp = 0; inp < P.n_in; ++inp) {
+  // The filter spectra of an input (both ears, 2 N floats from DRAM when every stream has its own set) and the samples
+  // of the next input are copied into shared memory asynchronously while the input is being transformed.
+  float* hbuf = reinterpret_cast<float*>(work + G::kTabF2);
+  float* xs = hbuf + 2 * G::N;
+  auto fetch_input = [&](int inp) {
     const float* x = P.in + s * P.in_stream_stride + inp * P.in_chan_stride;
-    float2 X[G::NB];
-    forward_real<DIM2>(
-        work, tw, mix_s,
-        [&](int n) { return fmul(__ldcs(x + (n >> 10) * P.in_chunk_stride + (n & 1023)), P.in_scale); }, G::B, X,
-        im0, imn);
-    const int l0 = dlen[inp], l1 = dlen[P.n_in + inp];
+    if (P.in_vec) {
+      for (int n = 4 * tid; n < G::B; n += 4 * G::NT) cp_async16(xs + n, x + (n >> 10) * P.in_chunk_stride + (n & 1023));
+    } else {
+      for (int n = tid; n < G::B; n += G::NT) cp_async4(xs + n, x + (n >> 10) * P.in_chunk_stride + (n & 1023));
+    }
+  };
+  auto fetch_filters = [&](int inp) {
     const float* h0 = hd + size_t(inp) * G::N;
     const float* h1 = hd + size_t(P.n_in + inp) * G::N;
+    for (int n = 4 * tid; n < G::N; n += 4 * G::NT) {
+      cp_async16(hbuf + n, h0 + n);
+      cp_async16(hbuf + G::N + n, h1 + n);
+    }
+  };
+  fetch_input(0);
+  cp_async_wait_all();
+  __syncthreads();
+
+  for (int inp = 0; inp < P.n_in; ++inp) {
+    float2 X[G::NB];
+    forward_real<DIM2>(
+        work, tw, mix_s, [&](int n) { return fmul(xs[n], P.in_scale); }, G::B, X, im0, imn, [&]() {
+          fetch_filters(inp);
+          if (inp + 1 < P.n_in) fetch_input(inp + 1);
+        });
+    const int l0 = dlen[inp], l1 = dlen[P.n_in + inp];
     const float w = wgt[inp];
 #pragma unroll
     for (int b = 0; b < G::NB; ++b) {
-      const float2 a0 = ld_stream(reinterpret_cast<const float2*>(h0) + kbin[b]);
-      const float2 a1 = ld_stream(reinterpret_cast<const float2*>(h1) + kbin[b]);
+      const float2 a0 = reinterpret_cast<const float2*>(hbuf)[kbin[b]];
+      const float2 a1 = reinterpret_cast<const float2*>(hbuf + G::N)[kbin[b]];
       mac_perm(acc[0][b], a0, X[b], kbin[b], l0);
       mac_perm(acc[1][b], a1, X[b], kbin[b], l1);
       if (P.n_blocks) {
@@ -260,7 +300,7 @@ __global__ void __launch_bounds__(64 * DIM2)
   float im0, imn;
   const float2* mix_s;
   const RowTw tw = stage_tables<DIM2>(work, eff8, mix, &mix_s);
-  forward_real<DIM2>(work, tw, mix_s, [&](int n) { return t[n]; }, len < G::B ? len : G::B, X, im0, imn);
+  forward_real<DIM2>(work, tw, mix_s, [&](int n) { return t[n]; }, len < G::B ? len : G::B, X, im0, imn, []() {});
   float2* o = reinterpret_cast<float2*>(spec + size_t(blockIdx.x) * G::N);
 #pragma unroll
   for (int b = 0; b < G::NB; ++b) o[(b % G::HB) * 1024 + threadIdx.x + G::NT * (b / G::HB)] = X[b];
@@ -289,9 +329,9 @@ template <int DIM2>
 static cudaError_t run_spectra(const mpeghb200_binaural* b, const float* d_taps, int n_filters, float* d_spec) {
   using G = Geo<DIM2>;
   cudaError_t e = cudaFuncSetAttribute(binaural_spectrum_kernel<DIM2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       int(G::kSmem));
+                                       int(G::kSmemTab));
   if (e != cudaSuccess) return e;
-  binaural_spectrum_kernel<DIM2><<<n_filters, G::NT, G::kSmem>>>(d_taps, b->len, d_spec, b->ctx->tables.eff8, b->d_mix);
+  binaural_spectrum_kernel<DIM2><<<n_filters, G::NT, G::kSmemTab>>>(d_taps, b->len, d_spec, b->ctx->tables.eff8, b->d_mix);
   return cudaGetLastError();
 }
 
@@ -422,6 +462,7 @@ mpeghb200_status mpeghb200_binaural_block_dev(mpeghb200_ctx* ctx, const mpeghb20
     P.in_stream_stride = b->n_in * 1024LL, P.in_chan_stride = 1024, P.in_chunk_stride = (long long)n_streams * b->n_in * 1024;
   }
   P.in_scale = in_scale, P.out_scale = out_scale;
+  P.in_vec = (reinterpret_cast<uintptr_t>(d_in) & 15) == 0;
   P.out = d_out, P.state = d_state, P.state_floats = (long long)mpeghb200_binaural_state_floats(b);
   P.set = d_filter_set;
   P.h_direct = b->d_hdirect, P.h_diffuse = b->d_hdiffuse, P.direct_len = b->d_dlen, P.diffuse_len = b->d_flen;
