@@ -25,58 +25,90 @@ struct RsParams {
   float f_up[60], f_down[60];
 };
 
+// UP / DOWN at compile time: the tap loops unroll completely, the filter taps become constant-bank operands of the
+// multiplies, and a thread takes four consecutive input samples (two consecutive decimator outputs) so that the
+// overlapping windows are loaded once, as 16-byte shared-memory loads, instead of once per tap.
+template <int UP, int DOWN>
 __global__ void __launch_bounds__(256) resample_kernel(const __grid_constant__ RsParams P) {
-  __shared__ float xin[32 + kIn];
-  __shared__ float poly[kIn][3];
-  __shared__ float yh[59 + 3 * kIn];
-  const int tid = threadIdx.x, up = P.up;
-  const int hist = 59 / up, taps = 60 / up;
+  constexpr int hist = 59 / UP, taps = 60 / UP;
+  constexpr int n_out = kIn * UP / DOWN;
+  __shared__ __align__(16) float xin[32 + kIn + 4];
+  __shared__ __align__(16) float poly[UP][kIn];  // branch-major: a thread stores its four samples of a branch as one float4
+  __shared__ __align__(16) float yh[DOWN == 2 ? 59 + UP * kIn + 5 : 4];
+  const int tid = threadIdx.x;
   const size_t u = blockIdx.x;
   const float* x = P.in + u * kIn;
   float* st = P.state + u * kStateFloats;
-  const int n_out = kIn * up / P.down;
   float* y = P.out + u * n_out;
 
   for (int i = tid; i < hist; i += 256) xin[i] = st[i];
   for (int i = tid; i < kIn; i += 256) xin[hist + i] = __ldcs(x + i);
-  if (P.down == 2)
+  if (DOWN == 2)
     for (int i = tid; i < 59; i += 256) yh[i] = st[32 + i];
   __syncthreads();
-  for (int n = tid; n < kIn; n += 256) {
-    float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f;
-    for (int k = 0; k < taps; ++k) {
-      const float v = xin[n + k];
-      p0 = fadd(p0, fmul(v, P.f_up[k * up]));
-      p1 = fadd(p1, fmul(v, P.f_up[k * up + 1]));
-      if (up == 3) p2 = fadd(p2, fmul(v, P.f_up[k * up + 2]));
+  {
+    constexpr int kW = (taps + 3 + 3) / 4;  // float4 loads covering samples n0 .. n0 + taps + 2
+    float w[4 * kW];
+    const int n0 = 4 * tid;
+#pragma unroll
+    for (int q = 0; q < kW; ++q) {
+      const float4 v = *reinterpret_cast<const float4*>(xin + n0 + 4 * q);
+      w[4 * q] = v.x, w[4 * q + 1] = v.y, w[4 * q + 2] = v.z, w[4 * q + 3] = v.w;
     }
-    poly[n][0] = p0, poly[n][1] = p1, poly[n][2] = p2;
+    float pb[UP][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int b = 0; b < UP; ++b) pb[b][j] = 0.0f;
+#pragma unroll
+      for (int k = 0; k < taps; ++k)
+#pragma unroll
+        for (int b = 0; b < UP; ++b) pb[b][j] = fadd(pb[b][j], fmul(w[j + k], P.f_up[k * UP + b]));
+    }
+#pragma unroll
+    for (int b = 0; b < UP; ++b)
+      *reinterpret_cast<float4*>(&poly[b][n0]) = make_float4(pb[b][0], pb[b][1], pb[b][2], pb[b][3]);
   }
   __syncthreads();
-  float* o = (P.down == 2) ? yh + 59 : y;
+  float* o = (DOWN == 2) ? yh + 59 : y;
   for (int n = tid; n < kIn; n += 256) {
     float mem[2];
-    mem[0] = n ? poly[n - 1][1] : st[92];
-    mem[1] = n ? poly[n - 1][2] : st[93];
-    for (int p = 0; p < up; ++p) {
+    mem[0] = n ? poly[1][n - 1] : st[92];
+    mem[1] = (UP == 3) ? (n ? poly[UP - 1][n - 1] : st[93]) : 0.0f;
+#pragma unroll
+    for (int p = 0; p < UP; ++p) {
       float v = 0.0f;
-      for (int q = p; q < up - 1; ++q) v = fadd(v, mem[q]);
-      for (int q = 0; q <= p; ++q) v = fadd(v, poly[n][q]);
-      o[n * up + p] = v;
+#pragma unroll
+      for (int q = p; q < UP - 1; ++q) v = fadd(v, mem[q]);
+#pragma unroll
+      for (int q = 0; q <= p; ++q) v = fadd(v, poly[q][n]);
+      o[n * UP + p] = v;
     }
   }
   __syncthreads();
-  if (P.down == 2) {
-    for (int n = tid; n < n_out; n += 256) {
-      float mac = 0.0f;
-#pragma unroll 4
-      for (int k = 0; k < 60; ++k) mac = fadd(mac, fmul(yh[2 * n + k], P.f_down[k]));
-      __stcs(y + n, mac);
+  if (DOWN == 2) {
+    for (int m = tid; m < n_out / 2; m += 256) {  // outputs 2m and 2m + 1 read yh[4m .. 4m + 61]
+      float w[64];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(yh + 4 * m + 4 * q);
+        w[4 * q] = v.x, w[4 * q + 1] = v.y, w[4 * q + 2] = v.z, w[4 * q + 3] = v.w;
+      }
+      float mac0 = 0.0f, mac1 = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 60; ++k) {
+        mac0 = fadd(mac0, fmul(w[k], P.f_down[k]));
+        mac1 = fadd(mac1, fmul(w[2 + k], P.f_down[k]));
+      }
+      __stcs(reinterpret_cast<float2*>(y) + m, make_float2(mac0, mac1));
     }
-    for (int i = tid; i < 59; i += 256) st[32 + i] = yh[kIn * up + i];
+    for (int i = tid; i < 59; i += 256) st[32 + i] = yh[kIn * UP + i];
   }
   for (int i = tid; i < hist; i += 256) st[i] = xin[kIn + i];
-  if (tid == 0) st[92] = poly[kIn - 1][1], st[93] = poly[kIn - 1][2];
+  if (tid == 0) {
+    st[92] = poly[1][kIn - 1];
+    st[93] = (UP == 3) ? poly[UP - 1][kIn - 1] : 0.0f;
+  }
 }
 
 }  // namespace
@@ -121,7 +153,13 @@ mpeghb200_status mpeghb200_resample_dev(mpeghb200_ctx* ctx, const mpeghb200_resa
   MB_CUDA(ctx, cudaSetDevice(ctx->device));
   RsParams P = r->P;
   P.in = d_in, P.out = d_out, P.state = d_state;
-  resample_kernel<<<n_units, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(P);
+  const cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  if (P.up == 2)
+    resample_kernel<2, 1><<<n_units, 256, 0, stream>>>(P);
+  else if (P.down == 1)
+    resample_kernel<3, 1><<<n_units, 256, 0, stream>>>(P);
+  else
+    resample_kernel<3, 2><<<n_units, 256, 0, stream>>>(P);
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   return MPEGHB200_OK;
