@@ -57,10 +57,11 @@ struct FcParams {
   int n_in, n_out, state_floats, max_active;
 };
 
-// 512-point transform of one warp's buffer (natural order in, natural order out).
+// 512-point transform of one warp's buffer, natural order in, up to its last pass: what is left is the radix-2 pass
+// out[i] = buf[i] + w_i buf[i + 256], out[i + 256] = buf[i] - w_i buf[i + 256] (w_i = rad2[i]), which the two callers
+// fuse with what they do to the result (they need half of it, or only its real part).
 template <bool INV>
-__device__ __forceinline__ void fft512_warp(float2* __restrict__ buf, int lane, const RowTw eff8,
-                                            const float2* __restrict__ rad2) {
+__device__ __forceinline__ void fft512_warp(float2* __restrict__ buf, int lane, const RowTw eff8) {
   float2 v[16];
   {
     const int r3 = 8 * (lane & 3) + 2 * ((lane >> 2) & 3) + (lane >> 4);
@@ -81,17 +82,6 @@ __device__ __forceinline__ void fft512_warp(float2* __restrict__ buf, int lane, 
     for (int t = 0; t < 16; ++t) buf[phys(base + 16 * t)] = v[t];
     __syncwarp();
   }
-#pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const int i = lane + 32 * u;
-    const float2 x0 = buf[phys(i)];
-    float2 t = buf[phys(i + 256)];
-    const float2 cs = rad2[i];
-    rot<INV>(t, cs.x, cs.y);
-    buf[phys(i + 256)] = make_float2(fsub(x0.x, t.x), fsub(x0.y, t.y));
-    buf[phys(i)] = make_float2(fadd(x0.x, t.x), fadd(x0.y, t.y));
-  }
-  __syncwarp();
 }
 
 __device__ __forceinline__ float clip_eq(float t, float r) {
@@ -163,13 +153,17 @@ __global__ void __launch_bounds__(kWarps * 32) format_conv_kernel(const __grid_c
         buf[phys(256 + i)] = make_float2(fmul(wr[u], cur[i]), 0.0f);
       }
       __syncwarp();
-      fft512_warp<true>(buf, lane, tw, rad2_s);
+      fft512_warp<true>(buf, lane, tw);
       float2* Xc = reinterpret_cast<float2*>(X + ci * 512);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < 8; ++u) {  // last pass: bins 0..255, and Re of bin 256 into the imaginary slot of bin 0
         const int k = lane + 32 * u;
-        float2 v = buf[phys(k)];
-        if (k == 0) v.y = buf[phys(256)].x;
+        const float2 x0 = buf[phys(k)];
+        float2 t = buf[phys(k + 256)];
+        const float2 cs = rad2_s[k];
+        rot<true>(t, cs.x, cs.y);
+        float2 v = make_float2(fadd(x0.x, t.x), fadd(x0.y, t.y));
+        if (k == 0) v.y = fsub(x0.x, t.x);
         Xc[k] = v;
       }
       __syncwarp();
@@ -273,15 +267,18 @@ __global__ void __launch_bounds__(kWarps * 32) format_conv_kernel(const __grid_c
         }
       }
       __syncwarp();
-      fft512_warp<false>(buf, lane, tw, rad2_s);
+      fft512_warp<false>(buf, lane, tw);
       float* o = yo + size_t(co) * 1024 + slot * 256;
       float* op = outprev + co * 256;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int i = lane + 32 * u;
-        const float a = fmul(buf[phys(i)].x, 0.001953125f);  // == x / 512 bit for bit (power of two)
+        // last pass, real parts only: Re(w t) = t.x c - t.y s for the e^{-j} family
+        const float2 x0 = buf[phys(i)], t = buf[phys(i + 256)], cs = rad2_s[i];
+        const float tr = fsub(fmul(t.x, cs.x), fmul(t.y, cs.y));
+        const float a = fmul(fadd(x0.x, tr), 0.001953125f);  // == x / 512 bit for bit (power of two)
         __stcs(o + i, fadd(fmul(a, wv[u]), fmul(op[i], wr[u])));
-        op[i] = fmul(buf[phys(256 + i)].x, 0.001953125f);
+        op[i] = fmul(fsub(x0.x, tr), 0.001953125f);
       }
       __syncwarp();
     }
