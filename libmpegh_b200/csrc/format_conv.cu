@@ -61,28 +61,23 @@ struct FcParams {
 // out[i] = buf[i] + w_i buf[i + 256], out[i + 256] = buf[i] - w_i buf[i + 256] (w_i = rad2[i]), which the two callers
 // fuse with what they do to the result (they need half of it, or only its real part).
 template <bool INV>
-__device__ __forceinline__ void fft512_warp(float2* __restrict__ buf, int lane, const RowTw eff8) {
-  float2 v[16];
-  {
-    const int r3 = 8 * (lane & 3) + 2 * ((lane >> 2) & 3) + (lane >> 4);
+__device__ __forceinline__ void fft512_tail(float2 (&v)[16], float2* __restrict__ buf, int lane, const RowTw eff8) {
+  // v[t] = point r3(lane) + 32 t on entry
+  stage_a<INV>(v, eff8);
 #pragma unroll
-    for (int t = 0; t < 16; ++t) v[t] = buf[phys(r3 + 32 * t)];
-    __syncwarp();
-    stage_a<INV>(v, eff8);
+  for (int e = 0; e < 16; ++e) buf[phys(16 * lane + e)] = v[e];
+  __syncwarp();
+  const int base = 256 * (lane >> 4) + (lane & 15);
 #pragma unroll
-    for (int e = 0; e < 16; ++e) buf[phys(16 * lane + e)] = v[e];
-    __syncwarp();
-  }
-  {
-    const int base = 256 * (lane >> 4) + (lane & 15);
+  for (int t = 0; t < 16; ++t) v[t] = buf[phys(base + 16 * t)];
+  stage_b<INV>(v, eff8, lane & 15);
 #pragma unroll
-    for (int t = 0; t < 16; ++t) v[t] = buf[phys(base + 16 * t)];
-    stage_b<INV>(v, eff8, lane & 15);
-#pragma unroll
-    for (int t = 0; t < 16; ++t) buf[phys(base + 16 * t)] = v[t];
-    __syncwarp();
-  }
+  for (int t = 0; t < 16; ++t) buf[phys(base + 16 * t)] = v[t];
+  __syncwarp();
 }
+
+// lane -> its digit-reversed position inside a group of 32 points (the order stage A wants its inputs in)
+__device__ __forceinline__ int rev32(int lane) { return 8 * (lane & 3) + 2 * ((lane >> 2) & 3) + (lane >> 4); }
 
 __device__ __forceinline__ float clip_eq(float t, float r) {
   float eq = __fsqrt_rn(__fdiv_rn(t, fadd(kEps, r)));
@@ -113,12 +108,18 @@ __global__ void __launch_bounds__(kWarps * 32) format_conv_kernel(const __grid_c
   float2* buf = work + warp * kBufStride;
 
   for (int i = tid; i < P.n_out * 256; i += blockDim.x) outprev[i] = st_out[i];
-  float wv[8], wr[8];  // window entries of the lane's sample positions i = lane + 32 u
+  // The lane's sample positions are i = r3 + 32 u, r3 = its digit-reversed lane number: the order in which stage A
+  // of a transform takes its inputs, so the input blocks go from global memory straight into the butterflies (any
+  // permutation inside a group of 32 samples is as coalesced as the identity).
+  const int r3 = rev32(lane);
+  float wv[8], wr[8];  // window entries of those positions
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
-    wv[u] = __ldg(P.win + lane + 32 * u);
-    wr[u] = __ldg(P.win + 255 - lane - 32 * u);
+    wv[u] = __ldg(P.win + r3 + 32 * u);
+    wr[u] = __ldg(P.win + 255 - r3 - 32 * u);
   }
+  if (tid < P.n_in)  // the frame's input rows on their way into L2 while the state is being read
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x + size_t(tid) * 1024), "r"(4096) : "memory");
   // per (output, ERB band) chains owned by this thread: smoothed energies carried in registers across slots
   constexpr int kChains = 4;  // ceil(24 * 58 / 384)
   float tprev[kChains], rprev[kChains];
@@ -146,14 +147,13 @@ __global__ void __launch_bounds__(kWarps * 32) format_conv_kernel(const __grid_c
     for (int ci = warp; ci < P.n_in; ci += kWarps) {
       const float* cur = x + size_t(ci) * 1024 + slot * 256;
       const float* prev = slot ? cur - 256 : st_in + ci * 256;
+      float2 v[16];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const int i = lane + 32 * u;
-        buf[phys(i)] = make_float2(fmul(prev[i], wv[u]), 0.0f);
-        buf[phys(256 + i)] = make_float2(fmul(wr[u], cur[i]), 0.0f);
+        v[u] = make_float2(fmul(prev[r3 + 32 * u], wv[u]), 0.0f);
+        v[8 + u] = make_float2(fmul(wr[u], cur[r3 + 32 * u]), 0.0f);
       }
-      __syncwarp();
-      fft512_warp<true>(buf, lane, tw);
+      fft512_tail<true>(v, buf, lane, tw);
       float2* Xc = reinterpret_cast<float2*>(X + ci * 512);
 #pragma unroll
       for (int u = 0; u < 8; ++u) {  // last pass: bins 0..255, and Re of bin 256 into the imaginary slot of bin 0
@@ -267,12 +267,16 @@ __global__ void __launch_bounds__(kWarps * 32) format_conv_kernel(const __grid_c
         }
       }
       __syncwarp();
-      fft512_warp<false>(buf, lane, tw);
+      float2 v[16];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) v[t] = buf[phys(r3 + 32 * t)];
+      __syncwarp();
+      fft512_tail<false>(v, buf, lane, tw);
       float* o = yo + size_t(co) * 1024 + slot * 256;
       float* op = outprev + co * 256;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const int i = lane + 32 * u;
+        const int i = r3 + 32 * u;
         // last pass, real parts only: Re(w t) = t.x c - t.y s for the e^{-j} family
         const float2 x0 = buf[phys(i)], t = buf[phys(i + 256)], cs = rad2_s[i];
         const float tr = fsub(fmul(t.x, cs.x), fmul(t.y, cs.y));
