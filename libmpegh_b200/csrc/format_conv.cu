@@ -54,7 +54,7 @@ struct FcParams {
   const float* win;  // [256]
   const float4* eff8;
   const float2* rad2;
-  int n_in, n_out, state_floats, max_active;
+  int n_in, n_out, state_floats, max_active, ranks;
 };
 
 // 512-point transform of one warp's buffer, natural order in, up to its last pass: what is left is the radix-2 pass
@@ -178,16 +178,27 @@ __global__ void __launch_bounds__(kWarps * 32) format_conv_kernel(const __grid_c
     float tcur[kChains];
 #pragma unroll
     for (int q = 0; q < kChains; ++q) tcur[q] = 0.0f;
-    for (int a = 0; a < P.max_active; ++a) {  // max_active >= 1: the first batch also clears Y of outputs without inputs
+    // max_active >= 1: the first pass also clears Y of outputs without inputs.  A pass covers `ranks` consecutive
+    // ranks (as many as the squares buffer holds, 2 for 12 outputs): half the barriers.
+    for (int a0 = 0; a0 < P.max_active; a0 += P.ranks) {
       // a warp takes whole outputs: which input, which table row are warp-uniform, the lane's 8 bins k = lane + 32 u
       for (int co = warp; co < P.n_out; co += kWarps) {
         const int* act = P.active + co * (1 + P.n_in);
+        const int na = __ldg(act);
         float2* yp = reinterpret_cast<float2*>(Y + co * kYStride) + lane;
-        if (a < __ldg(act)) {
-          const int ci = __ldg(act + 1 + a);
+        float2 y[8];
+        if (a0 && a0 < na) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) y[u] = yp[32 * u];
+        } else {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) y[u] = make_float2(0.0f, 0.0f);
+        }
+        for (int r = 0; r < P.ranks && a0 + r < na; ++r) {
+          const int ci = __ldg(act + 1 + a0 + r);
           const float* d = P.D + (size_t(co) * P.n_in + ci) * 257 + lane;
           const float2* xp = reinterpret_cast<const float2*>(X + ci * 512) + lane;
-          float2* sp = reinterpret_cast<float2*>(sq + co * kYStride) + lane;
+          float2* sp = reinterpret_cast<float2*>(sq + (r * P.n_out + co) * kYStride) + lane;
           float dk[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) dk[u] = __ldg(d + 32 * u);
@@ -197,28 +208,31 @@ __global__ void __launch_bounds__(kWarps * 32) format_conv_kernel(const __grid_c
             const float2 xv = xp[32 * u];
             const float d1 = (u == 0 && lane == 0) ? d_nyq : dk[u];
             const float tr = fmul(dk[u], xv.x), ti = fmul(d1, xv.y);
-            const float2 y = a ? yp[32 * u] : make_float2(0.0f, 0.0f);
-            yp[32 * u] = make_float2(fadd(tr, y.x), fadd(ti, y.y));
+            y[u] = make_float2(fadd(tr, y[u].x), fadd(ti, y[u].y));
             sp[32 * u] = make_float2(fmul(tr, tr), fmul(ti, ti));
           }
-        } else if (a == 0) {
+        }
+        if (a0 < na || a0 == 0) {
 #pragma unroll
-          for (int u = 0; u < 8; ++u) yp[32 * u] = make_float2(0.0f, 0.0f);
+          for (int u = 0; u < 8; ++u) yp[32 * u] = y[u];
         }
       }
       __syncthreads();
 #pragma unroll
       for (int q = 0; q < kChains; ++q) {
-        if (chain_erb[q] >= 0 && a < chain_na[q]) {
+        if (chain_erb[q] >= 0) {
           const int erb = chain_erb[q];
-          const float* sc = sq + chain_co[q] * kYStride;
           float t = tcur[q];
-          if (erb == 0) t = fadd(t, sc[0]);                 // DC
-          if (erb == kErb - 1) t = fadd(t, sc[1]);          // Nyquist, ahead of the band's bins
-          const int k0 = (erb == 0) ? 256 : (chain_k[q] & 0xffff), k1 = chain_k[q] >> 16;
-          for (int k = k0; k < k1; ++k) {
-            const float2 v = *reinterpret_cast<const float2*>(sc + 2 * k);
-            t = fadd(fadd(t, v.x), v.y);
+          for (int r = 0; r < P.ranks && a0 + r < chain_na[q]; ++r) {
+            const float* sc = sq + (r * P.n_out + chain_co[q]) * kYStride;
+            if (erb == 0) t = fadd(t, sc[0]);                 // DC
+            if (erb == kErb - 1) t = fadd(t, sc[1]);          // Nyquist, ahead of the band's bins
+            const int k0 = (erb == 0) ? 256 : (chain_k[q] & 0xffff), k1 = chain_k[q] >> 16;
+#pragma unroll 4
+            for (int k = k0; k < k1; ++k) {
+              const float2 v = *reinterpret_cast<const float2*>(sc + 2 * k);
+              t = fadd(fadd(t, v.x), v.y);
+            }
           }
           tcur[q] = t;
         }
@@ -235,6 +249,7 @@ __global__ void __launch_bounds__(kWarps * 32) format_conv_kernel(const __grid_c
         if (erb == 0) r = fmul(yc[0], yc[0]);
         if (erb == kErb - 1) r = fmul(yc[1], yc[1]);
         const int k0 = (erb == 0) ? 256 : (chain_k[q] & 0xffff), k1 = chain_k[q] >> 16;
+#pragma unroll 4
         for (int k = k0; k < k1; ++k) {
           const float2 v = *reinterpret_cast<const float2*>(yc + 2 * k);
           r = fadd(r, fmul(v.x, v.x));
@@ -382,7 +397,10 @@ mpeghb200_status mpeghb200_format_conv_dev(mpeghb200_ctx* ctx, const mpeghb200_f
   FcParams P{};
   P.in = d_in, P.out = d_out, P.state = d_state, P.D = h->d_D, P.active = h->d_active, P.win = h->d_win;
   P.eff8 = ctx->tables.eff8, P.rad2 = ctx->tables.rad2_512;
-  P.n_in = h->n_in, P.n_out = h->n_out, P.max_active = h->max_active > 0 ? h->max_active : 1, P.state_floats = int(mpeghb200_format_conv_state_floats(h));
+  P.n_in = h->n_in, P.n_out = h->n_out, P.max_active = h->max_active > 0 ? h->max_active : 1;
+  P.ranks = (2 * kWarps * kBufStride) / (h->n_out * kYStride);  // >= 1 by the static_assert above
+  P.ranks = P.ranks > 4 ? 4 : P.ranks;
+  P.state_floats = int(mpeghb200_format_conv_state_floats(h));
   const size_t smem = sizeof(float) * (size_t(2) * kWarps * kBufStride + size_t(h->n_in) * 512 +
                                        size_t(h->n_out) * (kYStride + 256 + kErb) + 2 + 64 + 500 + 512);
   MB_CUDA(ctx, cudaFuncSetAttribute(format_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
