@@ -478,6 +478,30 @@ mpeghb200_status mpeghb200_igf_tnf_dev(mpeghb200_ctx *ctx, const mpeghb200_bands
 /* whitening gain tables [2][64] (host, no GPU needed): pinned against the reference ROM by the tests */
 void mpeghb200_igf_whitening_rom(float *out128);
 
+/* ---- multichannel coding tool: inverse rotation / prediction boxes on pairs of channel spectra -------------------
+ * Replaces impeghd_mc_process (decoder/impeghd_multichannel.c:899; rotation :781, prediction :817) and the window
+ * loop around it (decoder/ia_core_coder_process.c:1043-1075) -- SURVEY.md section 8f rank 3, the step ahead of the
+ * seam.  A box works in place on two rows of a [unit][1024] spectrum array: downmix / residual in, the two channels
+ * out.  The boxes of one stream-frame form a group (d_group_first[g] .. d_group_first[g + 1]) and are applied in
+ * order; groups are independent.  Parsing (impeghd_mc_parse) and stereo filling stay on the host;
+ * mpeghb200_mct_resolve is the host half: band -> bin resolution per window exactly like the reference
+ * (coef_idx / mask: [n_windows][bands_per_window], sfb_offset: the band-end table of the block type). */
+#define MPEGHB200_MCT_MAX_SEG 64
+typedef struct mpeghb200_mct_box {
+  int32_t unit_l, unit_r; /* rows of the spectrum array */
+  int32_t op;             /* 0 / 1: prediction with pred_dir 0 / 1 (coef = alpha_q), 2: rotation (coef = angle index 0..64) */
+  int32_t n_seg;
+  int16_t start[MPEGHB200_MCT_MAX_SEG], len[MPEGHB200_MCT_MAX_SEG], coef[MPEGHB200_MCT_MAX_SEG];
+} mpeghb200_mct_box;
+mpeghb200_status mpeghb200_mct_resolve(int signal_type, int pred_dir, int fullband, int n_windows, int bins_per_window,
+                                       int bands_per_window, int total_sfb, const int16_t *sfb_offset,
+                                       const int32_t *coef_idx, const int32_t *mask, int unit_l, int unit_r,
+                                       mpeghb200_mct_box *out);
+mpeghb200_status mpeghb200_mct_dev(mpeghb200_ctx *ctx, float *d_spec, const mpeghb200_mct_box *d_boxes,
+                                   const int32_t *d_group_first, int n_groups, void *cuda_stream);
+/* the angle tables impeghd_mc_index_to_sin_alpha / _cos_alpha [65] as this library builds them */
+void mpeghb200_mct_rom(float *sin_alpha, float *cos_alpha);
+
 /* ---- element-wise steps between the renderers and the limiter -----------------
  * Bus add: d_out[i] = d_a[i] + d_b[i] over n_floats samples (a multiple of 4; d_out may alias d_a or d_b): the
  * bed + objects / bed + HOA / HOA + objects sums of decoder/ia_core_coder_decode_main.c:2185-2195, 2203-2213,

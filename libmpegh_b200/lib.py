@@ -79,6 +79,9 @@ class HoaSpatialDesc(ctypes.Structure):
 
 
 LTPF_SIDE_DTYPE = np.dtype([("unit", "<i4"), ("pitch_lag_idx", "<u2"), ("data_present", "u1"), ("gain_idx", "u1")])
+MCT_BOX_DTYPE = np.dtype([("unit_l", np.int32), ("unit_r", np.int32), ("op", np.int32), ("n_seg", np.int32),
+                          ("start", np.int16, 64), ("len", np.int16, 64), ("coef", np.int16, 64)])
+
 TNS_CHANNEL_DTYPE = np.dtype([
     ("unit", "<i4"), ("is_long", "<i4"), ("max_sfb", "<i4"), ("igf_active", "<i4"), ("igf_after_tns_synth", "<i4"),
     ("igf_sfb_start", "<i4"), ("igf_sfb_stop", "<i4"), ("n_filt", "<i4", 8), ("coef_res", "<i4", 8),
@@ -226,6 +229,12 @@ class Lib:
         c.mpeghb200_bands_destroy.argtypes = [vp]
         c.mpeghb200_igf_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
         c.mpeghb200_igf_dev.restype = i32
+        c.mpeghb200_mct_resolve.argtypes = [ctypes.c_int] * 7 + [vp, vp, vp, ctypes.c_int, ctypes.c_int, vp]
+        c.mpeghb200_mct_resolve.restype = i32
+        c.mpeghb200_mct_dev.argtypes = [vp, vp, vp, vp, ctypes.c_int, vp]
+        c.mpeghb200_mct_dev.restype = i32
+        c.mpeghb200_mct_rom.argtypes = [vp, vp]
+        c.mpeghb200_mct_rom.restype = None
         c.mpeghb200_bus_add_dev.argtypes = [vp, vp, vp, vp, sz, vp]
         c.mpeghb200_bus_add_dev.restype = i32
         c.mpeghb200_channel_mask_dev.argtypes = [vp, vp, vp, ctypes.c_int, vp]
@@ -354,6 +363,27 @@ class Lib:
 
     def tns_dev(self, d_coef, d_filters, d_chain_first, n_chains, stream=0):
         self.check(self.c.mpeghb200_tns_dev(self.ctx, d_coef, d_filters, d_chain_first, n_chains, stream))
+
+    # ---- multichannel coding tool -------------------------------------------------------------------
+    def mct_resolve(self, signal_type, pred_dir, fullband, n_windows, bins_per_window, bands_per_window, sfb_offset,
+                    coef_idx, mask, unit_l, unit_r):
+        """-> one MCT_BOX_DTYPE record; raises MpeghError on out-of-range side info"""
+        sfb = np.ascontiguousarray(sfb_offset, np.int16)
+        c = np.ascontiguousarray(coef_idx, np.int32)
+        m = np.ascontiguousarray(mask, np.int32)
+        box = np.zeros(1, MCT_BOX_DTYPE)
+        self.check(self.c.mpeghb200_mct_resolve(signal_type, pred_dir, fullband, n_windows, bins_per_window,
+                                                bands_per_window, len(sfb), sfb.ctypes.data, c.ctypes.data,
+                                                m.ctypes.data, unit_l, unit_r, box.ctypes.data))
+        return box[0]
+
+    def mct_dev(self, d_spec, d_boxes, d_group_first, n_groups, stream=0):
+        self.check(self.c.mpeghb200_mct_dev(self.ctx, d_spec, d_boxes, d_group_first, n_groups, stream))
+
+    def mct_rom(self):
+        s, c = np.zeros(65, np.float32), np.zeros(65, np.float32)
+        self.c.mpeghb200_mct_rom(s.ctypes.data, c.ctypes.data)
+        return s, c
 
     # ---- joint-stereo tools -------------------------------------------------------------------------
     def bands_create(self, sfb_long, sfb_short):

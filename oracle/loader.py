@@ -110,6 +110,9 @@ def load_oracle():
     lib.oracle_ltpf_cfg_init.argtypes = [ctypes.c_void_p, ctypes.c_int]
     lib.oracle_ltpf_state_init.argtypes = [ctypes.c_void_p]
     lib.oracle_ltpf_process.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p]
+    _mct_args = [_f32p, _f32p, _i32p, _i32p, ctypes.c_int, ctypes.c_int, _i16p] + [ctypes.c_int] * 4
+    lib.oracle_mct_process.argtypes = _mct_args
+    lib.oracle_mct_rom.argtypes = [_f32p, _f32p]
     lib.oracle_igf_tiles.argtypes = [ctypes.c_int] * 4 + [_i16p, _i32p]
     lib.oracle_igf_tiles.restype = ctypes.c_int
     lib.oracle_igf_whitening_table.argtypes = [_f32p]
@@ -235,6 +238,9 @@ def load_ref():
                                     _f32p, _f32p, _f32p, _f32p, _f32p]
     lib.ref_cpe_process.restype = ctypes.c_int
     lib.ref_mdst_rom.argtypes = [_f32p, _f32p]
+    _i16p = np.ctypeslib.ndpointer(dtype=np.int16, flags="C_CONTIGUOUS")
+    lib.ref_mct_process.argtypes = [_f32p, _f32p, _i32p, _i32p, ctypes.c_int, ctypes.c_int, _i16p] + [ctypes.c_int] * 4
+    lib.ref_mct_rom.argtypes = [_f32p, _f32p]
     lib.ref_ltpf_create.restype = ctypes.c_void_p
     lib.ref_ltpf_create.argtypes = [ctypes.c_int]
     lib.ref_ltpf_destroy.argtypes = [ctypes.c_void_p]

@@ -146,6 +146,28 @@ def fc_stage():
     lib.format_conv_destroy(h)
 
 
+def mct_stage():
+    """MCT boxes ahead of the seam: 256 streams x 24 channels, 12 boxes per stream-frame."""
+    import mct_cases
+    from libmpegh_b200.lib import MCT_BOX_DTYPE
+    S = 256
+    rng = np.random.default_rng(2)
+    recs, first = [], [0]
+    for s_ in range(S):
+        boxes = []
+        while len(boxes) < 12:
+            boxes += mct_cases.random_group(rng)
+        recs += mct_cases.resolve_group(lib, boxes[:12], s_ * 24)
+        first.append(len(recs))
+    spec = torch.randn(S * 24, 1024, device="cuda") * 500
+    d_rec = torch.from_numpy(np.array(recs, MCT_BOX_DTYPE).view(np.uint8).reshape(-1)).cuda()
+    d_first = torch.from_numpy(np.array(first, np.int32)).cuda()
+    ms = timeit(lambda i: lib.mct_dev(spec.data_ptr(), d_rec.data_ptr(), d_first.data_ptr(), S, st))
+    touched = sum(int(r["len"][:int(r["n_seg"])].sum()) for r in recs)
+    report("mct boxes, 256 streams x 24 ch, 12 boxes per stream-frame", ms, len(recs) * (4 * 4096 + 400),
+           touched, "bins_rotated_or_predicted", {"boxes": len(recs)})
+
+
 def tns_rs_stage():
     import tns_cases
     from libmpegh_b200.lib import TNS_FILTER_DTYPE
@@ -386,7 +408,7 @@ def fd_path_stage():
     lib.bands_destroy(bands)
 
 
-STAGES = {"binaural": binaural_stage, "hoa": hoa_chain_stage, "fc": fc_stage, "tns_rs": tns_rs_stage,
+STAGES = {"mct": mct_stage, "binaural": binaural_stage, "hoa": hoa_chain_stage, "fc": fc_stage, "tns_rs": tns_rs_stage,
           "fd_path": fd_path_stage,
           "spectral": spectral_stage,
           "obj": obj_stage, "hoa_render": hoa_render_stage}
