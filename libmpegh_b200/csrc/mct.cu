@@ -8,8 +8,8 @@
 // copies of a channel (process.c:1059-1072) when the caller lists them as further boxes.
 //
 // The boxes of one stream-frame form a group and are applied in order (a channel may sit in several boxes); bins
-// are independent, so a CTA owns a group, a thread owns the same four bins of every box, and no ordering between
-// threads is needed.  HBM traffic: 2 x 4 KB read + written per box (L1/L2 hits when a channel repeats).
+// are independent, so a CTA owns a 256-bin slice of a group, a thread owns the same four bins of every box, and no
+// ordering between threads is needed.  HBM traffic: 2 x 4 KB read + written per box (L1/L2 hits when a channel repeats).
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -41,28 +41,54 @@ void mct_tables(float* sn, float* cs) {
 
 constexpr int kNone = -32768;
 
-__global__ void __launch_bounds__(256)
+constexpr int kSlice = 256;    // bins per CTA: a group is spread over 1024 / kSlice CTAs (bins are independent)
+constexpr int kThreads = kSlice / 4;
+
+__global__ void __launch_bounds__(kThreads)
     mct_kernel(float* __restrict__ spec, const mpeghb200_mct_box* __restrict__ boxes,
                const int32_t* __restrict__ group_first, int n_groups) {
-  __shared__ short cmap[1024];  // coefficient index of every bin of the current box, kNone = bin not in any segment
+  __shared__ short cmap[kSlice];  // coefficient index of every bin of the current box, kNone = not in any segment
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = blockIdx.x;
-  for (int b = group_first[g]; b < group_first[g + 1]; ++b) {
-    const mpeghb200_mct_box& B = boxes[b];
+  const int g = blockIdx.x, bin0 = blockIdx.y * kSlice;
+  // The boxes of a group run one after the other, each a short dependent chain (record -> bin map -> rows): what
+  // bounds the kernel is latency.  The records of up to kBatch boxes are staged in shared memory with one
+  // cooperative copy and the row slices they touch are requested into L2 up front.
+  constexpr int kBatch = 16;
+  __shared__ __align__(16) mpeghb200_mct_box sbox[kBatch];
+  static_assert(sizeof(mpeghb200_mct_box) % 16 == 0, "records are copied as int4");
+  const int b_begin = group_first[g], b_end = group_first[g + 1];
+  for (int b0 = b_begin; b0 < b_end; b0 += kBatch) {
+  const int nb = (b_end - b0 < kBatch) ? b_end - b0 : kBatch;
+  __syncthreads();
+  {
+    const int4* src = reinterpret_cast<const int4*>(boxes + b0);
+    int4* dst = reinterpret_cast<int4*>(sbox);
+    for (int i = tid; i < nb * int(sizeof(mpeghb200_mct_box) / 16); i += kThreads) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  for (int i = tid; i < nb * 2 * (kSlice / 32); i += kThreads) {  // 128-byte lines of the slices of both rows
+    const int bx = i / (2 * (kSlice / 32)), rem = i - bx * 2 * (kSlice / 32);
+    const int unit = (rem & 1) ? sbox[bx].unit_r : sbox[bx].unit_l;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(spec + size_t(unit) * 1024 + bin0 + 32 * (rem >> 1)));
+  }
+  for (int bi = 0; bi < nb; ++bi) {
+    const mpeghb200_mct_box& B = sbox[bi];
     *reinterpret_cast<short4*>(cmap + 4 * tid) = make_short4(kNone, kNone, kNone, kNone);
     __syncthreads();
     const int n_seg = B.n_seg < MPEGHB200_MCT_MAX_SEG ? B.n_seg : MPEGHB200_MCT_MAX_SEG;
-    for (int s = warp; s < n_seg; s += 8) {
-      const int start = B.start[s], len = B.len[s];
+    for (int s = warp; s < n_seg; s += kThreads / 32) {
+      int start = B.start[s], end = start + B.len[s];
       const short c = B.coef[s];
-      if (start >= 0 && len > 0 && start + len <= 1024)
-        for (int i = lane; i < len; i += 32) cmap[start + i] = c;
+      if (start < 0 || end > 1024) continue;
+      start = (start > bin0 ? start : bin0) - bin0;
+      end = (end < bin0 + kSlice ? end : bin0 + kSlice) - bin0;
+      for (int i = start + lane; i < end; i += 32) cmap[i] = c;
     }
     __syncthreads();
     const short4 c4 = *reinterpret_cast<const short4*>(cmap + 4 * tid);
     if (c4.x != kNone || c4.y != kNone || c4.z != kNone || c4.w != kNone) {
-      float* pl = spec + size_t(B.unit_l) * 1024 + 4 * tid;
-      float* pr = spec + size_t(B.unit_r) * 1024 + 4 * tid;
+      float* pl = spec + size_t(B.unit_l) * 1024 + bin0 + 4 * tid;
+      float* pr = spec + size_t(B.unit_r) * 1024 + bin0 + 4 * tid;
       const float4 l4 = *reinterpret_cast<const float4*>(pl), r4 = *reinterpret_cast<const float4*>(pr);
       float l[4] = {l4.x, l4.y, l4.z, l4.w}, r[4] = {r4.x, r4.y, r4.z, r4.w};
       const short cc[4] = {c4.x, c4.y, c4.z, c4.w};
@@ -86,6 +112,7 @@ __global__ void __launch_bounds__(256)
       *reinterpret_cast<float4*>(pr) = make_float4(r[0], r[1], r[2], r[3]);
     }
     __syncthreads();  // cmap is rewritten by the next box
+  }
   }
 }
 
@@ -162,7 +189,7 @@ mpeghb200_status mpeghb200_mct_dev(mpeghb200_ctx* ctx, float* d_spec, const mpeg
     MB_CUDA(ctx, cudaMemcpyToSymbol(c_mct_cos, cs, sizeof cs));
     if (ctx->device < 64) tables_done[ctx->device] = true;
   }
-  mct_kernel<<<n_groups, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(d_spec, d_boxes, d_group_first, n_groups);
+  mct_kernel<<<dim3(n_groups, 1024 / kSlice), kThreads, 0, static_cast<cudaStream_t>(cuda_stream)>>>(d_spec, d_boxes, d_group_first, n_groups);
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   return MPEGHB200_OK;

@@ -8,6 +8,7 @@
  *   ia_core_coder_fd_frm_dec             decoder/ia_core_coder_imdct.c:832      -> mpeghb200_fd_synth_dev
  *   impeghd_tns_decode_coeff_ar_filter   decoder/ia_core_coder_tns.c:83         -> mpeghb200_tns_dev
  *   ia_core_coder_usac_ltpf_process      decoder/ia_core_coder_ltpf.c:395       -> mpeghb200_ltpf_dev
+ *   impeghd_mc_process                   decoder/impeghd_multichannel.c:899     -> mpeghb200_mct_dev
  *   impeghd_format_converter_process     decoder/ia_core_coder_process.c:641    -> mpeghb200_format_conv_dev
  *                                        (seam_interpose_fc.c)
  *   impeghd_peak_limiter_init/_process   decoder/impeghd_peak_limiter.c:146,190 -> mpeghb200_limiter_dev
@@ -57,6 +58,13 @@
 #include "ia_core_coder_main.h"
 #include "impeghd_error_codes.h"
 #include "impeghd_peak_limiter_struct_def.h"
+#include "impeghd_hoa_common_values.h"
+#include "impeghd_hoa_matrix_struct.h"
+#include "impeghd_hoa_matrix.h"
+#include "impd_drc_common.h"
+#include "impd_drc_extr_delta_coded_info.h"
+#include "impd_drc_struct.h"
+#include "ia_core_coder_config.h"
 
 #include "seam_internal.h"
 
@@ -83,7 +91,11 @@ static struct
   float *h_planar;
   float *d_ltpf_state;
   mpeghb200_ltpf_side *d_ltpf_side;
-  unsigned long n_fd_gpu, n_fd_host, n_tns, n_lim, n_ltpf, n_fc;
+  /* MCT scratch: two spectrum rows, one box, one group */
+  float *d_mct_spec;
+  mpeghb200_mct_box *d_mct_box;
+  int32_t *d_mct_first;
+  unsigned long n_fd_gpu, n_fd_host, n_tns, n_lim, n_ltpf, n_fc, n_mct;
 } g;
 
 void seam_die(const char *what, mpeghb200_status st)
@@ -96,8 +108,8 @@ static void seam_stats(void)
   if (getenv("MPEGHB200_SEAM_STATS"))
     fprintf(stderr,
             "mpeghb200 seam: fd_frm_dec gpu=%lu host(LPD transition)=%lu tns_filters gpu=%lu limiter_frames gpu=%lu "
-            "ltpf_frames gpu=%lu format_conv_frames gpu=%lu kernel_launches=%llu\n",
-            g.n_fd_gpu, g.n_fd_host, g.n_tns, g.n_lim, g.n_ltpf, g.n_fc,
+            "ltpf_frames gpu=%lu format_conv_frames gpu=%lu mct_boxes gpu=%lu kernel_launches=%llu\n",
+            g.n_fd_gpu, g.n_fd_host, g.n_tns, g.n_lim, g.n_ltpf, g.n_fc, g.n_mct,
             g.ctx ? (unsigned long long)mpeghb200_launch_count(g.ctx) : 0ull);
 }
 
@@ -117,6 +129,9 @@ static void seam_init(void)
   CK(mpeghb200_dev_alloc(g.ctx, MAX_NUM_CHANNELS * FRAME * sizeof(float), (void **)&g.d_lim_out));
   CK(mpeghb200_dev_alloc(g.ctx, 4096 * sizeof(float), (void **)&g.d_ltpf_state));
   CK(mpeghb200_dev_alloc(g.ctx, sizeof(mpeghb200_ltpf_side), (void **)&g.d_ltpf_side));
+  CK(mpeghb200_dev_alloc(g.ctx, 2 * FRAME * sizeof(float), (void **)&g.d_mct_spec));
+  CK(mpeghb200_dev_alloc(g.ctx, sizeof(mpeghb200_mct_box), (void **)&g.d_mct_box));
+  CK(mpeghb200_dev_alloc(g.ctx, 2 * sizeof(int32_t), (void **)&g.d_mct_first));
   g.h_planar = (float *)malloc(MAX_NUM_CHANNELS * FRAME * sizeof(float));
   atexit(seam_stats);
 }
@@ -178,6 +193,31 @@ VOID impeghd_tns_decode_coeff_ar_filter(WORD32 order, WORD32 coef_res, WORD16 *c
   CK(mpeghb200_tns_dev(g.ctx, g.d_coef, g.d_filt, g.d_chain, 1, NULL));
   CK(mpeghb200_d2h(g.ctx, ptr_spec, g.d_coef, (size_t)size * sizeof(float)));
   g.n_tns++;
+}
+
+/* ---- MCT: one window of one box per call (the window loop is the caller's, process.c:1043-1075) ---- */
+VOID impeghd_mc_process(ia_multichannel_data *ptr_mc_data, FLOAT32 *ptr_dmx, FLOAT32 *ptr_res,
+                        WORD32 *ptr_coeff_sfb_idx, WORD32 *ptr_mask, WORD32 bands_per_window, WORD32 total_sfb,
+                        WORD32 pair, const WORD16 *ptr_sfb_offset, WORD32 num_samples)
+{
+  mpeghb200_mct_box box;
+  const int32_t first[2] = {0, 1};
+  const int fullband = !ptr_mc_data->bandwise_coeff_flag[pair] && !ptr_mc_data->mask_flag[pair];
+  if (!ptr_mc_data->use_tool)
+    return;
+  seam_init();
+  CK(mpeghb200_mct_resolve(ptr_mc_data->signal_type, ptr_mc_data->pred_dir[pair], fullband, 1, num_samples,
+                           bands_per_window, total_sfb, ptr_sfb_offset, ptr_coeff_sfb_idx, ptr_mask, 0, 1, &box));
+  if (box.n_seg == 0)
+    return;
+  CK(mpeghb200_h2d(g.ctx, g.d_mct_spec, ptr_dmx, (size_t)num_samples * sizeof(float)));
+  CK(mpeghb200_h2d(g.ctx, g.d_mct_spec + FRAME, ptr_res, (size_t)num_samples * sizeof(float)));
+  CK(mpeghb200_h2d(g.ctx, g.d_mct_box, &box, sizeof(box)));
+  CK(mpeghb200_h2d(g.ctx, g.d_mct_first, first, sizeof(first)));
+  CK(mpeghb200_mct_dev(g.ctx, g.d_mct_spec, g.d_mct_box, g.d_mct_first, 1, NULL));
+  CK(mpeghb200_d2h(g.ctx, ptr_dmx, g.d_mct_spec, (size_t)num_samples * sizeof(float)));
+  CK(mpeghb200_d2h(g.ctx, ptr_res, g.d_mct_spec + FRAME, (size_t)num_samples * sizeof(float)));
+  g.n_mct++;
 }
 
 /* ---- LTPF: the filter state stays in the reference handle (the LPD path shares it), round trip per call ---- */

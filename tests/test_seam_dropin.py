@@ -83,10 +83,11 @@ def test_seam_dropin_bit_exact(tmp_path, name, stream, extra):
     assert r.returncode == 0, r.stderr[-600:]
     m = re.search(r"fd_frm_dec gpu=(\d+) host\(LPD transition\)=(\d+) tns_filters gpu=(\d+) "
                   r"limiter_frames gpu=(\d+) ltpf_frames gpu=(\d+) format_conv_frames gpu=(\d+) "
-                  r"kernel_launches=(\d+)", r.stderr)
+                  r"mct_boxes gpu=(\d+) kernel_launches=(\d+)", r.stderr)
     assert m, r.stderr[-600:]
-    fd_gpu, fd_host, _tns, lim, ltpf, fc, launches = map(int, m.groups())
-    assert fd_gpu > 0 and fd_host == 0 and lim > 0 and ltpf == fd_gpu and launches >= 2 * fd_gpu + lim + fc
+    fd_gpu, fd_host, _tns, lim, ltpf, fc, mct, launches = map(int, m.groups())
+    print(f"{name}: seam counters {m.group(0)}")
+    assert fd_gpu > 0 and fd_host == 0 and lim > 0 and ltpf == fd_gpu and launches >= 2 * fd_gpu + lim + fc + mct
     assert fc == 0  # none of the shipped streams reaches the format converter (see test_seam_format_converter)
     assert os.path.getsize(wav) == GOLD[name]["bytes"]
     assert _sha(wav) == GOLD[name]["sha256"], f"{name}: PCM differs from the reference decoder"
@@ -144,4 +145,46 @@ def test_seam_format_converter(tmp_path, cicp_in, cicp_out):
             assert "format_conv_frames gpu=4" in r.stderr, r.stderr[-400:]
         outs.append(np.load(out))
     assert outs[0].shape == outs[1].shape and outs[0].shape[0] == 4
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+
+
+MCT_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+import mct_cases
+from oracle import loader
+ref = loader.load_ref()
+rng = np.random.default_rng(77)
+outs = []
+for _ in range(6):
+    boxes = mct_cases.random_group(rng)
+    x = (rng.standard_normal((24, 1024)) * 500).astype(np.float32)
+    outs.append(mct_cases.apply_group(ref.ref_mct_process, x, boxes))
+np.save(sys.argv[2], np.stack(outs))
+"""
+
+
+@pytest.mark.gpu
+def test_seam_mct(tmp_path):
+    """The interposed impeghd_mc_process against the reference's own (none of the shipped streams uses the
+    multichannel coding tool): the harness of oracle/ref_harness_mct.c drives it once plainly and once with the
+    seam preloaded."""
+    libref = os.path.join(REF_DIR, "libmpeghref.so")
+    _need(libref, SEAM)
+    script = tmp_path / "mct.py"
+    script.write_text(MCT_SCRIPT)
+    outs = []
+    for preload in (None, SEAM):
+        env = dict(os.environ)
+        if preload:
+            env["LD_PRELOAD"], env["MPEGHB200_SEAM_STATS"] = preload, "1"
+        out = str(tmp_path / ("gpu.npy" if preload else "ref.npy"))
+        r = subprocess.run([sys.executable, str(script), ROOT, out], env=env, capture_output=True, text=True,
+                           timeout=600)
+        assert r.returncode == 0, r.stderr[-800:]
+        if preload:
+            m = re.search(r"mct_boxes gpu=(\d+)", r.stderr)
+            assert m and int(m.group(1)) > 6, r.stderr[-400:]
+        outs.append(np.load(out))
+    assert outs[0].shape == outs[1].shape
     assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))

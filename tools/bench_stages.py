@@ -422,6 +422,7 @@ hoa_render_stage()
 hoa_chain_stage()
 fc_stage()
 tns_rs_stage()
+mct_stage()
 spectral_stage()
 fd_path_stage()
 binaural_stage()
