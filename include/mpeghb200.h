@@ -518,6 +518,23 @@ mpeghb200_status mpeghb200_channel_mask_dev(mpeghb200_ctx *ctx, float *d_audio, 
  * spline interpolation into the per-sample curve lpcm_gains (libm) stay on the host: d_gains [n_seq][1024]. */
 mpeghb200_status mpeghb200_gain_apply_dev(mpeghb200_ctx *ctx, float *d_audio, const float *d_gains,
                                           const int32_t *d_seq_of_ch, int n_channels, void *cuda_stream);
+/* The same in the STFT domain the decoder's domain switcher produces (sub_band_domain_mode STFT256: 4 time slots x
+ * 256 bands per channel-frame, re / im planes [channel][4][256], im[slot][0] = the Nyquist bin):
+ * impd_drc_apply_gains_subband (decoder/impd_drc_process.c:243-385), called from impd_drc_fd_process (:610).
+ * Single-band groups multiply by the slot's gain, multi-band groups (2..4 bands) by the ordered sum of overlap weight
+ * x sequence gain.  d_gains [n_seq][4]: per gain sequence the value the reference picks from lpcm_gains at the slot
+ * centre, lpcm_gains[MAX_SIGNAL_DELAY - gain_delay_samples + offset + 256 slot + 127] (:328, :345); d_weights
+ * [rows][256]: overlap_weight of the bands of each multi-band group (impd_drc_generate_overlap_weights), rows of a
+ * group consecutive.  One call per selected DRC set, in the reference's order (:640-651). */
+typedef struct mpeghb200_drc_sb_channel {
+  int32_t first_seq;  /* first gain sequence of the channel's group (gain_idx_grp, :296-304); < 0: no DRC on this channel */
+  int32_t band_count; /* band_count_of_ch_group: 1 = single band, 2..4 = multi-band */
+  int32_t weight_row; /* first row of the group's overlap weights in d_weights (multi-band only) */
+  int32_t reserved;
+} mpeghb200_drc_sb_channel;
+mpeghb200_status mpeghb200_gain_subband_dev(mpeghb200_ctx *ctx, float *d_re, float *d_im,
+                                            const mpeghb200_drc_sb_channel *d_chan, const float *d_gains,
+                                            const float *d_weights, int n_channels, void *cuda_stream);
 
 /* ---- LTPF: long-term post-filter of FD channels, in place on the time signal after FD synthesis -------------
  * Replaces ia_core_coder_usac_ltpf_process (decoder/ia_core_coder_ltpf.c:395), called per FD channel right after

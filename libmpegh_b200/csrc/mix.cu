@@ -41,6 +41,49 @@ __global__ void __launch_bounds__(256)
   audio[size_t(c) * 256 + threadIdx.x] = x;
 }
 
+// DRC gains in the STFT domain: 4 time slots x 256 bands per channel-frame, re / im planes; im[0] of a slot is the
+// Nyquist bin.  impd_drc_apply_gains_subband (decoder/impd_drc_process.c:243-385): a single-band group multiplies
+// everything by the slot's gain; a multi-band group forms the band gain as the ordered sum of overlap weight x
+// sequence gain (:350-357) and gives the Nyquist bin the gain of band 255 (:366-369).
+__global__ void __launch_bounds__(256)
+    gain_subband_kernel(float* __restrict__ re, float* __restrict__ im, const mpeghb200_drc_sb_channel* __restrict__ chan,
+                        const float* __restrict__ gains, const float* __restrict__ weights, int n_channels) {
+  const int c = blockIdx.x, k = threadIdx.x;
+  if (c >= n_channels) return;
+  const mpeghb200_drc_sb_channel ch = chan[c];
+  if (ch.first_seq < 0) return;  // channel without a DRC channel group
+  float* r = re + size_t(c) * 1024;
+  float* q = im + size_t(c) * 1024;
+  const int nb = ch.band_count < 1 ? 1 : (ch.band_count > 4 ? 4 : ch.band_count);
+  float w[4] = {0.0f, 0.0f, 0.0f, 0.0f}, w_last[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  if (nb > 1) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if (b < nb) {
+        w[b] = __ldg(weights + size_t(ch.weight_row + b) * 256 + k);
+        w_last[b] = __ldg(weights + size_t(ch.weight_row + b) * 256 + 255);
+      }
+  }
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    float g, g_nyq;
+    if (nb == 1) {
+      g = g_nyq = __ldg(gains + size_t(ch.first_seq) * 4 + s);
+    } else {
+      g = 0.0f, g_nyq = 0.0f;
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (b < nb) {
+          const float gl = __ldg(gains + size_t(ch.first_seq + b) * 4 + s);
+          g = fadd(g, fmul(w[b], gl));
+          g_nyq = fadd(g_nyq, fmul(w_last[b], gl));
+        }
+    }
+    r[s * 256 + k] = fmul(r[s * 256 + k], g);
+    q[s * 256 + k] = fmul(q[s * 256 + k], k == 0 ? g_nyq : g);
+  }
+}
+
 }  // namespace
 }  // namespace mpeghb200
 
@@ -88,6 +131,21 @@ mpeghb200_status mpeghb200_gain_apply_dev(mpeghb200_ctx* ctx, float* d_audio, co
   MB_CUDA(ctx, cudaSetDevice(ctx->device));
   gain_apply_kernel<<<n_channels, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
       reinterpret_cast<float4*>(d_audio), reinterpret_cast<const float4*>(d_gains), d_seq_of_ch, n_channels);
+  ctx->launches.fetch_add(1);
+  MB_CUDA(ctx, cudaGetLastError());
+  return MPEGHB200_OK;
+}
+
+mpeghb200_status mpeghb200_gain_subband_dev(mpeghb200_ctx* ctx, float* d_re, float* d_im,
+                                            const mpeghb200_drc_sb_channel* d_chan, const float* d_gains,
+                                            const float* d_weights, int n_channels, void* cuda_stream) {
+  if (!ctx) return MPEGHB200_ERR_BAD_ARG;
+  if (n_channels < 0 || (n_channels > 0 && (!d_re || !d_im || !d_chan || !d_gains)))
+    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "gain_subband_dev: null buffer or negative channel count");
+  if (n_channels == 0) return MPEGHB200_OK;
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  gain_subband_kernel<<<n_channels, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(d_re, d_im, d_chan, d_gains,
+                                                                                      d_weights, n_channels);
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   return MPEGHB200_OK;

@@ -79,6 +79,9 @@ class HoaSpatialDesc(ctypes.Structure):
 
 
 LTPF_SIDE_DTYPE = np.dtype([("unit", "<i4"), ("pitch_lag_idx", "<u2"), ("data_present", "u1"), ("gain_idx", "u1")])
+DRC_SB_CHANNEL_DTYPE = np.dtype([("first_seq", np.int32), ("band_count", np.int32), ("weight_row", np.int32),
+                                 ("reserved", np.int32)])
+
 MCT_BOX_DTYPE = np.dtype([("unit_l", np.int32), ("unit_r", np.int32), ("op", np.int32), ("n_seg", np.int32),
                           ("start", np.int16, 64), ("len", np.int16, 64), ("coef", np.int16, 64)])
 
@@ -229,6 +232,8 @@ class Lib:
         c.mpeghb200_bands_destroy.argtypes = [vp]
         c.mpeghb200_igf_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
         c.mpeghb200_igf_dev.restype = i32
+        c.mpeghb200_gain_subband_dev.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
+        c.mpeghb200_gain_subband_dev.restype = i32
         c.mpeghb200_mct_resolve.argtypes = [ctypes.c_int] * 7 + [vp, vp, vp, ctypes.c_int, ctypes.c_int, vp]
         c.mpeghb200_mct_resolve.restype = i32
         c.mpeghb200_mct_dev.argtypes = [vp, vp, vp, vp, ctypes.c_int, vp]
@@ -407,6 +412,10 @@ class Lib:
 
     def igf_tnf_dev(self, bands, d_coef, d_side, d_tnf_state, n_units, stream=0):
         self.check(self.c.mpeghb200_igf_tnf_dev(self.ctx, bands, d_coef, d_side, d_tnf_state, n_units, stream))
+
+    def gain_subband_dev(self, d_re, d_im, d_chan, d_gains, d_weights, n_channels, stream=0):
+        self.check(self.c.mpeghb200_gain_subband_dev(self.ctx, d_re, d_im, d_chan, d_gains, d_weights, n_channels,
+                                                     stream))
 
     def bus_add_dev(self, d_a, d_b, d_out, n_floats, stream=0):
         self.check(self.c.mpeghb200_bus_add_dev(self.ctx, d_a, d_b, d_out, n_floats, stream))

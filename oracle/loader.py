@@ -110,6 +110,8 @@ def load_oracle():
     lib.oracle_ltpf_cfg_init.argtypes = [ctypes.c_void_p, ctypes.c_int]
     lib.oracle_ltpf_state_init.argtypes = [ctypes.c_void_p]
     lib.oracle_ltpf_process.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p]
+    lib.oracle_drc_gains_subband.argtypes = [_f32p, _f32p, ctypes.c_int, _i32p, _i32p, ctypes.c_int, _f32p, _f32p,
+                                             ctypes.c_int, ctypes.c_int, ctypes.c_int]
     _mct_args = [_f32p, _f32p, _i32p, _i32p, ctypes.c_int, ctypes.c_int, _i16p] + [ctypes.c_int] * 4
     lib.oracle_mct_process.argtypes = _mct_args
     lib.oracle_mct_rom.argtypes = [_f32p, _f32p]
@@ -241,6 +243,9 @@ def load_ref():
     _i16p = np.ctypeslib.ndpointer(dtype=np.int16, flags="C_CONTIGUOUS")
     lib.ref_mct_process.argtypes = [_f32p, _f32p, _i32p, _i32p, ctypes.c_int, ctypes.c_int, _i16p] + [ctypes.c_int] * 4
     lib.ref_mct_rom.argtypes = [_f32p, _f32p]
+    lib.ref_drc_gains_subband.argtypes = [_f32p, _f32p, ctypes.c_int, _i32p, _i32p, ctypes.c_int, _f32p, _f32p] + \
+        [ctypes.c_int] * 5
+    lib.ref_drc_gains_subband.restype = ctypes.c_int
     lib.ref_ltpf_create.restype = ctypes.c_void_p
     lib.ref_ltpf_create.argtypes = [ctypes.c_int]
     lib.ref_ltpf_destroy.argtypes = [ctypes.c_void_p]

@@ -1,0 +1,45 @@
+"""Seeded cases for the sub-band DRC gain application (decoder/impd_drc_process.c:243)."""
+import numpy as np
+
+
+def random_frame(rng, n_ch=None):
+    """One stream-frame in the STFT256 domain: channel groups with 1..4 bands, some channels without DRC."""
+    n_ch = int(rng.integers(1, 17)) if n_ch is None else n_ch
+    n_groups = int(rng.integers(1, 5))
+    band_count = rng.integers(1, 5, n_groups).astype(np.int32)
+    group_of_ch = rng.integers(-1, n_groups, n_ch).astype(np.int32)
+    n_seq = int(band_count.sum())
+    gains = (rng.random((n_seq, 4)) * 2).astype(np.float32)
+    weights = rng.random((n_groups, 4, 256)).astype(np.float32)
+    re = (rng.standard_normal((n_ch, 1024)) * 1000).astype(np.float32)
+    im = (rng.standard_normal((n_ch, 1024)) * 1000).astype(np.float32)
+    re[:, ::31] = -0.0
+    return dict(n_ch=n_ch, n_groups=n_groups, band_count=band_count, group_of_ch=group_of_ch, gains=gains,
+                weights=weights, re=re, im=im)
+
+
+def run_oracle(fn, fr, ref_args=None):
+    re, im = fr["re"].copy(), fr["im"].copy()
+    args = [re.reshape(-1), im.reshape(-1), fr["n_ch"], fr["group_of_ch"], fr["band_count"], fr["n_groups"],
+            np.ascontiguousarray(fr["gains"]).reshape(-1), np.ascontiguousarray(fr["weights"]).reshape(-1), 4, 256]
+    if ref_args is None:
+        fn(*args, 1)
+    else:
+        assert fn(*args, 3, *ref_args) == 0  # SUBBAND_DOMAIN_MODE_STFT256, delay_mode, gain_delay_samples
+    return re, im
+
+
+def channel_records(fr, seq0=0, row0=0):
+    """-> DRC_SB_CHANNEL_DTYPE records of the frame's channels; its gain sequences start at seq0 of the gains array
+    and its weight rows (4 per group here) at row0 of the weights array"""
+    from libmpegh_b200.lib import DRC_SB_CHANNEL_DTYPE
+    first = np.concatenate([[0], np.cumsum(fr["band_count"])[:-1]])
+    rec = np.zeros(fr["n_ch"], DRC_SB_CHANNEL_DTYPE)
+    for c, g in enumerate(fr["group_of_ch"]):
+        if g < 0:
+            rec[c]["first_seq"] = -1
+        else:
+            rec[c]["first_seq"] = seq0 + int(first[g])
+            rec[c]["band_count"] = int(fr["band_count"][g])
+            rec[c]["weight_row"] = row0 + 4 * int(g)
+    return rec

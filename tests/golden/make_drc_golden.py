@@ -1,0 +1,25 @@
+#!/usr/bin/env python3
+"""Golden vectors for the sub-band DRC gain application: outputs of the UNMODIFIED reference build (oracle/_ref,
+needs /root/reference) on the seeded cases of tests/drc_cases.py.
+Run from the repo root: python tests/golden/make_drc_golden.py"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import drc_cases  # noqa: E402
+from oracle import loader  # noqa: E402
+
+SEED, N = 4242, 8
+ref = loader.load_ref()
+assert ref is not None, "reference build missing"
+out = {"seed": SEED, "n_cases": N}
+rng = np.random.default_rng(SEED)
+for i in range(N):
+    fr = drc_cases.random_frame(rng)
+    out[f"re_{i}"], out[f"im_{i}"] = drc_cases.run_oracle(ref.ref_drc_gains_subband, fr, (0, 0))
+np.savez_compressed(os.path.join(ROOT, "tests", "golden", "drc_golden.npz"), **out)
+print("wrote drc_golden.npz")

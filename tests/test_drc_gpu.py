@@ -1,0 +1,66 @@
+"""Sub-band DRC gains on the GPU (mpeghb200_gain_subband_dev, csrc/mix.cu) against the oracle restatement of
+impd_drc_apply_gains_subband (decoder/impd_drc_process.c:243) and the reference-generated golden vectors."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(__file__))
+import drc_cases  # noqa: E402
+from oracle.loader import bits_equal  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "drc_golden.npz")
+
+
+def run_gpu(gpu_lib, frames):
+    """all frames in one launch: channels, gain sequences and weight rows concatenated"""
+    import torch
+    recs, gains, weights, re, im = [], [], [], [], []
+    seq0 = row0 = 0
+    for fr in frames:
+        recs.append(drc_cases.channel_records(fr, seq0, row0))
+        gains.append(fr["gains"]), weights.append(fr["weights"].reshape(-1, 256))
+        re.append(fr["re"]), im.append(fr["im"])
+        seq0 += fr["gains"].shape[0]
+        row0 += 4 * fr["n_groups"]
+    rec = np.concatenate(recs)
+    d_re = torch.from_numpy(np.concatenate(re)).cuda()
+    d_im = torch.from_numpy(np.concatenate(im)).cuda()
+    d_rec = torch.from_numpy(rec.view(np.uint8).reshape(-1)).cuda()
+    d_g = torch.from_numpy(np.concatenate(gains)).cuda()
+    d_w = torch.from_numpy(np.concatenate(weights)).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    gpu_lib.gain_subband_dev(d_re.data_ptr(), d_im.data_ptr(), d_rec.data_ptr(), d_g.data_ptr(), d_w.data_ptr(),
+                             len(rec), st)
+    torch.cuda.synchronize()
+    return d_re.cpu().numpy(), d_im.cpu().numpy()
+
+
+def test_golden(gpu_lib):
+    g = np.load(GOLD)
+    rng = np.random.default_rng(int(g["seed"]))
+    frames = [drc_cases.random_frame(rng) for _ in range(int(g["n_cases"]))]
+    re, im = run_gpu(gpu_lib, frames)
+    c = 0
+    for i, fr in enumerate(frames):
+        assert bits_equal(re[c:c + fr["n_ch"]], g[f"re_{i}"]) and bits_equal(im[c:c + fr["n_ch"]], g[f"im_{i}"]), i
+        c += fr["n_ch"]
+
+
+@pytest.mark.parametrize("n_frames,n_ch,seed", [(1, 1, 0), (9, None, 1), (256, 24, 2)])
+def test_matches_oracle(gpu_lib, oracle, n_frames, n_ch, seed):
+    rng = np.random.default_rng(1200 + seed)
+    frames = [drc_cases.random_frame(rng, n_ch) for _ in range(n_frames)]
+    re, im = run_gpu(gpu_lib, frames)
+    c = 0
+    for fr in frames:
+        a, b = drc_cases.run_oracle(oracle.oracle_drc_gains_subband, fr)
+        assert bits_equal(re[c:c + fr["n_ch"]], a) and bits_equal(im[c:c + fr["n_ch"]], b)
+        c += fr["n_ch"]
+
+
+def test_empty(gpu_lib):
+    import torch
+    gpu_lib.gain_subband_dev(0, 0, 0, 0, 0, 0, torch.cuda.current_stream().cuda_stream)
