@@ -535,6 +535,16 @@ typedef struct mpeghb200_drc_sb_channel {
 mpeghb200_status mpeghb200_gain_subband_dev(mpeghb200_ctx *ctx, float *d_re, float *d_im,
                                             const mpeghb200_drc_sb_channel *d_chan, const float *d_gains,
                                             const float *d_weights, int n_channels, void *cuda_stream);
+/* The whole STFT-domain DRC step of a frame in one launch, in place on the time signal d_audio [n_channels][1024]:
+ * domain switcher time -> frequency, the sub-band gains of n_sets (0..3) selected DRC sets in application order
+ * (d_chan [n_sets][n_channels]), frequency -> time -- decoder/ia_core_coder_decode_main.c:2128-2141, i.e.
+ * impeghd_domain_switcher_process (decoder/ia_core_coder_process.c:505) with ds_t2f = 1, impd_drc_fd_process
+ * (decoder/impd_drc_process.c:610), impeghd_domain_switcher_process with ds_t2f = 0.  Every channel takes the
+ * transform round trip, as in the reference.  d_state [n_channels][512] (zero at stream start): the previous input
+ * slot and the overlap of the output (stft_in_buf / stft_out_buf of ia_ds_state_struct). */
+mpeghb200_status mpeghb200_drc_stft_dev(mpeghb200_ctx *ctx, float *d_audio, float *d_state,
+                                        const mpeghb200_drc_sb_channel *d_chan, int n_sets, const float *d_gains,
+                                        const float *d_weights, int n_channels, void *cuda_stream);
 
 /* ---- LTPF: long-term post-filter of FD channels, in place on the time signal after FD synthesis -------------
  * Replaces ia_core_coder_usac_ltpf_process (decoder/ia_core_coder_ltpf.c:395), called per FD channel right after

@@ -57,28 +57,6 @@ struct FcParams {
   int n_in, n_out, state_floats, max_active, ranks;
 };
 
-// 512-point transform of one warp's buffer, natural order in, up to its last pass: what is left is the radix-2 pass
-// out[i] = buf[i] + w_i buf[i + 256], out[i + 256] = buf[i] - w_i buf[i + 256] (w_i = rad2[i]), which the two callers
-// fuse with what they do to the result (they need half of it, or only its real part).
-template <bool INV>
-__device__ __forceinline__ void fft512_tail(float2 (&v)[16], float2* __restrict__ buf, int lane, const RowTw eff8) {
-  // v[t] = point r3(lane) + 32 t on entry
-  stage_a<INV>(v, eff8);
-#pragma unroll
-  for (int e = 0; e < 16; ++e) buf[phys(16 * lane + e)] = v[e];
-  __syncwarp();
-  const int base = 256 * (lane >> 4) + (lane & 15);
-#pragma unroll
-  for (int t = 0; t < 16; ++t) v[t] = buf[phys(base + 16 * t)];
-  stage_b<INV>(v, eff8, lane & 15);
-#pragma unroll
-  for (int t = 0; t < 16; ++t) buf[phys(base + 16 * t)] = v[t];
-  __syncwarp();
-}
-
-// lane -> its digit-reversed position inside a group of 32 points (the order stage A wants its inputs in)
-__device__ __forceinline__ int rev32(int lane) { return 8 * (lane & 3) + 2 * ((lane >> 2) & 3) + (lane >> 4); }
-
 __device__ __forceinline__ float clip_eq(float t, float r) {
   float eq = __fsqrt_rn(__fdiv_rn(t, fadd(kEps, r)));
   return eq > kEqMax ? kEqMax : (eq < kEqMin ? kEqMin : eq);

@@ -234,6 +234,8 @@ class Lib:
         c.mpeghb200_igf_dev.restype = i32
         c.mpeghb200_gain_subband_dev.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
         c.mpeghb200_gain_subband_dev.restype = i32
+        c.mpeghb200_drc_stft_dev.argtypes = [vp, vp, vp, vp, ctypes.c_int, vp, vp, ctypes.c_int, vp]
+        c.mpeghb200_drc_stft_dev.restype = i32
         c.mpeghb200_mct_resolve.argtypes = [ctypes.c_int] * 7 + [vp, vp, vp, ctypes.c_int, ctypes.c_int, vp]
         c.mpeghb200_mct_resolve.restype = i32
         c.mpeghb200_mct_dev.argtypes = [vp, vp, vp, vp, ctypes.c_int, vp]
@@ -416,6 +418,10 @@ class Lib:
     def gain_subband_dev(self, d_re, d_im, d_chan, d_gains, d_weights, n_channels, stream=0):
         self.check(self.c.mpeghb200_gain_subband_dev(self.ctx, d_re, d_im, d_chan, d_gains, d_weights, n_channels,
                                                      stream))
+
+    def drc_stft_dev(self, d_audio, d_state, d_chan, n_sets, d_gains, d_weights, n_channels, stream=0):
+        self.check(self.c.mpeghb200_drc_stft_dev(self.ctx, d_audio, d_state, d_chan, n_sets, d_gains, d_weights,
+                                                 n_channels, stream))
 
     def bus_add_dev(self, d_a, d_b, d_out, n_floats, stream=0):
         self.check(self.c.mpeghb200_bus_add_dev(self.ctx, d_a, d_b, d_out, n_floats, stream))

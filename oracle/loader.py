@@ -112,6 +112,8 @@ def load_oracle():
     lib.oracle_ltpf_process.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p]
     lib.oracle_drc_gains_subband.argtypes = [_f32p, _f32p, ctypes.c_int, _i32p, _i32p, ctypes.c_int, _f32p, _f32p,
                                              ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.oracle_ds_t2f.argtypes = [_f32p, _f32p, _f32p, _f32p, _f32p, ctypes.c_int]
+    lib.oracle_ds_f2t.argtypes = [_f32p, _f32p, _f32p, _f32p, _f32p, ctypes.c_int]
     _mct_args = [_f32p, _f32p, _i32p, _i32p, ctypes.c_int, ctypes.c_int, _i16p] + [ctypes.c_int] * 4
     lib.oracle_mct_process.argtypes = _mct_args
     lib.oracle_mct_rom.argtypes = [_f32p, _f32p]
@@ -246,6 +248,11 @@ def load_ref():
     lib.ref_drc_gains_subband.argtypes = [_f32p, _f32p, ctypes.c_int, _i32p, _i32p, ctypes.c_int, _f32p, _f32p] + \
         [ctypes.c_int] * 5
     lib.ref_drc_gains_subband.restype = ctypes.c_int
+    lib.ref_ds_create.restype = ctypes.c_void_p
+    lib.ref_ds_create.argtypes = [ctypes.c_int]
+    lib.ref_ds_destroy.argtypes = [ctypes.c_void_p]
+    lib.ref_ds_t2f.argtypes = [ctypes.c_void_p, _f32p, _f32p, _f32p]
+    lib.ref_ds_f2t.argtypes = [ctypes.c_void_p, _f32p, _f32p, _f32p]
     lib.ref_ltpf_create.restype = ctypes.c_void_p
     lib.ref_ltpf_create.argtypes = [ctypes.c_int]
     lib.ref_ltpf_destroy.argtypes = [ctypes.c_void_p]

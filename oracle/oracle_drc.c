@@ -52,3 +52,56 @@ void oracle_drc_gains_subband(float *re, float *im, int n_ch, const int *group_o
     }
   }
 }
+
+/* ---- domain switcher: the STFT pair around the sub-band DRC (impeghd_domain_switcher_process,
+ * decoder/ia_core_coder_process.c:505-627; called at decoder/ia_core_coder_decode_main.c:2128 and :2140) ---------
+ * win = ia_core_coder_sine_window256.  Layout per channel as the reference leaves it in time_sample_stft: re / im
+ * planes of [4 slots][256]; im[slot][0] carries the Nyquist bin (:575-583). */
+void oracle_ds_t2f(const float *win, float *in_hist /*[n_ch][256]*/, const float *x /*[n_ch][1024]*/, float *re_out,
+                   float *im_out, int n_ch)
+{
+  float re[512], im[512];
+  for (int slot = 0; slot < 4; ++slot)
+    for (int ch = 0; ch < n_ch; ++ch)
+    {
+      float *h = in_hist + ch * 256;
+      const float *cur = x + ch * 1024 + slot * 256;
+      for (int i = 0; i < 256; ++i)
+      {
+        const float v = cur[i];
+        re[i] = h[i] * win[i];
+        re[256 + i] = win[255 - i] * v;
+        h[i] = v;
+        im[i] = im[256 + i] = 0.0f;
+      }
+      oracle_cplx_fft_pow2(re, im, 512); /* impeghd_rad2_cplx_fft (:570) */
+      float *ro = re_out + ch * 1024 + slot * 256, *io = im_out + ch * 1024 + slot * 256;
+      ro[0] = re[0];
+      io[0] = re[256];
+      for (int k = 1; k < 256; ++k) ro[k] = re[k], io[k] = im[k];
+    }
+}
+
+void oracle_ds_f2t(const float *win, float *out_hist /*[n_ch][256]*/, const float *re_in, const float *im_in,
+                   float *y /*[n_ch][1024]*/, int n_ch)
+{
+  float re[512], im[512];
+  for (int slot = 0; slot < 4; ++slot)
+    for (int ch = 0; ch < n_ch; ++ch)
+    {
+      const float *ri = re_in + ch * 1024 + slot * 256, *ii = im_in + ch * 1024 + slot * 256;
+      float *h = out_hist + ch * 256, *o = y + ch * 1024 + slot * 256;
+      re[0] = ri[0], re[256] = ii[0], im[0] = 0, im[256] = 0;
+      for (int k = 1; k < 256; ++k)
+      {
+        re[k] = ri[k], re[512 - k] = re[k];
+        im[k] = ii[k], im[512 - k] = -im[k];
+      }
+      oracle_cplx_ifft_pow2(re, im, 512); /* impeghd_rad2_cplx_ifft (:608) */
+      for (int i = 0; i < 256; ++i)
+      {
+        o[i] = (re[i] / 512.0f) * win[i] + h[i] * win[255 - i]; /* :613-616 */
+        h[i] = re[256 + i] / 512.0f;
+      }
+    }
+}

@@ -235,3 +235,73 @@ int ref_fc_process(void *q, const float *in, float *out)
     memcpy(out + (size_t)ch * 1024, u->time_sample_vector[ch], sizeof(float) * 1024);
   return err;
 }
+
+/* ---- domain switcher (impeghd_domain_switcher_process, decoder/ia_core_coder_process.c:505) -------------------- */
+IA_ERRORCODE impeghd_domain_switcher_process(ia_mpegh_dec_api_struct *p_obj_mpegh_dec, WORD32 *num_chn_out,
+                                             UWORD32 ds_t2f, FLOAT32 *scratch_buf);
+typedef struct
+{
+  ia_mpegh_dec_api_struct api;
+  ia_mpegh_dec_state_struct state;
+  ia_ds_param params;
+  FLOAT32 *in_ptr[MAX_NUM_CHANNELS], *out_ptr[MAX_NUM_CHANNELS];
+  FLOAT32 in_buf[MAX_NUM_CHANNELS][FC_STFT_FRAME], out_buf[MAX_NUM_CHANNELS][FC_STFT_FRAME];
+  ia_dec_data_struct *dec;
+  FLOAT32 *scratch, *stft;
+  int n_ch;
+} ref_ds_handle;
+
+void *ref_ds_create(int n_ch)
+{
+  ref_ds_handle *h = (ref_ds_handle *)calloc(1, sizeof(ref_ds_handle));
+  h->dec = (ia_dec_data_struct *)calloc(1, sizeof(ia_dec_data_struct));
+  h->scratch = (FLOAT32 *)calloc(1 << 20, sizeof(FLOAT32));
+  h->stft = (FLOAT32 *)calloc((size_t)MAX_NUM_CHANNELS * FC_STFT_FRAMEx2 * 4, sizeof(FLOAT32));
+  h->n_ch = n_ch;
+  h->api.p_state_mpeghd = &h->state;
+  h->state.pstr_dec_data = h->dec;
+  h->params.num_in_ch = h->params.num_out_ch = n_ch;
+  h->state.state_domain_switcher.ds_params = &h->params;
+  h->state.state_domain_switcher.stft_in_buf = h->in_ptr;
+  h->state.state_domain_switcher.stft_out_buf = h->out_ptr;
+  for (int c = 0; c < MAX_NUM_CHANNELS; c++)
+  {
+    h->in_ptr[c] = h->in_buf[c], h->out_ptr[c] = h->out_buf[c];
+    h->dec->str_usac_data.time_sample_stft[c] = h->stft + (size_t)c * FC_STFT_FRAMEx2 * 4; /* decode_main.c:2121 */
+  }
+  return h;
+}
+void ref_ds_destroy(void *q)
+{
+  ref_ds_handle *h = (ref_ds_handle *)q;
+  free(h->dec), free(h->scratch), free(h->stft), free(h);
+}
+/* x [n_ch][1024] -> re, im [n_ch][1024] (4 slots x 256) */
+int ref_ds_t2f(void *q, const float *x, float *re, float *im)
+{
+  ref_ds_handle *h = (ref_ds_handle *)q;
+  ia_usac_data_struct *u = &h->dec->str_usac_data;
+  int n_out = 0, err;
+  for (int c = 0; c < h->n_ch; c++) memcpy(u->time_sample_vector[c], x + (size_t)c * 1024, 4096);
+  err = (int)impeghd_domain_switcher_process(&h->api, &n_out, 1, h->scratch);
+  for (int c = 0; c < h->n_ch; c++)
+  {
+    memcpy(re + (size_t)c * 1024, u->time_sample_stft[c], 4096);
+    memcpy(im + (size_t)c * 1024, u->time_sample_stft[c] + 1024, 4096);
+  }
+  return err;
+}
+int ref_ds_f2t(void *q, const float *re, const float *im, float *y)
+{
+  ref_ds_handle *h = (ref_ds_handle *)q;
+  ia_usac_data_struct *u = &h->dec->str_usac_data;
+  int n_out = 0, err;
+  for (int c = 0; c < h->n_ch; c++)
+  {
+    memcpy(u->time_sample_stft[c], re + (size_t)c * 1024, 4096);
+    memcpy(u->time_sample_stft[c] + 1024, im + (size_t)c * 1024, 4096);
+  }
+  err = (int)impeghd_domain_switcher_process(&h->api, &n_out, 0, h->scratch);
+  for (int c = 0; c < h->n_ch; c++) memcpy(y + (size_t)c * 1024, u->time_sample_vector[c], 4096);
+  return err;
+}

@@ -43,3 +43,37 @@ def channel_records(fr, seq0=0, row0=0):
             rec[c]["band_count"] = int(fr["band_count"][g])
             rec[c]["weight_row"] = row0 + 4 * int(g)
     return rec
+
+
+def stft_chain(oracle, win, rng, n_frames, n_ch=12, ref=None, frames_out=None):
+    """Frames of the fused step (domain switcher t2f -> gains of 1..2 DRC sets -> f2t) with carried state, through the
+    oracle (or, ref given, through the reference: ref_ds_* and ref_drc_gains_subband).  -> [n_frames][n_ch][1024];
+    frames_out collects the per-frame side info for the GPU test."""
+    ih, oh = np.zeros((n_ch, 256), np.float32), np.zeros((n_ch, 256), np.float32)
+    h = ref.ref_ds_create(n_ch) if ref is not None else None
+    outs = []
+    for _ in range(n_frames):
+        x = (rng.standard_normal((n_ch, 1024)) * 3000).astype(np.float32)
+        sets = [random_frame(rng, n_ch) for _ in range(int(rng.integers(1, 3)))]
+        if frames_out is not None:
+            frames_out.append((x, sets))
+        re, im = np.zeros((n_ch, 1024), np.float32), np.zeros((n_ch, 1024), np.float32)
+        if ref is not None:
+            assert ref.ref_ds_t2f(h, x.reshape(-1), re.reshape(-1), im.reshape(-1)) == 0
+        else:
+            oracle.oracle_ds_t2f(win, ih.reshape(-1), x.reshape(-1), re.reshape(-1), im.reshape(-1), n_ch)
+        for fr in sets:
+            fr = dict(fr, re=re, im=im)
+            if ref is not None:
+                re, im = run_oracle(ref.ref_drc_gains_subband, fr, (0, 128))
+            else:
+                re, im = run_oracle(oracle.oracle_drc_gains_subband, fr)
+        y = np.zeros((n_ch, 1024), np.float32)
+        if ref is not None:
+            assert ref.ref_ds_f2t(h, re.reshape(-1), im.reshape(-1), y.reshape(-1)) == 0
+        else:
+            oracle.oracle_ds_f2t(win, oh.reshape(-1), re.reshape(-1), im.reshape(-1), y.reshape(-1), n_ch)
+        outs.append(y)
+    if h is not None:
+        ref.ref_ds_destroy(h)
+    return np.stack(outs)

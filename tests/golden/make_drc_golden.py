@@ -21,5 +21,9 @@ rng = np.random.default_rng(SEED)
 for i in range(N):
     fr = drc_cases.random_frame(rng)
     out[f"re_{i}"], out[f"im_{i}"] = drc_cases.run_oracle(ref.ref_drc_gains_subband, fr, (0, 0))
+# the fused chain (domain switcher t2f -> gains -> f2t), three frames through the reference
+out["chain_seed"], out["chain_frames"] = 99, 3
+win = np.ascontiguousarray(loader.golden_rom()["sine_256"], np.float32)
+out["chain_out"] = drc_cases.stft_chain(None, win, np.random.default_rng(99), 3, ref=ref)
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "drc_golden.npz"), **out)
 print("wrote drc_golden.npz")

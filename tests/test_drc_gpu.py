@@ -64,3 +64,34 @@ def test_matches_oracle(gpu_lib, oracle, n_frames, n_ch, seed):
 def test_empty(gpu_lib):
     import torch
     gpu_lib.gain_subband_dev(0, 0, 0, 0, 0, 0, torch.cuda.current_stream().cuda_stream)
+
+
+@pytest.mark.parametrize("n_ch,n_frames,seed", [(12, 3, 99), (1, 2, 5), (24 * 64, 2, 6)])
+def test_fused_stft_chain(gpu_lib, oracle, n_ch, n_frames, seed):
+    """mpeghb200_drc_stft_dev (domain switcher t2f -> sub-band gains -> f2t in one launch, carried state) against the
+    oracle chain; the (12, 3, 99) case is also the reference-made golden."""
+    import torch
+    from oracle import loader
+    win = np.ascontiguousarray(loader.golden_rom()["sine_256"], np.float32)
+    frames = []
+    want = drc_cases.stft_chain(oracle, win, np.random.default_rng(seed), n_frames, n_ch=n_ch, frames_out=frames)
+    if (n_ch, n_frames, seed) == (12, 3, 99):
+        assert bits_equal(want, np.load(GOLD)["chain_out"])
+    st = torch.cuda.current_stream().cuda_stream
+    d_state = torch.zeros(n_ch * 512, device="cuda")
+    for f, (x, sets) in enumerate(frames):
+        recs, gains, weights = [], [], []
+        seq0 = row0 = 0
+        for fr in sets:
+            recs.append(drc_cases.channel_records(fr, seq0, row0))
+            gains.append(fr["gains"]), weights.append(fr["weights"].reshape(-1, 256))
+            seq0 += fr["gains"].shape[0]
+            row0 += 4 * fr["n_groups"]
+        d_rec = torch.from_numpy(np.concatenate(recs).view(np.uint8).reshape(-1)).cuda()
+        d_g = torch.from_numpy(np.concatenate(gains)).cuda()
+        d_w = torch.from_numpy(np.concatenate(weights)).cuda()
+        d_x = torch.from_numpy(x.copy()).cuda()
+        gpu_lib.drc_stft_dev(d_x.data_ptr(), d_state.data_ptr(), d_rec.data_ptr(), len(sets), d_g.data_ptr(),
+                             d_w.data_ptr(), n_ch, st)
+        torch.cuda.synchronize()
+        assert bits_equal(d_x.cpu().numpy(), want[f]), f

@@ -36,3 +36,44 @@ def test_oracle_matches_golden():
         fr = drc_cases.random_frame(rng)
         re, im = drc_cases.run_oracle(o.oracle_drc_gains_subband, fr)
         assert loader.bits_equal(re, g[f"re_{i}"]) and loader.bits_equal(im, g[f"im_{i}"])
+
+
+def _win():
+    return np.ascontiguousarray(loader.golden_rom()["sine_256"], np.float32)
+
+
+@pytest.mark.parametrize("n_ch", [1, 5, 24])
+def test_domain_switcher_matches_reference(n_ch):
+    """oracle_ds_t2f / oracle_ds_f2t vs impeghd_domain_switcher_process (decoder/ia_core_coder_process.c:505) over
+    consecutive frames (carried input history and output overlap)."""
+    r = loader.load_ref()
+    if r is None:
+        pytest.skip("reference build not available")
+    o = loader.load_oracle()
+    win = _win()
+    rng = np.random.default_rng(40 + n_ch)
+    h = r.ref_ds_create(n_ch)
+    ih, oh = np.zeros((n_ch, 256), np.float32), np.zeros((n_ch, 256), np.float32)
+    for _ in range(4):
+        x = (rng.standard_normal((n_ch, 1024)) * 3000).astype(np.float32)
+        re, im, re2, im2 = (np.zeros((n_ch, 1024), np.float32) for _ in range(4))
+        assert r.ref_ds_t2f(h, x.reshape(-1), re.reshape(-1), im.reshape(-1)) == 0
+        o.oracle_ds_t2f(win, ih.reshape(-1), x.reshape(-1), re2.reshape(-1), im2.reshape(-1), n_ch)
+        assert loader.bits_equal(re, re2) and loader.bits_equal(im, im2)
+        g = (rng.random(re.shape) * 2).astype(np.float32)
+        re *= g
+        im *= g
+        y, y2 = np.zeros_like(re), np.zeros_like(re)
+        assert r.ref_ds_f2t(h, re.reshape(-1), im.reshape(-1), y.reshape(-1)) == 0
+        o.oracle_ds_f2t(win, oh.reshape(-1), re.reshape(-1), im.reshape(-1), y2.reshape(-1), n_ch)
+        assert loader.bits_equal(y, y2)
+    r.ref_ds_destroy(h)
+
+
+def test_stft_chain_matches_golden():
+    """t2f -> sub-band gains -> f2t, three frames with carried state, against vectors made by the reference."""
+    o = loader.load_oracle()
+    g = np.load(GOLD)
+    rng = np.random.default_rng(int(g["chain_seed"]))
+    out = drc_cases.stft_chain(o, _win(), rng, int(g["chain_frames"]))
+    assert loader.bits_equal(out, g["chain_out"])

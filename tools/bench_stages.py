@@ -168,6 +168,27 @@ def mct_stage():
            touched, "bins_rotated_or_predicted", {"boxes": len(recs)})
 
 
+def drc_stage():
+    """DRC in the STFT domain (domain switcher t2f -> sub-band gains -> f2t), 6144 channel-frames, one 3-band set."""
+    from libmpegh_b200.lib import DRC_SB_CHANNEL_DTYPE
+    U = 6144
+    rng = np.random.default_rng(4)
+    rec = np.zeros(U, DRC_SB_CHANNEL_DTYPE)
+    rec["first_seq"] = 3 * (np.arange(U) // 24)
+    rec["band_count"] = 3
+    rec["weight_row"] = 0
+    x = torch.randn(U, 1024, device="cuda") * 3000
+    state = torch.zeros(U * 512, device="cuda")
+    d_rec = torch.from_numpy(rec.view(np.uint8).reshape(-1)).cuda()
+    d_g = torch.from_numpy((rng.random((3 * (U // 24), 4)) * 0.2 + 0.9).astype(np.float32)).cuda()
+    w = rng.random((3, 256)).astype(np.float32)
+    d_w = torch.from_numpy((w / w.sum(0)).astype(np.float32)).cuda()
+    ms = timeit(lambda i: lib.drc_stft_dev(x.data_ptr(), state.data_ptr(), d_rec.data_ptr(), 1, d_g.data_ptr(),
+                                           d_w.data_ptr(), U, st))
+    report("drc in the STFT domain (t2f + 3-band gains + f2t), 6144 channel-frames", ms, U * (8192 + 4096), U * 1024,
+           "channel_samples")
+
+
 def tns_rs_stage():
     import tns_cases
     from libmpegh_b200.lib import TNS_FILTER_DTYPE
@@ -408,7 +429,7 @@ def fd_path_stage():
     lib.bands_destroy(bands)
 
 
-STAGES = {"mct": mct_stage, "binaural": binaural_stage, "hoa": hoa_chain_stage, "fc": fc_stage, "tns_rs": tns_rs_stage,
+STAGES = {"mct": mct_stage, "drc": drc_stage, "binaural": binaural_stage, "hoa": hoa_chain_stage, "fc": fc_stage, "tns_rs": tns_rs_stage,
           "fd_path": fd_path_stage,
           "spectral": spectral_stage,
           "obj": obj_stage, "hoa_render": hoa_render_stage}
@@ -423,6 +444,7 @@ hoa_chain_stage()
 fc_stage()
 tns_rs_stage()
 mct_stage()
+drc_stage()
 spectral_stage()
 fd_path_stage()
 binaural_stage()
