@@ -98,6 +98,9 @@ __global__ void __launch_bounds__(kWarps * 32) format_conv_kernel(const __grid_c
   }
   if (tid < P.n_in)  // the frame's input rows on their way into L2 while the state is being read
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x + size_t(tid) * 1024), "r"(4096) : "memory");
+  if (tid >= 32 && tid < 32 + P.n_in)  // and the previous frame's last input slots
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(st_in + size_t(tid - 32) * 256), "r"(1024)
+                 : "memory");
   // per (output, ERB band) chains owned by this thread: smoothed energies carried in registers across slots
   constexpr int kChains = 4;  // ceil(24 * 58 / 384)
   float tprev[kChains], rprev[kChains];
@@ -215,7 +218,9 @@ __global__ void __launch_bounds__(kWarps * 32) format_conv_kernel(const __grid_c
           tcur[q] = t;
         }
       }
-      __syncthreads();
+      // the squares are next overwritten by the following pass; after the last pass by phase 3, which starts behind
+      // the barrier that ends 2c: no barrier needed here then, and 2c joins the last pass's chain phase
+      if (a0 + P.ranks < P.max_active) __syncthreads();
     }
     // ---- 2c. realised energy, smoothing, EQ ----------------------------------------------------------------
 #pragma unroll
