@@ -459,8 +459,9 @@ __global__ void __launch_bounds__(kChunk, (NC <= 25) ? 3 : 2)
 
   // Ambience + spatial prediction per coefficient in a ROLLED loop (its body is big: unrolled 25 times it thrashed
   // the instruction cache -- ncu: most stall samples of the first version were "no instruction"); the sum is parked
-  // in the output element this thread owns and picked up again by the small unrolled loop below, which needs the
-  // register arrays v[] and d[].
+  // in a shared-memory column this thread owns (a round trip through the output element itself cost an L2 latency
+  // per coefficient) and picked up again by the small unrolled loop below, which needs the register arrays v[], d[].
+  extern __shared__ float ap_s[];  // [NC][kChunk]: the parked sums, one column per thread
 #pragma unroll 1
   for (int c = 0; c < NC; ++c) {
     const int in_en = pl.in_en[c], in_dis = pl.in_dis[c];
@@ -502,7 +503,7 @@ __global__ void __launch_bounds__(kChunk, (NC <= 25) ? 3 : 2)
       if (pl.pred_flag[0])
         for (int i = 0; i < in_dis; ++i) pred = fmul(pred, w[2]);
     }
-    y[size_t(c) * kFrame + t] = fadd(amb, pred);
+    ap_s[c * kChunk + tid] = fadd(amb, pred);
   }
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
@@ -512,15 +513,17 @@ __global__ void __launch_bounds__(kChunk, (NC <= 25) ? 3 : 2)
       for (int i = 0; i < in_en; ++i) vv = fmul(vv, w[3]);
       for (int i = 0; i < in_dis; ++i) vv = fmul(vv, w[2]);
     }
-    const float ap = y[size_t(c) * kFrame + t];  // written by this very thread above
-    __stcs(y + size_t(c) * kFrame + t, fadd(vv, fadd(ap, d[c])));
+    __stcs(y + size_t(c) * kFrame + t, fadd(vv, fadd(ap_s[c * kChunk + tid], d[c])));
   }
 }
 
 template <int NC>
 cudaError_t launch_render(const float* in, float* out, const Slot* slots, const Cfg& cfg, int n_streams,
                           cudaStream_t st) {
-  hoasp_render_kernel<NC><<<dim3(n_streams, kFrame / kChunk), kChunk, 0, st>>>(in, out, slots, cfg);
+  const int smem = NC * kChunk * int(sizeof(float));
+  cudaError_t e = cudaFuncSetAttribute(hoasp_render_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  hoasp_render_kernel<NC><<<dim3(n_streams, kFrame / kChunk), kChunk, smem, st>>>(in, out, slots, cfg);
   return cudaGetLastError();
 }
 
