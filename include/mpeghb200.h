@@ -546,6 +546,33 @@ mpeghb200_status mpeghb200_drc_stft_dev(mpeghb200_ctx *ctx, float *d_audio, floa
                                         const mpeghb200_drc_sb_channel *d_chan, int n_sets, const float *d_gains,
                                         const float *d_weights, int n_channels, void *cuda_stream);
 
+/* Time-domain multi-band DRC of one selected set, in place on d_audio [n_channels][1024]: phase-alignment all-pass
+ * cascade, Linkwitz-Riley band split (2, 3 or 4 bands), per-band gain curves, band sum --
+ * impd_drc_filter_banks_process (decoder/impd_drc_process.c:399; banks decoder/impd_drc_filter_bank.c:367-613) and the
+ * multiply-and-sum of impd_drc_apply_gains_and_add (:68-225), chained as in impd_drc_td_process (:529).  The host
+ * designs the coefficients (impd_drc_init_all_filter_banks) and interpolates the gains: d_gains [n_seq][1024], the
+ * bands of a channel group consecutive.  d_banks: one record per channel group plus, if needed, one for the channels
+ * outside every group (only its cascade applies).  d_state [n_channels][mpeghb200_drc_td_state_floats()], zero at
+ * stream start (the x_p / y_p memories of ia_iir_filter_struct). */
+typedef struct mpeghb200_drc_biquad {
+  float a1, a2, b0, b1, b2;
+} mpeghb200_drc_biquad;
+typedef struct mpeghb200_drc_td_bank {
+  int32_t n_bands;   /* 1..4 */
+  int32_t n_cascade; /* all-pass sections the reference runs: 0, or str_all_pass_cascade.num_filter + 1 (:604) */
+  /* 2 bands: lp, hp; 3: lp_1, hp_1, ap_2, lp_2, hp_2; 4: lp_1, hp_1, ap_2_low, ap_2_high, lp_3_low, hp_3_low, lp_3_high, hp_3_high */
+  mpeghb200_drc_biquad f[8];
+  mpeghb200_drc_biquad ap[9]; /* str_ap_cascade_filt[0 .. n_cascade - 1] */
+} mpeghb200_drc_td_bank;
+typedef struct mpeghb200_drc_td_channel {
+  int32_t bank;      /* index into d_banks */
+  int32_t first_seq; /* first gain sequence of the channel's group; < 0: channel outside every group */
+} mpeghb200_drc_td_channel;
+size_t mpeghb200_drc_td_state_floats(void);
+mpeghb200_status mpeghb200_drc_td_dev(mpeghb200_ctx *ctx, float *d_audio, float *d_state,
+                                      const mpeghb200_drc_td_channel *d_chan, const mpeghb200_drc_td_bank *d_banks,
+                                      const float *d_gains, int n_channels, void *cuda_stream);
+
 /* ---- LTPF: long-term post-filter of FD channels, in place on the time signal after FD synthesis -------------
  * Replaces ia_core_coder_usac_ltpf_process (decoder/ia_core_coder_ltpf.c:395), called per FD channel right after
  * ia_core_coder_fd_frm_dec (decoder/ia_core_coder_ext_ch_ele.c:1977); SURVEY.md section 8f rank 3.  The side record

@@ -1,0 +1,170 @@
+// drc_td.cu -- time-domain multi-band DRC: Linkwitz-Riley filter banks, per-band gain curves, band sum.
+//
+// Stands in for impd_drc_filter_banks_process (decoder/impd_drc_process.c:399) with the banks of
+// decoder/impd_drc_filter_bank.c (low/high pair :410, all-pass :367, two/three/four-band trees :486, :511, :550,
+// phase-alignment cascade :601) and for the multiply-and-sum of impd_drc_apply_gains_and_add (:68-225), as
+// impd_drc_td_process (:529) chains them for one selected DRC set.  SURVEY.md section 8f rank 2.  Coefficient design
+// (impd_drc_init_all_filter_banks), gain decoding and interpolation stay on the host.
+//
+// Every filter is a serial recurrence over the frame, and the all-pass sections of the reference run BACKWARDS over
+// it (filter_bank.c:380), so the stages of a tree cannot be fused per sample: a warp owns a channel-frame, keeps its
+// band signals in six shared-memory rows, and runs the independent recurrences of a stage on separate lanes (up to
+// four: the low/high pairs of stage 3 of the four-band tree); rows are assigned so that no lane writes a row another
+// lane reads in the same stage.  The sections of the phase-alignment cascade are applied per sample in one loop
+// (same order per section as the reference's section-after-section passes).  All 32 lanes move the data in and
+// apply the gains and the band sum.  Bound: the recurrence latency (about 16 cycles per sample and stage).
+#include "common.h"
+
+namespace mpeghb200 {
+namespace {
+
+constexpr int kN = 1024;
+constexpr int kRows = 6;
+constexpr int kTdWarps = 2;
+constexpr int kStateFloats = 17 * 4;
+
+// one branch of impd_drc_apply_low_high_filter: two cascaded sections with the same coefficients
+__device__ __forceinline__ void lh_branch(const mpeghb200_drc_biquad f, float* __restrict__ st,
+                                          const float* __restrict__ in, float* __restrict__ out) {
+  float s1 = st[0], s2 = st[1], s3 = st[2], s4 = st[3];
+#pragma unroll 4
+  for (int i = 0; i < kN; ++i) {
+    const float x = in[i];
+    const float t = fadd(s1, fmul(f.b0, x));
+    s1 = fadd(fsub(fmul(f.b1, x), fmul(f.a1, t)), s2);
+    s2 = fsub(fmul(f.b2, x), fmul(f.a2, t));
+    const float o = fadd(s3, fmul(f.b0, t));
+    s3 = fadd(fsub(fmul(f.b1, t), fmul(f.a1, o)), s4);
+    s4 = fsub(fmul(f.b2, t), fmul(f.a2, o));
+    out[i] = o;
+  }
+  st[0] = s1, st[1] = s2, st[2] = s3, st[3] = s4;
+}
+
+// impd_drc_iir_second_order_all_pass_filter: last sample first; state in slots 0 and 2 (x_p[2 ch], y_p[2 ch])
+__device__ __forceinline__ void allpass(const mpeghb200_drc_biquad f, float* __restrict__ st, const float* in,
+                                        float* out) {
+  float s1 = st[0], s2 = st[2];
+#pragma unroll 4
+  for (int i = kN - 1; i >= 0; --i) {
+    const float x = in[i];
+    const float y = fadd(fmul(f.b0, x), s1);
+    s1 = fadd(fsub(fmul(f.b1, x), fmul(f.a1, y)), s2);
+    s2 = fsub(fmul(f.b2, x), fmul(f.a2, y));
+    out[i] = y;
+  }
+  st[0] = s1, st[2] = s2;
+}
+
+__global__ void __launch_bounds__(32 * kTdWarps)
+    drc_td_kernel(float* __restrict__ audio, float* __restrict__ state, const mpeghb200_drc_td_channel* __restrict__ chan,
+                  const mpeghb200_drc_td_bank* __restrict__ banks, const float* __restrict__ gains, int n_ch) {
+  extern __shared__ __align__(16) float rows_all[];  // [kTdWarps][kRows][kN]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * kTdWarps + warp;
+  if (c >= n_ch) return;  // whole warp; no CTA-wide barrier below
+  float* B[kRows];
+#pragma unroll
+  for (int r = 0; r < kRows; ++r) B[r] = rows_all + (size_t(warp) * kRows + r) * kN;
+  const mpeghb200_drc_td_channel ch = chan[c];
+  const mpeghb200_drc_td_bank& bank = banks[ch.bank];
+  float* x = audio + size_t(c) * kN;
+  float* st = state + size_t(c) * kStateFloats;
+  const int nb = bank.n_bands < 1 ? 1 : (bank.n_bands > 4 ? 4 : bank.n_bands);
+  const int n_casc = bank.n_cascade < 0 ? 0 : (bank.n_cascade > 9 ? 9 : bank.n_cascade);
+  const bool grouped = ch.first_seq >= 0;
+  if (!grouped && n_casc == 0) return;  // untouched channel
+  for (int i = lane; i < kN / 4; i += 32)
+    reinterpret_cast<float4*>(B[0])[i] = __ldcs(reinterpret_cast<const float4*>(x) + i);
+  __syncwarp();
+  // ---- phase-alignment cascade, sections n_casc-1 .. 0, in place, last sample first (filter_bank.c:601) ----
+  if (n_casc > 0 && lane == 0) {
+    float s1[9], s2[9];
+    mpeghb200_drc_biquad f[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+      if (k < n_casc) f[k] = bank.ap[k], s1[k] = st[4 * (8 + k)], s2[k] = st[4 * (8 + k) + 2];
+    for (int i = kN - 1; i >= 0; --i) {
+      float v = B[0][i];
+#pragma unroll
+      for (int k = 8; k >= 0; --k)
+        if (k < n_casc) {
+          const float y = fadd(fmul(f[k].b0, v), s1[k]);
+          s1[k] = fadd(fsub(fmul(f[k].b1, v), fmul(f[k].a1, y)), s2[k]);
+          s2[k] = fsub(fmul(f[k].b2, v), fmul(f[k].a2, y));
+          v = y;
+        }
+      B[0][i] = v;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+      if (k < n_casc) st[4 * (8 + k)] = s1[k], st[4 * (8 + k) + 2] = s2[k];
+  }
+  __syncwarp();
+  if (!grouped) {  // outside every channel group: only the cascade applies (impd_drc_process.c:204-207)
+    for (int i = lane; i < kN / 4; i += 32) __stcs(reinterpret_cast<float4*>(x) + i, reinterpret_cast<float4*>(B[0])[i]);
+    return;
+  }
+  // ---- band split; row plan: no lane writes a row another lane reads in the same stage ----
+  const float* band[4] = {B[0], B[0], B[0], B[0]};
+  if (nb >= 2) {  // stage 1: B0 -> low B1, high B2
+    if (lane == 0) lh_branch(bank.f[0], st + 0, B[0], B[1]);
+    if (lane == 1) lh_branch(bank.f[1], st + 4, B[0], B[2]);
+    __syncwarp();
+    band[0] = B[1], band[1] = B[2];
+  }
+  if (nb == 3) {  // all-pass on the high branch (-> band 2) next to the second split of the low branch
+    if (lane == 0) allpass(bank.f[2], st + 8, B[2], B[3]);
+    if (lane == 1) lh_branch(bank.f[3], st + 12, B[1], B[4]);
+    if (lane == 2) lh_branch(bank.f[4], st + 16, B[1], B[5]);
+    __syncwarp();
+    band[0] = B[4], band[1] = B[5], band[2] = B[3];
+  } else if (nb == 4) {
+    if (lane == 0) allpass(bank.f[2], st + 8, B[1], B[1]);   // in place: a single reader / writer
+    if (lane == 1) allpass(bank.f[3], st + 12, B[2], B[2]);
+    __syncwarp();
+    if (lane == 0) lh_branch(bank.f[4], st + 16, B[1], B[0]);
+    if (lane == 1) lh_branch(bank.f[5], st + 20, B[1], B[3]);
+    if (lane == 2) lh_branch(bank.f[6], st + 24, B[2], B[4]);
+    if (lane == 3) lh_branch(bank.f[7], st + 28, B[2], B[5]);
+    __syncwarp();
+    band[0] = B[0], band[1] = B[3], band[2] = B[4], band[3] = B[5];
+  }
+  // ---- gains and band sum, highest band first (impd_drc_process.c:150-155, :211-219) ----
+  const float* g = gains + size_t(ch.first_seq) * kN;
+  for (int i = lane; i < kN; i += 32) {
+    float sum = 0.0f;
+#pragma unroll
+    for (int k = 3; k >= 0; --k)
+      if (k < nb) sum = fadd(sum, fmul(band[k][i], __ldg(g + k * kN + i)));
+    __stcs(x + i, sum);
+  }
+}
+
+}  // namespace
+}  // namespace mpeghb200
+
+using namespace mpeghb200;
+
+extern "C" {
+
+size_t mpeghb200_drc_td_state_floats(void) { return kStateFloats; }
+
+mpeghb200_status mpeghb200_drc_td_dev(mpeghb200_ctx* ctx, float* d_audio, float* d_state,
+                                      const mpeghb200_drc_td_channel* d_chan, const mpeghb200_drc_td_bank* d_banks,
+                                      const float* d_gains, int n_channels, void* cuda_stream) {
+  if (!ctx) return MPEGHB200_ERR_BAD_ARG;
+  if (n_channels < 0 || (n_channels > 0 && (!d_audio || !d_state || !d_chan || !d_banks || !d_gains)))
+    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "drc_td_dev: null buffer or negative channel count");
+  if (n_channels == 0) return MPEGHB200_OK;
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int smem = kTdWarps * kRows * kN * int(sizeof(float));
+  MB_CUDA(ctx, cudaFuncSetAttribute(drc_td_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  drc_td_kernel<<<(n_channels + kTdWarps - 1) / kTdWarps, 32 * kTdWarps, smem, static_cast<cudaStream_t>(cuda_stream)>>>(
+      d_audio, d_state, d_chan, d_banks, d_gains, n_channels);
+  ctx->launches.fetch_add(1);
+  MB_CUDA(ctx, cudaGetLastError());
+  return MPEGHB200_OK;
+}
+
+}  // extern "C"

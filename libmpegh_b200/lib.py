@@ -82,6 +82,10 @@ LTPF_SIDE_DTYPE = np.dtype([("unit", "<i4"), ("pitch_lag_idx", "<u2"), ("data_pr
 DRC_SB_CHANNEL_DTYPE = np.dtype([("first_seq", np.int32), ("band_count", np.int32), ("weight_row", np.int32),
                                  ("reserved", np.int32)])
 
+DRC_TD_BANK_DTYPE = np.dtype([("n_bands", np.int32), ("n_cascade", np.int32), ("f", np.float32, (8, 5)),
+                              ("ap", np.float32, (9, 5))])
+DRC_TD_CHANNEL_DTYPE = np.dtype([("bank", np.int32), ("first_seq", np.int32)])
+
 MCT_BOX_DTYPE = np.dtype([("unit_l", np.int32), ("unit_r", np.int32), ("op", np.int32), ("n_seg", np.int32),
                           ("start", np.int16, 64), ("len", np.int16, 64), ("coef", np.int16, 64)])
 
@@ -236,6 +240,9 @@ class Lib:
         c.mpeghb200_gain_subband_dev.restype = i32
         c.mpeghb200_drc_stft_dev.argtypes = [vp, vp, vp, vp, ctypes.c_int, vp, vp, ctypes.c_int, vp]
         c.mpeghb200_drc_stft_dev.restype = i32
+        c.mpeghb200_drc_td_dev.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
+        c.mpeghb200_drc_td_dev.restype = i32
+        c.mpeghb200_drc_td_state_floats.restype = sz
         c.mpeghb200_mct_resolve.argtypes = [ctypes.c_int] * 7 + [vp, vp, vp, ctypes.c_int, ctypes.c_int, vp]
         c.mpeghb200_mct_resolve.restype = i32
         c.mpeghb200_mct_dev.argtypes = [vp, vp, vp, vp, ctypes.c_int, vp]
@@ -422,6 +429,12 @@ class Lib:
     def drc_stft_dev(self, d_audio, d_state, d_chan, n_sets, d_gains, d_weights, n_channels, stream=0):
         self.check(self.c.mpeghb200_drc_stft_dev(self.ctx, d_audio, d_state, d_chan, n_sets, d_gains, d_weights,
                                                  n_channels, stream))
+
+    def drc_td_dev(self, d_audio, d_state, d_chan, d_banks, d_gains, n_channels, stream=0):
+        self.check(self.c.mpeghb200_drc_td_dev(self.ctx, d_audio, d_state, d_chan, d_banks, d_gains, n_channels, stream))
+
+    def drc_td_state_floats(self):
+        return int(self.c.mpeghb200_drc_td_state_floats())
 
     def bus_add_dev(self, d_a, d_b, d_out, n_floats, stream=0):
         self.check(self.c.mpeghb200_bus_add_dev(self.ctx, d_a, d_b, d_out, n_floats, stream))

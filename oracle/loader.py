@@ -112,6 +112,7 @@ def load_oracle():
     lib.oracle_ltpf_process.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p]
     lib.oracle_drc_gains_subband.argtypes = [_f32p, _f32p, ctypes.c_int, _i32p, _i32p, ctypes.c_int, _f32p, _f32p,
                                              ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.oracle_drc_td_channel.argtypes = [ctypes.c_void_p, _f32p, _f32p, ctypes.c_void_p]
     lib.oracle_ds_t2f.argtypes = [_f32p, _f32p, _f32p, _f32p, _f32p, ctypes.c_int]
     lib.oracle_ds_f2t.argtypes = [_f32p, _f32p, _f32p, _f32p, _f32p, ctypes.c_int]
     _mct_args = [_f32p, _f32p, _i32p, _i32p, ctypes.c_int, ctypes.c_int, _i16p] + [ctypes.c_int] * 4
@@ -400,6 +401,12 @@ def load_ref_ns():
     lib = ctypes.CDLL(so)
     lib.ref_samples_sat.argtypes = [_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _i32p, _i32p, _u8p]
     lib.ref_samples_sat.restype = ctypes.c_int
+    _i32q = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+    lib.ref_drctd_create.restype = ctypes.c_void_p
+    lib.ref_drctd_create.argtypes = [ctypes.c_int, _i32q, ctypes.c_int, ctypes.c_void_p]
+    lib.ref_drctd_destroy.argtypes = [ctypes.c_void_p]
+    lib.ref_drctd_process.argtypes = [ctypes.c_void_p, _f32p, _f32p]
+    lib.ref_drctd_process.restype = ctypes.c_int
     _ref_ns = lib
     return lib
 
@@ -594,6 +601,11 @@ class OracleResampler:
         out = np.zeros(1024 * self.up // self.down, np.float32)
         load_oracle().oracle_rs_process(self.state, self.up, self.down, self.f_up, self.f_down, x, out)
         return out
+
+
+# ---- time-domain multi-band DRC -------------------------------------------------------------------------
+DRC_BANK_DTYPE = np.dtype([("n_bands", np.int32), ("n_cascade", np.int32), ("f", np.float32, (8, 5)),
+                           ("ap", np.float32, (9, 5))])  # oracle_drc_bank / mpeghb200_drc_td_bank
 
 
 # ---- LTPF -----------------------------------------------------------------------------------------------

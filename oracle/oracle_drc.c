@@ -105,3 +105,88 @@ void oracle_ds_f2t(const float *win, float *out_hist /*[n_ch][256]*/, const floa
       }
     }
 }
+
+/* ---- time-domain multi-band DRC: filter banks, per-band gain curves, band sum -------------------------------
+ * impd_drc_filter_banks_process (decoder/impd_drc_process.c:399), the Linkwitz-Riley banks of
+ * decoder/impd_drc_filter_bank.c (low/high pair :410, all-pass :367, 2/3/4-band trees :486,:511,:550, phase
+ * alignment cascade :601) and the gain/sum stage of impd_drc_apply_gains_and_add (impd_drc_process.c:68-225) for one
+ * channel.  Reference quirks kept: the all-pass sections run BACKWARDS over the frame (:380) with carried state;
+ * the cascade runs sections num_filter .. 0 (:604), i.e. n_cascade = num_filter + 1 of them. */
+static void lowhigh(const oracle_drc_biquad *lp, const oracle_drc_biquad *hp, float *sl, float *sh, float *lo,
+                    float *hi, const float *in, int n)
+{
+  float s1l = sl[0], s2l = sl[1], s3l = sl[2], s4l = sl[3], s1h = sh[0], s2h = sh[1], s3h = sh[2], s4h = sh[3];
+  for (int i = 0; i < n; ++i)
+  {
+    const float x = in[i];
+    float t = s1l + lp->b0 * x;
+    s1l = (lp->b1 * x - lp->a1 * t) + s2l;
+    s2l = lp->b2 * x - lp->a2 * t;
+    const float ol = s3l + lp->b0 * t;
+    s3l = (lp->b1 * t - lp->a1 * ol) + s4l;
+    s4l = lp->b2 * t - lp->a2 * ol;
+    t = s1h + hp->b0 * x;
+    s1h = (hp->b1 * x - hp->a1 * t) + s2h;
+    s2h = hp->b2 * x - hp->a2 * t;
+    const float oh = s3h + hp->b0 * t;
+    s3h = (hp->b1 * t - hp->a1 * oh) + s4h;
+    s4h = hp->b2 * t - hp->a2 * oh;
+    lo[i] = ol, hi[i] = oh;
+  }
+  sl[0] = s1l, sl[1] = s2l, sl[2] = s3l, sl[3] = s4l, sh[0] = s1h, sh[1] = s2h, sh[2] = s3h, sh[3] = s4h;
+}
+
+static void allpass(const oracle_drc_biquad *f, float *st, float *out, const float *in, int n)
+{
+  float s1 = st[0], s2 = st[2]; /* x_p[2 ch], y_p[2 ch] */
+  for (int i = n - 1; i >= 0; --i)
+  {
+    const float x = in[i];
+    const float y = f->b0 * x + s1;
+    s1 = (f->b1 * x - f->a1 * y) + s2;
+    s2 = f->b2 * x - f->a2 * y;
+    out[i] = y;
+  }
+  st[0] = s1, st[2] = s2;
+}
+
+/* x [1024] in place; state [17][4] (bank filters 0..7, cascade sections 8..16); gains [n_bands][1024] or NULL for a
+ * channel outside every DRC channel group (then only the cascade touches it) */
+void oracle_drc_td_channel(const oracle_drc_bank *bank, float *state, float *x, const float *gains)
+{
+  static __thread float b[4][1024];
+  const int n = 1024;
+  for (int i = bank->n_cascade - 1; i >= 0; --i) allpass(&bank->ap[i], state + 4 * (8 + i), x, x, n);
+  if (!gains) return;
+  const oracle_drc_biquad *f = bank->f;
+  switch (bank->n_bands)
+  {
+  case 2:
+    lowhigh(&f[0], &f[1], state + 0, state + 4, b[0], b[1], x, n);
+    break;
+  case 3:
+    lowhigh(&f[0], &f[1], state + 0, state + 4, b[0], b[1], x, n);
+    allpass(&f[2], state + 8, b[2], b[1], n);
+    lowhigh(&f[3], &f[4], state + 12, state + 16, b[0], b[1], b[0], n);
+    break;
+  case 4:
+    lowhigh(&f[0], &f[1], state + 0, state + 4, b[0], b[1], x, n);
+    allpass(&f[2], state + 8, b[0], b[0], n);
+    allpass(&f[3], state + 12, b[2], b[1], n);
+    lowhigh(&f[4], &f[5], state + 16, state + 20, b[0], b[1], b[0], n);
+    lowhigh(&f[6], &f[7], state + 24, state + 28, b[2], b[3], b[2], n);
+    break;
+  default:
+    for (int i = 0; i < n; ++i) b[0][i] = x[i];
+    break;
+  }
+  const int nb = bank->n_bands < 1 ? 1 : bank->n_bands;
+  for (int k = 0; k < nb; ++k)
+    for (int i = 0; i < n; ++i) b[k][i] = b[k][i] * gains[k * 1024 + i];
+  for (int i = 0; i < n; ++i)
+  {
+    float sum = 0.0f;
+    for (int k = nb - 1; k >= 0; --k) sum = sum + b[k][i];
+    x[i] = sum;
+  }
+}

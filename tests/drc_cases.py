@@ -77,3 +77,64 @@ def stft_chain(oracle, win, rng, n_frames, n_ch=12, ref=None, frames_out=None):
     if h is not None:
         ref.ref_ds_destroy(h)
     return np.stack(outs)
+
+
+# ---- time-domain multi-band DRC (decoder/impd_drc_process.c:399, :68; decoder/impd_drc_filter_bank.c) ---------
+def random_biquad(rng):
+    """a stable second-order section (a1, a2, b0, b1, b2)"""
+    r, th = rng.uniform(0.3, 0.92), rng.uniform(0.05, 3.0)
+    return np.array([-2 * r * np.cos(th), r * r, rng.uniform(0.2, 1.0), rng.uniform(-1, 1), rng.uniform(-0.5, 0.5)],
+                    np.float32)
+
+
+def random_td_frame_setup(rng, n_ch=None):
+    """channel groups with 1..4 bands, a bank per group plus one for ungrouped channels (phase alignment cascades)"""
+    from oracle.loader import DRC_BANK_DTYPE
+    n_ch = int(rng.integers(1, 13)) if n_ch is None else n_ch
+    n_groups = int(rng.integers(1, 4))
+    banks = np.zeros(n_groups + 1, DRC_BANK_DTYPE)
+    for g in range(n_groups + 1):
+        banks[g]["n_bands"] = int(rng.integers(1, 5)) if g < n_groups else 1
+        banks[g]["n_cascade"] = int(rng.choice([0, 0, 2, 3, 5]))
+        banks[g]["f"] = np.stack([random_biquad(rng) for _ in range(8)])
+        banks[g]["ap"] = np.stack([random_biquad(rng) for _ in range(9)])
+    group_of_ch = rng.integers(-1, n_groups, n_ch).astype(np.int32)
+    return dict(n_ch=n_ch, n_groups=n_groups, banks=banks, group_of_ch=group_of_ch,
+                n_seq=int(banks["n_bands"][:n_groups].sum()))
+
+
+def td_frames(rng, setup, n_frames):
+    return [((rng.standard_normal((setup["n_ch"], 1024)) * 3000).astype(np.float32),
+             (rng.random((max(setup["n_seq"], 1), 1024)) + 0.5).astype(np.float32)) for _ in range(n_frames)]
+
+
+def td_oracle(oracle, setup, frames):
+    """-> [n_frames][n_ch][1024] through oracle_drc_td_channel, state carried per channel"""
+    first = np.concatenate([[0], np.cumsum(setup["banks"]["n_bands"][:setup["n_groups"]])])
+    state = np.zeros((setup["n_ch"], 17 * 4), np.float32)
+    outs = []
+    for x, gains in frames:
+        y = x.copy()
+        for c in range(setup["n_ch"]):
+            g = int(setup["group_of_ch"][c])
+            bank = setup["banks"][g if g >= 0 else setup["n_groups"]:][:1]
+            row = np.ascontiguousarray(y[c])
+            gp = None
+            if g >= 0:
+                gg = np.ascontiguousarray(gains[int(first[g]):int(first[g]) + int(bank["n_bands"][0])])
+                gp = gg.ctypes.data
+            oracle.oracle_drc_td_channel(bank.ctypes.data, state[c], row, gp)
+            y[c] = row
+        outs.append(y)
+    return np.stack(outs)
+
+
+def td_reference(ref_ns, setup, frames):
+    h = ref_ns.ref_drctd_create(setup["n_ch"], setup["group_of_ch"], setup["n_groups"], setup["banks"].ctypes.data)
+    outs = []
+    for x, gains in frames:
+        y = x.copy()
+        assert ref_ns.ref_drctd_process(h, y.reshape(-1), np.ascontiguousarray(gains).reshape(-1)) == 0
+        outs.append(y)
+    ref_ns.ref_drctd_destroy(h)
+    return np.stack(outs)

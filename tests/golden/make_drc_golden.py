@@ -25,5 +25,13 @@ for i in range(N):
 out["chain_seed"], out["chain_frames"] = 99, 3
 win = np.ascontiguousarray(loader.golden_rom()["sine_256"], np.float32)
 out["chain_out"] = drc_cases.stft_chain(None, win, np.random.default_rng(99), 3, ref=ref)
+# time-domain multi-band DRC through the reference (static functions: the -Dstatic= build)
+ref_ns = loader.load_ref_ns()
+out["td_seed"], out["td_cases"] = 3100, 4
+for i in range(4):
+    rng2 = np.random.default_rng(3100 + i)
+    setup = drc_cases.random_td_frame_setup(rng2)
+    frames = drc_cases.td_frames(rng2, setup, 2)
+    out[f"td_out_{i}"] = drc_cases.td_reference(ref_ns, setup, frames)
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "drc_golden.npz"), **out)
 print("wrote drc_golden.npz")

@@ -95,3 +95,65 @@ def test_fused_stft_chain(gpu_lib, oracle, n_ch, n_frames, seed):
                              d_w.data_ptr(), n_ch, st)
         torch.cuda.synchronize()
         assert bits_equal(d_x.cpu().numpy(), want[f]), f
+
+
+def run_td_gpu(gpu_lib, setups_frames):
+    """several independent streams (setup, frames) in one launch per frame index; -> list of [n_frames][n_ch][1024]"""
+    import torch
+    from libmpegh_b200.lib import DRC_TD_BANK_DTYPE, DRC_TD_CHANNEL_DTYPE
+    chans, banks = [], []
+    seq0 = bank0 = 0
+    for setup, _ in setups_frames:
+        first = np.concatenate([[0], np.cumsum(setup["banks"]["n_bands"][:setup["n_groups"]])])
+        ch = np.zeros(setup["n_ch"], DRC_TD_CHANNEL_DTYPE)
+        for c, g in enumerate(setup["group_of_ch"]):
+            ch[c]["bank"] = bank0 + (int(g) if g >= 0 else setup["n_groups"])
+            ch[c]["first_seq"] = seq0 + int(first[g]) if g >= 0 else -1
+        chans.append(ch)
+        banks.append(setup["banks"].astype(DRC_TD_BANK_DTYPE))
+        seq0 += max(setup["n_seq"], 1)
+        bank0 += len(setup["banks"])
+    chan = np.concatenate(chans)
+    n_ch = len(chan)
+    d_chan = torch.from_numpy(chan.view(np.uint8).reshape(-1)).cuda()
+    d_banks = torch.from_numpy(np.concatenate(banks).view(np.uint8).reshape(-1)).cuda()
+    d_state = torch.zeros(n_ch * gpu_lib.drc_td_state_floats(), device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    n_frames = len(setups_frames[0][1])
+    outs = []
+    for f in range(n_frames):
+        d_x = torch.from_numpy(np.concatenate([fr[f][0] for _, fr in setups_frames])).cuda()
+        d_g = torch.from_numpy(np.concatenate([fr[f][1] for _, fr in setups_frames])).cuda()
+        gpu_lib.drc_td_dev(d_x.data_ptr(), d_state.data_ptr(), d_chan.data_ptr(), d_banks.data_ptr(), d_g.data_ptr(),
+                           n_ch, st)
+        torch.cuda.synchronize()
+        outs.append(d_x.cpu().numpy())
+    res, c = [], 0
+    for setup, _ in setups_frames:
+        res.append(np.stack([o[c:c + setup["n_ch"]] for o in outs]))
+        c += setup["n_ch"]
+    return res
+
+
+def test_td_multiband_golden(gpu_lib):
+    g = np.load(GOLD)
+    sf = []
+    for i in range(int(g["td_cases"])):
+        rng = np.random.default_rng(int(g["td_seed"]) + i)
+        setup = drc_cases.random_td_frame_setup(rng)
+        sf.append((setup, drc_cases.td_frames(rng, setup, 2)))
+    got = run_td_gpu(gpu_lib, sf)
+    for i in range(len(sf)):
+        assert bits_equal(got[i], g[f"td_out_{i}"]), i
+
+
+@pytest.mark.parametrize("n_streams,seed", [(1, 0), (40, 1), (256, 2)])
+def test_td_multiband_matches_oracle(gpu_lib, oracle, n_streams, seed):
+    rng = np.random.default_rng(2200 + seed)
+    sf = []
+    for _ in range(n_streams):
+        setup = drc_cases.random_td_frame_setup(rng)
+        sf.append((setup, drc_cases.td_frames(rng, setup, 3 if n_streams < 100 else 2)))
+    got = run_td_gpu(gpu_lib, sf)
+    for (setup, frames), y in zip(sf, got):
+        assert bits_equal(y, drc_cases.td_oracle(oracle, setup, frames))

@@ -77,3 +77,27 @@ def test_stft_chain_matches_golden():
     rng = np.random.default_rng(int(g["chain_seed"]))
     out = drc_cases.stft_chain(o, _win(), rng, int(g["chain_frames"]))
     assert loader.bits_equal(out, g["chain_out"])
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_td_multiband_matches_reference(seed):
+    """oracle_drc_td_channel vs impd_drc_filter_banks_process + impd_drc_apply_gains_and_add (static, reached through
+    the -Dstatic= build), three frames with carried filter memories."""
+    r = loader.load_ref_ns()
+    if r is None:
+        pytest.skip("reference build not available")
+    o = loader.load_oracle()
+    rng = np.random.default_rng(60 + seed)
+    setup = drc_cases.random_td_frame_setup(rng)
+    frames = drc_cases.td_frames(rng, setup, 3)
+    assert loader.bits_equal(drc_cases.td_oracle(o, setup, frames), drc_cases.td_reference(r, setup, frames))
+
+
+def test_td_multiband_matches_golden():
+    o = loader.load_oracle()
+    g = np.load(GOLD)
+    for i in range(int(g["td_cases"])):
+        rng = np.random.default_rng(int(g["td_seed"]) + i)
+        setup = drc_cases.random_td_frame_setup(rng)
+        frames = drc_cases.td_frames(rng, setup, 2)
+        assert loader.bits_equal(drc_cases.td_oracle(o, setup, frames), g[f"td_out_{i}"])

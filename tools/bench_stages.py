@@ -189,6 +189,28 @@ def drc_stage():
            "channel_samples")
 
 
+def drc_td_stage():
+    """Time-domain multi-band DRC: 6144 channel-frames, 3-band Linkwitz-Riley banks, gain curves, band sum."""
+    import drc_cases
+    from libmpegh_b200.lib import DRC_TD_BANK_DTYPE, DRC_TD_CHANNEL_DTYPE
+    U = 6144
+    rng = np.random.default_rng(6)
+    banks = np.zeros(1, DRC_TD_BANK_DTYPE)
+    banks[0]["n_bands"], banks[0]["n_cascade"] = 3, 0
+    banks[0]["f"] = np.stack([drc_cases.random_biquad(rng) for _ in range(8)])
+    chan = np.zeros(U, DRC_TD_CHANNEL_DTYPE)
+    chan["first_seq"] = 3 * (np.arange(U) // 24)
+    x = torch.randn(U, 1024, device="cuda") * 3000
+    state = torch.zeros(U * lib.drc_td_state_floats(), device="cuda")
+    d_chan = torch.from_numpy(chan.view(np.uint8).reshape(-1)).cuda()
+    d_banks = torch.from_numpy(banks.view(np.uint8).reshape(-1)).cuda()
+    d_g = torch.rand(3 * (U // 24), 1024, device="cuda") * 0.2 + 0.9
+    ms = timeit(lambda i: lib.drc_td_dev(x.data_ptr(), state.data_ptr(), d_chan.data_ptr(), d_banks.data_ptr(),
+                                         d_g.data_ptr(), U, st))
+    report("drc time-domain 3-band (filter bank + gains + sum), 6144 channel-frames", ms, U * 8192, U * 1024,
+           "channel_samples")
+
+
 def tns_rs_stage():
     import tns_cases
     from libmpegh_b200.lib import TNS_FILTER_DTYPE
@@ -429,7 +451,7 @@ def fd_path_stage():
     lib.bands_destroy(bands)
 
 
-STAGES = {"mct": mct_stage, "drc": drc_stage, "binaural": binaural_stage, "hoa": hoa_chain_stage, "fc": fc_stage, "tns_rs": tns_rs_stage,
+STAGES = {"mct": mct_stage, "drc": drc_stage, "drc_td": drc_td_stage, "binaural": binaural_stage, "hoa": hoa_chain_stage, "fc": fc_stage, "tns_rs": tns_rs_stage,
           "fd_path": fd_path_stage,
           "spectral": spectral_stage,
           "obj": obj_stage, "hoa_render": hoa_render_stage}
@@ -445,6 +467,7 @@ fc_stage()
 tns_rs_stage()
 mct_stage()
 drc_stage()
+drc_td_stage()
 spectral_stage()
 fd_path_stage()
 binaural_stage()
