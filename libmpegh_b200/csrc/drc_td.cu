@@ -9,8 +9,9 @@
 // Every filter is a serial recurrence over the frame, and the all-pass sections of the reference run BACKWARDS over
 // it (filter_bank.c:380), so the stages of a tree cannot be fused per sample: a warp owns a channel-frame, keeps its
 // band signals in six shared-memory rows, and runs the independent recurrences of a stage on separate lanes (up to
-// four: the low/high pairs of stage 3 of the four-band tree); rows are assigned so that no lane writes a row another
-// lane reads in the same stage.  The sections of the phase-alignment cascade are applied per sample in one loop
+// four: the low/high pairs of stage 3 of the four-band tree) -- through one piece of code, parameters picked by lane
+// number, because divergent branches of a warp run one after the other; rows are assigned so that no lane writes a
+// row another lane reads in the same stage.  The sections of the phase-alignment cascade are applied per sample in one loop
 // (same order per section as the reference's section-after-section passes).  All 32 lanes move the data in and
 // apply the gains and the band sum.  Bound: the recurrence latency (about 16 cycles per sample and stage).
 #include "common.h"
@@ -45,13 +46,21 @@ __device__ __forceinline__ void lh_branch(const mpeghb200_drc_biquad f, float* _
 __device__ __forceinline__ void allpass(const mpeghb200_drc_biquad f, float* __restrict__ st, const float* in,
                                         float* out) {
   float s1 = st[0], s2 = st[2];
-#pragma unroll 4
-  for (int i = kN - 1; i >= 0; --i) {
-    const float x = in[i];
-    const float y = fadd(fmul(f.b0, x), s1);
-    s1 = fadd(fsub(fmul(f.b1, x), fmul(f.a1, y)), s2);
-    s2 = fsub(fmul(f.b2, x), fmul(f.a2, y));
-    out[i] = y;
+  // four samples per step, loaded before and stored after the step: `out` may be `in` (the loads of the next step
+  // would otherwise wait behind this step's stores, and the shared-memory latency would sit on the recurrence)
+  for (int i = kN - 4; i >= 0; i -= 4) {
+    const float4 x4 = *reinterpret_cast<const float4*>(in + i);
+    const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+    float ys[4];
+#pragma unroll
+    for (int e = 3; e >= 0; --e) {
+      const float x = xs[e];
+      const float y = fadd(fmul(f.b0, x), s1);
+      s1 = fadd(fsub(fmul(f.b1, x), fmul(f.a1, y)), s2);
+      s2 = fsub(fmul(f.b2, x), fmul(f.a2, y));
+      ys[e] = y;
+    }
+    *reinterpret_cast<float4*>(out + i) = make_float4(ys[0], ys[1], ys[2], ys[3]);
   }
   st[0] = s1, st[2] = s2;
 }
@@ -84,17 +93,21 @@ __global__ void __launch_bounds__(32 * kTdWarps)
 #pragma unroll
     for (int k = 0; k < 9; ++k)
       if (k < n_casc) f[k] = bank.ap[k], s1[k] = st[4 * (8 + k)], s2[k] = st[4 * (8 + k) + 2];
-    for (int i = kN - 1; i >= 0; --i) {
-      float v = B[0][i];
+    for (int i = kN - 4; i >= 0; i -= 4) {
+      const float4 x4 = *reinterpret_cast<const float4*>(B[0] + i);
+      float v[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-      for (int k = 8; k >= 0; --k)
-        if (k < n_casc) {
-          const float y = fadd(fmul(f[k].b0, v), s1[k]);
-          s1[k] = fadd(fsub(fmul(f[k].b1, v), fmul(f[k].a1, y)), s2[k]);
-          s2[k] = fsub(fmul(f[k].b2, v), fmul(f[k].a2, y));
-          v = y;
-        }
-      B[0][i] = v;
+      for (int e = 3; e >= 0; --e) {
+#pragma unroll
+        for (int k = 8; k >= 0; --k)
+          if (k < n_casc) {
+            const float y = fadd(fmul(f[k].b0, v[e]), s1[k]);
+            s1[k] = fadd(fsub(fmul(f[k].b1, v[e]), fmul(f[k].a1, y)), s2[k]);
+            s2[k] = fsub(fmul(f[k].b2, v[e]), fmul(f[k].a2, y));
+            v[e] = y;
+          }
+      }
+      *reinterpret_cast<float4*>(B[0] + i) = make_float4(v[0], v[1], v[2], v[3]);
     }
 #pragma unroll
     for (int k = 0; k < 9; ++k)
@@ -107,26 +120,28 @@ __global__ void __launch_bounds__(32 * kTdWarps)
   }
   // ---- band split; row plan: no lane writes a row another lane reads in the same stage ----
   const float* band[4] = {B[0], B[0], B[0], B[0]};
+  // Lanes that run concurrently must run the SAME code (separate branches of a warp are serialised): a stage picks
+  // its per-lane filter, memory and rows by lane number and calls one function.
   if (nb >= 2) {  // stage 1: B0 -> low B1, high B2
-    if (lane == 0) lh_branch(bank.f[0], st + 0, B[0], B[1]);
-    if (lane == 1) lh_branch(bank.f[1], st + 4, B[0], B[2]);
+    if (lane < 2) lh_branch(bank.f[lane], st + 4 * lane, B[0], lane ? B[2] : B[1]);
     __syncwarp();
     band[0] = B[1], band[1] = B[2];
   }
-  if (nb == 3) {  // all-pass on the high branch (-> band 2) next to the second split of the low branch
+  if (nb == 3) {  // all-pass on the high branch (-> band 2), second split of the low branch
     if (lane == 0) allpass(bank.f[2], st + 8, B[2], B[3]);
-    if (lane == 1) lh_branch(bank.f[3], st + 12, B[1], B[4]);
-    if (lane == 2) lh_branch(bank.f[4], st + 16, B[1], B[5]);
+    if (lane < 2) lh_branch(bank.f[3 + lane], st + 4 * (3 + lane), B[1], lane ? B[5] : B[4]);
     __syncwarp();
     band[0] = B[4], band[1] = B[5], band[2] = B[3];
   } else if (nb == 4) {
-    if (lane == 0) allpass(bank.f[2], st + 8, B[1], B[1]);   // in place: a single reader / writer
-    if (lane == 1) allpass(bank.f[3], st + 12, B[2], B[2]);
+    if (lane < 2) {  // in place: each row has a single reader / writer
+      float* r = lane ? B[2] : B[1];
+      allpass(bank.f[2 + lane], st + 4 * (2 + lane), r, r);
+    }
     __syncwarp();
-    if (lane == 0) lh_branch(bank.f[4], st + 16, B[1], B[0]);
-    if (lane == 1) lh_branch(bank.f[5], st + 20, B[1], B[3]);
-    if (lane == 2) lh_branch(bank.f[6], st + 24, B[2], B[4]);
-    if (lane == 3) lh_branch(bank.f[7], st + 28, B[2], B[5]);
+    if (lane < 4) {
+      float* out = lane == 0 ? B[0] : (lane == 1 ? B[3] : (lane == 2 ? B[4] : B[5]));
+      lh_branch(bank.f[4 + lane], st + 4 * (4 + lane), lane < 2 ? B[1] : B[2], out);
+    }
     __syncwarp();
     band[0] = B[0], band[1] = B[3], band[2] = B[4], band[3] = B[5];
   }

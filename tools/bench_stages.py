@@ -196,7 +196,9 @@ def drc_td_stage():
     U = 6144
     rng = np.random.default_rng(6)
     banks = np.zeros(1, DRC_TD_BANK_DTYPE)
-    banks[0]["n_bands"], banks[0]["n_cascade"] = 3, 0
+    nbands = int(os.environ.get("DRC_TD_BANDS", "3"))
+    banks[0]["n_bands"], banks[0]["n_cascade"] = nbands, int(os.environ.get("DRC_TD_CASCADE", "0"))
+    banks[0]["ap"] = np.stack([drc_cases.random_biquad(rng) for _ in range(9)])
     banks[0]["f"] = np.stack([drc_cases.random_biquad(rng) for _ in range(8)])
     chan = np.zeros(U, DRC_TD_CHANNEL_DTYPE)
     chan["first_seq"] = 3 * (np.arange(U) // 24)
@@ -207,7 +209,7 @@ def drc_td_stage():
     d_g = torch.rand(3 * (U // 24), 1024, device="cuda") * 0.2 + 0.9
     ms = timeit(lambda i: lib.drc_td_dev(x.data_ptr(), state.data_ptr(), d_chan.data_ptr(), d_banks.data_ptr(),
                                          d_g.data_ptr(), U, st))
-    report("drc time-domain 3-band (filter bank + gains + sum), 6144 channel-frames", ms, U * 8192, U * 1024,
+    report(f"drc time-domain {nbands}-band (filter bank + gains + sum), 6144 channel-frames", ms, U * 8192, U * 1024,
            "channel_samples")
 
 
