@@ -8,10 +8,10 @@
 //
 // Every filter is a serial recurrence over the frame, and the all-pass sections of the reference run BACKWARDS over
 // it (filter_bank.c:380), so the stages of a tree cannot be fused per sample: a warp owns a channel-frame, keeps its
-// band signals in six shared-memory rows, and runs the independent recurrences of a stage on separate lanes (up to
+// band signals in four shared-memory rows, and runs the independent recurrences of a stage on separate lanes (up to
 // four: the low/high pairs of stage 3 of the four-band tree) -- through one piece of code, parameters picked by lane
-// number, because divergent branches of a warp run one after the other; rows are assigned so that no lane writes a
-// row another lane reads in the same stage.  The sections of the phase-alignment cascade are applied per sample in one loop
+// number, because divergent branches of a warp run one after the other; the low branch of a pair overwrites the
+// pair's input row block by block, behind a warp barrier that follows the block loads of both branches.  The sections of the phase-alignment cascade are applied per sample in one loop
 // (same order per section as the reference's section-after-section passes).  All 32 lanes move the data in and
 // apply the gains and the band sum.  Bound: the recurrence latency (about 16 cycles per sample and stage).
 #include "common.h"
@@ -20,24 +20,36 @@ namespace mpeghb200 {
 namespace {
 
 constexpr int kN = 1024;
-constexpr int kRows = 6;
+constexpr int kRows = 4;
 constexpr int kTdWarps = 2;
 constexpr int kStateFloats = 17 * 4;
 
-// one branch of impd_drc_apply_low_high_filter: two cascaded sections with the same coefficients
-__device__ __forceinline__ void lh_branch(const mpeghb200_drc_biquad f, float* __restrict__ st,
-                                          const float* __restrict__ in, float* __restrict__ out) {
+// One branch of impd_drc_apply_low_high_filter: two cascaded sections with the same coefficients.  `out` may be the
+// row another lane of the stage (the other branch of the pair) reads as `in`: the loop works in blocks of four
+// samples, and every lane of `mask` (the lanes of this stage) holds its block before any of them stores
+// (__syncwarp); the block after that is already on its way, so the shared-memory latency stays off the recurrence.
+__device__ __forceinline__ void lh_branch(const mpeghb200_drc_biquad f, float* __restrict__ st, const float* in,
+                                          float* out, unsigned mask) {
   float s1 = st[0], s2 = st[1], s3 = st[2], s4 = st[3];
-#pragma unroll 4
-  for (int i = 0; i < kN; ++i) {
-    const float x = in[i];
-    const float t = fadd(s1, fmul(f.b0, x));
-    s1 = fadd(fsub(fmul(f.b1, x), fmul(f.a1, t)), s2);
-    s2 = fsub(fmul(f.b2, x), fmul(f.a2, t));
-    const float o = fadd(s3, fmul(f.b0, t));
-    s3 = fadd(fsub(fmul(f.b1, t), fmul(f.a1, o)), s4);
-    s4 = fsub(fmul(f.b2, t), fmul(f.a2, o));
-    out[i] = o;
+  float4 nx = *reinterpret_cast<const float4*>(in);
+  for (int i = 0; i < kN; i += 4) {
+    const float4 x4 = nx;
+    if (i + 4 < kN) nx = *reinterpret_cast<const float4*>(in + i + 4);
+    __syncwarp(mask);
+    const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+    float os[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float x = xs[e];
+      const float t = fadd(s1, fmul(f.b0, x));
+      s1 = fadd(fsub(fmul(f.b1, x), fmul(f.a1, t)), s2);
+      s2 = fsub(fmul(f.b2, x), fmul(f.a2, t));
+      const float o = fadd(s3, fmul(f.b0, t));
+      s3 = fadd(fsub(fmul(f.b1, t), fmul(f.a1, o)), s4);
+      s4 = fsub(fmul(f.b2, t), fmul(f.a2, o));
+      os[e] = o;
+    }
+    *reinterpret_cast<float4*>(out + i) = make_float4(os[0], os[1], os[2], os[3]);
   }
   st[0] = s1, st[1] = s2, st[2] = s3, st[3] = s4;
 }
@@ -122,28 +134,28 @@ __global__ void __launch_bounds__(32 * kTdWarps)
   const float* band[4] = {B[0], B[0], B[0], B[0]};
   // Lanes that run concurrently must run the SAME code (separate branches of a warp are serialised): a stage picks
   // its per-lane filter, memory and rows by lane number and calls one function.
-  if (nb >= 2) {  // stage 1: B0 -> low B1, high B2
-    if (lane < 2) lh_branch(bank.f[lane], st + 4 * lane, B[0], lane ? B[2] : B[1]);
+  if (nb >= 2) {  // stage 1: B0 -> low B0 (in place, see lh_branch), high B1
+    if (lane < 2) lh_branch(bank.f[lane], st + 4 * lane, B[0], lane ? B[1] : B[0], 0x3u);
     __syncwarp();
-    band[0] = B[1], band[1] = B[2];
+    band[0] = B[0], band[1] = B[1];
   }
   if (nb == 3) {  // all-pass on the high branch (-> band 2), second split of the low branch
-    if (lane == 0) allpass(bank.f[2], st + 8, B[2], B[3]);
-    if (lane < 2) lh_branch(bank.f[3 + lane], st + 4 * (3 + lane), B[1], lane ? B[5] : B[4]);
+    if (lane == 0) allpass(bank.f[2], st + 8, B[1], B[1]);
+    if (lane < 2) lh_branch(bank.f[3 + lane], st + 4 * (3 + lane), B[0], lane ? B[2] : B[0], 0x3u);
     __syncwarp();
-    band[0] = B[4], band[1] = B[5], band[2] = B[3];
+    band[0] = B[0], band[1] = B[2], band[2] = B[1];
   } else if (nb == 4) {
-    if (lane < 2) {  // in place: each row has a single reader / writer
-      float* r = lane ? B[2] : B[1];
+    if (lane < 2) {  // each row: one reader / writer
+      float* r = lane ? B[1] : B[0];
       allpass(bank.f[2 + lane], st + 4 * (2 + lane), r, r);
     }
     __syncwarp();
-    if (lane < 4) {
-      float* out = lane == 0 ? B[0] : (lane == 1 ? B[3] : (lane == 2 ? B[4] : B[5]));
-      lh_branch(bank.f[4 + lane], st + 4 * (4 + lane), lane < 2 ? B[1] : B[2], out);
+    if (lane < 4) {  // lanes 0, 1 split B0 into (B0, B2); lanes 2, 3 split B1 into (B1, B3)
+      float* out = lane == 0 ? B[0] : (lane == 1 ? B[2] : (lane == 2 ? B[1] : B[3]));
+      lh_branch(bank.f[4 + lane], st + 4 * (4 + lane), lane < 2 ? B[0] : B[1], out, 0xFu);
     }
     __syncwarp();
-    band[0] = B[0], band[1] = B[3], band[2] = B[4], band[3] = B[5];
+    band[0] = B[0], band[1] = B[2], band[2] = B[1], band[3] = B[3];
   }
   // ---- gains and band sum, highest band first (impd_drc_process.c:150-155, :211-219) ----
   const float* g = gains + size_t(ch.first_seq) * kN;
