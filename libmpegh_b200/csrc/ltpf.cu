@@ -162,32 +162,35 @@ __global__ void __launch_bounds__(kThreads)
       r[t] = s;
     }
     __syncthreads();
-    if (t == 0) {  // Levinson-Durbin (:229-262)
-      float rr[kLpc + 1], aa[kLpc + 1], rc[kLpc];
-      for (int i = 0; i <= kLpc; ++i) rr[i] = r[i], aa[i] = 0.0f;
-      rr[0] = fmaxf(rr[0], 100.0f);
-      rr[0] = fmul(rr[0], 1.0001f);
-      aa[0] = 1.0f;
-      rc[0] = __fdiv_rn(-rr[1], rr[0]);
-      aa[1] = rc[0];
-      float sigma2 = fadd(rr[0], fmul(rr[1], rc[0]));
+    if (t < 32) {  // Levinson-Durbin (:229-262) on warp 0: lane j holds rr[j] and aa[j]
+      // The inner sums are strictly ordered additions; what the warp buys is that the products, the table values
+      // and the symmetric coefficient update are there in one step each instead of as dependent local-memory
+      // accesses of one thread (this recursion used to cost as much as the 128-step zero-input response below).
+      // Every lane forms the same sum, so the early exit is uniform.
+      constexpr unsigned kAll = 0xffffffffu;
+      float rrl = (t <= kLpc) ? r[t] : 0.0f;
+      if (t == 0) rrl = fmul(fmaxf(rrl, 100.0f), 1.0001f);
+      const float rr0 = __shfl_sync(kAll, rrl, 0), rr1 = __shfl_sync(kAll, rrl, 1);
+      float rci = __fdiv_rn(-rr1, rr0);
+      float aal = (t == 0) ? 1.0f : (t == 1 ? rci : 0.0f);
+      float sigma2 = fadd(rr0, fmul(rr1, rci));
+#pragma unroll
       for (int i = 2; i <= kLpc; ++i) {
+        const float p = fmul(__shfl_sync(kAll, rrl, (i - t) & 31), aal);  // rr[i - j] * aa[j] on lane j
         float sum = 0.0f;
-        for (int j = 0; j < i; ++j) sum = fadd(sum, fmul(rr[i - j], aa[j]));
-        rc[i - 1] = __fdiv_rn(-sum, sigma2);
-        sigma2 = fmul(sigma2, fsub(1.0f, fmul(rc[i - 1], rc[i - 1])));
+#pragma unroll
+        for (int j = 0; j < i; ++j) sum = fadd(sum, __shfl_sync(kAll, p, j));
+        rci = __fdiv_rn(-sum, sigma2);
+        sigma2 = fmul(sigma2, fsub(1.0f, fmul(rci, rci)));
         if (sigma2 <= 1.0E-09f) {
-          for (int j = i; j <= kLpc; ++j) aa[j] = 0.0f;
+          if (t >= i) aal = 0.0f;
           break;
         }
-        for (int j = 1; j <= i / 2; ++j) {
-          const float v = fadd(aa[j], fmul(rc[i - 1], aa[i - j]));
-          aa[i - j] = fadd(aa[i - j], fmul(rc[i - 1], aa[j]));
-          aa[j] = v;
-        }
-        aa[i] = rc[i - 1];
+        const float other = __shfl_sync(kAll, aal, (i - t) & 31);  // aa[i - j], old value
+        if (t >= 1 && t < i) aal = fadd(aal, fmul(rci, other));
+        if (t == i) aal = rci;
       }
-      for (int i = 0; i <= kLpc; ++i) a[i] = aa[i];
+      if (t <= kLpc) a[t] = aal;
     }
     // start values of the zero-input response: the 24 samples before the transition (:270-288)
     if (t >= 32 && t < 32 + kLpc) {
