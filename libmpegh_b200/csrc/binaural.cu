@@ -108,15 +108,17 @@ __device__ __forceinline__ void forward_real(float2* __restrict__ work, const Ro
                                              float2 (&X)[8], float& im0, float& imn, Prefetch prefetch) {
   using G = Geo<DIM2>;
   const int tid = threadIdx.x;
+  // only the first half of every row is non-zero and all of it is real: staged as floats (see rows_1024 REAL_HALF)
+  float* workf = reinterpret_cast<float*>(work);
 #pragma unroll
-  for (int q = 0; q < G::N / G::NT; ++q) {
+  for (int q = 0; q < G::B / G::NT; ++q) {
     const int n = tid + G::NT * q;
     const float x = (n < n_valid) ? src(n) : 0.0f;
-    work[(n % DIM2) * kRowStride + phys(n / DIM2)] = make_float2(x, 0.0f);
+    workf[(n % DIM2) * (2 * kRowStride) + phys(n / DIM2)] = x;
   }
   __syncthreads();
   prefetch();
-  rows_1024<DIM2, true>(work, tw);
+  rows_1024<DIM2, true, true>(work, tw);
 #pragma unroll
   for (int c = 0; c < G::COLS; ++c) {
     const int i = tid + G::NT * c;

@@ -248,7 +248,10 @@ __device__ __forceinline__ int rev32(int lane) { return 8 * (lane & 3) + 2 * ((l
 
 // The row transforms (stages A..C) of all DIM2 rows, in place.  Entry: work holds the rows in natural order,
 // preceded by a __syncthreads() issued by the caller.  Exit: rows transformed, __syncthreads() issued.
-template <int DIM2, bool INV>
+// REAL_HALF: the input is real and zero beyond position 511 of every row (a zero-padded real block); the caller has
+// staged only the real parts, as floats, at rowf[phys(p)] (rowf = the row's memory viewed as float).  The zeros are
+// compile-time constants then, and what IEEE arithmetic allows to fold in pass 0 folds.
+template <int DIM2, bool INV, bool REAL_HALF = false>
 __device__ __forceinline__ void rows_1024(float2* __restrict__ work, const RowTw tw) {
   const int tid = threadIdx.x;
   const int r = tid >> 6, g = tid & 63;
@@ -258,8 +261,15 @@ __device__ __forceinline__ void rows_1024(float2* __restrict__ work, const RowTw
   {
     // digit-reversed read: butterfly b = 4g + q reads r3(g) + 64 q + 256 i
     const int r3 = ((g & 3) << 4) | (g & 12) | (g >> 4);
+    if constexpr (REAL_HALF) {
+      const float* rowf = reinterpret_cast<const float*>(row);
 #pragma unroll
-    for (int t = 0; t < 16; ++t) v[t] = row[phys(r3 + 64 * t)];
+      for (int t = 0; t < 16; ++t)
+        v[t] = (t < 8) ? make_float2(rowf[phys(r3 + 64 * t)], 0.0f) : make_float2(0.0f, 0.0f);
+    } else {
+#pragma unroll
+      for (int t = 0; t < 16; ++t) v[t] = row[phys(r3 + 64 * t)];
+    }
     __syncthreads();
     stage_a<INV>(v, tw);
 #pragma unroll
