@@ -293,51 +293,38 @@ __device__ void window_short(const float* xs, float* __restrict__ ov, float* __r
       const float4 o = ldcs4(ov + P4);
       v[0] = o.x, v[1] = o.y, v[2] = o.z, v[3] = o.w;
     } else if (P4 < 576) {
+      // `lo` (and below the block number k) differs between the two halves of a warp: everything that depends on
+      // them is a select on an index, a sign or a value, never a branch -- as branches they made the warp run every
+      // element twice, with a reconvergence each, and this loop was more than half of a short-block unit
       const float4 o = ldcs4(ov + P4);
       const float oo[4] = {o.x, o.y, o.z, o.w};
+      const bool neg = !lo && tkt != 3;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int t = t0 + e;
-        float a;
-        if (lo) {
-          a = xs[64 + t];
-        } else {
-          a = xs[191 - t];
-          if (tkt != 3) a = -a;
-        }
+        float a = xs[lo ? 64 + t : 191 - t];
+        a = neg ? -a : a;
         v[e] = mul_add_mul(a, wp.f[e], oo[e], wp.r[e]);
       }
     } else if (P4 < 1600) {
       const int k = (P4 - 576) >> 7;
       const float* xk = xs + 128 * k;
+      const bool last = k == 7;
+      const bool quirk = k == 0 && tkt == 3 && lo;  // reference quirk, basic_ops.c:404: w + 0, no 0 + x
+      const bool negf = lo ? (tkt != 3) : true;     // falling half of block k
+      const bool negr = !lo && tkt != 3;            // rising half of block k + 1
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int t = t0 + e;
-        float acc;
-        if (k == 0 && tkt == 3 && lo) {
-          acc = fmul(xk[63 - t], fadd(wc.r[e], 0.0f));  // reference quirk, basic_ops.c:404
-        } else {
-          float f;  // falling half of block k
-          if (lo) {
-            f = xk[63 - t];
-            if (tkt != 3) f = -f;
-          } else {
-            f = -xk[t - 64];
-          }
-          if (k != 7) f = fmul(f, wc.r[e]);
-          acc = fadd(0.0f, f);
-        }
-        if (k != 7) {  // rising half of block k + 1
-          float r;
-          if (lo) {
-            r = xk[128 + 64 + t];
-          } else {
-            r = xk[128 + 191 - t];
-            if (tkt != 3) r = -r;
-          }
-          acc = fadd(acc, fmul(r, wc.f[e]));
-        }
-        v[e] = acc;
+        float f = xk[lo ? 63 - t : t - 64];
+        f = negf ? -f : f;
+        const float w = quirk ? fadd(wc.r[e], 0.0f) : wc.r[e];
+        const float m = fmul(f, w);
+        float acc = quirk ? m : fadd(0.0f, last ? f : m);
+        float r = xk[last ? 0 : (lo ? 128 + 64 + t : 128 + 191 - t)];
+        r = negr ? -r : r;
+        const float acc2 = fadd(acc, fmul(r, wc.f[e]));
+        v[e] = last ? acc : acc2;
       }
     } else {
       v[0] = v[1] = v[2] = v[3] = 0.0f;
