@@ -278,15 +278,17 @@ __device__ __forceinline__ ShortWin load_short_win(const float* __restrict__ w, 
   return s;
 }
 
+// Iterations it0, it0 + it_step, ... of the 16: several warps can share one unit (it_step a divisor of 8, so that
+// the overlap position an iteration writes was read by the same warp eight iterations earlier).
 __device__ void window_short(const float* xs, float* __restrict__ ov, float* __restrict__ out, const Side sd,
-                             const DeviceTables& T, int lane) {
+                             const DeviceTables& T, int lane, int it0 = 0, int it_step = 1) {
   const int tkt = sd.tkt;
   const int t0 = (4 * lane + 64) & 127;
   const ShortWin wc = load_short_win(T.win_short[sd.shape], t0);
   const ShortWin wp = load_short_win(T.win_short[sd.shape_prev], t0);
   const bool lo = t0 < 64;  // t0 .. t0+3 lie on one side of 64
 #pragma unroll 1
-  for (int it = 0; it < 16; ++it) {
+  for (int it = it0; it < 16; it += it_step) {
     const int P4 = 4 * (lane + 32 * it);
     float v[4];
     if (P4 < 448) {
@@ -342,8 +344,11 @@ __device__ void window_short(const float* xs, float* __restrict__ ov, float* __r
 
 // General path: every window sequence and transform kernel type (EIGHT_SHORT frames and kernel switching
 // are rare; ONLY_LONG-family frames with kernel type 0 take fd_unit_long_fast instead).
+// window_later: for EIGHT_SHORT units stop after the post-twiddle (time-aliased samples in sm); the caller runs
+// window_short itself (slow_units shares it between the CTA's warps).
 __device__ __noinline__ void fd_unit_generic(const float* __restrict__ X, float* __restrict__ ov, float* __restrict__ o,
-                                             const Side sd, float* sm, const DeviceTables& T, int lane) {
+                                             const Side sd, float* sm, const DeviceTables& T, int lane,
+                                             bool window_later = false) {
   float2* smc = reinterpret_cast<float2*>(sm);
   const bool is_short = (sd.seq == 2);
   const float norm = is_short ? 0.0078125f : 0.0009765625f;  // 2 / (2N)
@@ -475,7 +480,7 @@ __device__ __noinline__ void fd_unit_generic(const float* __restrict__ X, float*
         posttwiddle_store(sm + 128 * T8, 128, sd.tkt, k, zr[4 * r + q], zi[4 * r + q], __ldg(T.tw64 + k), false);
       }
     __syncwarp();
-    window_short(sm, ov, o, sd, T, lane);
+    if (!window_later) window_short(sm, ov, o, sd, T, lane);
   }
 }
 
@@ -843,10 +848,25 @@ __device__ __noinline__ void slow_units(const float* __restrict__ coef, const ui
                                         float* __restrict__ overlap, float* __restrict__ out, const int* list, int count,
                                         float* slots, const DeviceTables& T) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int k = warp; k < count; k += 4) {
-    const size_t u = size_t(list[k]);
-    const Side sd = unpack_side(__ldg(side + u));
-    fd_unit_generic(coef + u * 1024, overlap + u * 1024, out + u * 1024, sd, slots + warp * kBufFloats, T, lane);
+  // What bounds the mixed-sequence step is the latency of the last short-block unit on its warp, and a CTA rarely has
+  // more than one or two such units: the transforms of up to four units run one per warp, then the windowing of
+  // each of them (more than a third of a unit, and parallel over its 16 float4 rows) is shared by all four warps.
+  for (int base = 0; base < count; base += 4) {
+    const int k = base + warp;
+    if (k < count) {
+      const size_t u = size_t(list[k]);
+      const Side sd = unpack_side(__ldg(side + u));
+      fd_unit_generic(coef + u * 1024, overlap + u * 1024, out + u * 1024, sd, slots + warp * kBufFloats, T, lane,
+                      /*window_later=*/true);
+    }
+    __syncthreads();
+    for (int j = base; j < count && j < base + 4; ++j) {
+      const size_t u = size_t(list[j]);
+      const Side sd = unpack_side(__ldg(side + u));
+      if (sd.seq == 2)
+        window_short(slots + (j - base) * kBufFloats, overlap + u * 1024, out + u * 1024, sd, T, lane, warp, 4);
+    }
+    __syncthreads();  // the slots are rewritten by the next batch
   }
 }
 
