@@ -352,6 +352,20 @@ __device__ __noinline__ void fd_unit_generic(const float* __restrict__ X, float*
   float2* smc = reinterpret_cast<float2*>(sm);
   const bool is_short = (sd.seq == 2);
   const float norm = is_short ? 0.0078125f : 0.0009765625f;  // 2 / (2N)
+  // The tables of this rarely taken path are cold in L1, and its table loads sit one by one behind shuffles and
+  // dependent arithmetic (the 16 pre-twiddle loads alone: 16 x ~250 cycles of L2 latency, a fifth of a short-block
+  // unit).  Ask for the lines now, while the coefficients are on their way; costs no register.
+  if (is_short) {
+    const char* t64 = reinterpret_cast<const char*>(T.tw64);           // 512 B
+    const char* eff = reinterpret_cast<const char*>(T.eff);            // 6 KB
+    const char* w0 = reinterpret_cast<const char*>(T.win_short[sd.shape]);
+    const char* w1 = reinterpret_cast<const char*>(T.win_short[sd.shape_prev]);
+    if (lane < 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(t64 + 128 * lane));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(eff + 128 * lane));
+    if (lane < 16) asm volatile("prefetch.global.L1 [%0];" ::"l"(eff + 4096 + 128 * lane));
+    if (lane < 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(w0 + 128 * lane));
+    if (lane >= 4 && lane < 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(w1 + 128 * (lane - 4)));
+  }
 
   float zr[16], zi[16];
   if (sd.tkt == 0) {
