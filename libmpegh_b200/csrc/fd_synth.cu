@@ -383,15 +383,25 @@ __device__ __noinline__ void fd_unit_generic(const float* __restrict__ X, float*
       eo[u].y = fmul(eo[u].y, norm);
     }
     const int mirror = is_short ? 3 : 31;
+    // Short blocks: the 64 twiddles are parked in the warp's (still unused) shared buffer with one coalesced load
+    // that overlaps the coefficient loads.  Read from global inside the loop, each of the 16 loads sat behind the
+    // shuffle of the previous iteration and cost its own L2 latency (~4 k cycles, a fifth of a short-block unit);
+    // holding all 16 in registers instead cost the fast path of this kernel 2 % (register allocation).
+    if (is_short) {
+      smc[lane] = __ldg(T.tw64 + lane);
+      smc[lane + 32] = __ldg(T.tw64 + lane + 32);
+      __syncwarp();
+    }
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
       const int c = is_short ? ((lane & 3) + 4 * u) : (lane + 32 * u);
-      const float2 cs = __ldg((is_short ? T.tw64 : T.tw512) + c);
+      const float2 cs = is_short ? smc[c] : __ldg(T.tw512 + c);
       const float a = eo[u].x;
       const float b = __shfl_xor_sync(kFull, eo[15 - u].y, mirror);
       zr[u] = fsub(-fmul(a, cs.x), fmul(b, cs.y));
       zi[u] = fsub(fmul(b, cs.x), fmul(a, cs.y));
     }
+    __syncwarp();  // the buffer is reused by the transpose below
   } else {
     // stage the scaled spectrum in shared memory, then evaluate the type-specific pre-twiddle per point
 #pragma unroll
