@@ -77,6 +77,33 @@ __device__ __forceinline__ void allpass(const mpeghb200_drc_biquad f, float* __r
   st[0] = s1, st[2] = s2;
 }
 
+// Phase-alignment cascade (filter_bank.c:601): sections NC-1 .. 0, in place, last sample first, applied per sample in
+// one loop (each section sees its samples in the reference's order).  One lane.
+template <int NC>
+__device__ __noinline__ void cascade(const mpeghb200_drc_td_bank& bank, float* __restrict__ st, float* row) {
+  float s1[NC], s2[NC];
+  mpeghb200_drc_biquad f[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) f[k] = bank.ap[k], s1[k] = st[4 * (8 + k)], s2[k] = st[4 * (8 + k) + 2];
+  for (int i = kN - 4; i >= 0; i -= 4) {
+    const float4 x4 = *reinterpret_cast<const float4*>(row + i);
+    float v[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+    for (int e = 3; e >= 0; --e) {
+#pragma unroll
+      for (int k = NC - 1; k >= 0; --k) {
+        const float y = fadd(fmul(f[k].b0, v[e]), s1[k]);
+        s1[k] = fadd(fsub(fmul(f[k].b1, v[e]), fmul(f[k].a1, y)), s2[k]);
+        s2[k] = fsub(fmul(f[k].b2, v[e]), fmul(f[k].a2, y));
+        v[e] = y;
+      }
+    }
+    *reinterpret_cast<float4*>(row + i) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+#pragma unroll
+  for (int k = 0; k < NC; ++k) st[4 * (8 + k)] = s1[k], st[4 * (8 + k) + 2] = s2[k];
+}
+
 __global__ void __launch_bounds__(32 * kTdWarps)
     drc_td_kernel(float* __restrict__ audio, float* __restrict__ state, const mpeghb200_drc_td_channel* __restrict__ chan,
                   const mpeghb200_drc_td_bank* __restrict__ banks, const float* __restrict__ gains, int n_ch) {
@@ -100,30 +127,17 @@ __global__ void __launch_bounds__(32 * kTdWarps)
   __syncwarp();
   // ---- phase-alignment cascade, sections n_casc-1 .. 0, in place, last sample first (filter_bank.c:601) ----
   if (n_casc > 0 && lane == 0) {
-    float s1[9], s2[9];
-    mpeghb200_drc_biquad f[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k)
-      if (k < n_casc) f[k] = bank.ap[k], s1[k] = st[4 * (8 + k)], s2[k] = st[4 * (8 + k) + 2];
-    for (int i = kN - 4; i >= 0; i -= 4) {
-      const float4 x4 = *reinterpret_cast<const float4*>(B[0] + i);
-      float v[4] = {x4.x, x4.y, x4.z, x4.w};
-#pragma unroll
-      for (int e = 3; e >= 0; --e) {
-#pragma unroll
-        for (int k = 8; k >= 0; --k)
-          if (k < n_casc) {
-            const float y = fadd(fmul(f[k].b0, v[e]), s1[k]);
-            s1[k] = fadd(fsub(fmul(f[k].b1, v[e]), fmul(f[k].a1, y)), s2[k]);
-            s2[k] = fsub(fmul(f[k].b2, v[e]), fmul(f[k].a2, y));
-            v[e] = y;
-          }
-      }
-      *reinterpret_cast<float4*>(B[0] + i) = make_float4(v[0], v[1], v[2], v[3]);
+    switch (n_casc) {  // section count at compile time: per-sample tests of it cost more than the sections
+      case 1: cascade<1>(bank, st, B[0]); break;
+      case 2: cascade<2>(bank, st, B[0]); break;
+      case 3: cascade<3>(bank, st, B[0]); break;
+      case 4: cascade<4>(bank, st, B[0]); break;
+      case 5: cascade<5>(bank, st, B[0]); break;
+      case 6: cascade<6>(bank, st, B[0]); break;
+      case 7: cascade<7>(bank, st, B[0]); break;
+      case 8: cascade<8>(bank, st, B[0]); break;
+      default: cascade<9>(bank, st, B[0]); break;
     }
-#pragma unroll
-    for (int k = 0; k < 9; ++k)
-      if (k < n_casc) st[4 * (8 + k)] = s1[k], st[4 * (8 + k) + 2] = s2[k];
   }
   __syncwarp();
   if (!grouped) {  // outside every channel group: only the cascade applies (impd_drc_process.c:204-207)
