@@ -30,6 +30,12 @@ constexpr int kPitch = kChunk + 1;
 constexpr int kMaxOut = 24;
 constexpr int kMaxCoef = 49;
 
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(unsigned(__cvta_generic_to_shared(smem_dst))), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 struct HoaParams {
   int n_out, n_coef, use_nfc, clip;
   float M[kMaxOut * kMaxCoef];
@@ -139,6 +145,351 @@ cudaError_t launch(const float* in, float* out, float* st, const float* nfc, con
                     st, nfc, P);
 }
 
+// One filter lane's cascade over a chunk row, cell counts at compile time (the reference gives every coefficient
+// of an order-N renderer the same N / 2 second-order cells and N % 2 first-order cell, so a warp is uniform in
+// practice): nothing predicated, the cells of consecutive samples overlap in the pipeline.  The gain multiply is
+// unconditional: x * 1.0f is x bit for bit, the reference skips it only when the gain is 1.
+template <int N2, bool N1, int LEN>
+__device__ __forceinline__ void nfc_cascade(float* row, const float (&c)[17], float (&st)[14]) {
+  for (int j0 = 0; j0 < LEN; j0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = row[j0 + u];  // off the dependent chain
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      float w = fmul(v[u], c[0]);
+#pragma unroll
+      for (int k = 0; k < N2; ++k) {
+        const float a1 = c[3 + 4 * k], a2 = c[4 + 4 * k], b1 = c[5 + 4 * k], b2 = c[6 + 4 * k];
+        const float x0 = w;
+        // ((x2*b2 - y1*a1) - y2*a2) + (x1*b1 + x0*b0), b0 = 1 (decoder/impeghd_hoa_nfc_filtering.c:72-77)
+        w = fadd(fsub(fsub(fmul(st[4 * k + 1], b2), fmul(st[4 * k + 2], a1)), fmul(st[4 * k + 3], a2)),
+                 fadd(fmul(st[4 * k], b1), x0));
+        st[4 * k + 3] = st[4 * k + 2];
+        st[4 * k + 2] = w;
+        st[4 * k + 1] = st[4 * k];
+        st[4 * k] = x0;
+      }
+      if (N1) {
+        const float x0 = w;
+        w = fadd(fsub(fmul(st[12], c[16]), fmul(st[13], c[15])), x0);  // :108-110
+        st[13] = w;
+        st[12] = x0;
+      }
+      v[u] = w;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) row[j0 + u] = v[u];
+  }
+}
+
+// ---- NFC on: the cascades run one stage ahead of the mix, on their own warps ---------------------------------
+// In hoa_render_kernel the 128 mixing threads wait at a barrier while <= NC lanes walk their IIR chains over the
+// chunk, and then the filter lanes wait for the mix.  Here the CTA has 128 mixing threads + ceil(NC / 32) filter
+// warps and a three-deep ring of 64-sample tiles: while the mixing warps apply M to stage k (thread = one sample
+// and one half of the outputs), the filter warps run stage k + 1 through the cascades in the next tile and the raw
+// stage k + 2 is on its way from HBM into the third by cp.async (no registers, no exposed latency).  One barrier
+// per stage.  Same expressions, same order: bit-identical.
+constexpr int kSub = 64;
+constexpr int kSubPitch = kSub + 1;  // odd: the filter lanes walk their rows without bank conflicts
+
+template <int NC, int NO>
+__global__ void __launch_bounds__(kChunk + 32 * ((NC + 31) / 32), NC <= 25 ? 7 : 1)
+    hoa_render_nfc_kernel(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ nfc_state,
+                          const float* __restrict__ nfc, const __grid_constant__ HoaParams P) {
+  pdl_prologue();
+  extern __shared__ float tile[];  // [3][NC][kSubPitch]
+  constexpr int kBuf = NC * kSubPitch;
+  constexpr int kSubs = kFrame / kSub;
+  const int t = threadIdx.x;
+  const size_t s = blockIdx.x;
+  const float* x = in + s * size_t(NC) * kFrame;
+  const int n_out = NO ? NO : P.n_out;
+  float* y = out + s * size_t(n_out) * kFrame;
+  const bool mixer = t < kChunk;
+  const int tn = t - kChunk;  // filter lane: coefficient index
+  const bool filt = !mixer && tn < NC;
+
+  float c[17], st[14];
+  if (filt) {
+#pragma unroll
+    for (int i = 0; i < 17; ++i) c[i] = __ldg(nfc + tn * 17 + i);
+#pragma unroll
+    for (int i = 0; i < 14; ++i) st[i] = nfc_state[(s * NC + tn) * 14 + i];
+  }
+  const int n2 = filt ? int(c[1]) : 0;
+  const bool n1 = filt && c[2] != 0.0f;
+  const bool scale = filt && c[0] != 1.0f;
+
+  // cell counts of this warp's lanes: uniform (always, with reference-designed coefficients) or mixed
+  int key = -1;
+  if (!mixer) {
+    const int mine = filt ? n2 * 2 + int(n1) : -1;
+    const int first = __shfl_sync(0xffffffffu, mine, 0);
+    key = __all_sync(0xffffffffu, !filt || mine == first) ? first : -1;
+  }
+  auto cascade = [&](float* row) {
+    switch (key) {
+      case 0: nfc_cascade<0, false, kSub>(row, c, st); return;
+      case 1: nfc_cascade<0, true, kSub>(row, c, st); return;
+      case 2: nfc_cascade<1, false, kSub>(row, c, st); return;
+      case 3: nfc_cascade<1, true, kSub>(row, c, st); return;
+      case 4: nfc_cascade<2, false, kSub>(row, c, st); return;
+      case 5: nfc_cascade<2, true, kSub>(row, c, st); return;
+      case 6: nfc_cascade<3, false, kSub>(row, c, st); return;
+      case 7: nfc_cascade<3, true, kSub>(row, c, st); return;
+      default: break;
+    }
+    for (int j = 0; j < kSub; ++j) {  // mixed cell counts in one warp: predicated cells
+      float w = row[j];
+      if (scale) w = fmul(w, c[0]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (k < n2) {
+          const float a1 = c[3 + 4 * k], a2 = c[4 + 4 * k], b1 = c[5 + 4 * k], b2 = c[6 + 4 * k];
+          const float x0 = w;
+          w = fadd(fsub(fsub(fmul(st[4 * k + 1], b2), fmul(st[4 * k + 2], a1)), fmul(st[4 * k + 3], a2)),
+                   fadd(fmul(st[4 * k], b1), x0));
+          st[4 * k + 3] = st[4 * k + 2];
+          st[4 * k + 2] = w;
+          st[4 * k + 1] = st[4 * k];
+          st[4 * k] = x0;
+        }
+      }
+      if (n1) {
+        const float x0 = w;
+        w = fadd(fsub(fmul(st[12], c[16]), fmul(st[13], c[15])), x0);
+        st[13] = w;
+        st[12] = x0;
+      }
+      row[j] = w;
+    }
+  };
+  // raw stage k -> tile k % 3, by the mixing threads (a warp copies 32 consecutive samples of a row)
+  auto fetch = [&](int k) {
+    float* b = tile + (k % 3) * kBuf;
+    const float* src = x + k * kSub;
+    for (int idx = t; idx < NC * kSub; idx += kChunk)
+      cp_async4(b + (idx >> 6) * kSubPitch + (idx & (kSub - 1)), src + size_t(idx >> 6) * kFrame + (idx & (kSub - 1)));
+  };
+  // one output row of the mix: och and the matrix row are compile-time or warp-uniform in every caller
+  auto mix_row = [&](const float (&xin)[NC], const float* Mr, float* yo) {
+    float val = 0.0f;
+#pragma unroll
+    for (int mn = 0; mn < NC; ++mn) val = fadd(val, fmul(Mr[mn], xin[mn]));
+    if (P.clip) {
+      val = (val < 32767.0f) ? val : 32767.0f;
+      val = (val > -32768.0f) ? val : -32768.0f;
+    }
+    __stcs(yo, val);
+  };
+
+  if (mixer) {
+    fetch(0);
+    cp_async_wait_all();
+  }
+  __syncthreads();
+  if (mixer) {
+    fetch(1);
+    cp_async_wait_all();
+  } else if (filt) {
+    cascade(tile + tn * kSubPitch);
+  }
+  __syncthreads();
+
+  const int smp = t & (kSub - 1);
+  for (int k = 0; k < kSubs; ++k) {
+    // here: tile k % 3 holds the filtered stage k, tile (k + 1) % 3 the raw stage k + 1
+    if (mixer) {
+      if (k + 2 < kSubs) fetch(k + 2);  // into the tile the mix of stage k - 1 has finished with
+      const float* cur = tile + (k % 3) * kBuf;
+      float xin[NC];
+#pragma unroll
+      for (int mn = 0; mn < NC; ++mn) xin[mn] = cur[mn * kSubPitch + smp];
+      float* yo = y + k * kSub + smp;
+      if (NO) {
+        constexpr int H = (NO ? NO : 2) / 2;
+        if (t < kSub) {
+#pragma unroll
+          for (int och = 0; och < H; ++och) mix_row(xin, P.M + och * NC, yo + size_t(och) * kFrame);
+        } else {
+#pragma unroll
+          for (int och = H; och < (NO ? NO : 2); ++och) mix_row(xin, P.M + och * NC, yo + size_t(och) * kFrame);
+        }
+      } else if (t < kSub) {
+        for (int och = 0; och < n_out; och += 2) mix_row(xin, P.M + och * NC, yo + size_t(och) * kFrame);
+      } else {
+        for (int och = 1; och < n_out; och += 2) mix_row(xin, P.M + och * NC, yo + size_t(och) * kFrame);
+      }
+      cp_async_wait_all();
+    } else if (filt && k + 1 < kSubs) {
+      cascade(tile + ((k + 1) % 3) * kBuf + tn * kSubPitch);
+    }
+    __syncthreads();
+  }
+  if (filt) {
+#pragma unroll
+    for (int i = 0; i < 14; ++i) nfc_state[(s * NC + tn) * 14 + i] = st[i];
+  }
+}
+
+template <int NC, int NO>
+cudaError_t launch_nfc(const float* in, float* out, float* st, const float* nfc, const HoaParams& P, int n_streams,
+                       cudaStream_t stream) {
+  auto k = hoa_render_nfc_kernel<NC, NO>;
+  const size_t smem = 3 * NC * kSubPitch * sizeof(float);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  return launch_pdl(k, dim3(n_streams), dim3(kChunk + 32 * ((NC + 31) / 32)), smem, stream, in, out, st, nfc, P);
+}
+
+// ---- tensor-core variant (opt-in, mpeghb200_hoa_renderer_set_tensor_mode) -------------------------------------
+// BASELINE.json's north_star allows tensor cores for this one contraction, within max |err| <= 2^-20 of full
+// scale instead of bit-identity.  The render matrix is applied as out^T[sample][och] = x^T[sample][mn] * M^T[mn][och]
+// with mma.sync m16n8k8 TF32 and the 3xTF32 split: every operand v = hi + lo with hi = tf32(v), lo = tf32(v - hi),
+// and hi*hi + (hi*lo + lo*hi) accumulated in fp32 (the cross terms in their own accumulator, so the big one sees
+// only ceil(n_coef / 8) additions).  Relative error per product ~2^-21.  NFC stays the exact serial cascade.
+// Samples are the M dimension (a 32-sample slice of the chunk per warp = two m16 tiles), the <= 24 outputs the N
+// dimension (three n8 tiles, no padding for 22.2), the coefficients K padded to a multiple of 8 with zero rows.
+constexpr int kPitchTc = 137;  // odd (NFC row walkers) and = 9 mod 32 (A fragments: k * 9 + m, two-way at worst)
+
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int NC>
+__global__ void __launch_bounds__(kChunk, NC <= 25 ? 4 : 2)
+    hoa_render_tc_kernel(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ nfc_state,
+                         const float* __restrict__ nfc, const __grid_constant__ HoaParams P) {
+  pdl_prologue();
+  constexpr int KS = (NC + 7) / 8;
+  extern __shared__ float tile[];  // [KS * 8][kPitchTc], rows >= NC stay zero
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tig = lane & 3;
+  const size_t s = blockIdx.x;
+  const float* x = in + s * size_t(NC) * kFrame;
+  const int n_out = P.n_out;
+  float* y = out + s * size_t(n_out) * kFrame;
+
+  // B fragments of M^T, split once: b0 = (k = tig, n = g), b1 = (k = tig + 4, n = g)
+  uint32_t bh[KS][3][2], bl[KS][3][2];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = ks * 8 + tig + 4 * h, och = nt * 8 + g;
+        const float m = (k < NC && och < n_out) ? P.M[och * NC + k] : 0.0f;
+        bh[ks][nt][h] = to_tf32(m);
+        bl[ks][nt][h] = to_tf32(fsub(m, __uint_as_float(bh[ks][nt][h])));
+      }
+  for (int r = NC; r < KS * 8; ++r) tile[r * kPitchTc + t] = 0.0f;
+
+  float c[17], st[14];
+  const bool nfc_thread = P.use_nfc && t < NC;
+  if (nfc_thread) {
+#pragma unroll
+    for (int i = 0; i < 17; ++i) c[i] = __ldg(nfc + t * 17 + i);
+#pragma unroll
+    for (int i = 0; i < 14; ++i) st[i] = nfc_state[(s * NC + t) * 14 + i];
+  }
+  const int n2 = nfc_thread ? int(c[1]) : 0;
+  const bool n1 = nfc_thread && c[2] != 0.0f;
+
+  for (int ck = 0; ck < kFrame / kChunk; ++ck) {
+#pragma unroll 5
+    for (int mn = 0; mn < NC; ++mn) tile[mn * kPitchTc + t] = __ldcs(x + size_t(mn) * kFrame + ck * kChunk + t);
+    __syncthreads();
+    if (nfc_thread) {  // the exact cascade of hoa_render_kernel
+      float* row = tile + t * kPitchTc;
+      const bool scale = c[0] != 1.0f;
+      for (int j = 0; j < kChunk; ++j) {
+        float v = row[j];
+        if (scale) v = fmul(v, c[0]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          if (k < n2) {
+            const float a1 = c[3 + 4 * k], a2 = c[4 + 4 * k], b1 = c[5 + 4 * k], b2 = c[6 + 4 * k];
+            const float x0 = v;
+            v = fadd(fsub(fsub(fmul(st[4 * k + 1], b2), fmul(st[4 * k + 2], a1)), fmul(st[4 * k + 3], a2)),
+                     fadd(fmul(st[4 * k], b1), x0));
+            st[4 * k + 3] = st[4 * k + 2];
+            st[4 * k + 2] = v;
+            st[4 * k + 1] = st[4 * k];
+            st[4 * k] = x0;
+          }
+        }
+        if (n1) {
+          const float x0 = v;
+          v = fadd(fsub(fmul(st[12], c[16]), fmul(st[13], c[15])), x0);
+          st[13] = v;
+          st[12] = x0;
+        }
+        row[j] = v;
+      }
+    }
+    if (P.use_nfc) __syncthreads();
+#pragma unroll 1
+    for (int mt = 0; mt < 2; ++mt) {
+      const int m0 = warp * 32 + mt * 16;
+      float hi[3][4], lo[3][4];
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hi[nt][j] = lo[nt][j] = 0.0f;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const float* a_lo_k = tile + (ks * 8 + tig) * kPitchTc + m0 + g;
+        const float af[4] = {a_lo_k[0], a_lo_k[8], a_lo_k[4 * kPitchTc], a_lo_k[4 * kPitchTc + 8]};
+        uint32_t ah[4], al[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ah[j] = to_tf32(af[j]);
+          al[j] = to_tf32(fsub(af[j], __uint_as_float(ah[j])));
+        }
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) {
+          mma_tf32(lo[nt], al, bh[ks][nt][0], bh[ks][nt][1]);
+          mma_tf32(lo[nt], ah, bl[ks][nt][0], bl[ks][nt][1]);
+          mma_tf32(hi[nt], ah, bh[ks][nt][0], bh[ks][nt][1]);
+        }
+      }
+      // c0 = (m = g, n = 2 tig), c1 = (g, 2 tig + 1), c2 = (g + 8, 2 tig), c3 = (g + 8, 2 tig + 1)
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int och = nt * 8 + 2 * tig + (j & 1);
+          float val = fadd(hi[nt][j], lo[nt][j]);
+          if (P.clip) {
+            val = (val < 32767.0f) ? val : 32767.0f;
+            val = (val > -32768.0f) ? val : -32768.0f;
+          }
+          if (och < n_out) __stcs(y + size_t(och) * kFrame + ck * kChunk + m0 + g + (j >> 1) * 8, val);
+        }
+    }
+    __syncthreads();
+  }
+  if (nfc_thread) {
+#pragma unroll
+    for (int i = 0; i < 14; ++i) nfc_state[(s * NC + t) * 14 + i] = st[i];
+  }
+}
+
+template <int NC>
+cudaError_t launch_tc(const float* in, float* out, float* st, const float* nfc, const HoaParams& P, int n_streams,
+                      cudaStream_t stream) {
+  return launch_pdl(hoa_render_tc_kernel<NC>, dim3(n_streams), dim3(kChunk),
+                    ((NC + 7) / 8) * 8 * kPitchTc * sizeof(float), stream, in, out, st, nfc, P);
+}
+
 }  // namespace
 }  // namespace mpeghb200
 
@@ -148,6 +499,7 @@ struct mpeghb200_hoa_renderer {
   mpeghb200_ctx* ctx = nullptr;
   HoaParams P{};
   float* d_nfc = nullptr;  // [n_coef][17]
+  bool tensor = false;     // 3xTF32 mma.sync contraction instead of the bit-exact one
 };
 
 extern "C" {
@@ -197,6 +549,12 @@ void mpeghb200_hoa_renderer_destroy(mpeghb200_hoa_renderer* r) {
   delete r;
 }
 
+mpeghb200_status mpeghb200_hoa_renderer_set_tensor_mode(mpeghb200_hoa_renderer* r, int on) {
+  if (!r) return MPEGHB200_ERR_BAD_ARG;
+  r->tensor = on != 0;
+  return MPEGHB200_OK;
+}
+
 size_t mpeghb200_hoa_nfc_state_floats(const mpeghb200_hoa_renderer* r) { return r ? size_t(r->P.n_coef) * 14 : 0; }
 
 mpeghb200_status mpeghb200_hoa_render_dev(mpeghb200_ctx* ctx, const mpeghb200_hoa_renderer* r, const float* d_in,
@@ -209,6 +567,35 @@ mpeghb200_status mpeghb200_hoa_render_dev(mpeghb200_ctx* ctx, const mpeghb200_ho
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   const HoaParams& P = r->P;
   cudaError_t e;
+  if (r->tensor) {
+    switch (P.n_coef) {
+      case 4: e = launch_tc<4>(d_in, d_out, d_nfc_state, r->d_nfc, P, n_streams, st); break;
+      case 9: e = launch_tc<9>(d_in, d_out, d_nfc_state, r->d_nfc, P, n_streams, st); break;
+      case 16: e = launch_tc<16>(d_in, d_out, d_nfc_state, r->d_nfc, P, n_streams, st); break;
+      case 25: e = launch_tc<25>(d_in, d_out, d_nfc_state, r->d_nfc, P, n_streams, st); break;
+      case 36: e = launch_tc<36>(d_in, d_out, d_nfc_state, r->d_nfc, P, n_streams, st); break;
+      default: e = launch_tc<49>(d_in, d_out, d_nfc_state, r->d_nfc, P, n_streams, st); break;
+    }
+    ctx->launches.fetch_add(1);
+    MB_CUDA(ctx, e);
+    return MPEGHB200_OK;
+  }
+  if (P.use_nfc) {
+    switch (P.n_coef) {
+      case 4: e = launch_nfc<4, 0>(d_in, d_out, d_nfc_state, r->d_nfc, P, n_streams, st); break;
+      case 9: e = launch_nfc<9, 0>(d_in, d_out, d_nfc_state, r->d_nfc, P, n_streams, st); break;
+      case 16: e = launch_nfc<16, 0>(d_in, d_out, d_nfc_state, r->d_nfc, P, n_streams, st); break;
+      case 25:
+        e = (P.n_out == 24) ? launch_nfc<25, 24>(d_in, d_out, d_nfc_state, r->d_nfc, P, n_streams, st)
+                            : launch_nfc<25, 0>(d_in, d_out, d_nfc_state, r->d_nfc, P, n_streams, st);
+        break;
+      case 36: e = launch_nfc<36, 0>(d_in, d_out, d_nfc_state, r->d_nfc, P, n_streams, st); break;
+      default: e = launch_nfc<49, 0>(d_in, d_out, d_nfc_state, r->d_nfc, P, n_streams, st); break;
+    }
+    ctx->launches.fetch_add(1);
+    MB_CUDA(ctx, e);
+    return MPEGHB200_OK;
+  }
   switch (P.n_coef) {
     case 4: e = launch<4, 0>(d_in, d_out, d_nfc_state, r->d_nfc, P, n_streams, st); break;
     case 9: e = launch<9, 0>(d_in, d_out, d_nfc_state, r->d_nfc, P, n_streams, st); break;

@@ -183,6 +183,8 @@ class Lib:
         c.mpeghb200_hoa_renderer_destroy.argtypes = [vp]
         c.mpeghb200_hoa_nfc_state_floats.argtypes = [vp]
         c.mpeghb200_hoa_nfc_state_floats.restype = sz
+        c.mpeghb200_hoa_renderer_set_tensor_mode.argtypes = [vp, ctypes.c_int]
+        c.mpeghb200_hoa_renderer_set_tensor_mode.restype = i32
         c.mpeghb200_hoa_render_dev.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, vp]
         c.mpeghb200_hoa_render_dev.restype = i32
         c.mpeghb200_binaural_create.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp,
@@ -339,6 +341,9 @@ class Lib:
         self.check(self.c.mpeghb200_hoa_renderer_create(self.ctx, m.ctypes.data, m.shape[0], m.shape[1],
                                                         None if n is None else n.ctypes.data, clip, ctypes.byref(h)))
         return h
+
+    def hoa_renderer_set_tensor_mode(self, h, on):
+        self.check(self.c.mpeghb200_hoa_renderer_set_tensor_mode(h, int(on)))
 
     def hoa_renderer_destroy(self, h):
         self.c.mpeghb200_hoa_renderer_destroy(h)

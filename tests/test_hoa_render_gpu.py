@@ -14,11 +14,13 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden", "hoa_ren_golden.npz")
 
 
 class DevHoa:
-    def __init__(self, lib, M, nfc, n_streams):
+    def __init__(self, lib, M, nfc, n_streams, tensor=False):
         import torch
         self.t, self.lib, self.S = torch, lib, n_streams
         self.n_out, self.n_coef = M.shape
         self.h = lib.hoa_renderer_create(M, nfc)
+        if tensor:
+            lib.hoa_renderer_set_tensor_mode(self.h, 1)
         self.state = torch.zeros(max(1, n_streams * lib.hoa_nfc_state_floats(self.h)), device="cuda")
 
     def run(self, x):
@@ -81,3 +83,65 @@ def test_full_size_properties(gpu_lib, oracle):
     assert bits_equal(out_p, out[perm])
     for s in rng.choice(S, 10, replace=False):
         assert bits_equal(out[s], loader.oracle_hoa_render(M, x[s], nfc, np.zeros((25, 14), np.float32))), s
+
+
+# ---- opt-in tensor-core mode (3xTF32 mma): BASELINE.json's float-stage tolerance instead of bit identity ----
+TOL_FLOAT = 2.0 ** -20 * 32768.0  # max |err| <= 2^-20 of full scale, full scale = 2^15 on this path
+
+
+@pytest.mark.parametrize("cfg", hoa_cases.CONFIGS, ids=hoa_cases.key)
+def test_tensor_mode_vs_oracle(gpu_lib, oracle, cfg):
+    """Same streams as test_streams_vs_oracle through the tensor-core contraction: within 2^-20 of full scale,
+    and the 24-bit PCM (truncation of 256 v, decoder/ia_core_coder_decode_main.c:247-261) within +-1 LSB."""
+    g = np.load(GOLD)
+    k = hoa_cases.key(cfg)
+    M, nfc = g[k + "_M"], (g[k + "_nfc"] if cfg[3] > 0 else None)
+    rng = np.random.default_rng(cfg[0] * 31 + cfg[1])
+    S, F = 9, 4
+    x = np.stack([hoa_cases.hoa_signal(rng, F, M.shape[1]) for _ in range(S)], axis=1)
+    states = [np.zeros((M.shape[1], 14), np.float32) for _ in range(S)]
+    r = DevHoa(gpu_lib, M, nfc, S, tensor=True)
+    worst = 0.0
+    for f in range(F):
+        got = r.run(x[f])
+        for s in range(S):
+            want = loader.oracle_hoa_render(M, x[f, s], nfc, states[s])
+            assert np.isfinite(got[s]).all()
+            # frame 1 is driven 60x over full scale to exercise the clip (and rings on in the NFC state of frame
+            # 2): the tolerance is relative to full scale, so it follows the input peak when that exceeds it
+            over = max(1.0, float(np.abs(x[max(0, f - 1):f + 1, s]).max()) / 32768.0)
+            err = float(np.abs(got[s].astype(np.float64) - want).max())
+            assert err <= TOL_FLOAT * over, (k, f, s, err, over)
+            if over == 1.0:
+                worst = max(worst, err)
+                lsb = np.abs(np.trunc(got[s].astype(np.float64) * 256) - np.trunc(want.astype(np.float64) * 256))
+                assert lsb.max() <= 1, (k, f, s, float(lsb.max()))
+    r.close()
+    print(f"tensor mode {k}: max |err| = {worst:.3e} (gate {TOL_FLOAT:.3e})")
+
+
+def test_tensor_mode_full_size(gpu_lib, oracle):
+    """BASELINE config 3 shape in tensor mode: permutation invariance (bit-exact: same code per stream) and
+    spot checks against the oracle within the float tolerance; NFC state carried identically to the exact mode."""
+    g = np.load(GOLD)
+    k = hoa_cases.key(hoa_cases.CONFIGS[0])
+    M, nfc = g[k + "_M"], g[k + "_nfc"]
+    rng = np.random.default_rng(2345)
+    S = 1024
+    x = rng.normal(0, 2000.0, size=(S, 25, 1024)).astype(np.float32)
+    r = DevHoa(gpu_lib, M, nfc, S, tensor=True)
+    out = r.run(x)
+    st_tc = r.state.cpu().numpy()
+    r.close()
+    r1 = DevHoa(gpu_lib, M, nfc, S)
+    r1.run(x)
+    assert bits_equal(st_tc, r1.state.cpu().numpy())  # the NFC cascade is the exact one in both modes
+    r1.close()
+    perm = rng.permutation(S)
+    r2 = DevHoa(gpu_lib, M, nfc, S, tensor=True)
+    out_p = r2.run(x[perm])
+    r2.close()
+    assert bits_equal(out_p, out[perm])
+    for s in rng.choice(S, 10, replace=False):
+        want = loader.oracle_hoa_render(M, x[s], nfc, np.zeros((25, 14), np.float32))
+        assert float(np.abs(out[s].astype(np.float64) - want).max()) <= TOL_FLOAT, s
