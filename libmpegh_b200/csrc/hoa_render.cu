@@ -9,13 +9,14 @@
 // out[och][t] = sum_mn M[och][mn] * x[mn][t], accumulated left to right from 0 with separately rounded
 // products and sums exactly like the reference (so no tensor cores and no FMA on this path: a TF32/BF16
 // product is 2^-11/2^-8 relative, far outside the +-1 LSB@24 bit gate, and any re-association changes LSBs).
-// One CTA per stream walks the frame in 128-sample chunks:
-//   load  x[mn][128] -> shared memory (coalesced rows, pitch 129 so the per-row IIR threads do not collide)
-//   NFC   thread mn < n_coef runs its cascade over the chunk in place (state in registers across chunks)
-//   mix   thread t owns sample t: its n_coef inputs sit in registers, M comes from the kernel-parameter
-//         constant bank (warp-uniform operand, no load instruction), 2 FP instructions per MAC
+// NFC off: hoa_render_kernel, one CTA per (stream, 128-sample chunk), a thread per sample: its n_coef inputs sit in
+//   registers, M comes from the kernel-parameter constant bank (warp-uniform operand, no load instruction),
+//   2 FP instructions per MAC.
+// NFC on:  hoa_render_nfc_kernel, one CTA per stream: filter warps (a lane per coefficient, cascade state in
+//   registers over the whole frame) run one 64-sample stage ahead of the mixing warps through a ring of tiles.
 // Algorithmic bytes per stream-frame: (n_coef + n_out) * 4096 (+ NFC state). For order 4 -> 22.2 that is
-// 200 KB against 1.23 M unfused mul+add: the stage is FP32-issue bound (~36 T op/s), not HBM bound.
+// 200 KB against 1.23 M unfused mul+add (+ ~20 k warp-instructions of cascades): the stage is FP32-issue bound
+// (tools/exp/fp_probe: 3.1-3.4 FMUL/FADD warp-instructions per cycle per SM), not HBM bound.
 #include <cstring>
 #include <new>
 
@@ -43,106 +44,53 @@ struct HoaParams {
 
 // NC = number of HOA coefficients (compile time: the sample's inputs live in registers);
 // NO = number of outputs when known at compile time, 0 = run-time loop
+// NFC off: every 128-sample chunk of every stream is independent, one CTA each; a thread owns one sample, reads its
+// NC inputs straight from global memory (a warp = 128 consecutive bytes of a row) and writes n_out outputs.
 template <int NC, int NO>
 __global__ void __launch_bounds__(kChunk)
-    hoa_render_kernel(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ nfc_state,
-                      const float* __restrict__ nfc, const __grid_constant__ HoaParams P) {
+    hoa_render_kernel(const float* __restrict__ in, float* __restrict__ out, const __grid_constant__ HoaParams P) {
   pdl_prologue();
-  extern __shared__ float tile[];  // [NC][kPitch]
   const int t = threadIdx.x;
-  const size_t s = blockIdx.x;
-  const float* x = in + s * size_t(NC) * kFrame;
+  const size_t s = blockIdx.x / (kFrame / kChunk);
+  const int ck = blockIdx.x % (kFrame / kChunk);
+  const float* x = in + s * size_t(NC) * kFrame + ck * kChunk + t;
   const int n_out = NO ? NO : P.n_out;
-  float* y = out + s * size_t(n_out) * kFrame;
+  float* yo = out + s * size_t(n_out) * kFrame + ck * kChunk + t;
 
-  // NFC thread state
-  float c[17], st[14];
-  const bool nfc_thread = P.use_nfc && t < NC;
-  if (nfc_thread) {
+  float xin[NC];
 #pragma unroll
-    for (int i = 0; i < 17; ++i) c[i] = __ldg(nfc + t * 17 + i);
+  for (int mn = 0; mn < NC; ++mn) xin[mn] = __ldcs(x + size_t(mn) * kFrame);
+  if (NO) {
 #pragma unroll
-    for (int i = 0; i < 14; ++i) st[i] = nfc_state[(s * NC + t) * 14 + i];
-  }
-  const int n2 = nfc_thread ? int(c[1]) : 0;
-  const bool n1 = nfc_thread && c[2] != 0.0f;
-
-  for (int ck = 0; ck < kFrame / kChunk; ++ck) {
-#pragma unroll 5
-    for (int mn = 0; mn < NC; ++mn) tile[mn * kPitch + t] = __ldcs(x + size_t(mn) * kFrame + ck * kChunk + t);
-    __syncthreads();
-    if (nfc_thread) {
-      float* row = tile + t * kPitch;
-      const bool scale = c[0] != 1.0f;
-      for (int j = 0; j < kChunk; ++j) {
-        float v = row[j];
-        if (scale) v = fmul(v, c[0]);
+    for (int och = 0; och < (NO ? NO : 1); ++och) {
+      float val = 0.0f;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          if (k < n2) {
-            const float a1 = c[3 + 4 * k], a2 = c[4 + 4 * k], b1 = c[5 + 4 * k], b2 = c[6 + 4 * k];
-            const float x0 = v;
-            // ((x2*b2 - y1*a1) - y2*a2) + (x1*b1 + x0*b0), b0 = 1 (decoder/impeghd_hoa_nfc_filtering.c:72-77)
-            v = fadd(fsub(fsub(fmul(st[4 * k + 1], b2), fmul(st[4 * k + 2], a1)), fmul(st[4 * k + 3], a2)),
-                     fadd(fmul(st[4 * k], b1), x0));
-            st[4 * k + 3] = st[4 * k + 2];
-            st[4 * k + 2] = v;
-            st[4 * k + 1] = st[4 * k];
-            st[4 * k] = x0;
-          }
-        }
-        if (n1) {
-          const float x0 = v;
-          v = fadd(fsub(fmul(st[12], c[16]), fmul(st[13], c[15])), x0);  // :108-110
-          st[13] = v;
-          st[12] = x0;
-        }
-        row[j] = v;
+      for (int mn = 0; mn < NC; ++mn) val = fadd(val, fmul(P.M[och * NC + mn], xin[mn]));
+      if (P.clip) {
+        val = (val < 32767.0f) ? val : 32767.0f;
+        val = (val > -32768.0f) ? val : -32768.0f;
       }
+      __stcs(yo + size_t(och) * kFrame, val);
     }
-    if (P.use_nfc) __syncthreads();
-    float xin[NC];
+  } else {
+    for (int och = 0; och < n_out; ++och) {
+      float val = 0.0f;
+      const float* Mr = P.M + och * NC;
 #pragma unroll
-    for (int mn = 0; mn < NC; ++mn) xin[mn] = tile[mn * kPitch + t];
-    float* yo = y + ck * kChunk + t;
-    if (NO) {
-#pragma unroll
-      for (int och = 0; och < (NO ? NO : 1); ++och) {
-        float val = 0.0f;
-#pragma unroll
-        for (int mn = 0; mn < NC; ++mn) val = fadd(val, fmul(P.M[och * NC + mn], xin[mn]));
-        if (P.clip) {
-          val = (val < 32767.0f) ? val : 32767.0f;
-          val = (val > -32768.0f) ? val : -32768.0f;
-        }
-        __stcs(yo + size_t(och) * kFrame, val);
+      for (int mn = 0; mn < NC; ++mn) val = fadd(val, fmul(Mr[mn], xin[mn]));
+      if (P.clip) {
+        val = (val < 32767.0f) ? val : 32767.0f;
+        val = (val > -32768.0f) ? val : -32768.0f;
       }
-    } else {
-      for (int och = 0; och < n_out; ++och) {
-        float val = 0.0f;
-        const float* Mr = P.M + och * NC;
-#pragma unroll
-        for (int mn = 0; mn < NC; ++mn) val = fadd(val, fmul(Mr[mn], xin[mn]));
-        if (P.clip) {
-          val = (val < 32767.0f) ? val : 32767.0f;
-          val = (val > -32768.0f) ? val : -32768.0f;
-        }
-        __stcs(yo + size_t(och) * kFrame, val);
-      }
+      __stcs(yo + size_t(och) * kFrame, val);
     }
-    __syncthreads();
-  }
-  if (nfc_thread) {
-#pragma unroll
-    for (int i = 0; i < 14; ++i) nfc_state[(s * NC + t) * 14 + i] = st[i];
   }
 }
 
 template <int NC, int NO>
-cudaError_t launch(const float* in, float* out, float* st, const float* nfc, const HoaParams& P, int n_streams,
+cudaError_t launch(const float* in, float* out, float*, const float*, const HoaParams& P, int n_streams,
                    cudaStream_t stream) {
-  return launch_pdl(hoa_render_kernel<NC, NO>, dim3(n_streams), dim3(kChunk), NC * kPitch * sizeof(float), stream, in, out,
-                    st, nfc, P);
+  return launch_pdl(hoa_render_kernel<NC, NO>, dim3(n_streams * (kFrame / kChunk)), dim3(kChunk), 0, stream, in, out, P);
 }
 
 // One filter lane's cascade over a chunk row, cell counts at compile time (the reference gives every coefficient
