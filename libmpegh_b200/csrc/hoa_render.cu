@@ -98,7 +98,16 @@ cudaError_t launch(const float* in, float* out, float*, const float*, const HoaP
 // practice): nothing predicated, the cells of consecutive samples overlap in the pipeline.  The gain multiply is
 // unconditional: x * 1.0f is x bit for bit, the reference skips it only when the gain is 1.
 template <int N2, bool N1, int LEN>
-__device__ __forceinline__ void nfc_cascade(float* row, const float (&c)[17], float (&st)[14]) {
+__device__ __forceinline__ void nfc_cascade(float* row, const float* __restrict__ cg, float (&st)[14]) {
+  // only the coefficients this instantiation uses, re-read (L1 hits) per call instead of held across the mix
+  float c[17];
+  c[0] = __ldg(cg);
+#pragma unroll
+  for (int i = 3; i < 3 + 4 * N2; ++i) c[i] = __ldg(cg + i);
+  if (N1) {
+    c[15] = __ldg(cg + 15);
+    c[16] = __ldg(cg + 16);
+  }
   for (int j0 = 0; j0 < LEN; j0 += 8) {
     float v[8];
 #pragma unroll
@@ -158,16 +167,14 @@ __global__ void __launch_bounds__(kChunk + 32 * ((NC + 31) / 32), NC <= 25 ? 7 :
   const int tn = t - kChunk;  // filter lane: coefficient index
   const bool filt = !mixer && tn < NC;
 
-  float c[17], st[14];
+  float st[14];
+  const float* cg = nfc + (filt ? tn : 0) * 17;
   if (filt) {
-#pragma unroll
-    for (int i = 0; i < 17; ++i) c[i] = __ldg(nfc + tn * 17 + i);
 #pragma unroll
     for (int i = 0; i < 14; ++i) st[i] = nfc_state[(s * NC + tn) * 14 + i];
   }
-  const int n2 = filt ? int(c[1]) : 0;
-  const bool n1 = filt && c[2] != 0.0f;
-  const bool scale = filt && c[0] != 1.0f;
+  const int n2 = filt ? int(__ldg(cg + 1)) : 0;
+  const bool n1 = filt && __ldg(cg + 2) != 0.0f;
 
   // cell counts of this warp's lanes: uniform (always, with reference-designed coefficients) or mixed
   int key = -1;
@@ -178,19 +185,21 @@ __global__ void __launch_bounds__(kChunk + 32 * ((NC + 31) / 32), NC <= 25 ? 7 :
   }
   auto cascade = [&](float* row) {
     switch (key) {
-      case 0: nfc_cascade<0, false, kSub>(row, c, st); return;
-      case 1: nfc_cascade<0, true, kSub>(row, c, st); return;
-      case 2: nfc_cascade<1, false, kSub>(row, c, st); return;
-      case 3: nfc_cascade<1, true, kSub>(row, c, st); return;
-      case 4: nfc_cascade<2, false, kSub>(row, c, st); return;
-      case 5: nfc_cascade<2, true, kSub>(row, c, st); return;
-      case 6: nfc_cascade<3, false, kSub>(row, c, st); return;
-      case 7: nfc_cascade<3, true, kSub>(row, c, st); return;
+      case 0: nfc_cascade<0, false, kSub>(row, cg, st); return;
+      case 1: nfc_cascade<0, true, kSub>(row, cg, st); return;
+      case 2: nfc_cascade<1, false, kSub>(row, cg, st); return;
+      case 3: nfc_cascade<1, true, kSub>(row, cg, st); return;
+      case 4: nfc_cascade<2, false, kSub>(row, cg, st); return;
+      case 5: nfc_cascade<2, true, kSub>(row, cg, st); return;
+      case 6: nfc_cascade<3, false, kSub>(row, cg, st); return;
+      case 7: nfc_cascade<3, true, kSub>(row, cg, st); return;
       default: break;
     }
-    for (int j = 0; j < kSub; ++j) {  // mixed cell counts in one warp: predicated cells
-      float w = row[j];
-      if (scale) w = fmul(w, c[0]);
+    float c[17];  // mixed cell counts in one warp: predicated cells
+#pragma unroll
+    for (int i = 0; i < 17; ++i) c[i] = __ldg(cg + i);
+    for (int j = 0; j < kSub; ++j) {
+      float w = fmul(row[j], c[0]);
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         if (k < n2) {
