@@ -97,13 +97,15 @@ cudaError_t launch(const float* in, float* out, float*, const float*, const HoaP
 // of an order-N renderer the same N / 2 second-order cells and N % 2 first-order cell, so a warp is uniform in
 // practice): nothing predicated, the cells of consecutive samples overlap in the pipeline.  The gain multiply is
 // unconditional: x * 1.0f is x bit for bit, the reference skips it only when the gain is 1.
-template <int N2, bool N1, int LEN>
+// A cascade is split over two filter warps a stage apart: the first runs the gain and cells [0, K1) (K0 = 0, GAIN),
+// the second cells [K0, N2) and the first-order cell.
+template <int K0, int K1, bool N1, bool GAIN, int LEN>
 __device__ __forceinline__ void nfc_cascade(float* row, const float* __restrict__ cg, float (&st)[14]) {
   // only the coefficients this instantiation uses, re-read (L1 hits) per call instead of held across the mix
   float c[17];
-  c[0] = __ldg(cg);
+  if (GAIN) c[0] = __ldg(cg);
 #pragma unroll
-  for (int i = 3; i < 3 + 4 * N2; ++i) c[i] = __ldg(cg + i);
+  for (int i = 3 + 4 * K0; i < 3 + 4 * K1; ++i) c[i] = __ldg(cg + i);
   if (N1) {
     c[15] = __ldg(cg + 15);
     c[16] = __ldg(cg + 16);
@@ -114,9 +116,9 @@ __device__ __forceinline__ void nfc_cascade(float* row, const float* __restrict_
     for (int u = 0; u < 8; ++u) v[u] = row[j0 + u];  // off the dependent chain
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      float w = fmul(v[u], c[0]);
+      float w = GAIN ? fmul(v[u], c[0]) : v[u];
 #pragma unroll
-      for (int k = 0; k < N2; ++k) {
+      for (int k = K0; k < K1; ++k) {
         const float a1 = c[3 + 4 * k], a2 = c[4 + 4 * k], b1 = c[5 + 4 * k], b2 = c[6 + 4 * k];
         const float x0 = w;
         // ((x2*b2 - y1*a1) - y2*a2) + (x1*b1 + x0*b0), b0 = 1 (decoder/impeghd_hoa_nfc_filtering.c:72-77)
@@ -140,22 +142,22 @@ __device__ __forceinline__ void nfc_cascade(float* row, const float* __restrict_
   }
 }
 
-// ---- NFC on: the cascades run one stage ahead of the mix, on their own warps ---------------------------------
-// In hoa_render_kernel the 128 mixing threads wait at a barrier while <= NC lanes walk their IIR chains over the
-// chunk, and then the filter lanes wait for the mix.  Here the CTA has 128 mixing threads + ceil(NC / 32) filter
-// warps and a three-deep ring of 64-sample tiles: while the mixing warps apply M to stage k (thread = one sample
-// and one half of the outputs), the filter warps run stage k + 1 through the cascades in the next tile and the raw
-// stage k + 2 is on its way from HBM into the third by cp.async (no registers, no exposed latency).  One barrier
-// per stage.  Same expressions, same order: bit-identical.
+// ---- NFC on: the cascades run ahead of the mix, on their own warps ------------------------------------------
+// The CTA of a stream has 64 mixing threads + two groups of ceil(NC / 32) filter warps (a lane per coefficient) and
+// a four-deep ring of 64-sample tiles.  In step k the mixing warps apply M to stage k (a thread per sample), filter group B runs the second half of the cascade over stage k + 1, group A the gain and the
+// first half over stage k + 2, and the raw stage k + 3 is on its way from HBM by cp.async (no registers, no exposed
+// latency).  One barrier per step.  A filter warp issues one sample per instruction, so with the whole cascade on
+// one warp that warp was the critical path of every step; split, it is about as long as a mixing warp's share.
+// Same expressions, same order: bit-identical.
 constexpr int kSub = 64;
 constexpr int kSubPitch = kSub + 1;  // odd: the filter lanes walk their rows without bank conflicts
 
 template <int NC, int NO>
-__global__ void __launch_bounds__(kChunk + 32 * ((NC + 31) / 32), NC <= 25 ? 7 : 1)
+__global__ void __launch_bounds__(kSub + 64 * ((NC + 31) / 32), NC <= 25 ? 7 : 1)
     hoa_render_nfc_kernel(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ nfc_state,
                           const float* __restrict__ nfc, const __grid_constant__ HoaParams P) {
   pdl_prologue();
-  extern __shared__ float tile[];  // [3][NC][kSubPitch]
+  extern __shared__ float tile[];  // [4][NC][kSubPitch]
   constexpr int kBuf = NC * kSubPitch;
   constexpr int kSubs = kFrame / kSub;
   const int t = threadIdx.x;
@@ -163,8 +165,10 @@ __global__ void __launch_bounds__(kChunk + 32 * ((NC + 31) / 32), NC <= 25 ? 7 :
   const float* x = in + s * size_t(NC) * kFrame;
   const int n_out = NO ? NO : P.n_out;
   float* y = out + s * size_t(n_out) * kFrame;
-  const bool mixer = t < kChunk;
-  const int tn = t - kChunk;  // filter lane: coefficient index
+  constexpr int kFilt = 32 * ((NC + 31) / 32);  // lanes of one filter group
+  const bool mixer = t < kSub;
+  const bool grp_b = t >= kSub + kFilt;
+  const int tn = t - kSub - (grp_b ? kFilt : 0);  // filter lane: coefficient index
   const bool filt = !mixer && tn < NC;
 
   float st[14];
@@ -176,26 +180,38 @@ __global__ void __launch_bounds__(kChunk + 32 * ((NC + 31) / 32), NC <= 25 ? 7 :
   const int n2 = filt ? int(__ldg(cg + 1)) : 0;
   const bool n1 = filt && __ldg(cg + 2) != 0.0f;
 
-  // cell counts of this warp's lanes: uniform (always, with reference-designed coefficients) or mixed
+  // cell counts of this warp's lanes: uniform (always, with reference-designed coefficients) or mixed; a CTA
+  // with a mixed warp anywhere runs every cascade whole, predicated, in group A
   int key = -1;
   if (!mixer) {
     const int mine = filt ? n2 * 2 + int(n1) : -1;
     const int first = __shfl_sync(0xffffffffu, mine, 0);
     key = __all_sync(0xffffffffu, !filt || mine == first) ? first : -1;
   }
+  const bool split = __syncthreads_and(mixer || key >= 0) != 0;
+  // group A: gain + cells [0, (n2 + 1) / 2); group B: the remaining second-order cells + the first-order cell
   auto cascade = [&](float* row) {
-    switch (key) {
-      case 0: nfc_cascade<0, false, kSub>(row, cg, st); return;
-      case 1: nfc_cascade<0, true, kSub>(row, cg, st); return;
-      case 2: nfc_cascade<1, false, kSub>(row, cg, st); return;
-      case 3: nfc_cascade<1, true, kSub>(row, cg, st); return;
-      case 4: nfc_cascade<2, false, kSub>(row, cg, st); return;
-      case 5: nfc_cascade<2, true, kSub>(row, cg, st); return;
-      case 6: nfc_cascade<3, false, kSub>(row, cg, st); return;
-      case 7: nfc_cascade<3, true, kSub>(row, cg, st); return;
-      default: break;
+    if (split && !grp_b) {
+      switch (key >> 1) {
+        case 0: nfc_cascade<0, 0, false, true, kSub>(row, cg, st); return;
+        case 1: nfc_cascade<0, 1, false, true, kSub>(row, cg, st); return;
+        case 2: nfc_cascade<0, 1, false, true, kSub>(row, cg, st); return;
+        default: nfc_cascade<0, 2, false, true, kSub>(row, cg, st); return;
+      }
     }
-    float c[17];  // mixed cell counts in one warp: predicated cells
+    if (split) {
+      switch (key) {
+        case 1: nfc_cascade<0, 0, true, false, kSub>(row, cg, st); return;   // n2 = 0 + first order
+        case 3: nfc_cascade<1, 1, true, false, kSub>(row, cg, st); return;   // n2 = 1 + first order
+        case 4: nfc_cascade<1, 2, false, false, kSub>(row, cg, st); return;  // n2 = 2
+        case 5: nfc_cascade<1, 2, true, false, kSub>(row, cg, st); return;
+        case 6: nfc_cascade<2, 3, false, false, kSub>(row, cg, st); return;  // n2 = 3
+        case 7: nfc_cascade<2, 3, true, false, kSub>(row, cg, st); return;
+        default: return;  // n2 <= 1 without a first-order cell: nothing left for group B
+      }
+    }
+    if (grp_b) return;
+    float c[17];  // mixed cell counts: predicated cells
 #pragma unroll
     for (int i = 0; i < 17; ++i) c[i] = __ldg(cg + i);
     for (int j = 0; j < kSub; ++j) {
@@ -222,12 +238,12 @@ __global__ void __launch_bounds__(kChunk + 32 * ((NC + 31) / 32), NC <= 25 ? 7 :
       row[j] = w;
     }
   };
-  // raw stage k -> tile k % 3, by the mixing threads (a warp copies 32 consecutive samples of a row)
+  // raw stage k -> tile k % 4, by the mixing threads (a warp copies 32 consecutive samples of a row)
   auto fetch = [&](int k) {
-    float* b = tile + (k % 3) * kBuf;
+    float* b = tile + (k & 3) * kBuf;
     const float* src = x + k * kSub;
-    for (int idx = t; idx < NC * kSub; idx += kChunk)
-      cp_async4(b + (idx >> 6) * kSubPitch + (idx & (kSub - 1)), src + size_t(idx >> 6) * kFrame + (idx & (kSub - 1)));
+#pragma unroll 5
+    for (int mn = 0; mn < NC; ++mn) cp_async4(b + mn * kSubPitch + t, src + size_t(mn) * kFrame + t);
   };
   // one output row of the mix: och and the matrix row are compile-time or warp-uniform in every caller
   auto mix_row = [&](const float (&xin)[NC], const float* Mr, float* yo) {
@@ -241,6 +257,7 @@ __global__ void __launch_bounds__(kChunk + 32 * ((NC + 31) / 32), NC <= 25 ? 7 :
     __stcs(yo, val);
   };
 
+  auto row_of = [&](int k) { return tile + (k & 3) * kBuf + tn * kSubPitch; };
   if (mixer) {
     fetch(0);
     cp_async_wait_all();
@@ -249,44 +266,48 @@ __global__ void __launch_bounds__(kChunk + 32 * ((NC + 31) / 32), NC <= 25 ? 7 :
   if (mixer) {
     fetch(1);
     cp_async_wait_all();
+  } else if (filt && !grp_b) {
+    cascade(row_of(0));
+  }
+  __syncthreads();
+  if (mixer) {
+    fetch(2);
+    cp_async_wait_all();
   } else if (filt) {
-    cascade(tile + tn * kSubPitch);
+    cascade(row_of(grp_b ? 0 : 1));
   }
   __syncthreads();
 
-  const int smp = t & (kSub - 1);
   for (int k = 0; k < kSubs; ++k) {
-    // here: tile k % 3 holds the filtered stage k, tile (k + 1) % 3 the raw stage k + 1
+    // here: tile k & 3 holds the filtered stage k, the next one stage k + 1 after group A, the next the raw stage k + 2
     if (mixer) {
-      if (k + 2 < kSubs) fetch(k + 2);  // into the tile the mix of stage k - 1 has finished with
-      const float* cur = tile + (k % 3) * kBuf;
+      if (k + 3 < kSubs) fetch(k + 3);  // into the tile the mix of stage k - 1 has finished with
+      const float* cur = tile + (k & 3) * kBuf;
       float xin[NC];
 #pragma unroll
-      for (int mn = 0; mn < NC; ++mn) xin[mn] = cur[mn * kSubPitch + smp];
-      float* yo = y + k * kSub + smp;
+      for (int mn = 0; mn < NC; ++mn) xin[mn] = cur[mn * kSubPitch + t];
+      float* yo = y + k * kSub + t;
       if (NO) {
-        constexpr int H = (NO ? NO : 2) / 2;
-        if (t < kSub) {
 #pragma unroll
-          for (int och = 0; och < H; ++och) mix_row(xin, P.M + och * NC, yo + size_t(och) * kFrame);
-        } else {
-#pragma unroll
-          for (int och = H; och < (NO ? NO : 2); ++och) mix_row(xin, P.M + och * NC, yo + size_t(och) * kFrame);
-        }
-      } else if (t < kSub) {
-        for (int och = 0; och < n_out; och += 2) mix_row(xin, P.M + och * NC, yo + size_t(och) * kFrame);
+        for (int och = 0; och < (NO ? NO : 1); ++och) mix_row(xin, P.M + och * NC, yo + size_t(och) * kFrame);
       } else {
-        for (int och = 1; och < n_out; och += 2) mix_row(xin, P.M + och * NC, yo + size_t(och) * kFrame);
+        for (int och = 0; och < n_out; ++och) mix_row(xin, P.M + och * NC, yo + size_t(och) * kFrame);
       }
       cp_async_wait_all();
-    } else if (filt && k + 1 < kSubs) {
-      cascade(tile + ((k + 1) % 3) * kBuf + tn * kSubPitch);
+    } else if (filt && k + (grp_b ? 1 : 2) < kSubs) {
+      cascade(row_of(k + (grp_b ? 1 : 2)));
     }
     __syncthreads();
   }
-  if (filt) {
+  if (filt) {  // each group writes back the state of the cells it ran
+    const int ka = split ? (n2 + 1) / 2 : 3;
 #pragma unroll
-    for (int i = 0; i < 14; ++i) nfc_state[(s * NC + tn) * 14 + i] = st[i];
+    for (int i = 0; i < 12; ++i)
+      if ((i / 4 < ka) != grp_b) nfc_state[(s * NC + tn) * 14 + i] = st[i];
+    if (grp_b == split) {
+      nfc_state[(s * NC + tn) * 14 + 12] = st[12];
+      nfc_state[(s * NC + tn) * 14 + 13] = st[13];
+    }
   }
 }
 
@@ -294,9 +315,9 @@ template <int NC, int NO>
 cudaError_t launch_nfc(const float* in, float* out, float* st, const float* nfc, const HoaParams& P, int n_streams,
                        cudaStream_t stream) {
   auto k = hoa_render_nfc_kernel<NC, NO>;
-  const size_t smem = 3 * NC * kSubPitch * sizeof(float);
+  const size_t smem = 4 * NC * kSubPitch * sizeof(float);
   if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-  return launch_pdl(k, dim3(n_streams), dim3(kChunk + 32 * ((NC + 31) / 32)), smem, stream, in, out, st, nfc, P);
+  return launch_pdl(k, dim3(n_streams), dim3(kSub + 64 * ((NC + 31) / 32)), smem, stream, in, out, st, nfc, P);
 }
 
 // ---- tensor-core variant (opt-in, mpeghb200_hoa_renderer_set_tensor_mode) -------------------------------------
