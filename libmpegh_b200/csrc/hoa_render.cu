@@ -324,7 +324,7 @@ cudaError_t launch_nfc(const float* in, float* out, float* st, const float* nfc,
 // BASELINE.json's north_star allows tensor cores for this one contraction, within max |err| <= 2^-20 of full
 // scale instead of bit-identity.  The render matrix is applied as out^T[sample][och] = x^T[sample][mn] * M^T[mn][och]
 // with mma.sync m16n8k8 TF32 and the 3xTF32 split: every operand v = hi + lo with hi = tf32(v), lo = tf32(v - hi),
-// and hi*hi + (hi*lo + lo*hi) accumulated in fp32 (the cross terms in their own accumulator, so the big one sees
+// and hi*hi + (hi*lo + lo*hi) accumulated in fp32 (the cross terms in their own accumulators, so the big one sees
 // only ceil(n_coef / 8) additions).  Relative error per product ~2^-21.  NFC stays the exact serial cascade.
 // Samples are the M dimension (a 32-sample slice of the chunk per warp = two m16 tiles), the <= 24 outputs the N
 // dimension (three n8 tiles, no padding for 22.2), the coefficients K padded to a multiple of 8 with zero rows.
@@ -336,7 +336,7 @@ __device__ __forceinline__ uint32_t to_tf32(float v) {
   return r;
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
+  asm(  // not volatile: a pure function of its operands, the scheduler may interleave independent chains
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -417,11 +417,11 @@ __global__ void __launch_bounds__(kChunk, NC <= 25 ? 4 : 2)
 #pragma unroll 1
     for (int mt = 0; mt < 2; ++mt) {
       const int m0 = warp * 32 + mt * 16;
-      float hi[3][4], lo[3][4];
+      float hi[3][4], lo[3][4], lo2[3][4];
 #pragma unroll
       for (int nt = 0; nt < 3; ++nt)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) hi[nt][j] = lo[nt][j] = 0.0f;
+        for (int j = 0; j < 4; ++j) hi[nt][j] = lo[nt][j] = lo2[nt][j] = 0.0f;
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
         const float* a_lo_k = tile + (ks * 8 + tig) * kPitchTc + m0 + g;
@@ -432,12 +432,13 @@ __global__ void __launch_bounds__(kChunk, NC <= 25 ? 4 : 2)
           ah[j] = to_tf32(af[j]);
           al[j] = to_tf32(fsub(af[j], __uint_as_float(ah[j])));
         }
+// nine independent accumulator chains per k step (an MMA waits for the one it depends on)
 #pragma unroll
-        for (int nt = 0; nt < 3; ++nt) {
-          mma_tf32(lo[nt], al, bh[ks][nt][0], bh[ks][nt][1]);
-          mma_tf32(lo[nt], ah, bl[ks][nt][0], bl[ks][nt][1]);
-          mma_tf32(hi[nt], ah, bh[ks][nt][0], bh[ks][nt][1]);
-        }
+        for (int nt = 0; nt < 3; ++nt) mma_tf32(lo[nt], al, bh[ks][nt][0], bh[ks][nt][1]);
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) mma_tf32(lo2[nt], ah, bl[ks][nt][0], bl[ks][nt][1]);
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) mma_tf32(hi[nt], ah, bh[ks][nt][0], bh[ks][nt][1]);
       }
       // c0 = (m = g, n = 2 tig), c1 = (g, 2 tig + 1), c2 = (g + 8, 2 tig), c3 = (g + 8, 2 tig + 1)
 #pragma unroll
@@ -445,7 +446,7 @@ __global__ void __launch_bounds__(kChunk, NC <= 25 ? 4 : 2)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int och = nt * 8 + 2 * tig + (j & 1);
-          float val = fadd(hi[nt][j], lo[nt][j]);
+          float val = fadd(hi[nt][j], fadd(lo[nt][j], lo2[nt][j]));
           if (P.clip) {
             val = (val < 32767.0f) ? val : 32767.0f;
             val = (val > -32768.0f) ? val : -32768.0f;
@@ -461,9 +462,97 @@ __global__ void __launch_bounds__(kChunk, NC <= 25 ? 4 : 2)
   }
 }
 
+// NFC off: no shared memory and no barriers either.  A CTA takes 256 samples of one stream, a warp 64 of them = four
+// m16 tiles; the A fragments come straight from global memory (a fragment register of a warp = 4 rows x 8 consecutive
+// samples = four full 32-byte sectors), the next tile's 16 loads are in flight under the current tile's 36 MMAs.
+constexpr int kTcSpan = 256;
+template <int NC>
+__global__ void __launch_bounds__(kChunk)
+    hoa_render_tc_direct_kernel(const float* __restrict__ in, float* __restrict__ out, const __grid_constant__ HoaParams P) {
+  pdl_prologue();
+  constexpr int KS = (NC + 7) / 8;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, g = lane >> 2, tig = lane & 3;
+  const size_t s = blockIdx.x / (kFrame / kTcSpan);
+  const int base = (blockIdx.x % (kFrame / kTcSpan)) * kTcSpan + warp * 64;
+  const float* x = in + s * size_t(NC) * kFrame + base + g;
+  const int n_out = P.n_out;
+  float* y = out + s * size_t(n_out) * kFrame + base + g;
+
+  uint32_t bh[KS][3][2], bl[KS][3][2];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = ks * 8 + tig + 4 * h, och = nt * 8 + g;
+        const float m = (k < NC && och < n_out) ? P.M[och * NC + k] : 0.0f;
+        bh[ks][nt][h] = to_tf32(m);
+        bl[ks][nt][h] = to_tf32(fsub(m, __uint_as_float(bh[ks][nt][h])));
+      }
+
+  auto load_tile = [&](int mt, float (&af)[KS][4]) {
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = ks * 8 + tig + 4 * h;
+        const bool ok = (ks * 8 + 4 * h + 3 < NC) || k < NC;  // compile-time true except in the padded last step
+        af[ks][2 * h] = ok ? __ldcs(x + size_t(k) * kFrame + mt * 16) : 0.0f;
+        af[ks][2 * h + 1] = ok ? __ldcs(x + size_t(k) * kFrame + mt * 16 + 8) : 0.0f;
+      }
+  };
+  float cur[KS][4], nxt[KS][4];
+  load_tile(0, cur);
+#pragma unroll 1
+  for (int mt = 0; mt < 4; ++mt) {
+    if (mt + 1 < 4) load_tile(mt + 1, nxt);
+    float hi[3][4], lo[3][4], lo2[3][4];
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) hi[nt][j] = lo[nt][j] = lo2[nt][j] = 0.0f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      uint32_t ah[4], al[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        ah[j] = to_tf32(cur[ks][j]);
+        al[j] = to_tf32(fsub(cur[ks][j], __uint_as_float(ah[j])));
+      }
+// nine independent accumulator chains per k step (an MMA waits for the one it depends on)
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) mma_tf32(lo[nt], al, bh[ks][nt][0], bh[ks][nt][1]);
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) mma_tf32(lo2[nt], ah, bl[ks][nt][0], bl[ks][nt][1]);
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) mma_tf32(hi[nt], ah, bh[ks][nt][0], bh[ks][nt][1]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int och = nt * 8 + 2 * tig + (j & 1);
+        float val = fadd(hi[nt][j], fadd(lo[nt][j], lo2[nt][j]));
+        if (P.clip) {
+          val = (val < 32767.0f) ? val : 32767.0f;
+          val = (val > -32768.0f) ? val : -32768.0f;
+        }
+        if (och < n_out) __stcs(y + size_t(och) * kFrame + mt * 16 + (j >> 1) * 8, val);
+      }
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cur[ks][j] = nxt[ks][j];
+  }
+}
+
 template <int NC>
 cudaError_t launch_tc(const float* in, float* out, float* st, const float* nfc, const HoaParams& P, int n_streams,
                       cudaStream_t stream) {
+  if (!P.use_nfc)
+    return launch_pdl(hoa_render_tc_direct_kernel<NC>, dim3(n_streams * (kFrame / kTcSpan)), dim3(kChunk), 0, stream, in,
+                      out, P);
   return launch_pdl(hoa_render_tc_kernel<NC>, dim3(n_streams), dim3(kChunk),
                     ((NC + 7) / 8) * 8 * kPitchTc * sizeof(float), stream, in, out, st, nfc, P);
 }
