@@ -220,7 +220,7 @@ mpeghb200_status mpeghb200_hoa_renderer_create(mpeghb200_ctx *ctx, const float *
                                                const float *nfc_coeffs, int clip, mpeghb200_hoa_renderer **out);
 void mpeghb200_hoa_renderer_destroy(mpeghb200_hoa_renderer *r);
 size_t mpeghb200_hoa_nfc_state_floats(const mpeghb200_hoa_renderer *r);
-/* Opt-in throughput mode for the one dense contraction of the path (out = M x, impeghd_hoa_renderer.c:203-221):
+/* Opt-in throughput mode for the one dense contraction of the path (out = M x, impeghd_hoa_renderer.c:231-253):
  * on != 0 applies the render matrix on the tensor cores (TF32 mma with the 3xTF32 operand split, fp32
  * accumulation) instead of the reference's left-to-right fp32 sum.  Results are then no longer bit-identical but
  * within BASELINE.json's float-stage tolerance, max |err| <= 2^-20 of full scale (2^-5 at the 16-bit scale of the
