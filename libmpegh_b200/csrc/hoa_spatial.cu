@@ -64,6 +64,7 @@ struct State {
 
 enum Win : int { kWinNone = 0, kWinInVec = 1, kWinOutVec = 2, kWinInDir = 3, kWinOutDir = 4 };
 
+constexpr int kVecPitch = (kMaxCoef + 3) / 4 * 4;
 struct Plan {
   float dyn_a[kMaxCh];
   int dyn_mode[kMaxCh];  // 0: a*x, 1: (x*a)*pow_table[arg][t], 2: pow(win[t], arg) * (a*x)
@@ -78,7 +79,9 @@ struct Plan {
   int pred_g[2][kMaxCoef], pred_n[2][kMaxCoef];
   int pred_idx[2][kMaxCoef][kMaxPred];
   float pred_fac[2][kMaxCoef][kMaxPred];
-  float vec_v[2 * kMaxCh][kMaxCoef];
+  // rows indexed by the coefficient itself (entries below vec_start unused), 16-byte pitch: the render kernel reads
+  // them as float4 (every thread reads the same row: one LDS.128 instead of four LDS.32 on the LSU pipe that bounds it)
+  alignas(16) float vec_v[2 * kMaxCh][kVecPitch];
 };
 
 struct Slot {
@@ -281,7 +284,7 @@ __global__ void __launch_bounds__(128)
       const int n = idx / kMaxCoef, e = idx - n * kMaxCoef;
       const int src = s_vec_slot[n];
       if (src < 0 || e >= nel) continue;
-      pl.vec_v[n][e] = (src < kMaxCh) ? st.prev_vec[src][e] : sd.vec[src - kMaxCh][e];
+      pl.vec_v[n][e + C.vec_start] = (src < kMaxCh) ? st.prev_vec[src][e] : sd.vec[src - kMaxCh][e];
     }
   }
   __syncthreads();
@@ -353,8 +356,9 @@ __global__ void __launch_bounds__(kChunk, (NC <= 25) ? 3 : 2)
     hoasp_render_kernel(const float* __restrict__ in, float* __restrict__ out, const Slot* __restrict__ slots,
                         const __grid_constant__ Cfg C) {
   __shared__ float xs[kMaxCh][kChunk];        // corrected transport samples (before clearing)
-  __shared__ Plan pl;                         // this stream's plan: every thread walks it, so keep it on chip
-  __shared__ float fine_rows[2 * kMaxCh][NC]; // mode-matrix rows of the direction entries
+  __shared__ __align__(16) Plan pl;           // this stream's plan: every thread walks it, so keep it on chip
+  constexpr int NC4 = (NC + 3) / 4;
+  __shared__ __align__(16) float fine_rows[2 * kMaxCh][NC4 * 4]; // mode-matrix rows of the direction entries
   const int tid = threadIdx.x;
   {
     const Plan& gp = slots[blockIdx.x].plan;
@@ -364,7 +368,7 @@ __global__ void __launch_bounds__(kChunk, (NC <= 25) ? 3 : 2)
     for (int i = tid; i < kHead; i += kChunk) dst[i] = src[i];
     if (gp.n_pred[0] | gp.n_pred[1])
       for (int i = kHead + tid; i < kPredEnd; i += kChunk) dst[i] = src[i];
-    const int nv = gp.n_vec_e * kMaxCoef;
+    const int nv = gp.n_vec_e * kVecPitch;
     for (int i = tid; i < nv; i += kChunk) dst[kPredEnd + i] = src[kPredEnd + i];
     const int nd = gp.n_dir_e;
     for (int i = tid; i < nd * NC; i += kChunk) {
@@ -414,16 +418,26 @@ __global__ void __launch_bounds__(kChunk, (NC <= 25) ? 3 : 2)
     if (t >= pl.vec_ns[n]) continue;
     const float xv = xc(pl.vec_ch[n]);
     const int win = pl.vec_win[n];
-    const float* V = pl.vec_v[n] - vs;
+    const float4* V4 = reinterpret_cast<const float4*>(pl.vec_v[n]);
     if (win == kWinNone) {
 #pragma unroll
-      for (int c = 0; c < NC; ++c)
-        if (c >= vs) v[c] = fadd(v[c], fmul(V[c], xv));
+      for (int q = 0; q < NC4; ++q) {
+        const float4 a = V4[q];
+        const float V[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (4 * q + e < NC && 4 * q + e >= vs) v[4 * q + e] = fadd(v[4 * q + e], fmul(V[e], xv));
+      }
     } else {
       const float wv = wsel(win);
 #pragma unroll
-      for (int c = 0; c < NC; ++c)
-        if (c >= vs) v[c] = fadd(v[c], fmul(fmul(V[c], wv), xv));
+      for (int q = 0; q < NC4; ++q) {
+        const float4 a = V4[q];
+        const float V[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (4 * q + e < NC && 4 * q + e >= vs) v[4 * q + e] = fadd(v[4 * q + e], fmul(fmul(V[e], wv), xv));
+      }
     }
   }
   // ---- direction signals: d[c] += (x * M[grid][c]) * win ------------------------------------------------------
@@ -433,13 +447,26 @@ __global__ void __launch_bounds__(kChunk, (NC <= 25) ? 3 : 2)
   for (int n = 0; n < pl.n_dir_e; ++n) {
     const float xv = xc(pl.dir_ch[n]);
     const int win = pl.dir_win[n];
+    const float4* F4 = reinterpret_cast<const float4*>(fine_rows[n]);
     if (win == kWinNone) {
 #pragma unroll
-      for (int c = 0; c < NC; ++c) d[c] = fadd(d[c], fmul(xv, fine_rows[n][c]));
+      for (int q = 0; q < NC4; ++q) {
+        const float4 a = F4[q];
+        const float F[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (4 * q + e < NC) d[4 * q + e] = fadd(d[4 * q + e], fmul(xv, F[e]));
+      }
     } else {
       const float wv = wsel(win);
 #pragma unroll
-      for (int c = 0; c < NC; ++c) d[c] = fadd(d[c], fmul(fmul(xv, fine_rows[n][c]), wv));
+      for (int q = 0; q < NC4; ++q) {
+        const float4 a = F4[q];
+        const float F[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (4 * q + e < NC) d[4 * q + e] = fadd(d[4 * q + e], fmul(fmul(xv, F[e]), wv));
+      }
     }
   }
 
