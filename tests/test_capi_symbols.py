@@ -52,3 +52,11 @@ def test_no_cpu_fallback_without_gpu(so_lib):
     with pytest.raises(MpeghError) as e:
         Lib().create(0)
     assert (e.value.code & 0xFFFFFFFF) == 0xFFFF8001
+
+
+def test_null_handles_are_rejected_without_a_device(so_lib):
+    """Argument checks come before any device work: a NULL renderer / context is MPEGHB200_ERR_BAD_ARG."""
+    c = so_lib.c
+    assert (c.mpeghb200_hoa_renderer_set_tensor_mode(None, 1) & 0xFFFFFFFF) == 0xFFFF8003
+    assert (c.mpeghb200_hoa_render_dev(None, None, None, None, None, 1, None) & 0xFFFFFFFF) == 0xFFFF8003
+    assert c.mpeghb200_hoa_nfc_state_floats(None) == 0
