@@ -131,24 +131,36 @@ mpeghb200_status mpeghb200_fd_submit(mpeghb200_fd_session* s, const float* h_coe
   const size_t per = ((n + n_chunks - 1) / n_chunks + 5) / 6 * 6;  // whole warps for every launch shape in use
   // the slot's previous frame has been waited for by the caller (depth check above), so its downloads are complete
   // and its device buffers are free
-  size_t used = 0;
-  for (size_t a = 0, i = 0; a < n; a += per, ++i) {
-    const size_t cnt = (a + per <= n) ? per : n - a;
-    if (!pin_coef) std::memcpy(sl.p_coef + a * 1024, h_coef + a * 1024, cnt * 4096);
-    MB_CUDA(ctx, cudaMemcpyAsync(sl.d_coef + a * 1024, src_coef + a * 1024, cnt * 4096, cudaMemcpyHostToDevice, s->up));
-    MB_CUDA(ctx, cudaMemcpyAsync(sl.d_side + a, src_side + a, cnt * sizeof(uint32_t), cudaMemcpyHostToDevice, s->up));
-    MB_CUDA(ctx, cudaEventRecord(sl.uploaded[i], s->up));
-    MB_CUDA(ctx, cudaStreamWaitEvent(s->comp, sl.uploaded[i], 0));
-    mpeghb200_status stt = fd_synth_launch(ctx, sl.d_coef + a * 1024, sl.d_side + a, s->d_overlap + a * 1024,
-                                           sl.d_out + a * 1024, int(cnt), s->comp);
-    if (stt != MPEGHB200_OK) return stt;
-    MB_CUDA(ctx, cudaEventRecord(sl.computed[i], s->comp));
-    MB_CUDA(ctx, cudaStreamWaitEvent(s->down, sl.computed[i], 0));
-    MB_CUDA(ctx, cudaMemcpyAsync(dst_out + a * 1024, sl.d_out + a * 1024, cnt * 4096, cudaMemcpyDeviceToHost, s->down));
-    MB_CUDA(ctx, cudaEventRecord(sl.done[i], s->down));
-    used = i + 1;
+  // A failure in the middle of the frame must not leave copies in flight that the caller cannot wait for (earlier
+  // chunks are enqueued already, including downloads into the caller's h_out): drain the three streams, then report.
+  auto enqueue = [&]() -> mpeghb200_status {
+    for (size_t a = 0, i = 0; a < n; a += per, ++i) {
+      const size_t cnt = (a + per <= n) ? per : n - a;
+      if (!pin_coef) std::memcpy(sl.p_coef + a * 1024, h_coef + a * 1024, cnt * 4096);
+      MB_CUDA(ctx, cudaMemcpyAsync(sl.d_coef + a * 1024, src_coef + a * 1024, cnt * 4096, cudaMemcpyHostToDevice, s->up));
+      MB_CUDA(ctx, cudaMemcpyAsync(sl.d_side + a, src_side + a, cnt * sizeof(uint32_t), cudaMemcpyHostToDevice, s->up));
+      MB_CUDA(ctx, cudaEventRecord(sl.uploaded[i], s->up));
+      MB_CUDA(ctx, cudaStreamWaitEvent(s->comp, sl.uploaded[i], 0));
+      mpeghb200_status stt = fd_synth_launch(ctx, sl.d_coef + a * 1024, sl.d_side + a, s->d_overlap + a * 1024,
+                                             sl.d_out + a * 1024, int(cnt), s->comp);
+      if (stt != MPEGHB200_OK) return stt;
+      MB_CUDA(ctx, cudaEventRecord(sl.computed[i], s->comp));
+      MB_CUDA(ctx, cudaStreamWaitEvent(s->down, sl.computed[i], 0));
+      MB_CUDA(ctx, cudaMemcpyAsync(dst_out + a * 1024, sl.d_out + a * 1024, cnt * 4096, cudaMemcpyDeviceToHost, s->down));
+      MB_CUDA(ctx, cudaEventRecord(sl.done[i], s->down));
+      sl.used = i + 1;
+    }
+    return MPEGHB200_OK;
+  };
+  sl.used = 0, sl.per = per;
+  const mpeghb200_status st = enqueue();
+  if (st != MPEGHB200_OK) {
+    cudaStreamSynchronize(s->up), cudaStreamSynchronize(s->comp), cudaStreamSynchronize(s->down);
+    cudaGetLastError();
+    sl.used = 0, sl.in_flight = false;
+    return st;  // the frame was not submitted: n_submitted is unchanged, nothing of it is in flight any more
   }
-  sl.used = used, sl.per = per, sl.in_flight = true;
+  sl.in_flight = true;
   s->n_submitted++;
   return MPEGHB200_OK;
 }

@@ -1006,12 +1006,8 @@ __global__ void __launch_bounds__(128, MPEGHB200_FD_CTAS_PER_SM)
 template <int B, int WARPS, int MIN_BLOCKS>
 static cudaError_t launch_variant(const float* d_coef, const uint32_t* d_side, float* d_overlap, float* d_out,
                                   int n_units, const DeviceTables& T, cudaStream_t stream) {
-  static bool configured = false;  // per template instance; benign race (idempotent attribute)
   auto kern = fd_synth_kernel<B, WARPS, MIN_BLOCKS>;
-  if (!configured) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    configured = true;
-  }
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   const int per_cta = B * WARPS;
   const int grid = (n_units + per_cta - 1) / per_cta;
   kern<<<grid, WARPS * 32, 0, stream>>>(d_coef, d_side, d_overlap, d_out, n_units, T);

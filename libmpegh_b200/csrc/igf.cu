@@ -802,11 +802,8 @@ mpeghb200_status mpeghb200_igf_stereo_dev(mpeghb200_ctx* ctx, const mpeghb200_ba
   MB_CUDA(ctx, cudaSetDevice(ctx->device));
   static const IgfRom R = make_rom();
   constexpr size_t smem = size_t(16) * kFrame * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    MB_CUDA(ctx, cudaFuncSetAttribute(igf_stereo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    configured = true;
-  }
+  // per device / context attribute: set on every call (a process may hold contexts on several GPUs)
+  MB_CUDA(ctx, cudaFuncSetAttribute(igf_stereo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   MB_CUDA(ctx, launch_pdl(igf_stereo_kernel, dim3(n_pairs), dim3(kThreads), smem, static_cast<cudaStream_t>(cuda_stream),
                           d_coef, d_tiles, d_side, d_mask, d_tnf_state, d_seed_out, bands->d_sfb_long, bands->n_long,
                           bands->d_sfb_short, bands->n_short, bands->d_bin2sfb_long, bands->d_bin2sfb_short, R));

@@ -371,11 +371,9 @@ cudaError_t launch_mix(const DevLayout* dl, int NL, const float* d_in, float* d_
                        int n_streams, cudaStream_t st) {
   const int half = (NL + 1) / 2;
   const size_t smem = MixSmem<NOBJ>::bytes(half);
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
+  if (smem > 48 * 1024) {  // per device / context attribute: set on every call
     cudaError_t e = cudaFuncSetAttribute(obj_mix_kernel<NOBJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   return launch_pdl(obj_mix_kernel<NOBJ>, dim3(NL > 1 ? 2 : 1, n_streams), dim3(half * kChunks), smem, st, dl, d_in, d_out,
                     d_scratch, n_obj);

@@ -382,11 +382,9 @@ mpeghb200_status mpeghb200_pcm_pack_dev(mpeghb200_ctx* ctx, const float* d_in, i
   }
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   const size_t smem = size_t(kPackSamples) * n_ch * (pcm_bits >> 3);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(pcm_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    configured = true;
-  }
+  // per device / context attribute: set on every call (a process may hold contexts on several GPUs)
+  if (smem > 48 * 1024)
+    MB_CUDA(ctx, cudaFuncSetAttribute(pcm_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   dim3 grid(kFrame / kPackSamples, n_streams);
   MB_CUDA(ctx, launch_pdl(pcm_pack_kernel, grid, dim3(kPackSamples), smem, st, d_in, d_out, d_delay, d_out_bytes, P));
   ctx->launches.fetch_add(1);

@@ -657,6 +657,9 @@ class FdSession:
         assert coef.shape == (self.n_streams, self.n_ch, FRAME_LEN) and side.shape == (self.n_streams, self.n_ch)
         if out is None:
             out = np.empty_like(coef)
+        # the library writes n_units * 4096 bytes through this pointer: refuse anything that is not exactly that
+        assert isinstance(out, np.ndarray) and out.dtype == np.float32 and out.flags.c_contiguous and \
+            out.flags.writeable and out.shape == coef.shape, "out must be a writable C-contiguous float32 array of coef's shape"
         self.lib.check(self.lib.c.mpeghb200_fd_execute(self.h, coef.ctypes.data, side.ctypes.data, out.ctypes.data))
         return out
 

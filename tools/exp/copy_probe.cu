@@ -59,7 +59,7 @@ int main() {
   run("probe<1,3>", [&](int g) { probe<1, 3><<<U / 3, 32>>>(a[g], b[g], c[g], U); });
   run("probe<2,3>", [&](int g) { probe<2, 3><<<U / 6, 64>>>(a[g], b[g], c[g], U); });
   run("probe<4,2>", [&](int g) { probe<4, 2><<<U / 8, 128>>>(a[g], b[g], c[g], U); });
-  run("memcpyD2D 50MB", [&](int g) { cudaMemcpyAsync(c[g], a[g], size_t(U) * 8192, cudaMemcpyDeviceToDevice); });
-  // the same at 16x the size per launch (one group = 16 x), to see the large-problem ceiling
+  // build on the GPU box: nvcc -arch=sm_100a -cudart shared -O2 -o copy_probe copy_probe.cu (the binary is never committed)
+  run("memcpyD2D 25MB", [&](int g) { cudaMemcpyAsync(c[g], a[g], size_t(U) * 4096, cudaMemcpyDeviceToDevice); });
   return 0;
 }
