@@ -144,6 +144,15 @@ mpeghb200_status mpeghb200_pcm_pack_dev(mpeghb200_ctx *ctx, const float *d_in, i
                                         const int32_t *out_ch_map, int32_t *d_delay, uint8_t *d_out,
                                         int32_t *d_out_bytes, int n_streams, void *cuda_stream);
 
+/* The same for a block of n_samples per channel (a multiple of 256) whose channels lie ch_stride floats apart:
+ * d_in [stream][n_ch][ch_stride].  The binaural renderer hands over fft_size/2 samples per channel at a time
+ * (num_samples_processed, decoder/ia_core_coder_decode_main.c:2839-2856) and the reference packs them with one
+ * ia_core_coder_samples_sat call.  mpeghb200_pcm_pack_dev = n_samples 1024, ch_stride 1024. */
+mpeghb200_status mpeghb200_pcm_pack_block_dev(mpeghb200_ctx *ctx, const float *d_in, int n_ch, int n_samples,
+                                              int ch_stride, int pcm_bits, const int32_t *out_ch_map,
+                                              int32_t *d_delay, uint8_t *d_out, int32_t *d_out_bytes, int n_streams,
+                                              void *cuda_stream);
+
 /* ---- object renderer: VBAP gains + ramped mix ------------------------------------------------------
  * Replaces impeghd_obj_renderer_dec (decoder/impeghd_obj_ren_dec.c:1319) and everything below
  * impegh_obj_ren_vbap_process (decoder/impeghd_obj_ren_vbap.c:485) for OAM frame length 1024.
@@ -169,6 +178,7 @@ typedef struct mpeghb200_obj_layout mpeghb200_obj_layout;
 mpeghb200_status mpeghb200_obj_layout_create(mpeghb200_ctx *ctx, const mpeghb200_obj_layout_desc *desc,
                                              mpeghb200_obj_layout **out);
 void mpeghb200_obj_layout_destroy(mpeghb200_obj_layout *layout);
+int mpeghb200_obj_layout_num_speakers(const mpeghb200_obj_layout *layout); /* n_spk */
 
 /* Per object and frame: the OAM decoder's descaled metadata after the host-side trigonometry (the reference
  * evaluates sin/cos/tan in double-precision libm, decoder/impeghd_3d_vec_basic_ops.c:86 and
@@ -220,6 +230,8 @@ mpeghb200_status mpeghb200_hoa_renderer_create(mpeghb200_ctx *ctx, const float *
                                                const float *nfc_coeffs, int clip, mpeghb200_hoa_renderer **out);
 void mpeghb200_hoa_renderer_destroy(mpeghb200_hoa_renderer *r);
 size_t mpeghb200_hoa_nfc_state_floats(const mpeghb200_hoa_renderer *r);
+int mpeghb200_hoa_renderer_num_out(const mpeghb200_hoa_renderer *r);
+int mpeghb200_hoa_renderer_num_coeffs(const mpeghb200_hoa_renderer *r);
 /* Opt-in throughput mode for the one dense contraction of the path (out = M x, impeghd_hoa_renderer.c:231-253):
  * on != 0 applies the render matrix on the tensor cores (TF32 mma with the 3xTF32 operand split, fp32
  * accumulation) instead of the reference's left-to-right fp32 sum.  Results are then no longer bit-identical but
@@ -257,6 +269,7 @@ mpeghb200_status mpeghb200_binaural_create(mpeghb200_ctx *ctx, int n_in, int len
                                            const float *inv_diffuse_weight, mpeghb200_binaural **out);
 void mpeghb200_binaural_destroy(mpeghb200_binaural *b);
 int mpeghb200_binaural_block_len(const mpeghb200_binaural *b);
+int mpeghb200_binaural_num_in(const mpeghb200_binaural *b);
 size_t mpeghb200_binaural_state_floats(const mpeghb200_binaural *b);
 /* Host copies of the prepared filter spectra in the reference's packed format (taps_direct / taps_diffuse of
  * ia_binaural_ren_pers_mem_str): h_direct [set][2][n_in][N], h_diffuse [set][n_diffuse_blocks][2][N]; either
@@ -326,6 +339,7 @@ mpeghb200_status mpeghb200_hoa_spatial_create(mpeghb200_ctx *ctx, const mpeghb20
                                               mpeghb200_hoa_spatial **out);
 void mpeghb200_hoa_spatial_destroy(mpeghb200_hoa_spatial *h);
 int mpeghb200_hoa_spatial_num_coeffs(const mpeghb200_hoa_spatial *h);
+int mpeghb200_hoa_spatial_num_transport(const mpeghb200_hoa_spatial *h);
 /* Per-stream device state (what ia_spatial_dec_str carries between frames + per-frame scratch), in bytes. */
 size_t mpeghb200_hoa_spatial_state_bytes(const mpeghb200_hoa_spatial *h);
 mpeghb200_status mpeghb200_hoa_spatial_state_init_dev(mpeghb200_ctx *ctx, const mpeghb200_hoa_spatial *h,
@@ -350,6 +364,8 @@ mpeghb200_status mpeghb200_format_conv_create(mpeghb200_ctx *ctx, int n_in, int 
                                               mpeghb200_format_conv **out);
 void mpeghb200_format_conv_destroy(mpeghb200_format_conv *h);
 size_t mpeghb200_format_conv_state_floats(const mpeghb200_format_conv *h);
+int mpeghb200_format_conv_num_in(const mpeghb200_format_conv *h);
+int mpeghb200_format_conv_num_out(const mpeghb200_format_conv *h);
 mpeghb200_status mpeghb200_format_conv_dev(mpeghb200_ctx *ctx, const mpeghb200_format_conv *h, const float *d_in,
                                            float *d_out, float *d_state, int n_streams, void *cuda_stream);
 
@@ -612,6 +628,84 @@ size_t mpeghb200_resampler_state_floats(const mpeghb200_resampler *r);
 int mpeghb200_resampler_out_len(const mpeghb200_resampler *r);
 mpeghb200_status mpeghb200_resample_dev(mpeghb200_ctx *ctx, const mpeghb200_resampler *r, const float *d_in,
                                         float *d_out, float *d_state, int n_units, void *cuda_stream);
+
+/* ---- chains: one BASELINE.json configuration end to end behind one host-buffer call --------------------------
+ * A chain owns everything one configuration of the post-parse path needs for n_streams streams on one GPU -- the
+ * per-stream state of every stage, device-resident intermediates, two frame slots of input / output staging and
+ * three CUDA streams (upload, compute, download) -- and runs the stages in the reference's order
+ * (decoder/ia_core_coder_decode_main.c:2736-2893, ia_core_coder_dec_ext_ele_proc :1949-2316):
+ *
+ *   core channels (dequantised spectra + FD side words -> FD synthesis, or time signals as they are)
+ *     = bed channels | object signals | HOA transport channels        (ia_signals_3d: num_ch, num_audio_obj,
+ *                                                                       num_hoa_transport_ch)
+ *   objects  -> VBAP gains + ramped mix into the layout (:2166-2216)     mpeghb200_obj_render_dev
+ *   HOA      -> spatial decode -> NFC + render matrix (:2217-2302)       mpeghb200_hoa_spatial_dev, _hoa_render_dev
+ *   bus adds bed + objects + HOA (ia_add_flt loops :2185-2302)           mpeghb200_bus_add_dev
+ *   format converter on the mix (:2752-2766)                             mpeghb200_format_conv_dev
+ *   binaural renderer (:2826-2860), a block every fft_size/2 samples     mpeghb200_binaural_block_dev
+ *   loudness gain + peak limiter (:2861-2867, impegh_dec_ln_pl_process)  mpeghb200_limiter_dev
+ *   PCM packer (:2895, ia_core_coder_samples_sat)                        mpeghb200_pcm_pack_dev
+ *
+ * With the binaural renderer on, the reference's limiter runs over time_sample_vector[0..1] while the packer reads
+ * ptr_binaural_output (:2861 vs :2895), i.e. it never touches the binaural signal; the chain therefore packs the
+ * renderer's output directly, like the reference does in effect.
+ *
+ * Only what has to cross the host link does: the core channels and the per-frame side records go up, packed PCM
+ * comes down (2, 3 or 4 bytes per output sample instead of 4 per intermediate sample of every stage).
+ *
+ * Host buffer layout of one frame (n_frames of them back to back in one submit):
+ *   core     [n_bed_ch + n_obj + n_hoa_transport regions][stream][channel of the region][1024] float
+ *            (region-major: all streams' bed channels, then all streams' object signals, then HOA transport)
+ *   fd_side  the same arrangement, one MPEGHB200_FD_SIDE word per channel (core_is_spectra only)
+ *   obj_side [stream][n_obj] mpeghb200_obj_side, hoa_side [stream] mpeghb200_hoa_spatial_side
+ *   pcm      [stream][pcm_bytes_per_frame]; pcm_bytes [stream] valid bytes (start-up delay trimming), or NULL.
+ *            With the binaural renderer: one PCM record per completed block, [stream][block_len * 2 * bytes]. */
+typedef struct mpeghb200_chain mpeghb200_chain;
+typedef struct mpeghb200_chain_desc {
+  int32_t n_streams;
+  int32_t core_is_spectra; /* 1: FD synthesis in front (spectra + side words); 0: time-domain core channels */
+  int32_t n_bed_ch, n_obj, n_hoa_transport;
+  int32_t pcm_bits;        /* 16, 24, 32 */
+  int32_t limiter;         /* 0: no limiter stage, 1: limiter on, 2: stage present with limiter_on = 0 (pure delay) */
+  int32_t start_delay;     /* delay_in_samples of every stream at start (the reference trims the limiter's 240) */
+  float loudness_gain;     /* (float)pow(10, dB / 20) from the host, 1.0f = off (decode_main.c:1533-1544) */
+  int32_t max_frames_per_call; /* frames one submit may carry (sizes the two staging slots); 0 = one PCM record */
+  const mpeghb200_obj_layout *obj_layout;     /* n_obj > 0 */
+  const mpeghb200_hoa_spatial *hoa_spatial;   /* n_hoa_transport > 0 */
+  const mpeghb200_hoa_renderer *hoa_renderer; /* n_hoa_transport > 0 */
+  const mpeghb200_format_conv *format_conv;   /* or NULL */
+  const mpeghb200_binaural *binaural;         /* or NULL */
+  const int32_t *out_ch_map;                  /* as mpeghb200_pcm_pack_dev, or NULL */
+  const int32_t *binaural_set_of_stream;      /* HOST [n_streams]: BRIR filter set per stream, or NULL (set 0) */
+} mpeghb200_chain_desc;
+typedef struct mpeghb200_chain_frame {
+  const float *core;
+  const uint32_t *fd_side;
+  const mpeghb200_obj_side *obj_side;
+  const mpeghb200_hoa_spatial_side *hoa_side;
+  uint8_t *pcm;
+  int32_t *pcm_bytes;
+} mpeghb200_chain_frame;
+mpeghb200_status mpeghb200_chain_open(mpeghb200_ctx *ctx, const mpeghb200_chain_desc *desc, mpeghb200_chain **out);
+void mpeghb200_chain_close(mpeghb200_chain *c);
+int mpeghb200_chain_out_channels(const mpeghb200_chain *c);
+/* floats of one frame's core buffer; bytes of one PCM record per stream (a frame, or a binaural block) */
+size_t mpeghb200_chain_core_floats(const mpeghb200_chain *c);
+size_t mpeghb200_chain_pcm_record_bytes(const mpeghb200_chain *c);
+int mpeghb200_chain_frames_per_record(const mpeghb200_chain *c); /* 1, or block_len / 1024 with the binaural renderer */
+/* HOST buffers, n_frames (1..max_frames_per_call <= MPEGHB200_CHAIN_MAX_FRAMES) consecutive frames per call; with the binaural renderer
+ * n_frames must be a multiple of frames_per_record.  submit enqueues and returns; wait blocks until the OLDEST
+ * submitted call is complete (its pcm / pcm_bytes filled).  At most two calls in flight: the download of one
+ * overlaps the upload of the next.  Page-locked host buffers (mpeghb200_host_alloc) are DMA'd in place.
+ * execute = drain, submit, wait. */
+#define MPEGHB200_CHAIN_MAX_FRAMES 8
+mpeghb200_status mpeghb200_chain_submit(mpeghb200_chain *c, const mpeghb200_chain_frame *host, int n_frames);
+mpeghb200_status mpeghb200_chain_wait(mpeghb200_chain *c);
+mpeghb200_status mpeghb200_chain_execute(mpeghb200_chain *c, const mpeghb200_chain_frame *host, int n_frames);
+/* The same stages on DEVICE buffers of the caller (same layouts, n_frames frames), on the caller's stream, without
+ * copies: what bench.py times with the inputs already resident in HBM. */
+mpeghb200_status mpeghb200_chain_run_dev(mpeghb200_chain *c, const mpeghb200_chain_frame *dev, int n_frames,
+                                         void *cuda_stream);
 
 #ifdef __cplusplus
 }

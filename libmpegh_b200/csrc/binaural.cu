@@ -427,6 +427,7 @@ void mpeghb200_binaural_destroy(mpeghb200_binaural* b) {
 }
 
 int mpeghb200_binaural_block_len(const mpeghb200_binaural* b) { return b ? b->N / 2 : 0; }
+int mpeghb200_binaural_num_in(const mpeghb200_binaural* b) { return b ? b->n_in : 0; }
 
 size_t mpeghb200_binaural_state_floats(const mpeghb200_binaural* b) {
   if (!b) return 0;

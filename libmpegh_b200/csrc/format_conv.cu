@@ -366,6 +366,9 @@ void mpeghb200_format_conv_destroy(mpeghb200_format_conv* h) {
   delete h;
 }
 
+int mpeghb200_format_conv_num_in(const mpeghb200_format_conv* h) { return h ? h->n_in : 0; }
+int mpeghb200_format_conv_num_out(const mpeghb200_format_conv* h) { return h ? h->n_out : 0; }
+
 size_t mpeghb200_format_conv_state_floats(const mpeghb200_format_conv* h) {
   return h ? size_t(h->n_in) * 256 + size_t(h->n_out) * (256 + 2 * kErb) : 0;
 }

@@ -623,6 +623,8 @@ mpeghb200_status mpeghb200_hoa_renderer_set_tensor_mode(mpeghb200_hoa_renderer* 
 }
 
 size_t mpeghb200_hoa_nfc_state_floats(const mpeghb200_hoa_renderer* r) { return r ? size_t(r->P.n_coef) * 14 : 0; }
+int mpeghb200_hoa_renderer_num_out(const mpeghb200_hoa_renderer* r) { return r ? r->P.n_out : 0; }
+int mpeghb200_hoa_renderer_num_coeffs(const mpeghb200_hoa_renderer* r) { return r ? r->P.n_coef : 0; }
 
 mpeghb200_status mpeghb200_hoa_render_dev(mpeghb200_ctx* ctx, const mpeghb200_hoa_renderer* r, const float* d_in,
                                           float* d_out, float* d_nfc_state, int n_streams, void* cuda_stream) {

@@ -631,6 +631,7 @@ void mpeghb200_hoa_spatial_destroy(mpeghb200_hoa_spatial* h) {
 
 size_t mpeghb200_hoa_spatial_state_bytes(const mpeghb200_hoa_spatial* h) { return h ? sizeof(Slot) : 0; }
 int mpeghb200_hoa_spatial_num_coeffs(const mpeghb200_hoa_spatial* h) { return h ? h->cfg.n_coef : 0; }
+int mpeghb200_hoa_spatial_num_transport(const mpeghb200_hoa_spatial* h) { return h ? h->cfg.n_transport : 0; }
 
 mpeghb200_status mpeghb200_hoa_spatial_state_init_dev(mpeghb200_ctx* ctx, const mpeghb200_hoa_spatial* h,
                                                       void* d_state, int n_streams, void* cuda_stream) {

@@ -475,6 +475,8 @@ mpeghb200_status mpeghb200_obj_layout_create(mpeghb200_ctx* ctx, const mpeghb200
   return MPEGHB200_OK;
 }
 
+int mpeghb200_obj_layout_num_speakers(const mpeghb200_obj_layout* L) { return L ? L->host.n_spk : 0; }
+
 void mpeghb200_obj_layout_destroy(mpeghb200_obj_layout* L) {
   if (!L) return;
   cudaSetDevice(L->ctx->device);

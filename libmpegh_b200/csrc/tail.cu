@@ -208,6 +208,7 @@ __global__ void limiter_state_init_kernel(float* state, int stride, int n_stream
 constexpr int kPackSamples = 256;  // samples per CTA
 struct PackParams {
   int n_ch, bits;
+  int n_samples, ch_stride;  // samples per channel in this call (a multiple of kPackSamples); floats between channels
   unsigned char pos[64];  // planar channel feeding interleave slot ch (the reference's channel_pos[])
 };
 
@@ -225,8 +226,8 @@ __global__ void __launch_bounds__(kPackSamples)
   const int tid = threadIdx.x;
   const int chunk = blockIdx.x, sidx = blockIdx.y;
   const int bps = P.bits >> 3;
-  const int frame_bytes = kFrame * P.n_ch * bps;
-  const float* x = in + size_t(sidx) * P.n_ch * kFrame;
+  const int frame_bytes = P.n_samples * P.n_ch * bps;
+  const float* x = in + size_t(sidx) * P.n_ch * P.ch_stride;
   const int d = delay ? delay[sidx] : 0;
   const int s = chunk * kPackSamples + tid;
   constexpr int kBatch = 8;
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(kPackSamples)
     float vin[kBatch];  // eight channel loads in flight before the first conversion
 #pragma unroll
     for (int q = 0; q < kBatch; ++q)
-      vin[q] = (ch0 + q < P.n_ch) ? __ldcs(x + size_t(P.pos[ch0 + q]) * kFrame + s) : 0.0f;
+      vin[q] = (ch0 + q < P.n_ch) ? __ldcs(x + size_t(P.pos[ch0 + q]) * P.ch_stride + s) : 0.0f;
 #pragma unroll
     for (int q = 0; q < kBatch; ++q) {
       const int ch = ch0 + q;
@@ -283,16 +284,16 @@ __global__ void __launch_bounds__(kPackSamples)
     }
   }
   if (chunk == 0 && tid == 0) {
-    if (out_bytes) out_bytes[sidx] = (d <= kFrame) ? (kFrame - d) * P.n_ch * bps : 0;
+    if (out_bytes) out_bytes[sidx] = (d <= P.n_samples) ? (P.n_samples - d) * P.n_ch * bps : 0;
   }
 }
 
 // the delay state is advanced by a separate tiny kernel so that every chunk CTA of a stream sees the old value
-__global__ void pcm_delay_advance_kernel(int* delay, int n_streams) {
+__global__ void pcm_delay_advance_kernel(int* delay, int n_streams, int n_samples) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_streams) {
     const int d = delay[i];
-    delay[i] = (d <= kFrame) ? 0 : d - kFrame;
+    delay[i] = (d <= n_samples) ? 0 : d - n_samples;
   }
 }
 
@@ -362,7 +363,17 @@ mpeghb200_status mpeghb200_limiter_dev(mpeghb200_ctx* ctx, const mpeghb200_limit
 mpeghb200_status mpeghb200_pcm_pack_dev(mpeghb200_ctx* ctx, const float* d_in, int n_ch, int pcm_bits,
                                         const int32_t* out_ch_map, int32_t* d_delay, uint8_t* d_out,
                                         int32_t* d_out_bytes, int n_streams, void* cuda_stream) {
+  return mpeghb200_pcm_pack_block_dev(ctx, d_in, n_ch, kFrame, kFrame, pcm_bits, out_ch_map, d_delay, d_out, d_out_bytes,
+                                      n_streams, cuda_stream);
+}
+
+mpeghb200_status mpeghb200_pcm_pack_block_dev(mpeghb200_ctx* ctx, const float* d_in, int n_ch, int n_samples,
+                                              int ch_stride, int pcm_bits, const int32_t* out_ch_map,
+                                              int32_t* d_delay, uint8_t* d_out, int32_t* d_out_bytes, int n_streams,
+                                              void* cuda_stream) {
   if (!ctx) return MPEGHB200_ERR_BAD_ARG;
+  if (n_samples <= 0 || n_samples % kPackSamples || ch_stride < n_samples)
+    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "pcm_pack_block_dev: n_samples must be a positive multiple of 256, ch_stride >= n_samples");
   if (n_ch <= 0 || n_ch > 64 || (pcm_bits != 16 && pcm_bits != 24 && pcm_bits != 32) || n_streams < 0 ||
       (n_streams > 0 && (!d_in || !d_out)))
     return fail(ctx, MPEGHB200_ERR_BAD_ARG, "pcm_pack_dev: bad channel count, sample size or buffer");
@@ -371,6 +382,8 @@ mpeghb200_status mpeghb200_pcm_pack_dev(mpeghb200_ctx* ctx, const float* d_in, i
   PackParams P;
   P.n_ch = n_ch;
   P.bits = pcm_bits;
+  P.n_samples = n_samples;
+  P.ch_stride = ch_stride;
   // decoder/ia_core_coder_decode_main.c:231-236: channel_pos[out_ch_map[ch]] = ch, -1 meaning identity
   for (int ch = 0; ch < 64; ++ch) P.pos[ch] = static_cast<unsigned char>(ch < n_ch ? ch : 0);
   if (out_ch_map) {
@@ -385,12 +398,12 @@ mpeghb200_status mpeghb200_pcm_pack_dev(mpeghb200_ctx* ctx, const float* d_in, i
   // per device / context attribute: set on every call (a process may hold contexts on several GPUs)
   if (smem > 48 * 1024)
     MB_CUDA(ctx, cudaFuncSetAttribute(pcm_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-  dim3 grid(kFrame / kPackSamples, n_streams);
+  dim3 grid(n_samples / kPackSamples, n_streams);
   MB_CUDA(ctx, launch_pdl(pcm_pack_kernel, grid, dim3(kPackSamples), smem, st, d_in, d_out, d_delay, d_out_bytes, P));
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   if (d_delay) {
-    pcm_delay_advance_kernel<<<(n_streams + 255) / 256, 256, 0, st>>>(d_delay, n_streams);
+    pcm_delay_advance_kernel<<<(n_streams + 255) / 256, 256, 0, st>>>(d_delay, n_streams, n_samples);
     ctx->launches.fetch_add(1);
     MB_CUDA(ctx, cudaGetLastError());
   }

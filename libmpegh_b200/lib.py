@@ -78,6 +78,20 @@ class HoaSpatialDesc(ctypes.Structure):
                                                "fade_windows", "dyn_win_pow_table", "dyn_win_func", "pow2_table")]
 
 
+class ChainDesc(ctypes.Structure):
+    """mpeghb200_chain_desc"""
+    _fields_ = [(n, ctypes.c_int32) for n in ("n_streams", "core_is_spectra", "n_bed_ch", "n_obj", "n_hoa_transport",
+                                              "pcm_bits", "limiter", "start_delay")] + \
+               [("loudness_gain", ctypes.c_float), ("max_frames_per_call", ctypes.c_int32)] + \
+               [(n, ctypes.c_void_p) for n in ("obj_layout", "hoa_spatial", "hoa_renderer", "format_conv", "binaural",
+                                               "out_ch_map", "binaural_set_of_stream")]
+
+
+class ChainFrame(ctypes.Structure):
+    """mpeghb200_chain_frame (host or device pointers)"""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("core", "fd_side", "obj_side", "hoa_side", "pcm", "pcm_bytes")]
+
+
 LTPF_SIDE_DTYPE = np.dtype([("unit", "<i4"), ("pitch_lag_idx", "<u2"), ("data_present", "u1"), ("gain_idx", "u1")])
 DRC_SB_CHANNEL_DTYPE = np.dtype([("first_seq", np.int32), ("band_count", np.int32), ("weight_row", np.int32),
                                  ("reserved", np.int32)])
@@ -275,6 +289,30 @@ class Lib:
         c.mpeghb200_stereo_save_dev.restype = i32
         c.mpeghb200_stereo_mdst_rom.argtypes = [vp, vp]
         c.mpeghb200_stereo_mdst_rom.restype = None
+        c.mpeghb200_pcm_pack_block_dev.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp,
+                                                   vp, vp, ctypes.c_int, vp]
+        c.mpeghb200_pcm_pack_block_dev.restype = i32
+        for name in ("obj_layout_num_speakers", "hoa_renderer_num_out", "hoa_renderer_num_coeffs", "binaural_num_in",
+                     "hoa_spatial_num_transport", "format_conv_num_in", "format_conv_num_out", "chain_out_channels",
+                     "chain_frames_per_record"):
+            f = getattr(c, "mpeghb200_" + name)
+            f.argtypes, f.restype = [vp], ctypes.c_int
+        c.mpeghb200_chain_open.argtypes = [vp, ctypes.POINTER(ChainDesc), ctypes.POINTER(vp)]
+        c.mpeghb200_chain_open.restype = i32
+        c.mpeghb200_chain_close.argtypes = [vp]
+        c.mpeghb200_chain_close.restype = None
+        c.mpeghb200_chain_core_floats.argtypes = [vp]
+        c.mpeghb200_chain_core_floats.restype = sz
+        c.mpeghb200_chain_pcm_record_bytes.argtypes = [vp]
+        c.mpeghb200_chain_pcm_record_bytes.restype = sz
+        c.mpeghb200_chain_submit.argtypes = [vp, ctypes.POINTER(ChainFrame), ctypes.c_int]
+        c.mpeghb200_chain_submit.restype = i32
+        c.mpeghb200_chain_wait.argtypes = [vp]
+        c.mpeghb200_chain_wait.restype = i32
+        c.mpeghb200_chain_execute.argtypes = [vp, ctypes.POINTER(ChainFrame), ctypes.c_int]
+        c.mpeghb200_chain_execute.restype = i32
+        c.mpeghb200_chain_run_dev.argtypes = [vp, ctypes.POINTER(ChainFrame), ctypes.c_int, vp]
+        c.mpeghb200_chain_run_dev.restype = i32
         self.ctx = None
 
     # ---- context ------------------------------------------------------------------------------
@@ -636,6 +674,17 @@ class Lib:
         self.check(self.c.mpeghb200_limiter_dev(self.ctx, ctypes.byref(p), d_in, d_out, d_state, d_gain, n_streams,
                                                 stream))
 
+    def chain_open(self, n_streams, **kw):
+        """kw: the fields of mpeghb200_chain_desc (handles as returned by the *_create wrappers)."""
+        return Chain(self, n_streams, **kw)
+
+    def pcm_pack_block_dev(self, d_in, n_ch, n_samples, ch_stride, bits, d_out, n_streams, ch_map=None, d_delay=None,
+                           d_out_bytes=None, stream=0):
+        m = None if ch_map is None else np.ascontiguousarray(ch_map, dtype=np.int32)
+        self.check(self.c.mpeghb200_pcm_pack_block_dev(self.ctx, d_in, n_ch, n_samples, ch_stride, bits,
+                                                       None if m is None else m.ctypes.data, d_delay, d_out,
+                                                       d_out_bytes, n_streams, stream))
+
     def pcm_pack_dev(self, d_in, n_ch, bits, d_out, n_streams, ch_map=None, d_delay=None, d_out_bytes=None, stream=0):
         m = None if ch_map is None else np.ascontiguousarray(ch_map, dtype=np.int32)
         self.check(self.c.mpeghb200_pcm_pack_dev(self.ctx, d_in, n_ch, bits, None if m is None else m.ctypes.data,
@@ -679,6 +728,82 @@ class FdSession:
     def close(self):
         if self.h:
             self.lib.c.mpeghb200_fd_close(self.h)
+            self.h = None
+
+
+class Chain:
+    """mpeghb200_chain_*: one configuration end to end; host buffers in, packed PCM out."""
+
+    def __init__(self, lib, n_streams, core_is_spectra=0, n_bed_ch=0, n_obj=0, n_hoa_transport=0, pcm_bits=24,
+                 limiter=1, start_delay=0, loudness_gain=1.0, obj_layout=None, hoa_spatial=None, hoa_renderer=None,
+                 format_conv=None, binaural=None, out_ch_map=None, binaural_set_of_stream=None,
+                 max_frames_per_call=0):
+        self.lib = lib
+        d = ChainDesc()
+        d.n_streams, d.core_is_spectra, d.n_bed_ch, d.n_obj, d.n_hoa_transport = n_streams, core_is_spectra, n_bed_ch, \
+            n_obj, n_hoa_transport
+        d.pcm_bits, d.limiter, d.start_delay, d.loudness_gain = pcm_bits, limiter, start_delay, loudness_gain
+        d.max_frames_per_call = max_frames_per_call
+        for name, h in (("obj_layout", obj_layout), ("hoa_spatial", hoa_spatial), ("hoa_renderer", hoa_renderer),
+                        ("format_conv", format_conv), ("binaural", binaural)):
+            setattr(d, name, h.value if isinstance(h, ctypes.c_void_p) else h)
+        keep = []
+        for name, a in (("out_ch_map", out_ch_map), ("binaural_set_of_stream", binaural_set_of_stream)):
+            if a is not None:
+                a = np.ascontiguousarray(a, np.int32)
+                keep.append(a)
+                setattr(d, name, a.ctypes.data)
+        h = ctypes.c_void_p()
+        lib.check(lib.c.mpeghb200_chain_open(lib.ctx, ctypes.byref(d), ctypes.byref(h)))
+        self.h, self.desc = h, d
+        self.n_streams = n_streams
+        self.n_core = n_bed_ch + n_obj + n_hoa_transport
+        self.n_out = lib.c.mpeghb200_chain_out_channels(h)
+        self.frames_per_record = lib.c.mpeghb200_chain_frames_per_record(h)
+        self.core_floats = int(lib.c.mpeghb200_chain_core_floats(h))
+        self.record_bytes = int(lib.c.mpeghb200_chain_pcm_record_bytes(h))
+
+    @staticmethod
+    def _ptr(a):
+        if a is None:
+            return None
+        if isinstance(a, np.ndarray):
+            assert a.flags.c_contiguous
+            return a.ctypes.data
+        return int(a)  # raw pointer (pinned torch tensor .data_ptr(), device pointer)
+
+    def frame(self, core, fd_side=None, obj_side=None, hoa_side=None, pcm=None, pcm_bytes=None):
+        f = ChainFrame()
+        f.core, f.fd_side, f.obj_side, f.hoa_side = self._ptr(core), self._ptr(fd_side), self._ptr(obj_side), \
+            self._ptr(hoa_side)
+        f.pcm, f.pcm_bytes = self._ptr(pcm), self._ptr(pcm_bytes)
+        return f
+
+    def alloc_out(self, n_frames=1):
+        n_rec = n_frames // self.frames_per_record
+        return (np.zeros((n_rec, self.n_streams, self.record_bytes), np.uint8),
+                np.zeros((n_rec, self.n_streams), np.int32))
+
+    def execute(self, n_frames=1, **kw):
+        """numpy host arrays (keyword names as in frame()); returns (pcm [records, streams, record_bytes], bytes)."""
+        if kw.get("pcm") is None:
+            kw["pcm"], kw["pcm_bytes"] = self.alloc_out(n_frames)
+        f = self.frame(**kw)
+        self.lib.check(self.lib.c.mpeghb200_chain_execute(self.h, ctypes.byref(f), n_frames))
+        return kw["pcm"], kw["pcm_bytes"]
+
+    def submit(self, frame, n_frames=1):
+        self.lib.check(self.lib.c.mpeghb200_chain_submit(self.h, ctypes.byref(frame), n_frames))
+
+    def wait(self):
+        self.lib.check(self.lib.c.mpeghb200_chain_wait(self.h))
+
+    def run_dev(self, frame, n_frames=1, stream=0):
+        self.lib.check(self.lib.c.mpeghb200_chain_run_dev(self.h, ctypes.byref(frame), n_frames, stream))
+
+    def close(self):
+        if self.h:
+            self.lib.c.mpeghb200_chain_close(self.h)
             self.h = None
 
 

@@ -407,8 +407,90 @@ def load_ref_ns():
     lib.ref_drctd_destroy.argtypes = [ctypes.c_void_p]
     lib.ref_drctd_process.argtypes = [ctypes.c_void_p, _f32p, _f32p]
     lib.ref_drctd_process.restype = ctypes.c_int
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    lib.ref_chain_create_fd.restype = vp
+    lib.ref_chain_create_fd.argtypes = [ci] * 6
+    lib.ref_chain_create_hoa.restype = vp
+    lib.ref_chain_create_hoa.argtypes = [ci, _i32q, ci, ci, ci, ctypes.c_float, ci, ci, ci, ctypes.POINTER(ci)]
+    lib.ref_chain_create_obj.restype = vp
+    lib.ref_chain_create_obj.argtypes = [ci] * 7 + [ctypes.POINTER(ci)]
+    lib.ref_chain_create_bin.restype = vp
+    lib.ref_chain_create_bin.argtypes = [ci] * 5 + [vp] * 6 + [ci, ci, ci, ctypes.POINTER(ci)]
+    lib.ref_chain_set_out.argtypes = [vp, ci, ci]
+    lib.ref_chain_stream_handle.restype = vp
+    lib.ref_chain_stream_handle.argtypes = [vp, ci, ci]
+    for n in ("ref_chain_threads", "ref_chain_rec_bytes", "ref_chain_frames_per_record"):
+        getattr(lib, n).argtypes = [vp]
+    lib.ref_chain_run.restype = ctypes.c_double
+    lib.ref_chain_run.argtypes = [vp, vp, vp, ci, vp, vp]
+    lib.ref_chain_destroy.argtypes = [vp]
+    lib.ref_hoa_ren_matrix.argtypes = [vp, _i32q, _f32p]
     _ref_ns = lib
     return lib
+
+
+class RefChain:
+    """oracle/ref_chain.c: the unmodified reference's stage functions chained per configuration over S streams on a
+    pool of pinned worker threads.  kind: "fd", "hoa", "bin", "obj"."""
+
+    def __init__(self, kind, S, n_threads=1, pcm_bits=24, start_delay=0, **kw):
+        self.ns = load_ref_ns()
+        assert self.ns is not None, "oracle/_ref/libmpeghref_ns.so not built"
+        err = ctypes.c_int(0)
+        self.kind, self.S = kind, S
+        if kind == "fd":
+            self.n_in = kw["n_ch"]
+            self.h = self.ns.ref_chain_create_fd(S, self.n_in, int(kw.get("tail", 1)), pcm_bits, start_delay, n_threads)
+        elif kind == "hoa":
+            cfg = np.array(list(kw["cfg"]) + [0, 0], np.int32)
+            cicp, order, lfe, radius = kw["ren"]
+            self.n_in = int(cfg[1])
+            self.h = self.ns.ref_chain_create_hoa(S, cfg, kw["side_bytes"], cicp, lfe, radius, pcm_bits, start_delay,
+                                                  n_threads, ctypes.byref(err))
+            info, m = np.zeros(4, np.int32), np.zeros(64 * 64, np.float32)
+            self.ns.ref_hoa_ren_matrix(self.ns.ref_chain_stream_handle(self.h, 0, 1), info, m)
+            self.n_out = int(info[0])
+            assert self.ns.ref_chain_set_out(self.h, self.n_out, n_threads) == 0
+        elif kind == "obj":
+            self.n_in = kw["n_obj"]
+            self.h = self.ns.ref_chain_create_obj(S, self.n_in, kw["cicp"], kw["n_spk"], pcm_bits, start_delay,
+                                                  n_threads, ctypes.byref(err))
+        elif kind == "bin":
+            f = kw["filters"]  # list of dicts (sets)
+            self._keep = [np.ascontiguousarray(np.stack([d[k] for d in f]), np.float32)
+                          for k in ("taps_direct", "taps_diffuse", "direct_fc", "diffuse_fc", "weight")]
+            td = self._keep[0]
+            self.n_in = td.shape[2]
+            sets = kw.get("sets")
+            self._sets = None if sets is None else np.ascontiguousarray(sets, np.int32)
+            self.h = self.ns.ref_chain_create_bin(S, self.n_in, td.shape[3], self._keep[1].shape[1], td.shape[0],
+                                                  None if self._sets is None else self._sets.ctypes.data,
+                                                  *[a.ctypes.data for a in self._keep], pcm_bits, start_delay,
+                                                  n_threads, ctypes.byref(err))
+        else:
+            raise ValueError(kind)
+        assert self.h and err.value == 0, (kind, hex(err.value & 0xFFFFFFFF))
+        self.rec_bytes = self.ns.ref_chain_rec_bytes(self.h)
+        self.fpr = self.ns.ref_chain_frames_per_record(self.h)
+        self.n_threads = self.ns.ref_chain_threads(self.h)
+
+    def run(self, x, side=None, want_pcm=True):
+        """x [F, S, n_in, 1024]; side [F, S, ...] or None -> (seconds, pcm [F/fpr, S, rec_bytes], bytes [F/fpr, S])"""
+        x = np.ascontiguousarray(x, np.float32)
+        F = x.shape[0]
+        assert x.shape[1:] == (self.S, self.n_in, 1024), x.shape
+        side = None if side is None else np.ascontiguousarray(side)
+        pcm = np.zeros((F // self.fpr, self.S, self.rec_bytes), np.uint8) if want_pcm else None
+        nb = np.zeros((F // self.fpr, self.S), np.int32) if want_pcm else None
+        t = self.ns.ref_chain_run(self.h, x.ctypes.data, None if side is None else side.ctypes.data, F,
+                                  None if pcm is None else pcm.ctypes.data, None if nb is None else nb.ctypes.data)
+        assert t >= 0, "reference stage reported an error"
+        return t, pcm, nb
+
+    def close(self):
+        if self.h:
+            self.ns.ref_chain_destroy(self.h)
+            self.h = None
 
 
 def bits_equal(a, b):
