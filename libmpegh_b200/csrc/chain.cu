@@ -276,7 +276,16 @@ mpeghb200_status mpeghb200_chain_open(mpeghb200_ctx* ctx, const mpeghb200_chain_
     e = dalloc(c, &c->d_obj_state, S * mpeghb200_obj_state_floats(d.obj_layout, d.n_obj), false);
     if (ok()) e = dalloc(c, &c->d_obj_scratch, S * mpeghb200_obj_scratch_floats(d.obj_layout, d.n_obj), false);
     if (ok()) e = dalloc(c, &c->d_objout, size_t(S) * n_mix * 1024, false);
-    if (ok()) st = mpeghb200_obj_state_init_dev(ctx, d.obj_layout, d.n_obj, nullptr, c->d_obj_state, S, c->comp);
+    // first_frame_flag[] as the reference handle starts out: set for its first MAX_NUM_OAM_OBJS = 24 objects only
+    // (ia_obj_ren_dec_state_struct is zero-allocated and impeghd_obj_renderer_dec_init marks 24 entries)
+    int32_t* d_first = nullptr;
+    if (ok()) e = dalloc(c, &d_first, size_t(d.n_obj), false);
+    if (ok()) {
+      int32_t first[MPEGHB200_OBJ_MAX_OBJECTS];
+      for (int o = 0; o < d.n_obj; ++o) first[o] = o < 24 ? 1 : 0;
+      e = cudaMemcpy(d_first, first, sizeof(int32_t) * d.n_obj, cudaMemcpyHostToDevice);
+    }
+    if (ok()) st = mpeghb200_obj_state_init_dev(ctx, d.obj_layout, d.n_obj, d_first, c->d_obj_state, S, c->comp);
   }
   if (ok() && d.n_hoa_transport > 0) {
     uint8_t* p = nullptr;
