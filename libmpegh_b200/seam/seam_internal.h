@@ -1,11 +1,19 @@
-/* seam_internal.h -- what the translation units of libmpeghb200_seam.so share. */
+/* seam_internal.h -- what the translation units of libmpeghgpu.so / libmpeghb200_seam.so share.
+ *
+ * Every interposed signal function turns its call into a REQUEST and hands it to seam_submit().  Outside a batch
+ * the request executes at once (a batch of one).  Inside mpeghb200_dec_execute_batch every decoder handle runs the
+ * reference's ia_mpegh_dec_execute on its own coroutine; seam_submit() parks the coroutine, and once every handle
+ * of the batch is parked (or finished) the scheduler hands all pending requests of one kind to that kind's
+ * BACK-END in one call: gather from the handles -> one upload -> ONE kernel launch over all of them -> one download
+ * -> scatter.  The handles then continue to their next interposed call.  (seam_core.c)
+ */
 #ifndef MPEGHB200_SEAM_INTERNAL_H
 #define MPEGHB200_SEAM_INTERNAL_H
+#include <stddef.h>
 #include "mpeghb200.h"
 
 mpeghb200_ctx *seam_ctx(void); /* creates the context on first use; never returns without one */
 void seam_die(const char *what, mpeghb200_status st);
-void seam_count_fc(void);
 #define CK(call)                                                                                   \
   do                                                                                               \
   {                                                                                                \
@@ -13,4 +21,66 @@ void seam_count_fc(void);
     if (st_ != MPEGHB200_OK)                                                                       \
       seam_die(#call, st_);                                                                        \
   } while (0)
+
+/* ---- requests ---- */
+typedef enum
+{
+  RQ_FD = 0, /* ia_core_coder_fd_frm_dec */
+  RQ_TNS,    /* ia_core_coder_tns_apply */
+  RQ_LTPF,   /* ia_core_coder_usac_ltpf_process */
+  RQ_LIM,    /* impeghd_peak_limiter_process */
+  RQ_OBJ,    /* impeghd_obj_renderer_dec */
+  RQ_PCM,    /* ia_core_coder_samples_sat */
+  RQ_KINDS
+} seam_kind;
+
+typedef struct seam_req
+{
+  int kind;
+  void *p[6];  /* pointers into the calling handle (meaning per kind) */
+  long v[6];   /* scalars */
+  int status;  /* back-end result handed back to the interposer (reference error code) */
+} seam_req;
+
+typedef void (*seam_backend)(seam_req **reqs, int n);
+void seam_register(int kind, seam_backend fn, const char *name);
+void seam_submit(seam_req *r);
+void seam_inline_lock(void);
+void seam_inline_unlock(void);
+
+/* ---- counters (MPEGHB200_SEAM_STATS=1 prints them at exit) ---- */
+typedef struct
+{
+  unsigned long fd_gpu, fd_host, tns, lim, ltpf, fc, mct, obj, obj_host, pcm, batches, batch_calls, max_batch;
+} seam_counters;
+extern seam_counters seam_n;
+
+/* ---- staging buffers that grow on demand: page-locked host + device of the same size ---- */
+typedef struct
+{
+  void *h, *d;
+  size_t cap;
+} seam_buf;
+void seam_need(seam_buf *b, size_t bytes);
+
+/* ---- device-resident per-handle state, keyed by a pointer inside the reference handle ----
+ * Slots live in blocks of consecutive records so that a batch whose keys sit in consecutive slots (the normal case:
+ * the same handle array batch after batch) is ONE launch over `n` streams at seam_pool_run's base pointer.  Keys
+ * never seen before get a fresh block in batch order; a batch that mixes blocks falls back to one launch per key. */
+typedef struct seam_block
+{
+  struct seam_block *next;
+  char *d;
+  int n;
+  const void **keys;
+} seam_block;
+typedef struct
+{
+  seam_block *blocks;
+  size_t stride; /* bytes per slot */
+} seam_pool;
+/* Finds (or creates: *fresh = 1) consecutive slots for keys[0..n).  Returns the device pointer of slot 0 when the n
+ * keys are consecutive in one block, NULL otherwise (use seam_pool_one per key then). */
+void *seam_pool_range(seam_pool *p, const void **keys, int n, int *fresh);
+void *seam_pool_one(seam_pool *p, const void *key, int *fresh);
 #endif

@@ -84,13 +84,20 @@
 #define FRAME 1024
 #define ERB 58
 
+/* converters by content: handles that decode like streams to the same layout share one (the downmix tensor is a pure
+ * function of the layout pair) */
+#define MAX_FC 8
 static struct
 {
-  const ia_format_conv_dmx_state *key;
   int n_in, n_out;
+  unsigned long long hash;
   mpeghb200_format_conv *fc;
+} conv[MAX_FC];
+static int n_conv;
+static struct
+{
   float *d_in, *d_out, *d_state;
-  float *h_state;
+  float *h_state, *h_D;
   size_t state_floats;
 } c;
 
@@ -103,8 +110,9 @@ impeghd_format_converter_process(ia_mpegh_dec_api_struct *p_obj_mpegh_dec, WORD3
   ia_usac_data_struct *u = &dec->str_usac_data;
   ia_format_conv_dmx_state *a;
   mpeghb200_ctx *ctx;
-  int n_in, n_out, ch;
+  int n_in, n_out, ch, k;
   float *p;
+  mpeghb200_format_conv *fc;
   (void)scratch_buf;
   if (fcs->fc_params == NULL)
     return IA_MPEGH_FORMAT_CONV_INIT_FATAL_INVALID_PARAM;
@@ -115,26 +123,43 @@ impeghd_format_converter_process(ia_mpegh_dec_api_struct *p_obj_mpegh_dec, WORD3
   if (n_out <= 0 || n_in <= 0)
     return IA_MPEGH_FORMAT_CONV_INIT_FATAL_INVALID_CHANNEL_NUM;
   ctx = seam_ctx();
-  if (c.key != a || c.n_in != n_in || c.n_out != n_out)
-  { /* first frame with this converter: take over the downmix tensor the reference designed */
-    float *D = (float *)malloc((size_t)n_out * n_in * FC_BANDS * sizeof(float));
+  seam_inline_lock();
+  if (!c.d_in)
+  {
+    CK(mpeghb200_dev_alloc(ctx, (size_t)FC_MAX_CHANNELS * FRAME * sizeof(float), (void **)&c.d_in));
+    CK(mpeghb200_dev_alloc(ctx, (size_t)FC_MAX_CHANNELS * FRAME * sizeof(float), (void **)&c.d_out));
+    CK(mpeghb200_dev_alloc(ctx, (size_t)FC_MAX_CHANNELS * (512 + 2 * ERB) * sizeof(float), (void **)&c.d_state));
+    c.h_state = (float *)malloc((size_t)FC_MAX_CHANNELS * (512 + 2 * ERB) * sizeof(float));
+    c.h_D = (float *)malloc((size_t)FC_MAX_CHANNELS * FC_MAX_CHANNELS * FC_BANDS * sizeof(float));
+  }
+  { /* take over the downmix tensor the reference designed (first frame with this layout pair: create the converter) */
+    unsigned long long h = 1469598103934665603ull;
+    const unsigned char *b;
+    size_t nb = (size_t)n_out * n_in * FC_BANDS * sizeof(float), q;
     int o, i;
     for (o = 0; o < n_out; o++)
       for (i = 0; i < n_in; i++)
-        memcpy(D + ((size_t)o * n_in + i) * FC_BANDS, a->downmix_mat[o][i], sizeof(float) * FC_BANDS);
-    if (c.fc)
-      mpeghb200_format_conv_destroy(c.fc);
-    CK(mpeghb200_format_conv_create(ctx, n_in, n_out, D, &c.fc));
-    free(D);
-    c.state_floats = mpeghb200_format_conv_state_floats(c.fc);
-    if (!c.d_in)
+        memcpy(c.h_D + ((size_t)o * n_in + i) * FC_BANDS, a->downmix_mat[o][i], sizeof(float) * FC_BANDS);
+    b = (const unsigned char *)c.h_D;
+    for (q = 0; q < nb; q++)
+      h = (h ^ b[q]) * 1099511628211ull;
+    for (k = 0; k < n_conv; k++)
+      if (conv[k].n_in == n_in && conv[k].n_out == n_out && conv[k].hash == h)
+        break;
+    if (k == n_conv)
     {
-      CK(mpeghb200_dev_alloc(ctx, (size_t)FC_MAX_CHANNELS * FRAME * sizeof(float), (void **)&c.d_in));
-      CK(mpeghb200_dev_alloc(ctx, (size_t)FC_MAX_CHANNELS * FRAME * sizeof(float), (void **)&c.d_out));
-      CK(mpeghb200_dev_alloc(ctx, (size_t)FC_MAX_CHANNELS * (512 + 2 * ERB) * sizeof(float), (void **)&c.d_state));
-      c.h_state = (float *)malloc((size_t)FC_MAX_CHANNELS * (512 + 2 * ERB) * sizeof(float));
+      if (n_conv == MAX_FC)
+      {
+        mpeghb200_format_conv_destroy(conv[0].fc);
+        conv[0] = conv[--n_conv];
+        k = n_conv;
+      }
+      conv[k].n_in = n_in, conv[k].n_out = n_out, conv[k].hash = h;
+      CK(mpeghb200_format_conv_create(ctx, n_in, n_out, c.h_D, &conv[k].fc));
+      n_conv++;
     }
-    c.key = a, c.n_in = n_in, c.n_out = n_out;
+    fc = conv[k].fc;
+    c.state_floats = mpeghb200_format_conv_state_floats(fc);
   }
   /* state layout of mpeghb200_format_conv_dev: in_prev [n_in][256], out_prev [n_out][256], t_prev, r_prev [n_out][58] */
   p = c.h_state;
@@ -149,7 +174,7 @@ impeghd_format_converter_process(ia_mpegh_dec_api_struct *p_obj_mpegh_dec, WORD3
   CK(mpeghb200_h2d(ctx, c.d_state, c.h_state, c.state_floats * sizeof(float)));
   for (ch = 0; ch < n_in; ch++)
     CK(mpeghb200_h2d(ctx, c.d_in + (size_t)ch * FRAME, u->time_sample_vector[ch], FRAME * sizeof(float)));
-  CK(mpeghb200_format_conv_dev(ctx, c.fc, c.d_in, c.d_out, c.d_state, 1, NULL));
+  CK(mpeghb200_format_conv_dev(ctx, fc, c.d_in, c.d_out, c.d_state, 1, NULL));
   for (ch = 0; ch < n_out; ch++)
     CK(mpeghb200_d2h(ctx, u->time_sample_vector[ch], c.d_out + (size_t)ch * FRAME, FRAME * sizeof(float)));
   CK(mpeghb200_d2h(ctx, c.h_state, c.d_state, c.state_floats * sizeof(float)));
@@ -163,6 +188,7 @@ impeghd_format_converter_process(ia_mpegh_dec_api_struct *p_obj_mpegh_dec, WORD3
   for (ch = 0; ch < n_out; ch++, p += ERB)
     memcpy(a->realized_energy_prev[ch], p, ERB * sizeof(float));
   st->ui_out_bytes = 1024 * n_out * sizeof(FLOAT32);
-  seam_count_fc();
+  seam_n.fc++;
+  seam_inline_unlock();
   return IA_MPEGH_DEC_NO_ERROR;
 }
