@@ -144,6 +144,14 @@ mpeghb200_status mpeghb200_pcm_pack_dev(mpeghb200_ctx *ctx, const float *d_in, i
                                         const int32_t *out_ch_map, int32_t *d_delay, uint8_t *d_out,
                                         int32_t *d_out_bytes, int n_streams, void *cuda_stream);
 
+/* Limiter and packer fused (what a chain's tail runs): the limited samples never make the planar fp32 round trip
+ * through HBM.  Arguments as the two calls above; results identical to mpeghb200_limiter_dev followed by
+ * mpeghb200_pcm_pack_dev. */
+mpeghb200_status mpeghb200_limiter_pack_dev(mpeghb200_ctx *ctx, const mpeghb200_limiter_params *p, const float *d_in,
+                                            float *d_state, const float *d_loudness_gain, int pcm_bits,
+                                            const int32_t *out_ch_map, int32_t *d_delay, uint8_t *d_pcm,
+                                            int32_t *d_pcm_bytes, int n_streams, void *cuda_stream);
+
 /* The same for a block of n_samples per channel (a multiple of 256) whose channels lie ch_stride floats apart:
  * d_in [stream][n_ch][ch_stride].  The binaural renderer hands over fft_size/2 samples per channel at a time
  * (num_samples_processed, decoder/ia_core_coder_decode_main.c:2839-2856) and the reference packs them with one

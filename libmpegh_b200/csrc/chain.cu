@@ -3,6 +3,7 @@
 // device-resident intermediates, two slots of input / output staging and three streams (upload, compute, download);
 // the stages themselves are the library's *_dev entry points, enqueued back to back on the compute stream in the
 // order of decoder/ia_core_coder_decode_main.c:2736-2893 (each is a programmatic-dependent launch, common.h).
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -56,6 +57,11 @@ struct mpeghb200_chain {
   float* d_binout = nullptr;   // [S][2][block_len]
   float* d_limout = nullptr;   // [S][n_out][1024]
   int ring_pos = 0;            // frames of the current binaural block already stored
+  // limiter + packer as ONE kernel (MPEGHB200_CHAIN_FUSED_TAIL=1).  Off by default: measured on B200 the fused tail is
+  // slower (config 3: 221 vs 159 us, config 5: 0.190 vs 0.156 ms per step) -- both kernels are latency-bound single
+  // waves of one CTA per stream, and the separate packer spreads its byte shuffling over 4 x more CTAs than the
+  // limiter's 128 threads per stream can; the fp32 round trip it saves is not what bounds the step.
+  bool fused_tail = false;
   std::vector<void*> owned;
 
   static constexpr int kDepth = 2;
@@ -162,13 +168,16 @@ mpeghb200_status run_frame(mpeghb200_chain* c, float* core, const uint32_t* fd_s
     return mpeghb200_pcm_pack_block_dev(ctx, c->d_binout, 2, c->block_len, c->block_len, d.pcm_bits,
                                         c->has_map ? c->ch_map : nullptr, c->d_delay, pcm, pcm_bytes, S, st);
   }
-  const float* tail = mix;
-  if (d.limiter) {
+  if (d.limiter && !c->fused_tail) {
     if ((s = mpeghb200_limiter_dev(ctx, &c->lim, mix, c->d_limout, c->d_lim_state, c->d_gain, S, st)) != MPEGHB200_OK)
       return s;
-    tail = c->d_limout;
+    return mpeghb200_pcm_pack_dev(ctx, c->d_limout, c->n_out, d.pcm_bits, c->has_map ? c->ch_map : nullptr, c->d_delay,
+                                  pcm, pcm_bytes, S, st);
   }
-  return mpeghb200_pcm_pack_dev(ctx, tail, c->n_out, d.pcm_bits, c->has_map ? c->ch_map : nullptr, c->d_delay, pcm,
+  if (d.limiter)  // limiter and packer in one pass: no planar fp32 round trip between them
+    return mpeghb200_limiter_pack_dev(ctx, &c->lim, mix, c->d_lim_state, c->d_gain, d.pcm_bits,
+                                      c->has_map ? c->ch_map : nullptr, c->d_delay, pcm, pcm_bytes, S, st);
+  return mpeghb200_pcm_pack_dev(ctx, mix, c->n_out, d.pcm_bits, c->has_map ? c->ch_map : nullptr, c->d_delay, pcm,
                                 pcm_bytes, S, st);
 }
 
@@ -317,7 +326,8 @@ mpeghb200_status mpeghb200_chain_open(mpeghb200_ctx* ctx, const mpeghb200_chain_
     if (st != MPEGHB200_OK) st = fail(ctx, st, "chain_open: limiter parameters");
     if (ok()) e = dalloc(c, &c->d_lim_state, S * mpeghb200_limiter_state_floats(&c->lim), false);
     if (ok()) st = mpeghb200_limiter_state_init_dev(ctx, &c->lim, c->d_lim_state, S, c->comp);
-    if (ok()) e = dalloc(c, &c->d_limout, size_t(S) * c->n_out * 1024, false);
+    if (const char* ev = getenv("MPEGHB200_CHAIN_FUSED_TAIL")) c->fused_tail = atoi(ev) != 0;
+    if (ok() && !c->fused_tail) e = dalloc(c, &c->d_limout, size_t(S) * c->n_out * 1024, false);
     if (ok() && d.loudness_gain != 1.0f) {
       e = dalloc(c, &c->d_gain, size_t(S), false);
       if (ok()) fill_kernel<<<(S + 255) / 256, 256, 0, c->comp>>>(c->d_gain, d.loudness_gain, S);

@@ -37,23 +37,13 @@ struct LimParams {
   float thr, ac, rc;
 };
 
-__global__ void __launch_bounds__(kLimThreads)
-    limiter_kernel(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ state,
-                   const float* __restrict__ loud_gain, const LimParams P) {
-  pdl_prologue();
-  __shared__ __align__(16) float m[kMaxAttack + kFrame + 16];   // channel maxima incl. history / sliding max
-  __shared__ __align__(16) float m2[kMaxAttack + kFrame + 16];  // ping-pong partner
-  __shared__ __align__(16) float g[kFrame];                     // gains; < 0 = pass through
+// Steps 1 - 4 for the CTA's stream: leaves the per-sample gains in g[] (< 0 = pass through) and advances the
+// smoother / history part of the state.  m, m2: [kMaxAttack + kFrame + 16] each, g: [kFrame], all in shared memory.
+__device__ __forceinline__ void limiter_gains(const float* __restrict__ x, float* __restrict__ st, const LimParams& P,
+                                              float lg, bool has_lg, float* m, float* m2, float* g) {
   const int tid = threadIdx.x;
   const int A = P.attack;
-  const size_t sidx = blockIdx.x;
-  const float* x = in + sidx * size_t(P.n_ch) * kFrame;
-  float* y = out + sidx * size_t(P.n_ch) * kFrame;
-  float* st = state + sidx * size_t(P.stride);
   float* st_hist = st + 4;
-  float* st_delay = st + 4 + A;
-  const float lg = loud_gain ? __ldg(loud_gain + sidx) : 1.0f;
-  const bool has_lg = loud_gain != nullptr;
   const float psg0 = st[1];
   const bool bypass = (!P.limiter_on) && (psg0 >= 1.0f);
 
@@ -146,6 +136,26 @@ __global__ void __launch_bounds__(kLimThreads)
     for (int i = tid; i < kFrame; i += kLimThreads) g[i] = -1.0f;
     __syncthreads();
   }
+
+}
+
+__global__ void __launch_bounds__(kLimThreads)
+    limiter_kernel(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ state,
+                   const float* __restrict__ loud_gain, const LimParams P) {
+  pdl_prologue();
+  __shared__ __align__(16) float m[kMaxAttack + kFrame + 16];   // channel maxima incl. history / sliding max
+  __shared__ __align__(16) float m2[kMaxAttack + kFrame + 16];  // ping-pong partner
+  __shared__ __align__(16) float g[kFrame];                     // gains; < 0 = pass through
+  const int tid = threadIdx.x;
+  const int A = P.attack;
+  const size_t sidx = blockIdx.x;
+  const float* x = in + sidx * size_t(P.n_ch) * kFrame;
+  float* y = out + sidx * size_t(P.n_ch) * kFrame;
+  float* st = state + sidx * size_t(P.stride);
+  float* st_delay = st + 4 + A;
+  const float lg = loud_gain ? __ldg(loud_gain + sidx) : 1.0f;
+  const bool has_lg = loud_gain != nullptr;
+  limiter_gains(x, st, P, lg, has_lg, m, m2, g);
 
   // 5. delayed output: sample i of the frame leaves as input sample i - A (this frame for i >= A, the delay line
   //    before), times the gain, clipped.  Straight from global memory (the frame is L2-resident since step 1, A is
@@ -288,6 +298,140 @@ __global__ void __launch_bounds__(kPackSamples)
   }
 }
 
+// ---- limiter + PCM packer in one pass -----------------------------------------------------------------
+// The chain's tail (limiter -> packer) without the planar fp32 round trip through HBM: the limited samples go from
+// registers through a 128-sample byte tile straight into the interleaved PCM record.  Same arithmetic as the two
+// kernels above, node for node.
+constexpr int kLpChunk = kLimThreads;  // samples per PCM tile: one per thread
+
+__device__ __forceinline__ int pcm_convert(float v, int bits) {
+  if (bits == 24) {
+    v = fmul(v, 256.0f);
+    if (v < -8388608.0f)
+      v = -8388608.0f;
+    else if (8388607.0f < v)
+      v = 8388607.0f;
+    return sat_cast(v);
+  }
+  if (bits == 16) {
+    if (v < -32768.0f)
+      v = -32768.0f;
+    else if (32767.0f < v)
+      v = 32767.0f;
+    return sat_cast(v);
+  }
+  v = fmul(v, 65536.0f);
+  if (v < -2147483647.0f) v = -2147483647.0f;
+  return (2147483647.0f < v) ? 0x7fffffff : sat_cast(v);
+}
+
+__global__ void __launch_bounds__(kLimThreads)
+    limiter_pack_kernel(const float* __restrict__ in, unsigned char* __restrict__ pcm, float* __restrict__ state,
+                        const float* __restrict__ loud_gain, int* __restrict__ delay, int* __restrict__ out_bytes,
+                        const LimParams P, const PackParams K) {
+  pdl_prologue();
+  __shared__ __align__(16) float m[kMaxAttack + kFrame + 16];
+  __shared__ __align__(16) float m2[kMaxAttack + kFrame + 16];
+  __shared__ __align__(16) float g[kFrame];
+  extern __shared__ __align__(16) unsigned char tile[];  // [kLpChunk][n_ch][bytes]
+  const int tid = threadIdx.x;
+  const int A = P.attack;
+  const size_t sidx = blockIdx.x;
+  const float* x = in + sidx * size_t(P.n_ch) * kFrame;
+  float* st = state + sidx * size_t(P.stride);
+  float* st_delay = st + 4 + A;
+  const float lg = loud_gain ? __ldg(loud_gain + sidx) : 1.0f;
+  const bool has_lg = loud_gain != nullptr;
+  const int d = delay ? delay[sidx] : 0;
+  limiter_gains(x, st, P, lg, has_lg, m, m2, g);
+
+  const float thr = P.thr;
+  const int bps = K.bits >> 3;
+  const int frame_bytes = kFrame * P.n_ch * bps;
+  const int tile_bytes = kLpChunk * P.n_ch * bps;
+  unsigned char* o = pcm + sidx * size_t(frame_bytes);
+  constexpr int kBatch = 8;
+  const int rec = P.n_ch * bps;           // bytes of one interleaved sample
+  const bool words = (rec & 3) == 0;      // the sample's record is assembled in registers, one 32-bit store per 4 bytes
+  for (int q = 0; q < kFrame / kLpChunk; ++q) {
+    const int i = q * kLpChunk + tid;
+    const float gi = g[i];
+    unsigned long long sh = 0;            // byte shift register of the record under construction
+    int have = 0, wpos = 0;
+    unsigned* tw = reinterpret_cast<unsigned*>(tile + size_t(tid) * rec);
+    for (int ch0 = 0; ch0 < P.n_ch; ch0 += kBatch) {
+      float vin[kBatch];
+#pragma unroll
+      for (int e = 0; e < kBatch; ++e) {
+        if (ch0 + e < P.n_ch) {
+          const int c = K.pos[ch0 + e];
+          if (i >= A) {
+            const float t = __ldg(x + size_t(c) * kFrame + i - A);
+            vin[e] = has_lg ? fmul(t, lg) : t;
+          } else {
+            vin[e] = st_delay[size_t(c) * A + i];  // already carries the loudness gain
+          }
+        } else {
+          vin[e] = 0.0f;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < kBatch; ++e) {
+        const int ch = ch0 + e;
+        if (ch >= P.n_ch) break;
+        float v = vin[e];
+        if (gi >= 0.0f) {
+          v = fmul(v, gi);
+          if (thr < v)
+            v = thr;
+          else if (v < -thr)
+            v = -thr;
+        }
+        const unsigned w = static_cast<unsigned>(pcm_convert(v, K.bits));
+        if (words) {
+          const unsigned long long bytes = bps == 4 ? w : (w & ((1u << (8 * bps)) - 1u));
+          sh |= bytes << (8 * have);
+          have += bps;
+          if (have >= 4) {
+            tw[wpos++] = static_cast<unsigned>(sh);
+            sh >>= 32;
+            have -= 4;
+          }
+        } else {
+          unsigned char* t = tile + size_t(tid) * rec + ch * bps;
+          t[0] = w & 0xff;
+          t[1] = (w >> 8) & 0xff;
+          if (bps > 2) t[2] = (w >> 16) & 0xff;
+          if (bps > 3) t[3] = (w >> 24) & 0xff;
+        }
+      }
+    }
+    __syncthreads();
+    const long long dst0 = (long long)(q * kLpChunk - d) * P.n_ch * bps;
+    if (dst0 >= 0 && (dst0 & 15) == 0 && (tile_bytes & 15) == 0) {
+      const uint4* t4 = reinterpret_cast<const uint4*>(tile);
+      uint4* o4 = reinterpret_cast<uint4*>(o + dst0);
+      for (int k = tid; k < tile_bytes / 16; k += kLimThreads) __stcs(o4 + k, t4[k]);
+    } else {
+      for (int k = tid; k < tile_bytes; k += kLimThreads) {
+        const long long p = dst0 + k;
+        if (p >= 0) o[p] = tile[k];
+      }
+    }
+    __syncthreads();
+  }
+  // the last A samples of the frame are the next frame's delay line (every read of the old one is behind a barrier)
+  for (int c = 0; c < P.n_ch; ++c)
+    for (int j = tid; j < A; j += kLimThreads) {
+      const float t = __ldg(x + size_t(c) * kFrame + kFrame - A + j);
+      st_delay[size_t(c) * A + j] = has_lg ? fmul(t, lg) : t;
+    }
+  if (tid == 0) {
+    if (out_bytes) out_bytes[sidx] = (d <= kFrame) ? (kFrame - d) * P.n_ch * bps : 0;
+    if (delay) delay[sidx] = (d <= kFrame) ? 0 : d - kFrame;
+  }
+}
+
 // the delay state is advanced by a separate tiny kernel so that every chunk CTA of a stream sees the old value
 __global__ void pcm_delay_advance_kernel(int* delay, int n_streams, int n_samples) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -355,6 +499,46 @@ mpeghb200_status mpeghb200_limiter_dev(mpeghb200_ctx* ctx, const mpeghb200_limit
   P.rc = p->release_const;
   MB_CUDA(ctx, launch_pdl(limiter_kernel, dim3(n_streams), dim3(kLimThreads), 0, static_cast<cudaStream_t>(cuda_stream),
                           d_in, d_out, d_state, d_loudness_gain, P));
+  ctx->launches.fetch_add(1);
+  MB_CUDA(ctx, cudaGetLastError());
+  return MPEGHB200_OK;
+}
+
+mpeghb200_status mpeghb200_limiter_pack_dev(mpeghb200_ctx* ctx, const mpeghb200_limiter_params* p, const float* d_in,
+                                            float* d_state, const float* d_loudness_gain, int pcm_bits,
+                                            const int32_t* out_ch_map, int32_t* d_delay, uint8_t* d_pcm,
+                                            int32_t* d_pcm_bytes, int n_streams, void* cuda_stream) {
+  if (!ctx || !p) return MPEGHB200_ERR_BAD_ARG;
+  if (n_streams < 0 || (pcm_bits != 16 && pcm_bits != 24 && pcm_bits != 32) ||
+      (n_streams > 0 && (!d_in || !d_state || !d_pcm)))
+    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "limiter_pack_dev: null buffer, bad sample size or negative stream count");
+  if (n_streams == 0) return MPEGHB200_OK;
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  LimParams P;
+  P.n_ch = p->n_ch;
+  P.attack = p->attack_samples;
+  P.limiter_on = p->limiter_on;
+  P.stride = int(mpeghb200_limiter_state_floats(p));
+  P.thr = p->threshold;
+  P.ac = p->attack_const;
+  P.rc = p->release_const;
+  PackParams K;
+  K.n_ch = p->n_ch;
+  K.bits = pcm_bits;
+  K.n_samples = kFrame;
+  K.ch_stride = kFrame;
+  for (int ch = 0; ch < 64; ++ch) K.pos[ch] = static_cast<unsigned char>(ch < p->n_ch ? ch : 0);
+  if (out_ch_map) {
+    for (int ch = 0; ch < p->n_ch; ++ch) {
+      const int m = out_ch_map[ch] == -1 ? ch : out_ch_map[ch];
+      if (m < 0 || m >= p->n_ch) return fail(ctx, MPEGHB200_ERR_BAD_ARG, "limiter_pack_dev: out_ch_map entry out of range");
+      K.pos[m] = static_cast<unsigned char>(ch);
+    }
+  }
+  const size_t smem = size_t(kLpChunk) * p->n_ch * (pcm_bits >> 3);
+  MB_CUDA(ctx, launch_pdl(limiter_pack_kernel, dim3(n_streams), dim3(kLimThreads), smem,
+                          static_cast<cudaStream_t>(cuda_stream), d_in, d_pcm, d_state, d_loudness_gain, d_delay,
+                          d_pcm_bytes, P, K));
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   return MPEGHB200_OK;

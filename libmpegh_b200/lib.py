@@ -289,6 +289,9 @@ class Lib:
         c.mpeghb200_stereo_save_dev.restype = i32
         c.mpeghb200_stereo_mdst_rom.argtypes = [vp, vp]
         c.mpeghb200_stereo_mdst_rom.restype = None
+        c.mpeghb200_limiter_pack_dev.argtypes = [vp, ctypes.POINTER(LimiterParams), vp, vp, vp, ctypes.c_int, vp, vp, vp,
+                                                 vp, ctypes.c_int, vp]
+        c.mpeghb200_limiter_pack_dev.restype = i32
         c.mpeghb200_pcm_pack_block_dev.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp,
                                                    vp, vp, ctypes.c_int, vp]
         c.mpeghb200_pcm_pack_block_dev.restype = i32
@@ -677,6 +680,13 @@ class Lib:
     def chain_open(self, n_streams, **kw):
         """kw: the fields of mpeghb200_chain_desc (handles as returned by the *_create wrappers)."""
         return Chain(self, n_streams, **kw)
+
+    def limiter_pack_dev(self, p, d_in, d_state, bits, d_pcm, n_streams, d_gain=None, ch_map=None, d_delay=None,
+                         d_pcm_bytes=None, stream=0):
+        m = None if ch_map is None else np.ascontiguousarray(ch_map, dtype=np.int32)
+        self.check(self.c.mpeghb200_limiter_pack_dev(self.ctx, ctypes.byref(p), d_in, d_state, d_gain, bits,
+                                                     None if m is None else m.ctypes.data, d_delay, d_pcm, d_pcm_bytes,
+                                                     n_streams, stream))
 
     def pcm_pack_block_dev(self, d_in, n_ch, n_samples, ch_stride, bits, d_out, n_streams, ch_map=None, d_delay=None,
                            d_out_bytes=None, stream=0):

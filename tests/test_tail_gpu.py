@@ -142,3 +142,40 @@ def test_fd_limiter_pack_chain_24bit(gpu_lib, oracle):
             y = loader.oracle_limiter_run(sts[s], td[f, s * C:(s + 1) * C])
             want, delays[s] = loader.oracle_samples_sat(y, 24, None, delays[s])
             assert nb[s] == want.size and np.array_equal(pcm[s, :want.size], want), (f, s)
+
+
+@pytest.mark.parametrize("n_ch,bits,limiter_on,cmap", [(2, 16, 1, [1, 0]), (12, 24, 1, None), (24, 24, 1, list(range(23, -1, -1))),
+                                                       (5, 32, 0, None), (1, 24, 1, None)])
+def test_fused_limiter_pack_equals_the_two_kernels(gpu_lib, n_ch, bits, limiter_on, cmap):
+    """mpeghb200_limiter_pack_dev (the chain tail) = mpeghb200_limiter_dev + mpeghb200_pcm_pack_dev: PCM bytes, byte
+    counts, delay counters and the limiter state identical over 6 frames of 9 streams (start-up delays 0 .. 1500,
+    a loudness gain per stream)."""
+    import torch
+    rng = np.random.default_rng(100 * n_ch + bits)
+    S, F = 9, 6
+    x = np.stack([tail_cases.limiter_signal(rng, F, n_ch) for _ in range(S)], axis=1)  # [F, S, C, 1024]
+    gains = torch.from_numpy(rng.uniform(0.5, 2.0, S).astype(np.float32)).cuda()
+    delays = [0, 240, 1, 1023, 1024, 1500, 7, 256, 512]
+    a, b = DevLimiter(gpu_lib, S, n_ch, limiter_on), DevLimiter(gpu_lib, S, n_ch, limiter_on)
+    da = torch.tensor(delays, dtype=torch.int32, device="cuda")
+    db = da.clone()
+    st = torch.cuda.current_stream().cuda_stream
+    nbytes = 1024 * n_ch * (bits // 8)
+    for f in range(F):
+        d_in = torch.from_numpy(x[f]).cuda()
+        d_lim = torch.empty_like(d_in)
+        pa = torch.zeros(S, nbytes, dtype=torch.uint8, device="cuda")
+        pb = torch.zeros(S, nbytes, dtype=torch.uint8, device="cuda")
+        na = torch.zeros(S, dtype=torch.int32, device="cuda")
+        nb = torch.zeros(S, dtype=torch.int32, device="cuda")
+        gpu_lib.limiter_dev(a.p, d_in.data_ptr(), d_lim.data_ptr(), a.state.data_ptr(), S, gains.data_ptr(), st)
+        gpu_lib.pcm_pack_dev(d_lim.data_ptr(), n_ch, bits, pa.data_ptr(), S, cmap, da.data_ptr(), na.data_ptr(), st)
+        gpu_lib.limiter_pack_dev(b.p, d_in.data_ptr(), b.state.data_ptr(), bits, pb.data_ptr(), S, gains.data_ptr(), cmap,
+                                 db.data_ptr(), nb.data_ptr(), st)
+        torch.cuda.synchronize()
+        na_, nb_ = na.cpu().numpy(), nb.cpu().numpy()
+        assert np.array_equal(na_, nb_) and np.array_equal(da.cpu().numpy(), db.cpu().numpy()), f
+        pa_, pb_ = pa.cpu().numpy(), pb.cpu().numpy()
+        for s in range(S):
+            assert np.array_equal(pa_[s, :na_[s]], pb_[s, :nb_[s]]), (f, s)
+        assert np.array_equal(a.state.cpu().numpy().view(np.uint32), b.state.cpu().numpy().view(np.uint32)), f
