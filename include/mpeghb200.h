@@ -163,7 +163,8 @@ mpeghb200_status mpeghb200_pcm_pack_block_dev(mpeghb200_ctx *ctx, const float *d
 
 /* ---- object renderer: VBAP gains + ramped mix ------------------------------------------------------
  * Replaces impeghd_obj_renderer_dec (decoder/impeghd_obj_ren_dec.c:1319) and everything below
- * impegh_obj_ren_vbap_process (decoder/impeghd_obj_ren_vbap.c:485) for OAM frame length 1024.
+ * impegh_obj_ren_vbap_process (decoder/impeghd_obj_ren_vbap.c:485); OAM frame length 1024 here, sub-frames of 512 /
+ * 256 samples through mpeghb200_obj_render_sub_dev below.
  *
  * Layout tables: the reference's init (impeghd_obj_renderer_dec_init, impeghd_obj_ren_dec.c:1057) stays host
  * code; after it has run, copy these members of ia_obj_ren_dec_state_struct
@@ -220,6 +221,20 @@ mpeghb200_status mpeghb200_obj_state_init_dev(mpeghb200_ctx *ctx, const mpeghb20
 mpeghb200_status mpeghb200_obj_render_dev(mpeghb200_ctx *ctx, const mpeghb200_obj_layout *layout, int n_obj,
                                           const mpeghb200_obj_side *d_side, const float *d_in, float *d_out,
                                           float *d_state, float *d_scratch, int n_streams, void *cuda_stream);
+
+/* OAM sub-frames (decoder/ia_core_coder_decode_main.c:1383-1410): when the OAM frame length is 512 or 256 the
+ * reference renders a core frame in 2 or 4 calls of impeghd_obj_renderer_dec, each over frame_len samples starting at
+ * sample_offset (a multiple of frame_len) of the same 1024-sample rows, with that sub-frame's metadata (the host
+ * passes the matching side records; sub_frame_number bookkeeping stays host) and the gain ramp spread over frame_len
+ * samples.  Only [sample_offset, sample_offset + frame_len) of d_out is written.  d_metadata_set [n_streams]
+ * (device, or NULL = all 0) is sub_frame_number - 1 of each stream's call: the reference applies its first-frame rule
+ * (ramp starts at the final gains) only to calls rendering with set 0, because it tests first_frame_flag[set *
+ * num_objects + obj] (decoder/impeghd_obj_ren_vbap.c:497); an object first rendered with another set ramps up from
+ * zero gains instead.  mpeghb200_obj_render_dev = frame_len 1024, sample_offset 0, set 0. */
+mpeghb200_status mpeghb200_obj_render_sub_dev(mpeghb200_ctx *ctx, const mpeghb200_obj_layout *layout, int n_obj,
+                                              const mpeghb200_obj_side *d_side, const float *d_in, float *d_out,
+                                              float *d_state, float *d_scratch, int n_streams, int frame_len,
+                                              int sample_offset, const int32_t *d_metadata_set, void *cuda_stream);
 
 /* ---- HOA loudspeaker rendering: NFC filtering + render matrix + clip ---------------------------------
  * Replaces impeghd_hoa_ren_block_process (decoder/impeghd_hoa_renderer.c:181) incl. the near-field

@@ -129,7 +129,8 @@ constexpr int kGainWarps = 4;
 
 __global__ void __launch_bounds__(32 * kGainWarps)
     obj_gains_kernel(const DevLayout* __restrict__ Lp, const mpeghb200_obj_side* __restrict__ side,
-                     float* __restrict__ state, float* __restrict__ scratch, int n_obj, int n_streams) {
+                     float* __restrict__ state, float* __restrict__ scratch, int n_obj, int n_streams, float frame_len,
+                     const int32_t* __restrict__ meta_set) {
   pdl_prologue();
   __shared__ float ls_all[kGainWarps][kMaxLs];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -211,14 +212,18 @@ __global__ void __launch_bounds__(32 * kGainWarps)
   for (int i = 0; i < NL; ++i) gain_sum = fadd(gain_sum, __shfl_sync(0xffffffffu, sq, i));
   gain_sum = __fsqrt_rn(gain_sum);
   float* st = state + size_t(idx) * (NL + 1);
-  const bool first = st[0] != 0.0f;
+  // The first-frame rule (start the ramp at the final gains) only fires for calls rendering with metadata set 0:
+  // the reference tests first_frame_flag[sub_frame_offset + obj] (decoder/impeghd_obj_ren_vbap.c:497), an entry it
+  // never clears for sets > 0 and whose gains land in a row the mixer does not read; the object's own flag is
+  // cleared by every call all the same (decoder/impeghd_obj_ren_dec.c:1367).
+  const bool first = st[0] != 0.0f && (meta_set == nullptr || meta_set[idx / n_obj] == 0);
   __syncwarp();
   float* sc = scratch + size_t(idx) * NL * 2;
   if (lane < NL) {
     float f = value;
     if (gain_sum != 0.0f) f = __fdiv_rn(fmul(f, s.gain), gain_sum);
     const float init = first ? f : st[1 + lane];
-    const float step = __fdiv_rn(fsub(f, init), 1024.0f);
+    const float step = __fdiv_rn(fsub(f, init), frame_len);  // OAM frame length: 1024, or a sub-frame of 512 / 256
     reinterpret_cast<float2*>(sc)[lane] = make_float2(fadd(init, step), step);
     st[1 + lane] = f;
   }
@@ -262,7 +267,7 @@ struct MixSmem {
 template <int NOBJ>
 __global__ void __launch_bounds__(kMixMaxThreads)
     obj_mix_kernel(const DevLayout* __restrict__ Lp, const float* __restrict__ in, float* __restrict__ out,
-                   const float* __restrict__ scratch, int n_obj) {
+                   const float* __restrict__ scratch, int n_obj, int n_chunks, int sample_offset) {
   pdl_prologue();
   extern __shared__ __align__(16) float smem_f[];
   using SM = MixSmem<NOBJ>;
@@ -275,11 +280,11 @@ __global__ void __launch_bounds__(kMixMaxThreads)
   const int n_pairs = NOBJ * n_c;                              // (object, channel) chains, padded objects included
   float* stage = smem_f;                                       // [2][kChunks][kChunkStride]: x[chunk][obj][4]
   float* bound = smem_f + SM::kStageFloats;                    // [n_pairs][kChunks + 1]: chunk-start scales, step
-  const float* xs = in + size_t(s) * n_obj * kFrame;
+  const float* xs = in + size_t(s) * n_obj * kFrame + sample_offset;  // n_chunks * 64 samples from sample_offset on
 
   auto issue = [&](int t) {
     float* dst = stage + (t & 1) * kChunks * SM::kChunkStride;
-    for (int p = threadIdx.x; p < kChunks * NOBJ; p += blockDim.x) {
+    for (int p = threadIdx.x; p < n_chunks * NOBJ; p += blockDim.x) {
       const int chunk = p / NOBJ, o = p % NOBJ;
       if (o < n_obj)
         cp_async16(dst + chunk * SM::kChunkStride + o * kStep, xs + size_t(o) * kFrame + chunk * kCLen + t * kStep);
@@ -306,10 +311,10 @@ __global__ void __launch_bounds__(kMixMaxThreads)
     float v0 = t0.x, v1 = t1.x;
     float* b0 = bound + p * (kChunks + 1);
     float* b1 = bound + (two ? q : p) * (kChunks + 1);
-    for (int c = 0; c < kChunks; ++c) {
+    for (int c = 0; c < n_chunks; ++c) {
       b0[c] = v0;
       if (two) b1[c] = v1;
-      if (c + 1 < kChunks) {
+      if (c + 1 < n_chunks) {
 #pragma unroll 8
         for (int k = 0; k < kCLen; ++k) v0 = fadd(v0, t0.y), v1 = fadd(v1, t1.y);
       }
@@ -319,7 +324,7 @@ __global__ void __launch_bounds__(kMixMaxThreads)
   }
   __syncthreads();
   const int ci = threadIdx.x % n_c, chunk = threadIdx.x / n_c;
-  const bool active = chunk < kChunks;
+  const bool active = chunk < n_chunks;
   float scale[NOBJ], step[NOBJ];
 #pragma unroll
   for (int o = 0; o < NOBJ; ++o) {
@@ -327,7 +332,8 @@ __global__ void __launch_bounds__(kMixMaxThreads)
     scale[o] = active ? b[chunk] : 0.f;
     step[o] = active ? b[kChunks] : 0.f;
   }
-  float* y = out + (size_t(s) * L.n_spk + L.nonlfe_to_spk[c_first + ci]) * kFrame + (active ? chunk : 0) * kCLen;
+  float* y = out + (size_t(s) * L.n_spk + L.nonlfe_to_spk[c_first + ci]) * kFrame + sample_offset +
+             (active ? chunk : 0) * kCLen;
   for (int t = 0; t < kSteps; ++t) {
     if (t + 1 < kSteps) {
       issue(t + 1);
@@ -361,14 +367,14 @@ __global__ void __launch_bounds__(kMixMaxThreads)
   // LFE rows stay zero (decode_main.c:1374 memset)
   if (blockIdx.x == 0)
     for (int l = 0; l < L.n_lfe; ++l) {
-      float4* z = reinterpret_cast<float4*>(out + (size_t(s) * L.n_spk + L.lfe_spk[l]) * kFrame);
-      for (int j = threadIdx.x; j < kFrame / 4; j += blockDim.x) z[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4* z = reinterpret_cast<float4*>(out + (size_t(s) * L.n_spk + L.lfe_spk[l]) * kFrame + sample_offset);
+      for (int j = threadIdx.x; j < n_chunks * kCLen / 4; j += blockDim.x) z[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
 template <int NOBJ>
 cudaError_t launch_mix(const DevLayout* dl, int NL, const float* d_in, float* d_out, const float* d_scratch, int n_obj,
-                       int n_streams, cudaStream_t st) {
+                       int n_streams, int n_chunks, int sample_offset, cudaStream_t st) {
   const int half = (NL + 1) / 2;
   const size_t smem = MixSmem<NOBJ>::bytes(half);
   if (smem > 48 * 1024) {  // per device / context attribute: set on every call
@@ -376,7 +382,7 @@ cudaError_t launch_mix(const DevLayout* dl, int NL, const float* d_in, float* d_
     if (e != cudaSuccess) return e;
   }
   return launch_pdl(obj_mix_kernel<NOBJ>, dim3(NL > 1 ? 2 : 1, n_streams), dim3(half * kChunks), smem, st, dl, d_in, d_out,
-                    d_scratch, n_obj);
+                    d_scratch, n_obj, n_chunks, sample_offset);
 }
 
 __global__ void obj_state_init_kernel(float* state, const int* first, int n_obj, int nl1, size_t total) {
@@ -509,7 +515,18 @@ mpeghb200_status mpeghb200_obj_state_init_dev(mpeghb200_ctx* ctx, const mpeghb20
 mpeghb200_status mpeghb200_obj_render_dev(mpeghb200_ctx* ctx, const mpeghb200_obj_layout* L, int n_obj,
                                           const mpeghb200_obj_side* d_side, const float* d_in, float* d_out,
                                           float* d_state, float* d_scratch, int n_streams, void* cuda_stream) {
+  return mpeghb200_obj_render_sub_dev(ctx, L, n_obj, d_side, d_in, d_out, d_state, d_scratch, n_streams, kFrame, 0,
+                                      nullptr, cuda_stream);
+}
+
+mpeghb200_status mpeghb200_obj_render_sub_dev(mpeghb200_ctx* ctx, const mpeghb200_obj_layout* L, int n_obj,
+                                              const mpeghb200_obj_side* d_side, const float* d_in, float* d_out,
+                                              float* d_state, float* d_scratch, int n_streams, int frame_len,
+                                              int sample_offset, const int32_t* d_metadata_set, void* cuda_stream) {
   if (!ctx || !L) return MPEGHB200_ERR_BAD_ARG;
+  if ((frame_len != 256 && frame_len != 512 && frame_len != 1024) || sample_offset < 0 || sample_offset % frame_len ||
+      sample_offset + frame_len > kFrame)
+    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "obj_render_sub_dev: OAM frame length 256 / 512 / 1024 at a multiple of itself");
   if (n_obj <= 0 || n_obj > kMaxObj) return fail(ctx, MPEGHB200_ERR_UNSUPPORTED, "obj_render_dev: 1..32 objects");
   if (n_streams < 0 || (n_streams > 0 && (!d_side || !d_in || !d_out || !d_state || !d_scratch)))
     return fail(ctx, MPEGHB200_ERR_BAD_ARG, "obj_render_dev: null buffer or negative stream count");
@@ -519,7 +536,7 @@ mpeghb200_status mpeghb200_obj_render_dev(mpeghb200_ctx* ctx, const mpeghb200_ob
   const DevLayout* dl = static_cast<const DevLayout*>(L->d_desc);
   const int n_pairs = n_obj * n_streams;
   MB_CUDA(ctx, launch_pdl(obj_gains_kernel, dim3((n_pairs + kGainWarps - 1) / kGainWarps), dim3(32 * kGainWarps), 0, st, dl,
-                          d_side, d_state, d_scratch, n_obj, n_streams));
+                          d_side, d_state, d_scratch, n_obj, n_streams, float(frame_len), d_metadata_set));
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   const int NL = L->host.n_non_lfe;
@@ -527,13 +544,13 @@ mpeghb200_status mpeghb200_obj_render_dev(mpeghb200_ctx* ctx, const mpeghb200_ob
     return fail(ctx, MPEGHB200_ERR_UNSUPPORTED, "obj_render_dev: more than 24 non-LFE loudspeakers");
   cudaError_t e;
   if (n_obj <= 8)
-    e = launch_mix<8>(dl, NL, d_in, d_out, d_scratch, n_obj, n_streams, st);
+    e = launch_mix<8>(dl, NL, d_in, d_out, d_scratch, n_obj, n_streams, frame_len / kCLen, sample_offset, st);
   else if (n_obj <= 16)
-    e = launch_mix<16>(dl, NL, d_in, d_out, d_scratch, n_obj, n_streams, st);
+    e = launch_mix<16>(dl, NL, d_in, d_out, d_scratch, n_obj, n_streams, frame_len / kCLen, sample_offset, st);
   else if (n_obj <= 24)
-    e = launch_mix<24>(dl, NL, d_in, d_out, d_scratch, n_obj, n_streams, st);
+    e = launch_mix<24>(dl, NL, d_in, d_out, d_scratch, n_obj, n_streams, frame_len / kCLen, sample_offset, st);
   else
-    e = launch_mix<32>(dl, NL, d_in, d_out, d_scratch, n_obj, n_streams, st);
+    e = launch_mix<32>(dl, NL, d_in, d_out, d_scratch, n_obj, n_streams, frame_len / kCLen, sample_offset, st);
   MB_CUDA(ctx, e);
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());

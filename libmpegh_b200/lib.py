@@ -191,6 +191,9 @@ class Lib:
         c.mpeghb200_obj_state_init_dev.restype = i32
         c.mpeghb200_obj_render_dev.argtypes = [vp, vp, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_int, vp]
         c.mpeghb200_obj_render_dev.restype = i32
+        c.mpeghb200_obj_render_sub_dev.argtypes = [vp, vp, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int,
+                                                   ctypes.c_int, vp, vp]
+        c.mpeghb200_obj_render_sub_dev.restype = i32
         c.mpeghb200_hoa_renderer_create.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int,
                                                     ctypes.POINTER(vp)]
         c.mpeghb200_hoa_renderer_create.restype = i32
@@ -658,6 +661,11 @@ class Lib:
     def obj_render_dev(self, layout, n_obj, d_side, d_in, d_out, d_state, d_scratch, n_streams, stream=0):
         self.check(self.c.mpeghb200_obj_render_dev(self.ctx, layout, n_obj, d_side, d_in, d_out, d_state, d_scratch,
                                                    n_streams, stream))
+
+    def obj_render_sub_dev(self, layout, n_obj, d_side, d_in, d_out, d_state, d_scratch, n_streams, frame_len,
+                           sample_offset, d_metadata_set=None, stream=0):
+        self.check(self.c.mpeghb200_obj_render_sub_dev(self.ctx, layout, n_obj, d_side, d_in, d_out, d_state, d_scratch,
+                                                       n_streams, frame_len, sample_offset, d_metadata_set, stream))
 
     # ---- tail of the chain ----------------------------------------------------------------------
     def limiter_params(self, n_ch, sample_rate=48000, limiter_on=1):

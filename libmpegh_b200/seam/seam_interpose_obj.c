@@ -7,8 +7,8 @@
  * loudspeaker vectors, imaginary-speaker downmix) becomes an mpeghb200_obj_layout -- the side record of SURVEY.md row
  * a1 filled from a REAL handle --, the frame's OAM values (the *_descaled arrays the reference's OAM parser wrote)
  * become mpeghb200_obj_side records through the library's host trigonometry, previous gains and first-frame flags
- * live on the device, one slot per renderer state.  Frames whose OAM frame length is shorter than the core frame
- * (sub-frames of 256 / 512 samples) are forwarded to the reference function and counted.
+ * live on the device, one slot per renderer state.  OAM sub-frames (frame length 512 / 256: two / four calls per
+ * core frame, each with its own metadata set) go through mpeghb200_obj_render_sub_dev.
  *
  * PCM packer: stateless apart from the start-up delay counter, which stays in the handle.  The function is `static`
  * in the reference; it is reachable for interposition only in a reference build that gives it external linkage
@@ -102,7 +102,7 @@ static struct
   seam_pool pool[MPEGHB200_OBJ_MAX_OBJECTS + 1]; /* device state by object count */
 } lay[MAX_LAYOUTS];
 static int n_lay;
-static seam_buf b_obj_in, b_obj_out, b_obj_side, b_obj_scratch, b_obj_first;
+static seam_buf b_obj_in, b_obj_out, b_obj_side, b_obj_scratch, b_obj_first, b_obj_set;
 
 static void fill_desc(const ia_obj_ren_dec_state_struct *s, mpeghb200_obj_layout_desc *d)
 {
@@ -149,10 +149,13 @@ static int layout_of(const ia_obj_ren_dec_state_struct *s)
   return n_lay++;
 }
 
-/* one group: same layout, same object count.  p[0] = ia_obj_ren_dec_state_struct, p[1] = in [n_obj][1024],
- * p[2] = out [n_spk][1024] */
+/* one group: same layout, same object count, same OAM frame length.  p[0] = ia_obj_ren_dec_state_struct, p[1] = in
+ * (rows of 1024, already offset to the sub-frame), p[2] = out (likewise), v[0] = OAM frame length (1024, or a
+ * sub-frame of 512 / 256: decode_main.c:1383-1410), v[1] = index of the first object's metadata
+ * ((sub_frame_number - 1) * num_objects, impeghd_obj_ren_dec.c:1331) */
 static void obj_group(seam_req **rq, int n, int L, int n_obj)
 {
+  const int flen = (int)rq[0]->v[0];
   mpeghb200_ctx *ctx = seam_ctx();
   const int n_spk = lay[L].desc.n_spk;
   const size_t in_b = (size_t)n * n_obj * FRAME * sizeof(float), out_b = (size_t)n * n_spk * FRAME * sizeof(float);
@@ -167,23 +170,30 @@ static void obj_group(seam_req **rq, int n, int L, int n_obj)
   seam_need(&b_obj_in, in_b), seam_need(&b_obj_out, out_b), seam_need(&b_obj_side, side_b);
   seam_need(&b_obj_scratch, (size_t)n * sc_f * sizeof(float));
   seam_need(&b_obj_first, (size_t)n_obj * sizeof(int32_t));
+  seam_need(&b_obj_set, (size_t)n * sizeof(int32_t));
   for (i = 0; i < n; i++)
   {
     const ia_obj_ren_dec_state_struct *s = (const ia_obj_ren_dec_state_struct *)rq[i]->p[0];
     const ia_oam_dec_state_struct *md = &s->str_obj_md_dec_state;
     keys[i] = s;
+    const int k0 = (int)rq[i]->v[1];
+    ((int32_t *)b_obj_set.h)[i] = k0 / n_obj; /* the metadata set: sub_frame_number - 1 */
     for (o = 0; o < n_obj; o++)
     {
-      params[o][0] = md->azimuth_descaled[o], params[o][1] = md->elevation_descaled[o];
-      params[o][2] = md->radius_descaled[o], params[o][3] = md->gain_descaled[o];
-      params[o][4] = md->spread_width_descaled[o], params[o][5] = md->spread_height_descaled[o];
-      params[o][6] = md->spread_depth_descaled[o];
+      const int k = k0 + o;
+      params[o][0] = md->azimuth_descaled[k], params[o][1] = md->elevation_descaled[k];
+      params[o][2] = md->radius_descaled[k], params[o][3] = md->gain_descaled[k];
+      params[o][4] = md->spread_width_descaled[k], params[o][5] = md->spread_height_descaled[k];
+      params[o][6] = md->spread_depth_descaled[k];
     }
     mpeghb200_obj_side_from_polar(&params[0][0], n_obj, (mpeghb200_obj_side *)b_obj_side.h + (size_t)i * n_obj);
-    memcpy((float *)b_obj_in.h + (size_t)i * n_obj * FRAME, rq[i]->p[1], (size_t)n_obj * FRAME * sizeof(float));
+    for (o = 0; o < n_obj; o++) /* the sub-frame's samples to the head of the staging rows */
+      memcpy((float *)b_obj_in.h + ((size_t)i * n_obj + o) * FRAME, (const float *)rq[i]->p[1] + (size_t)o * FRAME,
+             (size_t)flen * sizeof(float));
   }
   CK(mpeghb200_h2d(ctx, b_obj_in.d, b_obj_in.h, in_b));
   CK(mpeghb200_h2d(ctx, b_obj_side.d, b_obj_side.h, side_b));
+  CK(mpeghb200_h2d(ctx, b_obj_set.d, b_obj_set.h, (size_t)n * sizeof(int32_t)));
   base = (float *)seam_pool_range(pool, keys, n, &fresh);
   for (i = 0; i < n; i++)
   {
@@ -198,16 +208,20 @@ static void obj_group(seam_req **rq, int n, int L, int n_obj)
       CK(mpeghb200_obj_state_init_dev(ctx, lay[L].h, n_obj, (const int32_t *)b_obj_first.d, st, 1, NULL));
     }
     if (!base)
-      CK(mpeghb200_obj_render_dev(ctx, lay[L].h, n_obj, (const mpeghb200_obj_side *)b_obj_side.d + (size_t)i * n_obj,
-                                  (const float *)b_obj_in.d + (size_t)i * n_obj * FRAME,
-                                  (float *)b_obj_out.d + (size_t)i * n_spk * FRAME, st, (float *)b_obj_scratch.d, 1, NULL));
+      CK(mpeghb200_obj_render_sub_dev(ctx, lay[L].h, n_obj, (const mpeghb200_obj_side *)b_obj_side.d + (size_t)i * n_obj,
+                                      (const float *)b_obj_in.d + (size_t)i * n_obj * FRAME,
+                                      (float *)b_obj_out.d + (size_t)i * n_spk * FRAME, st, (float *)b_obj_scratch.d, 1,
+                                      flen, 0, (const int32_t *)b_obj_set.d + i, NULL));
   }
   if (base)
-    CK(mpeghb200_obj_render_dev(ctx, lay[L].h, n_obj, (const mpeghb200_obj_side *)b_obj_side.d, (const float *)b_obj_in.d,
-                                (float *)b_obj_out.d, base, (float *)b_obj_scratch.d, n, NULL));
+    CK(mpeghb200_obj_render_sub_dev(ctx, lay[L].h, n_obj, (const mpeghb200_obj_side *)b_obj_side.d,
+                                    (const float *)b_obj_in.d, (float *)b_obj_out.d, base, (float *)b_obj_scratch.d, n,
+                                    flen, 0, (const int32_t *)b_obj_set.d, NULL));
   CK(mpeghb200_d2h(ctx, b_obj_out.h, b_obj_out.d, out_b));
-  for (i = 0; i < n; i++)
-    memcpy(rq[i]->p[2], (float *)b_obj_out.h + (size_t)i * n_spk * FRAME, (size_t)n_spk * FRAME * sizeof(float));
+  for (i = 0; i < n; i++) /* the reference accumulates into rows its caller zeroed: every sample is written once */
+    for (o = 0; o < n_spk; o++)
+      memcpy((float *)rq[i]->p[2] + (size_t)o * FRAME, (float *)b_obj_out.h + ((size_t)i * n_spk + o) * FRAME,
+             (size_t)flen * sizeof(float));
   free(keys);
   seam_n.obj += (unsigned long)n;
 }
@@ -222,7 +236,8 @@ static void be_obj(seam_req **rq, int n)
     for (b = a + 1; b < n; b++)
     {
       const ia_obj_ren_dec_state_struct *sb = (const ia_obj_ren_dec_state_struct *)rq[b]->p[0];
-      if (sb->str_obj_md_dec_state.num_objects != n_obj || sb->cicp_out_idx != sa->cicp_out_idx ||
+      if (rq[b]->v[0] != rq[a]->v[0] || sb->str_obj_md_dec_state.num_objects != n_obj ||
+          sb->cicp_out_idx != sa->cicp_out_idx ||
           sb->num_cicp_speakers != sa->num_cicp_speakers || layout_of(sb) != L)
         break;
     }
@@ -240,9 +255,11 @@ impeghd_obj_renderer_dec(ia_obj_ren_dec_state_struct *ptr_obj_ren_dec_state, FLO
   seam_req r;
   if (md->num_objects <= 0)
     return IA_MPEGH_DEC_NO_ERROR;
-  if (cc_frame_len != FRAME || md->p_obj_md_cfg->frame_length != FRAME || md->sub_frame_number != 1 ||
+  const int flen = md->p_obj_md_cfg->frame_length;
+  if (cc_frame_len != FRAME || (flen != 256 && flen != 512 && flen != FRAME) || md->sub_frame_number < 1 ||
+      md->sub_frame_number * md->num_objects > MAX_OAM_FRAMES * MAX_NUM_OAM_OBJS ||
       md->num_objects > MPEGHB200_OBJ_MAX_OBJECTS || ptr_obj_ren_dec_state->num_cicp_speakers > MPEGHB200_OBJ_MAX_LS)
-  { /* OAM sub-frames (256 / 512 samples): forwarded, counted, stated in DESIGN.md */
+  { /* a shape outside the GPU path (core frame length other than 1024, more than 32 objects): forwarded, counted */
     static fn_t real;
     if (!real)
       real = (fn_t)dlsym(RTLD_NEXT, "impeghd_obj_renderer_dec");
@@ -251,6 +268,7 @@ impeghd_obj_renderer_dec(ia_obj_ren_dec_state_struct *ptr_obj_ren_dec_state, FLO
   }
   r.kind = RQ_OBJ;
   r.p[0] = ptr_obj_ren_dec_state, r.p[1] = p_in_buf, r.p[2] = p_out_buf;
+  r.v[0] = flen, r.v[1] = (md->sub_frame_number - 1) * md->num_objects;
   seam_submit(&r);
   return IA_MPEGH_DEC_NO_ERROR;
 }

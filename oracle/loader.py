@@ -76,6 +76,8 @@ def load_oracle():
     lib.oracle_obj_trig.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
     lib.oracle_obj_gains.argtypes = [ctypes.c_void_p, ctypes.c_void_p, _f32p]
     lib.oracle_obj_render.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _f32p, _f32p]
+    lib.oracle_obj_render_sub.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _f32p, _f32p,
+                                          ctypes.c_int, ctypes.c_int, ctypes.c_int]
     lib.oracle_hoa_render.argtypes = [_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, _f32p,
                                       ctypes.c_int, ctypes.c_int, _f32p]
     lib.oracle_cplx_fft_pow2.argtypes = [_f32p, _f32p, ctypes.c_int]
@@ -199,6 +201,9 @@ def load_ref():
     lib.ref_obj_first_flags.argtypes = [ctypes.c_void_p, _i32p, ctypes.c_int]
     lib.ref_obj_render.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int, _f32p, _f32p, _f32p]
     lib.ref_obj_render.restype = ctypes.c_int
+    lib.ref_obj_render_subframes.argtypes = [ctypes.c_void_p, _f32p, _i32p, ctypes.c_int, ctypes.c_int, _f32p, _f32p,
+                                             _i32p]
+    lib.ref_obj_render_subframes.restype = ctypes.c_int
     lib.ref_hoa_ren_create.restype = ctypes.c_void_p
     lib.ref_hoa_ren_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int,
                                        ctypes.POINTER(ctypes.c_int)]
@@ -353,6 +358,33 @@ def oracle_obj_render(L, st, side, x):
     out = np.zeros((L.n_spk, 1024), np.float32)
     load_oracle().oracle_obj_render(ctypes.byref(L), ctypes.byref(st), ctypes.c_void_p(side.ctypes.data), x.shape[0],
                                     x, out)
+    return out
+
+
+def subframe_sets(present, num_iter):
+    """Which metadata set each sub-frame call renders with: the sub_frame_number bookkeeping of
+    impeghd_obj_md_dec_ren_process (decoder/ia_core_coder_decode_main.c:1388-1404), minus one."""
+    n, used = 0, []
+    for i, p in enumerate(present):
+        if p:
+            n += 1
+            if n > num_iter:
+                n %= num_iter
+        elif i == 0:
+            n = num_iter
+        used.append(n - 1)
+    return used
+
+
+def oracle_obj_render_subframes(L, st, params, present, frame_len, x):
+    """params [n_sub, n_obj, 7]; x [n_obj, 1024] -> out [n_spk, 1024] (the frame rendered in n_sub calls)"""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.zeros((L.n_spk, 1024), np.float32)
+    n_sub = 1024 // frame_len
+    for i, k in enumerate(subframe_sets(present, n_sub)):
+        side = oracle_obj_side(params[k])
+        load_oracle().oracle_obj_render_sub(ctypes.byref(L), ctypes.byref(st), ctypes.c_void_p(side.ctypes.data),
+                                            x.shape[0], x, out, frame_len, i * frame_len, k)
     return out
 
 

@@ -202,18 +202,22 @@ void oracle_obj_gains(const oracle_obj_layout *L, const oracle_obj_side *s, floa
       fg[i] = (fg[i] * s->gain) / gain_sum;
 }
 
-/* one frame: in [n_obj][1024], out [n_spk][1024] (overwritten: zero + sum over objects, LFE rows zero) */
-void oracle_obj_render(const oracle_obj_layout *L, oracle_obj_state *st, const oracle_obj_side *side, int n_obj,
-                       const float *in, float *out)
+/* one call of impeghd_obj_renderer_dec (decoder/impeghd_obj_ren_dec.c:1319): frame_len samples from `offset` on of
+ * 1024-sample rows, the gain ramp spread over frame_len samples; accumulates into out (the caller zeroed it once per
+ * core frame, decoder/ia_core_coder_decode_main.c:1374) */
+void oracle_obj_render_sub(const oracle_obj_layout *L, oracle_obj_state *st, const oracle_obj_side *side, int n_obj,
+                           const float *in, float *out, int frame_len, int offset, int metadata_set)
 {
   int obj, ch, j;
-  memset(out, 0, sizeof(float) * 1024 * L->n_spk);
   for (obj = 0; obj < n_obj; obj++)
   {
     float fg[44];
     int lfe = 0;
     oracle_obj_gains(L, &side[obj], fg);
-    if (st->first_frame[obj])
+    /* impeghd_obj_ren_vbap.c:497 tests first_frame_flag[sub_frame_offset + obj] and writes initial_gains of THAT row:
+     * only a call rendering with metadata set 0 starts the ramp at the final gains; :1367 clears the object's own flag
+     * after every call */
+    if (st->first_frame[obj] && metadata_set == 0)
       memcpy(st->initial_gains[obj], fg, sizeof(float) * L->n_non_lfe);
     for (ch = 0; ch < L->n_spk; ch++)
     {
@@ -224,11 +228,11 @@ void oracle_obj_render(const oracle_obj_layout *L, oracle_obj_state *st, const o
       else
       {
         int ci = ch - lfe;
-        float step = (fg[ci] - st->initial_gains[obj][ci]) / 1024;
+        float step = (fg[ci] - st->initial_gains[obj][ci]) / frame_len;
         float scale = st->initial_gains[obj][ci] + step;
-        float *o = out + (size_t)ch * 1024;
-        const float *x = in + (size_t)obj * 1024;
-        for (j = 0; j < 1024; j++)
+        float *o = out + (size_t)ch * 1024 + offset;
+        const float *x = in + (size_t)obj * 1024 + offset;
+        for (j = 0; j < frame_len; j++)
         {
           o[j] = o[j] + x[j] * scale;
           scale = scale + step;
@@ -238,4 +242,12 @@ void oracle_obj_render(const oracle_obj_layout *L, oracle_obj_state *st, const o
     memcpy(st->initial_gains[obj], fg, sizeof(float) * L->n_non_lfe);
     st->first_frame[obj] = 0;
   }
+}
+
+/* one frame: in [n_obj][1024], out [n_spk][1024] (overwritten: zero + sum over objects, LFE rows zero) */
+void oracle_obj_render(const oracle_obj_layout *L, oracle_obj_state *st, const oracle_obj_side *side, int n_obj,
+                       const float *in, float *out)
+{
+  memset(out, 0, sizeof(float) * 1024 * L->n_spk);
+  oracle_obj_render_sub(L, st, side, n_obj, in, out, 1024, 0, 0);
 }

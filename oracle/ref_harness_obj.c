@@ -131,3 +131,53 @@ int ref_obj_render(void *p, const float *params, int n_obj, const float *in, flo
       memcpy(gains_out + o * CICP_MAX_NUM_LS, h->st.initial_gains[o], sizeof(float) * CICP_MAX_NUM_LS);
   return (int)err;
 }
+
+/* One core frame with OAM sub-frames: the loop of impeghd_obj_md_dec_ren_process (ia_core_coder_decode_main.c:1383-1410)
+ * around the reference's impeghd_obj_renderer_dec.  params [n_sub][n_obj][7] = the metadata sets of the frame's
+ * sub-frames as the OAM parser would have left them (index sub * n_obj + obj), present [n_sub] =
+ * sub_frame_obj_md_present; frame_len = 256 or 512 (n_sub = 1024 / frame_len).  used_set [n_sub] (optional) receives
+ * the index of the set each call rendered with (sub_frame_number - 1). */
+int ref_obj_render_subframes(void *p, const float *params, const int *present, int n_obj, int frame_len, const float *in,
+                             float *out, int *used_set)
+{
+  ref_obj_handle *h = (ref_obj_handle *)p;
+  ia_oam_dec_state_struct *md = &h->st.str_obj_md_dec_state;
+  const int num_iter = 1024 / frame_len;
+  IA_ERRORCODE err = 0;
+  int i, o;
+  md->num_objects = n_obj;
+  h->md_cfg.frame_length = frame_len;
+  for (i = 0; i < num_iter; i++)
+    for (o = 0; o < n_obj; o++)
+    {
+      const float *q = params + ((size_t)i * n_obj + o) * 7;
+      const int k = i * n_obj + o;
+      md->azimuth_descaled[k] = q[0];
+      md->elevation_descaled[k] = q[1];
+      md->radius_descaled[k] = q[2];
+      md->gain_descaled[k] = q[3];
+      md->spread_width_descaled[k] = q[4];
+      md->spread_height_descaled[k] = q[5];
+      md->spread_depth_descaled[k] = q[6];
+    }
+  memset(out, 0, sizeof(float) * 1024 * h->st.num_cicp_speakers);
+  md->sub_frame_number = 0;
+  for (i = 0; i < num_iter; i++)
+  {
+    if (present[i])
+    {
+      md->sub_frame_number++;
+      if (md->sub_frame_number > num_iter)
+        md->sub_frame_number = md->sub_frame_number % num_iter;
+    }
+    else if (i == 0)
+    {
+      md->sub_frame_number = num_iter;
+    }
+    if (used_set)
+      used_set[i] = md->sub_frame_number - 1;
+    err |= impeghd_obj_renderer_dec(&h->st, (FLOAT32 *)in + i * frame_len, out + i * frame_len, 1024);
+  }
+  h->md_cfg.frame_length = 1024;
+  return (int)err;
+}

@@ -100,3 +100,36 @@ def test_full_size_properties(gpu_lib, oracle):
         st = loader.oracle_obj_state_new(24)
         assert bits_equal(out[s], loader.oracle_obj_render(L, st, loader.oracle_obj_side(params[s]), x[s])), s
     assert not out[:, 3].any()  # LFE row untouched (zero)
+
+
+@pytest.mark.parametrize("frame_len", [256, 512])
+def test_oam_subframes_vs_oracle(gpu_lib, oracle, frame_len):
+    """OAM frame length 256 / 512: 4 / 2 mpeghb200_obj_render_sub_dev calls per core frame, each with the metadata set
+    the reference's sub_frame_number bookkeeping selects; 6 streams x 5 frames, state carried on the device."""
+    import torch
+    rng = np.random.default_rng(900 + frame_len)
+    S, F, O, n_sub = 6, 5, 9, 1024 // frame_len
+    L = loader.obj_layout_from_arrays(loader.obj_layout_golden(19))
+    sts = [loader.oracle_obj_state_new(24) for _ in range(S)]
+    r = DevObjRenderer(gpu_lib, 19, S, O)
+    st = torch.cuda.current_stream().cuda_stream
+    for f in range(F):
+        params = np.stack([obj_cases.random_params(rng, n_sub, O) for _ in range(S)])      # [S, n_sub, O, 7]
+        present = (rng.random((S, n_sub)) < 0.7).astype(np.int32)
+        x = np.stack([obj_cases.object_audio(rng, 1, O)[0] for _ in range(S)])             # [S, O, 1024]
+        d_in = torch.from_numpy(x).cuda()
+        d_out = torch.full((S, r.n_spk, 1024), float("nan"), device="cuda")
+        used = np.array([loader.subframe_sets(present[s], n_sub) for s in range(S)])        # [S, n_sub]
+        for i in range(n_sub):
+            side = gpu_lib.obj_side_from_polar(np.stack([params[s, used[s, i]] for s in range(S)]))
+            d_side = torch.from_numpy(side.view(np.float32).reshape(S, O, 16).copy()).cuda()
+            d_set = torch.from_numpy(np.ascontiguousarray(used[:, i], np.int32)).cuda()
+            gpu_lib.obj_render_sub_dev(r.layout, O, d_side.data_ptr(), d_in.data_ptr(), d_out.data_ptr(),
+                                       r.state.data_ptr(), r.scratch.data_ptr(), S, frame_len, i * frame_len,
+                                       d_set.data_ptr(), st)
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy()
+        for s in range(S):
+            want = loader.oracle_obj_render_subframes(L, sts[s], params[s], present[s], frame_len, x[s])
+            assert bits_equal(got[s], want), (frame_len, f, s, float(np.abs(got[s] - want).max()))
+    r.close()

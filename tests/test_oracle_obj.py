@@ -54,3 +54,30 @@ def test_obj_golden(oracle):
         for f in range(params.shape[0]):
             got = loader.oracle_obj_render(L, st, loader.oracle_obj_side(params[f]), x[f])
             assert bits_equal(got, g[f"cicp{cicp}_out"][f]), (cicp, f)
+
+
+@pytest.mark.parametrize("frame_len", [256, 512])
+def test_oam_subframes_vs_reference(ref, oracle, frame_len):
+    """OAM frame length 256 / 512: the reference renders a core frame in 4 / 2 calls (decode_main.c:1383-1410); the
+    oracle's sub-frame call chained with the same sub_frame_number bookkeeping must give the same frame."""
+    err = ctypes.c_int()
+    h = ref.ref_obj_create(19, ctypes.byref(err))
+    assert err.value == 0
+    L = loader.obj_layout_from_arrays(loader.ref_obj_layout_arrays(ref, h))
+    n_obj, n_sub, F = 7, 1024 // frame_len, 6
+    st = loader.oracle_obj_state_new(24)
+    rng = np.random.default_rng(frame_len)
+    for f in range(F):
+        params = obj_cases.random_params(rng, n_sub, n_obj)
+        present = (rng.random(n_sub) < 0.7).astype(np.int32)
+        if f == 0:
+            present[0] = frame_len == 512  # 256: the stream's very first call renders with set 3, not set 0
+        x = obj_cases.object_audio(rng, 1, n_obj)[0]
+        want = np.zeros((L.n_spk, 1024), np.float32)
+        used = np.zeros(n_sub, np.int32)
+        assert ref.ref_obj_render_subframes(h, params.reshape(-1), present, n_obj, frame_len, x.reshape(-1),
+                                            want.reshape(-1), used) == 0
+        assert list(used) == loader.subframe_sets(present, n_sub)
+        got = loader.oracle_obj_render_subframes(L, st, params, present, frame_len, x)
+        assert bits_equal(got, want), (frame_len, f, float(np.abs(got - want).max()))
+    ref.ref_obj_destroy(h)

@@ -188,3 +188,54 @@ def test_seam_mct(tmp_path):
         outs.append(np.load(out))
     assert outs[0].shape == outs[1].shape
     assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+
+
+OBJ_SUB_SCRIPT = r"""
+import sys, ctypes, numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+import obj_cases
+from oracle import loader
+ref = loader.load_ref()
+frame_len, out_path = int(sys.argv[2]), sys.argv[3]
+err = ctypes.c_int(0)
+h = ref.ref_obj_create(19, ctypes.byref(err))
+assert err.value == 0
+n_obj, n_sub = 7, 1024 // frame_len
+rng = np.random.default_rng(frame_len)
+outs = []
+for f in range(5):
+    params = obj_cases.random_params(rng, n_sub, n_obj)
+    present = (rng.random(n_sub) < 0.7).astype(np.int32)
+    x = obj_cases.object_audio(rng, 1, n_obj)[0]
+    y = np.zeros((12, 1024), np.float32)
+    used = np.zeros(n_sub, np.int32)
+    assert ref.ref_obj_render_subframes(h, params.reshape(-1), present, n_obj, frame_len, x.reshape(-1), y.reshape(-1), used) == 0
+    outs.append(y)
+np.save(out_path, np.stack(outs))
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("frame_len", [256, 512])
+def test_seam_oam_subframes(tmp_path, frame_len):
+    """OAM sub-frames through the interposed impeghd_obj_renderer_dec (none of the shipped streams uses them): the
+    sub-frame loop of oracle/ref_harness_obj.c drives the reference's function once plainly and once with the seam
+    preloaded; 4 / 2 GPU renders per core frame, identical output."""
+    libref = os.path.join(REF_DIR, "libmpeghref.so")
+    _need(libref, SEAM)
+    script = tmp_path / "objsub.py"
+    script.write_text(OBJ_SUB_SCRIPT)
+    outs = []
+    for preload in (None, SEAM):
+        env = dict(os.environ)
+        if preload:
+            env["LD_PRELOAD"], env["MPEGHB200_SEAM_STATS"] = preload, "1"
+        out = str(tmp_path / ("gpu.npy" if preload else "ref.npy"))
+        r = subprocess.run([sys.executable, str(script), ROOT, str(frame_len), out], env=env, capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-800:]
+        if preload:
+            m = re.search(r"obj_render gpu=(\d+) host\(sub-frames\)=(\d+)", r.stderr)
+            assert m and int(m.group(1)) == 5 * (1024 // frame_len) and int(m.group(2)) == 0, r.stderr[-400:]
+        outs.append(np.load(out))
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
