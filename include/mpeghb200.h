@@ -255,11 +255,15 @@ void mpeghb200_hoa_renderer_destroy(mpeghb200_hoa_renderer *r);
 size_t mpeghb200_hoa_nfc_state_floats(const mpeghb200_hoa_renderer *r);
 int mpeghb200_hoa_renderer_num_out(const mpeghb200_hoa_renderer *r);
 int mpeghb200_hoa_renderer_num_coeffs(const mpeghb200_hoa_renderer *r);
-/* Opt-in throughput mode for the one dense contraction of the path (out = M x, impeghd_hoa_renderer.c:231-253):
- * on != 0 applies the render matrix on the tensor cores (TF32 mma with the 3xTF32 operand split, fp32
- * accumulation) instead of the reference's left-to-right fp32 sum.  Results are then no longer bit-identical but
- * within BASELINE.json's float-stage tolerance, max |err| <= 2^-20 of full scale (2^-5 at the 16-bit scale of the
- * path); the NFC cascade and the clip are unchanged.  Off by default. */
+/* Opt-in throughput modes for the one dense contraction of the path (out = M x, impeghd_hoa_renderer.c:231-253),
+ * which apply the render matrix on the tensor cores instead of the reference's left-to-right fp32 sum:
+ *   1  legacy mma.sync TF32 with the two-term 3xTF32 operand split (any order, NFC on or off);
+ *   2  tcgen05.mma kind::tf32, accumulators in tensor memory, EXACT three-term TF32 split of both operands (six
+ *      products per k step): NFC-off renderers with at most 32 coefficients (order <= 4) and 32 outputs.
+ * Results are then no longer bit-identical but within BASELINE.json's float-stage tolerance, max |err| <= 2^-20 of
+ * full scale (2^-5 at the 16-bit scale of the path); mode 2 also holds the final 24-bit PCM within +-1 LSB for
+ * programme-level signals (a few ulp of fp32 accumulation-order difference is all that is left).  The NFC cascade
+ * and the clip are unchanged.  0 (default) = the bit-exact fp32 kernels. */
 mpeghb200_status mpeghb200_hoa_renderer_set_tensor_mode(mpeghb200_hoa_renderer *r, int on);
 mpeghb200_status mpeghb200_hoa_render_dev(mpeghb200_ctx *ctx, const mpeghb200_hoa_renderer *r, const float *d_in,
                                           float *d_out, float *d_nfc_state, int n_streams, void *cuda_stream);

@@ -19,6 +19,7 @@
 // (tools/exp/fp_probe: 3.1-3.4 FMUL/FADD warp-instructions per cycle per SM), not HBM bound.
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "common.h"
 
@@ -562,11 +563,20 @@ cudaError_t launch_tc(const float* in, float* out, float* st, const float* nfc, 
 
 using namespace mpeghb200;
 
+namespace mpeghb200 {
+// hoa_render_umma.cu: the contraction on tcgen05 / TMEM
+void umma_prepare_b(const float* M, int n_out, int n_coef, float* terms);
+size_t umma_b_bytes();
+cudaError_t hoa_render_umma_launch(const float* d_in, float* d_out, const void* d_b, int n_coef, int n_out, int clip,
+                                   int n_streams, int sm_count, cudaStream_t st);
+}  // namespace mpeghb200
+
 struct mpeghb200_hoa_renderer {
   mpeghb200_ctx* ctx = nullptr;
   HoaParams P{};
   float* d_nfc = nullptr;  // [n_coef][17]
-  bool tensor = false;     // 3xTF32 mma.sync contraction instead of the bit-exact one
+  int tensor = 0;          // 0: bit-exact fp32; 1: legacy mma.sync 3xTF32; 2: tcgen05 + TMEM, exact 3-term TF32 split
+  void* d_umma_b = nullptr;
 };
 
 extern "C" {
@@ -613,12 +623,27 @@ void mpeghb200_hoa_renderer_destroy(mpeghb200_hoa_renderer* r) {
   if (!r) return;
   cudaSetDevice(r->ctx->device);
   cudaFree(r->d_nfc);
+  cudaFree(r->d_umma_b);
   delete r;
 }
 
 mpeghb200_status mpeghb200_hoa_renderer_set_tensor_mode(mpeghb200_hoa_renderer* r, int on) {
   if (!r) return MPEGHB200_ERR_BAD_ARG;
-  r->tensor = on != 0;
+  if (on < 0 || on > 2) return fail(r->ctx, MPEGHB200_ERR_BAD_ARG, "hoa_renderer_set_tensor_mode: mode 0, 1 or 2");
+  if (on == 2) {
+    if (r->P.use_nfc || r->P.n_coef > 32 || r->P.n_out > 32)
+      return fail(r->ctx, MPEGHB200_ERR_UNSUPPORTED,
+                  "hoa_renderer_set_tensor_mode(2): the tcgen05 contraction covers NFC-off renderers of order <= 4 "
+                  "(25 coefficients) to at most 32 loudspeakers");
+    if (!r->d_umma_b) {
+      MB_CUDA(r->ctx, cudaSetDevice(r->ctx->device));
+      std::vector<float> terms(umma_b_bytes() / sizeof(float));
+      umma_prepare_b(r->P.M, r->P.n_out, r->P.n_coef, terms.data());
+      MB_CUDA(r->ctx, cudaMalloc(&r->d_umma_b, umma_b_bytes()));
+      MB_CUDA(r->ctx, cudaMemcpy(r->d_umma_b, terms.data(), umma_b_bytes(), cudaMemcpyHostToDevice));
+    }
+  }
+  r->tensor = on;
   return MPEGHB200_OK;
 }
 
@@ -636,6 +661,12 @@ mpeghb200_status mpeghb200_hoa_render_dev(mpeghb200_ctx* ctx, const mpeghb200_ho
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   const HoaParams& P = r->P;
   cudaError_t e;
+  if (r->tensor == 2) {
+    e = hoa_render_umma_launch(d_in, d_out, r->d_umma_b, P.n_coef, P.n_out, P.clip, n_streams, ctx->sm_count, st);
+    ctx->launches.fetch_add(1);
+    MB_CUDA(ctx, e);
+    return MPEGHB200_OK;
+  }
   if (r->tensor) {
     switch (P.n_coef) {
       case 4: e = launch_tc<4>(d_in, d_out, d_nfc_state, r->d_nfc, P, n_streams, st); break;

@@ -20,7 +20,7 @@ class DevHoa:
         self.n_out, self.n_coef = M.shape
         self.h = lib.hoa_renderer_create(M, nfc)
         if tensor:
-            lib.hoa_renderer_set_tensor_mode(self.h, 1)
+            lib.hoa_renderer_set_tensor_mode(self.h, int(tensor))
         self.state = torch.zeros(max(1, n_streams * lib.hoa_nfc_state_floats(self.h)), device="cuda")
 
     def run(self, x):
@@ -170,3 +170,70 @@ def test_tensor_mode_full_size(gpu_lib, oracle):
     for s in rng.choice(S, 10, replace=False):
         want = loader.oracle_hoa_render(M, x[s], nfc, np.zeros((25, 14), np.float32))
         assert float(np.abs(out[s].astype(np.float64) - want).max()) <= TOL_FLOAT, s
+
+
+# ---- tcgen05 / TMEM contraction (tensor mode 2): exact three-term TF32 split, +-1 LSB at 24 bit ----
+UMMA_CFGS = [c for c in hoa_cases.CONFIGS if c[3] == 0 and (c[1] + 1) ** 2 <= 32]
+
+
+@pytest.mark.parametrize("cfg", UMMA_CFGS, ids=hoa_cases.key)
+def test_umma_mode_vs_oracle(gpu_lib, oracle, cfg):
+    """NFC-off renderers through tcgen05.mma kind::tf32 with the exact hi/mid/lo split of both operands: max |err|
+    within a few ulp of the result (gate: 2^-20 of full scale / 8 = one 24-bit LSB) and the 24-bit PCM (truncation of 256 v,
+    decoder/ia_core_coder_decode_main.c:247-261) within +-1 LSB -- north_star's gate for the tensor-core
+    contraction -- on programme-level signals (hoa_cases: sigma 2000, omni x 3); the 60 x over-driven frame checks the
+    clip."""
+    g = np.load(GOLD)
+    k = hoa_cases.key(cfg)
+    M = g[k + "_M"]
+    rng = np.random.default_rng(cfg[0] * 31 + cfg[1])
+    S, F = 9, 4
+    x = np.stack([hoa_cases.hoa_signal(rng, F, M.shape[1]) for _ in range(S)], axis=1)
+    r = DevHoa(gpu_lib, M, None, S, tensor=2)
+    worst = worst_lsb = 0.0
+    for f in range(F):
+        got = r.run(x[f])
+        for s in range(S):
+            want = loader.oracle_hoa_render(M, x[f, s], None, None)
+            assert np.isfinite(got[s]).all()
+            over = max(1.0, float(np.abs(x[f, s]).max()) / 32768.0)
+            err = float(np.abs(got[s].astype(np.float64) - want).max())
+            assert err <= TOL_FLOAT / 8 * over, (k, f, s, err, over)
+            if over == 1.0:
+                worst = max(worst, err)
+                lsb = np.abs(np.trunc(got[s].astype(np.float64) * 256) - np.trunc(want.astype(np.float64) * 256))
+                worst_lsb = max(worst_lsb, float(lsb.max()))
+    r.close()
+    print(f"tcgen05 mode {k}: max |err| = {worst:.3e} (float gate {TOL_FLOAT:.3e}), 24-bit PCM within {worst_lsb:.0f} LSB")
+    assert worst_lsb <= 1.0
+
+
+def test_umma_mode_full_size_and_limits(gpu_lib, oracle):
+    """BASELINE config 3 shape (order 4 -> 22.2, 1024 streams) without NFC through the tcgen05 contraction: stream
+    independence under permutation (bit-exact: same code per tile), spot checks within +-1 LSB at 24 bit, and the
+    mode is refused where it does not apply (NFC on, order > 4)."""
+    from libmpegh_b200.lib import MpeghError
+    g = np.load(GOLD)
+    k = hoa_cases.key(hoa_cases.CONFIGS[1])
+    M = g[k + "_M"]
+    rng = np.random.default_rng(2346)
+    S = 1024
+    x = rng.normal(0, 2000.0, size=(S, 25, 1024)).astype(np.float32)
+    r = DevHoa(gpu_lib, M, None, S, tensor=2)
+    out = r.run(x)
+    r.close()
+    perm = rng.permutation(S)
+    r2 = DevHoa(gpu_lib, M, None, S, tensor=2)
+    out_p = r2.run(x[perm])
+    r2.close()
+    assert bits_equal(out_p, out[perm])
+    for s in rng.choice(S, 12, replace=False):
+        want = loader.oracle_hoa_render(M, x[s], None, None)
+        lsb = np.abs(np.trunc(out[s].astype(np.float64) * 256) - np.trunc(want.astype(np.float64) * 256))
+        assert float(lsb.max()) <= 1.0, s
+    k0 = hoa_cases.key(hoa_cases.CONFIGS[0])
+    with pytest.raises(MpeghError):
+        DevHoa(gpu_lib, g[k0 + "_M"], g[k0 + "_nfc"], 1, tensor=2)      # NFC on
+    k6 = hoa_cases.key(hoa_cases.CONFIGS[5])
+    with pytest.raises(MpeghError):
+        DevHoa(gpu_lib, g[k6 + "_M"], None, 1, tensor=2)                # order 6: 49 coefficients

@@ -291,7 +291,7 @@ def hoa_render_stage():
     import hoa_cases  # noqa: E402
     g = np.load(os.path.join(ROOT, "tests", "golden", "hoa_ren_golden.npz"))
     k = hoa_cases.key(hoa_cases.CONFIGS[0])
-    for use_nfc, tensor in ((1, 0), (0, 0), (1, 1), (0, 1)):
+    for use_nfc, tensor in ((1, 0), (0, 0), (1, 1), (0, 1), (0, 2)):
         S = 1024
         h = lib.hoa_renderer_create(g[k + "_M"], g[k + "_nfc"] if use_nfc else None)
         lib.hoa_renderer_set_tensor_mode(h, tensor)
@@ -299,7 +299,7 @@ def hoa_render_stage():
         hout = torch.empty(S, 24, 1024, device="cuda")
         hst = torch.zeros(S * 25 * 14, device="cuda")
         ms = timeit(lambda i: lib.hoa_render_dev(h, hin.data_ptr(), hout.data_ptr(), hst.data_ptr(), S, st))
-        report(f"hoa_render order 4 -> 22.2, 1024 streams, nfc={use_nfc}" + (", tensor mode (3xTF32 mma)" if tensor else ""), ms, S * (25 + 24) * 4096, S * 24 * 1024,
+        report(f"hoa_render order 4 -> 22.2, 1024 streams, nfc={use_nfc}" + (["", ", tensor mode 1 (mma.sync 3xTF32)", ", tensor mode 2 (tcgen05 + TMEM, exact split)"][tensor]), ms, S * (25 + 24) * 4096, S * 24 * 1024,
                "output_channel_samples", {"fp32_unfused_Gops": S * 24 * 25 * 1024 * 2 / (ms * 1e-3) / 1e9})
         lib.hoa_renderer_destroy(h)
 
