@@ -38,9 +38,10 @@ constexpr int kKSteps = kK / 8;              // tf32: K = 8 per instruction
 constexpr int kABytes = kTileM * kK * 4;     // one split term of the A tile: 16 KB
 constexpr int kBBytes = kN * kK * 4;         // one split term of B: 4 KB
 constexpr int kBStep = 3 * kN * 8 * 4;       // one k step of the stacked B operand [hi | mid | lo] (96 rows x 8): 3072 B
-constexpr int kTmemCols = 256;               // accumulators: 96 + 64 + 32 columns (allocations are powers of two)
+constexpr int kTmemCols = 128;               // one accumulator set of 96 columns (allocations are powers of two)
 constexpr int kThreads = 256;               // 8 warps: warps w and w + 4 share the TMEM lanes 32 (w % 4) ..
-constexpr int kSmem = 2 * 3 * kABytes + 3 * kBBytes + 64;  // two A stages: 108.6 KB, 2 CTAs per SM
+constexpr int kATerms = 2;                   // A terms staged: x = hi + mid to within 2^-24 |x| (round-to-nearest split)
+constexpr int kSmem = kATerms * kABytes + 3 * kBBytes + 64;  // 44 KB: 4 CTAs per SM
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -85,7 +86,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
-__device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+// round to the nearest TF32 value (11 significant bits; the low 13 mantissa bits of the result are zero)
+__device__ __forceinline__ float tf32_rn(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
 
 // B: the three exact TF32 terms of the padded render matrix in the canonical K-major layout, prepared on the host
 struct UmmaB {
@@ -96,53 +102,58 @@ struct UmmaB {
 // lane -> (m % 8, k % 4): a warp's store covers 32 distinct banks, its load 4 coefficient rows x 32 contiguous bytes.
 // Work item (coefficient quad kq, group of 8 samples g): warp w takes g = w + kWarps * i, so that every address is a
 // per-thread base plus a compile-time constant.
-__device__ __forceinline__ void stage_tile(unsigned char* sA, const float* __restrict__ x, int n_coef, int warp, int lane) {
+constexpr int kWarps = kThreads / 32;
+constexpr int kG = (kTileM / 8) / kWarps;  // sample groups per warp: 2
+constexpr int kQ = kK / 4;                 // coefficient quads: 8
+
+__device__ __forceinline__ void stage_load(float (&v)[kQ * kG], const float* __restrict__ x, int n_coef, int warp, int lane) {
   const int lm = lane >> 2, lk = lane & 3;
-  constexpr int kWarps = kThreads / 32;
-  constexpr int kG = (kTileM / 8) / kWarps;  // sample groups per warp: 2
-  constexpr int kQ = kK / 4;                 // coefficient quads: 8
   const float* xt = x + size_t(lk) * kFrame + 8 * warp + lm;
-  unsigned char* st = sA + lm * 16 + lk * 4 + warp * 256;
-  float v[kQ * kG];
 #pragma unroll
   for (int kq = 0; kq < kQ; ++kq)
 #pragma unroll
     for (int i = 0; i < kG; ++i)
       v[kq * kG + i] = (4 * kq + lk < n_coef) ? __ldg(xt + size_t(4 * kq) * kFrame + 8 * kWarps * i) : 0.0f;
+}
+
+__device__ __forceinline__ void stage_store(unsigned char* sA, const float (&v)[kQ * kG], int n_coef, int warp, int lane) {
+  const int lm = lane >> 2, lk = lane & 3;
+  unsigned char* st = sA + lm * 16 + lk * 4 + warp * 256;
 #pragma unroll
   for (int kq = 0; kq < kQ; ++kq) {
     if (4 * kq < n_coef) {  // quads beyond the coefficient count stay at their initial zeros
 #pragma unroll
       for (int i = 0; i < kG; ++i) {
         const float a = v[kq * kG + i];
-        const float hi = tf32_trunc(a);
-        const float r = __fsub_rn(a, hi);  // exact
-        const float mid = tf32_trunc(r);
-        const float lo = __fsub_rn(r, mid);  // exact, <= 2 significant bits
+        // round-to-nearest split: |a - hi| <= 2^-12 |a|, |a - hi - mid| <= 2^-24 |a| -- two TF32 terms carry the whole
+        // fp32 value to within half an ulp (a truncating split would need three)
+        const float hi = tf32_rn(a);
+        const float mid = tf32_rn(__fsub_rn(a, hi));
         unsigned char* q = st + (kq & 1) * 128 + (kWarps * i) * 256 + (kq >> 1) * 4096;
         *reinterpret_cast<float*>(q) = hi;
         *reinterpret_cast<float*>(q + kABytes) = mid;
-        *reinterpret_cast<float*>(q + 2 * kABytes) = lo;
       }
     }
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+// FAST: n_out == 24 and clip on (the path's own configuration: no per-output predicates, immediate store offsets)
+template <bool FAST>
+__global__ void __launch_bounds__(kThreads, 4)
     hoa_render_umma_kernel(const float* __restrict__ in, float* __restrict__ out, const UmmaB* __restrict__ Bg, int n_coef,
                            int n_out, int clip, int n_tiles) {
   pdl_prologue();
   extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char* sA = smem;                          // [2 stages][3 terms][kKSteps][4096 B]
-  unsigned char* sB = smem + 2 * 3 * kABytes;        // [kKSteps][96 rows x 8: 3072 B], terms stacked along N
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + 3 * kBBytes);
+  unsigned char* sA = smem;                          // [2 terms][kKSteps][4096 B]
+  unsigned char* sB = smem + kATerms * kABytes;      // [kKSteps][96 rows x 8: 3072 B], terms stacked along N
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + 3 * kBBytes);  // the MMAs of the staged tile completed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // ---- one-time set-up: B terms, zero padding of A (coefficients >= n_coef are never written), barrier, TMEM ----
   for (int i = tid; i < 3 * kBBytes / 16; i += kThreads)
     reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(Bg) + i);
-  for (int i = tid; i < 2 * 3 * kABytes / 16; i += kThreads) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < kATerms * kABytes / 16; i += kThreads) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -158,78 +169,80 @@ __global__ void __launch_bounds__(kThreads, 2)
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *tmem_slot;
   const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
-  uint32_t phase = 0;
   auto tile_x = [&](int tile) { return in + size_t(tile >> 3) * n_coef * kFrame + (tile & 7) * kTileM; };
 
-  int tile = blockIdx.x, buf = 0;
-  if (tile < n_tiles) stage_tile(sA, tile_x(tile), n_coef, warp, lane);
-  for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
-    // the staged tile (generic-proxy writes) -> visible to the tensor core's async proxy; the previous epilogue's TMEM
-    // loads are behind this barrier too
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  // One CTA keeps one tile in flight (stage -> MMA -> epilogue); four CTAs per SM overlap each other's phases, and the
+  // global loads of a CTA's next tile are issued before it waits for its MMAs.
+  float v[kQ * kG];
+  uint32_t phase = 0;
+  int tile = blockIdx.x;
+  if (tile < n_tiles) stage_load(v, tile_x(tile), n_coef, warp, lane);
+  for (; tile < n_tiles; tile += gridDim.x) {
+    stage_store(sA, v, n_coef, warp, lane);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staged tile -> visible to the async proxy
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // The six products that matter as THREE independent accumulator chains, the B terms stacked along N:
-      //   D1[128 x 96] = A_hi  * [B_hi | B_mid | B_lo]     columns   0 ..  95
-      //   D2[128 x 64] = A_mid * [B_hi | B_mid]            columns  96 .. 159
-      //   D3[128 x 32] = A_lo  * [B_hi]                    columns 160 .. 191
-      // (back-to-back MMAs into ONE accumulator serialise on its latency: 24 dependent N = 32 MMAs cost ~10 k cycles
-      // per tile, measured; three chains of four do not)
-      const uint32_t a_stage = a_base + buf * 3 * kABytes;
+      // x = hi + mid to half an ulp (round-to-nearest split), M = hi + mid + lo exactly.  Two MMAs per k step,
+      // the B terms stacked along N; the second MMA's columns overlap the first's so that products of equal magnitude
+      // share an accumulator:
+      //   D[:,  0: 96] (+)= A_hi  * [B_hi | B_mid | B_lo]      -> hi*hi | hi*mid | hi*lo
+      //   D[:, 32: 96]  += A_mid * [B_hi | B_mid]                        + mid*hi | + mid*mid
 #pragma unroll
       for (int ks = 0; ks < kKSteps; ++ks) {
         // K-major, no swizzle: LBO = the two 16-byte K halves of a core-matrix pair (128 B), SBO = 8-row groups (256 B)
         const uint64_t bd = umma_desc(b_base + ks * kBStep, 128, 256);
-        umma_tf32(tmem_d, umma_desc(a_stage + ks * 4096, 128, 256), bd, idesc_n(96), ks > 0);
-        umma_tf32(tmem_d + 96, umma_desc(a_stage + kABytes + ks * 4096, 128, 256), bd, idesc_n(64), ks > 0);
-        umma_tf32(tmem_d + 160, umma_desc(a_stage + 2 * kABytes + ks * 4096, 128, 256), bd, idesc_n(32), ks > 0);
+        umma_tf32(tmem_d, umma_desc(a_base + ks * 4096, 128, 256), bd, idesc_n(96), ks > 0);
+        umma_tf32(tmem_d + 32, umma_desc(a_base + kABytes + ks * 4096, 128, 256), bd, idesc_n(64), 1);
       }
       // arrives on the barrier when every MMA above has completed (implies tcgen05.fence::before_thread_sync)
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                    : "memory");
     }
-    // while the tensor core works on this tile, the CUDA cores split the next one into the other stage
     const int next = tile + gridDim.x;
-    if (next < n_tiles) stage_tile(sA + (buf ^ 1) * 3 * kABytes, tile_x(next), n_coef, warp, lane);
+    if (next < n_tiles) stage_load(v, tile_x(next), n_coef, warp, lane);
     mbar_wait(bar, phase);
     phase ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // ---- epilogue: D row m = TMEM lane m; warps w and w + 4 own lanes 32 (w % 4) .. + 31 and take alternate groups
-    //      of four outputs.  The six partial products of an output are summed in fp32, smallest first, clipped,
-    //      stored ----
-    const int m = (warp & 3) * 32 + lane;
-    const uint32_t taddr = tmem_d + (uint32_t((warp & 3) * 32) << 16);
-    float* y = out + size_t(tile >> 3) * n_out * kFrame + (tile & 7) * kTileM + m;
-    for (int c0 = 4 * (warp >> 2); c0 < n_out; c0 += 8) {
-      uint32_t q[6][4];
-      // column offsets of (lo,hi) (hi,lo) (mid,mid) (mid,hi) (hi,mid) (hi,hi)
-      const uint32_t col[6] = {160u, 64u, 96u + 32u, 96u, 32u, 0u};
+    // ---- epilogue: D row m = TMEM lane m; warps w and w + 4 own lanes 32 (w % 4) .. + 31 and take alternate groups of
+    //      four outputs.  Columns [0, 32) hold hi*hi, [32, 64) hi*mid + mid*hi, [64, 96) hi*lo + mid*mid: summed in
+    //      fp32, smallest first, clipped, stored ----
+    {
+      const int m = (warp & 3) * 32 + lane;
+      const int c_first = 4 * (warp >> 2);
+      const uint32_t taddr = tmem_d + (uint32_t((warp & 3) * 32) << 16) + uint32_t(c_first);
+      float* y = out + size_t(tile >> 3) * n_out * kFrame + (tile & 7) * kTileM + m + size_t(c_first) * kFrame;
+      uint32_t q[3][3][4];
 #pragma unroll
-      for (int p = 0; p < 6; ++p)
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(q[p][0]), "=r"(q[p][1]), "=r"(q[p][2]), "=r"(q[p][3])
-                     : "r"(taddr + col[p] + uint32_t(c0))
-                     : "memory");
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(q[c][p][0]), "=r"(q[c][p][1]), "=r"(q[c][p][2]), "=r"(q[c][p][3])
+                       : "r"(taddr + uint32_t(64 - 32 * p + 8 * c))
+                       : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int n_left = n_out - c_first;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (c0 + j < n_out) {
-          float val = __uint_as_float(q[0][j]);
+      for (int c = 0; c < 3; ++c)
 #pragma unroll
-          for (int p = 1; p < 6; ++p) val = __fadd_rn(val, __uint_as_float(q[p][j]));
-          if (clip) {
-            val = (val < 32767.0f) ? val : 32767.0f;
-            val = (val > -32768.0f) ? val : -32768.0f;
+        for (int j = 0; j < 4; ++j) {
+          if (FAST || 8 * c + j < n_left) {
+            float val = __fadd_rn(__fadd_rn(__uint_as_float(q[c][0][j]), __uint_as_float(q[c][1][j])),
+                                  __uint_as_float(q[c][2][j]));
+            if (FAST || clip) {
+              val = (val < 32767.0f) ? val : 32767.0f;
+              val = (val > -32768.0f) ? val : -32768.0f;
+            }
+            __stcs(y + (8 * c + j) * kFrame, val);
           }
-          __stcs(y + size_t(c0 + j) * kFrame, val);
         }
-      }
     }
+    // the accumulator and the A stage are free again once every warp has its results in registers
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
   }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
   if (warp == 0) {
     const uint32_t n_cols = kTmemCols;
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(n_cols) : "memory");
@@ -266,11 +279,13 @@ size_t umma_b_bytes() { return sizeof(UmmaB); }
 cudaError_t hoa_render_umma_launch(const float* d_in, float* d_out, const void* d_b, int n_coef, int n_out, int clip,
                                    int n_streams, int sm_count, cudaStream_t st) {
   if (n_coef > kK || n_out > kN) return cudaErrorInvalidValue;
-  cudaError_t e = cudaFuncSetAttribute(hoa_render_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+  const bool fast = n_out == 24 && clip;
+  auto kern = fast ? hoa_render_umma_kernel<true> : hoa_render_umma_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
   if (e != cudaSuccess) return e;
   const int n_tiles = n_streams * (kFrame / kTileM);
-  const int grid = n_tiles < 2 * sm_count ? n_tiles : 2 * sm_count;  // 2 CTAs per SM (108 KB of shared memory, 256 TMEM columns each)
-  return launch_pdl(hoa_render_umma_kernel, dim3(grid), dim3(kThreads), size_t(kSmem), st, d_in, d_out,
+  const int grid = n_tiles < 4 * sm_count ? n_tiles : 4 * sm_count;  // 4 CTAs per SM: 4 x 44 KB of shared memory, 4 x 128 = all 512 TMEM columns
+  return launch_pdl(kern, dim3(grid), dim3(kThreads), size_t(kSmem), st, d_in, d_out,
                     static_cast<const UmmaB*>(d_b), n_coef, n_out, clip, n_tiles);
 }
 
