@@ -310,6 +310,32 @@ def cpu_chain_baseline(spec, n_threads, sample_streams, n_frames, repeats=1):
             "ms_per_unit": t / units * 1e3, "audio_s_per_wall_s": S * n_frames * repeats * 1024 / 48000.0 / t}
 
 
+def cpu_testbench_baseline(n_proc, repeats=8):
+    """BASELINE.json configs[0]: the UNMODIFIED reference testbench (oracle/_ref/ia_mpeghd_testbench, built from
+    /root/reference by oracle/Makefile) decoding smoke_test_suite/inp/sine_1khz_000_cicp1.mhas on the host cores, one
+    process per core, `repeats` decodes each.  None when the build did not travel."""
+    tb = os.path.join(ROOT, "oracle", "_ref", "ia_mpeghd_testbench")
+    stream = os.path.join(ROOT, "oracle", "_ref", "smoke", "sine_1khz_000_cicp1.mhas")
+    if not (os.path.exists(tb) and os.path.exists(stream)):
+        return None
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        cmd = "for i in $(seq %d); do %s -ifile:%s -ofile:%s/o_$$.wav > /dev/null 2>&1 || exit 1; done" % (
+            repeats, tb, stream, tmp)
+        subprocess.run(["sh", "-c", cmd.replace("seq %d" % repeats, "seq 1")], check=False)  # page the binary in
+        t0 = time.perf_counter()
+        procs = [subprocess.Popen(["sh", "-c", cmd]) for _ in range(n_proc)]
+        rcs = [p.wait() for p in procs]
+        dt = time.perf_counter() - t0
+    if any(rcs):
+        return None
+    audio_s = n_proc * repeats * 469 * 1024 / 48000.0   # 469 output frames of one channel per decode
+    return {"workload": "configs[0]: sine_1khz_000_cicp1.mhas through the unmodified ia_mpeghd_testbench (parse + "
+                        "signal path + WAV write), one process per host core",
+            "processes": n_proc, "decodes_per_process": repeats, "wall_s": dt, "audio_s_per_wall_s": audio_s / dt,
+            "value": audio_s * 48000.0 / dt, "unit": UNIT, "kind": "reference"}
+
+
 # bounded CPU samples: (streams per thread, frames) sized for about a second of work per thread
 CPU_SAMPLE = {"hoa": (2, 24), "binaural": (1, 32), "objects": (4, 48), "fd_4096": (4, 48), "fd": (16, 200)}
 
@@ -362,6 +388,7 @@ def reference_arm(args, rank):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    line["configs0_cpu_testbench"] = cpu_testbench_baseline(n_threads)
     if not args.no_configs:
         line["configs"] = {}
         for name in CHAIN_CONFIGS:
@@ -767,6 +794,7 @@ def main():
             fd.name = "fd"
             per, frames = CPU_SAMPLE["fd"]
             line["cpu_baseline"] = cpu_chain_baseline(fd, 1, per, frames)
+            line["configs0_cpu_testbench"] = cpu_testbench_baseline(cpu_threads())
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     lib.close()

@@ -144,12 +144,16 @@ mpeghb200_status mpeghb200_pcm_pack_dev(mpeghb200_ctx *ctx, const float *d_in, i
                                         const int32_t *out_ch_map, int32_t *d_delay, uint8_t *d_out,
                                         int32_t *d_out_bytes, int n_streams, void *cuda_stream);
 
-/* Limiter and packer fused (what a chain's tail runs): the limited samples never make the planar fp32 round trip
- * through HBM.  Arguments as the two calls above; results identical to mpeghb200_limiter_dev followed by
- * mpeghb200_pcm_pack_dev. */
+/* Limiter and packer together (what a chain's tail runs): a gains kernel (one CTA per stream: channel maxima, sliding
+ * maximum, the serial smoother) and an apply-and-pack kernel (delayed sample x gain, clip, PCM bytes; four CTAs per
+ * stream) -- the limited samples never make the planar fp32 round trip through HBM and the data-parallel half of the
+ * limiter is not tied to the smoother's one CTA per stream.  d_scratch [n_streams *
+ * mpeghb200_limiter_pack_scratch_floats] (gains + the previous delay line).  Other arguments as the two calls above;
+ * results identical to mpeghb200_limiter_dev followed by mpeghb200_pcm_pack_dev. */
+size_t mpeghb200_limiter_pack_scratch_floats(const mpeghb200_limiter_params *p);
 mpeghb200_status mpeghb200_limiter_pack_dev(mpeghb200_ctx *ctx, const mpeghb200_limiter_params *p, const float *d_in,
-                                            float *d_state, const float *d_loudness_gain, int pcm_bits,
-                                            const int32_t *out_ch_map, int32_t *d_delay, uint8_t *d_pcm,
+                                            float *d_state, float *d_scratch, const float *d_loudness_gain,
+                                            int pcm_bits, const int32_t *out_ch_map, int32_t *d_delay, uint8_t *d_pcm,
                                             int32_t *d_pcm_bytes, int n_streams, void *cuda_stream);
 
 /* The same for a block of n_samples per channel (a multiple of 256) whose channels lie ch_stride floats apart:

@@ -43,6 +43,7 @@ struct mpeghb200_chain {
   float* d_fc_state = nullptr;
   float* d_bin_state = nullptr;
   float* d_lim_state = nullptr;
+  float* d_lim_scratch = nullptr;
   float* d_gain = nullptr;
   int32_t* d_delay = nullptr;
   int32_t* d_bin_set = nullptr;
@@ -57,10 +58,11 @@ struct mpeghb200_chain {
   float* d_binout = nullptr;   // [S][2][block_len]
   float* d_limout = nullptr;   // [S][n_out][1024]
   int ring_pos = 0;            // frames of the current binaural block already stored
-  // limiter + packer as ONE kernel (MPEGHB200_CHAIN_FUSED_TAIL=1).  Off by default: measured on B200 the fused tail is
-  // slower (config 3: 221 vs 159 us, config 5: 0.190 vs 0.156 ms per step) -- both kernels are latency-bound single
-  // waves of one CTA per stream, and the separate packer spreads its byte shuffling over 4 x more CTAs than the
-  // limiter's 128 threads per stream can; the fp32 round trip it saves is not what bounds the step.
+  // The tail as mpeghb200_limiter_dev + mpeghb200_pcm_pack_dev (default) or as limiter gains kernel + apply-and-pack
+  // kernel (MPEGHB200_CHAIN_FUSED_TAIL=1).  Measured equal on B200 (config 3: 0.400 vs 0.414 ms per step, config 5:
+  // 0.161 vs 0.162): ncu of the gains kernel (profiles/r2_limiter_gains_ncu.json) puts 46 % of its 63 us on the global
+  // loads of the channel maxima and 32 % on the barrier behind the serial smoother -- the output phase the split moves
+  // out was never the cost.  (A single fused kernel, one CTA per stream, was slower than both.)
   bool fused_tail = false;
   std::vector<void*> owned;
 
@@ -174,8 +176,8 @@ mpeghb200_status run_frame(mpeghb200_chain* c, float* core, const uint32_t* fd_s
     return mpeghb200_pcm_pack_dev(ctx, c->d_limout, c->n_out, d.pcm_bits, c->has_map ? c->ch_map : nullptr, c->d_delay,
                                   pcm, pcm_bytes, S, st);
   }
-  if (d.limiter)  // limiter and packer in one pass: no planar fp32 round trip between them
-    return mpeghb200_limiter_pack_dev(ctx, &c->lim, mix, c->d_lim_state, c->d_gain, d.pcm_bits,
+  if (d.limiter)  // gains kernel + apply-and-pack kernel: no planar fp32 round trip between limiter and packer
+    return mpeghb200_limiter_pack_dev(ctx, &c->lim, mix, c->d_lim_state, c->d_lim_scratch, c->d_gain, d.pcm_bits,
                                       c->has_map ? c->ch_map : nullptr, c->d_delay, pcm, pcm_bytes, S, st);
   return mpeghb200_pcm_pack_dev(ctx, mix, c->n_out, d.pcm_bits, c->has_map ? c->ch_map : nullptr, c->d_delay, pcm,
                                 pcm_bytes, S, st);
@@ -328,6 +330,7 @@ mpeghb200_status mpeghb200_chain_open(mpeghb200_ctx* ctx, const mpeghb200_chain_
     if (ok()) st = mpeghb200_limiter_state_init_dev(ctx, &c->lim, c->d_lim_state, S, c->comp);
     if (const char* ev = getenv("MPEGHB200_CHAIN_FUSED_TAIL")) c->fused_tail = atoi(ev) != 0;
     if (ok() && !c->fused_tail) e = dalloc(c, &c->d_limout, size_t(S) * c->n_out * 1024, false);
+    if (ok() && c->fused_tail) e = dalloc(c, &c->d_lim_scratch, S * mpeghb200_limiter_pack_scratch_floats(&c->lim), false);
     if (ok() && d.loudness_gain != 1.0f) {
       e = dalloc(c, &c->d_gain, size_t(S), false);
       if (ok()) fill_kernel<<<(S + 255) / 256, 256, 0, c->comp>>>(c->d_gain, d.loudness_gain, S);

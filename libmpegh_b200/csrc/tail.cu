@@ -298,11 +298,45 @@ __global__ void __launch_bounds__(kPackSamples)
   }
 }
 
-// ---- limiter + PCM packer in one pass -----------------------------------------------------------------
-// The chain's tail (limiter -> packer) without the planar fp32 round trip through HBM: the limited samples go from
-// registers through a 128-sample byte tile straight into the interleaved PCM record.  Same arithmetic as the two
-// kernels above, node for node.
-constexpr int kLpChunk = kLimThreads;  // samples per PCM tile: one per thread
+// ---- limiter + PCM packer as a gains kernel and an apply-and-pack kernel -------------------------------
+// The chain's tail without the planar fp32 round trip between limiter and packer, and without tying the data-parallel
+// part of the limiter (delayed samples x gain, clip) to the one CTA per stream that the serial smoother needs:
+//   limiter_gains_kernel       one CTA per stream: steps 1 - 4 (channel maxima, sliding maximum, raw gain, smoother),
+//                              writes the 1024 gains, hands the OLD delay line to the apply kernel and stores the new
+//   limiter_apply_pack_kernel  four CTAs per stream (256 samples each): delayed sample x gain, clip, PCM conversion,
+//                              byte tile, coalesced store -- the packer's structure with the limiter's step 5 in front
+// Same arithmetic as limiter_kernel + pcm_pack_kernel, node for node.
+__global__ void __launch_bounds__(kLimThreads)
+    limiter_gains_kernel(const float* __restrict__ in, float* __restrict__ state, const float* __restrict__ loud_gain,
+                         float* __restrict__ gains, float* __restrict__ dl_old, const LimParams P) {
+  pdl_prologue();
+  __shared__ __align__(16) float m[kMaxAttack + kFrame + 16];
+  __shared__ __align__(16) float m2[kMaxAttack + kFrame + 16];
+  __shared__ __align__(16) float g[kFrame];
+  const int tid = threadIdx.x;
+  const int A = P.attack;
+  const size_t sidx = blockIdx.x;
+  const float* x = in + sidx * size_t(P.n_ch) * kFrame;
+  float* st = state + sidx * size_t(P.stride);
+  float* st_delay = st + 4 + A;
+  const float lg = loud_gain ? __ldg(loud_gain + sidx) : 1.0f;
+  const bool has_lg = loud_gain != nullptr;
+  limiter_gains(x, st, P, lg, has_lg, m, m2, g);
+  float4* go = reinterpret_cast<float4*>(gains + sidx * kFrame);
+  for (int i = tid; i < kFrame / 4; i += kLimThreads) go[i] = reinterpret_cast<const float4*>(g)[i];
+  // delay line: the old one goes to the apply kernel, the last A samples of this frame (with the loudness gain)
+  // become the new one; A is a multiple of 4
+  float* dlo = dl_old + sidx * size_t(P.n_ch) * A;
+  const int a4 = A / 4;
+  for (int i = tid; i < P.n_ch * a4; i += kLimThreads) {
+    const int c = i / a4, j = 4 * (i - c * a4);
+    float4* d = reinterpret_cast<float4*>(st_delay + size_t(c) * A + j);
+    *reinterpret_cast<float4*>(dlo + size_t(c) * A + j) = *d;
+    float4 t = __ldg(reinterpret_cast<const float4*>(x + size_t(c) * kFrame + kFrame - A + j));
+    if (has_lg) t = make_float4(fmul(t.x, lg), fmul(t.y, lg), fmul(t.z, lg), fmul(t.w, lg));
+    *d = t;
+  }
+}
 
 __device__ __forceinline__ int pcm_convert(float v, int bits) {
   if (bits == 24) {
@@ -325,110 +359,93 @@ __device__ __forceinline__ int pcm_convert(float v, int bits) {
   return (2147483647.0f < v) ? 0x7fffffff : sat_cast(v);
 }
 
-__global__ void __launch_bounds__(kLimThreads)
-    limiter_pack_kernel(const float* __restrict__ in, unsigned char* __restrict__ pcm, float* __restrict__ state,
-                        const float* __restrict__ loud_gain, int* __restrict__ delay, int* __restrict__ out_bytes,
-                        const LimParams P, const PackParams K) {
+__global__ void __launch_bounds__(kPackSamples)
+    limiter_apply_pack_kernel(const float* __restrict__ in, const float* __restrict__ gains, const float* __restrict__ dl_old,
+                              const float* __restrict__ loud_gain, unsigned char* __restrict__ out,
+                              int* __restrict__ delay, int* __restrict__ out_bytes, int attack, float thr,
+                              const PackParams P) {
   pdl_prologue();
-  __shared__ __align__(16) float m[kMaxAttack + kFrame + 16];
-  __shared__ __align__(16) float m2[kMaxAttack + kFrame + 16];
-  __shared__ __align__(16) float g[kFrame];
-  extern __shared__ __align__(16) unsigned char tile[];  // [kLpChunk][n_ch][bytes]
+  extern __shared__ __align__(16) unsigned char tile[];  // [kPackSamples][n_ch][bytes]
   const int tid = threadIdx.x;
-  const int A = P.attack;
-  const size_t sidx = blockIdx.x;
-  const float* x = in + sidx * size_t(P.n_ch) * kFrame;
-  float* st = state + sidx * size_t(P.stride);
-  float* st_delay = st + 4 + A;
+  const int chunk = blockIdx.x, sidx = blockIdx.y;
+  const int bps = P.bits >> 3;
+  const int frame_bytes = kFrame * P.n_ch * bps;
+  const float* x = in + size_t(sidx) * P.n_ch * kFrame;
+  const float* dlo = dl_old + size_t(sidx) * P.n_ch * attack;
+  const int d = delay ? delay[sidx] : 0;
+  const int s = chunk * kPackSamples + tid;
+  const float gi = __ldg(gains + size_t(sidx) * kFrame + s);
   const float lg = loud_gain ? __ldg(loud_gain + sidx) : 1.0f;
   const bool has_lg = loud_gain != nullptr;
-  const int d = delay ? delay[sidx] : 0;
-  limiter_gains(x, st, P, lg, has_lg, m, m2, g);
-
-  const float thr = P.thr;
-  const int bps = K.bits >> 3;
-  const int frame_bytes = kFrame * P.n_ch * bps;
-  const int tile_bytes = kLpChunk * P.n_ch * bps;
-  unsigned char* o = pcm + sidx * size_t(frame_bytes);
+  const int rec = P.n_ch * bps;
+  const bool words = (rec & 3) == 0;  // the sample's record is assembled in registers, one 32-bit store per 4 bytes
+  unsigned long long sh = 0;
+  int have = 0, wpos = 0;
+  unsigned* tw = reinterpret_cast<unsigned*>(tile + size_t(tid) * rec);
   constexpr int kBatch = 8;
-  const int rec = P.n_ch * bps;           // bytes of one interleaved sample
-  const bool words = (rec & 3) == 0;      // the sample's record is assembled in registers, one 32-bit store per 4 bytes
-  for (int q = 0; q < kFrame / kLpChunk; ++q) {
-    const int i = q * kLpChunk + tid;
-    const float gi = g[i];
-    unsigned long long sh = 0;            // byte shift register of the record under construction
-    int have = 0, wpos = 0;
-    unsigned* tw = reinterpret_cast<unsigned*>(tile + size_t(tid) * rec);
-    for (int ch0 = 0; ch0 < P.n_ch; ch0 += kBatch) {
-      float vin[kBatch];
+  for (int ch0 = 0; ch0 < P.n_ch; ch0 += kBatch) {
+    float vin[kBatch];
 #pragma unroll
-      for (int e = 0; e < kBatch; ++e) {
-        if (ch0 + e < P.n_ch) {
-          const int c = K.pos[ch0 + e];
-          if (i >= A) {
-            const float t = __ldg(x + size_t(c) * kFrame + i - A);
-            vin[e] = has_lg ? fmul(t, lg) : t;
-          } else {
-            vin[e] = st_delay[size_t(c) * A + i];  // already carries the loudness gain
-          }
+    for (int q = 0; q < kBatch; ++q) {
+      if (ch0 + q < P.n_ch) {
+        const int c = P.pos[ch0 + q];
+        if (s >= attack) {
+          const float t = __ldcs(x + size_t(c) * kFrame + s - attack);
+          vin[q] = has_lg ? fmul(t, lg) : t;
         } else {
-          vin[e] = 0.0f;
+          vin[q] = __ldcs(dlo + size_t(c) * attack + s);  // already carries the loudness gain
         }
-      }
-#pragma unroll
-      for (int e = 0; e < kBatch; ++e) {
-        const int ch = ch0 + e;
-        if (ch >= P.n_ch) break;
-        float v = vin[e];
-        if (gi >= 0.0f) {
-          v = fmul(v, gi);
-          if (thr < v)
-            v = thr;
-          else if (v < -thr)
-            v = -thr;
-        }
-        const unsigned w = static_cast<unsigned>(pcm_convert(v, K.bits));
-        if (words) {
-          const unsigned long long bytes = bps == 4 ? w : (w & ((1u << (8 * bps)) - 1u));
-          sh |= bytes << (8 * have);
-          have += bps;
-          if (have >= 4) {
-            tw[wpos++] = static_cast<unsigned>(sh);
-            sh >>= 32;
-            have -= 4;
-          }
-        } else {
-          unsigned char* t = tile + size_t(tid) * rec + ch * bps;
-          t[0] = w & 0xff;
-          t[1] = (w >> 8) & 0xff;
-          if (bps > 2) t[2] = (w >> 16) & 0xff;
-          if (bps > 3) t[3] = (w >> 24) & 0xff;
-        }
+      } else {
+        vin[q] = 0.0f;
       }
     }
-    __syncthreads();
-    const long long dst0 = (long long)(q * kLpChunk - d) * P.n_ch * bps;
-    if (dst0 >= 0 && (dst0 & 15) == 0 && (tile_bytes & 15) == 0) {
-      const uint4* t4 = reinterpret_cast<const uint4*>(tile);
-      uint4* o4 = reinterpret_cast<uint4*>(o + dst0);
-      for (int k = tid; k < tile_bytes / 16; k += kLimThreads) __stcs(o4 + k, t4[k]);
-    } else {
-      for (int k = tid; k < tile_bytes; k += kLimThreads) {
-        const long long p = dst0 + k;
-        if (p >= 0) o[p] = tile[k];
+#pragma unroll
+    for (int q = 0; q < kBatch; ++q) {
+      const int ch = ch0 + q;
+      if (ch >= P.n_ch) break;
+      float v = vin[q];
+      if (gi >= 0.0f) {
+        v = fmul(v, gi);
+        if (thr < v)
+          v = thr;
+        else if (v < -thr)
+          v = -thr;
+      }
+      const unsigned w = static_cast<unsigned>(pcm_convert(v, P.bits));
+      if (words) {
+        const unsigned long long bytes = bps == 4 ? w : (w & ((1u << (8 * bps)) - 1u));
+        sh |= bytes << (8 * have);
+        have += bps;
+        if (have >= 4) {
+          tw[wpos++] = static_cast<unsigned>(sh);
+          sh >>= 32;
+          have -= 4;
+        }
+      } else {
+        unsigned char* t = tile + size_t(tid) * rec + ch * bps;
+        t[0] = w & 0xff;
+        t[1] = (w >> 8) & 0xff;
+        if (bps > 2) t[2] = (w >> 16) & 0xff;
+        if (bps > 3) t[3] = (w >> 24) & 0xff;
       }
     }
-    __syncthreads();
   }
-  // the last A samples of the frame are the next frame's delay line (every read of the old one is behind a barrier)
-  for (int c = 0; c < P.n_ch; ++c)
-    for (int j = tid; j < A; j += kLimThreads) {
-      const float t = __ldg(x + size_t(c) * kFrame + kFrame - A + j);
-      st_delay[size_t(c) * A + j] = has_lg ? fmul(t, lg) : t;
+  __syncthreads();
+  const int tile_bytes = kPackSamples * P.n_ch * bps;
+  const long long dst0 = (long long)(chunk * kPackSamples - d) * P.n_ch * bps;
+  unsigned char* o = out + size_t(sidx) * frame_bytes;
+  if (dst0 >= 0 && (dst0 & 15) == 0 && (tile_bytes & 15) == 0) {
+    const uint4* t4 = reinterpret_cast<const uint4*>(tile);
+    uint4* o4 = reinterpret_cast<uint4*>(o + dst0);
+    for (int i = tid; i < tile_bytes / 16; i += kPackSamples) __stcs(o4 + i, t4[i]);
+  } else {
+    for (int i = tid; i < tile_bytes; i += kPackSamples) {
+      const long long p = dst0 + i;
+      if (p >= 0) o[p] = tile[i];
     }
-  if (tid == 0) {
+  }
+  if (chunk == 0 && tid == 0) {
     if (out_bytes) out_bytes[sidx] = (d <= kFrame) ? (kFrame - d) * P.n_ch * bps : 0;
-    if (delay) delay[sidx] = (d <= kFrame) ? 0 : d - kFrame;
   }
 }
 
@@ -504,16 +521,21 @@ mpeghb200_status mpeghb200_limiter_dev(mpeghb200_ctx* ctx, const mpeghb200_limit
   return MPEGHB200_OK;
 }
 
+size_t mpeghb200_limiter_pack_scratch_floats(const mpeghb200_limiter_params* p) {
+  return p ? size_t(kFrame) + size_t(p->n_ch) * p->attack_samples : 0;  // gains + the old delay line, per stream
+}
+
 mpeghb200_status mpeghb200_limiter_pack_dev(mpeghb200_ctx* ctx, const mpeghb200_limiter_params* p, const float* d_in,
-                                            float* d_state, const float* d_loudness_gain, int pcm_bits,
-                                            const int32_t* out_ch_map, int32_t* d_delay, uint8_t* d_pcm,
+                                            float* d_state, float* d_scratch, const float* d_loudness_gain,
+                                            int pcm_bits, const int32_t* out_ch_map, int32_t* d_delay, uint8_t* d_pcm,
                                             int32_t* d_pcm_bytes, int n_streams, void* cuda_stream) {
   if (!ctx || !p) return MPEGHB200_ERR_BAD_ARG;
   if (n_streams < 0 || (pcm_bits != 16 && pcm_bits != 24 && pcm_bits != 32) ||
-      (n_streams > 0 && (!d_in || !d_state || !d_pcm)))
+      (n_streams > 0 && (!d_in || !d_state || !d_scratch || !d_pcm)))
     return fail(ctx, MPEGHB200_ERR_BAD_ARG, "limiter_pack_dev: null buffer, bad sample size or negative stream count");
   if (n_streams == 0) return MPEGHB200_OK;
   MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   LimParams P;
   P.n_ch = p->n_ch;
   P.attack = p->attack_samples;
@@ -535,12 +557,24 @@ mpeghb200_status mpeghb200_limiter_pack_dev(mpeghb200_ctx* ctx, const mpeghb200_
       K.pos[m] = static_cast<unsigned char>(ch);
     }
   }
-  const size_t smem = size_t(kLpChunk) * p->n_ch * (pcm_bits >> 3);
-  MB_CUDA(ctx, launch_pdl(limiter_pack_kernel, dim3(n_streams), dim3(kLimThreads), smem,
-                          static_cast<cudaStream_t>(cuda_stream), d_in, d_pcm, d_state, d_loudness_gain, d_delay,
-                          d_pcm_bytes, P, K));
+  float* d_gains = d_scratch;
+  float* d_dl_old = d_scratch + size_t(n_streams) * kFrame;
+  MB_CUDA(ctx, launch_pdl(limiter_gains_kernel, dim3(n_streams), dim3(kLimThreads), 0, st, d_in, d_state, d_loudness_gain,
+                          d_gains, d_dl_old, P));
+  ctx->launches.fetch_add(1);
+  const size_t smem = size_t(kPackSamples) * p->n_ch * (pcm_bits >> 3);
+  if (smem > 48 * 1024)
+    MB_CUDA(ctx, cudaFuncSetAttribute(limiter_apply_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  MB_CUDA(ctx, launch_pdl(limiter_apply_pack_kernel, dim3(kFrame / kPackSamples, n_streams), dim3(kPackSamples), smem, st,
+                          d_in, (const float*)d_gains, (const float*)d_dl_old, d_loudness_gain, d_pcm, d_delay, d_pcm_bytes,
+                          p->attack_samples, p->threshold, K));
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
+  if (d_delay) {
+    pcm_delay_advance_kernel<<<(n_streams + 255) / 256, 256, 0, st>>>(d_delay, n_streams, kFrame);
+    ctx->launches.fetch_add(1);
+    MB_CUDA(ctx, cudaGetLastError());
+  }
   return MPEGHB200_OK;
 }
 

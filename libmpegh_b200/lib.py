@@ -292,8 +292,10 @@ class Lib:
         c.mpeghb200_stereo_save_dev.restype = i32
         c.mpeghb200_stereo_mdst_rom.argtypes = [vp, vp]
         c.mpeghb200_stereo_mdst_rom.restype = None
-        c.mpeghb200_limiter_pack_dev.argtypes = [vp, ctypes.POINTER(LimiterParams), vp, vp, vp, ctypes.c_int, vp, vp, vp,
-                                                 vp, ctypes.c_int, vp]
+        c.mpeghb200_limiter_pack_dev.argtypes = [vp, ctypes.POINTER(LimiterParams), vp, vp, vp, vp, ctypes.c_int, vp, vp,
+                                                 vp, vp, ctypes.c_int, vp]
+        c.mpeghb200_limiter_pack_scratch_floats.argtypes = [ctypes.POINTER(LimiterParams)]
+        c.mpeghb200_limiter_pack_scratch_floats.restype = sz
         c.mpeghb200_limiter_pack_dev.restype = i32
         c.mpeghb200_pcm_pack_block_dev.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp,
                                                    vp, vp, ctypes.c_int, vp]
@@ -689,10 +691,13 @@ class Lib:
         """kw: the fields of mpeghb200_chain_desc (handles as returned by the *_create wrappers)."""
         return Chain(self, n_streams, **kw)
 
-    def limiter_pack_dev(self, p, d_in, d_state, bits, d_pcm, n_streams, d_gain=None, ch_map=None, d_delay=None,
-                         d_pcm_bytes=None, stream=0):
+    def limiter_pack_scratch_floats(self, p):
+        return int(self.c.mpeghb200_limiter_pack_scratch_floats(ctypes.byref(p)))
+
+    def limiter_pack_dev(self, p, d_in, d_state, d_scratch, bits, d_pcm, n_streams, d_gain=None, ch_map=None,
+                         d_delay=None, d_pcm_bytes=None, stream=0):
         m = None if ch_map is None else np.ascontiguousarray(ch_map, dtype=np.int32)
-        self.check(self.c.mpeghb200_limiter_pack_dev(self.ctx, ctypes.byref(p), d_in, d_state, d_gain, bits,
+        self.check(self.c.mpeghb200_limiter_pack_dev(self.ctx, ctypes.byref(p), d_in, d_state, d_scratch, d_gain, bits,
                                                      None if m is None else m.ctypes.data, d_delay, d_pcm, d_pcm_bytes,
                                                      n_streams, stream))
 

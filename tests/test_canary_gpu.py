@@ -74,7 +74,10 @@ def test_tail_kernels(gpu_lib, n_ch, bits):
         delay = Guarded(S, "int32", fill=np.array([0, 1, 240, 1023, 1024, 2000, 7], np.int32))
         nb = Guarded(S, "int32")
         if fused:
-            gpu_lib.limiter_pack_dev(p, d_in.ptr, state.ptr, bits, pcm.ptr, S, None, None, delay.ptr, nb.ptr, st)
+            scr = Guarded(S * gpu_lib.limiter_pack_scratch_floats(p))
+            gpu_lib.limiter_pack_dev(p, d_in.ptr, state.ptr, scr.ptr, bits, pcm.ptr, S, None, None, delay.ptr, nb.ptr, st)
+            torch.cuda.synchronize()
+            scr.check(f"tail fused {n_ch}ch {bits}bit scratch")
         else:
             gpu_lib.limiter_dev(p, d_in.ptr, d_lim.ptr, state.ptr, S, None, st)
             gpu_lib.pcm_pack_dev(d_lim.ptr, n_ch, bits, pcm.ptr, S, None, delay.ptr, nb.ptr, st)

@@ -161,6 +161,7 @@ def test_fused_limiter_pack_equals_the_two_kernels(gpu_lib, n_ch, bits, limiter_
     db = da.clone()
     st = torch.cuda.current_stream().cuda_stream
     nbytes = 1024 * n_ch * (bits // 8)
+    scratch = torch.empty(S * gpu_lib.limiter_pack_scratch_floats(b.p), device="cuda")
     for f in range(F):
         d_in = torch.from_numpy(x[f]).cuda()
         d_lim = torch.empty_like(d_in)
@@ -170,8 +171,8 @@ def test_fused_limiter_pack_equals_the_two_kernels(gpu_lib, n_ch, bits, limiter_
         nb = torch.zeros(S, dtype=torch.int32, device="cuda")
         gpu_lib.limiter_dev(a.p, d_in.data_ptr(), d_lim.data_ptr(), a.state.data_ptr(), S, gains.data_ptr(), st)
         gpu_lib.pcm_pack_dev(d_lim.data_ptr(), n_ch, bits, pa.data_ptr(), S, cmap, da.data_ptr(), na.data_ptr(), st)
-        gpu_lib.limiter_pack_dev(b.p, d_in.data_ptr(), b.state.data_ptr(), bits, pb.data_ptr(), S, gains.data_ptr(), cmap,
-                                 db.data_ptr(), nb.data_ptr(), st)
+        gpu_lib.limiter_pack_dev(b.p, d_in.data_ptr(), b.state.data_ptr(), scratch.data_ptr(), bits, pb.data_ptr(), S,
+                                 gains.data_ptr(), cmap, db.data_ptr(), nb.data_ptr(), st)
         torch.cuda.synchronize()
         na_, nb_ = na.cpu().numpy(), nb.cpu().numpy()
         assert np.array_equal(na_, nb_) and np.array_equal(da.cpu().numpy(), db.cpu().numpy()), f
