@@ -31,6 +31,8 @@ typedef enum
   RQ_LIM,    /* impeghd_peak_limiter_process */
   RQ_OBJ,    /* impeghd_obj_renderer_dec */
   RQ_PCM,    /* ia_core_coder_samples_sat */
+  RQ_HOAREN, /* impeghd_hoa_ren_block_process */
+  RQ_RESAMPLE, /* impeghd_resample */
   RQ_KINDS
 } seam_kind;
 
@@ -51,7 +53,8 @@ void seam_inline_unlock(void);
 /* ---- counters (MPEGHB200_SEAM_STATS=1 prints them at exit) ---- */
 typedef struct
 {
-  unsigned long fd_gpu, fd_host, tns, lim, ltpf, fc, mct, obj, obj_host, pcm, batches, batch_calls, max_batch;
+  unsigned long fd_gpu, fd_host, tns, lim, ltpf, fc, mct, obj, obj_host, pcm, batches, batch_calls, max_batch, hoa_ren,
+      hoa_ren_host, resample;
 } seam_counters;
 extern seam_counters seam_n;
 

@@ -239,3 +239,88 @@ def test_seam_oam_subframes(tmp_path, frame_len):
             assert m and int(m.group(1)) == 5 * (1024 // frame_len) and int(m.group(2)) == 0, r.stderr[-400:]
         outs.append(np.load(out))
     assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+
+
+def _run_pair(tmp_path, script_text, args, counter_regex, expect):
+    """Runs a harness script once plainly (reference code) and once with the seam preloaded (GPU); returns both arrays."""
+    libref = os.path.join(REF_DIR, "libmpeghref.so")
+    _need(libref, SEAM)
+    script = tmp_path / "h.py"
+    script.write_text(script_text)
+    outs = []
+    for preload in (None, SEAM):
+        env = dict(os.environ)
+        if preload:
+            env["LD_PRELOAD"], env["MPEGHB200_SEAM_STATS"] = preload, "1"
+        out = str(tmp_path / ("gpu.npy" if preload else "ref.npy"))
+        r = subprocess.run([sys.executable, str(script), ROOT, *[str(a) for a in args], out], env=env,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-800:]
+        if preload:
+            m = re.search(counter_regex, r.stderr)
+            assert m and [int(x) for x in m.groups()] == expect, r.stderr[-400:]
+        outs.append(np.load(out))
+    return outs
+
+
+HOA_REN_SCRIPT = r"""
+import sys, ctypes, numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+import hoa_cases
+from oracle import loader
+ref = loader.load_ref()
+cicp, order, lfe, radius, out_path = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), float(sys.argv[5]), sys.argv[6]
+err = ctypes.c_int(0)
+h = ref.ref_hoa_ren_create(cicp, order, lfe, radius, 48000, ctypes.byref(err))
+assert err.value == 0
+M, nfc, n_out = loader.ref_hoa_ren_tables(ref, h, order)
+rng = np.random.default_rng(cicp + order)
+x = hoa_cases.hoa_signal(rng, 4, M.shape[1])
+outs = []
+for f in range(4):
+    y = np.zeros((n_out, 1024), np.float32)
+    assert ref.ref_hoa_ren_process(h, x[f].reshape(-1), M.shape[1], 1024, 1, y.reshape(-1)) == 0
+    outs.append(y)
+np.save(out_path, np.stack(outs))
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", [(13, 4, 1, 1.5), (6, 3, 1, 0.0), (19, 4, 0, 0.8)])
+def test_seam_hoa_renderer(tmp_path, cfg):
+    """The interposed impeghd_hoa_ren_block_process (no shipped stream carries HOA): oracle/ref_harness_hoa.c designs the
+    matrix / NFC filters with the reference's own init and drives the function, once plainly and once with the seam
+    preloaded; the NFC memories travel through the reference struct, so four consecutive frames must agree."""
+    outs = _run_pair(tmp_path, HOA_REN_SCRIPT, cfg, r"hoa_render gpu=(\d+) host=(\d+)", [4, 0])
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+
+
+RS_SCRIPT = r"""
+import sys, os, ctypes, numpy as np
+sys.path.insert(0, sys.argv[1])
+from oracle import loader
+# the interposer reads the reference library's filter ROM: make its symbols visible (an application that links the
+# reference library has them in the global scope anyway)
+ctypes.CDLL(os.path.join(sys.argv[1], "oracle", "_ref", "libmpeghref.so"), mode=ctypes.RTLD_GLOBAL)
+ref = loader.load_ref()
+up, down, out_path = int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
+h = [ref.ref_rs_create(up, down) for _ in range(3)]
+rng = np.random.default_rng(10 * up + down)
+outs = []
+for f in range(4):
+    for c in range(3):
+        x = rng.normal(0, 5000, 1024).astype(np.float32)
+        y = np.zeros(1024 * up // down, np.float32)
+        ref.ref_rs_process(h[c], x, y)
+        outs.append(y)
+np.save(out_path, np.stack(outs))
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("up,down", [(2, 1), (3, 1), (3, 2)])
+def test_seam_resampler(tmp_path, up, down):
+    """The interposed impeghd_resample (no shipped stream is below 48 kHz): three channels x four frames through
+    oracle/ref_harness_rs.c, delay lines carried in ia_resampler_struct."""
+    outs = _run_pair(tmp_path, RS_SCRIPT, (up, down), r"resample gpu=(\d+)", [12])
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
