@@ -324,3 +324,42 @@ def test_seam_resampler(tmp_path, up, down):
     oracle/ref_harness_rs.c, delay lines carried in ia_resampler_struct."""
     outs = _run_pair(tmp_path, RS_SCRIPT, (up, down), r"resample gpu=(\d+)", [12])
     assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+
+
+HOASP_SCRIPT = r"""
+import sys, os, ctypes, numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+import hoasp_cases
+from oracle import loader
+# the interposer reads the reference library's HOA ROM tables (see RS_SCRIPT)
+ctypes.CDLL(os.path.join(sys.argv[1], "oracle", "_ref", "libmpeghref.so"), mode=ctypes.RTLD_GLOBAL)
+ref = loader.load_ref()
+cfg, out_path = hoasp_cases.CONFIGS[int(sys.argv[2])], sys.argv[3]
+S, F = 3, 10
+hs = []
+for s in range(S):
+    err = ctypes.c_int()
+    hs.append(ref.ref_hoasp_create(hoasp_cases.cfg_array(cfg), ctypes.byref(err)))
+    assert err.value == 0
+n_coef = (cfg[0] + 1) ** 2
+rng = np.random.default_rng(sum(cfg) + 3)
+gens = [hoasp_cases.SideGen(cfg, np.random.default_rng(17 * s + 1), wild_exp=True) for s in range(S)]
+outs = np.zeros((F, S, n_coef, 1024), np.float32)
+for f in range(F):
+    x = hoasp_cases.signals(rng, S, cfg[1])
+    for s in range(S):                     # three decoders interleaved: the state is found by struct, not by call order
+        sd = gens[s].next()
+        assert ref.ref_hoasp_process(hs[s], sd.ctypes.data, x[s].reshape(-1), outs[f, s].reshape(-1)) == 0
+np.save(out_path, outs)
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg_idx", range(6))
+def test_seam_hoa_spatial(tmp_path, cfg_idx):
+    """The four interposed stage functions of impeghd_hoa_spatial_process (inverse gain control, ambience synthesis,
+    channel reassignment, predominant-sound synthesis; no shipped stream carries HOA): oracle/ref_harness_hoasp.c fills
+    the frame parameters the reference's side-info parser would and calls them in the reference's order, three decoders
+    interleaved over ten frames with independency-frame gain resets, plainly and with the seam preloaded."""
+    outs = _run_pair(tmp_path, HOASP_SCRIPT, (cfg_idx,), r"hoa_spatial gpu=(\d+) host=(\d+)", [30, 0])
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
