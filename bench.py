@@ -46,14 +46,17 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 STREAMS, CHANNELS, FRAME = 256, 24, 1024
 UNITS = STREAMS * CHANNELS
 BYTES_PER_UNIT = 16384  # coef 4096 + overlap r/w 2*4096 + out 4096
+FRAMES_PER_LAUNCH = 8  # a step = this many consecutive frames of every stream, one launch
 METRIC = "channel-samples/s (FD synthesis: IMDCT+window+OLA, 256 streams x 24 ch x 1024)"
 UNIT = "channel-samples/s"
 CHAIN_CONFIGS = ("hoa", "binaural", "objects", "fd_4096")
 
 
-def set_streams(n):
-    global STREAMS, UNITS, METRIC
+def set_streams(n, frames=None):
+    global STREAMS, UNITS, METRIC, FRAMES_PER_LAUNCH
     STREAMS, UNITS = n, n * CHANNELS
+    if frames:
+        FRAMES_PER_LAUNCH = max(1, frames)
     METRIC = f"channel-samples/s (FD synthesis: IMDCT+window+OLA, {n} streams x 24 ch x 1024)"
 
 
@@ -66,7 +69,7 @@ def workload_name():
 def config_dict():
     """Identical in both arms (the driver compares the two lines' config)."""
     return {"workload": workload_name(), "streams_per_gpu": STREAMS, "channels": CHANNELS, "frame": FRAME,
-            "sharding": "streams by rank, no collective"}
+            "frames_per_step": FRAMES_PER_LAUNCH, "sharding": "streams by rank, no collective"}
 
 
 def make_side(rng, n_units, mixed=False):
@@ -382,7 +385,9 @@ def reference_arm(args, rank):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(),
         "realtime_factor": value / CHANNELS / 48000.0,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "reference",
-                         "sample": f"{sample_streams} of the workload's {STREAMS} streams x 24 ch per step, "
+                         "sample": f"one frame of {sample_streams} of the workload's {STREAMS} streams x 24 ch per step "
+                                   f"(the GPU arm's step hands {FRAMES_PER_LAUNCH} frames to one launch; a CPU core "
+                                   "walks them one by one either way), "
                                    f"{args.steps} steps, ia_core_coder_fd_frm_dec per channel-frame on {used} "
                                    "persistent pinned worker threads (oracle/ref_chain.c), timed inside C"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -575,6 +580,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--groups", type=int, default=8, help="stream groups rotated through (working set > L2)")
+    ap.add_argument("--frames-per-launch", type=int, default=FRAMES_PER_LAUNCH,
+                    help="consecutive frames of every stream handed to one launch (mpeghb200_fd_synth_frames_dev)")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="headline only (skip the chain configurations)")
@@ -584,7 +591,7 @@ def main():
     ap.add_argument("--streams", type=int, default=STREAMS,
                     help="streams per GPU (default 256 = BASELINE.json configs[1]; 4096 = the north-star stream count)")
     args = ap.parse_args()
-    set_streams(args.streams)
+    set_streams(args.streams, args.frames_per_launch)
     args.warmup = max(args.warmup, 3)
 
     rank = int(os.environ.get("RANK", "0"))
@@ -625,24 +632,36 @@ def main():
     G = max(1, args.groups)
     gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
     rng = np.random.default_rng(1234 + rank)
-    coef = [torch.randn(UNITS, FRAME, device="cuda", generator=gen) * 500.0 for _ in range(G)]
+    FPL = FRAMES_PER_LAUNCH
+    GF = max(2, -(-G // FPL))  # groups for the FPL-frame launch: GF * FPL * 50 MB of spectra + PCM, >> L2 as well
+    coef = [torch.randn(UNITS, FRAME, device="cuda", generator=gen) * 500.0 for _ in range(max(G, GF * FPL))]
     ovl = [torch.zeros(UNITS, FRAME, device="cuda") for _ in range(G)]
     outb = [torch.empty(UNITS, FRAME, device="cuda") for _ in range(G)]
+    # the FPL-frame launch reads [FPL][UNITS][1024] blocks
+    coef_f = [torch.stack(coef[g * FPL:(g + 1) * FPL]) for g in range(GF)] if FPL > 1 else None
+    outb_f = [torch.empty(FPL, UNITS, FRAME, device="cuda") for _ in range(GF)] if FPL > 1 else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(mixed, with_clocks):
-        """W warm-up + K timed steps of one workload variant; returns (ms_per_step, launches, clocks)."""
-        side = [torch.from_numpy(fd_cases.pack_side(make_side(rng, UNITS, mixed)).astype(np.int32)).cuda()
-                for _ in range(G)]
+    def timed(mixed, with_clocks, frames):
+        """W warm-up + K timed steps of one workload variant; returns (ms_per_step, launches, clocks).  frames = 1:
+        a step is one frame of every stream (mpeghb200_fd_synth_dev); frames > 1: that many consecutive frames of
+        every stream in one launch (mpeghb200_fd_synth_frames_dev)."""
+        n_g = G if frames == 1 else GF
+        side = [torch.from_numpy(np.stack([fd_cases.pack_side(make_side(rng, UNITS, mixed)) for _ in range(frames)])
+                                 .astype(np.int32)).cuda() for _ in range(n_g)]
 
         def step(i):
-            g = i % G
-            lib.fd_synth_dev(coef[g].data_ptr(), side[g].data_ptr(), ovl[g].data_ptr(), outb[g].data_ptr(), UNITS,
-                             stream.cuda_stream)
+            g = i % n_g
+            if frames == 1:
+                lib.fd_synth_dev(coef[g].data_ptr(), side[g].data_ptr(), ovl[g].data_ptr(), outb[g].data_ptr(), UNITS,
+                                 stream.cuda_stream)
+            else:
+                lib.fd_synth_frames_dev(coef_f[g].data_ptr(), side[g].data_ptr(), ovl[g].data_ptr(),
+                                        outb_f[g].data_ptr(), UNITS, frames, stream.cuda_stream)
 
         sampler = ClockSampler(local_rank)
         sampling = rank == 0 and with_clocks
@@ -687,9 +706,18 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()) / args.steps, n_launch, clk
 
-    ms_per_step, launches, clocks = timed(False, True)
-    value = world * UNITS * FRAME / (ms_per_step * 1e-3)
-    ms_mixed, _, _ = timed(True, False)
+    ms_per_step, launches, clocks = timed(False, True, FPL)
+    value = world * UNITS * FPL * FRAME / (ms_per_step * 1e-3)
+    ms_mixed, _, _ = timed(True, False, FPL)
+    single = None
+    if FPL > 1:  # the same workload one frame per launch (round 1's step)
+        k_keep = args.steps
+        args.steps = max(1, min(args.steps * FPL, 20000))
+        ms_1, _, _ = timed(False, False, 1)
+        ms_1m, _, _ = timed(True, False, 1)
+        args.steps = k_keep
+        single = (ms_1, ms_1m)
+    del coef_f, outb_f
 
     # ---- e2e: host buffers through the session API, copies inside the timed region --------------
     sess = lib.fd_open(STREAMS, CHANNELS)
@@ -755,30 +783,50 @@ def main():
             configs[name] = res
 
     if rank == 0:
-        achieved = BYTES_PER_UNIT * UNITS / (ms_per_step * 1e-3) / 1e9
+        achieved = BYTES_PER_UNIT * UNITS * FPL / (ms_per_step * 1e-3) / 1e9
+        own_min = (8192 + 8192 / FPL) * UNITS * FPL  # spectra in + PCM out every frame, overlap r/w once per launch
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "fd_synth_traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        traffic_f = None
+        tpath = os.path.join(ROOT, "profiles", "fd_synth_frames_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("frames_per_launch") == FPL and tj.get("n_units") == UNITS:
+                traffic_f = tj.get("dram_bytes_per_launch")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(),
-            "notes": {"l2_policy": f"inputs larger than L2: {G} stream groups rotated, "
-                      f"{G * 3 * UNITS * FRAME * 4 / 1e6:.0f} MB working set, state carried per group",
+            "notes": {"l2_policy": f"inputs larger than L2: {GF if FPL > 1 else G} stream groups rotated, "
+                      f"{(GF * (2 * FPL + 1) if FPL > 1 else G * 3) * UNITS * FRAME * 4 / 1e6:.0f} MB working set, "
+                      "state carried per group",
                       "host_numa_binding": (f"rank 0 on {len(numa_cpus)} CPUs of its GPU's NUMA node" if numa_cpus
                                             else "none")},
             "realtime_factor": value / CHANNELS / 48000.0,
             "mixed_sequence_variant": {
                 "note": "same shape with ~8 % LONG_START/EIGHT_SHORT/LONG_STOP frames (SURVEY.md 8d variant)",
-                "ms_per_step": ms_mixed, "value": world * UNITS * FRAME / (ms_mixed * 1e-3),
-                "roofline_frac": BYTES_PER_UNIT * UNITS / (ms_mixed * 1e-3) / 1e9 / peak},
+                "ms_per_step": ms_mixed, "value": world * UNITS * FPL * FRAME / (ms_mixed * 1e-3),
+                "roofline_frac": BYTES_PER_UNIT * UNITS * FPL / (ms_mixed * 1e-3) / 1e9 / peak},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic,
-                         "traffic_source": "profiles/fd_synth_traffic.json (one ncu --set full capture of this kernel, "
-                                           "committed; not measured in this run)",
+                         "frac": achieved / peak, "traffic": traffic if FPL == 1 else traffic_f,
+                         "traffic_source": ("profiles/fd_synth_traffic.json" if FPL == 1 else
+                                            "profiles/fd_synth_frames_traffic.json") +
+                                           " (one ncu --set full capture of this kernel, committed; not measured in "
+                                           "this run)",
                          "peak_source": peak_src,
-                         "kernel": "fd_synth_ws_kernel", "algorithmic_bytes_per_launch": BYTES_PER_UNIT * UNITS},
+                         "kernel": "fd_synth_ws_kernel" if FPL == 1 else "fd_synth_ws_frames_kernel",
+                         "algorithmic_bytes_per_unit": BYTES_PER_UNIT,
+                         "algorithmic_bytes_per_launch": BYTES_PER_UNIT * UNITS * FPL,
+                         "note": "SURVEY.md 8(d): 16 KB per channel-frame (spectra in, overlap read + write, PCM out), "
+                                 "what ia_core_coder_fd_frm_dec moves per call" +
+                                 ("" if FPL == 1 else
+                                  f"; with {FPL} frames per launch a unit's overlap stays on the SM between frames, so "
+                                  f"the launch's own minimum is {own_min / UNITS / FPL:.0f} B per channel-frame: "
+                                  "frac_of_own_minimum is the fraction of the HBM peak on that smaller figure (the "
+                                  "kernel is then bound by issue / shared-memory throughput, not HBM)"),
+                         "frac_of_own_minimum": own_min / (ms_per_step * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": UNITS * FRAME * 4 + UNITS * 4,
                     "d2h_bytes_per_step": UNITS * FRAME * 4, "ms_per_step": e2e_s * 1e3,
                     "h2d_GBps": (UNITS * FRAME * 4 + UNITS * 4) / e2e_s / 1e9, "d2h_GBps": UNITS * FRAME * 4 / e2e_s / 1e9,
@@ -787,6 +835,14 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if single:
+            line["single_frame_launch_variant"] = {
+                "note": "the same workload one frame of every stream per launch (mpeghb200_fd_synth_dev; the step of "
+                        "round 1's bench line)",
+                "ms_per_step": single[0], "value": world * UNITS * FRAME / (single[0] * 1e-3),
+                "roofline_frac": BYTES_PER_UNIT * UNITS / (single[0] * 1e-3) / 1e9 / peak,
+                "mixed_sequence_ms_per_step": single[1],
+                "mixed_sequence_roofline_frac": BYTES_PER_UNIT * UNITS / (single[1] * 1e-3) / 1e9 / peak}
         if configs:
             line["configs"] = configs
         if not args.no_cpu_baseline:

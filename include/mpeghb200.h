@@ -92,6 +92,16 @@ mpeghb200_status mpeghb200_host_free(mpeghb200_ctx *ctx, void *hptr);
 mpeghb200_status mpeghb200_fd_synth_dev(mpeghb200_ctx *ctx, const float *d_coef, const uint32_t *d_side,
                                         float *d_overlap, float *d_out, int n_units, void *cuda_stream);
 
+/* n_frames consecutive frames of every unit in ONE launch, for feeds that have them at hand (file decoding, any
+ * look-ahead of the parse half): coef / side / out are [n_frames][n_units][...], overlap [n_units][1024] as above
+ * (read before frame 0, replaced after the last frame).  The result is what n_frames calls of mpeghb200_fd_synth_dev
+ * give, bit for bit; between two ONLY_LONG-family frames a unit's overlap stays on the SM (ia_core_coder_fd_frm_dec
+ * writes and re-reads it through memory, decoder/ia_core_coder_imdct.c:807-813), which removes up to half of the
+ * launch's HBM traffic.  n_units * n_frames < 2^31. */
+mpeghb200_status mpeghb200_fd_synth_frames_dev(mpeghb200_ctx *ctx, const float *d_coef, const uint32_t *d_side,
+                                               float *d_overlap, float *d_out, int n_units, int n_frames,
+                                               void *cuda_stream);
+
 /* Host-buffer session: device-resident overlap state for n_streams x n_ch channels, pinned staging. */
 typedef struct mpeghb200_fd_session mpeghb200_fd_session;
 mpeghb200_status mpeghb200_fd_open(mpeghb200_ctx *ctx, int n_streams, int n_ch, mpeghb200_fd_session **out);

@@ -8,6 +8,8 @@
 #include "common.h"
 
 namespace mpeghb200 {
+mpeghb200_status fd_synth_frames_launch(mpeghb200_ctx* ctx, const float* d_coef, const uint32_t* d_side,
+                                        float* d_overlap, float* d_out, int n_units, int n_frames, cudaStream_t stream);
 mpeghb200_status fd_synth_launch(mpeghb200_ctx* ctx, const float* d_coef, const uint32_t* d_side, float* d_overlap,
                                  float* d_out, int n_units, cudaStream_t stream);
 }
@@ -50,6 +52,19 @@ static bool dma_ready(const void* p) {
 }
 
 extern "C" {
+
+mpeghb200_status mpeghb200_fd_synth_frames_dev(mpeghb200_ctx* ctx, const float* d_coef, const uint32_t* d_side,
+                                               float* d_overlap, float* d_out, int n_units, int n_frames,
+                                               void* cuda_stream) {
+  if (!ctx) return MPEGHB200_ERR_BAD_ARG;
+  if (n_units < 0 || n_frames < 0 || (n_units > 0 && n_frames > 0 && (!d_coef || !d_side || !d_overlap || !d_out)))
+    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "fd_synth_frames_dev: null buffer or negative count");
+  if (n_frames > 0 && n_units > 0x7fffffff / n_frames)
+    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "fd_synth_frames_dev: n_units * n_frames does not fit 31 bits");
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return fd_synth_frames_launch(ctx, d_coef, d_side, d_overlap, d_out, n_units, n_frames,
+                                static_cast<cudaStream_t>(cuda_stream));
+}
 
 mpeghb200_status mpeghb200_fd_synth_dev(mpeghb200_ctx* ctx, const float* d_coef, const uint32_t* d_side,
                                         float* d_overlap, float* d_out, int n_units, void* cuda_stream) {

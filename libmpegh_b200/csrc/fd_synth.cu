@@ -1001,6 +1001,185 @@ __global__ void __launch_bounds__(128, MPEGHB200_FD_CTAS_PER_SM)
   }
 }
 
+
+// ---- F consecutive frames of every unit in one launch ------------------------------------------------
+// A decoder that serves files (or any feed with F frames of a stream at hand) can hand them over together:
+// coef / side / out are [F][n_units], the overlap state is one buffer per unit.  A CTA walks its units frame by frame,
+// so the unit's overlap never leaves the SM between two ONLY_LONG-family frames: role C's lanes write exactly the
+// positions they read (i4 and 1020 - i4), so the new overlap is simply kept in the registers that held the old one and
+// only the unit's last frame (or a frame followed by a LONG_STOP / generic-path frame) stores it.  Per channel-frame
+// that removes up to 8 KB of the 16 KB of traffic, and the launch's ramp and tail are paid once per F frames.
+// A unit that meets a generic-path frame (EIGHT_SHORT, other transform kernels) leaves the pipeline from that frame
+// on: role C notes (unit, frame) and one warp finishes the unit's remaining frames in order after the fast pass.
+template <bool STORE>
+__device__ __forceinline__ void phase_c_carry(float4 (&ovv)[8], const TabC& tc, const float* sm, float* __restrict__ ov,
+                                              float* __restrict__ o, int lane) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int i4 = 4 * (lane + 32 * it), j4 = 1020 - i4;
+    const float4 P = ld4(sm + 512 + i4), Q = ld4(sm + 508 - i4);
+    const float4 r_lo = win4(P, tc.f[it], ovv[it], rev4(tc.r[it]));
+    const float4 r_hi = win4(neg4(rev4(P)), tc.r[it], ovv[4 + it], rev4(tc.f[it]));
+    stcs4(o + i4, r_lo);
+    stcs4(o + j4, r_hi);
+    ovv[it] = neg4(rev4(Q));
+    ovv[4 + it] = neg4(Q);
+    if (STORE) {
+      st4(ov + i4, ovv[it]);
+      st4(ov + j4, ovv[4 + it]);
+    }
+  }
+}
+
+__device__ __noinline__ void slow_units_frames(const float* __restrict__ coef, const uint32_t* __restrict__ side,
+                                               float* __restrict__ overlap, float* __restrict__ out, const int* list,
+                                               int count, float* slots, const DeviceTables& T, int n_units,
+                                               int n_frames) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = warp; k < count; k += 4) {
+    const int e = list[k];
+    const size_t u = size_t(e) / size_t(n_frames);
+    for (int f = e - int(u) * n_frames; f < n_frames; ++f) {
+      const size_t q = size_t(f) * n_units + u;
+      fd_unit_generic(coef + q * 1024, overlap + u * 1024, out + q * 1024, unpack_side(__ldg(side + q)),
+                      slots + warp * kBufFloats, T, lane);
+      __syncwarp();  // the next frame's lanes read overlap positions other lanes of this warp just wrote
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128, MPEGHB200_FD_CTAS_PER_SM)
+    fd_synth_ws_frames_kernel(const float* __restrict__ coef, const uint32_t* __restrict__ side,
+                              float* __restrict__ overlap, float* __restrict__ out, int n_units, int n_frames,
+                              const __grid_constant__ DeviceTables T) {
+  __shared__ __align__(16) float slots[kSlots][kBufFloats];
+  __shared__ int fast_flag[kSlots];
+  __shared__ int slow_list[kSlowCap];  // unit * n_frames + first generic-path frame
+  __shared__ int slow_count;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  grid_launch_dependents();
+  if (threadIdx.x == 96) slow_count = 0;
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int n_local = first < n_units ? (n_units - first + stride - 1) / stride : 0;
+  const int n_items = n_local * n_frames;  // item i = frame i % F of the CTA's unit number i / F
+  constexpr int AB = 1, BC = 1 + kSlots, FREE = 1 + 2 * kSlots;
+  auto is_fast = [](const Side& sd) { return sd.seq != 2 && sd.tkt == 0; };
+
+  if (warp == 0) {
+    // ---------------- role A ----------------
+    TabA ta;
+    load_tab_a(ta, T, lane);
+    grid_dependency_wait();
+    float2 eo[2][16];
+    uint32_t sw[2];
+    int un = first, fn = 0;  // (unit, frame) of the item whose loads are issued next
+    bool left = false;       // the current unit has left the pipeline
+    auto issue = [&](int buf) {
+      const size_t q = size_t(fn) * n_units + un;
+      sw[buf] = __ldg(side + q);
+      load_coef(eo[buf], coef + q * 1024, lane);
+      if (fn == 0 && lane == 0)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(overlap + size_t(un) * 1024), "r"(4096)
+                     : "memory");
+      if (++fn == n_frames) fn = 0, un += stride;
+    };
+    if (n_items > 0) issue(0);
+    int f = 0;
+    auto body = [&](auto cur_c, int i) {
+      constexpr int cur = decltype(cur_c)::value;
+      const int slot = i % kSlots;
+      if (i + 1 < n_items) issue(cur ^ 1);
+      if (i >= kSlots) bar_sync64(FREE + slot);
+      if (f == 0) left = false;
+      const bool fast = !left && is_fast(unpack_side(sw[cur]));
+      left = !fast;
+      if (lane == 0) fast_flag[slot] = fast;
+      if (fast) phase_a(eo[cur], ta, slots[slot], T, lane);
+      bar_arrive64(AB + slot);
+      if (++f == n_frames) f = 0;
+    };
+    for (int i = 0; i < n_items; i += 2) {
+      body(std::integral_constant<int, 0>{}, i);
+      if (i + 1 < n_items) body(std::integral_constant<int, 1>{}, i + 1);
+    }
+  } else if (warp <= 2) {
+    // ---------------- role B ----------------
+    TabB tb;
+    load_tab_b(tb, T, lane);
+    grid_dependency_wait();
+    for (int i = warp - 1; i < n_items; i += 2) {
+      const int slot = i % kSlots;
+      bar_sync64(AB + slot);
+      if (fast_flag[slot]) phase_b(tb, slots[slot], lane);
+      bar_arrive64(BC + slot);
+    }
+  } else {
+    // ---------------- role C ----------------
+    TabC tc0, tc1;
+    load_tab_c(tc0, T.win_long[0], lane);
+    load_tab_c(tc1, T.win_long[1], lane);
+    grid_dependency_wait();
+    int u = first, f = 0;
+    int mode = 0;       // 0: in the pipeline, 1: handed to the slow pass, 2: generic path in line (list full)
+    bool have = false;  // ovv holds the unit's current overlap (the previous frame did not store it)
+    float4 ovv[8];
+    for (int i = 0; i < n_items; ++i) {
+      const int slot = i % kSlots;
+      const size_t q = size_t(f) * n_units + u;
+      const Side sd = unpack_side(__ldg(side + q));
+      float* ov = overlap + size_t(u) * 1024;
+      float* o = out + q * 1024;
+      if (f == 0) mode = 0, have = false;
+      const bool fast = mode == 0 && is_fast(sd);
+      const bool start_like = (sd.seq == 0 || sd.seq == 1);
+      bool keep = false;  // the next frame takes the overlap from the registers
+      if (fast && start_like && f + 1 < n_frames) {
+        const Side nx = unpack_side(__ldg(side + q + n_units));
+        keep = is_fast(nx) && (nx.seq == 0 || nx.seq == 1);
+      }
+      if (fast && start_like && !have) load_overlap(ovv, ov, lane);
+      bar_sync64(BC + slot);
+      if (fast) {
+        if (start_like) {
+          if (keep) {
+            if (sd.shape_prev)
+              phase_c_carry<false>(ovv, tc1, slots[slot], ov, o, lane);
+            else
+              phase_c_carry<false>(ovv, tc0, slots[slot], ov, o, lane);
+          } else {
+            if (sd.shape_prev)
+              phase_c_carry<true>(ovv, tc1, slots[slot], ov, o, lane);
+            else
+              phase_c_carry<true>(ovv, tc0, slots[slot], ov, o, lane);
+          }
+        } else {
+          phase_c_stop(slots[slot], ov, o, T.win_short[sd.shape_prev], lane);
+          __syncwarp();  // its overlap stores are read back by other lanes' loads of the next frame
+        }
+      } else {
+        if (mode == 0) {
+          if (slow_count < kSlowCap) {  // only this warp writes slow_count
+            if (lane == 0) slow_list[slow_count] = u * n_frames + f, slow_count = slow_count + 1;
+            __syncwarp();
+            mode = 1;
+          } else {
+            mode = 2;
+          }
+        }
+        if (mode == 2) {
+          fd_unit_generic(coef + q * 1024, ov, o, sd, slots[slot], T, lane);
+          __syncwarp();
+        }
+      }
+      have = keep;
+      if (i + kSlots < n_items) bar_arrive64(FREE + slot);
+      if (++f == n_frames) f = 0, u += stride;
+    }
+  }
+  __syncthreads();
+  if (slow_count) slow_units_frames(coef, side, overlap, out, slow_list, slow_count, &slots[0][0], T, n_units, n_frames);
+}
+
 }  // namespace
 
 template <int B, int WARPS, int MIN_BLOCKS>
@@ -1046,6 +1225,26 @@ mpeghb200_status fd_synth_launch(mpeghb200_ctx* ctx, const float* d_coef, const 
       break;
     }
   }
+  ctx->launches.fetch_add(1);
+  MB_CUDA(ctx, e);
+  return MPEGHB200_OK;
+}
+
+
+mpeghb200_status fd_synth_frames_launch(mpeghb200_ctx* ctx, const float* d_coef, const uint32_t* d_side,
+                                        float* d_overlap, float* d_out, int n_units, int n_frames, cudaStream_t stream) {
+  if (n_units == 0 || n_frames == 0) return MPEGHB200_OK;
+  if (n_frames == 1) return fd_synth_launch(ctx, d_coef, d_side, d_overlap, d_out, n_units, stream);
+  const int ctas = ctx->sm_count * MPEGHB200_FD_CTAS_PER_SM;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(n_units < ctas ? n_units : ctas), cfg.blockDim = dim3(128), cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, fd_synth_ws_frames_kernel, d_coef, d_side, d_overlap, d_out, n_units,
+                                     n_frames, ctx->tables);
+  if (e == cudaSuccess) e = cudaGetLastError();
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, e);
   return MPEGHB200_OK;

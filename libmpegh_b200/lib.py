@@ -157,6 +157,8 @@ class Lib:
         c.mpeghb200_host_free.restype = i32
         c.mpeghb200_fd_synth_dev.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, vp]
         c.mpeghb200_fd_synth_dev.restype = i32
+        c.mpeghb200_fd_synth_frames_dev.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp]
+        c.mpeghb200_fd_synth_frames_dev.restype = i32
         c.mpeghb200_fd_open.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
         c.mpeghb200_fd_open.restype = i32
         c.mpeghb200_fd_execute.argtypes = [vp, vp, vp, vp]
@@ -375,6 +377,11 @@ class Lib:
     def fd_synth_dev(self, d_coef, d_side, d_overlap, d_out, n_units, stream=0):
         """Raw device pointers (ints), e.g. torch tensor .data_ptr(); stream = cudaStream_t as int."""
         self.check(self.c.mpeghb200_fd_synth_dev(self.ctx, d_coef, d_side, d_overlap, d_out, n_units, stream))
+
+    def fd_synth_frames_dev(self, d_coef, d_side, d_overlap, d_out, n_units, n_frames, stream=0):
+        """coef / side / out [n_frames][n_units][...]: n_frames consecutive frames of every unit in one launch."""
+        self.check(self.c.mpeghb200_fd_synth_frames_dev(self.ctx, d_coef, d_side, d_overlap, d_out, n_units, n_frames,
+                                                        stream))
 
     def fd_open(self, n_streams, n_ch):
         return FdSession(self, n_streams, n_ch)

@@ -196,3 +196,57 @@ def test_session_submit_wait_pipelined(gpu_lib, oracle):
         sess.wait()  # nothing in flight: no-op
     finally:
         sess.close()
+
+
+def run_frames_dev(lib, coef, side_packed, overlap):
+    """coef [F,U,1024], side [F,U], overlap [U,1024] -> (out [F,U,1024], new_overlap) via mpeghb200_fd_synth_frames_dev."""
+    import torch
+    d_coef = torch.from_numpy(np.ascontiguousarray(coef)).cuda()
+    d_side = torch.from_numpy(np.ascontiguousarray(side_packed.astype(np.int32))).cuda()
+    d_ov = torch.from_numpy(np.ascontiguousarray(overlap)).cuda()
+    d_out = torch.full_like(d_coef, float("nan"))
+    lib.fd_synth_frames_dev(d_coef.data_ptr(), d_side.data_ptr(), d_ov.data_ptr(), d_out.data_ptr(), coef.shape[1],
+                            coef.shape[0], torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return d_out.cpu().numpy(), d_ov.cpu().numpy()
+
+
+@pytest.mark.parametrize("F,U,kswitch,long_only", [(4, 185, 0.0, False), (7, 185, 0.3, False), (2, 1, 0.0, False),
+                                                   (5, 3000, 0.0, True), (3, 3000, 0.1, False), (1, 50, 0.0, False)])
+def test_frames_launch_vs_oracle(gpu_lib, oracle, F, U, kswitch, long_only):
+    """F frames of every unit in one launch == the oracle walking the frames one by one, with legal window-sequence
+    chains (LONG_START -> EIGHT_SHORT ... -> LONG_STOP inside the launch, so units leave the register-carried fast path
+    and come back in a later launch), transform-kernel switching, ragged unit counts and two launches chained."""
+    rng = np.random.default_rng(F * 1000 + U)
+    side = fd_cases.random_side(rng, 2 * F, U, kernel_switch_prob=kswitch)
+    if long_only:
+        side[:, :, 0] = 0
+    coef = fd_cases.random_coef(rng, (2 * F, U, 1024))
+    ov_o = fd_cases.random_coef(rng, (U, 1024), sigma=0.3)
+    ov_g = ov_o.copy()
+    out_o = np.zeros((2 * F, U, 1024), np.float32)
+    assert oracle.oracle_fd_frm_dec_batch(coef, ov_o, out_o, side, 2 * F, U) == 0
+    for half in range(2):
+        sl = slice(half * F, (half + 1) * F)
+        out, ov_g = run_frames_dev(gpu_lib, coef[sl], fd_cases.pack_side(side[sl]), ov_g)
+        for f in range(F):
+            assert bits_equal(out[f], out_o[sl][f]), (half, f, int((out[f].view(np.uint32) != out_o[sl][f].view(np.uint32)).sum()))
+    assert bits_equal(ov_g, ov_o)
+
+
+def test_frames_launch_equals_single_frame_launches(gpu_lib):
+    """At configs[1]'s size with ~8 % transition frames, including more generic-path units per CTA than the slow list
+    holds (every unit of the first 300 goes EIGHT_SHORT in frame 1)."""
+    rng = np.random.default_rng(99)
+    F, U = 4, 6144
+    side = fd_cases.random_side(rng, F, U)
+    side[1, :300, 0] = 2
+    coef = fd_cases.random_coef(rng, (F, U, 1024))
+    ov0 = fd_cases.random_coef(rng, (U, 1024), sigma=0.3)
+    packed = fd_cases.pack_side(side)
+    out, ov = run_frames_dev(gpu_lib, coef, packed, ov0)
+    ov1 = ov0
+    for f in range(F):
+        o1, ov1 = run_dev(gpu_lib, coef[f], packed[f], ov1)
+        assert bits_equal(out[f], o1), f
+    assert bits_equal(ov, ov1)
