@@ -216,9 +216,12 @@ class ChainSpec:
         elif name == "fd_4096":
             self.n_in, self.n_out, self.fpr = 24, 24, 1
             self.workload = (f"configs[1] shape at the north-star stream count: {S} streams x 24 ch, spectra -> FD "
-                             "synthesis (value: that kernel alone; e2e: -> limiter -> 24-bit PCM as one chain)")
+                             "synthesis (value: that kernel alone, up to 4 frames of every stream per launch; e2e: -> limiter "
+                             "-> 24-bit PCM as one chain)")
             self.bytes_per_unit = 24 * BYTES_PER_UNIT
-            self.bytes_formula = "24 channel-frames x (coef 4096 + overlap r/w 8192 + out 4096)"
+            self.bytes_formula = ("24 channel-frames x (coef 4096 + overlap r/w 8192 + out 4096), SURVEY.md 8(d)'s "
+                                  "figure; with F frames per launch the overlap stays on the SM between frames "
+                                  "(own minimum 8192 + 8192 / F per channel-frame)")
             self.value_samples = 24 * 1024
             self.value_what = "channel-samples/s (24 x 1024 per stream-frame)"
             self.h2d = 24 * 4096 + 24 * 4
@@ -471,13 +474,17 @@ def bench_chain(lib, spec, args, rank, world, dist, torch, peak):
     # ---- value: resident inputs ----
     if name == "fd_4096":
         # the FD synthesis kernel alone at 4096 streams (north-star stream count), state per group
+        FDF = min(FRAMES_PER_LAUNCH, 4)  # frames of every stream per launch (403 MB of spectra per frame)
         ovl = [torch.zeros(S * 24, 1024, device="cuda") for _ in range(G)]
-        outb = torch.empty(S * 24, 1024, device="cuda")
+        outb = torch.empty(FDF, S * 24, 1024, device="cuda")
+        core_f = [torch.randn(FDF, S * 24, 1024, device="cuda", generator=gen) * sigma for _ in range(G)]
+        side_f = [torch.from_numpy(np.stack([fd_cases.pack_side(make_side(rng, S * 24)) for _ in range(FDF)])
+                                   .astype(np.int32)).cuda() for _ in range(G)]
 
         def step(i):
             g_ = i % G
-            lib.fd_synth_dev(core_d[g_].data_ptr(), side_d[g_].data_ptr(), ovl[g_].data_ptr(), outb.data_ptr(), S * 24,
-                             st.cuda_stream)
+            lib.fd_synth_frames_dev(core_f[g_].data_ptr(), side_f[g_].data_ptr(), ovl[g_].data_ptr(), outb.data_ptr(),
+                                    S * 24, FDF, st.cuda_stream)
     else:
         frames = []
         for i in range(max(G, len(side_d) if side_d else 1) * 2):
@@ -505,8 +512,10 @@ def bench_chain(lib, spec, args, rank, world, dist, torch, peak):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / steps
+    value_frames = 1
     if name == "fd_4096":
-        del ovl, outb
+        del ovl, outb, core_f, side_f
+        value_frames = FDF
 
     # ---- e2e: pinned host buffers through submit / wait, two calls in flight ----
     n_host = 2
@@ -552,19 +561,20 @@ def bench_chain(lib, spec, args, rank, world, dist, torch, peak):
         fn(h)
     del core_d, h_core, h_pcm
 
-    units = S  # per step and rank: S stream-frames (stream-blocks for the binaural chain)
+    units = S * value_frames  # per step and rank: stream-frames (stream-blocks for the binaural chain)
     achieved = spec.bytes_per_unit * units / (ms * 1e-3) / 1e9
     value = world * units * spec.value_samples / (ms * 1e-3)
     h2d, d2h = spec.h2d * S, spec.d2h * S
     return {
         "workload": spec.workload, "streams_per_gpu": S, "value": value, "unit": UNIT, "value_is": spec.value_what,
         "ms_per_step": ms, "steps": steps, "units_per_step_per_gpu": units,
-        "audio_s_per_wall_s": world * S * F * 1024 / 48000.0 / (ms * 1e-3),
+        "audio_s_per_wall_s": world * S * F * value_frames * 1024 / 48000.0 / (ms * 1e-3),
         "gpu_launches": int(launches), "launches_per_step": launches / steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "scope": "all kernels of the chain step (not only the dominant one)",
                      "algorithmic_bytes_per_unit": spec.bytes_per_unit, "bytes_formula": spec.bytes_formula},
-        "e2e": {"value": world * units * spec.value_samples / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
+        "value_frames_per_launch": value_frames,
+        "e2e": {"value": world * S * spec.value_samples / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "h2d_GBps": h2d / e2e_s / 1e9, "d2h_GBps": d2h / e2e_s / 1e9,
                 "audio_s_per_wall_s": world * S * F * 1024 / 48000.0 / e2e_s,
