@@ -308,6 +308,19 @@ mpeghb200_status mpeghb200_binaural_create(mpeghb200_ctx *ctx, int n_in, int len
                                            int n_sets, const float *taps_direct, const float *taps_diffuse,
                                            const float *direct_fc, const float *diffuse_fc,
                                            const float *inv_diffuse_weight, mpeghb200_binaural **out);
+/* The same renderer from what the reference's own init left in ia_binaural_ren_pers_mem_str
+ * (decoder/impeghd_binaural_renderer.h:52-76): fft_size, the packed filter spectra taps_direct[2][n_in][..] (rows of
+ * direct_row_stride floats, the first fft_size of each are used, the two ears direct_ear_stride floats apart; in
+ * direct_process_size[2][..] the ears are direct_size_stride entries apart), taps_diffuse[block][2][..], the multiply lengths direct_process_size /
+ * diffuse_process_size[block][2] and diffuse_weight[n_in].  One filter set.  This is what the drop-in uses: nothing is
+ * re-designed, the filters are the reference's bit for bit.  fft_size 2048 or 8192. */
+mpeghb200_status mpeghb200_binaural_create_from_state(mpeghb200_ctx *ctx, int fft_size, int n_in, int n_diffuse_blocks,
+                                                      const float *h_direct, size_t direct_row_stride,
+                                                      size_t direct_ear_stride, const float *h_diffuse,
+                                                      size_t diffuse_row_stride,
+                                                      const int32_t *direct_process_size, int direct_size_stride,
+                                                      const int32_t *diffuse_process_size,
+                                                      const float *diffuse_weight, mpeghb200_binaural **out);
 void mpeghb200_binaural_destroy(mpeghb200_binaural *b);
 int mpeghb200_binaural_block_len(const mpeghb200_binaural *b);
 int mpeghb200_binaural_num_in(const mpeghb200_binaural *b);

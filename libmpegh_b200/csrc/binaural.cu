@@ -419,6 +419,66 @@ mpeghb200_status mpeghb200_binaural_create(mpeghb200_ctx* ctx, int n_in, int len
   return MPEGHB200_OK;
 }
 
+mpeghb200_status mpeghb200_binaural_create_from_state(mpeghb200_ctx* ctx, int fft_size, int n_in, int n_diffuse_blocks,
+                                                      const float* h_direct, size_t direct_row_stride,
+                                                      size_t direct_ear_stride, const float* h_diffuse,
+                                                      size_t diffuse_row_stride,
+                                                      const int32_t* direct_process_size, int direct_size_stride,
+                                                      const int32_t* diffuse_process_size,
+                                                      const float* diffuse_weight, mpeghb200_binaural** out) {
+  if (!ctx || !out) return MPEGHB200_ERR_BAD_ARG;
+  *out = nullptr;
+  if (n_in < 1 || n_in > 32 || n_diffuse_blocks < 0 || n_diffuse_blocks > 2 || !h_direct || !direct_process_size ||
+      !diffuse_weight || direct_size_stride < n_in || direct_row_stride < size_t(fft_size) ||
+      direct_ear_stride < size_t(n_in) * direct_row_stride ||
+      (n_diffuse_blocks && (!h_diffuse || !diffuse_process_size || diffuse_row_stride < size_t(fft_size))))
+    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "binaural_create_from_state: 1..32 inputs, 0..2 diffuse blocks, non-null tables");
+  if (fft_size != 2048 && fft_size != 8192)
+    return fail(ctx, MPEGHB200_ERR_UNSUPPORTED, "binaural_create_from_state: 2048- and 8192-point transforms only");
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  auto* b = new (std::nothrow) mpeghb200_binaural();
+  if (!b) return MPEGHB200_ERR_NO_MEM;
+  const int N = fft_size;
+  b->ctx = ctx, b->n_in = n_in, b->len = N / 2, b->n_blocks = n_diffuse_blocks, b->n_sets = 1, b->N = N, b->dim2 = N / 1024;
+  std::vector<float2> mix(size_t(b->dim2) * 1024);
+  {
+    const std::vector<float>& mc = rom_table(ROM_MIXED_RAD_COS);
+    const std::vector<float>& ms = rom_table(ROM_MIXED_RAD_SIN);
+    const int fac = 16 / b->dim2;
+    for (int j = 0; j < b->dim2; ++j)
+      for (int i = 0; i < 1024; ++i)
+        mix[size_t(j) * 1024 + i] = make_float2(mc[(i * b->dim2 + j) * fac], ms[(i * b->dim2 + j) * fac]);
+  }
+  const size_t n_dir = size_t(2) * n_in, n_dif = size_t(n_diffuse_blocks) * 2;
+  std::vector<int32_t> dlen(n_dir), flen(n_dif ? n_dif : 1);
+  for (int o = 0; o < 2; ++o)
+    for (int i = 0; i < n_in; ++i) dlen[size_t(o) * n_in + i] = direct_process_size[o * direct_size_stride + i];
+  for (size_t i = 0; i < n_dif; ++i) flen[i] = diffuse_process_size[i];  // [block][2]
+  cudaError_t e = cudaMalloc(&b->d_mix, mix.size() * sizeof(float2));
+  if (e == cudaSuccess) e = cudaMemcpy(b->d_mix, mix.data(), mix.size() * sizeof(float2), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&b->d_hdirect, n_dir * N * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&b->d_hdiffuse, (n_dif ? n_dif : 1) * N * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&b->d_dlen, dlen.size() * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&b->d_flen, flen.size() * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&b->d_weight, size_t(n_in) * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(b->d_dlen, dlen.data(), dlen.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(b->d_flen, flen.data(), flen.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(b->d_weight, diffuse_weight, size_t(n_in) * sizeof(float), cudaMemcpyHostToDevice);
+  for (int o = 0; o < 2 && e == cudaSuccess; ++o)  // rows of N floats out of rows of row_stride floats
+    e = cudaMemcpy2D(b->d_hdirect + size_t(o) * n_in * N, size_t(N) * sizeof(float), h_direct + o * direct_ear_stride,
+                     direct_row_stride * sizeof(float), size_t(N) * sizeof(float), size_t(n_in), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && n_dif)
+    e = cudaMemcpy2D(b->d_hdiffuse, size_t(N) * sizeof(float), h_diffuse, diffuse_row_stride * sizeof(float),
+                     size_t(N) * sizeof(float), n_dif, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    b->release();
+    delete b;
+    return cuda_fail(ctx, e, "binaural_create_from_state");
+  }
+  *out = b;
+  return MPEGHB200_OK;
+}
+
 void mpeghb200_binaural_destroy(mpeghb200_binaural* b) {
   if (!b) return;
   cudaSetDevice(b->ctx->device);

@@ -33,7 +33,8 @@ typedef enum
   RQ_PCM,    /* ia_core_coder_samples_sat */
   RQ_HOAREN, /* impeghd_hoa_ren_block_process */
   RQ_RESAMPLE, /* impeghd_resample */
-  RQ_HOASP,  /* the four signal stages of impeghd_hoa_spatial_process */
+  RQ_HOASP,    /* the four signal stages of impeghd_hoa_spatial_process */
+  RQ_BINAURAL, /* impeghd_binaural_struct_process_ld_ola, one request per completed block */
   RQ_KINDS
 } seam_kind;
 
@@ -55,7 +56,7 @@ void seam_inline_unlock(void);
 typedef struct
 {
   unsigned long fd_gpu, fd_host, tns, lim, ltpf, fc, mct, obj, obj_host, pcm, batches, batch_calls, max_batch, hoa_ren,
-      hoa_ren_host, resample, hoa_spatial, hoa_spatial_host;
+      hoa_ren_host, resample, hoa_spatial, hoa_spatial_host, binaural, binaural_host;
 } seam_counters;
 extern seam_counters seam_n;
 

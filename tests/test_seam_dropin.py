@@ -363,3 +363,54 @@ def test_seam_hoa_spatial(tmp_path, cfg_idx):
     interleaved over ten frames with independency-frame gain resets, plainly and with the seam preloaded."""
     outs = _run_pair(tmp_path, HOASP_SCRIPT, (cfg_idx,), r"hoa_spatial gpu=(\d+) host=(\d+)", [30, 0])
     assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+
+
+BIN_SCRIPT = r"""
+import sys, os, ctypes, numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+import bin_cases
+from oracle import loader
+ref = loader.load_ref()
+n_in, length, nb, feed, out_path = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), sys.argv[6]
+rng = np.random.default_rng(n_in * 7 + length + nb)
+f = bin_cases.with_cutoffs(rng, bin_cases.brir_set(rng, n_in, length, nb))
+hs = []
+for s in range(2):   # two renderers with the same BRIR set (one GPU renderer, two state slots), interleaved
+    err = ctypes.c_int()
+    td, tdf = f["taps_direct"], f["taps_diffuse"]
+    hs.append(ref.ref_bin_create(n_in, length, nb, td.reshape(-1), np.ascontiguousarray(tdf).reshape(-1),
+                                 f["direct_fc"].reshape(-1).copy(), np.ascontiguousarray(f["diffuse_fc"]).reshape(-1),
+                                 f["weight"], 0, ctypes.byref(err)))
+    assert err.value == 0
+info = np.zeros(8, np.int32)
+ref.ref_bin_info(hs[0], info)
+B = int(info[2])
+T = 4
+x = [bin_cases.signal(rng, T, n_in, B) for _ in range(2)]
+streams = [np.concatenate(list(xx), axis=1) for xx in x]   # [n_in, T*B]
+outs = [[], []]
+buf = np.zeros((2, 32768), np.float32)
+pos = 0
+while pos < T * B:
+    n = min(feed, T * B - pos)
+    for s in range(2):
+        got = ref.ref_bin_process(hs[s], np.ascontiguousarray(streams[s][:, pos:pos + n]).reshape(-1), n, buf.reshape(-1), 32768)
+        if got:
+            outs[s].append(buf[:, :got].copy())
+    pos += n
+res = np.stack([np.concatenate(o, axis=1) for o in outs])
+assert res.shape[2] >= (T - 1) * B
+np.save(out_path, res)
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,blocks", [((24, 4096, 1, 1024), 8), ((5, 1024, 1, 1024), 8), ((21, 4096, 0, 1024), 8),
+                                        ((11, 3000, 1, 1000), 8), ((3, 700, 1, 2500), 8)])
+def test_seam_binaural(tmp_path, cfg, blocks):
+    """The interposed impeghd_binaural_struct_process_ld_ola (no shipped stream selects binaural rendering): the
+    reference's own init designs the filter spectra, the interposer takes them from ia_binaural_ren_pers_mem_str as
+    they are.  Fed 1024 samples per call like the decoder does, and with call lengths that leave partial blocks
+    (1000) or complete two blocks in one call (2500 at B = 1024); two renderers interleaved share one GPU renderer."""
+    outs = _run_pair(tmp_path, BIN_SCRIPT, cfg, r"binaural_blocks gpu=(\d+) host\(calls\)=(\d+)", [blocks, 0])
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
