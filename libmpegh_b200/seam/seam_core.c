@@ -58,11 +58,13 @@ static void seam_stats(void)
             "ltpf_frames gpu=%lu format_conv_frames gpu=%lu mct_boxes gpu=%lu kernel_launches=%llu "
             "obj_render gpu=%lu host(sub-frames)=%lu pcm_pack gpu=%lu batch_calls=%lu backend_rounds=%lu max_batch=%lu "
             "hoa_render gpu=%lu host=%lu resample gpu=%lu hoa_spatial gpu=%lu host=%lu "
-            "binaural_blocks gpu=%lu host(calls)=%lu\n",
+            "binaural_blocks gpu=%lu host(calls)=%lu "
+            "stereo_tools gpu=%lu host=%lu igf mono=%lu tnf=%lu stereo=%lu host=%lu\n",
             seam_n.fd_gpu, seam_n.fd_host, seam_n.tns, seam_n.lim, seam_n.ltpf, seam_n.fc, seam_n.mct,
             g_ctx ? (unsigned long long)mpeghb200_launch_count(g_ctx) : 0ull, seam_n.obj, seam_n.obj_host, seam_n.pcm,
             seam_n.batch_calls, seam_n.batches, seam_n.max_batch, seam_n.hoa_ren, seam_n.hoa_ren_host, seam_n.resample, seam_n.hoa_spatial,
-            seam_n.hoa_spatial_host, seam_n.binaural, seam_n.binaural_host);
+            seam_n.hoa_spatial_host, seam_n.binaural, seam_n.binaural_host, seam_n.stereo, seam_n.stereo_host, seam_n.igf,
+            seam_n.igf_tnf, seam_n.igf_stereo, seam_n.igf_host);
 }
 
 mpeghb200_ctx *seam_ctx(void)

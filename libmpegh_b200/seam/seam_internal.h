@@ -35,6 +35,9 @@ typedef enum
   RQ_RESAMPLE, /* impeghd_resample */
   RQ_HOASP,    /* the four signal stages of impeghd_hoa_spatial_process */
   RQ_BINAURAL, /* impeghd_binaural_struct_process_ld_ola, one request per completed block */
+  RQ_STEREO,   /* impeghd_ms_stereo, ia_core_coder_cplx_pred_upmixing */
+  RQ_IGF,      /* ia_core_coder_igf_mono (+ its TNF step), ia_core_coder_igf_tnf */
+  RQ_IGFST,    /* ia_core_coder_igf_apply_stereo */
   RQ_KINDS
 } seam_kind;
 
@@ -56,7 +59,7 @@ void seam_inline_unlock(void);
 typedef struct
 {
   unsigned long fd_gpu, fd_host, tns, lim, ltpf, fc, mct, obj, obj_host, pcm, batches, batch_calls, max_batch, hoa_ren,
-      hoa_ren_host, resample, hoa_spatial, hoa_spatial_host, binaural, binaural_host;
+      hoa_ren_host, resample, hoa_spatial, hoa_spatial_host, binaural, binaural_host, stereo, stereo_host, igf, igf_tnf, igf_stereo, igf_host;
 } seam_counters;
 extern seam_counters seam_n;
 

@@ -168,18 +168,8 @@ def oracle_samples_sat(planar, pcmsize, ch_map=None, delay=0):
     return out[:nb].copy(), int(d[0])
 
 
-def load_ref():
-    """The reference build, or None if oracle/_ref has not been built."""
-    global _ref
-    if _ref is not None:
-        return _ref
-    so = os.path.join(HERE, "_ref", "libmpeghref.so")
-    if not os.path.exists(so):
-        if os.path.isdir("/root/reference/decoder"):
-            build("ref")
-        else:
-            return None
-    lib = ctypes.CDLL(so)
+def _bind_harnesses(lib):
+    """ctypes signatures of the function-level harnesses (oracle/ref_harness_*.c): both reference builds carry them."""
     lib.ref_fd_create.restype = ctypes.c_void_p
     lib.ref_fd_destroy.argtypes = [ctypes.c_void_p]
     lib.ref_fd_frm_dec.argtypes = [ctypes.c_void_p, _f32p, _f32p, _f32p] + [ctypes.c_int] * 5
@@ -278,6 +268,21 @@ def load_ref():
     lib.ref_rs_destroy.argtypes = [ctypes.c_void_p]
     lib.ref_rs_filters.argtypes = [_f32p, _f32p]
     lib.ref_rs_process.argtypes = [ctypes.c_void_p, _f32p, _f32p]
+
+
+def load_ref():
+    """The reference build, or None if oracle/_ref has not been built."""
+    global _ref
+    if _ref is not None:
+        return _ref
+    so = os.path.join(HERE, "_ref", "libmpeghref.so")
+    if not os.path.exists(so):
+        if os.path.isdir("/root/reference/decoder"):
+            build("ref")
+        else:
+            return None
+    lib = ctypes.CDLL(so)
+    _bind_harnesses(lib)
     _ref = lib
     return lib
 
@@ -431,6 +436,7 @@ def load_ref_ns():
         else:
             return None
     lib = ctypes.CDLL(so)
+    _bind_harnesses(lib)
     lib.ref_samples_sat.argtypes = [_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _i32p, _i32p, _u8p]
     lib.ref_samples_sat.restype = ctypes.c_int
     _i32q = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")

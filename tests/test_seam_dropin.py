@@ -414,3 +414,134 @@ def test_seam_binaural(tmp_path, cfg, blocks):
     (1000) or complete two blocks in one call (2500 at B = 1024); two renderers interleaved share one GPU renderer."""
     outs = _run_pair(tmp_path, BIN_SCRIPT, cfg, r"binaural_blocks gpu=(\d+) host\(calls\)=(\d+)", [blocks, 0])
     assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+
+
+CPE_SCRIPT = r"""
+import sys, os, numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+import stereo_cases, tns_cases
+from oracle import loader
+which, out_path = sys.argv[2], sys.argv[3]
+ref = loader.load_ref() if which == "stock" else loader.load_ref_ns()
+outs = []
+for seed in range(6):
+    rng = np.random.default_rng(9000 + seed)
+    frames = stereo_cases.random_pair_sequence(rng, 8)
+    coef = rng.normal(0, 800, (8, 2, 1024)).astype(np.float32)
+    h = ref.ref_cpe_create(stereo_cases.SAMPLING_RATE_IDX, tns_cases.TNS_MAX_LONG, tns_cases.TNS_MAX_SHORT)
+    pcm, spec = np.zeros((8, 2, 1024), np.float32), np.zeros((8, 2, 1024), np.float32)
+    for f, fr in enumerate(frames):
+        err = ref.ref_cpe_process(h, fr["sd"].tobytes(), fr["grp"], fr["tns_on_lr"],
+                                  np.ascontiguousarray(fr["n_filt"].reshape(-1)),
+                                  np.ascontiguousarray(fr["filt"].reshape(-1)), fr["max_sfb"], coef[f, 0], coef[f, 1],
+                                  pcm[f, 0], pcm[f, 1], spec[f, 0], spec[f, 1])
+        assert err == 0, err
+    ref.ref_cpe_destroy(h)
+    outs.append(np.stack([pcm, spec]))
+np.save(out_path, np.stack(outs))
+"""
+
+
+def _cpe_tool_counts():
+    import stereo_cases
+    ms = cplx = 0
+    for seed in range(6):
+        rng = np.random.default_rng(9000 + seed)
+        for fr in stereo_cases.random_pair_sequence(rng, 8):
+            tool = int(fr["sd"]["tool"])
+            ms += tool in (1, 2)
+            cplx += tool == 3
+    return ms, cplx
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["stock", "ns"])
+def test_seam_stereo_tools(tmp_path, which):
+    """ia_core_coder_data_process of the unmodified reference on a channel pair (oracle/ref_harness_cpe.c fills
+    ia_usac_data_struct the way the parser does): M/S and complex prediction, long and short blocks with window groups,
+    TNS before or after the stereo tools, spectrum save, FD synthesis.  With the seam preloaded impeghd_ms_stereo
+    becomes a GPU call; ia_core_coder_cplx_pred_upmixing too in the reference build that gives it external linkage
+    ("ns"), while against the stock library complex prediction stays in the reference.  PCM and saved spectra agree
+    bit for bit either way."""
+    if which == "ns":
+        _need(os.path.join(REF_DIR, "libmpeghref_ns.so"))
+    ms, cplx = _cpe_tool_counts()
+    assert ms > 5 and cplx > 5
+    outs = _run_pair(tmp_path, CPE_SCRIPT, (which,), r"stereo_tools gpu=(\d+) host=(\d+)",
+                     [ms + (cplx if which == "ns" else 0), 0])
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+
+
+IGF_SCRIPT = r"""
+import sys, os, numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests"); sys.path.insert(0, sys.argv[1] + "/tests/golden")
+import igf_cases
+import make_igf_golden as mg
+from oracle import loader
+ref = loader.load_ref()
+mode, out_path = sys.argv[2], sys.argv[3]
+outs, seeds = [], []
+for ci, cfg in enumerate(igf_cases.CONFIGS):
+    h, grid = mg.reference_grid(cfg)
+    rng = np.random.default_rng((12000 if mode == "mono" else 14000) + ci)
+    for k in range(24):
+        wt = int(rng.random() < 0.3)
+        if mode == "mono":
+            sd, coef, tiles = igf_cases.random_frame(rng, cfg, grid, win_type=wt)
+            y = coef.copy()
+            seeds.append([ref.ref_igf_process(h, sd.tobytes(), y, tiles), 0])
+            outs.append(np.stack([y, y]))
+        else:
+            sd_l, sd_r, mask, coef, tiles = igf_cases.random_pair_frame(rng, cfg, grid, win_type=wt)
+            ms_after = int(rng.integers(2))
+            y = coef.copy()
+            sv = np.zeros(2, np.uint32)
+            ref.ref_igf_stereo_process(h, sd_l.tobytes(), sd_r.tobytes(), igf_cases.mask_reference_layout(mask, sd_l),
+                                       ms_after, y[0], y[1], np.ascontiguousarray(tiles[0]).reshape(-1),
+                                       np.ascontiguousarray(tiles[1]).reshape(-1), sv)
+            seeds.append([int(sv[0]), int(sv[1])])
+            outs.append(y)
+    ref.ref_igf_destroy(h)
+res = np.concatenate([np.stack(outs).reshape(len(outs), -1),
+                      np.array(seeds, np.uint32).view(np.float32).reshape(len(outs), 2)], axis=1)
+np.save(out_path, res)
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["mono", "stereo"])
+def test_seam_igf(tmp_path, mode):
+    """The interposed IGF entry points of the unmodified reference through oracle/ref_harness_cpe.c: the mono path
+    (ia_core_coder_igf_mono + ia_core_coder_igf_tnf, the side record filled from igf_config / igf_dec_data / seed_value
+    of the real ia_usac_data_struct, TNF spectrum and mask carried in the struct) and the joint-stereo path
+    (ia_core_coder_igf_apply_stereo, then impeghd_ms_stereo over the IGF range on the spectra and on the TNF spectra,
+    then ia_core_coder_igf_tnf per channel), long and short blocks, all configurations of igf_cases.CONFIGS; spectra
+    and noise seeds agree bit for bit."""
+    rx = r"igf mono=(\d+) tnf=(\d+) stereo=(\d+) host=(\d+)"
+    libref = os.path.join(REF_DIR, "libmpeghref.so")
+    _need(libref, SEAM)
+    script = tmp_path / "h.py"
+    script.write_text(IGF_SCRIPT)
+    outs = []
+    for preload in (None, SEAM):
+        env = dict(os.environ)
+        if preload:
+            env["LD_PRELOAD"], env["MPEGHB200_SEAM_STATS"] = preload, "1"
+        out = str(tmp_path / ("gpu.npy" if preload else "ref.npy"))
+        r = subprocess.run([sys.executable, str(script), ROOT, mode, out], env=env, capture_output=True, text=True,
+                           timeout=900)
+        assert r.returncode == 0, r.stderr[-800:]
+        if preload:
+            m = re.search(rx, r.stderr)
+            assert m, r.stderr[-400:]
+            mono, tnf, st, host = (int(x) for x in m.groups())
+            import igf_cases
+            n = 24 * len(igf_cases.CONFIGS)
+            print(mode, dict(mono=mono, tnf=tnf, stereo=st, host=host))
+            assert host == 0
+            if mode == "mono":
+                assert mono == n and st == 0
+            else:
+                assert 0 < st <= n and mono == 0  # pairs with both channels silent never reach the tool
+        outs.append(np.load(out))
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
