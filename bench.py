@@ -316,12 +316,12 @@ def cpu_chain_baseline(spec, n_threads, sample_streams, n_frames, repeats=1):
             "ms_per_unit": t / units * 1e3, "audio_s_per_wall_s": S * n_frames * repeats * 1024 / 48000.0 / t}
 
 
-def cpu_testbench_baseline(n_proc, repeats=8):
+def cpu_testbench_baseline(n_proc, repeats=8, stream_name="sine_1khz_000_cicp1.mhas", channels=1):
     """BASELINE.json configs[0]: the UNMODIFIED reference testbench (oracle/_ref/ia_mpeghd_testbench, built from
     /root/reference by oracle/Makefile) decoding smoke_test_suite/inp/sine_1khz_000_cicp1.mhas on the host cores, one
     process per core, `repeats` decodes each.  None when the build did not travel."""
     tb = os.path.join(ROOT, "oracle", "_ref", "ia_mpeghd_testbench")
-    stream = os.path.join(ROOT, "oracle", "_ref", "smoke", "sine_1khz_000_cicp1.mhas")
+    stream = os.path.join(ROOT, "oracle", "_ref", "smoke", stream_name)
     if not (os.path.exists(tb) and os.path.exists(stream)):
         return None
     import tempfile
@@ -336,10 +336,10 @@ def cpu_testbench_baseline(n_proc, repeats=8):
     if any(rcs):
         return None
     audio_s = n_proc * repeats * 469 * 1024 / 48000.0   # 469 output frames of one channel per decode
-    return {"workload": "configs[0]: sine_1khz_000_cicp1.mhas through the unmodified ia_mpeghd_testbench (parse + "
+    return {"workload": f"configs[0]: {stream_name} through the unmodified ia_mpeghd_testbench (parse + "
                         "signal path + WAV write), one process per host core",
             "processes": n_proc, "decodes_per_process": repeats, "wall_s": dt, "audio_s_per_wall_s": audio_s / dt,
-            "value": audio_s * 48000.0 / dt, "unit": UNIT, "kind": "reference"}
+            "value": audio_s * 48000.0 * channels / dt, "unit": UNIT, "kind": "reference"}
 
 
 # bounded CPU samples: (streams per thread, frames) sized for about a second of work per thread

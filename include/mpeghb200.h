@@ -588,6 +588,11 @@ mpeghb200_status mpeghb200_bus_add_dev(mpeghb200_ctx *ctx, const float *d_a, con
                                        size_t n_floats, void *cuda_stream);
 mpeghb200_status mpeghb200_channel_mask_dev(mpeghb200_ctx *ctx, float *d_audio, const uint8_t *d_on, int n_channels,
                                             void *cuda_stream);
+/* Planar <-> interleaved, per stream: to_planar != 0 turns d_in [stream][n_samples][n_ch] into d_out
+ * [stream][n_ch][n_samples], 0 the reverse (the interleaved copy impegh_dec_peak_limiter builds around the limiter,
+ * decoder/ia_core_coder_decode_main.c:1429-1460).  n_ch <= 64 (33 KB of shared memory at most); d_in != d_out. */
+mpeghb200_status mpeghb200_interleave_dev(mpeghb200_ctx *ctx, const float *d_in, float *d_out, int n_ch, int n_samples,
+                                          int to_planar, int n_streams, void *cuda_stream);
 /* Per-sample gain curves: d_audio[c][s] *= d_gains[d_seq_of_ch[c]][s] for every
  * channel with d_seq_of_ch[c] >= 0 -- the time-domain application of single-band DRC gain sequences,
  * impd_drc_apply_gains_and_add (decoder/impd_drc_process.c:68-175).  Gain decoding, DRC set selection and the

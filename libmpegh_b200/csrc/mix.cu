@@ -41,6 +41,42 @@ __global__ void __launch_bounds__(256)
   audio[size_t(c) * 256 + threadIdx.x] = x;
 }
 
+// Planar <-> interleaved.  The reference's limiter works on an interleaved copy of the frame ([sample][channel],
+// impegh_dec_peak_limiter, decoder/ia_core_coder_decode_main.c:1429-1460); the kernels are planar.  A CTA moves a tile of
+// 128 samples of one stream through shared memory so that both sides are contiguous in global memory.
+constexpr int kIlvTile = 128;
+__global__ void __launch_bounds__(256)
+    interleave_kernel(const float* __restrict__ in, float* __restrict__ out, int n_ch, int n_samples, int to_planar) {
+  extern __shared__ float tile[];  // [n_ch][kIlvTile + 1]
+  const size_t s = blockIdx.y;
+  const int j0 = blockIdx.x * kIlvTile;
+  const int nj = min(kIlvTile, n_samples - j0);
+  const float* src = in + s * size_t(n_ch) * n_samples;
+  float* dst = out + s * size_t(n_ch) * n_samples;
+  const int total = nj * n_ch;
+  if (to_planar) {
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {  // e = j * n_ch + c, contiguous in the source
+      const int j = e / n_ch, c = e - j * n_ch;
+      tile[c * (kIlvTile + 1) + j] = src[size_t(j0) * n_ch + e];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {  // e = c * nj + j, rows contiguous in the destination
+      const int c = e / nj, j = e - c * nj;
+      dst[size_t(c) * n_samples + j0 + j] = tile[c * (kIlvTile + 1) + j];
+    }
+  } else {
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+      const int c = e / nj, j = e - c * nj;
+      tile[c * (kIlvTile + 1) + j] = src[size_t(c) * n_samples + j0 + j];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+      const int j = e / n_ch, c = e - j * n_ch;
+      dst[size_t(j0) * n_ch + e] = tile[c * (kIlvTile + 1) + j];
+    }
+  }
+}
+
 // DRC gains in the STFT domain: 4 time slots x 256 bands per channel-frame, re / im planes; im[0] of a slot is the
 // Nyquist bin.  impd_drc_apply_gains_subband (decoder/impd_drc_process.c:243-385): a single-band group multiplies
 // everything by the slot's gain; a multi-band group forms the band gain as the ordered sum of overlap weight x
@@ -103,6 +139,21 @@ mpeghb200_status mpeghb200_bus_add_dev(mpeghb200_ctx* ctx, const float* d_a, con
   const int grid = int(want < size_t(ctx->sm_count) * 8 ? want : size_t(ctx->sm_count) * 8);
   bus_add_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
       reinterpret_cast<const float4*>(d_a), reinterpret_cast<const float4*>(d_b), reinterpret_cast<float4*>(d_out), n4);
+  ctx->launches.fetch_add(1);
+  MB_CUDA(ctx, cudaGetLastError());
+  return MPEGHB200_OK;
+}
+
+mpeghb200_status mpeghb200_interleave_dev(mpeghb200_ctx* ctx, const float* d_in, float* d_out, int n_ch, int n_samples,
+                                          int to_planar, int n_streams, void* cuda_stream) {
+  if (!ctx) return MPEGHB200_ERR_BAD_ARG;
+  if (n_streams < 0 || n_ch < 1 || n_ch > 64 || n_samples < 1 || (n_streams > 0 && (!d_in || !d_out || d_in == d_out)))
+    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "interleave_dev: 1..64 channels, distinct non-null buffers");
+  if (n_streams == 0) return MPEGHB200_OK;
+  MB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t smem = size_t(n_ch) * (kIlvTile + 1) * sizeof(float);
+  interleave_kernel<<<dim3((n_samples + kIlvTile - 1) / kIlvTile, n_streams), 256, smem,
+                      static_cast<cudaStream_t>(cuda_stream)>>>(d_in, d_out, n_ch, n_samples, to_planar != 0);
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   return MPEGHB200_OK;

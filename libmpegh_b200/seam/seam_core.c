@@ -29,6 +29,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/mman.h>
+#include <time.h>
 #include <ucontext.h>
 #include <unistd.h>
 
@@ -41,6 +42,7 @@ seam_counters seam_n;
 static mpeghb200_ctx *g_ctx;
 static seam_backend g_backend[RQ_KINDS];
 static const char *g_backend_name[RQ_KINDS];
+static double g_t_parse, g_t_backend[RQ_KINDS]; /* wall time of the batch scheduler: handles running / back-end rounds */
 static pthread_mutex_t g_init_mu = PTHREAD_MUTEX_INITIALIZER;
 
 void seam_die(const char *what, mpeghb200_status st)
@@ -65,6 +67,15 @@ static void seam_stats(void)
             seam_n.batch_calls, seam_n.batches, seam_n.max_batch, seam_n.hoa_ren, seam_n.hoa_ren_host, seam_n.resample, seam_n.hoa_spatial,
             seam_n.hoa_spatial_host, seam_n.binaural, seam_n.binaural_host, seam_n.stereo, seam_n.stereo_host, seam_n.igf,
             seam_n.igf_tnf, seam_n.igf_stereo, seam_n.igf_host);
+  if (getenv("MPEGHB200_SEAM_STATS") && g_t_parse > 0.0)
+  {
+    int k;
+    fprintf(stderr, "mpeghb200 seam: batch scheduler wall time: reference code on the parse threads %.3f s", g_t_parse);
+    for (k = 0; k < RQ_KINDS; k++)
+      if (g_t_backend[k] > 0.0)
+        fprintf(stderr, ", %s %.3f s", g_backend_name[k] ? g_backend_name[k] : "?", g_t_backend[k]);
+    fprintf(stderr, "\n");
+  }
 }
 
 mpeghb200_ctx *seam_ctx(void)
@@ -250,9 +261,20 @@ static struct
   coro *batch;
   int n;
   volatile int quit;
+  seam_par_fn job; /* non-NULL: the round is a parallel loop of a back-end, not handles to run */
+  void *job_arg;
+  int job_n;
 } g_pool;
+static int g_in_round; /* the scheduler is serving back-ends: the workers sit at the `go` barrier */
 static char **g_stacks;
 static int g_n_stacks;
+
+static double now_s(void)
+{
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
 
 static void run_slice(coro *batch, int n, int first, int step)
 {
@@ -276,7 +298,14 @@ static void *worker_main(void *arg)
     pthread_barrier_wait(&g_pool.go);
     if (g_pool.quit)
       break;
-    run_slice(g_pool.batch, g_pool.n, w->idx + 1, g_pool.n_workers + 1);
+    if (g_pool.job)
+    {
+      int i;
+      for (i = w->idx + 1; i < g_pool.job_n; i += g_pool.n_workers + 1)
+        g_pool.job(i, g_pool.job_arg);
+    }
+    else
+      run_slice(g_pool.batch, g_pool.n, w->idx + 1, g_pool.n_workers + 1);
     pthread_barrier_wait(&g_pool.done);
   }
   return NULL;
@@ -303,6 +332,25 @@ static void pool_start(void)
     g_pool.w[i].idx = i;
     pthread_create(&g_pool.w[i].th, NULL, worker_main, &g_pool.w[i]);
   }
+}
+
+/* The gather / scatter loops of a back-end, spread over the parse threads (idle while the scheduler serves a round).
+ * Outside a batch round (a single handle, an interposed call made from outside ia_mpegh_dec_execute) it is a plain loop. */
+void seam_parallel_for(int n, seam_par_fn fn, void *arg)
+{
+  int i;
+  if (!g_in_round || g_pool.n_workers == 0 || n < 2 * (g_pool.n_workers + 1))
+  {
+    for (i = 0; i < n; i++)
+      fn(i, arg);
+    return;
+  }
+  g_pool.job = fn, g_pool.job_arg = arg, g_pool.job_n = n;
+  pthread_barrier_wait(&g_pool.go);
+  for (i = 0; i < n; i += g_pool.n_workers + 1)
+    fn(i, arg);
+  pthread_barrier_wait(&g_pool.done);
+  g_pool.job = NULL;
 }
 
 /* The format converter and the MCT boxes are not request-ised yet: they compute inside the interposer with shared
@@ -360,6 +408,7 @@ IA_ERRORCODE mpeghb200_dec_execute_batch(pVOID *objs, pVOID *ins, pVOID *outs, W
   for (;;)
   {
     const int use_workers = g_pool.n_workers > 0 && n > 1;
+    double t0 = now_s(), t1;
     /* run every coroutine that is neither finished nor parked until it parks or finishes */
     if (use_workers)
     {
@@ -372,6 +421,7 @@ IA_ERRORCODE mpeghb200_dec_execute_batch(pVOID *objs, pVOID *ins, pVOID *outs, W
     {
       run_slice(batch, n, 0, 1);
     }
+    g_t_parse += now_s() - t0;
     remaining = 0;
     for (i = 0; i < n; i++)
       remaining += !batch[i].done;
@@ -386,7 +436,11 @@ IA_ERRORCODE mpeghb200_dec_execute_batch(pVOID *objs, pVOID *ins, pVOID *outs, W
           reqs[m++] = batch[i].pending;
       if (!m)
         continue;
+      t1 = now_s();
+      g_in_round = use_workers;
       g_backend[k](reqs, m);
+      g_in_round = 0;
+      g_t_backend[k] += now_s() - t1;
       seam_n.batches++;
       for (i = 0; i < n; i++)
         if (!batch[i].done && batch[i].pending && batch[i].pending->kind == k)

@@ -63,6 +63,10 @@ typedef struct
 } seam_counters;
 extern seam_counters seam_n;
 
+/* gather / scatter loops of a back-end on all parse threads: fn(i, arg) for i in [0, n), any order, any thread */
+typedef void (*seam_par_fn)(int i, void *arg);
+void seam_parallel_for(int n, seam_par_fn fn, void *arg);
+
 /* ---- staging buffers that grow on demand: page-locked host + device of the same size ---- */
 typedef struct
 {

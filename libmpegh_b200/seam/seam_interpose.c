@@ -77,23 +77,32 @@
 /* ---- FD synthesis ------------------------------------------------------------------------------------ */
 static seam_buf b_coef, b_ovl, b_out, b_side;
 
+static void fd_gather(int i, void *arg)
+{
+  seam_req **rq = (seam_req **)arg;
+  ia_usac_data_struct *u = (ia_usac_data_struct *)rq[i]->p[0];
+  const int ch = (int)rq[i]->v[0];
+  memcpy((float *)b_coef.h + (size_t)i * FRAME, u->coef[ch], FRAME * sizeof(float));
+  memcpy((float *)b_ovl.h + (size_t)i * FRAME, u->overlap_data_ptr[ch], FRAME * sizeof(float));
+  ((uint32_t *)b_side.h)[i] = MPEGHB200_FD_SIDE(u->window_sequence[ch], u->window_shape[ch], u->window_shape_prev[ch],
+                                                u->prev_aliasing_symmetry[ch], u->curr_aliasing_symmetry[ch]);
+}
+static void fd_scatter(int i, void *arg)
+{
+  seam_req **rq = (seam_req **)arg;
+  ia_usac_data_struct *u = (ia_usac_data_struct *)rq[i]->p[0];
+  const int ch = (int)rq[i]->v[0];
+  memcpy(u->time_sample_vector[ch], (float *)b_out.h + (size_t)i * FRAME, FRAME * sizeof(float));
+  memcpy(u->overlap_data_ptr[ch], (float *)b_ovl.h + (size_t)i * FRAME, FRAME * sizeof(float));
+}
+
 /* p[0] = usac_data, v[0] = channel */
 static void be_fd(seam_req **rq, int n)
 {
   mpeghb200_ctx *ctx = seam_ctx();
   const size_t fb = (size_t)n * FRAME * sizeof(float);
-  int i;
   seam_need(&b_coef, fb), seam_need(&b_ovl, fb), seam_need(&b_out, fb), seam_need(&b_side, (size_t)n * sizeof(uint32_t));
-  for (i = 0; i < n; i++)
-  {
-    ia_usac_data_struct *u = (ia_usac_data_struct *)rq[i]->p[0];
-    const int ch = (int)rq[i]->v[0];
-    memcpy((float *)b_coef.h + (size_t)i * FRAME, u->coef[ch], FRAME * sizeof(float));
-    memcpy((float *)b_ovl.h + (size_t)i * FRAME, u->overlap_data_ptr[ch], FRAME * sizeof(float));
-    ((uint32_t *)b_side.h)[i] =
-        MPEGHB200_FD_SIDE(u->window_sequence[ch], u->window_shape[ch], u->window_shape_prev[ch],
-                          u->prev_aliasing_symmetry[ch], u->curr_aliasing_symmetry[ch]);
-  }
+  seam_parallel_for(n, fd_gather, rq);
   CK(mpeghb200_h2d(ctx, b_coef.d, b_coef.h, fb));
   CK(mpeghb200_h2d(ctx, b_ovl.d, b_ovl.h, fb));
   CK(mpeghb200_h2d(ctx, b_side.d, b_side.h, (size_t)n * sizeof(uint32_t)));
@@ -101,13 +110,7 @@ static void be_fd(seam_req **rq, int n)
                             n, NULL));
   CK(mpeghb200_d2h(ctx, b_out.h, b_out.d, fb));
   CK(mpeghb200_d2h(ctx, b_ovl.h, b_ovl.d, fb));
-  for (i = 0; i < n; i++)
-  {
-    ia_usac_data_struct *u = (ia_usac_data_struct *)rq[i]->p[0];
-    const int ch = (int)rq[i]->v[0];
-    memcpy(u->time_sample_vector[ch], (float *)b_out.h + (size_t)i * FRAME, FRAME * sizeof(float));
-    memcpy(u->overlap_data_ptr[ch], (float *)b_ovl.h + (size_t)i * FRAME, FRAME * sizeof(float));
-  }
+  seam_parallel_for(n, fd_scatter, rq);
   seam_n.fd_gpu += (unsigned long)n;
 }
 
@@ -273,34 +276,53 @@ VOID impeghd_mc_process(ia_multichannel_data *ptr_mc_data, FLOAT32 *ptr_dmx, FLO
 static seam_buf b_ltpf_state, b_ltpf_side, b_ltpf_audio;
 
 /* p[0] = ia_ltpf_data_str, p[1] = time_sample_vector */
+static void ltpf_gather(int i, void *arg)
+{
+  seam_req **rq = (seam_req **)arg;
+  const size_t ns = mpeghb200_ltpf_state_floats(48000);
+  const ia_ltpf_data_str *l = (const ia_ltpf_data_str *)rq[i]->p[0];
+  const int hist = l->pitch_max + LTPF_NUM_FILT_COEF1 / 2;
+  float *st = (float *)b_ltpf_state.h + (size_t)i * ns;
+  mpeghb200_ltpf_side *sd = (mpeghb200_ltpf_side *)b_ltpf_side.h + i;
+  int32_t iv;
+  memset(st, 0, ns * sizeof(float));
+  iv = l->prev_pitch, memcpy(&st[0], &iv, 4);
+  iv = l->prev_pitch_fr, memcpy(&st[1], &iv, 4);
+  iv = l->prev_gain_idx, memcpy(&st[2], &iv, 4);
+  st[3] = l->prev_gain;
+  memcpy(&st[4], l->prev_in_buf, 6 * sizeof(float));
+  memcpy(&st[16], l->prev_out_buf, (size_t)hist * sizeof(float));
+  sd->unit = i;
+  sd->data_present = (uint8_t)l->data_present;
+  sd->pitch_lag_idx = (uint16_t)l->pitch_lag_idx;
+  sd->gain_idx = (uint8_t)l->gain_idx;
+  memcpy((float *)b_ltpf_audio.h + (size_t)i * FRAME, rq[i]->p[1], FRAME * sizeof(float));
+}
+static void ltpf_scatter(int i, void *arg)
+{
+  seam_req **rq = (seam_req **)arg;
+  const size_t ns = mpeghb200_ltpf_state_floats(48000);
+  ia_ltpf_data_str *l = (ia_ltpf_data_str *)rq[i]->p[0];
+  const int hist = l->pitch_max + LTPF_NUM_FILT_COEF1 / 2;
+  const float *st = (const float *)b_ltpf_state.h + (size_t)i * ns;
+  int32_t iv;
+  memcpy(&iv, &st[0], 4), l->prev_pitch = iv;
+  memcpy(&iv, &st[1], 4), l->prev_pitch_fr = iv;
+  memcpy(&iv, &st[2], 4), l->prev_gain_idx = iv;
+  l->prev_gain = st[3];
+  memcpy(l->prev_in_buf, &st[4], 6 * sizeof(float));
+  memcpy(l->prev_out_buf, &st[16], (size_t)hist * sizeof(float));
+  memcpy(rq[i]->p[1], (float *)b_ltpf_audio.h + (size_t)i * FRAME, FRAME * sizeof(float));
+}
+
 static void be_ltpf(seam_req **rq, int n)
 {
   mpeghb200_ctx *ctx = seam_ctx();
   const size_t ns = mpeghb200_ltpf_state_floats(48000);
-  int i;
   seam_need(&b_ltpf_state, (size_t)n * ns * sizeof(float));
   seam_need(&b_ltpf_side, (size_t)n * sizeof(mpeghb200_ltpf_side));
   seam_need(&b_ltpf_audio, (size_t)n * FRAME * sizeof(float));
-  memset(b_ltpf_state.h, 0, (size_t)n * ns * sizeof(float));
-  for (i = 0; i < n; i++)
-  {
-    const ia_ltpf_data_str *l = (const ia_ltpf_data_str *)rq[i]->p[0];
-    const int hist = l->pitch_max + LTPF_NUM_FILT_COEF1 / 2;
-    float *st = (float *)b_ltpf_state.h + (size_t)i * ns;
-    mpeghb200_ltpf_side *sd = (mpeghb200_ltpf_side *)b_ltpf_side.h + i;
-    int32_t iv;
-    iv = l->prev_pitch, memcpy(&st[0], &iv, 4);
-    iv = l->prev_pitch_fr, memcpy(&st[1], &iv, 4);
-    iv = l->prev_gain_idx, memcpy(&st[2], &iv, 4);
-    st[3] = l->prev_gain;
-    memcpy(&st[4], l->prev_in_buf, 6 * sizeof(float));
-    memcpy(&st[16], l->prev_out_buf, (size_t)hist * sizeof(float));
-    sd->unit = i;
-    sd->data_present = (uint8_t)l->data_present;
-    sd->pitch_lag_idx = (uint16_t)l->pitch_lag_idx;
-    sd->gain_idx = (uint8_t)l->gain_idx;
-    memcpy((float *)b_ltpf_audio.h + (size_t)i * FRAME, rq[i]->p[1], FRAME * sizeof(float));
-  }
+  seam_parallel_for(n, ltpf_gather, rq);
   CK(mpeghb200_h2d(ctx, b_ltpf_state.d, b_ltpf_state.h, (size_t)n * ns * sizeof(float)));
   CK(mpeghb200_h2d(ctx, b_ltpf_side.d, b_ltpf_side.h, (size_t)n * sizeof(mpeghb200_ltpf_side)));
   CK(mpeghb200_h2d(ctx, b_ltpf_audio.d, b_ltpf_audio.h, (size_t)n * FRAME * sizeof(float)));
@@ -308,20 +330,7 @@ static void be_ltpf(seam_req **rq, int n)
                         (float *)b_ltpf_state.d, n, NULL));
   CK(mpeghb200_d2h(ctx, b_ltpf_audio.h, b_ltpf_audio.d, (size_t)n * FRAME * sizeof(float)));
   CK(mpeghb200_d2h(ctx, b_ltpf_state.h, b_ltpf_state.d, (size_t)n * ns * sizeof(float)));
-  for (i = 0; i < n; i++)
-  {
-    ia_ltpf_data_str *l = (ia_ltpf_data_str *)rq[i]->p[0];
-    const int hist = l->pitch_max + LTPF_NUM_FILT_COEF1 / 2;
-    const float *st = (const float *)b_ltpf_state.h + (size_t)i * ns;
-    int32_t iv;
-    memcpy(&iv, &st[0], 4), l->prev_pitch = iv;
-    memcpy(&iv, &st[1], 4), l->prev_pitch_fr = iv;
-    memcpy(&iv, &st[2], 4), l->prev_gain_idx = iv;
-    l->prev_gain = st[3];
-    memcpy(l->prev_in_buf, &st[4], 6 * sizeof(float));
-    memcpy(l->prev_out_buf, &st[16], (size_t)hist * sizeof(float));
-    memcpy(rq[i]->p[1], (float *)b_ltpf_audio.h + (size_t)i * FRAME, FRAME * sizeof(float));
-  }
+  seam_parallel_for(n, ltpf_scatter, rq);
   seam_n.ltpf += (unsigned long)n;
 }
 
@@ -383,6 +392,22 @@ IA_ERRORCODE impeghd_peak_limiter_init(ia_peak_limiter_struct *pstr_peak_limiter
   return real(pstr_peak_limiter, channel_num, sample_rate, ptr_buff);
 }
 
+typedef struct
+{
+  seam_req **rq;
+  size_t bytes;
+} lim_arg;
+static void lim_gather(int i, void *arg)
+{
+  const lim_arg *a = (const lim_arg *)arg;
+  memcpy((char *)b_lim_in.h + (size_t)i * a->bytes, a->rq[i]->p[1], a->bytes);
+}
+static void lim_scatter(int i, void *arg)
+{
+  const lim_arg *a = (const lim_arg *)arg;
+  memcpy(a->rq[i]->p[1], (const char *)b_lim_out.h + (size_t)i * a->bytes, a->bytes);
+}
+
 /* one group: n requests with the same channel count / rate / mode.  p[0] = ia_peak_limiter_struct, p[1] = samples
  * (interleaved [1024][n_ch], in place) */
 static void lim_group(seam_req **rq, int n)
@@ -396,23 +421,20 @@ static void lim_group(seam_req **rq, int n)
   const void **keys = (const void **)malloc(sizeof(void *) * (size_t)n);
   float *base;
   size_t stride;
-  int i, c, j, fresh = 0;
+  lim_arg la;
+  int i, fresh = 0;
   CK(mpeghb200_limiter_params_init(&prm, n_ch, (int)l0->sample_rate, (int)l0->limiter_on));
   stride = mpeghb200_limiter_state_floats(&prm);
   pool->stride = stride * sizeof(float);
   for (i = 0; i < n; i++)
     keys[i] = rq[i]->p[0];
   seam_need(&b_lim_in, fb), seam_need(&b_lim_out, fb);
-  /* the caller hands over interleaved [sample][channel] (impegh_dec_peak_limiter); the kernel is planar */
-  for (i = 0; i < n; i++)
-  {
-    const float *src = (const float *)rq[i]->p[1];
-    float *dst = (float *)b_lim_in.h + (size_t)i * n_ch * FRAME;
-    for (c = 0; c < n_ch; c++)
-      for (j = 0; j < FRAME; j++)
-        dst[c * FRAME + j] = src[j * n_ch + c];
-  }
+  /* the caller hands over interleaved [sample][channel] (impegh_dec_peak_limiter); the kernel is planar: the frames
+   * travel as they are and are turned on the device */
+  la.rq = rq, la.bytes = (size_t)n_ch * FRAME * sizeof(float);
+  seam_parallel_for(n, lim_gather, &la);
   CK(mpeghb200_h2d(ctx, b_lim_in.d, b_lim_in.h, fb));
+  CK(mpeghb200_interleave_dev(ctx, (const float *)b_lim_in.d, (float *)b_lim_out.d, n_ch, FRAME, 1, n, NULL));
   base = (float *)seam_pool_range(pool, keys, n, &fresh);
   if (base)
   {
@@ -421,7 +443,7 @@ static void lim_group(seam_req **rq, int n)
     for (i = 0; i < n; i++)
       if (lim_take_dirty(keys[i]) && !fresh)
         CK(mpeghb200_limiter_state_init_dev(ctx, &prm, base + (size_t)i * stride, 1, NULL));
-    CK(mpeghb200_limiter_dev(ctx, &prm, (const float *)b_lim_in.d, (float *)b_lim_out.d, base, NULL, n, NULL));
+    CK(mpeghb200_limiter_dev(ctx, &prm, (const float *)b_lim_out.d, (float *)b_lim_in.d, base, NULL, n, NULL));
   }
   else
   { /* the batch does not line up with the slot order: one launch per handle, each on its own slot */
@@ -430,19 +452,13 @@ static void lim_group(seam_req **rq, int n)
       float *st = (float *)seam_pool_one(pool, keys[i], &fresh);
       if (lim_take_dirty(keys[i]) || fresh)
         CK(mpeghb200_limiter_state_init_dev(ctx, &prm, st, 1, NULL));
-      CK(mpeghb200_limiter_dev(ctx, &prm, (const float *)b_lim_in.d + (size_t)i * n_ch * FRAME,
-                               (float *)b_lim_out.d + (size_t)i * n_ch * FRAME, st, NULL, 1, NULL));
+      CK(mpeghb200_limiter_dev(ctx, &prm, (const float *)b_lim_out.d + (size_t)i * n_ch * FRAME,
+                               (float *)b_lim_in.d + (size_t)i * n_ch * FRAME, st, NULL, 1, NULL));
     }
   }
+  CK(mpeghb200_interleave_dev(ctx, (const float *)b_lim_in.d, (float *)b_lim_out.d, n_ch, FRAME, 0, n, NULL));
   CK(mpeghb200_d2h(ctx, b_lim_out.h, b_lim_out.d, fb));
-  for (i = 0; i < n; i++)
-  {
-    float *dst = (float *)rq[i]->p[1];
-    const float *src = (const float *)b_lim_out.h + (size_t)i * n_ch * FRAME;
-    for (c = 0; c < n_ch; c++)
-      for (j = 0; j < FRAME; j++)
-        dst[j * n_ch + c] = src[c * FRAME + j];
-  }
+  seam_parallel_for(n, lim_scatter, &la);
   free(keys);
   seam_n.lim += (unsigned long)n;
 }

@@ -149,6 +149,44 @@ static int layout_of(const ia_obj_ren_dec_state_struct *s)
   return n_lay++;
 }
 
+typedef struct
+{
+  seam_req **rq;
+  const void **keys;
+  int n_obj, n_spk, flen;
+} obj_arg;
+static void obj_gather(int i, void *arg)
+{
+  const obj_arg *a = (const obj_arg *)arg;
+  const ia_obj_ren_dec_state_struct *s = (const ia_obj_ren_dec_state_struct *)a->rq[i]->p[0];
+  const ia_oam_dec_state_struct *md = &s->str_obj_md_dec_state;
+  const int n_obj = a->n_obj, k0 = (int)a->rq[i]->v[1];
+  float params[MPEGHB200_OBJ_MAX_OBJECTS][7];
+  int o;
+  a->keys[i] = s;
+  ((int32_t *)b_obj_set.h)[i] = k0 / n_obj; /* the metadata set: sub_frame_number - 1 */
+  for (o = 0; o < n_obj; o++)
+  {
+    const int k = k0 + o;
+    params[o][0] = md->azimuth_descaled[k], params[o][1] = md->elevation_descaled[k];
+    params[o][2] = md->radius_descaled[k], params[o][3] = md->gain_descaled[k];
+    params[o][4] = md->spread_width_descaled[k], params[o][5] = md->spread_height_descaled[k];
+    params[o][6] = md->spread_depth_descaled[k];
+  }
+  mpeghb200_obj_side_from_polar(&params[0][0], n_obj, (mpeghb200_obj_side *)b_obj_side.h + (size_t)i * n_obj);
+  for (o = 0; o < n_obj; o++) /* the sub-frame's samples to the head of the staging rows */
+    memcpy((float *)b_obj_in.h + ((size_t)i * n_obj + o) * FRAME, (const float *)a->rq[i]->p[1] + (size_t)o * FRAME,
+           (size_t)a->flen * sizeof(float));
+}
+static void obj_scatter(int i, void *arg)
+{ /* the reference accumulates into rows its caller zeroed: every sample is written once */
+  const obj_arg *a = (const obj_arg *)arg;
+  int o;
+  for (o = 0; o < a->n_spk; o++)
+    memcpy((float *)a->rq[i]->p[2] + (size_t)o * FRAME, (float *)b_obj_out.h + ((size_t)i * a->n_spk + o) * FRAME,
+           (size_t)a->flen * sizeof(float));
+}
+
 /* one group: same layout, same object count, same OAM frame length.  p[0] = ia_obj_ren_dec_state_struct, p[1] = in
  * (rows of 1024, already offset to the sub-frame), p[2] = out (likewise), v[0] = OAM frame length (1024, or a
  * sub-frame of 512 / 256: decode_main.c:1383-1410), v[1] = index of the first object's metadata
@@ -163,7 +201,7 @@ static void obj_group(seam_req **rq, int n, int L, int n_obj)
   const size_t st_f = mpeghb200_obj_state_floats(lay[L].h, n_obj), sc_f = mpeghb200_obj_scratch_floats(lay[L].h, n_obj);
   seam_pool *pool = &lay[L].pool[n_obj];
   const void **keys = (const void **)malloc(sizeof(void *) * (size_t)n);
-  float params[MPEGHB200_OBJ_MAX_OBJECTS][7];
+  obj_arg oa;
   float *base;
   int i, o, fresh = 0;
   pool->stride = st_f * sizeof(float);
@@ -171,26 +209,8 @@ static void obj_group(seam_req **rq, int n, int L, int n_obj)
   seam_need(&b_obj_scratch, (size_t)n * sc_f * sizeof(float));
   seam_need(&b_obj_first, (size_t)n_obj * sizeof(int32_t));
   seam_need(&b_obj_set, (size_t)n * sizeof(int32_t));
-  for (i = 0; i < n; i++)
-  {
-    const ia_obj_ren_dec_state_struct *s = (const ia_obj_ren_dec_state_struct *)rq[i]->p[0];
-    const ia_oam_dec_state_struct *md = &s->str_obj_md_dec_state;
-    keys[i] = s;
-    const int k0 = (int)rq[i]->v[1];
-    ((int32_t *)b_obj_set.h)[i] = k0 / n_obj; /* the metadata set: sub_frame_number - 1 */
-    for (o = 0; o < n_obj; o++)
-    {
-      const int k = k0 + o;
-      params[o][0] = md->azimuth_descaled[k], params[o][1] = md->elevation_descaled[k];
-      params[o][2] = md->radius_descaled[k], params[o][3] = md->gain_descaled[k];
-      params[o][4] = md->spread_width_descaled[k], params[o][5] = md->spread_height_descaled[k];
-      params[o][6] = md->spread_depth_descaled[k];
-    }
-    mpeghb200_obj_side_from_polar(&params[0][0], n_obj, (mpeghb200_obj_side *)b_obj_side.h + (size_t)i * n_obj);
-    for (o = 0; o < n_obj; o++) /* the sub-frame's samples to the head of the staging rows */
-      memcpy((float *)b_obj_in.h + ((size_t)i * n_obj + o) * FRAME, (const float *)rq[i]->p[1] + (size_t)o * FRAME,
-             (size_t)flen * sizeof(float));
-  }
+  oa.rq = rq, oa.keys = keys, oa.n_obj = n_obj, oa.n_spk = n_spk, oa.flen = flen;
+  seam_parallel_for(n, obj_gather, &oa);
   CK(mpeghb200_h2d(ctx, b_obj_in.d, b_obj_in.h, in_b));
   CK(mpeghb200_h2d(ctx, b_obj_side.d, b_obj_side.h, side_b));
   CK(mpeghb200_h2d(ctx, b_obj_set.d, b_obj_set.h, (size_t)n * sizeof(int32_t)));
@@ -218,10 +238,7 @@ static void obj_group(seam_req **rq, int n, int L, int n_obj)
                                     (const float *)b_obj_in.d, (float *)b_obj_out.d, base, (float *)b_obj_scratch.d, n,
                                     flen, 0, (const int32_t *)b_obj_set.d, NULL));
   CK(mpeghb200_d2h(ctx, b_obj_out.h, b_obj_out.d, out_b));
-  for (i = 0; i < n; i++) /* the reference accumulates into rows its caller zeroed: every sample is written once */
-    for (o = 0; o < n_spk; o++)
-      memcpy((float *)rq[i]->p[2] + (size_t)o * FRAME, (float *)b_obj_out.h + ((size_t)i * n_spk + o) * FRAME,
-             (size_t)flen * sizeof(float));
+  seam_parallel_for(n, obj_scatter, &oa);
   free(keys);
   seam_n.obj += (unsigned long)n;
 }
@@ -276,6 +293,36 @@ impeghd_obj_renderer_dec(ia_obj_ren_dec_state_struct *ptr_obj_ren_dec_state, FLO
 /* ---- PCM packer ------------------------------------------------------------------------------------------------- */
 static seam_buf b_pcm_in, b_pcm_out, b_pcm_delay;
 
+typedef struct
+{
+  seam_req **rq;
+  int n_ch, ns, bps;
+} pcm_arg;
+static void pcm_gather(int i, void *arg)
+{
+  const pcm_arg *a = (const pcm_arg *)arg;
+  FLOAT32 **rows = (FLOAT32 **)a->rq[i]->p[1];
+  int c;
+  for (c = 0; c < a->n_ch; c++)
+    memcpy((float *)b_pcm_in.h + ((size_t)i * a->n_ch + c) * a->ns, rows[c], (size_t)a->ns * sizeof(float));
+  ((int32_t *)b_pcm_delay.h)[i] = *(const WORD32 *)a->rq[i]->p[3];
+}
+static void pcm_scatter(int i, void *arg)
+{
+  const pcm_arg *a = (const pcm_arg *)arg;
+  seam_req *r = a->rq[i];
+  WORD32 *delay = (WORD32 *)r->p[3], *out_bytes = (WORD32 *)r->p[4], *m = (WORD32 *)r->p[2];
+  const int n_ch = a->n_ch, ns = a->ns, bps = a->bps, d = *delay;
+  const int nb = d <= ns ? n_ch * (ns - d) * bps : 0;
+  int c;
+  memcpy(r->p[0], (const unsigned char *)b_pcm_out.h + (size_t)i * n_ch * ns * bps, (size_t)nb);
+  *delay = d <= ns ? 0 : d - ns; /* decode_main.c:223-232 */
+  for (c = 0; c < n_ch; c++)    /* the reference rewrites -1 entries of the caller's map in place (:236) */
+    if (m[c] == -1)
+      m[c] = c;
+  *out_bytes = (d <= ns ? n_ch * (ns - d) : 0) * ((int)r->v[3] >> 3); /* :313 */
+}
+
 /* p[0] = outbuffer, p[1] = out_samples (FLOAT32 **), p[2] = out_ch_map, p[3] = ptr_delay_samples, p[4] = out_bytes,
  * v[0] = num_samples_out, v[1] = pcmsize, v[2] = num_channel_out */
 static void pcm_group(seam_req **rq, int n)
@@ -284,34 +331,19 @@ static void pcm_group(seam_req **rq, int n)
   const int ns = (int)rq[0]->v[0], bits = (int)rq[0]->v[1], n_ch = (int)rq[0]->v[2], bps = bits / 8;
   const size_t in_b = (size_t)n * n_ch * ns * sizeof(float), out_b = (size_t)n * n_ch * ns * bps;
   int32_t map[MAX_NUM_CHANNELS];
-  int i, c;
+  pcm_arg pa;
+  int c;
   seam_need(&b_pcm_in, in_b), seam_need(&b_pcm_out, out_b), seam_need(&b_pcm_delay, (size_t)n * sizeof(int32_t));
   for (c = 0; c < n_ch; c++)
     map[c] = ((const WORD32 *)rq[0]->p[2])[c];
-  for (i = 0; i < n; i++)
-  {
-    FLOAT32 **rows = (FLOAT32 **)rq[i]->p[1];
-    for (c = 0; c < n_ch; c++)
-      memcpy((float *)b_pcm_in.h + ((size_t)i * n_ch + c) * ns, rows[c], (size_t)ns * sizeof(float));
-    ((int32_t *)b_pcm_delay.h)[i] = *(const WORD32 *)rq[i]->p[3];
-  }
+  pa.rq = rq, pa.n_ch = n_ch, pa.ns = ns, pa.bps = bps;
+  seam_parallel_for(n, pcm_gather, &pa);
   CK(mpeghb200_h2d(ctx, b_pcm_in.d, b_pcm_in.h, in_b));
   CK(mpeghb200_h2d(ctx, b_pcm_delay.d, b_pcm_delay.h, (size_t)n * sizeof(int32_t)));
   CK(mpeghb200_pcm_pack_block_dev(ctx, (const float *)b_pcm_in.d, n_ch, ns, ns, bits, map, (int32_t *)b_pcm_delay.d,
                                   (uint8_t *)b_pcm_out.d, NULL, n, NULL));
   CK(mpeghb200_d2h(ctx, b_pcm_out.h, b_pcm_out.d, out_b));
-  for (i = 0; i < n; i++)
-  {
-    WORD32 *delay = (WORD32 *)rq[i]->p[3], *out_bytes = (WORD32 *)rq[i]->p[4], *m = (WORD32 *)rq[i]->p[2];
-    const int d = *delay;
-    const int nb = d <= ns ? n_ch * (ns - d) * bps : 0;
-    memcpy(rq[i]->p[0], (const unsigned char *)b_pcm_out.h + (size_t)i * n_ch * ns * bps, (size_t)nb);
-    *delay = d <= ns ? 0 : d - ns; /* decode_main.c:223-232 */
-    for (c = 0; c < n_ch; c++)    /* the reference rewrites -1 entries of the caller's map in place (:236) */
-      if (m[c] == -1)
-        m[c] = c;
-    *out_bytes = (d <= ns ? n_ch * (ns - d) : 0) * ((int)rq[i]->v[3] >> 3); /* :313 */
-  }
+  seam_parallel_for(n, pcm_scatter, &pa);
   seam_n.pcm += (unsigned long)n;
 }
 
