@@ -1048,6 +1048,7 @@ __device__ __noinline__ void slow_units_frames(const float* __restrict__ coef, c
   }
 }
 
+template <bool DEFER>
 __global__ void __launch_bounds__(128, MPEGHB200_FD_CTAS_PER_SM)
     fd_synth_ws_frames_kernel(const float* __restrict__ coef, const uint32_t* __restrict__ side,
                               float* __restrict__ overlap, float* __restrict__ out, int n_units, int n_frames,
@@ -1092,7 +1093,7 @@ __global__ void __launch_bounds__(128, MPEGHB200_FD_CTAS_PER_SM)
       if (i >= kSlots) bar_sync64(FREE + slot);
       if (f == 0) left = false;
       const bool fast = !left && is_fast(unpack_side(sw[cur]));
-      left = !fast;
+      left = DEFER && !fast;  // without deferral a generic-path frame is done in line and the unit stays in the pipeline
       if (lane == 0) fast_flag[slot] = fast;
       if (fast) phase_a(eo[cur], ta, slots[slot], T, lane);
       bar_arrive64(AB + slot);
@@ -1157,7 +1158,10 @@ __global__ void __launch_bounds__(128, MPEGHB200_FD_CTAS_PER_SM)
           __syncwarp();  // its overlap stores are read back by other lanes' loads of the next frame
         }
       } else {
-        if (mode == 0) {
+        if (!DEFER) {
+          fd_unit_generic(coef + q * 1024, ov, o, sd, slots[slot], T, lane);
+          __syncwarp();
+        } else if (mode == 0) {
           if (slow_count < kSlowCap) {  // only this warp writes slow_count
             if (lane == 0) slow_list[slow_count] = u * n_frames + f, slow_count = slow_count + 1;
             __syncwarp();
@@ -1166,7 +1170,7 @@ __global__ void __launch_bounds__(128, MPEGHB200_FD_CTAS_PER_SM)
             mode = 2;
           }
         }
-        if (mode == 2) {
+        if (DEFER && mode == 2) {
           fd_unit_generic(coef + q * 1024, ov, o, sd, slots[slot], T, lane);
           __syncwarp();
         }
@@ -1242,8 +1246,13 @@ mpeghb200_status fd_synth_frames_launch(mpeghb200_ctx* ctx, const float* d_coef,
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr, cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, fd_synth_ws_frames_kernel, d_coef, d_side, d_overlap, d_out, n_units,
-                                     n_frames, ctx->tables);
+  // generic-path frames (EIGHT_SHORT, other transform kernels) in line: the unit's later ONLY_LONG-family frames stay on
+  // the fast path.  MPEGHB200_FD_VARIANT=10 selects the deferring form (a unit leaves the pipeline at its first such frame).
+  cudaError_t e = ctx->fd_variant == 10
+                      ? cudaLaunchKernelEx(&cfg, fd_synth_ws_frames_kernel<true>, d_coef, d_side, d_overlap, d_out, n_units,
+                                           n_frames, ctx->tables)
+                      : cudaLaunchKernelEx(&cfg, fd_synth_ws_frames_kernel<false>, d_coef, d_side, d_overlap, d_out,
+                                           n_units, n_frames, ctx->tables);
   if (e == cudaSuccess) e = cudaGetLastError();
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, e);
