@@ -291,9 +291,14 @@ mpeghb200_status mpeghb200_hoa_render_dev(mpeghb200_ctx *ctx, const mpeghb200_ho
  * parameterisation, for n_sets independent filter sets (1 = every stream shares one BRIR set):
  *   taps_direct [set][2][n_in][len_direct], taps_diffuse [set][n_diffuse_blocks][2][len_direct],
  *   direct_fc [set][2][n_in], diffuse_fc [set][2][n_diffuse_blocks], inv_diffuse_weight [set][n_in].
- * The transform length N is the smallest power of two >= 2 * len_direct; N = 2048 and N = 8192 are supported
- * (the reference's own N = 4096 and N = 16384 e^{+j} transforms read outside their rows / lack the column
- * stage: MPEGHB200_ERR_UNSUPPORTED).  A block is B = N/2 samples per input.
+ * The transform length N is the smallest power of two >= 2 * len_direct (impeghd_binaural_struct_init, :200-205); a
+ * block is B = N/2 samples per input.  N = 2048 and N = 8192 (direct filters of 513 .. 1024 and 2049 .. 4096 taps) run on
+ * tuned kernels; N = 16 .. 1024 (8 .. 512 taps) and N = 16384 (4097 .. 8192 taps) on a generic one that mirrors the
+ * reference's transforms pass for pass -- for N = 16384 including the missing column stage of impeghd_cplx_ifft_8k
+ * (decoder/impeghd_ifft.c:1318-1359), i.e. it reproduces what the reference computes, which is not a convolution.
+ * N = 4096 (1025 .. 2048 taps) is refused with MPEGHB200_ERR_UNSUPPORTED: impeghd_cplx_ifft_4 (:1212) reads two floats
+ * behind the transform's buffer, so the reference's result depends on what an earlier tool left in the shared scratch
+ * (tests/test_oracle_binaural.py::test_ifft_4096_depends_on_stale_scratch) and there is nothing to reproduce.
  *
  * block_dev: one block for every stream.  d_in layout 0 = [stream][n_in][B]; layout 1 = [B/1024][stream][n_in][1024]
  * (B/1024 consecutive decoder frames stacked, what the reference accumulates in input_mem_buf).  Inputs are
@@ -313,7 +318,7 @@ mpeghb200_status mpeghb200_binaural_create(mpeghb200_ctx *ctx, int n_in, int len
  * direct_row_stride floats, the first fft_size of each are used, the two ears direct_ear_stride floats apart; in
  * direct_process_size[2][..] the ears are direct_size_stride entries apart), taps_diffuse[block][2][..], the multiply lengths direct_process_size /
  * diffuse_process_size[block][2] and diffuse_weight[n_in].  One filter set.  This is what the drop-in uses: nothing is
- * re-designed, the filters are the reference's bit for bit.  fft_size 2048 or 8192. */
+ * re-designed, the filters are the reference's bit for bit.  fft_size: every length mpeghb200_binaural_create takes. */
 mpeghb200_status mpeghb200_binaural_create_from_state(mpeghb200_ctx *ctx, int fft_size, int n_in, int n_diffuse_blocks,
                                                       const float *h_direct, size_t direct_row_stride,
                                                       size_t direct_ear_stride, const float *h_diffuse,

@@ -322,10 +322,35 @@ struct mpeghb200_binaural {
   int32_t* d_flen = nullptr;
   float* d_weight = nullptr;
   float2* d_mix = nullptr;
+  // transform lengths without a tuned kernel (N <= 1024, N = 16384): binaural_generic.cu
+  bool generic = false;
+  float* d_w = nullptr;
+  float* d_mc = nullptr;
+  float* d_ms = nullptr;
   void release() {
     cudaFree(d_hdirect), cudaFree(d_hdiffuse), cudaFree(d_dlen), cudaFree(d_flen), cudaFree(d_weight), cudaFree(d_mix);
+    cudaFree(d_w), cudaFree(d_mc), cudaFree(d_ms);
   }
 };
+
+namespace mpeghb200 {
+size_t binaural_generic_work_floats(int N);
+cudaError_t binaural_generic_tables(float** d_w, float** d_mc, float** d_ms);
+cudaError_t binaural_generic_spectra(const float* d_taps, int len, int n_filters, float* d_spec, int N, const float* d_w,
+                                     const float* d_mc, const float* d_ms);
+cudaError_t binaural_generic_block(const float* d_in, long long in_stream_stride, long long in_chan_stride,
+                                   long long in_chunk_stride, float in_scale, float out_scale, float* d_out, float* d_state,
+                                   long long state_floats, const int32_t* d_set, const float* h_direct,
+                                   const float* h_diffuse, const int32_t* dlen, const int32_t* flen, const float* weight,
+                                   int n_in, int n_blocks, int N, const float* d_w, const float* d_mc, const float* d_ms,
+                                   int n_streams, cudaStream_t st);
+}  // namespace mpeghb200
+// which transform lengths exist: 0 = none, 1 = tuned kernels, 2 = generic path
+static int binaural_size_class(int N) {
+  if (N == 2048 || N == 8192) return 1;
+  if ((N >= 16 && N <= 1024) || N == 16384) return 2;
+  return 0;
+}
 
 template <int DIM2>
 static cudaError_t run_spectra(const mpeghb200_binaural* b, const float* d_taps, int n_filters, float* d_spec) {
@@ -349,25 +374,25 @@ mpeghb200_status mpeghb200_binaural_create(mpeghb200_ctx* ctx, int n_in, int len
       !taps_direct || !direct_fc || !inv_diffuse_weight || (n_diffuse_blocks && (!taps_diffuse || !diffuse_fc)))
     return fail(ctx, MPEGHB200_ERR_BAD_ARG, "binaural_create: 1..32 inputs, 0..2 diffuse blocks, non-null tables");
   int N = 2;
-  while (N < 2 * len_direct) N <<= 1;
-  if (N < 2048) N = 2048;  // shorter filters: zero-padded to the smallest supported transform
-  if (N != 2048 && N != 8192)
+  while (N < 2 * len_direct) N <<= 1;  // impeghd_binaural_struct_init (decoder/impeghd_binaural_renderer.c:200-205)
+  if (!binaural_size_class(N))
     return fail(ctx, MPEGHB200_ERR_UNSUPPORTED,
-                "binaural_create: direct length must give a 2048- or 8192-point transform (the reference's "
-                "4096- and 16384-point e^{+j} transforms read outside their rows / skip the column stage)");
-  if (N == 2048 && len_direct <= 512)
-    return fail(ctx, MPEGHB200_ERR_UNSUPPORTED, "binaural_create: direct length below 513 (transform < 2048)");
+                N == 4096 ? "binaural_create: direct lengths of 1025 .. 2048 taps give a 4096-point transform, for which the "
+                            "reference's output depends on stale scratch memory (impeghd_cplx_ifft_4 reads behind its "
+                            "buffer, decoder/impeghd_ifft.c:1225-1228): there is no result to reproduce"
+                          : "binaural_create: direct length must be 8 .. 8192 taps");
   MB_CUDA(ctx, cudaSetDevice(ctx->device));
   auto* b = new (std::nothrow) mpeghb200_binaural();
   if (!b) return MPEGHB200_ERR_NO_MEM;
   b->ctx = ctx, b->n_in = n_in, b->len = len_direct, b->n_blocks = n_diffuse_blocks, b->n_sets = n_sets;
   b->N = N, b->dim2 = N / 1024;
+  b->generic = binaural_size_class(N) == 2;
   const int B = N / 2;
   const size_t n_dir = size_t(n_sets) * 2 * n_in, n_dif = size_t(n_sets) * n_diffuse_blocks * 2;
 
   // inter-stage twiddles [j][i] from the [1024][16] table (decoder/impeghd_fft_ifft_rom.c:1122,4401)
-  std::vector<float2> mix(size_t(b->dim2) * 1024);
-  {
+  std::vector<float2> mix(b->generic ? 1 : size_t(b->dim2) * 1024);
+  if (!b->generic) {
     const std::vector<float>& mc = rom_table(ROM_MIXED_RAD_COS);
     const std::vector<float>& ms = rom_table(ROM_MIXED_RAD_SIN);
     const int fac = 16 / b->dim2;
@@ -388,6 +413,7 @@ mpeghb200_status mpeghb200_binaural_create(mpeghb200_ctx* ctx, int n_in, int len
   float* d_taps = nullptr;
   cudaError_t e = cudaMalloc(&b->d_mix, mix.size() * sizeof(float2));
   if (e == cudaSuccess) e = cudaMemcpy(b->d_mix, mix.data(), mix.size() * sizeof(float2), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && b->generic) e = binaural_generic_tables(&b->d_w, &b->d_mc, &b->d_ms);
   if (e == cudaSuccess) e = cudaMalloc(&b->d_hdirect, n_dir * N * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&b->d_hdiffuse, (n_dif ? n_dif : 1) * N * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&b->d_dlen, dlen.size() * sizeof(int32_t));
@@ -403,7 +429,10 @@ mpeghb200_status mpeghb200_binaural_create(mpeghb200_ctx* ctx, int n_in, int len
     const size_t nf = pass ? n_dif : n_dir;
     if (!nf) continue;
     e = cudaMemcpy(d_taps, pass ? taps_diffuse : taps_direct, nf * len_direct * sizeof(float), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess)
+    if (e == cudaSuccess && b->generic)
+      e = binaural_generic_spectra(d_taps, len_direct, int(nf), pass ? b->d_hdiffuse : b->d_hdirect, N, b->d_w, b->d_mc,
+                                   b->d_ms);
+    else if (e == cudaSuccess)
       e = (b->dim2 == 8) ? run_spectra<8>(b, d_taps, int(nf), pass ? b->d_hdiffuse : b->d_hdirect)
                          : run_spectra<2>(b, d_taps, int(nf), pass ? b->d_hdiffuse : b->d_hdirect);
     ctx->launches.fetch_add(1);
@@ -433,15 +462,18 @@ mpeghb200_status mpeghb200_binaural_create_from_state(mpeghb200_ctx* ctx, int ff
       direct_ear_stride < size_t(n_in) * direct_row_stride ||
       (n_diffuse_blocks && (!h_diffuse || !diffuse_process_size || diffuse_row_stride < size_t(fft_size))))
     return fail(ctx, MPEGHB200_ERR_BAD_ARG, "binaural_create_from_state: 1..32 inputs, 0..2 diffuse blocks, non-null tables");
-  if (fft_size != 2048 && fft_size != 8192)
-    return fail(ctx, MPEGHB200_ERR_UNSUPPORTED, "binaural_create_from_state: 2048- and 8192-point transforms only");
+  if (!binaural_size_class(fft_size))
+    return fail(ctx, MPEGHB200_ERR_UNSUPPORTED,
+                "binaural_create_from_state: transform lengths 16 .. 1024, 2048, 8192 and 16384 (the reference's "
+                "4096-point result depends on stale scratch memory)");
   MB_CUDA(ctx, cudaSetDevice(ctx->device));
   auto* b = new (std::nothrow) mpeghb200_binaural();
   if (!b) return MPEGHB200_ERR_NO_MEM;
   const int N = fft_size;
   b->ctx = ctx, b->n_in = n_in, b->len = N / 2, b->n_blocks = n_diffuse_blocks, b->n_sets = 1, b->N = N, b->dim2 = N / 1024;
-  std::vector<float2> mix(size_t(b->dim2) * 1024);
-  {
+  b->generic = binaural_size_class(N) == 2;
+  std::vector<float2> mix(b->generic ? 1 : size_t(b->dim2) * 1024);
+  if (!b->generic) {
     const std::vector<float>& mc = rom_table(ROM_MIXED_RAD_COS);
     const std::vector<float>& ms = rom_table(ROM_MIXED_RAD_SIN);
     const int fac = 16 / b->dim2;
@@ -456,6 +488,7 @@ mpeghb200_status mpeghb200_binaural_create_from_state(mpeghb200_ctx* ctx, int ff
   for (size_t i = 0; i < n_dif; ++i) flen[i] = diffuse_process_size[i];  // [block][2]
   cudaError_t e = cudaMalloc(&b->d_mix, mix.size() * sizeof(float2));
   if (e == cudaSuccess) e = cudaMemcpy(b->d_mix, mix.data(), mix.size() * sizeof(float2), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && b->generic) e = binaural_generic_tables(&b->d_w, &b->d_mc, &b->d_ms);
   if (e == cudaSuccess) e = cudaMalloc(&b->d_hdirect, n_dir * N * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&b->d_hdiffuse, (n_dif ? n_dif : 1) * N * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&b->d_dlen, dlen.size() * sizeof(int32_t));
@@ -491,7 +524,8 @@ int mpeghb200_binaural_num_in(const mpeghb200_binaural* b) { return b ? b->n_in 
 
 size_t mpeghb200_binaural_state_floats(const mpeghb200_binaural* b) {
   if (!b) return 0;
-  return size_t(b->N) + size_t(b->n_blocks + 1) * b->N + 4;  // tail [2][B], ring, write index (+ padding)
+  // tail [2][B], ring, write index (+ padding); the generic path keeps its per-stream workspace behind them
+  return size_t(b->N) + size_t(b->n_blocks + 1) * b->N + 4 + (b->generic ? binaural_generic_work_floats(b->N) : 0);
 }
 
 mpeghb200_status mpeghb200_binaural_spectra(mpeghb200_ctx* ctx, const mpeghb200_binaural* b, float* h_direct,
@@ -533,7 +567,14 @@ mpeghb200_status mpeghb200_binaural_block_dev(mpeghb200_ctx* ctx, const mpeghb20
   P.n_in = b->n_in, P.n_blocks = b->n_blocks;
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   cudaError_t e;
-  if (b->dim2 == 8) {
+  if (b->generic) {
+    if (in_layout == 1 && (B % 1024))
+      return fail(ctx, MPEGHB200_ERR_BAD_ARG, "binaural_block_dev: layout 1 stacks whole 1024-sample frames; this renderer's "
+                                              "block is shorter");
+    e = binaural_generic_block(d_in, P.in_stream_stride, P.in_chan_stride, P.in_chunk_stride, in_scale, out_scale, d_out,
+                               d_state, P.state_floats, d_filter_set, b->d_hdirect, b->d_hdiffuse, b->d_dlen, b->d_flen,
+                               b->d_weight, b->n_in, b->n_blocks, b->N, b->d_w, b->d_mc, b->d_ms, n_streams, st);
+  } else if (b->dim2 == 8) {
     e = cudaFuncSetAttribute(binaural_block_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Geo<8>::kSmem));
     if (e == cudaSuccess) binaural_block_kernel<8><<<n_streams, Geo<8>::NT, Geo<8>::kSmem, st>>>(P);
   } else {

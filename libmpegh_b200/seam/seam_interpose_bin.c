@@ -240,9 +240,11 @@ WORD32 impeghd_binaural_struct_process_ld_ola(FLOAT32 **ptr_src, FLOAT32 **ptr_d
   ia_binaural_ren_pers_mem_str *b = ptr_binaural;
   const WORD32 B = b->processed_samples;
   WORD32 n_in_samps, n_out = 0, idx = 0, len, inp, R;
-  if ((b->fft_size != 2048 && b->fft_size != 8192) || B != b->fft_size / 2 || b->num_output != 2 || b->num_input < 1 ||
-      b->num_input > 32 || b->diffuse_blocks < 0 || b->diffuse_blocks > 1)
-  { /* the transform sizes whose reference output is not a function of the input, and the
+  const int fft = b->fft_size;
+  const int size_ok = fft == 2048 || fft == 8192 || fft == 16384 || (fft >= 16 && fft <= 1024 && !(fft & (fft - 1)));
+  if (!size_ok || B != fft / 2 || b->num_output != 2 || b->num_input < 1 || b->num_input > 32 || b->diffuse_blocks < 0 ||
+      b->diffuse_blocks > 1)
+  { /* the 4096-point renderer, whose reference output is not a function of the input, and the
        two-diffuse-block ring the reference indexes out of bounds, stay where they are */
     typedef WORD32 (*fn_t)(FLOAT32 **, FLOAT32 **, WORD32, FLOAT32 *, ia_binaural_ren_pers_mem_str *, FLOAT32 *);
     static fn_t real;

@@ -203,6 +203,7 @@ def _bind_harnesses(lib):
     lib.ref_hoa_ren_process.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p]
     lib.ref_hoa_ren_process.restype = ctypes.c_int
     lib.ref_cplx_ifft_8k.argtypes = [_f32p, _f32p, ctypes.c_int]
+    lib.ref_cplx_ifft_8k_fill.argtypes = [_f32p, _f32p, ctypes.c_int, ctypes.c_float]
     lib.ref_cplx_fft_16k.argtypes = [_f32p, _f32p, ctypes.c_int]
     lib.ref_bin_create.restype = ctypes.c_void_p
     lib.ref_bin_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p, _f32p, _f32p, _f32p, _f32p,

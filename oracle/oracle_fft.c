@@ -2,7 +2,7 @@
  *
  * Plain-C restatement of
  *   impeghd_rad2_cplx_fft    decoder/impeghd_fft.c:297    e^{-j} transform, n = 2^k <= 1024
- *   impeghd_cplx_ifft_8k     decoder/impeghd_ifft.c:1264  n = 1024 x {2, 8} (see note on 4096 / 16384)
+ *   impeghd_cplx_ifft_8k     decoder/impeghd_ifft.c:1264  n = 1024 x {2, 8, 16} (see the notes on 4096 and 16384)
  *   impeghd_cplx_fft_16k     decoder/impeghd_fft.c:1415   n = 1024 x {2, 4, 8, 16}
  * The e^{-j} transform is the conjugate mirror of oracle_cplx_ifft_pow2 (oracle_fd.c) node for node, with
  * one rounding difference: its first pass forms a - 2b as (a - b) - b (impeghd_fft.c:352-386), two
@@ -12,10 +12,14 @@
  * Reference behaviour kept bug for bug (the binaural renderer's results depend on it):
  *   - impeghd_cplx_ifft_8 (impeghd_ifft.c:1118) writes bins 2 and 6 as (n21 - x4, n20 + x5) / (n21 + x4,
  *     n20 - x5): real and imaginary parts of the even half are swapped relative to an 8-point e^{+j} DFT.
- *   - impeghd_cplx_ifft_8k has no column transform for n = 16384 and its 4-point column transform
- *     (impeghd_cplx_ifft_4) reads elements 4 and 6 of 4-element rows, i.e. outside the row and, for the
- *     last row, outside the initialised scratch: n = 4096 and n = 16384 are not restated (undefined /
- *     meaningless in the reference); oracle_cplx_ifft_big returns -1 for them.
+ *   - impeghd_cplx_ifft_8k has no column transform for n = 16384 (impeghd_ifft.c:1318-1359): what comes back is the
+ *     twiddled row transforms, transposed.  Restated as it is (a pure function of the input; pinned by
+ *     tests/test_oracle_binaural.py).
+ *   - its 4-point column transform (impeghd_cplx_ifft_4, :1212) reads elements 4 and 6 of 4-element rows: the
+ *     imaginary row, the next row's (not yet transformed) real part and, for row 1023, two floats BEHIND the transform's
+ *     interim buffer -- scratch memory the transform never wrote.  n = 4096 is therefore not a function of its input
+ *     (tests/test_oracle_binaural.py::test_ifft_4096_depends_on_stale_scratch shows two different results for one input)
+ *     and is not restated: oracle_cplx_ifft_big returns -1 for it.
  */
 #include <string.h>
 
@@ -321,8 +325,8 @@ static int big_transform(float *re, float *im, int n, int inverse)
   }
   if (dim2 * 1024 != n || (dim2 != 2 && dim2 != 4 && dim2 != 8 && dim2 != 16))
     return -1;
-  if (inverse && (dim2 == 4 || dim2 == 16))
-    return -1; /* see header */
+  if (inverse && dim2 == 4)
+    return -1; /* the reference's 4-point e^{+j} column transform reads outside the transform's buffers: see header */
   for (i = 0; i < dim2; i++)
   {
     for (j = 0; j < dim1; j++)
@@ -358,8 +362,12 @@ static int big_transform(float *re, float *im, int n, int inverse)
       float a = cr[0] + cr[1], b = cr[0] - cr[1], c = ci[0] + ci[1], d = ci[0] - ci[1];
       cr[0] = a, cr[1] = b, ci[0] = c, ci[1] = d;
     }
-    else
+    else if (!inverse)
       oracle_cplx_fft_pow2(cr, ci, 16);
+    /* inverse, dim2 == 16: impeghd_cplx_ifft_8k has no column transform for this size (impeghd_ifft.c:1318-1359 tests
+     * 8192, 4096 and 2048 only): the twiddled row outputs are written back as they are.  Not a Fourier transform of the
+     * input, but a pure function of it, and what the reference's binaural renderer runs on for direct filters of 4097 ..
+     * 8192 taps. */
     for (j = 0; j < dim2; j++)
       re[j * dim1 + i] = cr[j], im[j * dim1 + i] = ci[j];
   }

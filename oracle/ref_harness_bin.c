@@ -57,6 +57,16 @@ void ref_cplx_ifft_8k(float *re, float *im, int n)
   impeghd_cplx_ifft_8k(re, im, scratch, n);
   free(scratch);
 }
+/* the same with every float of the scratch preset to `fill` (what an earlier user of the shared scratch left there) */
+void ref_cplx_ifft_8k_fill(float *re, float *im, int n, float fill)
+{
+  float *scratch = (float *)malloc(8 * 16384 * sizeof(float));
+  int i;
+  for (i = 0; i < 8 * 16384; i++)
+    scratch[i] = fill;
+  impeghd_cplx_ifft_8k(re, im, scratch, n);
+  free(scratch);
+}
 void ref_cplx_fft_16k(float *re, float *im, int n)
 {
   float *scratch = (float *)calloc(8 * 16384, sizeof(float));

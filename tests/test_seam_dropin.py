@@ -406,7 +406,8 @@ np.save(out_path, res)
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("cfg,blocks", [((24, 4096, 1, 1024), 8), ((5, 1024, 1, 1024), 8), ((21, 4096, 0, 1024), 8),
-                                        ((11, 3000, 1, 1000), 8), ((3, 700, 1, 2500), 8)])
+                                        ((11, 3000, 1, 1000), 8), ((3, 700, 1, 2500), 8),
+                                        ((4, 300, 1, 1024), 8), ((2, 5000, 1, 1024), 8)])
 def test_seam_binaural(tmp_path, cfg, blocks):
     """The interposed impeghd_binaural_struct_process_ld_ola (no shipped stream selects binaural rendering): the
     reference's own init designs the filter spectra, the interposer takes them from ia_binaural_ren_pers_mem_str as
