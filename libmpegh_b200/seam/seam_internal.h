@@ -38,6 +38,8 @@ typedef enum
   RQ_STEREO,   /* impeghd_ms_stereo, ia_core_coder_cplx_pred_upmixing */
   RQ_IGF,      /* ia_core_coder_igf_mono (+ its TNF step), ia_core_coder_igf_tnf */
   RQ_IGFST,    /* ia_core_coder_igf_apply_stereo */
+  RQ_DRCSB,    /* impd_drc_apply_gains_subband */
+  RQ_DRCTD,    /* impd_drc_filter_banks_process + impd_drc_apply_gains_and_add */
   RQ_KINDS
 } seam_kind;
 
@@ -59,9 +61,13 @@ void seam_inline_unlock(void);
 typedef struct
 {
   unsigned long fd_gpu, fd_host, tns, lim, ltpf, fc, mct, obj, obj_host, pcm, batches, batch_calls, max_batch, hoa_ren,
-      hoa_ren_host, resample, hoa_spatial, hoa_spatial_host, binaural, binaural_host, stereo, stereo_host, igf, igf_tnf, igf_stereo, igf_host;
+      hoa_ren_host, resample, hoa_spatial, hoa_spatial_host, binaural, binaural_host, stereo, stereo_host, igf, igf_tnf, igf_stereo, igf_host, drc_sb, drc_td, drc_host;
 } seam_counters;
 extern seam_counters seam_n;
+
+/* the reference's own definition of an interposed function (dlsym RTLD_NEXT); aborts with a message when the reference
+ * library is not in the global symbol scope (a dlopen without RTLD_GLOBAL) instead of calling through NULL */
+void *seam_real(const char *name);
 
 /* gather / scatter loops of a back-end on all parse threads: fn(i, arg) for i in [0, n), any order, any thread */
 typedef void (*seam_par_fn)(int i, void *arg);

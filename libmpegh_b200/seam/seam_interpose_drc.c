@@ -1,0 +1,448 @@
+/* seam_interpose_drc.c -- libmpeghgpu.so: application of the decoded DRC gains.
+ *
+ *   impd_drc_apply_gains_subband    decoder/impd_drc_process.c:243   -> mpeghb200_gain_subband_dev   (STFT256 domain)
+ *   impd_drc_filter_banks_process   decoder/impd_drc_process.c:399  \
+ *   impd_drc_apply_gains_and_add    decoder/impd_drc_process.c:68   /  -> mpeghb200_drc_td_dev         (time domain)
+ *
+ * Gain decoding, DRC set selection and the interpolation into per-sample gain curves (impd_drc_get_gain and below: libm
+ * splines) stay in the reference; these interposers read the finished curves out of ia_drc_gain_buffer_struct the way
+ * the reference's own application code does (lpcm_gains + MAX_SIGNAL_DELAY - gain_delay_samples [+ one frame in
+ * DELAY_MODE_LOW]), the channel groups out of ia_drc_instructions_struct, the overlap weights out of
+ * ia_drc_overlap_params_struct and the filter-bank coefficients out of ia_filter_banks_struct.
+ *
+ * Time domain: the reference splits a frame into band signals (filter_banks_process) and then multiplies and sums them
+ * (apply_gains_and_add); the kernel does both at once, so the first call only records its arguments and the second one
+ * files the request.  impd_drc_apply_gains_and_add is `static` in the reference: this pair is taken over only when the
+ * reference library in use exports it (the build oracle/Makefile makes with -Dstatic= on the one file); against the stock
+ * library both calls are forwarded and time-domain DRC stays in the reference.  The filter memories then live on the
+ * device, one slot per (ia_drc_gain_dec_struct, selected set).
+ */
+#define _GNU_SOURCE
+#include <stdlib.h>
+#include <string.h>
+
+#include <impeghd_type_def.h>
+#include "impd_drc_common.h"
+#include "impd_drc_extr_delta_coded_info.h"
+#include "impd_drc_struct.h"
+#include "impeghd_intrinsics_flt.h"
+#include "ia_core_coder_cnst.h"
+#include "ia_core_coder_defines.h"
+#include "ia_core_coder_bitbuffer.h"
+#include "ia_core_coder_interface.h"
+#include "ia_core_coder_info.h"
+#include <ia_core_coder_rom.h>
+#include "ia_core_coder_dec.h"
+#include "ia_core_coder_acelp_info.h"
+#include "ia_core_coder_channelinfo.h"
+#include "ia_core_coder_channel.h"
+#include "ia_core_coder_env_extr.h"
+#include "ia_core_coder_igf_data_struct.h"
+#include "impeghd_memory_standards.h"
+#include "ia_core_coder_stereo_lpd.h"
+#include "ia_core_coder_tns_usac.h"
+#include "ia_core_coder_windows.h"
+#include "impeghd_hoa_common_values.h"
+#include "impeghd_hoa_matrix_struct.h"
+#include "impeghd_hoa_matrix.h"
+#include "ia_core_coder_config.h"
+#include "ia_core_coder_struct_def.h"
+#include "impeghd_hoa_dec_struct.h"
+#include "impeghd_error_codes.h"
+#include <impeghd_fft_ifft.h>
+#include "impeghd_mhas_parse.h"
+#include "impeghd_multichannel.h"
+#include "impeghd_tbe_dec.h"
+#include "impeghd_binaural.h"
+#include "impeghd_ele_interaction_intrfc.h"
+#include "impeghd_hoa_data_types.h"
+#include "impeghd_hoa_frame_params.h"
+#include "impeghd_hoa_nfc_filtering.h"
+#include "impeghd_hoa_space_positions.h"
+#include "impeghd_hoa_simple_mtrx.h"
+#include "impeghd_hoa_render_mtrx.h"
+#include "impeghd_hoa_renderer.h"
+#include "impeghd_hoa_spatial_decoder_struct.h"
+#include "impeghd_hoa_spatial_decoder.h"
+#include "impeghd_hoa_decoder.h"
+#include "impeghd_3d_vec_struct_def.h"
+#include "impeghd_cicp_defines.h"
+#include "impeghd_cicp_struct_def.h"
+#include "impeghd_oam_dec_defines.h"
+#include "impeghd_oam_dec_struct_def.h"
+#include "impeghd_obj_ren_dec_defines.h"
+#include "impeghd_obj_ren_dec_struct_def.h"
+#include "impeghd_uni_drc_struct.h"
+#include "ia_core_coder_main.h"
+#include "ia_core_coder_arith_dec.h"
+#include "ia_core_coder_bit_extract.h"
+#include "ia_core_coder_func_def.h"
+#include "impeghd_binaural_renderer.h"
+#include "impeghd_format_conv_defines.h"
+#include "impeghd_format_conv_rom.h"
+#include "impeghd_format_conv_data.h"
+#include "impeghd_peak_limiter_struct_def.h"
+#include "impeghd_resampler.h"
+#include "ia_core_coder_struct.h"
+#include "ia_core_coder_create.h"
+#include "impeghd_cicp_2_geometry_rom.h"
+#include "impeghd_cicp_2_geometry.h"
+#include "impeghd_obj_ren_dec.h"
+
+
+#include <dlfcn.h>
+#include <stdio.h>
+#include "impd_drc_filter_bank.h"
+#include "impd_drc_gain_dec.h"
+#include "impd_drc_multi_band.h"
+#include "impd_drc_process_audio.h"
+#include "seam_internal.h"
+
+#define FRAME 1024
+#define SB 256
+#define SLOTS 4
+#define MAX_SEQ (CHANNEL_GROUP_COUNT_MAX * BAND_COUNT_MAX)
+
+static int gain_offset(const ia_drc_params_struct *p)
+{
+  return MAX_SIGNAL_DELAY - p->gain_delay_samples + (p->delay_mode == DELAY_MODE_LOW ? p->drc_frame_size : 0);
+}
+
+/* ---- sub-band gains ---------------------------------------------------------------------------------------------- */
+typedef struct
+{
+  int n_ch, n_seq, n_rows;
+  FLOAT32 **re, **im; /* rows sig_idx = 0 .. n_ch - 1 */
+  mpeghb200_drc_sb_channel chan[MAX_CHANNEL_COUNT];
+  float gains[MAX_SEQ][SLOTS];
+  const float *wrow[MAX_SEQ]; /* overlap_weight[256] of every (multi-band group, band) */
+} sb_job;
+static seam_buf b_sb_re, b_sb_im, b_sb_chan, b_sb_gain, b_sb_w;
+
+static void be_drc_sb(seam_req **rq, int n)
+{
+  mpeghb200_ctx *ctx = seam_ctx();
+  int N = 0, Q = 0, R = 0, i, c, k, c0 = 0, q0 = 0, r0 = 0;
+  for (i = 0; i < n; i++)
+  {
+    const sb_job *j = (const sb_job *)rq[i]->p[0];
+    N += j->n_ch, Q += j->n_seq, R += j->n_rows;
+  }
+  seam_need(&b_sb_re, (size_t)N * FRAME * sizeof(float)), seam_need(&b_sb_im, (size_t)N * FRAME * sizeof(float));
+  seam_need(&b_sb_chan, (size_t)N * sizeof(mpeghb200_drc_sb_channel));
+  seam_need(&b_sb_gain, (size_t)(Q ? Q : 1) * SLOTS * sizeof(float)), seam_need(&b_sb_w, (size_t)(R ? R : 1) * SB * sizeof(float));
+  for (i = 0; i < n; i++)
+  {
+    const sb_job *j = (const sb_job *)rq[i]->p[0];
+    for (c = 0; c < j->n_ch; c++)
+    {
+      mpeghb200_drc_sb_channel *d = (mpeghb200_drc_sb_channel *)b_sb_chan.h + c0 + c;
+      *d = j->chan[c];
+      if (d->first_seq >= 0)
+        d->first_seq += q0, d->weight_row += r0;
+      memcpy((float *)b_sb_re.h + (size_t)(c0 + c) * FRAME, j->re[c], FRAME * sizeof(float));
+      memcpy((float *)b_sb_im.h + (size_t)(c0 + c) * FRAME, j->im[c], FRAME * sizeof(float));
+    }
+    memcpy((float *)b_sb_gain.h + (size_t)q0 * SLOTS, j->gains, (size_t)j->n_seq * SLOTS * sizeof(float));
+    for (k = 0; k < j->n_rows; k++)
+      memcpy((float *)b_sb_w.h + (size_t)(r0 + k) * SB, j->wrow[k], SB * sizeof(float));
+    c0 += j->n_ch, q0 += j->n_seq, r0 += j->n_rows;
+  }
+  CK(mpeghb200_h2d(ctx, b_sb_re.d, b_sb_re.h, (size_t)N * FRAME * sizeof(float)));
+  CK(mpeghb200_h2d(ctx, b_sb_im.d, b_sb_im.h, (size_t)N * FRAME * sizeof(float)));
+  CK(mpeghb200_h2d(ctx, b_sb_chan.d, b_sb_chan.h, (size_t)N * sizeof(mpeghb200_drc_sb_channel)));
+  CK(mpeghb200_h2d(ctx, b_sb_gain.d, b_sb_gain.h, (size_t)(Q ? Q : 1) * SLOTS * sizeof(float)));
+  CK(mpeghb200_h2d(ctx, b_sb_w.d, b_sb_w.h, (size_t)(R ? R : 1) * SB * sizeof(float)));
+  CK(mpeghb200_gain_subband_dev(ctx, (float *)b_sb_re.d, (float *)b_sb_im.d, (const mpeghb200_drc_sb_channel *)b_sb_chan.d,
+                                (const float *)b_sb_gain.d, (const float *)b_sb_w.d, N, NULL));
+  CK(mpeghb200_d2h(ctx, b_sb_re.h, b_sb_re.d, (size_t)N * FRAME * sizeof(float)));
+  CK(mpeghb200_d2h(ctx, b_sb_im.h, b_sb_im.d, (size_t)N * FRAME * sizeof(float)));
+  for (i = 0, c0 = 0; i < n; i++)
+  {
+    const sb_job *j = (const sb_job *)rq[i]->p[0];
+    for (c = 0; c < j->n_ch; c++)
+    {
+      memcpy(j->re[c], (float *)b_sb_re.h + (size_t)(c0 + c) * FRAME, FRAME * sizeof(float));
+      memcpy(j->im[c], (float *)b_sb_im.h + (size_t)(c0 + c) * FRAME, FRAME * sizeof(float));
+    }
+    c0 += j->n_ch;
+  }
+  seam_n.drc_sb += (unsigned long)N;
+}
+
+IA_ERRORCODE impd_drc_apply_gains_subband(FLOAT32 *deinterleaved_audio_re[], FLOAT32 *deinterleaved_audio_im[],
+                                          ia_drc_instructions_struct *pstr_drc_instruction_arr,
+                                          ia_drc_gain_dec_struct *pstr_drc_gain_dec, WORD32 sel_drc_idx)
+{
+  ia_drc_params_struct *p = &pstr_drc_gain_dec->ia_drc_params_struct;
+  const ia_drc_gain_buffer_struct *gb = &pstr_drc_gain_dec->drc_gain_buffers.pstr_gain_buf[sel_drc_idx];
+  const WORD32 ii = p->sel_drc_array[sel_drc_idx].drc_instrns_idx;
+  const ia_drc_instructions_struct *ins;
+  int first[CHANNEL_GROUP_COUNT_MAX], row[CHANNEL_GROUP_COUNT_MAX], g, b, c, s, off;
+  sb_job j;
+  seam_req r;
+  if (p->sub_band_domain_mode != SUBBAND_DOMAIN_MODE_STFT256 || p->drc_frame_size != FRAME ||
+      (ii >= 0 && pstr_drc_instruction_arr[ii].num_drc_ch_groups > CHANNEL_GROUP_COUNT_MAX))
+  { /* the QMF domains are not part of the decoder's signal path (the domain switcher is STFT256): forwarded */
+    typedef IA_ERRORCODE (*fn_t)(FLOAT32 **, FLOAT32 **, ia_drc_instructions_struct *, ia_drc_gain_dec_struct *, WORD32);
+    static fn_t real;
+    if (!real)
+      real = (fn_t)seam_real("impd_drc_apply_gains_subband");
+    seam_n.drc_host++;
+    return real(deinterleaved_audio_re, deinterleaved_audio_im, pstr_drc_instruction_arr, pstr_drc_gain_dec, sel_drc_idx);
+  }
+  if (ii < 0)
+    return IA_MPEGH_DEC_NO_ERROR;
+  ins = &pstr_drc_instruction_arr[ii];
+  if (ins->drc_set_id <= 0)
+    return IA_MPEGH_DEC_NO_ERROR;
+  for (g = 0; g < ins->num_drc_ch_groups; g++)
+    if (ins->band_count_of_ch_group[g] < 1 || ins->band_count_of_ch_group[g] > BAND_COUNT_MAX)
+    { /* not a band count the parser produces: leave it to the reference */
+      typedef IA_ERRORCODE (*fn_t)(FLOAT32 **, FLOAT32 **, ia_drc_instructions_struct *, ia_drc_gain_dec_struct *, WORD32);
+      seam_n.drc_host++;
+      return ((fn_t)seam_real("impd_drc_apply_gains_subband"))(deinterleaved_audio_re, deinterleaved_audio_im,
+                                                                       pstr_drc_instruction_arr, pstr_drc_gain_dec,
+                                                                       sel_drc_idx);
+    }
+  if (p->num_ch_process == -1) /* :318-325 */
+    p->num_ch_process = ins->audio_num_chan;
+  if (ins->audio_num_chan < p->channel_offset + p->num_ch_process)
+    return IA_MPEGD_DRC_INIT_FATAL_UNSUPPORTED_CH_COUNT;
+  off = gain_offset(p);
+  memset(&j, 0, sizeof(j));
+  for (g = 0; g < ins->num_drc_ch_groups; g++)
+  {
+    const int nb = ins->band_count_of_ch_group[g] < 1 ? 1 : ins->band_count_of_ch_group[g];
+    first[g] = j.n_seq, row[g] = j.n_rows;
+    for (b = 0; b < nb; b++)
+    {
+      const float *l = gb->pstr_buf_interp[first[g] + b].lpcm_gains + off;
+      for (s = 0; s < SLOTS; s++)
+        j.gains[j.n_seq][s] = l[s * SB + (SB - 1) / 2]; /* the slot centre (:328, :345) */
+      j.n_seq++;
+      if (nb > 1)
+        j.wrow[j.n_rows++] =
+            pstr_drc_gain_dec->str_overlap_params.str_grp_overlap_params[g].str_band_overlap_params[b].overlap_weight;
+    }
+  }
+  j.n_ch = p->num_ch_process;
+  j.re = deinterleaved_audio_re, j.im = deinterleaved_audio_im;
+  for (c = 0; c < j.n_ch; c++)
+  {
+    g = ins->channel_group_of_ch[p->channel_offset + c];
+    j.chan[c].first_seq = g >= 0 ? first[g] : -1;
+    j.chan[c].band_count = g >= 0 ? ins->band_count_of_ch_group[g] : 0;
+    j.chan[c].weight_row = g >= 0 ? row[g] : 0;
+  }
+  r.kind = RQ_DRCSB;
+  r.p[0] = &j;
+  seam_submit(&r);
+  return IA_MPEGH_DEC_NO_ERROR;
+}
+
+/* ---- time domain: filter banks + gains + band sum ---------------------------------------------------------------- */
+typedef struct
+{
+  int n_ch, n_seq, n_banks;
+  const void *key;
+  FLOAT32 **audio; /* rows of the frame, channel_offset already taken off */
+  mpeghb200_drc_td_channel chan[MAX_CHANNEL_COUNT];
+  mpeghb200_drc_td_bank bank[10];
+  const float *gain[MAX_SEQ]; /* 1024 samples each */
+} td_job;
+static seam_buf b_td_x, b_td_chan, b_td_bank, b_td_gain;
+static seam_pool td_pool[MAX_CHANNEL_COUNT + 1]; /* by channel count of the request */
+
+static void td_run(td_job *j, float *d_state)
+{
+  mpeghb200_ctx *ctx = seam_ctx();
+  int c, k;
+  seam_need(&b_td_x, (size_t)j->n_ch * FRAME * sizeof(float)), seam_need(&b_td_chan, sizeof(j->chan));
+  seam_need(&b_td_bank, sizeof(j->bank)), seam_need(&b_td_gain, (size_t)(j->n_seq ? j->n_seq : 1) * FRAME * sizeof(float));
+  for (c = 0; c < j->n_ch; c++)
+    memcpy((float *)b_td_x.h + (size_t)c * FRAME, j->audio[c], FRAME * sizeof(float));
+  for (k = 0; k < j->n_seq; k++)
+    memcpy((float *)b_td_gain.h + (size_t)k * FRAME, j->gain[k], FRAME * sizeof(float));
+  memcpy(b_td_chan.h, j->chan, sizeof(j->chan)), memcpy(b_td_bank.h, j->bank, sizeof(j->bank));
+  CK(mpeghb200_h2d(ctx, b_td_x.d, b_td_x.h, (size_t)j->n_ch * FRAME * sizeof(float)));
+  CK(mpeghb200_h2d(ctx, b_td_chan.d, b_td_chan.h, sizeof(j->chan)));
+  CK(mpeghb200_h2d(ctx, b_td_bank.d, b_td_bank.h, sizeof(j->bank)));
+  CK(mpeghb200_h2d(ctx, b_td_gain.d, b_td_gain.h, (size_t)(j->n_seq ? j->n_seq : 1) * FRAME * sizeof(float)));
+  CK(mpeghb200_drc_td_dev(ctx, (float *)b_td_x.d, d_state, (const mpeghb200_drc_td_channel *)b_td_chan.d,
+                          (const mpeghb200_drc_td_bank *)b_td_bank.d, (const float *)b_td_gain.d, j->n_ch, NULL));
+  CK(mpeghb200_d2h(ctx, b_td_x.h, b_td_x.d, (size_t)j->n_ch * FRAME * sizeof(float)));
+  for (c = 0; c < j->n_ch; c++)
+    memcpy(j->audio[c], (float *)b_td_x.h + (size_t)c * FRAME, FRAME * sizeof(float));
+}
+
+/* the banks differ from handle to handle (they are designed from the stream's DRC configuration), so a request is
+ * its own launch; the filter memories of its channels sit in a device slot of their own */
+static void be_drc_td(seam_req **rq, int n)
+{
+  int i, fresh;
+  for (i = 0; i < n; i++)
+  {
+    td_job *j = (td_job *)rq[i]->p[0];
+    seam_pool *pool = &td_pool[j->n_ch];
+    float *st;
+    pool->stride = (size_t)j->n_ch * mpeghb200_drc_td_state_floats() * sizeof(float);
+    fresh = 0;
+    st = (float *)seam_pool_one(pool, j->key, &fresh);
+    if (fresh)
+      CK(mpeghb200_dev_memset(seam_ctx(), st, 0, pool->stride));
+    td_run(j, st);
+    seam_n.drc_td += (unsigned long)j->n_ch;
+  }
+}
+
+static void set_f(mpeghb200_drc_biquad *d, const ia_iir_filter_struct *s)
+{
+  d->a1 = s->a1, d->a2 = s->a2, d->b0 = s->b0, d->b1 = s->b1, d->b2 = s->b2;
+}
+static void bank_of(mpeghb200_drc_td_bank *d, const ia_drc_filter_bank_struct *b, int n_bands)
+{
+  int i;
+  memset(d, 0, sizeof(*d));
+  d->n_bands = n_bands;
+  d->n_cascade = b->str_all_pass_cascade.num_filter > 0 ? b->str_all_pass_cascade.num_filter + 1 : 0; /* filter_bank.c:604 */
+  if (d->n_cascade > CASCADE_ALLPASS_COUNT_MAX)
+    d->n_cascade = CASCADE_ALLPASS_COUNT_MAX;
+  for (i = 0; i < d->n_cascade; i++)
+    set_f(&d->ap[i], &b->str_all_pass_cascade.str_ap_cascade_filt[i].str_ap_stage);
+  if (n_bands == 2)
+    set_f(&d->f[0], &b->str_two_band_filt_bank.str_lp), set_f(&d->f[1], &b->str_two_band_filt_bank.str_hp);
+  else if (n_bands == 3)
+  {
+    const ia_three_band_filt_struct *t = &b->str_three_band_filt_bank;
+    set_f(&d->f[0], &t->str_lp_stage_1), set_f(&d->f[1], &t->str_hp_stage_1), set_f(&d->f[2], &t->str_ap_stage_2);
+    set_f(&d->f[3], &t->str_lp_stage_2), set_f(&d->f[4], &t->str_hp_stage_2);
+  }
+  else if (n_bands == 4)
+  {
+    const ia_four_band_filt_struct *t = &b->str_four_band_filt_bank;
+    set_f(&d->f[0], &t->str_lp_stage_1), set_f(&d->f[1], &t->str_hp_stage_1);
+    set_f(&d->f[2], &t->str_ap_stage_2_low), set_f(&d->f[3], &t->str_ap_stage_2_high);
+    set_f(&d->f[4], &t->str_lp_stage_3_low), set_f(&d->f[5], &t->str_hp_stage_3_low);
+    set_f(&d->f[6], &t->str_lp_stage_3_high), set_f(&d->f[7], &t->str_hp_stage_3_high);
+  }
+}
+
+typedef VOID (*add_fn)(ia_drc_gain_dec_struct *, FLOAT32 **, ia_drc_instructions_struct *, WORD32, WORD32);
+typedef IA_ERRORCODE (*banks_fn)(FLOAT32 **, ia_drc_instructions_struct *, ia_drc_gain_dec_struct *, WORD32);
+static add_fn real_add(void)
+{
+  static add_fn f;
+  static int looked;
+  if (!looked)
+    f = (add_fn)dlsym(RTLD_NEXT, "impd_drc_apply_gains_and_add"), looked = 1;
+  return f; /* NULL: `static` in the reference library in use */
+}
+/* MPEGHB200_SEAM_DRC_TD_HOST=1 leaves the pair in the reference even where it could be taken over (tests) */
+static int td_enabled(void)
+{
+  static int on = -1;
+  if (on < 0)
+    on = real_add() != NULL && !getenv("MPEGHB200_SEAM_DRC_TD_HOST");
+  return on;
+}
+
+/* what the pending filter_banks_process call of this thread was given (no yield between the two calls) */
+static __thread FLOAT32 **tl_audio;
+static __thread const ia_drc_gain_dec_struct *tl_dec;
+static __thread int tl_sel = -1;
+
+static int td_on_gpu(const ia_drc_instructions_struct *arr, const ia_drc_gain_dec_struct *dec, int sel)
+{
+  const ia_drc_params_struct *p = &dec->ia_drc_params_struct;
+  const int ii = p->sel_drc_array[sel].drc_instrns_idx;
+  const ia_drc_instructions_struct *ins;
+  int g;
+  if (!td_enabled() || ii < 0 || p->drc_frame_size != FRAME || p->num_ch_process < 1 || p->num_ch_process > MAX_CHANNEL_COUNT)
+    return 0;
+  ins = &arr[ii];
+  if (ins->drc_set_id <= 0 || ins->num_drc_ch_groups < 0 || ins->num_drc_ch_groups > 8 ||
+      ins->audio_num_chan < p->channel_offset + p->num_ch_process)
+    return 0;
+  for (g = 0; g < ins->num_drc_ch_groups; g++)
+  {
+    const int nb = ins->band_count_of_ch_group[g];
+    if (nb < 1 || nb > 4 || (p->multiband_sel_drc_idx != sel && nb != 1))
+      return 0;
+  }
+  return 1;
+}
+
+IA_ERRORCODE impd_drc_filter_banks_process(FLOAT32 *audio_io_buf[], ia_drc_instructions_struct *pstr_drc_instruction_arr,
+                                           ia_drc_gain_dec_struct *pstr_drc_gain_dec, WORD32 sel_drc_idx)
+{
+  if (!td_on_gpu(pstr_drc_instruction_arr, pstr_drc_gain_dec, sel_drc_idx))
+  {
+    static banks_fn real;
+    if (!real)
+      real = (banks_fn)seam_real("impd_drc_filter_banks_process");
+    tl_sel = -1;
+    seam_n.drc_host++;
+    return real(audio_io_buf, pstr_drc_instruction_arr, pstr_drc_gain_dec, sel_drc_idx);
+  }
+  tl_audio = audio_io_buf, tl_dec = pstr_drc_gain_dec, tl_sel = sel_drc_idx;
+  return IA_MPEGH_DEC_NO_ERROR;
+}
+
+/* `static` in the stock reference (see the file header) */
+VOID impd_drc_apply_gains_and_add(ia_drc_gain_dec_struct *pstr_drc_gain_dec, FLOAT32 *channel_audio[],
+                                  ia_drc_instructions_struct *pstr_drc_instruction_arr, WORD32 impd_apply_gains,
+                                  WORD32 sel_drc_idx)
+{
+  const ia_drc_params_struct *p = &pstr_drc_gain_dec->ia_drc_params_struct;
+  const ia_drc_gain_buffer_struct *gb = &pstr_drc_gain_dec->drc_gain_buffers.pstr_gain_buf[sel_drc_idx];
+  const ia_drc_instructions_struct *ins;
+  const int pass = p->multiband_sel_drc_idx != sel_drc_idx;
+  int first[8], g, b, c, off;
+  td_job j;
+  seam_req r;
+  if (tl_sel != sel_drc_idx || tl_dec != pstr_drc_gain_dec || impd_apply_gains != 1 || tl_audio != channel_audio)
+  { /* not the pair recorded above (the bank split ran in the reference): the reference finishes it */
+    tl_sel = -1;
+    real_add()(pstr_drc_gain_dec, channel_audio, pstr_drc_instruction_arr, impd_apply_gains, sel_drc_idx);
+    return;
+  }
+  tl_sel = -1;
+  ins = &pstr_drc_instruction_arr[p->sel_drc_array[sel_drc_idx].drc_instrns_idx];
+  off = gain_offset(p);
+  memset(&j, 0, sizeof(j));
+  j.n_ch = p->num_ch_process, j.audio = channel_audio;
+  j.key = (const char *)pstr_drc_gain_dec + sel_drc_idx;
+  for (g = 0; g < ins->num_drc_ch_groups; g++)
+  {
+    const int nb = ins->band_count_of_ch_group[g];
+    first[g] = j.n_seq;
+    for (b = 0; b < nb; b++)
+      j.gain[j.n_seq++] = gb->pstr_buf_interp[first[g] + b].lpcm_gains + off;
+    if (pass) /* a set that is not the multi-band one: no split, no phase alignment (:417-424) */
+      memset(&j.bank[g], 0, sizeof(j.bank[g])), j.bank[g].n_bands = 1;
+    else
+      bank_of(&j.bank[g], &pstr_drc_gain_dec->ia_filter_banks_struct.str_drc_filter_bank[g], nb);
+  }
+  g = ins->num_drc_ch_groups; /* the bank of the channels outside every group: its cascade only (:452-457) */
+  if (pass)
+    memset(&j.bank[g], 0, sizeof(j.bank[g])), j.bank[g].n_bands = 1;
+  else
+    bank_of(&j.bank[g], &pstr_drc_gain_dec->ia_filter_banks_struct.str_drc_filter_bank[g], 1);
+  j.n_banks = g + 1;
+  for (c = 0; c < j.n_ch; c++)
+  {
+    g = ins->channel_group_of_ch[p->channel_offset + c];
+    j.chan[c].bank = g >= 0 ? g : ins->num_drc_ch_groups;
+    j.chan[c].first_seq = g >= 0 ? first[g] : -1;
+  }
+  r.kind = RQ_DRCTD;
+  r.p[0] = &j;
+  seam_submit(&r);
+}
+
+__attribute__((constructor)) static void seam_register_drc(void)
+{
+  seam_register(RQ_DRCSB, be_drc_sb, "drc_apply_gains_subband");
+  seam_register(RQ_DRCTD, be_drc_td, "drc filter banks + gains");
+}

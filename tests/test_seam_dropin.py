@@ -546,3 +546,86 @@ def test_seam_igf(tmp_path, mode):
                 assert 0 < st <= n and mono == 0  # pairs with both channels silent never reach the tool
         outs.append(np.load(out))
     assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+
+
+DRC_SCRIPT = r"""
+import sys, os, numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+import drc_cases
+from oracle import loader
+mode, out_path = sys.argv[2], sys.argv[3]
+outs = []
+n_channels = 0
+if mode == "subband":
+    ref = loader.load_ref()
+    for seed in range(12):
+        rng = np.random.default_rng(600 + seed)
+        fr = drc_cases.random_frame(rng)
+        re, im = drc_cases.run_oracle(ref.ref_drc_gains_subband, fr, (int(rng.integers(0, 2)), int(rng.integers(0, 400))))
+        pad = np.zeros((2, 16, 1024), np.float32)
+        pad[0, :fr["n_ch"]], pad[1, :fr["n_ch"]] = re, im
+        outs.append(pad)
+        n_channels += fr["n_ch"]
+else:
+    # the interposers look the reference's own functions up behind themselves (see RS_SCRIPT)
+    import ctypes
+    ctypes.CDLL(os.path.join(sys.argv[1], "oracle", "_ref", "libmpeghref_ns.so"), mode=ctypes.RTLD_GLOBAL)
+    ref = loader.load_ref_ns()
+    for seed in range(8):
+        rng = np.random.default_rng(700 + seed)
+        setup = drc_cases.random_td_frame_setup(rng)
+        frames = drc_cases.td_frames(rng, setup, 3)
+        y = drc_cases.td_reference(ref, setup, frames)
+        pad = np.zeros((3, 12, 1024), np.float32)
+        pad[:, :setup["n_ch"]] = y
+        outs.append(pad)
+        n_channels += 3 * setup["n_ch"]
+np.save(out_path, np.stack(outs))
+print("CHANNELS", n_channels)
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["subband", "td_ns", "td_host"])
+def test_seam_drc(tmp_path, mode):
+    """Application of the DRC gains through the unmodified reference functions (oracle/ref_harness_drc.c,
+    ref_harness_ns.c fill ia_drc_gain_dec_struct / ia_drc_instructions_struct the way the gain decoder leaves them):
+    impd_drc_apply_gains_subband (STFT256 domain: single- and multi-band groups, channels without a group, both delay
+    modes, gain delays) with the stock library; impd_drc_filter_banks_process + impd_drc_apply_gains_and_add (time domain:
+    2 / 3 / 4-band Linkwitz-Riley banks, phase-alignment cascades, three frames with carried filter memories) with the
+    reference build that exports the second, `static`, function; against the stock library that pair is forwarded
+    to the reference, which "td_host" forces (MPEGHB200_SEAM_DRC_TD_HOST=1) to cover the forwarding path."""
+    libref = os.path.join(REF_DIR, "libmpeghref.so")
+    _need(libref, SEAM)
+    if mode != "subband":
+        _need(os.path.join(REF_DIR, "libmpeghref_ns.so"))
+    script = tmp_path / "h.py"
+    script.write_text(DRC_SCRIPT)
+    outs, n_channels = [], 0
+    for preload in (None, SEAM):
+        env = dict(os.environ)
+        if preload:
+            env["LD_PRELOAD"], env["MPEGHB200_SEAM_STATS"] = preload, "1"
+            if mode == "td_host":
+                env["MPEGHB200_SEAM_DRC_TD_HOST"] = "1"
+        out = str(tmp_path / ("gpu.npy" if preload else "ref.npy"))
+        r = subprocess.run([sys.executable, str(script), ROOT, mode, out], env=env, capture_output=True, text=True,
+                           timeout=900)
+        assert r.returncode == 0, r.stderr[-800:]
+        n_channels = int(re.search(r"CHANNELS (\d+)", r.stdout).group(1))
+        if preload:
+            m = re.search(r"drc_channels subband=(\d+) time_domain=(\d+) host\(calls\)=(\d+)", r.stderr)
+            if mode == "td_host" and not m:  # nothing reached the GPU, so no context and no statistics line
+                outs.append(np.load(out))
+                continue
+            assert m, r.stderr[-400:]
+            sb, td, host = (int(x) for x in m.groups())
+            print(mode, dict(subband=sb, time_domain=td, host=host, channels=n_channels))
+            if mode == "subband":
+                assert sb == n_channels and td == 0 and host == 0
+            elif mode == "td_ns":
+                assert td == n_channels and host == 0
+            else:
+                assert td == 0 and host > 0  # the pair stays in the reference
+        outs.append(np.load(out))
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
