@@ -828,6 +828,7 @@ def main():
                          "peak_source": peak_src,
                          "kernel": "fd_synth_ws_kernel" if FPL == 1 else "fd_synth_ws_frames_kernel",
                          "algorithmic_bytes_per_unit": BYTES_PER_UNIT,
+                         "units_per_launch": UNITS * FPL,  # channel-frames: streams x channels x frames_per_step
                          "algorithmic_bytes_per_launch": BYTES_PER_UNIT * UNITS * FPL,
                          "note": "SURVEY.md 8(d): 16 KB per channel-frame (spectra in, overlap read + write, PCM out), "
                                  "what ia_core_coder_fd_frm_dec moves per call" +
