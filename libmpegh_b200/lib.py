@@ -272,6 +272,8 @@ class Lib:
         c.mpeghb200_mct_rom.restype = None
         c.mpeghb200_bus_add_dev.argtypes = [vp, vp, vp, vp, sz, vp]
         c.mpeghb200_bus_add_dev.restype = i32
+        c.mpeghb200_interleave_dev.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
+        c.mpeghb200_interleave_dev.restype = i32
         c.mpeghb200_channel_mask_dev.argtypes = [vp, vp, vp, ctypes.c_int, vp]
         c.mpeghb200_channel_mask_dev.restype = i32
         c.mpeghb200_ltpf_state_floats.argtypes = [ctypes.c_int]
@@ -496,6 +498,11 @@ class Lib:
 
     def bus_add_dev(self, d_a, d_b, d_out, n_floats, stream=0):
         self.check(self.c.mpeghb200_bus_add_dev(self.ctx, d_a, d_b, d_out, n_floats, stream))
+
+    def interleave_dev(self, d_in, d_out, n_ch, n_samples, to_planar, n_streams, stream=0):
+        """to_planar: [stream][n_samples][n_ch] -> [stream][n_ch][n_samples]; else the reverse."""
+        self.check(self.c.mpeghb200_interleave_dev(self.ctx, d_in, d_out, n_ch, n_samples, int(to_planar), n_streams,
+                                                   stream))
 
     def channel_mask_dev(self, d_audio, d_on, n_channels, stream=0):
         self.check(self.c.mpeghb200_channel_mask_dev(self.ctx, d_audio, d_on, n_channels, stream))

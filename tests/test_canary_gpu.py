@@ -128,3 +128,41 @@ def test_hoa_render(gpu_lib, cfg_idx, mode):
     for b, n in ((d_in, "in"), (d_out, "out"), (state, "nfc state")):
         b.check(f"hoa_render {k} mode {mode} {n}")
     gpu_lib.hoa_renderer_destroy(h)
+
+
+@pytest.mark.parametrize("F,U", [(2, 1), (3, 7), (8, 148 * 3 + 5)])
+def test_fd_synth_frames_ragged_counts(gpu_lib, F, U):
+    """The multi-frame launch: coefficients / PCM [F][U][1024], overlap [U][1024], with generic-path frames inside."""
+    import torch
+    rng = np.random.default_rng(F * 100 + U)
+    side = fd_cases.pack_side(fd_cases.random_side(rng, F, U, kernel_switch_prob=0.2)).astype(np.int32)
+    coef = Guarded(F * U * 1024, fill=fd_cases.random_coef(rng, (F, U, 1024)))
+    ov, out = Guarded(U * 1024), Guarded(F * U * 1024)
+    d_side = Guarded(F * U, "int32", fill=side)
+    gpu_lib.fd_synth_frames_dev(coef.ptr, d_side.ptr, ov.ptr, out.ptr, U, F, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for b, n in ((coef, "coef"), (ov, "overlap"), (out, "out"), (d_side, "side")):
+        b.check(f"fd_synth_frames F={F} U={U} {n}")
+
+
+@pytest.mark.parametrize("n_in,length,nb", [(3, 300, 1), (2, 40, 0), (2, 5000, 1)])
+def test_binaural_generic_sizes(gpu_lib, n_in, length, nb):
+    """The generic binaural path keeps its per-stream workspace behind the carried state: state and output guarded."""
+    import torch
+    import bin_cases
+    rng = np.random.default_rng(length)
+    f = bin_cases.brir_set(rng, n_in, length, nb)
+    h = gpu_lib.binaural_create(f["taps_direct"][None], f["taps_diffuse"][None], f["direct_fc"][None],
+                                f["diffuse_fc"][None], f["weight"][None])
+    B, S = gpu_lib.binaural_block_len(h), 3
+    x = rng.normal(0, 0.1, (S, n_in, B)).astype(np.float32)
+    d_in = Guarded(x.size, fill=x)
+    d_out = Guarded(S * 2 * B)
+    state = Guarded(S * gpu_lib.binaural_state_floats(h))
+    for _ in range(2):
+        gpu_lib.binaural_block_dev(h, d_in.ptr, d_out.ptr, state.ptr, S, 0, 1.0, 1.0, None,
+                                   torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for b, n in ((d_in, "in"), (d_out, "out"), (state, "state")):
+        b.check(f"binaural N={2 * B} {n}")
+    gpu_lib.binaural_destroy(h)

@@ -60,3 +60,24 @@ def test_gain_apply(gpu_lib):
     sel = seq >= 0
     want[sel] = x[sel] * g[seq[sel]]
     assert bits_equal(d.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("n_ch,n_samples,S", [(1, 1024, 3), (2, 1024, 5), (12, 1024, 7), (24, 1024, 2), (64, 1024, 1),
+                                             (5, 100, 3), (13, 4096, 2)])
+def test_interleave_round_trip(gpu_lib, n_ch, n_samples, S):
+    """mpeghb200_interleave_dev: [stream][sample][channel] <-> [stream][channel][sample], the copy the reference builds
+    around its limiter (decoder/ia_core_coder_decode_main.c:1429-1460); pure data movement, compared with numpy."""
+    import torch
+    rng = np.random.default_rng(n_ch * 1000 + n_samples)
+    x = rng.standard_normal((S, n_samples, n_ch)).astype(np.float32)
+    x[0, 0, 0] = -0.0
+    d_x = torch.from_numpy(x).cuda()
+    d_p = torch.full((S, n_ch, n_samples), float("nan"), device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    gpu_lib.interleave_dev(d_x.data_ptr(), d_p.data_ptr(), n_ch, n_samples, True, S, st)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_p.cpu().numpy().view(np.uint32), np.ascontiguousarray(x.transpose(0, 2, 1)).view(np.uint32))
+    d_y = torch.full((S, n_samples, n_ch), float("nan"), device="cuda")
+    gpu_lib.interleave_dev(d_p.data_ptr(), d_y.data_ptr(), n_ch, n_samples, False, S, st)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_y.cpu().numpy().view(np.uint32), x.view(np.uint32))
