@@ -632,6 +632,15 @@ mpeghb200_status mpeghb200_drc_stft_dev(mpeghb200_ctx *ctx, float *d_audio, floa
                                         const mpeghb200_drc_sb_channel *d_chan, int n_sets, const float *d_gains,
                                         const float *d_weights, int n_channels, void *cuda_stream);
 
+/* The two halves of the domain switcher on their own (impeghd_domain_switcher_process with ds_t2f = 1 / 0,
+ * decoder/ia_core_coder_process.c:556-585, :589-619), for callers that apply the gains as a separate step
+ * (mpeghb200_gain_subband_dev on the two planes): to_frequency != 0 reads d_audio [n_channels][1024] and writes d_spec
+ * [n_channels][2048] = re [4][256] | im [4][256] in the reference's packed form (time_sample_stft: im[slot][0] carries the
+ * Nyquist bin); 0 reads d_spec and writes d_audio.  d_state [n_channels][512] as above: the first half belongs to the
+ * forward direction (previous input slot), the second to the inverse one (output overlap); each call touches its own. */
+mpeghb200_status mpeghb200_stft_dev(mpeghb200_ctx *ctx, float *d_audio, float *d_spec, float *d_state, int to_frequency,
+                                    int n_channels, void *cuda_stream);
+
 /* Time-domain multi-band DRC of one selected set, in place on d_audio [n_channels][1024]: phase-alignment all-pass
  * cascade, Linkwitz-Riley band split (2, 3 or 4 bands), per-band gain curves, band sum --
  * impd_drc_filter_banks_process (decoder/impd_drc_process.c:399; banks decoder/impd_drc_filter_bank.c:367-613) and the

@@ -26,12 +26,16 @@ struct DsParams {
   const mpeghb200_drc_sb_channel* chan;  // [n_sets][n_ch]
   const float* gains;                    // [n_seq][4]
   const float* weights;                  // [rows][256]
+  float* spec;                           // stand-alone transforms: [n_ch][2048] = re [4][256] | im [4][256], im[slot][0] = Nyquist
   const float* win;                      // [256]
   const float4* eff8;
   const float2* rad2;
   int n_ch, n_sets;
 };
 
+// MODE 0: the fused step.  MODE 1 / 2: one half of the domain switcher on its own (time -> frequency into P.spec,
+// frequency -> time out of it), for callers that run the gain application as a separate step (the drop-in library).
+template <int MODE>
 __global__ void __launch_bounds__(32 * kDsWarps) drc_stft_kernel(const __grid_constant__ DsParams P) {
   __shared__ __align__(16) float2 work[kDsWarps][kDsBuf];
   __shared__ __align__(16) float twf[500];
@@ -45,41 +49,62 @@ __global__ void __launch_bounds__(32 * kDsWarps) drc_stft_kernel(const __grid_co
   float2* buf = work[warp];
   float* x = P.audio + size_t(c) * 1024;
   float* st = P.state + size_t(c) * 512;
+  float* sp = MODE == 0 ? nullptr : P.spec + size_t(c) * 2048;
   const int r3 = rev32(lane);
   float wv[8], wr[8], hist[8], ohist[8];  // the lane's sample positions are i = r3 + 32 u (see format_conv.cu)
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
     wv[u] = __ldg(P.win + r3 + 32 * u);
     wr[u] = __ldg(P.win + 255 - r3 - 32 * u);
-    hist[u] = st[r3 + 32 * u];
-    ohist[u] = st[256 + r3 + 32 * u];
+    hist[u] = MODE != 2 ? st[r3 + 32 * u] : 0.0f;
+    ohist[u] = MODE != 1 ? st[256 + r3 + 32 * u] : 0.0f;
   }
   for (int slot = 0; slot < 4; ++slot) {
     // ---- time -> frequency (process.c:556-585) ----
     float2 v[16];
     float* xs = x + slot * 256;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const float cur = xs[r3 + 32 * u];
-      v[u] = make_float2(fmul(hist[u], wv[u]), 0.0f);
-      v[8 + u] = make_float2(fmul(wr[u], cur), 0.0f);
-      hist[u] = cur;
-    }
-    fft512_tail<false>(v, buf, lane, tw);
     float re[8], im[8], nyq = 0.0f;  // bins k = lane + 32 u
+    if (MODE != 2) {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int k = lane + 32 * u;
-      const float2 x0 = buf[phys(k)];
-      float2 t = buf[phys(k + 256)];
-      const float2 cs = rad2_s[k];
-      rot<false>(t, cs.x, cs.y);
-      re[u] = fadd(x0.x, t.x), im[u] = fadd(x0.y, t.y);
-      if (k == 0) nyq = fsub(x0.x, t.x);
+      for (int u = 0; u < 8; ++u) {
+        const float cur = xs[r3 + 32 * u];
+        v[u] = make_float2(fmul(hist[u], wv[u]), 0.0f);
+        v[8 + u] = make_float2(fmul(wr[u], cur), 0.0f);
+        hist[u] = cur;
+      }
+      fft512_tail<false>(v, buf, lane, tw);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = lane + 32 * u;
+        const float2 x0 = buf[phys(k)];
+        float2 t = buf[phys(k + 256)];
+        const float2 cs = rad2_s[k];
+        rot<false>(t, cs.x, cs.y);
+        re[u] = fadd(x0.x, t.x), im[u] = fadd(x0.y, t.y);
+        if (k == 0) nyq = fsub(x0.x, t.x);
+      }
+      __syncwarp();
     }
-    __syncwarp();
+    if (MODE == 1) {  // the reference's packed layout: Im of bin 0 is dropped, its slot carries Re of bin 256
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = lane + 32 * u;
+        sp[slot * 256 + k] = re[u];
+        sp[1024 + slot * 256 + k] = k == 0 ? nyq : im[u];
+      }
+      continue;
+    }
+    if (MODE == 2) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = lane + 32 * u;
+        re[u] = sp[slot * 256 + k];
+        im[u] = sp[1024 + slot * 256 + k];
+        if (k == 0) nyq = im[u];
+      }
+    }
     // ---- sub-band gains, one selected DRC set after the other (impd_drc_process.c:640-651, :243-385) ----
-    for (int set = 0; set < P.n_sets; ++set) {
+    for (int set = 0; MODE == 0 && set < P.n_sets; ++set) {
       const mpeghb200_drc_sb_channel ch = P.chan[size_t(set) * P.n_ch + c];
       if (ch.first_seq < 0) continue;
       const int nb = ch.band_count < 1 ? 1 : (ch.band_count > 4 ? 4 : ch.band_count);
@@ -138,8 +163,8 @@ __global__ void __launch_bounds__(32 * kDsWarps) drc_stft_kernel(const __grid_co
   }
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
-    st[r3 + 32 * u] = hist[u];
-    st[256 + r3 + 32 * u] = ohist[u];
+    if (MODE != 2) st[r3 + 32 * u] = hist[u];
+    if (MODE != 1) st[256 + r3 + 32 * u] = ohist[u];
   }
 }
 
@@ -150,14 +175,9 @@ using namespace mpeghb200;
 
 extern "C" {
 
-mpeghb200_status mpeghb200_drc_stft_dev(mpeghb200_ctx* ctx, float* d_audio, float* d_state,
-                                        const mpeghb200_drc_sb_channel* d_chan, int n_sets, const float* d_gains,
-                                        const float* d_weights, int n_channels, void* cuda_stream) {
-  if (!ctx) return MPEGHB200_ERR_BAD_ARG;
-  if (n_channels < 0 || n_sets < 0 || n_sets > 3 || (n_channels > 0 && (!d_audio || !d_state)) ||
-      (n_channels > 0 && n_sets > 0 && (!d_chan || !d_gains)))
-    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "drc_stft_dev: null buffer, negative channel count or more than 3 sets");
-  if (n_channels == 0) return MPEGHB200_OK;
+static mpeghb200_status stft_launch(mpeghb200_ctx* ctx, int mode, float* d_audio, float* d_spec, float* d_state,
+                                    const mpeghb200_drc_sb_channel* d_chan, int n_sets, const float* d_gains,
+                                    const float* d_weights, int n_channels, void* cuda_stream) {
   MB_CUDA(ctx, cudaSetDevice(ctx->device));
   static float* d_win[64] = {};
   if (ctx->device >= 64) return fail(ctx, MPEGHB200_ERR_UNSUPPORTED, "drc_stft_dev: device index above 63");
@@ -169,13 +189,41 @@ mpeghb200_status mpeghb200_drc_stft_dev(mpeghb200_ctx* ctx, float* d_audio, floa
     d_win[ctx->device] = p;
   }
   DsParams P{};
-  P.audio = d_audio, P.state = d_state, P.chan = d_chan, P.gains = d_gains, P.weights = d_weights;
+  P.audio = d_audio, P.state = d_state, P.chan = d_chan, P.gains = d_gains, P.weights = d_weights, P.spec = d_spec;
   P.win = d_win[ctx->device], P.eff8 = ctx->tables.eff8, P.rad2 = ctx->tables.rad2_512;
   P.n_ch = n_channels, P.n_sets = n_sets;
-  drc_stft_kernel<<<(n_channels + kDsWarps - 1) / kDsWarps, 32 * kDsWarps, 0, static_cast<cudaStream_t>(cuda_stream)>>>(P);
+  const dim3 grid((n_channels + kDsWarps - 1) / kDsWarps), block(32 * kDsWarps);
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (mode == 0)
+    drc_stft_kernel<0><<<grid, block, 0, st>>>(P);
+  else if (mode == 1)
+    drc_stft_kernel<1><<<grid, block, 0, st>>>(P);
+  else
+    drc_stft_kernel<2><<<grid, block, 0, st>>>(P);
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   return MPEGHB200_OK;
+}
+
+mpeghb200_status mpeghb200_drc_stft_dev(mpeghb200_ctx* ctx, float* d_audio, float* d_state,
+                                        const mpeghb200_drc_sb_channel* d_chan, int n_sets, const float* d_gains,
+                                        const float* d_weights, int n_channels, void* cuda_stream) {
+  if (!ctx) return MPEGHB200_ERR_BAD_ARG;
+  if (n_channels < 0 || n_sets < 0 || n_sets > 3 || (n_channels > 0 && (!d_audio || !d_state)) ||
+      (n_channels > 0 && n_sets > 0 && (!d_chan || !d_gains)))
+    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "drc_stft_dev: null buffer, negative channel count or more than 3 sets");
+  if (n_channels == 0) return MPEGHB200_OK;
+  return stft_launch(ctx, 0, d_audio, nullptr, d_state, d_chan, n_sets, d_gains, d_weights, n_channels, cuda_stream);
+}
+
+mpeghb200_status mpeghb200_stft_dev(mpeghb200_ctx* ctx, float* d_audio, float* d_spec, float* d_state, int to_frequency,
+                                    int n_channels, void* cuda_stream) {
+  if (!ctx) return MPEGHB200_ERR_BAD_ARG;
+  if (n_channels < 0 || (n_channels > 0 && (!d_audio || !d_spec || !d_state)))
+    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "stft_dev: null buffer or negative channel count");
+  if (n_channels == 0) return MPEGHB200_OK;
+  return stft_launch(ctx, to_frequency ? 1 : 2, d_audio, d_spec, d_state, nullptr, 0, nullptr, nullptr, n_channels,
+                     cuda_stream);
 }
 
 }  // extern "C"

@@ -260,6 +260,8 @@ class Lib:
         c.mpeghb200_gain_subband_dev.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
         c.mpeghb200_gain_subband_dev.restype = i32
         c.mpeghb200_drc_stft_dev.argtypes = [vp, vp, vp, vp, ctypes.c_int, vp, vp, ctypes.c_int, vp]
+        c.mpeghb200_stft_dev.argtypes = [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp]
+        c.mpeghb200_stft_dev.restype = i32
         c.mpeghb200_drc_stft_dev.restype = i32
         c.mpeghb200_drc_td_dev.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
         c.mpeghb200_drc_td_dev.restype = i32
@@ -489,6 +491,10 @@ class Lib:
     def drc_stft_dev(self, d_audio, d_state, d_chan, n_sets, d_gains, d_weights, n_channels, stream=0):
         self.check(self.c.mpeghb200_drc_stft_dev(self.ctx, d_audio, d_state, d_chan, n_sets, d_gains, d_weights,
                                                  n_channels, stream))
+
+    def stft_dev(self, d_audio, d_spec, d_state, to_frequency, n_channels, stream=0):
+        """One half of the domain switcher: d_audio [n][1024] <-> d_spec [n][2048] (re | im planes)."""
+        self.check(self.c.mpeghb200_stft_dev(self.ctx, d_audio, d_spec, d_state, int(to_frequency), n_channels, stream))
 
     def drc_td_dev(self, d_audio, d_state, d_chan, d_banks, d_gains, n_channels, stream=0):
         self.check(self.c.mpeghb200_drc_td_dev(self.ctx, d_audio, d_state, d_chan, d_banks, d_gains, n_channels, stream))

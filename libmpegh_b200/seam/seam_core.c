@@ -62,12 +62,13 @@ static void seam_stats(void)
             "hoa_render gpu=%lu host=%lu resample gpu=%lu hoa_spatial gpu=%lu host=%lu "
             "binaural_blocks gpu=%lu host(calls)=%lu "
             "stereo_tools gpu=%lu host=%lu igf mono=%lu tnf=%lu stereo=%lu host=%lu "
-            "drc_channels subband=%lu time_domain=%lu host(calls)=%lu\n",
+            "drc_channels subband=%lu time_domain=%lu host(calls)=%lu stft=%lu\n",
             seam_n.fd_gpu, seam_n.fd_host, seam_n.tns, seam_n.lim, seam_n.ltpf, seam_n.fc, seam_n.mct,
             g_ctx ? (unsigned long long)mpeghb200_launch_count(g_ctx) : 0ull, seam_n.obj, seam_n.obj_host, seam_n.pcm,
             seam_n.batch_calls, seam_n.batches, seam_n.max_batch, seam_n.hoa_ren, seam_n.hoa_ren_host, seam_n.resample, seam_n.hoa_spatial,
             seam_n.hoa_spatial_host, seam_n.binaural, seam_n.binaural_host, seam_n.stereo, seam_n.stereo_host, seam_n.igf,
-            seam_n.igf_tnf, seam_n.igf_stereo, seam_n.igf_host, seam_n.drc_sb, seam_n.drc_td, seam_n.drc_host);
+            seam_n.igf_tnf, seam_n.igf_stereo, seam_n.igf_host, seam_n.drc_sb, seam_n.drc_td, seam_n.drc_host,
+            seam_n.drc_stft);
   if (getenv("MPEGHB200_SEAM_STATS") && g_t_parse > 0.0)
   {
     int k;

@@ -38,6 +38,7 @@ typedef enum
   RQ_STEREO,   /* impeghd_ms_stereo, ia_core_coder_cplx_pred_upmixing */
   RQ_IGF,      /* ia_core_coder_igf_mono (+ its TNF step), ia_core_coder_igf_tnf */
   RQ_IGFST,    /* ia_core_coder_igf_apply_stereo */
+  RQ_DS,       /* impeghd_domain_switcher_process (time <-> STFT256 around sub-band DRC) */
   RQ_DRCSB,    /* impd_drc_apply_gains_subband */
   RQ_DRCTD,    /* impd_drc_filter_banks_process + impd_drc_apply_gains_and_add */
   RQ_KINDS
@@ -61,7 +62,7 @@ void seam_inline_unlock(void);
 typedef struct
 {
   unsigned long fd_gpu, fd_host, tns, lim, ltpf, fc, mct, obj, obj_host, pcm, batches, batch_calls, max_batch, hoa_ren,
-      hoa_ren_host, resample, hoa_spatial, hoa_spatial_host, binaural, binaural_host, stereo, stereo_host, igf, igf_tnf, igf_stereo, igf_host, drc_sb, drc_td, drc_host;
+      hoa_ren_host, resample, hoa_spatial, hoa_spatial_host, binaural, binaural_host, stereo, stereo_host, igf, igf_tnf, igf_stereo, igf_host, drc_sb, drc_td, drc_host, drc_stft;
 } seam_counters;
 extern seam_counters seam_n;
 

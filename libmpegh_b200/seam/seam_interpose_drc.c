@@ -1,5 +1,6 @@
 /* seam_interpose_drc.c -- libmpeghgpu.so: application of the decoded DRC gains.
  *
+ *   impeghd_domain_switcher_process decoder/ia_core_coder_process.c:505 -> mpeghb200_stft_dev        (time <-> STFT256)
  *   impd_drc_apply_gains_subband    decoder/impd_drc_process.c:243   -> mpeghb200_gain_subband_dev   (STFT256 domain)
  *   impd_drc_filter_banks_process   decoder/impd_drc_process.c:399  \
  *   impd_drc_apply_gains_and_add    decoder/impd_drc_process.c:68   /  -> mpeghb200_drc_td_dev         (time domain)
@@ -441,8 +442,104 @@ VOID impd_drc_apply_gains_and_add(ia_drc_gain_dec_struct *pstr_drc_gain_dec, FLO
   seam_submit(&r);
 }
 
+/* ---- the domain switcher around sub-band DRC (impeghd_domain_switcher_process, ia_core_coder_process.c:505) ------- */
+/* p[0] = ia_usac_data_struct, p[1] = ia_ds_state_struct; v[0] = n_ch, v[1] = ds_t2f */
+static seam_buf b_ds_x, b_ds_spec, b_ds_state;
+
+static void ds_group(seam_req **rq, int n, int t2f)
+{
+  mpeghb200_ctx *ctx = seam_ctx();
+  int N = 0, i, c, c0;
+  for (i = 0; i < n; i++)
+    N += (int)rq[i]->v[0];
+  seam_need(&b_ds_x, (size_t)N * FRAME * sizeof(float)), seam_need(&b_ds_spec, (size_t)N * 2 * FRAME * sizeof(float));
+  seam_need(&b_ds_state, (size_t)N * 512 * sizeof(float));
+  for (i = 0, c0 = 0; i < n; c0 += (int)rq[i]->v[0], i++)
+  {
+    ia_usac_data_struct *u = (ia_usac_data_struct *)rq[i]->p[0];
+    const ia_ds_state_struct *ds = (const ia_ds_state_struct *)rq[i]->p[1];
+    for (c = 0; c < (int)rq[i]->v[0]; c++)
+    {
+      float *st = (float *)b_ds_state.h + (size_t)(c0 + c) * 512;
+      memcpy(st, ds->stft_in_buf[c], 256 * sizeof(float)), memcpy(st + 256, ds->stft_out_buf[c], 256 * sizeof(float));
+      if (t2f)
+        memcpy((float *)b_ds_x.h + (size_t)(c0 + c) * FRAME, u->time_sample_vector[c], FRAME * sizeof(float));
+      else
+        memcpy((float *)b_ds_spec.h + (size_t)(c0 + c) * 2 * FRAME, u->time_sample_stft[c], 2 * FRAME * sizeof(float));
+    }
+  }
+  if (t2f)
+    CK(mpeghb200_h2d(ctx, b_ds_x.d, b_ds_x.h, (size_t)N * FRAME * sizeof(float)));
+  else
+    CK(mpeghb200_h2d(ctx, b_ds_spec.d, b_ds_spec.h, (size_t)N * 2 * FRAME * sizeof(float)));
+  CK(mpeghb200_h2d(ctx, b_ds_state.d, b_ds_state.h, (size_t)N * 512 * sizeof(float)));
+  CK(mpeghb200_stft_dev(ctx, (float *)b_ds_x.d, (float *)b_ds_spec.d, (float *)b_ds_state.d, t2f, N, NULL));
+  if (t2f)
+    CK(mpeghb200_d2h(ctx, b_ds_spec.h, b_ds_spec.d, (size_t)N * 2 * FRAME * sizeof(float)));
+  else
+    CK(mpeghb200_d2h(ctx, b_ds_x.h, b_ds_x.d, (size_t)N * FRAME * sizeof(float)));
+  CK(mpeghb200_d2h(ctx, b_ds_state.h, b_ds_state.d, (size_t)N * 512 * sizeof(float)));
+  for (i = 0, c0 = 0; i < n; c0 += (int)rq[i]->v[0], i++)
+  {
+    ia_usac_data_struct *u = (ia_usac_data_struct *)rq[i]->p[0];
+    ia_ds_state_struct *ds = (ia_ds_state_struct *)rq[i]->p[1];
+    for (c = 0; c < (int)rq[i]->v[0]; c++)
+    {
+      const float *st = (const float *)b_ds_state.h + (size_t)(c0 + c) * 512;
+      if (t2f)
+      {
+        memcpy(ds->stft_in_buf[c], st, 256 * sizeof(float));
+        memcpy(u->time_sample_stft[c], (float *)b_ds_spec.h + (size_t)(c0 + c) * 2 * FRAME, 2 * FRAME * sizeof(float));
+      }
+      else
+      {
+        memcpy(ds->stft_out_buf[c], st + 256, 256 * sizeof(float));
+        memcpy(u->time_sample_vector[c], (float *)b_ds_x.h + (size_t)(c0 + c) * FRAME, FRAME * sizeof(float));
+      }
+    }
+  }
+  seam_n.drc_stft += (unsigned long)N;
+}
+
+static void be_ds(seam_req **rq, int n)
+{
+  int a = 0, b;
+  while (a < n)
+  {
+    for (b = a + 1; b < n && rq[b]->v[1] == rq[a]->v[1]; b++)
+      ;
+    ds_group(rq + a, b - a, (int)rq[a]->v[1]);
+    a = b;
+  }
+}
+
+IA_ERRORCODE impeghd_domain_switcher_process(ia_mpegh_dec_api_struct *p_obj_mpegh_dec, WORD32 *num_chn_out, UWORD32 ds_t2f,
+                                             FLOAT32 *scratch_buf)
+{
+  ia_mpegh_dec_state_struct *state = p_obj_mpegh_dec->p_state_mpeghd;
+  ia_dec_data_struct *dec = (ia_dec_data_struct *)state->pstr_dec_data;
+  ia_ds_state_struct *ds = &state->state_domain_switcher;
+  seam_req r;
+  int n_ch;
+  (void)scratch_buf;
+  if (ds->ds_params == NULL)
+    return IA_MPEGH_DEC_EXE_FATAL_DOMAIN_SWITCHER_PROCESS_FAILED;
+  *num_chn_out = ds->ds_params->num_out_ch;
+  n_ch = ds_t2f ? ds->ds_params->num_in_ch : ds->ds_params->num_out_ch;
+  if (n_ch > 0)
+  {
+    r.kind = RQ_DS;
+    r.p[0] = &dec->str_usac_data, r.p[1] = ds;
+    r.v[0] = n_ch, r.v[1] = ds_t2f != 0;
+    seam_submit(&r);
+  }
+  state->ui_out_bytes = 1024 * *num_chn_out * sizeof(FLOAT32); /* :622 */
+  return IA_MPEGH_DEC_NO_ERROR;
+}
+
 __attribute__((constructor)) static void seam_register_drc(void)
 {
+  seam_register(RQ_DS, be_ds, "domain_switcher");
   seam_register(RQ_DRCSB, be_drc_sb, "drc_apply_gains_subband");
   seam_register(RQ_DRCTD, be_drc_td, "drc filter banks + gains");
 }

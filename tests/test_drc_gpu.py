@@ -97,6 +97,41 @@ def test_fused_stft_chain(gpu_lib, oracle, n_ch, n_frames, seed):
         assert bits_equal(d_x.cpu().numpy(), want[f]), f
 
 
+@pytest.mark.parametrize("n_ch,seed", [(1, 3), (7, 4), (24 * 16, 5)])
+def test_stft_halves(gpu_lib, oracle, n_ch, seed):
+    """mpeghb200_stft_dev: the two halves of the domain switcher as separate launches (what the drop-in library uses
+    around the interposed gain application) against the oracle's t2f / f2t (pinned to impeghd_domain_switcher_process by
+    tests/test_oracle_drc.py), three frames with the carried input slot and output overlap."""
+    import torch
+    from oracle import loader
+    win = np.ascontiguousarray(loader.golden_rom()["sine_256"], np.float32)
+    rng = np.random.default_rng(seed)
+    ih, oh = np.zeros((n_ch, 256), np.float32), np.zeros((n_ch, 256), np.float32)
+    st = torch.cuda.current_stream().cuda_stream
+    d_state = torch.zeros(n_ch * 512, device="cuda")
+    for f in range(3):
+        x = (rng.standard_normal((n_ch, 1024)) * 3000).astype(np.float32)
+        re, im = np.zeros((n_ch, 1024), np.float32), np.zeros((n_ch, 1024), np.float32)
+        oracle.oracle_ds_t2f(win, ih.reshape(-1), x.reshape(-1), re.reshape(-1), im.reshape(-1), n_ch)
+        d_x = torch.from_numpy(x.copy()).cuda()
+        d_spec = torch.full((n_ch, 2048), float("nan"), device="cuda")
+        gpu_lib.stft_dev(d_x.data_ptr(), d_spec.data_ptr(), d_state.data_ptr(), True, n_ch, st)
+        torch.cuda.synchronize()
+        spec = d_spec.cpu().numpy()
+        assert bits_equal(spec[:, :1024], re) and bits_equal(spec[:, 1024:], im), f
+        # a gain per bin in between, like the DRC step, so that the way back does not just undo the way there
+        g = (rng.random((n_ch, 2048)) + 0.5).astype(np.float32)
+        spec2 = (spec * g).astype(np.float32)
+        y = np.zeros((n_ch, 1024), np.float32)
+        oracle.oracle_ds_f2t(win, oh.reshape(-1), np.ascontiguousarray(spec2[:, :1024]).reshape(-1),
+                             np.ascontiguousarray(spec2[:, 1024:]).reshape(-1), y.reshape(-1), n_ch)
+        d_spec2 = torch.from_numpy(spec2).cuda()
+        d_y = torch.full((n_ch, 1024), float("nan"), device="cuda")
+        gpu_lib.stft_dev(d_y.data_ptr(), d_spec2.data_ptr(), d_state.data_ptr(), False, n_ch, st)
+        torch.cuda.synchronize()
+        assert bits_equal(d_y.cpu().numpy(), y), f
+
+
 def run_td_gpu(gpu_lib, setups_frames):
     """several independent streams (setup, frames) in one launch per frame index; -> list of [n_frames][n_ch][1024]"""
     import torch

@@ -566,6 +566,16 @@ if mode == "subband":
         pad[0, :fr["n_ch"]], pad[1, :fr["n_ch"]] = re, im
         outs.append(pad)
         n_channels += fr["n_ch"]
+elif mode == "stft_chain":
+    ref = loader.load_ref()
+    for seed in range(4):
+        rng = np.random.default_rng(800 + seed)
+        n_ch = int(rng.integers(1, 13))
+        y = drc_cases.stft_chain(None, None, rng, 3, n_ch, ref=ref)   # t2f -> gains of 1..2 sets -> f2t, 3 frames
+        pad = np.zeros((3, 12, 1024), np.float32)
+        pad[:, :n_ch] = y
+        outs.append(pad)
+        n_channels += 3 * n_ch
 else:
     # the interposers look the reference's own functions up behind themselves (see RS_SCRIPT)
     import ctypes
@@ -586,18 +596,20 @@ print("CHANNELS", n_channels)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["subband", "td_ns", "td_host"])
+@pytest.mark.parametrize("mode", ["subband", "stft_chain", "td_ns", "td_host"])
 def test_seam_drc(tmp_path, mode):
     """Application of the DRC gains through the unmodified reference functions (oracle/ref_harness_drc.c,
     ref_harness_ns.c fill ia_drc_gain_dec_struct / ia_drc_instructions_struct the way the gain decoder leaves them):
-    impd_drc_apply_gains_subband (STFT256 domain: single- and multi-band groups, channels without a group, both delay
+    the chain of ia_core_coder_decode_main.c:2128-2141 -- impeghd_domain_switcher_process time -> STFT256, the gains of
+    one or two selected sets, impeghd_domain_switcher_process back, three frames with the carried input slot and output
+    overlap ("stft_chain"); impd_drc_apply_gains_subband (STFT256 domain: single- and multi-band groups, channels without a group, both delay
     modes, gain delays) with the stock library; impd_drc_filter_banks_process + impd_drc_apply_gains_and_add (time domain:
     2 / 3 / 4-band Linkwitz-Riley banks, phase-alignment cascades, three frames with carried filter memories) with the
     reference build that exports the second, `static`, function; against the stock library that pair is forwarded
     to the reference, which "td_host" forces (MPEGHB200_SEAM_DRC_TD_HOST=1) to cover the forwarding path."""
     libref = os.path.join(REF_DIR, "libmpeghref.so")
     _need(libref, SEAM)
-    if mode != "subband":
+    if mode in ("td_ns", "td_host"):
         _need(os.path.join(REF_DIR, "libmpeghref_ns.so"))
     script = tmp_path / "h.py"
     script.write_text(DRC_SCRIPT)
@@ -614,15 +626,17 @@ def test_seam_drc(tmp_path, mode):
         assert r.returncode == 0, r.stderr[-800:]
         n_channels = int(re.search(r"CHANNELS (\d+)", r.stdout).group(1))
         if preload:
-            m = re.search(r"drc_channels subband=(\d+) time_domain=(\d+) host\(calls\)=(\d+)", r.stderr)
+            m = re.search(r"drc_channels subband=(\d+) time_domain=(\d+) host\(calls\)=(\d+) stft=(\d+)", r.stderr)
             if mode == "td_host" and not m:  # nothing reached the GPU, so no context and no statistics line
                 outs.append(np.load(out))
                 continue
             assert m, r.stderr[-400:]
-            sb, td, host = (int(x) for x in m.groups())
-            print(mode, dict(subband=sb, time_domain=td, host=host, channels=n_channels))
+            sb, td, host, stft = (int(x) for x in m.groups())
+            print(mode, dict(subband=sb, time_domain=td, host=host, stft=stft, channels=n_channels))
             if mode == "subband":
                 assert sb == n_channels and td == 0 and host == 0
+            elif mode == "stft_chain":  # both halves of the domain switcher per channel-frame, gains of 1..2 sets
+                assert stft == 2 * n_channels and n_channels <= sb <= 2 * n_channels and host == 0
             elif mode == "td_ns":
                 assert td == n_channels and host == 0
             else:
