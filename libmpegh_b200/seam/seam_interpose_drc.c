@@ -2,8 +2,9 @@
  *
  *   impeghd_domain_switcher_process decoder/ia_core_coder_process.c:505 -> mpeghb200_stft_dev        (time <-> STFT256)
  *   impd_drc_apply_gains_subband    decoder/impd_drc_process.c:243   -> mpeghb200_gain_subband_dev   (STFT256 domain)
+ *   impd_drc_td_process             decoder/impd_drc_process.c:529   -> mpeghb200_drc_td_dev         (time domain, the whole step)
  *   impd_drc_filter_banks_process   decoder/impd_drc_process.c:399  \
- *   impd_drc_apply_gains_and_add    decoder/impd_drc_process.c:68   /  -> mpeghb200_drc_td_dev         (time domain)
+ *   impd_drc_apply_gains_and_add    decoder/impd_drc_process.c:68   /  -> the same, for callers of the two halves
  *
  * Gain decoding, DRC set selection and the interpolation into per-sample gain curves (impd_drc_get_gain and below: libm
  * splines) stay in the reference; these interposers read the finished curves out of ia_drc_gain_buffer_struct the way
@@ -12,11 +13,13 @@
  * ia_drc_overlap_params_struct and the filter-bank coefficients out of ia_filter_banks_struct.
  *
  * Time domain: the reference splits a frame into band signals (filter_banks_process) and then multiplies and sums them
- * (apply_gains_and_add); the kernel does both at once, so the first call only records its arguments and the second one
- * files the request.  impd_drc_apply_gains_and_add is `static` in the reference: this pair is taken over only when the
- * reference library in use exports it (the build oracle/Makefile makes with -Dstatic= on the one file); against the stock
- * library both calls are forwarded and time-domain DRC stays in the reference.  The filter memories then live on the
- * device, one slot per (ia_drc_gain_dec_struct, selected set).
+ * (apply_gains_and_add); the kernel does both at once.  impd_drc_td_process, the function the decoder calls, is taken
+ * over as a whole: the reference's impd_drc_get_gain for every selected set, then one request per set -- this works
+ * against the stock reference library.  The two halves are interposed as well for callers that use them directly: the
+ * first call only records its arguments, the second one files the request; impd_drc_apply_gains_and_add is `static` in
+ * the reference, so that pair is reachable only when the reference library in use exports it (the build oracle/Makefile
+ * makes with -Dstatic= on the one file) and is forwarded otherwise.  The filter memories live on the device, one slot
+ * per (ia_drc_gain_dec_struct, selected set).
  */
 #define _GNU_SOURCE
 #include <stdlib.h>
@@ -353,17 +356,19 @@ static __thread FLOAT32 **tl_audio;
 static __thread const ia_drc_gain_dec_struct *tl_dec;
 static __thread int tl_sel = -1;
 
-static int td_on_gpu(const ia_drc_instructions_struct *arr, const ia_drc_gain_dec_struct *dec, int sel)
+/* a selected set the kernel covers: a positive set id, at most 8 channel groups of 1 .. 4 bands, and only the multi-band
+ * set may split (the others are gain-only, :417-424) */
+static int td_shape_ok(const ia_drc_instructions_struct *arr, const ia_drc_gain_dec_struct *dec, int sel, int n_ch)
 {
   const ia_drc_params_struct *p = &dec->ia_drc_params_struct;
   const int ii = p->sel_drc_array[sel].drc_instrns_idx;
   const ia_drc_instructions_struct *ins;
   int g;
-  if (!td_enabled() || ii < 0 || p->drc_frame_size != FRAME || p->num_ch_process < 1 || p->num_ch_process > MAX_CHANNEL_COUNT)
+  if (ii < 0 || p->drc_frame_size != FRAME || n_ch < 1 || n_ch > MAX_CHANNEL_COUNT)
     return 0;
   ins = &arr[ii];
   if (ins->drc_set_id <= 0 || ins->num_drc_ch_groups < 0 || ins->num_drc_ch_groups > 8 ||
-      ins->audio_num_chan < p->channel_offset + p->num_ch_process)
+      ins->audio_num_chan < p->channel_offset + n_ch)
     return 0;
   for (g = 0; g < ins->num_drc_ch_groups; g++)
   {
@@ -372,6 +377,46 @@ static int td_on_gpu(const ia_drc_instructions_struct *arr, const ia_drc_gain_de
       return 0;
   }
   return 1;
+}
+static int td_on_gpu(const ia_drc_instructions_struct *arr, const ia_drc_gain_dec_struct *dec, int sel)
+{
+  return td_enabled() && td_shape_ok(arr, dec, sel, dec->ia_drc_params_struct.num_ch_process);
+}
+
+/* the request of one selected set: channel records, banks, gain curves */
+static void td_build(td_job *j, ia_drc_gain_dec_struct *dec, ia_drc_instructions_struct *arr, int sel, FLOAT32 **audio)
+{
+  const ia_drc_params_struct *p = &dec->ia_drc_params_struct;
+  const ia_drc_gain_buffer_struct *gb = &dec->drc_gain_buffers.pstr_gain_buf[sel];
+  const ia_drc_instructions_struct *ins = &arr[p->sel_drc_array[sel].drc_instrns_idx];
+  const int pass = p->multiband_sel_drc_idx != sel, off = gain_offset(p);
+  int first[8], g, b, c;
+  memset(j, 0, sizeof(*j));
+  j->n_ch = p->num_ch_process, j->audio = audio;
+  j->key = (const char *)dec + sel;
+  for (g = 0; g < ins->num_drc_ch_groups; g++)
+  {
+    const int nb = ins->band_count_of_ch_group[g];
+    first[g] = j->n_seq;
+    for (b = 0; b < nb; b++)
+      j->gain[j->n_seq++] = gb->pstr_buf_interp[first[g] + b].lpcm_gains + off;
+    if (pass) /* a set that is not the multi-band one: no split, no phase alignment (:417-424) */
+      j->bank[g].n_bands = 1;
+    else
+      bank_of(&j->bank[g], &dec->ia_filter_banks_struct.str_drc_filter_bank[g], nb);
+  }
+  g = ins->num_drc_ch_groups; /* the bank of the channels outside every group: its cascade only (:452-457) */
+  if (pass)
+    j->bank[g].n_bands = 1;
+  else
+    bank_of(&j->bank[g], &dec->ia_filter_banks_struct.str_drc_filter_bank[g], 1);
+  j->n_banks = g + 1;
+  for (c = 0; c < j->n_ch; c++)
+  {
+    g = ins->channel_group_of_ch[p->channel_offset + c];
+    j->chan[c].bank = g >= 0 ? g : ins->num_drc_ch_groups;
+    j->chan[c].first_seq = g >= 0 ? first[g] : -1;
+  }
 }
 
 IA_ERRORCODE impd_drc_filter_banks_process(FLOAT32 *audio_io_buf[], ia_drc_instructions_struct *pstr_drc_instruction_arr,
@@ -395,11 +440,6 @@ VOID impd_drc_apply_gains_and_add(ia_drc_gain_dec_struct *pstr_drc_gain_dec, FLO
                                   ia_drc_instructions_struct *pstr_drc_instruction_arr, WORD32 impd_apply_gains,
                                   WORD32 sel_drc_idx)
 {
-  const ia_drc_params_struct *p = &pstr_drc_gain_dec->ia_drc_params_struct;
-  const ia_drc_gain_buffer_struct *gb = &pstr_drc_gain_dec->drc_gain_buffers.pstr_gain_buf[sel_drc_idx];
-  const ia_drc_instructions_struct *ins;
-  const int pass = p->multiband_sel_drc_idx != sel_drc_idx;
-  int first[8], g, b, c, off;
   td_job j;
   seam_req r;
   if (tl_sel != sel_drc_idx || tl_dec != pstr_drc_gain_dec || impd_apply_gains != 1 || tl_audio != channel_audio)
@@ -409,37 +449,69 @@ VOID impd_drc_apply_gains_and_add(ia_drc_gain_dec_struct *pstr_drc_gain_dec, FLO
     return;
   }
   tl_sel = -1;
-  ins = &pstr_drc_instruction_arr[p->sel_drc_array[sel_drc_idx].drc_instrns_idx];
-  off = gain_offset(p);
-  memset(&j, 0, sizeof(j));
-  j.n_ch = p->num_ch_process, j.audio = channel_audio;
-  j.key = (const char *)pstr_drc_gain_dec + sel_drc_idx;
-  for (g = 0; g < ins->num_drc_ch_groups; g++)
-  {
-    const int nb = ins->band_count_of_ch_group[g];
-    first[g] = j.n_seq;
-    for (b = 0; b < nb; b++)
-      j.gain[j.n_seq++] = gb->pstr_buf_interp[first[g] + b].lpcm_gains + off;
-    if (pass) /* a set that is not the multi-band one: no split, no phase alignment (:417-424) */
-      memset(&j.bank[g], 0, sizeof(j.bank[g])), j.bank[g].n_bands = 1;
-    else
-      bank_of(&j.bank[g], &pstr_drc_gain_dec->ia_filter_banks_struct.str_drc_filter_bank[g], nb);
-  }
-  g = ins->num_drc_ch_groups; /* the bank of the channels outside every group: its cascade only (:452-457) */
-  if (pass)
-    memset(&j.bank[g], 0, sizeof(j.bank[g])), j.bank[g].n_bands = 1;
-  else
-    bank_of(&j.bank[g], &pstr_drc_gain_dec->ia_filter_banks_struct.str_drc_filter_bank[g], 1);
-  j.n_banks = g + 1;
-  for (c = 0; c < j.n_ch; c++)
-  {
-    g = ins->channel_group_of_ch[p->channel_offset + c];
-    j.chan[c].bank = g >= 0 ? g : ins->num_drc_ch_groups;
-    j.chan[c].first_seq = g >= 0 ? first[g] : -1;
-  }
+  td_build(&j, pstr_drc_gain_dec, pstr_drc_instruction_arr, sel_drc_idx, channel_audio);
   r.kind = RQ_DRCTD;
   r.p[0] = &j;
   seam_submit(&r);
+}
+
+/* The whole time-domain step (decoder/impd_drc_process.c:529): the reference's own gain decoding for every selected set
+ * (impd_drc_get_gain: exported, stays reference code), then banks + gains + band sum of every set on the GPU.  This is
+ * the form that works against the stock reference library, where impd_drc_apply_gains_and_add cannot be reached. */
+IA_ERRORCODE impd_drc_td_process(FLOAT32 *audio_in_out_buf[], ia_drc_gain_dec_struct *pstr_drc_gain_dec,
+                                 ia_drc_config *pstr_drc_config, ia_drc_gain_struct *pstr_drc_gain, FLOAT32 ln_gain_db,
+                                 FLOAT32 boost_fac, FLOAT32 compress_fac, WORD32 drc_characteristic_target)
+{
+  typedef IA_ERRORCODE (*td_fn)(FLOAT32 **, ia_drc_gain_dec_struct *, ia_drc_config *, ia_drc_gain_struct *, FLOAT32, FLOAT32,
+                                FLOAT32, WORD32);
+  typedef IA_ERRORCODE (*gain_fn)(ia_drc_gain_buffers_struct *, ia_drc_gain_dec_struct *, ia_drc_config *,
+                                  ia_drc_gain_struct *, FLOAT32, FLOAT32, WORD32, FLOAT32, WORD32);
+  static gain_fn get_gain;
+  ia_drc_instructions_struct *arr = pstr_drc_config->str_drc_instruction_str;
+  ia_drc_params_struct *p = &pstr_drc_gain_dec->ia_drc_params_struct;
+  int sel, ok = !getenv("MPEGHB200_SEAM_DRC_TD_HOST"), npc = p->num_ch_process;
+  IA_ERRORCODE err;
+  if (!pstr_drc_config->apply_drc)
+    return IA_MPEGH_DEC_NO_ERROR;
+  for (sel = p->drc_set_counter - 1; ok && sel >= 0; sel--)
+  { /* every selected set must be one the kernel covers, with the channel count the reference would arrive at (:562-573) */
+    const int ii = p->sel_drc_array[sel].drc_instrns_idx;
+    if (ii < 0)
+      ok = 0;
+    else
+    {
+      if (npc == -1)
+        npc = arr[ii].audio_num_chan;
+      ok = arr[ii].audio_num_chan >= p->channel_offset + npc && td_shape_ok(arr, pstr_drc_gain_dec, sel, npc);
+    }
+  }
+  if (!ok)
+  {
+    static td_fn real;
+    if (!real)
+      real = (td_fn)seam_real("impd_drc_td_process");
+    seam_n.drc_host++;
+    return real(audio_in_out_buf, pstr_drc_gain_dec, pstr_drc_config, pstr_drc_gain, ln_gain_db, boost_fac, compress_fac,
+                drc_characteristic_target);
+  }
+  if (!get_gain)
+    get_gain = (gain_fn)seam_real("impd_drc_get_gain");
+  for (sel = p->drc_set_counter - 1; sel >= 0; sel--)
+    if ((err = get_gain(&pstr_drc_gain_dec->drc_gain_buffers, pstr_drc_gain_dec, pstr_drc_config, pstr_drc_gain, compress_fac,
+                        boost_fac, drc_characteristic_target, ln_gain_db, sel)) != IA_MPEGH_DEC_NO_ERROR)
+      return err;
+  for (sel = p->drc_set_counter - 1; sel >= 0; sel--)
+  {
+    td_job j;
+    seam_req r;
+    if (p->num_ch_process == -1)
+      p->num_ch_process = arr[p->sel_drc_array[sel].drc_instrns_idx].audio_num_chan;
+    td_build(&j, pstr_drc_gain_dec, arr, sel, audio_in_out_buf);
+    r.kind = RQ_DRCTD;
+    r.p[0] = &j;
+    seam_submit(&r);
+  }
+  return IA_MPEGH_DEC_NO_ERROR;
 }
 
 /* ---- the domain switcher around sub-band DRC (impeghd_domain_switcher_process, ia_core_coder_process.c:505) ------- */

@@ -245,6 +245,12 @@ def _bind_harnesses(lib):
     lib.ref_drc_gains_subband.argtypes = [_f32p, _f32p, ctypes.c_int, _i32p, _i32p, ctypes.c_int, _f32p, _f32p] + \
         [ctypes.c_int] * 5
     lib.ref_drc_gains_subband.restype = ctypes.c_int
+    lib.ref_drctd_whole_create.restype = ctypes.c_void_p
+    lib.ref_drctd_whole_create.argtypes = [ctypes.c_int, np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS"),
+                                           ctypes.c_int, ctypes.c_void_p]
+    lib.ref_drctd_whole_destroy.argtypes = [ctypes.c_void_p]
+    lib.ref_drctd_whole_process.argtypes = [ctypes.c_void_p, _f32p, _f32p]
+    lib.ref_drctd_whole_process.restype = ctypes.c_int
     lib.ref_ds_create.restype = ctypes.c_void_p
     lib.ref_ds_create.argtypes = [ctypes.c_int]
     lib.ref_ds_destroy.argtypes = [ctypes.c_void_p]

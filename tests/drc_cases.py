@@ -138,3 +138,15 @@ def td_reference(ref_ns, setup, frames):
         outs.append(y)
     ref_ns.ref_drctd_destroy(h)
     return np.stack(outs)
+
+
+def td_reference_whole(ref, setup, frames):
+    """the same through impd_drc_td_process (gain-buffer bookkeeping of impd_drc_get_gain included); stock library"""
+    h = ref.ref_drctd_whole_create(setup["n_ch"], setup["group_of_ch"], setup["n_groups"], setup["banks"].ctypes.data)
+    outs = []
+    for x, gains in frames:
+        y = x.copy()
+        assert ref.ref_drctd_whole_process(h, y.reshape(-1), np.ascontiguousarray(gains).reshape(-1)) == 0
+        outs.append(y)
+    ref.ref_drctd_whole_destroy(h)
+    return np.stack(outs)

@@ -93,6 +93,20 @@ def test_td_multiband_matches_reference(seed):
     assert loader.bits_equal(drc_cases.td_oracle(o, setup, frames), drc_cases.td_reference(r, setup, frames))
 
 
+@pytest.mark.parametrize("seed", range(4))
+def test_td_whole_process_matches_oracle(seed):
+    """the same through impd_drc_td_process of the STOCK build (oracle/ref_harness_drc.c: impd_drc_get_gain's buffer
+    bookkeeping in front, no spline nodes): what the drop-in's whole-step interposer is tested against."""
+    r = loader.load_ref()
+    if r is None:
+        pytest.skip("reference build not available")
+    o = loader.load_oracle()
+    rng = np.random.default_rng(160 + seed)
+    setup = drc_cases.random_td_frame_setup(rng)
+    frames = drc_cases.td_frames(rng, setup, 3)
+    assert loader.bits_equal(drc_cases.td_oracle(o, setup, frames), drc_cases.td_reference_whole(r, setup, frames))
+
+
 def test_td_multiband_matches_golden():
     o = loader.load_oracle()
     g = np.load(GOLD)

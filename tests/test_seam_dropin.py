@@ -576,6 +576,20 @@ elif mode == "stft_chain":
         pad[:, :n_ch] = y
         outs.append(pad)
         n_channels += 3 * n_ch
+elif mode == "td_whole":
+    # impd_drc_td_process as the decoder calls it, STOCK library; the interposer calls the reference's impd_drc_get_gain
+    import ctypes
+    ctypes.CDLL(os.path.join(sys.argv[1], "oracle", "_ref", "libmpeghref.so"), mode=ctypes.RTLD_GLOBAL)
+    ref = loader.load_ref()
+    for seed in range(8):
+        rng = np.random.default_rng(700 + seed)
+        setup = drc_cases.random_td_frame_setup(rng)
+        frames = drc_cases.td_frames(rng, setup, 3)
+        y = drc_cases.td_reference_whole(ref, setup, frames)
+        pad = np.zeros((3, 12, 1024), np.float32)
+        pad[:, :setup["n_ch"]] = y
+        outs.append(pad)
+        n_channels += 3 * setup["n_ch"]
 else:
     # the interposers look the reference's own functions up behind themselves (see RS_SCRIPT)
     import ctypes
@@ -596,13 +610,14 @@ print("CHANNELS", n_channels)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["subband", "stft_chain", "td_ns", "td_host"])
+@pytest.mark.parametrize("mode", ["subband", "stft_chain", "td_whole", "td_ns", "td_host"])
 def test_seam_drc(tmp_path, mode):
     """Application of the DRC gains through the unmodified reference functions (oracle/ref_harness_drc.c,
     ref_harness_ns.c fill ia_drc_gain_dec_struct / ia_drc_instructions_struct the way the gain decoder leaves them):
     the chain of ia_core_coder_decode_main.c:2128-2141 -- impeghd_domain_switcher_process time -> STFT256, the gains of
     one or two selected sets, impeghd_domain_switcher_process back, three frames with the carried input slot and output
-    overlap ("stft_chain"); impd_drc_apply_gains_subband (STFT256 domain: single- and multi-band groups, channels without a group, both delay
+    overlap ("stft_chain"); impd_drc_td_process as the decoder calls it, with the STOCK library ("td_whole": 2 / 3 / 4-band
+    banks, phase-alignment cascades, three frames, the reference's own impd_drc_get_gain in front); impd_drc_apply_gains_subband (STFT256 domain: single- and multi-band groups, channels without a group, both delay
     modes, gain delays) with the stock library; impd_drc_filter_banks_process + impd_drc_apply_gains_and_add (time domain:
     2 / 3 / 4-band Linkwitz-Riley banks, phase-alignment cascades, three frames with carried filter memories) with the
     reference build that exports the second, `static`, function; against the stock library that pair is forwarded
@@ -637,7 +652,7 @@ def test_seam_drc(tmp_path, mode):
                 assert sb == n_channels and td == 0 and host == 0
             elif mode == "stft_chain":  # both halves of the domain switcher per channel-frame, gains of 1..2 sets
                 assert stft == 2 * n_channels and n_channels <= sb <= 2 * n_channels and host == 0
-            elif mode == "td_ns":
+            elif mode in ("td_ns", "td_whole"):
                 assert td == n_channels and host == 0
             else:
                 assert td == 0 and host > 0  # the pair stays in the reference
