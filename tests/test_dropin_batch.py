@@ -141,3 +141,38 @@ def test_handle_at_a_time_equals_batch(tmp_path):
         assert r.returncode == 0, r.stderr[-800:]
         out.append(json.loads(r.stdout.strip().splitlines()[-1]))
     assert [x["fnv1a64"] for x in out[0]["streams"]] == [x["fnv1a64"] for x in out[1]["streams"]]
+
+
+@pytest.mark.gpu
+def test_batch_with_a_truncated_stream(tmp_path):
+    """Handles of one batch end at different times and one of them ends on a damaged frame: a copy of the 6-channel stream
+    cut in the middle of a frame decodes next to full streams.  The full streams stay byte-identical to the reference
+    decoder; the truncated handle delivers a prefix of its reference PCM and its failure stays its own."""
+    full6, full19 = seam_cases.stream_path("sine_1khz_cicp6.mhas"), seam_cases.stream_path("sine_1khz_cicp19.mhas")
+    _need(TOOL, full6, full19)
+    cut = tmp_path / "cut.mhas"
+    data = open(full6, "rb").read()
+    cut.write_bytes(data[:int(len(data) * 0.43) + 7])
+    r = subprocess.run([TOOL, "-n:3", "-write:9", f"-o:{tmp_path}/t", full6, str(cut), full19], env=_env(),
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-800:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    assert res["handles"] == 9
+    for j in range(3):
+        assert _sha(f"{tmp_path}/t_{j}.wav") == GOLD["cicp6_mhas"]["sha256"], j
+        assert _sha(f"{tmp_path}/t_{6 + j}.wav") == GOLD["cicp19_mhas"]["sha256"], j
+    # what the unmodified reference testbench makes of the same damaged file (it stops with "insufficient input bytes")
+    tb = os.path.join(REF_DIR, "ia_mpeghd_testbench")
+    _need(tb)
+    subprocess.run([tb, f"-ifile:{cut}", f"-ofile:{tmp_path}/cut_ref.wav"], stdout=subprocess.DEVNULL,
+                   stderr=subprocess.DEVNULL, timeout=300)
+    ref_cut = open(f"{tmp_path}/cut_ref.wav", "rb").read()[44:]
+    full = open(f"{tmp_path}/t_0.wav", "rb").read()[44:]
+    assert 0.3 * len(full) < len(ref_cut) < 0.6 * len(full) and ref_cut == full[:len(ref_cut)]
+    for j in range(3):
+        st = res["streams"][3 + j]
+        got = open(f"{tmp_path}/t_{3 + j}.wav", "rb").read()[44:]
+        assert st["bytes"] == len(got)
+        n = min(len(got), len(ref_cut))
+        assert got[:n] == ref_cut[:n], j
+        assert abs(len(got) - len(ref_cut)) <= 6 * 1024 * 2, (len(got), len(ref_cut))  # at most the damaged frame apart
