@@ -9,11 +9,12 @@
  * (test/impeghd_main.c:227-248), so that a test can compare every handle with the reference's own output without
  * gigabytes of files.
  *
- *   mpeghb200_batch_decode [-n:<copies>] [-batch:0|1] [-write:<K>] [-cicp:<idx>] [-pcmsz:<bits>] -o:<prefix> in1 [in2 ..]
+ *   mpeghb200_batch_decode [-n:<copies>] [-batch:0|1|2] [-write:<K>] [-cicp:<idx>] [-pcmsz:<bits>] -o:<prefix> in1 [in2 ..]
  *
  * -batch:0 advances the handles one ia_mpegh_dec_execute at a time instead (same GPU stages, a launch per handle).
  * Prints one JSON line: handles, frames, wall seconds, audio-seconds per wall-second, per-handle hashes.
  */
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -81,6 +82,40 @@ static double now(void)
   return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
 }
 
+/* -batch:2: the reference's threading contract (one handle per thread is safe): every handle is decoded to the end by a
+ * thread of its own through the unchanged ia_mpegh_dec_execute */
+static void *decode_thread(void *arg)
+{
+  stream_t *s = (stream_t *)arg;
+  while (s->active)
+  {
+    const ia_output_config *oc = &s->api.output_config;
+    const unsigned char *p = (const unsigned char *)s->out_buf;
+    IA_ERRORCODE err;
+    WORD32 b;
+    refill(s);
+    if (s->api.input_config.num_inp_bytes <= 0)
+      break;
+    err = ia_mpegh_dec_execute(s->obj, &s->api.input_config, &s->api.output_config);
+    if (err == IA_MPEGH_DEC_EXE_NONFATAL_INSUFFICIENT_SD_BYTES || err == IA_MPEGH_DEC_EXE_NONFATAL_INSUFFICIENT_HOA_BYTES ||
+        err == IA_MPEGH_DEC_EXE_NONFATAL_INSUFFICIENT_METADATA_BYTES || (err & 0x80000000))
+      break;
+    for (b = 0; b < oc->num_out_bytes; b++)
+      s->hash = (s->hash ^ p[b]) * 1099511628211ull;
+    s->total_bytes += oc->num_out_bytes;
+    if (oc->num_out_bytes > 0)
+    {
+      s->frames++;
+      if (s->out)
+        fwrite(s->out_buf, 1, (size_t)oc->num_out_bytes, s->out);
+    }
+    if (s->buff_size <= 0)
+      break;
+  }
+  s->active = 0;
+  return NULL;
+}
+
 int main(int argc, char **argv)
 {
   int copies = 1, use_batch = 1, n_write = 1, cicp = IMPEGHD_CONFIG_PARAM_CICP_IDX_DFLT_VAL;
@@ -111,7 +146,7 @@ int main(int argc, char **argv)
   }
   if (!n_files || copies < 1 || !prefix)
   {
-    fprintf(stderr, "usage: %s [-n:<copies>] [-batch:0|1] [-write:<K>] [-cicp:<idx>] [-pcmsz:<bits>] -o:<prefix> in1 [in2 ..]\n",
+    fprintf(stderr, "usage: %s [-n:<copies>] [-batch:0|1|2] [-write:<K>] [-cicp:<idx>] [-pcmsz:<bits>] -o:<prefix> in1 [in2 ..]\n",
             argv[0]);
     return 2;
   }
@@ -192,7 +227,17 @@ int main(int argc, char **argv)
   t_init = now() - t0;
   /* ---- the hot loop: one batch call advances every stream that still has input by one frame ---- */
   t0 = now();
-  for (;;)
+  if (use_batch == 2)
+  {
+    pthread_t *th = (pthread_t *)calloc((size_t)n, sizeof(pthread_t));
+    for (i = 0; i < n; i++)
+      pthread_create(&th[i], NULL, decode_thread, &st[i]);
+    for (i = 0; i < n; i++)
+      pthread_join(th[i], NULL), total_frames += st[i].frames;
+    free(th);
+    t_dec = now() - t0;
+  }
+  for (; use_batch != 2;)
   {
     n_active = 0;
     for (i = 0; i < n; i++)

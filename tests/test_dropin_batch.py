@@ -176,3 +176,22 @@ def test_batch_with_a_truncated_stream(tmp_path):
         n = min(len(got), len(ref_cut))
         assert got[:n] == ref_cut[:n], j
         assert abs(len(got) - len(ref_cut)) <= 6 * 1024 * 2, (len(got), len(ref_cut))  # at most the damaged frame apart
+
+
+@pytest.mark.gpu
+def test_one_application_thread_per_handle(tmp_path):
+    """The reference's threading contract (one handle per thread is safe) holds for the drop-in: twelve
+    threads, each decoding its own handle to the end through the unchanged ia_mpegh_dec_execute at the same time
+    (four different streams x 3), produce the reference decoder's PCM."""
+    streams = ["sine_1khz_000_cicp1.mhas", "sine_1khz_cicp6.mhas", "sine_1khz_cicp16.mhas", "sine_1khz_cicp19.mp4"]
+    golds = ["cicp1_mhas", "cicp6_mhas", "cicp16_mhas", "cicp19_mp4"]
+    _need(TOOL, *[seam_cases.stream_path(s) for s in streams])
+    r = subprocess.run([TOOL, "-n:3", "-batch:2", "-write:12", f"-o:{tmp_path}/th",
+                        *[seam_cases.stream_path(s) for s in streams]], env=_env(), capture_output=True, text=True,
+                       timeout=1800)
+    assert r.returncode == 0, r.stderr[-800:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    assert res["handles"] == 12 and res["batch"] == 2
+    for k, g in enumerate(golds):
+        for j in range(3):
+            assert _sha(f"{tmp_path}/th_{3 * k + j}.wav") == GOLD[g]["sha256"], (g, j)
