@@ -9,7 +9,7 @@
  * (test/impeghd_main.c:227-248), so that a test can compare every handle with the reference's own output without
  * gigabytes of files.
  *
- *   mpeghb200_batch_decode [-n:<copies>] [-batch:0|1|2] [-write:<K>] [-cicp:<idx>] [-pcmsz:<bits>] -o:<prefix> in1 [in2 ..]
+ *   mpeghb200_batch_decode [-n:<copies>] [-batch:0|1|2] [-cycles:<K>] [-write:<K>] [-cicp:<idx>] [-pcmsz:<bits>] -o:<prefix> in1 [in2 ..]
  *
  * -batch:0 advances the handles one ia_mpegh_dec_execute at a time instead (same GPU stages, a launch per handle).
  * Prints one JSON line: handles, frames, wall seconds, audio-seconds per wall-second, per-handle hashes.
@@ -118,7 +118,7 @@ static void *decode_thread(void *arg)
 
 int main(int argc, char **argv)
 {
-  int copies = 1, use_batch = 1, n_write = 1, cicp = IMPEGHD_CONFIG_PARAM_CICP_IDX_DFLT_VAL;
+  int copies = 1, use_batch = 1, n_write = 1, cicp = IMPEGHD_CONFIG_PARAM_CICP_IDX_DFLT_VAL, cycles = 1, cycle;
   int pcmsz = IMPEGHD_CONFIG_PARAM_PCM_WD_SZ_DFLT_VAL, n_files = 0, n, i, k, n_active;
   const char *prefix = NULL, *files[256];
   stream_t *st;
@@ -139,6 +139,8 @@ int main(int argc, char **argv)
       cicp = atoi(argv[i] + 6);
     else if (!strncmp(argv[i], "-pcmsz:", 7))
       pcmsz = atoi(argv[i] + 7);
+    else if (!strncmp(argv[i], "-cycles:", 8))
+      cycles = atoi(argv[i] + 8);
     else if (!strncmp(argv[i], "-o:", 3))
       prefix = argv[i] + 3;
     else if (n_files < 256)
@@ -146,11 +148,16 @@ int main(int argc, char **argv)
   }
   if (!n_files || copies < 1 || !prefix)
   {
-    fprintf(stderr, "usage: %s [-n:<copies>] [-batch:0|1|2] [-write:<K>] [-cicp:<idx>] [-pcmsz:<bits>] -o:<prefix> in1 [in2 ..]\n",
+    fprintf(stderr, "usage: %s [-n:<copies>] [-batch:0|1|2] [-cycles:<K>] [-write:<K>] [-cicp:<idx>] [-pcmsz:<bits>] -o:<prefix> in1 [in2 ..]\n",
             argv[0]);
     return 2;
   }
   n = n_files * copies;
+  /* -cycles:K: create, decode and delete all handles K times in this process (a server's handles come and go); one
+   * JSON line per cycle */
+  for (cycle = 0; cycle < cycles; cycle++)
+  {
+  t_dec = 0.0, total_frames = 0;
   st = (stream_t *)calloc((size_t)n, sizeof(stream_t));
   objs = (pVOID *)calloc((size_t)n, sizeof(pVOID)), ins = (pVOID *)calloc((size_t)n, sizeof(pVOID));
   outs = (pVOID *)calloc((size_t)n, sizeof(pVOID));
@@ -316,5 +323,8 @@ int main(int argc, char **argv)
     impeghd_mp4_fw_close(s->in);
   }
   printf("]}\n");
+  fflush(stdout);
+  free(st), free(objs), free(ins), free(outs), free(errs), free(map);
+  }
   return 0;
 }

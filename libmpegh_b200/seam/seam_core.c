@@ -35,6 +35,8 @@
 
 #include <impeghd_type_def.h>
 #include "impeghd_error_codes.h"
+#include "impeghd_memory_standards.h"
+#include "impeghd_api.h"
 
 #include "seam_internal.h"
 
@@ -42,6 +44,7 @@ seam_counters seam_n;
 static mpeghb200_ctx *g_ctx;
 static seam_backend g_backend[RQ_KINDS];
 static const char *g_backend_name[RQ_KINDS];
+static unsigned long g_blocks_made, g_blocks_freed; /* device state blocks created / freed with their handles */
 static double g_t_parse, g_t_backend[RQ_KINDS]; /* wall time of the batch scheduler: handles running / back-end rounds */
 static pthread_mutex_t g_init_mu = PTHREAD_MUTEX_INITIALIZER;
 
@@ -69,6 +72,9 @@ static void seam_stats(void)
             seam_n.hoa_spatial_host, seam_n.binaural, seam_n.binaural_host, seam_n.stereo, seam_n.stereo_host, seam_n.igf,
             seam_n.igf_tnf, seam_n.igf_stereo, seam_n.igf_host, seam_n.drc_sb, seam_n.drc_td, seam_n.drc_host,
             seam_n.drc_stft);
+  if (getenv("MPEGHB200_SEAM_STATS"))
+    fprintf(stderr, "mpeghb200 seam: device state blocks created=%lu freed with their handles=%lu\n", g_blocks_made,
+            g_blocks_freed);
   if (getenv("MPEGHB200_SEAM_STATS") && g_t_parse > 0.0)
   {
     int k;
@@ -145,9 +151,17 @@ static seam_block *pool_find(seam_pool *p, const void *key, int *idx)
   return NULL;
 }
 
+/* every pool that owns slots, so that ia_mpegh_dec_delete can drop the ones of the handle that goes away */
+#define MAX_POOLS 512
+static seam_pool *g_pools[MAX_POOLS];
+static int g_n_pools;
+
 static seam_block *pool_new_block(seam_pool *p, const void **keys, int n)
 {
   seam_block *b = (seam_block *)calloc(1, sizeof(*b));
+  if (!p->registered && g_n_pools < MAX_POOLS)
+    g_pools[g_n_pools++] = p, p->registered = 1;
+  g_blocks_made++;
   b->n = n;
   b->keys = (const void **)malloc(sizeof(void *) * (size_t)n);
   memcpy(b->keys, keys, sizeof(void *) * (size_t)n);
@@ -192,6 +206,40 @@ void *seam_pool_one(seam_pool *p, const void *key, int *fresh)
     return b->d + p->stride * (size_t)idx;
   *fresh = 1;
   return pool_new_block(p, &key, 1)->d;
+}
+
+/* A decoder handle is deleted: the device state that was keyed by addresses inside its memory [lo, hi) is dead.  Its
+ * slots lose their key (a new handle the allocator puts at the same address starts from fresh state, as the reference's
+ * own create + init gives it); a block without a live slot is freed. */
+static void pools_release_range(const char *lo, const char *hi)
+{
+  int k, i;
+  for (k = 0; k < g_n_pools; k++)
+  {
+    seam_block **link = &g_pools[k]->blocks, *b;
+    while ((b = *link) != NULL)
+    {
+      int live = 0;
+      for (i = 0; i < b->n; i++)
+      {
+        const char *key = (const char *)b->keys[i];
+        if (key && key >= lo && key < hi)
+          b->keys[i] = NULL;
+        live += b->keys[i] != NULL;
+      }
+      if (!live)
+      {
+        *link = b->next;
+        if (g_ctx)
+          mpeghb200_dev_free(g_ctx, b->d);
+        free(b->keys);
+        free(b);
+        g_blocks_freed++;
+      }
+      else
+        link = &b->next;
+    }
+  }
 }
 
 /* ---- coroutines and the batch scheduler ------------------------------------------------------------------------- */
@@ -510,7 +558,20 @@ IA_ERRORCODE ia_mpegh_dec_execute(pVOID p_ia_module_obj, pVOID pv_input, pVOID p
 IA_ERRORCODE ia_mpegh_dec_delete(pVOID pv_output)
 {
   static api1_fn real;
+  const ia_output_config *oc = (const ia_output_config *)pv_output;
+  const char *lo[NUM_MEMTABS], *hi[NUM_MEMTABS];
+  IA_ERRORCODE err;
+  int i, n = 0;
   if (!real)
     real = (api1_fn)next_sym("ia_mpegh_dec_delete");
-  return real(pv_output);
+  /* the handle's memory blocks (decoder/impeghd_api.c:341-392): every persistent struct of the handle lives in them */
+  for (i = 0; oc && i < NUM_MEMTABS; i++)
+    if (oc->mem_info_table[i].mem_ptr && oc->mem_info_table[i].ui_size)
+      lo[n] = (const char *)oc->mem_info_table[i].mem_ptr, hi[n] = lo[n] + oc->mem_info_table[i].ui_size, n++;
+  err = real(pv_output);
+  pthread_mutex_lock(&g_batch_mu);
+  for (i = 0; i < n; i++)
+    pools_release_range(lo[i], hi[i]);
+  pthread_mutex_unlock(&g_batch_mu);
+  return err;
 }

@@ -97,6 +97,7 @@ typedef struct
 {
   seam_block *blocks;
   size_t stride; /* bytes per slot */
+  int registered; /* known to the core, which drops a deleted handle's slots (ia_mpegh_dec_delete) */
 } seam_pool;
 /* Finds (or creates: *fresh = 1) consecutive slots for keys[0..n).  Returns the device pointer of slot 0 when the n
  * keys are consecutive in one block, NULL otherwise (use seam_pool_one per key then). */

@@ -195,3 +195,29 @@ def test_one_application_thread_per_handle(tmp_path):
     for k, g in enumerate(golds):
         for j in range(3):
             assert _sha(f"{tmp_path}/th_{3 * k + j}.wav") == GOLD[g]["sha256"], (g, j)
+
+
+@pytest.mark.gpu
+def test_handles_come_and_go(tmp_path):
+    """A server's handles are created and deleted all the time, and the allocator hands the next handle the addresses of
+    the last one: three create / decode / delete cycles of 8 + 8 handles in one process.  Every cycle decodes the
+    reference's PCM (the device state keyed by addresses inside a deleted handle is dropped with it, so the next handle
+    at that address starts from fresh limiter / object-renderer state), and the state blocks are freed with the handles."""
+    streams = ["sine_1khz_cicp19.mhas", "sine_1khz_cicp6.mhas"]
+    _need(TOOL, *[seam_cases.stream_path(s) for s in streams])
+    r = subprocess.run([TOOL, "-n:8", "-cycles:3", "-write:16", f"-o:{tmp_path}/c",
+                        *[seam_cases.stream_path(s) for s in streams]], env=_env(), capture_output=True, text=True,
+                       timeout=1800)
+    assert r.returncode == 0, r.stderr[-800:]
+    lines = [json.loads(l) for l in r.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 3
+    for res in lines:
+        assert res["handles"] == 16
+        assert {s["fnv1a64"] for s in res["streams"][:8]} == {lines[0]["streams"][0]["fnv1a64"]}
+        assert {s["fnv1a64"] for s in res["streams"][8:]} == {lines[0]["streams"][8]["fnv1a64"]}
+    assert _sha(f"{tmp_path}/c_0.wav") == GOLD["cicp19_mhas"]["sha256"]
+    assert _sha(f"{tmp_path}/c_8.wav") == GOLD["cicp6_mhas"]["sha256"]
+    m = re.search(r"device state blocks created=(\d+) freed with their handles=(\d+)", r.stderr)
+    assert m, r.stderr[-400:]
+    made, freed = int(m.group(1)), int(m.group(2))
+    assert made >= 3 and freed == made, (made, freed)
