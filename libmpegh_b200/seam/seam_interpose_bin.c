@@ -87,7 +87,7 @@
 #include "seam_internal.h"
 
 /* ---- renderers by content ---- */
-#define MAX_BIN 8
+#define MAX_BIN 64
 static struct
 {
   unsigned long long hash;

@@ -100,7 +100,7 @@
 #define ST_STATE 2048 /* mpeghb200_stereo_state_floats(): the two saved spectra */
 
 /* ---- band tables by (long table, short table); a tool that only knows one block type gets a one-band dummy for the other */
-#define MAX_BANDS 16
+#define MAX_BANDS 64
 static struct
 {
   const WORD16 *tl, *ts;

@@ -86,7 +86,7 @@
 
 /* converters by content: handles that decode like streams to the same layout share one (the downmix tensor is a pure
  * function of the layout pair) */
-#define MAX_FC 8
+#define MAX_FC 64
 static struct
 {
   int n_in, n_out;

@@ -100,7 +100,7 @@
 #define SENTINEL_BITS 0x7FC0B200u
 
 /* ---- decoders by content ---- */
-#define MAX_HOASP 8
+#define MAX_HOASP 64
 static struct
 {
   unsigned long long hash;

@@ -94,7 +94,7 @@
 #define FRAME 1024
 
 /* ---- layouts by content ---- */
-#define MAX_LAYOUTS 16
+#define MAX_LAYOUTS 64
 static struct
 {
   mpeghb200_obj_layout_desc desc;

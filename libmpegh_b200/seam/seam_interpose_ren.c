@@ -111,7 +111,7 @@ static const float *rs_rom(int three)
 #define FRAME 1024
 
 /* ---- HOA renderer ------------------------------------------------------------------------------------------------ */
-#define MAX_REN 16
+#define MAX_REN 64
 static struct
 {
   unsigned long long hash;
