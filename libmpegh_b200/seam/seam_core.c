@@ -540,11 +540,25 @@ IA_ERRORCODE ia_mpegh_dec_create(pVOID pv_input, pVOID pv_output)
   return real(pv_input, pv_output);
 }
 
+static void release_handle_state(const ia_output_config *oc)
+{
+  int i;
+  pthread_mutex_lock(&g_batch_mu);
+  for (i = 0; oc && i < NUM_MEMTABS; i++)
+    if (oc->mem_info_table[i].mem_ptr && oc->mem_info_table[i].ui_size)
+      pools_release_range((const char *)oc->mem_info_table[i].mem_ptr,
+                          (const char *)oc->mem_info_table[i].mem_ptr + oc->mem_info_table[i].ui_size);
+  pthread_mutex_unlock(&g_batch_mu);
+}
+
 IA_ERRORCODE ia_mpegh_dec_init(pVOID p_ia_module_obj, pVOID pv_input, pVOID pv_output)
 {
   static api3_fn real;
   if (!real)
     real = (api3_fn)next_sym("ia_mpegh_dec_init");
+  /* (re-)initialisation: the reference sets up its persistent structs again (limiter, renderers, converter ...), so
+   * what the device holds for this handle is the past; the frames init itself decodes start from fresh state */
+  release_handle_state((const ia_output_config *)pv_output);
   return real(p_ia_module_obj, pv_input, pv_output);
 }
 
@@ -559,19 +573,10 @@ IA_ERRORCODE ia_mpegh_dec_delete(pVOID pv_output)
 {
   static api1_fn real;
   const ia_output_config *oc = (const ia_output_config *)pv_output;
-  const char *lo[NUM_MEMTABS], *hi[NUM_MEMTABS];
-  IA_ERRORCODE err;
-  int i, n = 0;
   if (!real)
     real = (api1_fn)next_sym("ia_mpegh_dec_delete");
-  /* the handle's memory blocks (decoder/impeghd_api.c:341-392): every persistent struct of the handle lives in them */
-  for (i = 0; oc && i < NUM_MEMTABS; i++)
-    if (oc->mem_info_table[i].mem_ptr && oc->mem_info_table[i].ui_size)
-      lo[n] = (const char *)oc->mem_info_table[i].mem_ptr, hi[n] = lo[n] + oc->mem_info_table[i].ui_size, n++;
-  err = real(pv_output);
-  pthread_mutex_lock(&g_batch_mu);
-  for (i = 0; i < n; i++)
-    pools_release_range(lo[i], hi[i]);
-  pthread_mutex_unlock(&g_batch_mu);
-  return err;
+  /* the handle's memory blocks (decoder/impeghd_api.c:341-392): every persistent struct of the handle lives in them;
+   * the table itself sits in the caller's ia_output_config and survives the delete */
+  release_handle_state(oc);
+  return real(pv_output);
 }
