@@ -540,6 +540,14 @@ IA_ERRORCODE ia_mpegh_dec_create(pVOID pv_input, pVOID pv_output)
   return real(pv_input, pv_output);
 }
 
+void seam_release_range(const void *lo, const void *hi)
+{ /* back-ends (the other users of the pools) only run while every handle of the batch is parked; the handles of a
+     batch run side by side, hence the lock */
+  seam_inline_lock();
+  pools_release_range((const char *)lo, (const char *)hi);
+  seam_inline_unlock();
+}
+
 static void release_handle_state(const ia_output_config *oc)
 {
   int i;

@@ -103,4 +103,7 @@ typedef struct
  * keys are consecutive in one block, NULL otherwise (use seam_pool_one per key then). */
 void *seam_pool_range(seam_pool *p, const void **keys, int n, int *fresh);
 void *seam_pool_one(seam_pool *p, const void *key, int *fresh);
+/* The reference has re-initialised everything inside [lo, hi) in place (ia_core_coder_decoder_flush_api, from inside an
+ * execute call): slots keyed by addresses in that range start over.  Callable from a handle's coroutine. */
+void seam_release_range(const void *lo, const void *hi);
 #endif

@@ -609,6 +609,23 @@ IA_ERRORCODE impeghd_domain_switcher_process(ia_mpegh_dec_api_struct *p_obj_mpeg
   return IA_MPEGH_DEC_NO_ERROR;
 }
 
+/* ---- mid-stream re-initialisation (a changed configuration packet, decoder/ia_core_coder_decode_main.c:2519-2533) ---
+ * ia_core_coder_decoder_flush_api clears the handle's persistent structs in place and initialises the decoder again:
+ * the device state keyed by their addresses is the past. */
+IA_ERRORCODE ia_core_coder_decoder_flush_api(ia_mpegh_dec_api_struct *p_obj_mpegh_dec)
+{
+  typedef IA_ERRORCODE (*fn_t)(ia_mpegh_dec_api_struct *);
+  static fn_t real;
+  int i;
+  if (!real)
+    real = (fn_t)seam_real("ia_core_coder_decoder_flush_api");
+  for (i = 0; i < 4; i++) /* NUM_MEMTABS: persistent, scratch, input, output */
+    if (p_obj_mpegh_dec->pp_mem_mpeghd && p_obj_mpegh_dec->pp_mem_mpeghd[i] && p_obj_mpegh_dec->p_mem_info_mpeghd)
+      seam_release_range(p_obj_mpegh_dec->pp_mem_mpeghd[i],
+                         (const char *)p_obj_mpegh_dec->pp_mem_mpeghd[i] + p_obj_mpegh_dec->p_mem_info_mpeghd[i].ui_size);
+  return real(p_obj_mpegh_dec);
+}
+
 __attribute__((constructor)) static void seam_register_drc(void)
 {
   seam_register(RQ_DS, be_ds, "domain_switcher");

@@ -221,3 +221,27 @@ def test_handles_come_and_go(tmp_path):
     assert m, r.stderr[-400:]
     made, freed = int(m.group(1)), int(m.group(2))
     assert made >= 3 and freed == made, (made, freed)
+
+
+@pytest.mark.gpu
+def test_configuration_change_mid_stream(tmp_path):
+    """Three MHAS streams back to back in one file (12-, 6-, 12-channel output): every new configuration packet makes
+    the reference flush and re-initialise the decoder in place inside ia_mpegh_dec_execute
+    (ia_core_coder_decode_main.c:2519-2533 -> ia_core_coder_decoder_flush_api).  The drop-in drops the device state of the
+    handle at that point, so the third part -- same structs, same addresses, same channel count as the first -- starts
+    from fresh limiter and object-renderer state like the reference does: byte-identical WAV."""
+    parts = ["sine_1khz_cicp19.mhas", "sine_1khz_cicp6.mhas", "sine_1khz_cicp19.mhas"]
+    tb = os.path.join(REF_DIR, "ia_mpeghd_testbench")
+    _need(TB_GPU, tb, *[seam_cases.stream_path(s) for s in parts])
+    cat = tmp_path / "cat.mhas"
+    cat.write_bytes(b"".join(open(seam_cases.stream_path(s), "rb").read() for s in parts))
+    subprocess.run([tb, f"-ifile:{cat}", f"-ofile:{tmp_path}/ref.wav"], stdout=subprocess.DEVNULL,
+                   stderr=subprocess.DEVNULL, timeout=600)
+    ref_bytes = os.path.getsize(f"{tmp_path}/ref.wav")
+    assert ref_bytes > 2 * (GOLD["cicp19_mhas"]["bytes"] - 44)  # the reference really decoded all three parts
+    r = subprocess.run([TB_GPU, f"-ifile:{cat}", f"-ofile:{tmp_path}/gpu.wav"], env=_env(), stdout=subprocess.DEVNULL,
+                       stderr=subprocess.PIPE, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-600:]
+    c = _counters(r.stderr)
+    assert c["obj_render gpu"] > 1000 and c["limiter_frames gpu"] > 1000
+    assert _sha(f"{tmp_path}/gpu.wav") == _sha(f"{tmp_path}/ref.wav")
