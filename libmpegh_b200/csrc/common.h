@@ -40,6 +40,7 @@ struct mpeghb200_ctx {
   int sm_count = 0;
   std::string last_error;
   std::atomic<uint64_t> launches{0};
+  bool pack_generic = false;  // MPEGHB200_PACK_GENERIC=1: the byte-wise PCM packer for every channel count (comparison)
   int fd_variant = 7;  // launch shape, see fd_synth_launch (7 = warp-specialised persistent CTAs, 3 per SM)
   mpeghb200::DeviceTables tables;
   std::vector<void*> owned;  // device allocations released by destroy()

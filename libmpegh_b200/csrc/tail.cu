@@ -298,6 +298,81 @@ __global__ void __launch_bounds__(kPackSamples)
   }
 }
 
+// The same for channel counts that are a multiple of four (22.2, 7.1.4, 5.1.2 ...), sample size at compile time: four
+// channels of a sample are converted in registers and leave as 2 / 3 / 4 whole 32-bit words (the generic kernel stores
+// byte by byte and spends 46 instructions per value, ncu: issue-active 67 %, LSU wavefronts 66 %, DRAM 33 %).
+template <int BITS>
+__device__ __forceinline__ unsigned pcm_convert_t(float v) {
+  if (BITS == 24) {
+    v = fmul(v, 256.0f);
+    v = v < -8388608.0f ? -8388608.0f : (8388607.0f < v ? 8388607.0f : v);
+    return static_cast<unsigned>(sat_cast(v));
+  }
+  if (BITS == 16) {
+    v = v < -32768.0f ? -32768.0f : (32767.0f < v ? 32767.0f : v);
+    return static_cast<unsigned>(sat_cast(v));
+  }
+  v = fmul(v, 65536.0f);
+  if (v < -2147483647.0f) v = -2147483647.0f;
+  return (2147483647.0f < v) ? 0x7fffffffu : static_cast<unsigned>(sat_cast(v));
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(kPackSamples)
+    pcm_pack4_kernel(const float* __restrict__ in, unsigned char* __restrict__ out, int* __restrict__ delay,
+                     int* __restrict__ out_bytes, const PackParams P) {
+  pdl_prologue();
+  extern __shared__ __align__(16) unsigned char tile[];  // [kPackSamples][n_ch][bytes]
+  constexpr int BPS = BITS / 8;
+  const int tid = threadIdx.x;
+  const int chunk = blockIdx.x, sidx = blockIdx.y;
+  const int rec = P.n_ch * BPS;
+  const int frame_bytes = P.n_samples * rec;
+  const float* x = in + size_t(sidx) * P.n_ch * P.ch_stride;
+  const int d = delay ? delay[sidx] : 0;
+  const int s = chunk * kPackSamples + tid;
+  unsigned* tw = reinterpret_cast<unsigned*>(tile + size_t(tid) * rec);
+  for (int ch0 = 0; ch0 < P.n_ch; ch0 += 8) {
+    float vin[8];  // eight channel loads in flight before the first conversion (n_ch % 4 == 0: whole groups of four)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) vin[q] = (ch0 + q < P.n_ch) ? __ldcs(x + size_t(P.pos[ch0 + q]) * P.ch_stride + s) : 0.0f;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      if (ch0 + 4 * g >= P.n_ch) break;
+      const unsigned w0 = pcm_convert_t<BITS>(vin[4 * g]), w1 = pcm_convert_t<BITS>(vin[4 * g + 1]),
+                     w2 = pcm_convert_t<BITS>(vin[4 * g + 2]), w3 = pcm_convert_t<BITS>(vin[4 * g + 3]);
+      if (BITS == 24) {
+        tw[0] = (w0 & 0xffffffu) | (w1 << 24);
+        tw[1] = ((w1 >> 8) & 0xffffu) | (w2 << 16);
+        tw[2] = ((w2 >> 16) & 0xffu) | (w3 << 8);
+      } else if (BITS == 16) {
+        tw[0] = (w0 & 0xffffu) | (w1 << 16);
+        tw[1] = (w2 & 0xffffu) | (w3 << 16);
+      } else {
+        tw[0] = w0, tw[1] = w1, tw[2] = w2, tw[3] = w3;
+      }
+      tw += BPS;
+    }
+  }
+  __syncthreads();
+  const int tile_bytes = kPackSamples * rec;
+  const long long dst0 = (long long)(chunk * kPackSamples - d) * rec;
+  unsigned char* o = out + size_t(sidx) * frame_bytes;
+  if (dst0 >= 0 && (dst0 & 15) == 0 && (tile_bytes & 15) == 0) {
+    const uint4* t4 = reinterpret_cast<const uint4*>(tile);
+    uint4* o4 = reinterpret_cast<uint4*>(o + dst0);
+    for (int i = tid; i < tile_bytes / 16; i += kPackSamples) __stcs(o4 + i, t4[i]);
+  } else {
+    for (int i = tid; i < tile_bytes; i += kPackSamples) {
+      const long long p = dst0 + i;
+      if (p >= 0) o[p] = tile[i];
+    }
+  }
+  if (chunk == 0 && tid == 0) {
+    if (out_bytes) out_bytes[sidx] = (d <= P.n_samples) ? (P.n_samples - d) * rec : 0;
+  }
+}
+
 // ---- limiter + PCM packer as a gains kernel and an apply-and-pack kernel -------------------------------
 // The chain's tail without the planar fp32 round trip between limiter and packer, and without tying the data-parallel
 // part of the limiter (delayed samples x gain, clip) to the one CTA per stream that the serial smoother needs:
@@ -614,10 +689,19 @@ mpeghb200_status mpeghb200_pcm_pack_block_dev(mpeghb200_ctx* ctx, const float* d
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   const size_t smem = size_t(kPackSamples) * n_ch * (pcm_bits >> 3);
   // per device / context attribute: set on every call (a process may hold contexts on several GPUs)
-  if (smem > 48 * 1024)
-    MB_CUDA(ctx, cudaFuncSetAttribute(pcm_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   dim3 grid(n_samples / kPackSamples, n_streams);
-  MB_CUDA(ctx, launch_pdl(pcm_pack_kernel, grid, dim3(kPackSamples), smem, st, d_in, d_out, d_delay, d_out_bytes, P));
+  auto launch = [&](void (*k)(const float*, unsigned char*, int*, int*, PackParams)) -> mpeghb200_status {
+    // per device / context attribute: set on every call (a process may hold contexts on several GPUs)
+    if (smem > 48 * 1024) MB_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    MB_CUDA(ctx, launch_pdl(k, grid, dim3(kPackSamples), smem, st, d_in, d_out, d_delay, d_out_bytes, P));
+    return MPEGHB200_OK;
+  };
+  mpeghb200_status ls;
+  if (n_ch % 4 == 0 && !ctx->pack_generic)
+    ls = pcm_bits == 24 ? launch(pcm_pack4_kernel<24>) : pcm_bits == 16 ? launch(pcm_pack4_kernel<16>) : launch(pcm_pack4_kernel<32>);
+  else
+    ls = launch(pcm_pack_kernel);
+  if (ls != MPEGHB200_OK) return ls;
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   if (d_delay) {
