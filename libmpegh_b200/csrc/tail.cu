@@ -332,12 +332,13 @@ __global__ void __launch_bounds__(kPackSamples)
   const int d = delay ? delay[sidx] : 0;
   const int s = chunk * kPackSamples + tid;
   unsigned* tw = reinterpret_cast<unsigned*>(tile + size_t(tid) * rec);
-  for (int ch0 = 0; ch0 < P.n_ch; ch0 += 8) {
-    float vin[8];  // eight channel loads in flight before the first conversion (n_ch % 4 == 0: whole groups of four)
+  constexpr int kB = 24;  // channel loads in flight before the first conversion (n_ch % 4 == 0: whole groups of four)
+  for (int ch0 = 0; ch0 < P.n_ch; ch0 += kB) {
+    float vin[kB];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) vin[q] = (ch0 + q < P.n_ch) ? __ldcs(x + size_t(P.pos[ch0 + q]) * P.ch_stride + s) : 0.0f;
+    for (int q = 0; q < kB; ++q) vin[q] = (ch0 + q < P.n_ch) ? __ldcs(x + size_t(P.pos[ch0 + q]) * P.ch_stride + s) : 0.0f;
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
+    for (int g = 0; g < kB / 4; ++g) {
       if (ch0 + 4 * g >= P.n_ch) break;
       const unsigned w0 = pcm_convert_t<BITS>(vin[4 * g]), w1 = pcm_convert_t<BITS>(vin[4 * g + 1]),
                      w2 = pcm_convert_t<BITS>(vin[4 * g + 2]), w3 = pcm_convert_t<BITS>(vin[4 * g + 3]);
