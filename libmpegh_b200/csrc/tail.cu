@@ -51,7 +51,7 @@ __device__ __forceinline__ void limiter_gains(const float* __restrict__ x, float
     // 1. channel maxima (fmax semantics of the reference: NaN operands are dropped)
     float4 acc[2];
     acc[0] = acc[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 6
+#pragma unroll 12
     for (int c = 0; c < P.n_ch; ++c) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kLimThreads)
   float4 gv[2];
 #pragma unroll
   for (int h = 0; h < 2; ++h) gv[h] = *reinterpret_cast<const float4*>(g + 4 * (tid + kLimThreads * h));
-#pragma unroll 4
+#pragma unroll 8
   for (int c = 0; c < P.n_ch; ++c) {
     float* dl = st_delay + size_t(c) * A;
     const float* xc = x + size_t(c) * kFrame;
