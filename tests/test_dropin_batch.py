@@ -245,3 +245,25 @@ def test_configuration_change_mid_stream(tmp_path):
     c = _counters(r.stderr)
     assert c["obj_render gpu"] > 1000 and c["limiter_frames gpu"] > 1000
     assert _sha(f"{tmp_path}/gpu.wav") == _sha(f"{tmp_path}/ref.wav")
+
+
+def test_integration_doc_lists_what_is_exported():
+    """CPU: every reference function INTEGRATION.md's table names as interposed is a defined export of libmpeghgpu.so, and
+    every reference-named export of the library appears in the document (no drift between the two)."""
+    _need(GPULIB)
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    table = doc[doc.index("| interposed reference function"):doc.index("**Batching without a source patch.**")]
+    named = set()
+    for row in table.splitlines()[2:]:
+        cells = row.split("|")
+        if len(cells) > 2:
+            named |= set(re.findall(r"`((?:ia_core_coder|impeghd|impd_drc|ia_mpegh)_[a-z0-9_]+)`", cells[1]))
+    syms = subprocess.run(["nm", "-D", "--defined-only", GPULIB], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT ((?:ia_core_coder|impeghd|impd_drc)_[a-z0-9_]+)\b", syms))
+    callers = {"impeghd_hoa_spatial_process"}  # named in the table only as the caller of the four interposed stages
+    assert len(named - callers) >= 26
+    missing = {n for n in named - callers if n not in exported}
+    assert not missing, f"named in INTEGRATION.md but not exported: {sorted(missing)}"
+    helpers = {"ia_core_coder_decoder_flush_api"}  # lifecycle hook, described in the tests section of the document
+    undocumented = {e for e in exported if e not in named and e not in helpers and e not in doc}
+    assert not undocumented, f"exported but not in INTEGRATION.md: {sorted(undocumented)}"
