@@ -41,6 +41,7 @@ struct mpeghb200_ctx {
   std::string last_error;
   std::atomic<uint64_t> launches{0};
   bool pack_generic = false;  // MPEGHB200_PACK_GENERIC=1: the byte-wise PCM packer for every channel count (comparison)
+  int lim_variant = 3;  // MPEGHB200_LIM_VARIANT: bit 0 = 256 threads per stream (else 128), bit 1 = smoother release fast path
   int fd_variant = 7;  // launch shape, see fd_synth_launch (7 = warp-specialised persistent CTAs, 3 per SM)
   mpeghb200::DeviceTables tables;
   std::vector<void*> owned;  // device allocations released by destroy()
@@ -63,6 +64,7 @@ mpeghb200_status cuda_fail(mpeghb200_ctx* ctx, cudaError_t e, const char* what);
 // then wait until the predecessor has completed and its writes are visible.  What is saved is the launch latency
 // and CTA ramp-up between the stages.  Every kernel launched this way MUST call pdl_prologue() (or wait itself)
 // before it touches global memory.
+extern bool g_pdl_enabled;  // ctx.cu; MPEGHB200_NO_PDL=1 launches every stage fully serialised (comparison / lanes probe)
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -76,7 +78,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr, cfg.numAttrs = 1;
+  cfg.attrs = attr, cfg.numAttrs = g_pdl_enabled ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 #endif

@@ -7,6 +7,8 @@
 
 namespace mpeghb200 {
 
+bool g_pdl_enabled = true;
+
 static std::mutex g_err_mu;
 static std::string g_create_error;
 
@@ -162,6 +164,8 @@ mpeghb200_status mpeghb200_create(mpeghb200_ctx** out, int device_ordinal) {
   if (!ctx) return MPEGHB200_ERR_NO_MEM;
   ctx->device = device_ordinal;
   if (const char* v = std::getenv("MPEGHB200_FD_VARIANT")) ctx->fd_variant = std::atoi(v);
+  if (const char* v = std::getenv("MPEGHB200_LIM_VARIANT")) ctx->lim_variant = std::atoi(v);
+  if (const char* v = std::getenv("MPEGHB200_NO_PDL")) mpeghb200::g_pdl_enabled = std::atoi(v) == 0;
   if (const char* v = std::getenv("MPEGHB200_PACK_GENERIC")) ctx->pack_generic = std::atoi(v) != 0;
   e = cudaSetDevice(device_ordinal);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_ordinal);

@@ -28,19 +28,23 @@
 namespace mpeghb200 {
 namespace {
 
-constexpr int kLimThreads = 128;
 constexpr int kMaxAttack = 240;
 constexpr int kFrame = 1024;
 
 struct LimParams {
   int n_ch, attack, limiter_on, stride;  // stride = floats of state per stream
   float thr, ac, rc;
+  int fast_release;  // smoother: blocks of eight unit gains take the three-operation release chain (bit-identical)
 };
 
 // Steps 1 - 4 for the CTA's stream: leaves the per-sample gains in g[] (< 0 = pass through) and advances the
 // smoother / history part of the state.  m, m2: [kMaxAttack + kFrame + 16] each, g: [kFrame], all in shared memory.
+// NT threads per stream (128 or 256): a thread owns kFrame / 4 / NT float4 positions of every channel.
+template <int NT>
 __device__ __forceinline__ void limiter_gains(const float* __restrict__ x, float* __restrict__ st, const LimParams& P,
                                               float lg, bool has_lg, float* m, float* m2, float* g) {
+  constexpr int kLimThreads = NT;
+  constexpr int kVec = kFrame / 4 / NT;
   const int tid = threadIdx.x;
   const int A = P.attack;
   float* st_hist = st + 4;
@@ -49,12 +53,13 @@ __device__ __forceinline__ void limiter_gains(const float* __restrict__ x, float
 
   if (!bypass) {
     // 1. channel maxima (fmax semantics of the reference: NaN operands are dropped)
-    float4 acc[2];
-    acc[0] = acc[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc[kVec];
+#pragma unroll
+    for (int h = 0; h < kVec; ++h) acc[h] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 12
     for (int c = 0; c < P.n_ch; ++c) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < kVec; ++h) {
         float4 v = __ldg(reinterpret_cast<const float4*>(x + size_t(c) * kFrame) + tid + kLimThreads * h);
         if (has_lg) v = make_float4(fmul(v.x, lg), fmul(v.y, lg), fmul(v.z, lg), fmul(v.w, lg));
         acc[h].x = fmaxf(acc[h].x, fabsf(v.x));
@@ -65,7 +70,7 @@ __device__ __forceinline__ void limiter_gains(const float* __restrict__ x, float
     }
     for (int i = tid; i < A; i += kLimThreads) m[i] = st_hist[i];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < kVec; ++h) {
       const int i = 4 * (tid + kLimThreads * h);
       m[A + i] = acc[h].x, m[A + i + 1] = acc[h].y, m[A + i + 2] = acc[h].z, m[A + i + 3] = acc[h].w;
     }
@@ -112,6 +117,20 @@ __device__ __forceinline__ void limiter_gains(const float* __restrict__ x, float
           const float4 a = *reinterpret_cast<const float4*>(g + i0);
           const float4 b = *reinterpret_cast<const float4*>(g + i0 + 4);
           float gv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+          // Eight unit gains with the state at or below 1: every sample takes gain >= pre_smoothed_gain, i.e.
+          // gain_modified = 1, release coefficient, psg = 1 + rc * (psg - 1) -- and psg <= 1 is kept by each step
+          // (psg - 1 <= 0, so is its product with rc >= 0, and 1 plus that rounds to at most 1).  The test on the
+          // gains does not depend on the running state, so only the three-operation chain is waited for.
+          const bool ones = P.fast_release && fminf(fminf(fminf(a.x, a.y), fminf(a.z, a.w)), fminf(fminf(b.x, b.y), fminf(b.z, b.w))) == 1.0f &&
+                            fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w))) == 1.0f;
+          if (ones && psg <= 1.0f && rc >= 0.0f) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              psg = fadd(1.0f, fmul(rc, fsub(psg, 1.0f)));
+              gv[e] = psg;
+            }
+            gm = 1.0f;
+          } else {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const float gain = gv[e];
@@ -121,6 +140,7 @@ __device__ __forceinline__ void limiter_gains(const float* __restrict__ x, float
             const float r = fadd(gm, fmul(up ? rc : ac, fsub(psg, gm)));
             psg = up ? r : fmaxf(r, gain);
             gv[e] = psg;
+          }
           }
           *reinterpret_cast<float4*>(g + i0) = make_float4(gv[0], gv[1], gv[2], gv[3]);
           *reinterpret_cast<float4*>(g + i0 + 4) = make_float4(gv[4], gv[5], gv[6], gv[7]);
@@ -139,9 +159,12 @@ __device__ __forceinline__ void limiter_gains(const float* __restrict__ x, float
 
 }
 
-__global__ void __launch_bounds__(kLimThreads)
+template <int NT>
+__global__ void __launch_bounds__(NT)
     limiter_kernel(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ state,
                    const float* __restrict__ loud_gain, const LimParams P) {
+  constexpr int kLimThreads = NT;
+  constexpr int kVec = kFrame / 4 / NT;
   pdl_prologue();
   __shared__ __align__(16) float m[kMaxAttack + kFrame + 16];   // channel maxima incl. history / sliding max
   __shared__ __align__(16) float m2[kMaxAttack + kFrame + 16];  // ping-pong partner
@@ -155,22 +178,22 @@ __global__ void __launch_bounds__(kLimThreads)
   float* st_delay = st + 4 + A;
   const float lg = loud_gain ? __ldg(loud_gain + sidx) : 1.0f;
   const bool has_lg = loud_gain != nullptr;
-  limiter_gains(x, st, P, lg, has_lg, m, m2, g);
+  limiter_gains<NT>(x, st, P, lg, has_lg, m, m2, g);
 
   // 5. delayed output: sample i of the frame leaves as input sample i - A (this frame for i >= A, the delay line
   //    before), times the gain, clipped.  Straight from global memory (the frame is L2-resident since step 1, A is
   //    a multiple of 4 so every float4 stays aligned): no staging, no barriers, loads of several channels in flight.
   const float thr = P.thr;
-  float4 gv[2];
+  float4 gv[kVec];
 #pragma unroll
-  for (int h = 0; h < 2; ++h) gv[h] = *reinterpret_cast<const float4*>(g + 4 * (tid + kLimThreads * h));
+  for (int h = 0; h < kVec; ++h) gv[h] = *reinterpret_cast<const float4*>(g + 4 * (tid + kLimThreads * h));
 #pragma unroll 8
   for (int c = 0; c < P.n_ch; ++c) {
     float* dl = st_delay + size_t(c) * A;
     const float* xc = x + size_t(c) * kFrame;
-    float4 xv[2];
+    float4 xv[kVec];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < kVec; ++h) {
       const int i = 4 * (tid + kLimThreads * h);
       if (i >= A) {
         xv[h] = __ldg(reinterpret_cast<const float4*>(xc + i - A));
@@ -186,7 +209,7 @@ __global__ void __launch_bounds__(kLimThreads)
       *reinterpret_cast<float4*>(dl + 4 * tid) = t;
     }
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < kVec; ++h) {
       const int i = 4 * (tid + kLimThreads * h);
       float r[4] = {xv[h].x, xv[h].y, xv[h].z, xv[h].w};
       const float gg[4] = {gv[h].x, gv[h].y, gv[h].z, gv[h].w};
@@ -382,7 +405,8 @@ __global__ void __launch_bounds__(kPackSamples)
 //   limiter_apply_pack_kernel  four CTAs per stream (256 samples each): delayed sample x gain, clip, PCM conversion,
 //                              byte tile, coalesced store -- the packer's structure with the limiter's step 5 in front
 // Same arithmetic as limiter_kernel + pcm_pack_kernel, node for node.
-__global__ void __launch_bounds__(kLimThreads)
+template <int NT>
+__global__ void __launch_bounds__(NT)
     limiter_gains_kernel(const float* __restrict__ in, float* __restrict__ state, const float* __restrict__ loud_gain,
                          float* __restrict__ gains, float* __restrict__ dl_old, const LimParams P) {
   pdl_prologue();
@@ -397,7 +421,8 @@ __global__ void __launch_bounds__(kLimThreads)
   float* st_delay = st + 4 + A;
   const float lg = loud_gain ? __ldg(loud_gain + sidx) : 1.0f;
   const bool has_lg = loud_gain != nullptr;
-  limiter_gains(x, st, P, lg, has_lg, m, m2, g);
+  constexpr int kLimThreads = NT;
+  limiter_gains<NT>(x, st, P, lg, has_lg, m, m2, g);
   float4* go = reinterpret_cast<float4*>(gains + sidx * kFrame);
   for (int i = tid; i < kFrame / 4; i += kLimThreads) go[i] = reinterpret_cast<const float4*>(g)[i];
   // delay line: the old one goes to the apply kernel, the last A samples of this frame (with the loudness gain)
@@ -590,8 +615,13 @@ mpeghb200_status mpeghb200_limiter_dev(mpeghb200_ctx* ctx, const mpeghb200_limit
   P.thr = p->threshold;
   P.ac = p->attack_const;
   P.rc = p->release_const;
-  MB_CUDA(ctx, launch_pdl(limiter_kernel, dim3(n_streams), dim3(kLimThreads), 0, static_cast<cudaStream_t>(cuda_stream),
-                          d_in, d_out, d_state, d_loudness_gain, P));
+  P.fast_release = (ctx->lim_variant & 2) != 0;
+  if (ctx->lim_variant & 1)
+    MB_CUDA(ctx, launch_pdl(limiter_kernel<256>, dim3(n_streams), dim3(256), 0, static_cast<cudaStream_t>(cuda_stream),
+                            d_in, d_out, d_state, d_loudness_gain, P));
+  else
+    MB_CUDA(ctx, launch_pdl(limiter_kernel<128>, dim3(n_streams), dim3(128), 0, static_cast<cudaStream_t>(cuda_stream),
+                            d_in, d_out, d_state, d_loudness_gain, P));
   ctx->launches.fetch_add(1);
   MB_CUDA(ctx, cudaGetLastError());
   return MPEGHB200_OK;
@@ -620,6 +650,7 @@ mpeghb200_status mpeghb200_limiter_pack_dev(mpeghb200_ctx* ctx, const mpeghb200_
   P.thr = p->threshold;
   P.ac = p->attack_const;
   P.rc = p->release_const;
+  P.fast_release = (ctx->lim_variant & 2) != 0;
   PackParams K;
   K.n_ch = p->n_ch;
   K.bits = pcm_bits;
@@ -635,8 +666,12 @@ mpeghb200_status mpeghb200_limiter_pack_dev(mpeghb200_ctx* ctx, const mpeghb200_
   }
   float* d_gains = d_scratch;
   float* d_dl_old = d_scratch + size_t(n_streams) * kFrame;
-  MB_CUDA(ctx, launch_pdl(limiter_gains_kernel, dim3(n_streams), dim3(kLimThreads), 0, st, d_in, d_state, d_loudness_gain,
-                          d_gains, d_dl_old, P));
+  if (ctx->lim_variant & 1)
+    MB_CUDA(ctx, launch_pdl(limiter_gains_kernel<256>, dim3(n_streams), dim3(256), 0, st, d_in, d_state, d_loudness_gain,
+                            d_gains, d_dl_old, P));
+  else
+    MB_CUDA(ctx, launch_pdl(limiter_gains_kernel<128>, dim3(n_streams), dim3(128), 0, st, d_in, d_state, d_loudness_gain,
+                            d_gains, d_dl_old, P));
   ctx->launches.fetch_add(1);
   const size_t smem = size_t(kPackSamples) * p->n_ch * (pcm_bits >> 3);
   if (smem > 48 * 1024)
