@@ -41,7 +41,8 @@ struct mpeghb200_ctx {
   std::string last_error;
   std::atomic<uint64_t> launches{0};
   bool pack_generic = false;  // MPEGHB200_PACK_GENERIC=1: the byte-wise PCM packer for every channel count (comparison)
-  int lim_variant = 3;  // MPEGHB200_LIM_VARIANT: bit 0 = 256 threads per stream (else 128), bit 1 = smoother release fast path
+  int lim_variant = 7;  // MPEGHB200_LIM_VARIANT: bit 0 = 256 threads per stream (else 128), bit 1 = smoother release fast path,
+                        // bit 2 = channel loads batched in the output phase for launches of at most 4 streams per SM
   int fd_variant = 7;  // launch shape, see fd_synth_launch (7 = warp-specialised persistent CTAs, 3 per SM)
   mpeghb200::DeviceTables tables;
   std::vector<void*> owned;  // device allocations released by destroy()

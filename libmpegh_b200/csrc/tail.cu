@@ -229,6 +229,77 @@ __global__ void __launch_bounds__(NT)
   }
 }
 
+// The same limiter for launches of few streams (at most four CTAs per SM): with so few warps on an SM the output
+// phase above is bound by the latency of its channel loads, which the compiler keeps one behind the other (32
+// registers).  Here the loads of CB channels are issued before the first one is used, and the delay line is renewed
+// after the output loop (behind a barrier: other threads still read the old one) so that no store sits between them.
+template <int CB>
+__global__ void __launch_bounds__(256, 4)
+    limiter_deep_kernel(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ state,
+                        const float* __restrict__ loud_gain, const LimParams P) {
+  constexpr int NT = 256;
+  pdl_prologue();
+  __shared__ __align__(16) float m[kMaxAttack + kFrame + 16];
+  __shared__ __align__(16) float m2[kMaxAttack + kFrame + 16];
+  __shared__ __align__(16) float g[kFrame];
+  const int tid = threadIdx.x;
+  const int A = P.attack;
+  const size_t sidx = blockIdx.x;
+  const float* x = in + sidx * size_t(P.n_ch) * kFrame;
+  float* y = out + sidx * size_t(P.n_ch) * kFrame;
+  float* st = state + sidx * size_t(P.stride);
+  float* st_delay = st + 4 + A;
+  const float lg = loud_gain ? __ldg(loud_gain + sidx) : 1.0f;
+  const bool has_lg = loud_gain != nullptr;
+  limiter_gains<NT>(x, st, P, lg, has_lg, m, m2, g);
+  const float thr = P.thr;
+  const int i = 4 * tid;
+  const float4 gq = *reinterpret_cast<const float4*>(g + i);
+  const float gg[4] = {gq.x, gq.y, gq.z, gq.w};
+  for (int c0 = 0; c0 < P.n_ch; c0 += CB) {
+    float4 xv[CB];
+#pragma unroll
+    for (int q = 0; q < CB; ++q) {
+      const int c = c0 + q;
+      if (c < P.n_ch) {
+        if (i >= A)
+          xv[q] = __ldg(reinterpret_cast<const float4*>(x + size_t(c) * kFrame + i - A));
+        else
+          xv[q] = *reinterpret_cast<const float4*>(st_delay + size_t(c) * A + i);  // already carries the loudness gain
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < CB; ++q) {
+      const int c = c0 + q;
+      if (c < P.n_ch) {
+        float4 v = xv[q];
+        if (has_lg && i >= A) v = make_float4(fmul(v.x, lg), fmul(v.y, lg), fmul(v.z, lg), fmul(v.w, lg));
+        float r[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (gg[e] >= 0.0f) {
+            float t = fmul(r[e], gg[e]);
+            if (thr < t)
+              t = thr;
+            else if (t < -thr)
+              t = -thr;
+            r[e] = t;
+          }
+        }
+        __stcs(reinterpret_cast<float4*>(y + size_t(c) * kFrame + i), make_float4(r[0], r[1], r[2], r[3]));
+      }
+    }
+  }
+  __syncthreads();  // every read of the old delay line is done
+  const int a4 = A / 4;
+  for (int k = tid; k < P.n_ch * a4; k += NT) {
+    const int c = k / a4, j = 4 * (k - c * a4);
+    float4 t = __ldg(reinterpret_cast<const float4*>(x + size_t(c) * kFrame + kFrame - A + j));
+    if (has_lg) t = make_float4(fmul(t.x, lg), fmul(t.y, lg), fmul(t.z, lg), fmul(t.w, lg));
+    *reinterpret_cast<float4*>(st_delay + size_t(c) * A + j) = t;
+  }
+}
+
 __global__ void limiter_state_init_kernel(float* state, int stride, int n_streams) {
   const size_t n = size_t(stride) * n_streams;
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
@@ -616,7 +687,10 @@ mpeghb200_status mpeghb200_limiter_dev(mpeghb200_ctx* ctx, const mpeghb200_limit
   P.ac = p->attack_const;
   P.rc = p->release_const;
   P.fast_release = (ctx->lim_variant & 2) != 0;
-  if (ctx->lim_variant & 1)
+  if ((ctx->lim_variant & 4) && n_streams <= 4 * ctx->sm_count)
+    MB_CUDA(ctx, launch_pdl(limiter_deep_kernel<8>, dim3(n_streams), dim3(256), 0, static_cast<cudaStream_t>(cuda_stream),
+                            d_in, d_out, d_state, d_loudness_gain, P));
+  else if (ctx->lim_variant & 1)
     MB_CUDA(ctx, launch_pdl(limiter_kernel<256>, dim3(n_streams), dim3(256), 0, static_cast<cudaStream_t>(cuda_stream),
                             d_in, d_out, d_state, d_loudness_gain, P));
   else

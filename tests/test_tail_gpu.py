@@ -56,6 +56,31 @@ def test_limiter_streams_vs_oracle(gpu_lib, oracle, n_ch, limiter_on):
             assert bits_equal(got[s], loader.oracle_limiter_run(sts[s], x[f, s])), (f, s)
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 7])
+def test_limiter_launch_variants(oracle, variant, monkeypatch):
+    """Every launch form of the limiter (MPEGHB200_LIM_VARIANT: 128 / 256 threads per stream, the release fast path of the
+    smoother, batched channel loads for small launches -- the default, 7, takes the last one at these sizes and the plain
+    256-thread kernel beyond four streams per SM) against the oracle, with a loudness gain, over engaged, releasing and
+    quiet frames."""
+    from libmpegh_b200.lib import Lib
+    monkeypatch.setenv("MPEGHB200_LIM_VARIANT", str(variant))
+    lib = Lib().create(0)
+    try:
+        rng = np.random.default_rng(100 + variant)
+        S, C, F = 7, 12, 10
+        x = np.stack([tail_cases.limiter_signal(rng, F, C) for _ in range(S)], axis=1)
+        x[:, 2] *= np.float32(0.01)
+        gains = np.array([oracle.oracle_loudness_gain(db) for db in (-6.0, 0.5, 3.0, 12.0, 0.0, -1.0, 2.0)], np.float32)
+        sts = [loader.oracle_limiter_new(C) for _ in range(S)]
+        lim = DevLimiter(lib, S, C)
+        for f in range(F):
+            got = lim.run(x[f], gains)
+            for s in range(S):
+                assert bits_equal(got[s], loader.oracle_limiter_run(sts[s], x[f, s] * gains[s])), (variant, f, s)
+    finally:
+        lib.close()
+
+
 def test_limiter_with_loudness_gain(gpu_lib, oracle):
     rng = np.random.default_rng(11)
     S, C, F = 4, 6, 5
