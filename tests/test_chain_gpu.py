@@ -77,6 +77,56 @@ def test_chain_objects_config5(gpu_lib, oracle):
     gpu_lib.obj_layout_destroy(lay)
 
 
+def test_chain_full_size_properties(gpu_lib, oracle):
+    """BASELINE.json's stream counts (configs[2]: 1024 HOA streams, configs[4]: 512 object streams per GPU) through a
+    size-independent property: the batch is D distinct streams repeated S / D times in scrambled order, every copy must
+    produce the bytes of its original, and the D originals are checked against the oracle chain.  Three frames, state
+    carried on the device; covers the launch forms that depend on the stream count (limiter beyond four streams per SM)."""
+    D = 4
+    rng = np.random.default_rng(97)
+    # ---- configs[2] ----
+    cfg, tables, M, nfc, hsp, hren = hoa_setup(gpu_lib)
+    S, T = 1024, cfg[1]
+    perm = rng.permutation(S)
+    src = perm % D  # stream s is a copy of distinct stream src[s]
+    ch = gpu_lib.chain_open(S, n_hoa_transport=T, hoa_spatial=hsp, hoa_renderer=hren, pcm_bits=24, limiter=1, start_delay=240)
+    orc = chain_cases.OracleChain(D, hoa=(cfg, tables, M, nfc), pcm_bits=24, start_delay=240)
+    gens = [hoasp_cases.SideGen(cfg, np.random.default_rng(70 + d)) for d in range(D)]
+    for f in range(3):
+        sides = np.array([gen.next() for gen in gens], hoasp_cases.SIDE_DTYPE)
+        x = rng.normal(0, 4000.0, size=(D, T, 1024)).astype(np.float32)
+        pcm, nb = ch.execute(1, core=x[src], hoa_side=sides[src])
+        want = orc.frame(hoa=x, hoa_sides=sides)
+        for d in range(D):
+            first = int(np.flatnonzero(src == d)[0])
+            check_records(pcm[0][first:first + 1], nb[0][first:first + 1], want[d:d + 1], ("hoa full", f, d))
+            same = src == d
+            assert np.all(nb[0][same] == nb[0][first]) and np.all(pcm[0][same] == pcm[0][first]), ("hoa copies", f, d)
+    ch.close()
+    gpu_lib.hoa_renderer_destroy(hren)
+    gpu_lib.hoa_spatial_destroy(hsp)
+    # ---- configs[4] ----
+    S, O = 512, 32
+    perm = rng.permutation(S)
+    src = perm % D
+    lay = gpu_lib.obj_layout_create(loader.obj_layout_golden(19))
+    ch = gpu_lib.chain_open(S, n_obj=O, obj_layout=lay, pcm_bits=24, limiter=1, start_delay=240)
+    orc = chain_cases.OracleChain(D, n_obj=O, obj_cicp=19, pcm_bits=24, start_delay=240)
+    params = np.stack([obj_cases.random_params(rng, 3, O) for _ in range(D)], axis=1)  # [F, D, O, 7]
+    x = np.stack([obj_cases.object_audio(rng, 3, O) for _ in range(D)], axis=1)
+    for f in range(3):
+        side = gpu_lib.obj_side_from_polar(params[f][src])
+        pcm, nb = ch.execute(1, core=x[f][src], obj_side=side)
+        want = orc.frame(obj=x[f], obj_params=params[f])
+        for d in range(D):
+            first = int(np.flatnonzero(src == d)[0])
+            check_records(pcm[0][first:first + 1], nb[0][first:first + 1], want[d:d + 1], ("obj full", f, d))
+            same = src == d
+            assert np.all(nb[0][same] == nb[0][first]) and np.all(pcm[0][same] == pcm[0][first]), ("obj copies", f, d)
+    ch.close()
+    gpu_lib.obj_layout_destroy(lay)
+
+
 def test_chain_bed_objects_format_conv_16bit(gpu_lib, oracle):
     """22.2 bed + 8 objects rendered into 22.2, summed, format-converted to 7.1.4, limited, 16-bit PCM with a
     channel map; spectra in front (FD synthesis of bed and object signals on the device)."""
