@@ -489,8 +489,29 @@ __global__ void __launch_bounds__(kChunk, (NC <= 25) ? 3 : 2)
   // in a shared-memory column this thread owns (a round trip through the output element itself cost an L2 latency
   // per coefficient) and picked up again by the small unrolled loop below, which needs the register arrays v[], d[].
   extern __shared__ float ap_s[];  // [NC][kChunk]: the parked sums, one column per thread
+  // Frames without spatial prediction (the usual case; the flag is the same for the whole CTA) do not need that loop:
+  // for a coefficient above the ambient order the sum is one reassigned transport sample, which the unrolled loop below
+  // fetches itself, and the few ambient-order coefficients are a small matrix product whose inputs are parked once in
+  // the (then unused) top rows of ap_s.  ncu of the rolled loop with the bench's side info: 38 instructions per
+  // coefficient and sample for one load and one addition, 49 % of the kernel's instructions.  Same operations in the
+  // same order, so bit-identical; frames with prediction (or an ambient order that covers more than half of the
+  // coefficients) take the general loop.
+  const int low = C.low_order;
+  const bool direct = !any_pred && 2 * low <= NC;
+  if (direct) {
+    for (int m = 0; m < low; ++m) {
+      const int src = pl.reassign[m];
+      ap_s[(NC - 1 - m) * kChunk + tid] = src < 0 ? 0.0f : xs[src][tid];
+    }
+    for (int c = 0; c < low; ++c) {
+      float amb = 0.0f;
+      for (int m = 0; m < low; ++m)
+        amb = fadd(amb, fmul(__ldg(C.order_matrix + c * low + m), ap_s[(NC - 1 - m) * kChunk + tid]));
+      ap_s[c * kChunk + tid] = fadd(amb, 0.0f);
+    }
+  }
 #pragma unroll 1
-  for (int c = 0; c < NC; ++c) {
+  for (int c = direct ? NC : 0; c < NC; ++c) {
     const int in_en = pl.in_en[c], in_dis = pl.in_dis[c];
     float amb;
     if (c >= C.low_order) {
@@ -540,7 +561,14 @@ __global__ void __launch_bounds__(kChunk, (NC <= 25) ? 3 : 2)
       for (int i = 0; i < in_en; ++i) vv = fmul(vv, w[3]);
       for (int i = 0; i < in_dis; ++i) vv = fmul(vv, w[2]);
     }
-    __stcs(y + size_t(c) * kFrame + t, fadd(vv, fadd(ap_s[c * kChunk + tid], d[c])));
+    float ap;
+    if (direct && c >= low) {
+      const int src = pl.reassign[c];
+      ap = fadd(src < 0 ? 0.0f : xs[src][tid], 0.0f);
+    } else {
+      ap = ap_s[c * kChunk + tid];
+    }
+    __stcs(y + size_t(c) * kFrame + t, fadd(vv, fadd(ap, d[c])));
   }
 }
 
