@@ -324,22 +324,26 @@ __device__ __forceinline__ int sat_cast(float v) {
 
 __global__ void __launch_bounds__(kPackSamples)
     pcm_pack_kernel(const float* __restrict__ in, unsigned char* __restrict__ out, int* __restrict__ delay,
-                    int* __restrict__ out_bytes, const PackParams P) {
+                    int* __restrict__ out_bytes, const __grid_constant__ PackParams P) {
   pdl_prologue();
   extern __shared__ __align__(16) unsigned char tile[];  // [kPackSamples][n_ch][bytes]
   const int tid = threadIdx.x;
   const int chunk = blockIdx.x, sidx = blockIdx.y;
   const int bps = P.bits >> 3;
   const int frame_bytes = P.n_samples * P.n_ch * bps;
-  const float* x = in + size_t(sidx) * P.n_ch * P.ch_stride;
   const int d = delay ? delay[sidx] : 0;
   const int s = chunk * kPackSamples + tid;
+  // row offsets of the interleave slots, once per CTA (indexing P.pos[] per load made the compiler copy the
+  // table to local memory and redo 64-bit address arithmetic for every value: ncu, 12 instructions per load)
+  __shared__ unsigned row_off[64];
+  if (tid < P.n_ch) row_off[tid] = unsigned(P.pos[tid]) * unsigned(P.ch_stride);
+  __syncthreads();
+  const float* xs = in + size_t(sidx) * P.n_ch * P.ch_stride + s;
   constexpr int kBatch = 8;
   for (int ch0 = 0; ch0 < P.n_ch; ch0 += kBatch) {
     float vin[kBatch];  // eight channel loads in flight before the first conversion
 #pragma unroll
-    for (int q = 0; q < kBatch; ++q)
-      vin[q] = (ch0 + q < P.n_ch) ? __ldcs(x + size_t(P.pos[ch0 + q]) * P.ch_stride + s) : 0.0f;
+    for (int q = 0; q < kBatch; ++q) vin[q] = (ch0 + q < P.n_ch) ? __ldcs(xs + row_off[ch0 + q]) : 0.0f;
 #pragma unroll
     for (int q = 0; q < kBatch; ++q) {
       const int ch = ch0 + q;
@@ -414,7 +418,7 @@ __device__ __forceinline__ unsigned pcm_convert_t(float v) {
 template <int BITS>
 __global__ void __launch_bounds__(kPackSamples)
     pcm_pack4_kernel(const float* __restrict__ in, unsigned char* __restrict__ out, int* __restrict__ delay,
-                     int* __restrict__ out_bytes, const PackParams P) {
+                     int* __restrict__ out_bytes, const __grid_constant__ PackParams P) {
   pdl_prologue();
   extern __shared__ __align__(16) unsigned char tile[];  // [kPackSamples][n_ch][bytes]
   constexpr int BPS = BITS / 8;
@@ -422,15 +426,18 @@ __global__ void __launch_bounds__(kPackSamples)
   const int chunk = blockIdx.x, sidx = blockIdx.y;
   const int rec = P.n_ch * BPS;
   const int frame_bytes = P.n_samples * rec;
-  const float* x = in + size_t(sidx) * P.n_ch * P.ch_stride;
   const int d = delay ? delay[sidx] : 0;
   const int s = chunk * kPackSamples + tid;
+  __shared__ unsigned row_off[64];  // as in pcm_pack_kernel
+  if (tid < P.n_ch) row_off[tid] = unsigned(P.pos[tid]) * unsigned(P.ch_stride);
+  __syncthreads();
+  const float* xs = in + size_t(sidx) * P.n_ch * P.ch_stride + s;
   unsigned* tw = reinterpret_cast<unsigned*>(tile + size_t(tid) * rec);
   constexpr int kB = 24;  // channel loads in flight before the first conversion (n_ch % 4 == 0: whole groups of four)
   for (int ch0 = 0; ch0 < P.n_ch; ch0 += kB) {
     float vin[kB];
 #pragma unroll
-    for (int q = 0; q < kB; ++q) vin[q] = (ch0 + q < P.n_ch) ? __ldcs(x + size_t(P.pos[ch0 + q]) * P.ch_stride + s) : 0.0f;
+    for (int q = 0; q < kB; ++q) vin[q] = (ch0 + q < P.n_ch) ? __ldcs(xs + row_off[ch0 + q]) : 0.0f;
 #pragma unroll
     for (int g = 0; g < kB / 4; ++g) {
       if (ch0 + 4 * g >= P.n_ch) break;
