@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(kPackSamples)
     limiter_apply_pack_kernel(const float* __restrict__ in, const float* __restrict__ gains, const float* __restrict__ dl_old,
                               const float* __restrict__ loud_gain, unsigned char* __restrict__ out,
                               int* __restrict__ delay, int* __restrict__ out_bytes, int attack, float thr,
-                              const PackParams P) {
+                              const __grid_constant__ PackParams P) {
   pdl_prologue();
   extern __shared__ __align__(16) unsigned char tile[];  // [kPackSamples][n_ch][bytes]
   const int tid = threadIdx.x;
@@ -557,6 +557,9 @@ __global__ void __launch_bounds__(kPackSamples)
   const float lg = loud_gain ? __ldg(loud_gain + sidx) : 1.0f;
   const bool has_lg = loud_gain != nullptr;
   const int rec = P.n_ch * bps;
+  __shared__ unsigned char slot_ch[64];  // planar channel of every interleave slot (P.pos[] indexed per load went through local memory)
+  if (tid < P.n_ch) slot_ch[tid] = P.pos[tid];
+  __syncthreads();
   const bool words = (rec & 3) == 0;  // the sample's record is assembled in registers, one 32-bit store per 4 bytes
   unsigned long long sh = 0;
   int have = 0, wpos = 0;
@@ -567,7 +570,7 @@ __global__ void __launch_bounds__(kPackSamples)
 #pragma unroll
     for (int q = 0; q < kBatch; ++q) {
       if (ch0 + q < P.n_ch) {
-        const int c = P.pos[ch0 + q];
+        const int c = slot_ch[ch0 + q];
         if (s >= attack) {
           const float t = __ldcs(x + size_t(c) * kFrame + s - attack);
           vin[q] = has_lg ? fmul(t, lg) : t;
