@@ -1057,6 +1057,7 @@ __global__ void __launch_bounds__(128, MPEGHB200_FD_CTAS_PER_SM)
   __shared__ int fast_flag[kSlots];
   __shared__ int slow_list[kSlowCap];  // unit * n_frames + first generic-path frame
   __shared__ int slow_count;
+  __shared__ __align__(16) float coefbuf[2][1024];  // role A's coefficient prefetch (cp.async), two rows
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   grid_launch_dependents();
   if (threadIdx.x == 96) slow_count = 0;
@@ -1071,14 +1072,25 @@ __global__ void __launch_bounds__(128, MPEGHB200_FD_CTAS_PER_SM)
     TabA ta;
     load_tab_a(ta, T, lane);
     grid_dependency_wait();
-    float2 eo[2][16];
-    uint32_t sw[2];
+    // ONE copy of phase A in the loop (role A heads the pipeline, and 15 % of the kernel's stall samples were
+    // instruction-cache misses of the three roles' unrolled code; two copies existed only to give the two register
+    // sets of the coefficient prefetch compile-time indices).  The next item's 4 KB of coefficients now arrive by
+    // cp.async in one of two shared-memory rows of this warp and are read into ONE register set right before phase A.
+    float2 eo[16];
+    uint32_t sw_cur = 0, sw_nxt = 0;
     int un = first, fn = 0;  // (unit, frame) of the item whose loads are issued next
     bool left = false;       // the current unit has left the pipeline
     auto issue = [&](int buf) {
       const size_t q = size_t(fn) * n_units + un;
-      sw[buf] = __ldg(side + q);
-      load_coef(eo[buf], coef + q * 1024, lane);
+      sw_nxt = __ldg(side + q);
+      const float* src = coef + q * 1024;
+      float* dst = &coefbuf[buf][0];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(dst + 4 * (lane + 32 * k)));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + 4 * (lane + 32 * k)) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
       if (fn == 0 && lane == 0)
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(overlap + size_t(un) * 1024), "r"(4096)
                      : "memory");
@@ -1086,22 +1098,26 @@ __global__ void __launch_bounds__(128, MPEGHB200_FD_CTAS_PER_SM)
     };
     if (n_items > 0) issue(0);
     int f = 0;
-    auto body = [&](auto cur_c, int i) {
-      constexpr int cur = decltype(cur_c)::value;
-      const int slot = i % kSlots;
-      if (i + 1 < n_items) issue(cur ^ 1);
+#pragma unroll 1
+    for (int i = 0; i < n_items; ++i) {
+      const int slot = i % kSlots, buf = i & 1;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();  // every lane's copies of item i have landed and are visible to the whole warp
+      sw_cur = sw_nxt;
+      if (i + 1 < n_items) issue(buf ^ 1);  // that row was read into registers in the previous iteration
       if (i >= kSlots) bar_sync64(FREE + slot);
       if (f == 0) left = false;
-      const bool fast = !left && is_fast(unpack_side(sw[cur]));
+      const bool fast = !left && is_fast(unpack_side(sw_cur));
       left = DEFER && !fast;  // without deferral a generic-path frame is done in line and the unit stays in the pipeline
       if (lane == 0) fast_flag[slot] = fast;
-      if (fast) phase_a(eo[cur], ta, slots[slot], T, lane);
+      if (fast) {
+        const float2* c2 = reinterpret_cast<const float2*>(&coefbuf[buf][0]);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) eo[u] = c2[lane + 32 * u];
+        phase_a(eo, ta, slots[slot], T, lane);
+      }
       bar_arrive64(AB + slot);
       if (++f == n_frames) f = 0;
-    };
-    for (int i = 0; i < n_items; i += 2) {
-      body(std::integral_constant<int, 0>{}, i);
-      if (i + 1 < n_items) body(std::integral_constant<int, 1>{}, i + 1);
     }
   } else if (warp <= 2) {
     // ---------------- role B ----------------
