@@ -1057,7 +1057,7 @@ __global__ void __launch_bounds__(128, MPEGHB200_FD_CTAS_PER_SM)
   __shared__ int fast_flag[kSlots];
   __shared__ int slow_list[kSlowCap];  // unit * n_frames + first generic-path frame
   __shared__ int slow_count;
-  __shared__ __align__(16) float coefbuf[2][1024];  // role A's coefficient prefetch (cp.async), two rows
+  __shared__ __align__(16) float coefbuf[3][1024];  // role A's coefficient prefetch (cp.async), three rows
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   grid_launch_dependents();
   if (threadIdx.x == 96) slow_count = 0;
@@ -1096,15 +1096,22 @@ __global__ void __launch_bounds__(128, MPEGHB200_FD_CTAS_PER_SM)
                      : "memory");
       if (++fn == n_frames) fn = 0, un += stride;
     };
+    // three rows: the copies of the next TWO items are outstanding while phase A works on the current one (with one
+    // item ahead a quarter of role A's stall samples were waits for the row)
     if (n_items > 0) issue(0);
-    int f = 0;
+    sw_cur = sw_nxt;
+    if (n_items > 1) issue(1);
+    int f = 0, buf = 0;
 #pragma unroll 1
     for (int i = 0; i < n_items; ++i) {
-      const int slot = i % kSlots, buf = i & 1;
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      const int slot = i % kSlots;
+      if (i + 1 < n_items)
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncwarp();  // every lane's copies of item i have landed and are visible to the whole warp
-      sw_cur = sw_nxt;
-      if (i + 1 < n_items) issue(buf ^ 1);  // that row was read into registers in the previous iteration
+      const uint32_t sw_i1 = sw_nxt;                                  // side word of item i + 1
+      if (i + 2 < n_items) issue(buf == 0 ? 2 : buf - 1);             // row (i + 2) % 3: read into registers in iteration i - 1
       if (i >= kSlots) bar_sync64(FREE + slot);
       if (f == 0) left = false;
       const bool fast = !left && is_fast(unpack_side(sw_cur));
@@ -1118,6 +1125,8 @@ __global__ void __launch_bounds__(128, MPEGHB200_FD_CTAS_PER_SM)
       }
       bar_arrive64(AB + slot);
       if (++f == n_frames) f = 0;
+      sw_cur = sw_i1;
+      buf = buf == 2 ? 0 : buf + 1;
     }
   } else if (warp <= 2) {
     // ---------------- role B ----------------
