@@ -1057,7 +1057,8 @@ __global__ void __launch_bounds__(128, MPEGHB200_FD_CTAS_PER_SM)
   __shared__ int fast_flag[kSlots];
   __shared__ int slow_list[kSlowCap];  // unit * n_frames + first generic-path frame
   __shared__ int slow_count;
-  __shared__ __align__(16) float coefbuf[3][1024];  // role A's coefficient prefetch (cp.async), three rows
+  __shared__ __align__(128) float coefbuf[3][1024];  // role A's coefficient prefetch (bulk copies), three rows
+  __shared__ __align__(8) unsigned long long rowbar[3];  // their mbarriers
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   grid_launch_dependents();
   if (threadIdx.x == 96) slow_count = 0;
@@ -1075,7 +1076,8 @@ __global__ void __launch_bounds__(128, MPEGHB200_FD_CTAS_PER_SM)
     // ONE copy of phase A in the loop (role A heads the pipeline, and 15 % of the kernel's stall samples were
     // instruction-cache misses of the three roles' unrolled code; two copies existed only to give the two register
     // sets of the coefficient prefetch compile-time indices).  The next item's 4 KB of coefficients now arrive by
-    // cp.async in one of two shared-memory rows of this warp and are read into ONE register set right before phase A.
+    // bulk copy (TMA) in one of three shared-memory rows of this warp and are read into ONE register set right before
+    // phase A.
     float2 eo[16];
     uint32_t sw_cur = 0, sw_nxt = 0;
     int un = first, fn = 0;  // (unit, frame) of the item whose loads are issued next
@@ -1084,13 +1086,15 @@ __global__ void __launch_bounds__(128, MPEGHB200_FD_CTAS_PER_SM)
       const size_t q = size_t(fn) * n_units + un;
       sw_nxt = __ldg(side + q);
       const float* src = coef + q * 1024;
-      float* dst = &coefbuf[buf][0];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(dst + 4 * (lane + 32 * k)));
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + 4 * (lane + 32 * k)) : "memory");
+      if (lane == 0) {
+        // one bulk copy (TMA) of the unit's 4 KB row, completion counted in bytes on the row's mbarrier
+        const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(&coefbuf[buf][0]));
+        const unsigned b = static_cast<unsigned>(__cvta_generic_to_shared(&rowbar[buf]));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(4096) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+                     "l"(src), "r"(4096), "r"(b)
+                     : "memory");
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
       if (fn == 0 && lane == 0)
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(overlap + size_t(un) * 1024), "r"(4096)
                      : "memory");
@@ -1098,18 +1102,37 @@ __global__ void __launch_bounds__(128, MPEGHB200_FD_CTAS_PER_SM)
     };
     // three rows: the copies of the next TWO items are outstanding while phase A works on the current one (with one
     // item ahead a quarter of role A's stall samples were waits for the row)
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(&rowbar[r]))), "r"(1) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
     if (n_items > 0) issue(0);
     sw_cur = sw_nxt;
     if (n_items > 1) issue(1);
     int f = 0, buf = 0;
+    unsigned par = 0;  // phase parity of the row barriers: flips every third item
 #pragma unroll 1
     for (int i = 0; i < n_items; ++i) {
       const int slot = i % kSlots;
-      if (i + 1 < n_items)
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-      else
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncwarp();  // every lane's copies of item i have landed and are visible to the whole warp
+      {  // item i's row has landed: its mbarrier completes phase (i / 3) & 1
+        const unsigned b = static_cast<unsigned>(__cvta_generic_to_shared(&rowbar[buf]));
+        const unsigned parity = par;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "ROW_WAIT_%=:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+            "@p bra ROW_DONE_%=;\n\t"
+            "bra ROW_WAIT_%=;\n\t"
+            "ROW_DONE_%=:\n\t"
+            "}\n" ::"r"(b),
+            "r"(parity)
+            : "memory");
+      }
+      __syncwarp();  // the previous iteration's reads of the row that is refilled next are done in every lane
       const uint32_t sw_i1 = sw_nxt;                                  // side word of item i + 1
       if (i + 2 < n_items) issue(buf == 0 ? 2 : buf - 1);             // row (i + 2) % 3: read into registers in iteration i - 1
       if (i >= kSlots) bar_sync64(FREE + slot);
@@ -1126,7 +1149,7 @@ __global__ void __launch_bounds__(128, MPEGHB200_FD_CTAS_PER_SM)
       bar_arrive64(AB + slot);
       if (++f == n_frames) f = 0;
       sw_cur = sw_i1;
-      buf = buf == 2 ? 0 : buf + 1;
+      if (buf == 2) buf = 0, par ^= 1u; else ++buf;
     }
   } else if (warp <= 2) {
     // ---------------- role B ----------------
