@@ -836,7 +836,9 @@ def main():
                                   f"; with {FPL} frames per launch a unit's overlap stays on the SM between frames, so "
                                   f"the launch's own minimum is {own_min / UNITS / FPL:.0f} B per channel-frame: "
                                   "frac_of_own_minimum is the fraction of the HBM peak on that smaller figure (the "
-                                  "kernel is then bound by issue / shared-memory throughput, not HBM)"),
+                                  "kernel is then bound by issue / shared-memory throughput, not HBM); frac, on the "
+                                  "per-call figure, exceeds 1 when the launch is faster than a kernel that moved all "
+                                  "16 KB per channel-frame could be"),
                          "frac_of_own_minimum": own_min / (ms_per_step * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": UNITS * FRAME * 4 + UNITS * 4,
                     "d2h_bytes_per_step": UNITS * FRAME * 4, "ms_per_step": e2e_s * 1e3,
