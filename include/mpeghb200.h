@@ -97,7 +97,8 @@ mpeghb200_status mpeghb200_fd_synth_dev(mpeghb200_ctx *ctx, const float *d_coef,
  * (read before frame 0, replaced after the last frame).  The result is what n_frames calls of mpeghb200_fd_synth_dev
  * give, bit for bit; between two ONLY_LONG-family frames a unit's overlap stays on the SM (ia_core_coder_fd_frm_dec
  * writes and re-reads it through memory, decoder/ia_core_coder_imdct.c:807-813), which removes up to half of the
- * launch's HBM traffic.  n_units * n_frames < 2^31. */
+ * launch's HBM traffic.  n_units * n_frames < 2^31; coef, overlap and out on 16-byte boundaries (the coefficient rows
+ * travel by TMA bulk copy), else MPEGHB200_ERR_BAD_ARG. */
 mpeghb200_status mpeghb200_fd_synth_frames_dev(mpeghb200_ctx *ctx, const float *d_coef, const uint32_t *d_side,
                                                float *d_overlap, float *d_out, int n_units, int n_frames,
                                                void *cuda_stream);

@@ -61,6 +61,9 @@ mpeghb200_status mpeghb200_fd_synth_frames_dev(mpeghb200_ctx* ctx, const float* 
     return fail(ctx, MPEGHB200_ERR_BAD_ARG, "fd_synth_frames_dev: null buffer or negative count");
   if (n_frames > 0 && n_units > 0x7fffffff / n_frames)
     return fail(ctx, MPEGHB200_ERR_BAD_ARG, "fd_synth_frames_dev: n_units * n_frames does not fit 31 bits");
+  // the coefficient rows travel by bulk copy, overlap and output as float4: every buffer on a 16-byte boundary
+  if ((reinterpret_cast<uintptr_t>(d_coef) | reinterpret_cast<uintptr_t>(d_overlap) | reinterpret_cast<uintptr_t>(d_out)) & 15)
+    return fail(ctx, MPEGHB200_ERR_BAD_ARG, "fd_synth_frames_dev: coef, overlap and out must be 16-byte aligned");
   MB_CUDA(ctx, cudaSetDevice(ctx->device));
   return fd_synth_frames_launch(ctx, d_coef, d_side, d_overlap, d_out, n_units, n_frames,
                                 static_cast<cudaStream_t>(cuda_stream));

@@ -250,3 +250,19 @@ def test_frames_launch_equals_single_frame_launches(gpu_lib):
         o1, ov1 = run_dev(gpu_lib, coef[f], packed[f], ov1)
         assert bits_equal(out[f], o1), f
     assert bits_equal(ov, ov1)
+
+
+def test_frames_launch_rejects_misaligned_buffers(gpu_lib):
+    """The multi-frame launch moves coefficient rows by TMA bulk copy and the rest as float4: a buffer that is not on a
+    16-byte boundary is refused with MPEGHB200_ERR_BAD_ARG instead of faulting on the device."""
+    import torch
+    U, F = 8, 2
+    coef = torch.zeros(F * U * 1024 + 4, device="cuda")
+    side = torch.zeros(F * U, dtype=torch.int32, device="cuda")
+    ov = torch.zeros(U * 1024, device="cuda")
+    out = torch.zeros(F * U * 1024, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    gpu_lib.fd_synth_frames_dev(coef.data_ptr(), side.data_ptr(), ov.data_ptr(), out.data_ptr(), U, F, st)  # aligned: fine
+    with pytest.raises(Exception):
+        gpu_lib.fd_synth_frames_dev(coef.data_ptr() + 4, side.data_ptr(), ov.data_ptr(), out.data_ptr(), U, F, st)
+    torch.cuda.synchronize()
